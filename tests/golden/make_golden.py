@@ -1,0 +1,68 @@
+"""Regenerates tests/golden/*.npz. Runs only where /root/reference and oracle/_ref/ref_dump exist
+(the build container); the GPU box uses the committed .npz files.
+
+Each fixture is the full stage dump of the UNMODIFIED reference (oracle/ref_dump.c linked against the
+reference objects) on one of the reference's own sample inputs / test cases
+(reference tests/test_fpocket.py:65-132, data/sample/).
+"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from dumpio import read_dump  # noqa: E402
+
+REF = os.environ.get("FPK_REFERENCE", "/root/reference")
+DUMP = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
+
+# name, input file (under data/sample), ref_dump flags, fpocket options
+CASES = [
+    ("1UYD", "1UYD.pdb", ["--seed", "11"], []),                                   # test_fpocket.py:65 default params
+    ("3LKF", "3LKF.pdb", ["--seed", "12"], []),
+    ("5WA6", "5WA6.pdb", ["--seed", "13"], []),
+    ("7TAA_m28_M74", "7TAA.pdb", ["--seed", "14"], ["-m", "2.8", "-M", "7.4"]),  # test_fpocket.py:73
+    ("1ATP_D36", "1ATP.pdb", ["--seed", "15"], ["-D", "3.6"]),                   # test_fpocket.py:95
+    ("1UYD_explicit", "1UYD.pdb", ["--seed", "16"], ["-r", "1224:PU8:A"]),       # test_fpocket.py:117
+    ("2P0R_mod_aD", "2P0R_mod.pdb", ["--seed", "17"], ["-a", "D"]),              # test_fpocket.py:125
+    ("5RGF_cif", "5RGF.cif", ["--seed", "18"], []),                              # test_mmcif.py:77
+    ("md_2yex", "mdpocket/2yex.pdb", ["--md"], []),                           # mdpocket.c:833 call shape
+    ("md_3ot3_S", "mdpocket/3ot3.pdb", ["--md", "--score"], []),              # -S drug-score increments
+]
+
+
+def main():
+    tmp = tempfile.mkdtemp(prefix="fpkgold")
+    for name, fn, dflags, opts in CASES:
+        src = os.path.join(REF, "data", "sample", fn)
+        if not os.path.exists(src):
+            print("skip", name, "(no", src, ")")
+            continue
+        loc = os.path.join(tmp, os.path.basename(fn))
+        shutil.copy(src, loc)
+        os.chmod(loc, 0o644)
+        out = os.path.join(tmp, name + ".dump")
+        subprocess.run([DUMP, out] + dflags + ["-f", loc] + opts, check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, cwd=tmp)
+        d = read_dump(out)
+        d["seed"] = np.array([int(dflags[dflags.index("--seed") + 1]) if "--seed" in dflags else 0])
+        for k in ("pdb.name", "pdb.type", "pdbw.name", "pdbw.type", "qh.centres", "sph1.f"):
+            d.pop(k, None)
+        # the reference reads only the flushed part of qhull's output (see oracle/ref_dump.c): keep the full
+        # tet list, how many lines were visible and the (possibly cut) last visible line
+        seen = d.pop("qh.tets_seen")
+        assert np.array_equal(seen[:-1], d["qh.tets"][:len(seen) - 1])
+        d["qh.n_seen"] = np.array([len(seen)])
+        d["qh.last_seen"] = seen[-1].copy()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+        print(name, "sites", len(d["qh.tets"]), "tets; spheres", len(d["sph0.f"]), "pockets", len(d["fin.off"]) - 1)
+    shutil.rmtree(tmp)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,49 @@
+"""Helpers shared by the CPU and GPU parity tests: load a golden fixture (tests/golden/*.npz, made by
+tests/golden/make_golden.py from the unmodified reference) and compare results field by field."""
+import glob
+import os
+
+import numpy as np
+
+import oracle_lib as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ALL = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "*.npz")))
+FPOCKET_CASES = [c for c in ALL if not c.startswith("md_")]
+MD_CASES = [c for c in ALL if c.startswith("md_")]
+
+DESC_F = ["score", "drug_score", "hydrophobicity_score", "volume_score", "volume", "convex_hull_volume",
+          "prop_polar_atm", "mean_asph_ray", "masph_sacc", "apolar_asphere_prop", "mean_loc_hyd_dens", "as_density",
+          "as_max_dst", "flex", "nas_norm", "polarity_score_norm", "mean_loc_hyd_dens_norm", "prop_asapol_norm",
+          "as_density_norm", "as_max_dst_norm", "surf_vdw14", "surf_vdw22", "surf_pol_vdw14", "surf_pol_vdw22",
+          "surf_apol_vdw14", "surf_apol_vdw22", "as_max_r"]
+DESC_I = ["nb_asph", "polarity_score", "charge_score", "n_abpa", "nAlphaApol", "nAlphaPol"]
+
+
+def load(name):
+    d = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    n = int(d["qh.n_seen"][0])
+    seen = d["qh.tets"][:n].copy()
+    seen[n - 1] = d["qh.last_seen"]
+    d["qh.tets_seen"] = seen            # exactly what the reference parsed (voronoi.c:395-445, unflushed tail lost)
+    return d
+
+
+def inputs(d, **kw):
+    return O.structure_from_dump(d), O.params_from_dump(d, mc_seed=int(d["seed"][0]), **kw)
+
+
+def eq_nan(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+
+
+def canon_sphere_keys(neigh):
+    """sorted 4-tuples of contacted atoms: the order-free identity of an alpha sphere"""
+    return [tuple(sorted(int(v) for v in row)) for row in neigh]
+
+
+def pocket_sets(r, clusters):
+    """set of frozensets of sphere keys for the given cluster indices"""
+    keys = canon_sphere_keys(r["sph_neigh"])
+    return [frozenset(keys[s] for s in r["cl_sph"][r["cl_off"][c]:r["cl_off"][c + 1]]) for c in clusters]

@@ -1,0 +1,72 @@
+"""CPU: pins the oracle (oracle/oracle.c) to the UNMODIFIED reference, through the stage dumps in
+tests/golden (made by tests/golden/make_golden.py with oracle/_ref/ref_dump).
+
+Given the tetrahedra exactly as the reference read them from qhull (order, vertex order, lost tail),
+every stage of the oracle must be BIT-IDENTICAL to the reference: kept spheres, types, clusters,
+every descriptor (including the Monte-Carlo volume when fed the same libc rand() stream and the
+convex-hull volume), per-atom ASA side effects, drop decisions and final ranking.
+The oracle's own exact Delaunay must equal qhull's tetrahedra as a set.
+"""
+import numpy as np
+import pytest
+
+import golden_cases as G
+import oracle_lib as O
+
+
+@pytest.mark.parametrize("case", G.FPOCKET_CASES)
+def test_oracle_bit_exact_on_reference_tets(case):
+    d = G.load(case)
+    st, p = G.inputs(d)
+    r = O.search_pocket(st, p, tets=d["qh.tets_seen"], rng_mode=O.RNG_LIBC)
+    assert r["n_spheres"] == len(d["sph0.f"])
+    assert np.array_equal(r["sph_xyzr"], d["sph0.f"][:, :4])
+    assert np.array_equal(r["sph_bary"], d["sph0.f"][:, 4:7])
+    assert np.array_equal(r["sph_neigh"], d["sph0.i"][:, :4])
+    assert np.array_equal(r["sph_type"], d["sph0.i"][:, 4])
+    assert np.array_equal(r["cl_off"], d["pre.off"])
+    assert np.array_equal(r["cl_sph"], d["pre.sph"])
+    D, F, I = r["desc"], d["pre.desc_f"], d["pre.desc_i"]
+    for k, n in enumerate(G.DESC_F):
+        assert G.eq_nan(D[n], F[:, k]), n
+    assert np.array_equal(D["bary"], F[:, 27:30])
+    for k, n in enumerate(G.DESC_I):
+        assert np.array_equal(D[n], I[:, k]), n
+    assert np.array_equal(D["aa_compo"], I[:, 11:31])
+    assert G.eq_nan(r["atom_fx"], d["atom_fx"])
+    # final pockets: same clusters, same rank order (psorting.c quicksort incl. tie behaviour)
+    ref_first = [int(d["fin.sph"][o]) for o in d["fin.off"][:-1]]
+    mine = [int(r["cl_sph"][r["cl_off"][c]]) for c in r["rank_to_cluster"]]
+    assert mine == ref_first
+    assert np.array_equal(D["score"][r["rank_to_cluster"]], d["fin.desc_f"][:, 0])
+
+
+@pytest.mark.parametrize("case", G.ALL)
+def test_oracle_delaunay_equals_qhull(case):
+    d = G.load(case)
+    st, _ = G.inputs(d)
+    _, ki, _ = O.sites(st)
+    rc, t, vol = O.delaunay(ki)
+    assert rc == 0
+    assert np.array_equal(t, O.canonicalize(d["qh.tets"]))
+    assert vol > 0
+
+
+@pytest.mark.parametrize("case", G.MD_CASES)
+def test_oracle_md_grids(case):
+    d = G.load(case)
+    st, p = G.inputs(d)
+    score = int(case.endswith("_S"))
+    org, dims, dens, freq, r = O.md_grids(st, p, use_drug_score=score, tets=d["qh.tets_seen"])
+    assert np.array_equal(org, d["grid.origin"][:3])
+    assert tuple(dims) == d["grid.dens"].shape
+    assert np.array_equal(dens, d["grid.dens"])
+    assert np.array_equal(freq, d["grid.freq"])
+
+
+def test_reference_tail_loss_is_real():
+    """The reference parses qhull's output file before it is flushed (voronoi.c:138-146), so it sees
+    only whole 4096-byte blocks: document that the fixtures carry this, so nobody 'fixes' the oracle."""
+    d = G.load("1UYD")
+    assert int(d["qh.out_len"][1]) == (int(d["qh.out_len"][0]) // 4096) * 4096
+    assert int(d["qh.n_seen"][0]) < len(d["qh.tets"])
