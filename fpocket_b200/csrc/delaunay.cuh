@@ -1,0 +1,502 @@
+// Parallel exact 3-D Delaunay triangulation of one point set by one thread block.
+//
+// Replaces the reference's call into the vendored qhull (reference src/voronoi.c:111-138 ->
+// src/qhull/src/qvoronoi/qvoronoi.c:236 run_qvoronoi -> libqhull.c:60 qh_qhull): instead of a
+// sequential lifted convex hull with tolerance-based facet merging, points are inserted by
+// Bowyer-Watson cavity retriangulation, MANY POINTS PER STEP: every thread owns one pending point,
+// finds its cavity on a read-only mesh while claiming the cavity and its rim with atomicMin on a
+// per-tet owner word (lowest insertion rank wins), and the winners of a step - whose claimed sets
+// are disjoint by construction - rewrite the mesh concurrently. Predicates are exact
+// (predicates.cuh) with Devillers-Teillaud symbolic perturbation, so the result is THE Delaunay
+// triangulation of the lattice points, independent of insertion order and thread timing.
+//
+// The phases are plain per-thread functions separated by block barriers; the same functions are
+// stepped sequentially by tests/hostemu (a test-only host build of this header, never shipped).
+#pragma once
+#include "predicates.cuh"
+
+namespace fpk {
+
+enum { T_DEAD = -2, V_INF = -1, OWN_FREE = 0x7fffffff, CAVMAX = 128 };
+enum { ST_IDLE = 0, ST_CLAIMED = 1, ST_LOST = 2, ST_BIG = 3, ST_DUP = 4, ST_WIN = 5, ST_ERR = 6 };
+enum { C_NTET = 0, C_NFREE0 = 1, C_NFREE1 = 2, C_RECENT = 3, C_STATUS = 4, C_SUBROUND = 5, C_NDUP = 6, C_NBIG = 7,
+       C_NSUB = 8, C_NRETRY = 9, C_NEXACT = 10, C_COUNT = 16 };
+enum { DERR_NONE = 0, DERR_DEGENERATE = 1, DERR_CAPACITY = 2, DERR_WALK = 3, DERR_ROTATE = 4 };
+
+struct DelaunayCtx {
+    int n;              // sites
+    const double *P;    // [3n] lattice coordinates (integers stored in doubles)
+    int *tv, *tn;       // [4*cap] tet vertices / neighbours (neighbour k is opposite vertex k)
+    int *own, *rim;     // [cap] claim words (priority of the claimant, OWN_FREE if none): cavity / rim
+    int *mark;          // [cap] rank of the winner whose cavity holds this tet
+    int *cavpos;        // [cap] position of the tet in that winner's cavity list
+    int cap;
+    int *cnt;           // [C_COUNT] counters (C_*)
+    int *freest[2];     // two free-slot stacks [cap] used alternately: pop from one, push to the other
+    const int *order;   // [n] insertion order (site ids)
+    int *hint;          // [hg^3] a recently created tet near each cell
+    int hg;
+    double hmin[3], hinv;
+    int nthreads;
+    int *cav;           // [nthreads*CAVMAX] cavity tets of the thread's point
+    int *newid;         // [nthreads*CAVMAX*4] new tet on face q of cavity tet i (-1: interior face)
+    int *tinfo;         // [nthreads*4] {rank of current point or -1, state, ncav, unused}
+    int *cursor;        // [nthreads*2] {next, end} of the thread's chunk of `order`
+    int *bigcav, *bignewid;   // [cap], [4*cap]: serial path for cavities > CAVMAX
+    int first4[4];      // sites of the initial simplex (skipped by phase_assign)
+};
+
+// ---- insertion order: biased randomised rounds (BRIO), Morton order inside a round --------------------------
+FPK_HD uint32_t hash32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+FPK_HD int brio_nrounds(int n)
+{
+    int lg = 0;
+    while ((1 << (lg + 1)) <= n) lg++;
+    int r = lg - 3;
+    return r < 1 ? 1 : (r > 24 ? 24 : r);
+}
+FPK_HD uint64_t spread10(uint32_t v)
+{
+    uint64_t x = v & 0x3ffu;
+    x = (x | (x << 16)) & 0x30000ffull;
+    x = (x | (x << 8)) & 0x300f00full;
+    x = (x | (x << 4)) & 0x30c30c3ull;
+    x = (x | (x << 2)) & 0x9249249ull;
+    return x;
+}
+// key = round(8 bits) | morton(30 bits) | site(24 bits); the last round holds half of the points
+FPK_HD uint64_t brio_key(int site_id, const double *p, const double mn[3], double inv1024, int nrounds)
+{
+    uint32_t h = hash32((uint32_t)site_id * 2654435761u + 12345u) | (1u << (nrounds - 1));
+    int k = 0;
+    while (!((h >> k) & 1u)) k++;
+    int round = nrounds - 1 - k;
+    int q[3];
+    for (int a = 0; a < 3; a++) {
+        int v = (int)((p[a] - mn[a]) * inv1024);
+        q[a] = v < 0 ? 0 : (v > 1023 ? 1023 : v);
+    }
+    uint64_t m = spread10((uint32_t)q[0]) | (spread10((uint32_t)q[1]) << 1) | (spread10((uint32_t)q[2]) << 2);
+    return ((uint64_t)round << 54) | (m << 24) | (uint64_t)(uint32_t)site_id;
+}
+
+FPK_HD void ld4(const int *base, int t, int v[4])
+{
+#if defined(__CUDA_ARCH__)
+    int4 q = *reinterpret_cast<const int4 *>(base + 4 * (size_t)t);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+#else
+    const int *p = base + 4 * (size_t)t;
+    v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[3] = p[3];
+#endif
+}
+FPK_HD void st4(int *base, int t, const int v[4])
+{
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<int4 *>(base + 4 * (size_t)t) = make_int4(v[0], v[1], v[2], v[3]);
+#else
+    int *p = base + 4 * (size_t)t;
+    p[0] = v[0]; p[1] = v[1]; p[2] = v[2]; p[3] = v[3];
+#endif
+}
+FPK_HD int atomic_min_i(int *p, int v)
+{
+#if defined(__CUDA_ARCH__)
+    return atomicMin(p, v);
+#else
+    int o = *p; if (v < o) *p = v; return o;
+#endif
+}
+FPK_HD int atomic_add_i(int *p, int v)
+{
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, v);
+#else
+    int o = *p; *p = o + v; return o;
+#endif
+}
+
+FPK_HD const double *site(const DelaunayCtx &c, int i) { return c.P + 3 * (size_t)i; }
+
+// insphere with symbolic perturbation (Devillers & Teillaud): points ordered by site index
+FPK_HD int insphere_sos(const DelaunayCtx &c, const int v[4], int p)
+{
+    int r = insphere(site(c, v[0]), site(c, v[1]), site(c, v[2]), site(c, v[3]), site(c, p));
+    if (r) return r;
+    int idx[5] = {v[0], v[1], v[2], v[3], p};
+    for (int i = 1; i < 5; i++) {
+        int k = idx[i], j = i - 1;
+        while (j >= 0 && idx[j] > k) { idx[j + 1] = idx[j]; j--; }
+        idx[j + 1] = k;
+    }
+    for (int i = 4; i > 0; i--) {
+        int q = idx[i], o;
+        if (q == p) return -1;
+        if (q == v[3] && (o = orient3d(site(c, v[0]), site(c, v[1]), site(c, v[2]), site(c, p))) != 0) return o;
+        if (q == v[2] && (o = orient3d(site(c, v[0]), site(c, v[1]), site(c, p), site(c, v[3]))) != 0) return o;
+        if (q == v[1] && (o = orient3d(site(c, v[0]), site(c, p), site(c, v[2]), site(c, v[3]))) != 0) return o;
+        if (q == v[0] && (o = orient3d(site(c, p), site(c, v[1]), site(c, v[2]), site(c, v[3]))) != 0) return o;
+    }
+    return -1;
+}
+
+// orientation of tet v with the vertex in `slot` replaced by point p
+FPK_HD int orient_sub(const DelaunayCtx &c, const int v[4], int slot, int p)
+{
+    const double *q0 = site(c, slot == 0 ? p : v[0]), *q1 = site(c, slot == 1 ? p : v[1]);
+    const double *q2 = site(c, slot == 2 ? p : v[2]), *q3 = site(c, slot == 3 ? p : v[3]);
+    return orient3d(q0, q1, q2, q3);
+}
+
+FPK_HD int inf_slot(const int v[4])
+{
+    return v[0] < 0 ? 0 : (v[1] < 0 ? 1 : (v[2] < 0 ? 2 : (v[3] < 0 ? 3 : -1)));
+}
+
+// is point p inside the (perturbed) circumsphere of tet t?  Ghost tets (one vertex at infinity) are in
+// conflict when p is beyond their hull facet, or on its plane and inside the facet's circumcircle.
+FPK_HD bool in_conflict(const DelaunayCtx &c, int t, const int v[4], int p)
+{
+    int k = inf_slot(v);
+    if (k < 0) return insphere_sos(c, v, p) > 0;
+    int o = orient_sub(c, v, k, p);
+    if (o) return o > 0;
+    int nb = c.tn[4 * (size_t)t + k], w[4];
+    ld4(c.tv, nb, w);
+    return insphere_sos(c, w, p) > 0;
+}
+
+FPK_HD int hint_cell(const DelaunayCtx &c, const double *p)
+{
+    int g = c.hg, ix = (int)((p[0] - c.hmin[0]) * c.hinv), iy = (int)((p[1] - c.hmin[1]) * c.hinv), iz = (int)((p[2] - c.hmin[2]) * c.hinv);
+    ix = ix < 0 ? 0 : (ix >= g ? g - 1 : ix); iy = iy < 0 ? 0 : (iy >= g ? g - 1 : iy); iz = iz < 0 ? 0 : (iz >= g ? g - 1 : iz);
+    return (ix * g + iy) * g + iz;
+}
+
+// ---- serial set-up by one thread: first simplex + its four ghosts -------------------------------------
+FPK_HD bool pts_equal(const double *a, const double *b) { return a[0] == b[0] && a[1] == b[1] && a[2] == b[2]; }
+FPK_HD bool pts_collinear(const double *a, const double *b, const double *c)
+{
+    i128 ux = (long long)(b[0] - a[0]), uy = (long long)(b[1] - a[1]), uz = (long long)(b[2] - a[2]);
+    i128 vx = (long long)(c[0] - a[0]), vy = (long long)(c[1] - a[1]), vz = (long long)(c[2] - a[2]);
+    return (uy * vz - uz * vy) == 0 && (uz * vx - ux * vz) == 0 && (ux * vy - uy * vx) == 0;
+}
+
+// returns the 4 sites used (so the caller can skip them) or sets C_STATUS = DERR_DEGENERATE
+FPK_HDN void delaunay_init(DelaunayCtx &c, int first4[4])
+{
+    for (int k = 0; k < C_COUNT; k++) c.cnt[k] = 0;
+    first4[0] = first4[1] = first4[2] = first4[3] = -1;
+    if (c.n < 4) { c.cnt[C_STATUS] = DERR_DEGENERATE; return; }
+    int f[4] = {c.order[0], -1, -1, -1};
+    for (int i = 1; i < c.n && f[1] < 0; i++) if (!pts_equal(site(c, c.order[i]), site(c, f[0]))) f[1] = c.order[i];
+    if (f[1] >= 0) for (int i = 1; i < c.n && f[2] < 0; i++) if (!pts_collinear(site(c, f[0]), site(c, f[1]), site(c, c.order[i]))) f[2] = c.order[i];
+    if (f[2] >= 0) for (int i = 1; i < c.n && f[3] < 0; i++) if (orient3d(site(c, f[0]), site(c, f[1]), site(c, f[2]), site(c, c.order[i])) != 0) f[3] = c.order[i];
+    if (f[3] < 0) { c.cnt[C_STATUS] = DERR_DEGENERATE; return; }
+    if (orient3d(site(c, f[0]), site(c, f[1]), site(c, f[2]), site(c, f[3])) < 0) { int t = f[0]; f[0] = f[1]; f[1] = t; }
+    // tet 0 = finite; tets 1..4 = ghosts g_i = tet 0 with v_i := infinity and two other slots swapped (odd permutation)
+    int T[5][4];
+    for (int k = 0; k < 4; k++) T[0][k] = f[k];
+    for (int i = 0; i < 4; i++) {
+        for (int k = 0; k < 4; k++) T[1 + i][k] = f[k];
+        T[1 + i][i] = V_INF;
+        int a = (i + 1) & 3, b = (i + 2) & 3, tmp = T[1 + i][a];
+        T[1 + i][a] = T[1 + i][b]; T[1 + i][b] = tmp;
+    }
+    for (int x = 0; x < 5; x++) {
+        int nb[4] = {-1, -1, -1, -1};
+        for (int k = 0; k < 4; k++)
+            for (int y = 0; y < 5 && nb[k] < 0; y++) {
+                if (y == x) continue;
+                int shared = 0;
+                for (int q = 0; q < 4; q++) { if (q == k) continue; for (int r = 0; r < 4; r++) if (T[y][r] == T[x][q]) { shared++; break; } }
+                if (shared == 3) nb[k] = y;
+            }
+        st4(c.tv, x, T[x]); st4(c.tn, x, nb);
+        c.own[x] = OWN_FREE; c.rim[x] = OWN_FREE; c.mark[x] = -1;
+    }
+    c.cnt[C_NTET] = 5;
+    c.cnt[C_RECENT] = 0;
+    for (int k = 0; k < 4; k++) { first4[k] = f[k]; c.first4[k] = f[k]; }
+}
+
+// ---- phase A: locate the point, grow its cavity while claiming it ----------------------------------------
+// Two claim words per tet, both lowered with atomicMin to the claimant's priority:
+//   own[t]  - t is in the claimant's CAVITY (will be destroyed)
+//   rim[t]  - t is face-adjacent to the claimant's cavity (its adjacency will be rewritten)
+// Two insertions may proceed together iff no tet is in one cavity and in the other's cavity or rim
+// (cavities neither overlap nor touch through a face: then neither new star can conflict with the other
+// point); sharing a rim tet is harmless. The claimant with the smaller priority value wins a contested tet.
+FPK_HD int prio_of(int rank) { return (int)(((hash32((uint32_t)rank ^ 0x9e3779b9u) & 0x7fu) << 24) | (uint32_t)rank); }
+FPK_HD int ld_cg(const int *p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+
+// list/cap: where the cavity goes. Returns a ST_* state; *ncav_out = number of cavity tets recorded.
+FPK_HDN int locate_and_claim(DelaunayCtx &c, int rank, int *list, int cap, int *ncav_out)
+{
+    const int p = c.order[rank];
+    const int prio = prio_of(rank);
+    const double *pp = site(c, p);
+    *ncav_out = 0;
+    // starting tet: hint grid, else the most recent tet; follow forwarding pointers of dead tets
+    int t = c.hint[hint_cell(c, pp)];
+    if (t < 0) t = c.cnt[C_RECENT];
+    for (int hop = 0; hop < 64 && c.tv[4 * (size_t)t] == T_DEAD; hop++) t = c.tn[4 * (size_t)t];
+    if (c.tv[4 * (size_t)t] == T_DEAD) {
+        t = c.cnt[C_RECENT];
+        for (int hop = 0; hop < 64 && c.tv[4 * (size_t)t] == T_DEAD; hop++) t = c.tn[4 * (size_t)t];
+        if (c.tv[4 * (size_t)t] == T_DEAD) return ST_ERR;
+    }
+    // visibility walk
+    int v[4], nb[4];
+    const int maxsteps = c.cnt[C_NTET] + 64;
+    for (int steps = 0;; steps++) {
+        if (steps > maxsteps) return ST_ERR;
+        ld4(c.tv, t, v);
+        int k = inf_slot(v);
+        if (k >= 0) {
+            if (in_conflict(c, t, v, p)) break;
+            t = c.tn[4 * (size_t)t + k];
+            continue;
+        }
+        if (pts_equal(site(c, v[0]), pp) || pts_equal(site(c, v[1]), pp) || pts_equal(site(c, v[2]), pp) || pts_equal(site(c, v[3]), pp))
+            return ST_DUP;
+        int go = -1;
+        for (int q = 0; q < 4 && go < 0; q++)
+            if (orient_sub(c, v, q, p) < 0) go = q;
+        if (go < 0) break;
+        t = c.tn[4 * (size_t)t + go];
+    }
+    // breadth-first cavity; own[t]==prio doubles as the visited flag of cavity tets, rim[t]==prio of rim tets
+    if (ld_cg(&c.rim[t]) < prio) return ST_LOST;
+    if (atomic_min_i(&c.own[t], prio) < prio) return ST_LOST;
+    list[0] = t;
+    int ncav = 1;
+    for (int qi = 0; qi < ncav; qi++) {
+        int cur = list[qi];
+        ld4(c.tn, cur, nb);
+        for (int q = 0; q < 4; q++) {
+            int x = nb[q];
+            int oc = ld_cg(&c.own[x]);
+            if (oc == prio) continue;                                   // already in my cavity
+            if (oc < prio) { *ncav_out = ncav; return ST_LOST; }        // in (or next to) a stronger cavity
+            int rr = ld_cg(&c.rim[x]);
+            if (rr == prio) continue;                                   // already known as my rim
+            ld4(c.tv, x, v);
+            if (in_conflict(c, x, v, p)) {
+                if (rr < prio) { *ncav_out = ncav; return ST_LOST; }    // a stronger insertion rewrites x's adjacency
+                if (ncav >= cap) { *ncav_out = ncav; return ST_BIG; }
+                list[ncav++] = x;                                       // recorded first so that a reset finds it
+                if (atomic_min_i(&c.own[x], prio) < prio) { *ncav_out = ncav; return ST_LOST; }
+            } else {
+                atomic_min_i(&c.rim[x], prio);
+            }
+        }
+    }
+    *ncav_out = ncav;
+    return ST_CLAIMED;
+}
+
+// ---- phase C: did every claim survive? -------------------------------------------------------------------
+FPK_HD bool verify_claims(const DelaunayCtx &c, int rank, const int *list, int ncav)
+{
+    const int prio = prio_of(rank);
+    for (int i = 0; i < ncav; i++) {
+        int cur = list[i], nb[4];
+        if (ld_cg(&c.own[cur]) != prio || ld_cg(&c.rim[cur]) < prio) return false;
+        ld4(c.tn, cur, nb);
+        for (int q = 0; q < 4; q++)
+            if (ld_cg(&c.own[nb[q]]) < prio) return false;               // rim tet inside a stronger cavity
+    }
+    return true;
+}
+
+// ---- phase R: drop all claims (mesh still untouched, so the rims are still reachable) ----------------------
+FPK_HD void reset_claims(DelaunayCtx &c, const int *list, int ncav)
+{
+    for (int i = 0; i < ncav; i++) {
+        int cur = list[i], nb[4];
+        ld4(c.tn, cur, nb);
+        c.own[cur] = OWN_FREE; c.rim[cur] = OWN_FREE;
+        for (int q = 0; q < 4; q++) { c.own[nb[q]] = OWN_FREE; c.rim[nb[q]] = OWN_FREE; }
+    }
+}
+
+FPK_HD int alloc_tet(DelaunayCtx &c, int popstack)
+{
+    int i = atomic_add_i(&c.cnt[C_NFREE0 + popstack], -1) - 1;
+    if (i >= 0) return c.freest[popstack][i];
+    int t = atomic_add_i(&c.cnt[C_NTET], 1);
+    if (t >= c.cap) { c.cnt[C_STATUS] = DERR_CAPACITY; return -1; }
+    return t;
+}
+
+// ---- phase D: a winner replaces its cavity by the star of p --------------------------------------------------
+FPK_HDN bool commit_insertion(DelaunayCtx &c, int rank, const int *list, int *newid, int ncav, int popstack)
+{
+    const int p = c.order[rank];
+    for (int i = 0; i < ncav; i++) { c.mark[list[i]] = rank; c.cavpos[list[i]] = i; }
+    int firstnew = -1;
+    int v[4], nb[4], w[4], wn[4];
+    // one new tet per rim face
+    for (int i = 0; i < ncav; i++) {
+        int cur = list[i];
+        ld4(c.tv, cur, v); ld4(c.tn, cur, nb);
+        for (int q = 0; q < 4; q++) {
+            int o = nb[q];
+            if (c.mark[o] == rank) { newid[4 * i + q] = -1; continue; }
+            int nt = alloc_tet(c, popstack);
+            if (nt < 0) return false;
+            newid[4 * i + q] = nt;
+            if (firstnew < 0) firstnew = nt;
+            int nv[4] = {v[0], v[1], v[2], v[3]};
+            nv[q] = p;
+            st4(c.tv, nt, nv);
+            c.tn[4 * (size_t)nt + q] = o;
+            c.own[nt] = OWN_FREE; c.rim[nt] = OWN_FREE; c.mark[nt] = -1;
+            // back pointer: the slot of o that faced cur through this face
+            ld4(c.tv, o, w); ld4(c.tn, o, wn);
+            for (int r = 0; r < 4; r++) {
+                if (wn[r] != cur) continue;
+                bool inface = false;
+                for (int z = 0; z < 4; z++) inface |= (z != q && v[z] == w[r]);
+                if (!inface) { c.tn[4 * (size_t)o + r] = nt; break; }
+            }
+        }
+    }
+    // adjacency between the new tets: rotate around each rim edge through the cavity
+    for (int i = 0; i < ncav; i++) {
+        int cur0 = list[i];
+        ld4(c.tv, cur0, v);
+        for (int q = 0; q < 4; q++) {
+            int nt = newid[4 * i + q];
+            if (nt < 0) continue;
+            for (int j = 0; j < 4; j++) {
+                if (j == q) continue;
+                int e0 = -9, e1 = -9;           // the rim edge: vertices of cur0 other than v[q], v[j]
+                for (int z = 0; z < 4; z++) if (z != q && z != j) { if (e0 == -9) e0 = v[z]; else e1 = v[z]; }
+                int cur = cur0, wv = v[j], other = v[q];
+                int found = -1;
+                for (int guard = 0; guard <= ncav + 1; guard++) {
+                    ld4(c.tv, cur, w); ld4(c.tn, cur, wn);
+                    int ws = (w[0] == wv) ? 0 : (w[1] == wv) ? 1 : (w[2] == wv) ? 2 : 3;
+                    int nx = wn[ws];
+                    if (c.mark[nx] != rank) { found = newid[4 * c.cavpos[cur] + ws]; break; }
+                    ld4(c.tv, nx, w);
+                    int apex = -9;
+                    for (int z = 0; z < 4; z++) if (w[z] != other && w[z] != e0 && w[z] != e1) apex = w[z];
+                    wv = other; other = apex; cur = nx;
+                }
+                if (found < 0) { c.cnt[C_STATUS] = DERR_ROTATE; return false; }
+                c.tn[4 * (size_t)nt + j] = found;
+            }
+        }
+    }
+    // retire the cavity: dead tets forward to a new one and go to the push stack
+    int *pushst = c.freest[popstack ^ 1];
+    int base = atomic_add_i(&c.cnt[C_NFREE0 + (popstack ^ 1)], ncav);
+    for (int i = 0; i < ncav; i++) {
+        int cur = list[i];
+        c.tv[4 * (size_t)cur] = T_DEAD;
+        c.tn[4 * (size_t)cur] = firstnew;
+        pushst[base + i] = cur;
+    }
+    c.hint[hint_cell(c, site(c, p))] = firstnew;
+    c.cnt[C_RECENT] = firstnew;
+    return true;
+}
+
+// =========================== per-thread phase wrappers (block-synchronous driver) ===========================
+// P0: take the next point of my chunk if I have none pending. Returns true if this thread has work.
+FPK_HD bool phase_assign(DelaunayCtx &c, int tid)
+{
+    int *ti = c.tinfo + 4 * tid, *cu = c.cursor + 2 * tid;
+    while (ti[0] < 0 && cu[0] < cu[1]) {
+        int r = cu[0]++, s = c.order[r];
+        if (s != c.first4[0] && s != c.first4[1] && s != c.first4[2] && s != c.first4[3]) ti[0] = r;
+    }
+    ti[1] = ST_IDLE;
+    return ti[0] >= 0;
+}
+FPK_HD void phase_claim(DelaunayCtx &c, int tid)
+{
+    int *ti = c.tinfo + 4 * tid;
+    if (ti[0] < 0) return;
+    int ncav = 0;
+    ti[1] = locate_and_claim(c, ti[0], c.cav + (size_t)tid * CAVMAX, CAVMAX, &ncav);
+    ti[2] = ncav;
+}
+FPK_HD void phase_verify(DelaunayCtx &c, int tid)
+{
+    int *ti = c.tinfo + 4 * tid;
+    if (ti[0] < 0 || ti[1] != ST_CLAIMED) return;
+    ti[1] = verify_claims(c, ti[0], c.cav + (size_t)tid * CAVMAX, ti[2]) ? ST_WIN : ST_LOST;
+}
+FPK_HD void phase_reset(DelaunayCtx &c, int tid)
+{
+    int *ti = c.tinfo + 4 * tid;
+    if (ti[0] < 0) return;
+    if (ti[1] == ST_WIN || ti[1] == ST_LOST || ti[1] == ST_BIG || ti[1] == ST_CLAIMED)
+        reset_claims(c, c.cav + (size_t)tid * CAVMAX, ti[2]);
+}
+FPK_HD void phase_commit(DelaunayCtx &c, int tid)
+{
+    int *ti = c.tinfo + 4 * tid;
+    if (ti[0] < 0) return;
+    int popstack = c.cnt[C_SUBROUND] & 1;
+    if (ti[1] == ST_WIN) {
+        commit_insertion(c, ti[0], c.cav + (size_t)tid * CAVMAX, c.newid + (size_t)tid * CAVMAX * 4, ti[2], popstack);
+        ti[0] = -1;
+    } else if (ti[1] == ST_DUP) {
+        atomic_add_i(&c.cnt[C_NDUP], 1);
+        ti[0] = -1;
+    } else if (ti[1] == ST_ERR) {
+        c.cnt[C_STATUS] = DERR_WALK;
+        ti[0] = -1;
+    } else if (ti[1] == ST_LOST) {
+        atomic_add_i(&c.cnt[C_NRETRY], 1);
+    }
+}
+// serial tail of a sub-round, one thread: insert at most one over-sized cavity, then flip the free stacks
+FPK_HDN void phase_serial(DelaunayCtx &c)
+{
+    int popstack = c.cnt[C_SUBROUND] & 1;
+    for (int t = 0; t < c.nthreads; t++) {
+        int *ti = c.tinfo + 4 * t;
+        if (ti[0] >= 0 && ti[1] == ST_BIG) {
+            int ncav = 0;
+            int st = locate_and_claim(c, ti[0], c.bigcav, c.cap, &ncav);
+            reset_claims(c, c.bigcav, ncav);
+            if (st == ST_CLAIMED) commit_insertion(c, ti[0], c.bigcav, c.bignewid, ncav, popstack);
+            else if (st != ST_DUP) c.cnt[C_STATUS] = DERR_CAPACITY;
+            c.cnt[C_NBIG]++;
+            ti[0] = -1;
+            break;
+        }
+    }
+    if (c.cnt[C_NFREE0 + popstack] < 0) c.cnt[C_NFREE0 + popstack] = 0;
+    c.cnt[C_SUBROUND]++;
+    c.cnt[C_NSUB]++;
+}
+
+// chunk [lo,hi) of `order` handed to thread tid for a round [r0,r1)
+FPK_HD void round_chunk(int r0, int r1, int tid, int nthreads, int *lo, int *hi)
+{
+    int len = r1 - r0, cs = (len + nthreads - 1) / nthreads;
+    int a = r0 + tid * cs, b = a + cs;
+    if (a > r1) a = r1;
+    if (b > r1) b = r1;
+    *lo = a; *hi = b;
+}
+
+}  // namespace fpk
