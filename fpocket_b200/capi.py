@@ -19,6 +19,7 @@ FPK_ERR_NO_POCKETS = -7
 
 FPK_ATOM_H = 1
 FPK_ATOM_XPOCKET = 2
+FPK_ATOM_H1 = 4
 
 _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int32)

@@ -1,0 +1,762 @@
+// libfpocket_cuda: host side of the C ABI declared in include/fpocket_cuda.h.
+//
+// Host work here is packing (flatten the caller's arrays into pinned staging buffers, one H2D copy per
+// array), launching the kernels and unpacking (slices of a few large D2H buffers). Every stage of the
+// hot path runs on the GPU; there is no CPU implementation behind these entry points.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "k_hull_md.cuh"
+
+using namespace fpk;
+
+// ------------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int g_dev = -1, g_sms = 0;
+static bool g_init = false;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) return fail(FPK_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char *fpk_last_error(void) { return g_err.c_str(); }
+extern "C" const char *fpk_version(void) { return "fpocket_b200 0.1 (sm_100a)"; }
+
+extern "C" void fpk_default_params(fpk_params *p)
+{
+    memset(p, 0, sizeof *p);
+    p->asph_min_size = (float)3.4; p->asph_max_size = (float)6.2; p->clust_max_dist = (float)2.4;
+    p->refine_min_apolar_asphere_prop = (float)0.0; p->min_as_density = (float)0.7;
+    p->min_apol_neigh = 3; p->nb_mcv_iter = 300; p->min_pock_nb_asph = 15;
+    p->do_asa_and_volume = 1; p->min_n_explicit_pocket_atoms = 4; p->mc_seed = 20260101ull;
+}
+
+// asa.c:438-454 get_points_on_sphere(100): computed with the host libm exactly as the reference does
+static void spiral_points(float *pts)
+{
+    const int nop = 100;
+    float inc = (float)(3.1415926535897932384626433832795 * (3.0 - sqrt(5.0)));
+    float off = (float)(2.0 / (double)(float)nop);
+    for (int k = 0; k < nop; k++) {
+        float y = (float)((double)(((float)k) * off) - 1.0 + ((double)off / 2.0));
+        float r = (float)sqrt(1.0 - (double)(y * y));
+        float phi = (float)k * inc;
+        pts[3 * k] = (float)(cos((double)phi) * (double)r);
+        pts[3 * k + 1] = y;
+        pts[3 * k + 2] = (float)(sin((double)phi) * (double)r);
+    }
+}
+
+extern "C" int fpk_init(const int *devices, int ndev)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(FPK_ERR_NO_DEVICE, "no CUDA device (%s); libfpocket_cuda has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    int dev = 0;
+    if (devices && ndev > 0) dev = devices[0];
+    else cudaGetDevice(&dev);
+    cudaDeviceProp pr;
+    CK(cudaGetDeviceProperties(&pr, dev));
+    if (pr.major < 10) return fail(FPK_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev, pr.major, pr.minor);
+    CK(cudaSetDevice(dev));
+    g_dev = dev; g_sms = pr.multiProcessorCount;
+    float pts[300];
+    spiral_points(pts);
+    CK(cudaMemcpyToSymbol(c_spiral, pts, sizeof pts));
+    g_init = true;
+    return FPK_OK;
+}
+extern "C" void fpk_shutdown(void) { g_init = false; }
+
+static int ensure_init()
+{
+    if (g_init) { cudaSetDevice(g_dev); return FPK_OK; }
+    return fpk_init(nullptr, 0);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+struct Arena {
+    char *base = nullptr;
+    size_t cap = 0, used = 0;
+    template <class T> T *take(size_t n)
+    {
+        used = (used + 255) & ~(size_t)255;
+        T *p = reinterpret_cast<T *>(base + used);
+        used += n * sizeof(T);
+        return p;
+    }
+    void release() { if (base) cudaFree(base); base = nullptr; cap = used = 0; }
+};
+// first pass with base == nullptr just measures
+template <class F> static int arena_build(Arena &A, F layout)
+{
+    Arena m; m.base = nullptr; m.used = 0;
+    layout(m);
+    size_t need = m.used + 4096;
+    if (need > A.cap) {
+        A.release();
+        cudaError_t e = cudaMalloc(&A.base, need);
+        if (e != cudaSuccess) return fail(FPK_ERR_CUDA, "cudaMalloc(%zu bytes): %s", need, cudaGetErrorString(e));
+        A.cap = need;
+    }
+    A.used = 0;
+    layout(A);
+    return FPK_OK;
+}
+
+struct HostResults {            // owner of the unpacked host arrays of one fetch
+    int refs = 0;
+    std::vector<float> xyzr, bary, atom_fx;
+    std::vector<int> neigh, cluster, cl_off, cl_sph, cl_atom_off, cl_atoms, rank, tets;
+    std::vector<uint8_t> type;
+    std::vector<fpk_desc> desc;
+};
+
+struct fpk_batch {
+    int n = 0;
+    fpk_params prm;
+    std::vector<StructDev> S;
+    std::vector<int> natoms;
+    long long tot_atoms = 0, tot_w = 0, tot_sites = 0, tot_xlig = 0, tot_sphcap = 0, tot_tetcap = 0;
+    int max_sites = 0, max_w = 0, max_sphcap = 0;
+    int md_shared_props = 0;           // mdpocket: all frames share the property arrays
+    // stage 1 device
+    Arena A1, A2;
+    BatchDev B;
+    StructDev *dS = nullptr;
+    DelScratch *dDel = nullptr; int nDel = 0;
+    ClusterScratch *dClu = nullptr; int nClu = 0;
+    int *d_counters = nullptr;         // [8] work counters
+    int *d_order = nullptr;
+    // stage 2
+    PocketDev Pk;
+    int *d_clbase = nullptr, *d_sbase = nullptr;
+    DelScratch *dHull = nullptr; int nHull = 0;
+    DescScratch *dDesc = nullptr; int nDesc = 0;
+    // compact outputs (device)
+    float4 *c_xyzr = nullptr; float *c_bary = nullptr; int4 *c_neigh = nullptr; uint8_t *c_type = nullptr; int *c_cluster = nullptr;
+    int *c_cl_sph = nullptr, *c_cl_off = nullptr;
+    std::vector<int> h_counts, h_clbase, h_sbase;
+    long long tot_spheres = 0, tot_clusters = 0, tot_tets = 0;
+    // timing / accounting
+    cudaEvent_t ev[8];
+    float ms[8] = {0};
+    long long launches = 0, h2d = 0, d2h = 0;
+    bool events = false;
+    ~fpk_batch() { A1.release(); A2.release(); if (events) for (auto &e : ev) cudaEventDestroy(e); }
+};
+
+static inline size_t sph_cap_for(const fpk_params &p, int nsites, double factor_override)
+{
+    // typical proteins keep ~0.6 spheres per heavy atom at default radii; everything (7 tets/atom) otherwise
+    double f = factor_override > 0 ? factor_override : ((p.asph_max_size <= 6.3f && p.asph_min_size >= 3.3f) ? 1.6 : 7.2);
+    return (size_t)(f * nsites) + 64;
+}
+
+static int batch_pack(fpk_batch *b, const fpk_structure *in, int n, const fpk_params *p, double cap_factor)
+{
+    b->n = n; b->prm = *p;
+    b->S.resize(n); b->natoms.resize(n);
+    long long ao = 0, wo = 0, so = 0, xo = 0, sc = 0, tc = 0;
+    for (int k = 0; k < n; k++) {
+        const fpk_structure &s = in[k];
+        if (s.natoms < 0 || (s.natoms > 0 && (!s.x || !s.y || !s.z || !s.radius || !s.electroneg || !s.bfactor || !s.atom_id || !s.res_id || !s.aa_idx || !s.flags)))
+            return fail(FPK_ERR_BAD_ARG, "structure %d: NULL atom array", k);
+        if (s.natoms_w > 0 && (!s.wx || !s.wy || !s.wz || !s.wradius || !s.welectroneg || !s.wflags))
+            return fail(FPK_ERR_BAD_ARG, "structure %d: NULL pdb_w_lig array", k);
+        if (s.natoms_w == 0 && !s.same_pdb)
+            return fail(FPK_ERR_BAD_ARG, "structure %d: natoms_w == 0 requires same_pdb = 1", k);
+        StructDev &d = b->S[k];
+        memset(&d, 0, sizeof d);
+        int ns = 0;
+        for (int i = 0; i < s.natoms; i++) ns += !(s.flags[i] & FPK_ATOM_H);
+        // contacted atoms are made unique by id (pocket.c:1298) but ASA works on pointers (asa.c:51): both coincide iff ids are unique
+        bool inc = true;
+        for (int i = 1; i < s.natoms && inc; i++) inc = s.atom_id[i] > s.atom_id[i - 1];
+        if (!inc) {
+            std::vector<int> ids(s.atom_id, s.atom_id + s.natoms);
+            std::sort(ids.begin(), ids.end());
+            if (std::adjacent_find(ids.begin(), ids.end()) != ids.end())
+                return fail(FPK_ERR_BAD_ARG, "structure %d: duplicate atom ids are not supported", k);
+        }
+        d.atom_off = (int)ao; d.natoms = s.natoms; d.prop_off = (int)ao;
+        d.w_off = (int)wo; d.natoms_w = s.natoms_w;
+        d.site_off = (int)so; d.nsites = ns;
+        d.xlig_off = (int)xo; d.n_xlig = s.n_xlig;
+        d.same_pdb = s.same_pdb;
+        d.avg_b = s.avg_bfactor; d.min_b = s.min_bfactor; d.max_b = s.max_bfactor;
+        d.sph_off = (int)sc; d.sph_cap = (int)sph_cap_for(*p, ns, cap_factor);
+        d.tet_off = (int)tc; d.tet_cap = p->want_tets ? 8 * ns + 64 : 0;
+        b->natoms[k] = s.natoms;
+        ao += s.natoms; wo += s.natoms_w; so += ns; xo += s.n_xlig; sc += d.sph_cap; tc += d.tet_cap;
+        b->max_sites = std::max(b->max_sites, ns);
+        b->max_w = std::max(b->max_w, s.natoms_w ? s.natoms_w : s.natoms);
+        b->max_sphcap = std::max(b->max_sphcap, d.sph_cap);
+        if (ao > 2000000000ll || sc + n > 2000000000ll || tc > 500000000ll) return fail(FPK_ERR_BAD_ARG, "batch too large for 32-bit offsets; split it");
+    }
+    b->tot_atoms = ao; b->tot_w = wo; b->tot_sites = so; b->tot_xlig = xo; b->tot_sphcap = sc; b->tot_tetcap = tc;
+    return FPK_OK;
+}
+
+static size_t del_scratch_layout(Arena &a, DelScratch &x, int nmax, int scap, int nthreads, bool with_filter)
+{
+    int npad = 1;
+    while (npad < nmax) npad <<= 1;
+    int cap = 10 * nmax + 256;
+    x.cap = cap;
+    x.P = a.take<double>(3 * (size_t)nmax);
+    x.keys = a.take<unsigned long long>(npad);
+    x.order = a.take<int>(nmax);
+    x.tv = a.take<int>(4 * (size_t)cap); x.tn = a.take<int>(4 * (size_t)cap);
+    x.own = a.take<int>(cap); x.rim = a.take<int>(cap); x.mark = a.take<int>(cap); x.cavpos = a.take<int>(cap);
+    x.free0 = a.take<int>(cap); x.free1 = a.take<int>(cap);
+    x.hint = a.take<int>(32 * 32 * 32);
+    x.cav = a.take<int>((size_t)nthreads * CAVMAX); x.newid = a.take<int>((size_t)nthreads * CAVMAX * 4);
+    x.tinfo = a.take<int>(4 * (size_t)nthreads); x.cursor = a.take<int>(2 * (size_t)nthreads);
+    x.bigcav = a.take<int>(cap); x.bignewid = a.take<int>(4 * (size_t)cap);
+    x.cnt = a.take<int>(C_COUNT); x.rstart = a.take<int>(40);
+    x.scap = with_filter ? scap : 0;
+    x.rawkey = a.take<int4>(with_filter ? scap : 1); x.rawxyzr = a.take<float4>(with_filter ? scap : 1);
+    x.sitecnt = a.take<int>(with_filter ? nmax + 1 : 1); x.bucket = a.take<int>(with_filter ? scap : 1);
+    return a.used;
+}
+
+template <class T> static int h2d_gather(fpk_batch *b, T *dst, const fpk_structure *in, int n, const T *const fpk_structure::*field,
+                                         const int fpk_structure::*count, std::vector<char> &stage)
+{
+    size_t tot = 0;
+    for (int k = 0; k < n; k++) tot += (size_t)(in[k].*count);
+    if (!tot) return FPK_OK;
+    stage.resize(tot * sizeof(T));
+    T *h = reinterpret_cast<T *>(stage.data());
+    size_t o = 0;
+    for (int k = 0; k < n; k++) {
+        size_t c = (size_t)(in[k].*count);
+        if (c) memcpy(h + o, in[k].*field, c * sizeof(T));
+        o += c;
+    }
+    CK(cudaMemcpy(dst, h, tot * sizeof(T), cudaMemcpyHostToDevice));
+    b->h2d += (long long)(tot * sizeof(T));
+    return FPK_OK;
+}
+
+static int batch_upload(fpk_batch *b, const fpk_structure *in)
+{
+    const int n = b->n;
+    int occ1 = 2, occ3 = 4;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_delaunay_filter, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_cluster, 256, 0);
+    occ1 = std::max(1, std::min(occ1, 4)); occ3 = std::max(1, std::min(occ3, 4));
+    b->nDel = std::max(1, std::min(n, g_sms * occ1));
+    b->nClu = std::max(1, std::min(n, g_sms * occ3));
+    std::vector<DelScratch> hDel(b->nDel);
+    std::vector<ClusterScratch> hClu(b->nClu);
+    BatchDev &B = b->B;
+    memset(&B, 0, sizeof B);
+    int rc = arena_build(b->A1, [&](Arena &a) {
+        b->dS = a.take<StructDev>(n);
+        float *ax = a.take<float>(b->tot_atoms), *ay = a.take<float>(b->tot_atoms), *az = a.take<float>(b->tot_atoms);
+        float *ar = a.take<float>(b->tot_atoms), *ae = a.take<float>(b->tot_atoms), *ab = a.take<float>(b->tot_atoms);
+        int *aid = a.take<int>(b->tot_atoms), *ares = a.take<int>(b->tot_atoms);
+        int8_t *aaa = a.take<int8_t>(b->tot_atoms);
+        uint8_t *afl = a.take<uint8_t>(b->tot_atoms);
+        float *wx = a.take<float>(b->tot_w), *wy = a.take<float>(b->tot_w), *wz = a.take<float>(b->tot_w), *wr = a.take<float>(b->tot_w),
+              *we = a.take<float>(b->tot_w);
+        uint8_t *wfl = a.take<uint8_t>(b->tot_w);
+        int *s2a = a.take<int>(b->tot_sites);
+        float *xl = a.take<float>(3 * b->tot_xlig + 1);
+        B.ax = ax; B.ay = ay; B.az = az; B.arad = ar; B.aen = ae; B.abf = ab; B.aid = aid; B.ares = ares; B.aaa = aaa; B.afl = afl;
+        B.wx = wx; B.wy = wy; B.wz = wz; B.wrad = wr; B.wen = we; B.wfl = wfl; B.site2atom = s2a; B.xlig = xl;
+        B.s_xyzr = a.take<float4>(b->tot_sphcap); B.s_bary = a.take<float>(3 * b->tot_sphcap);
+        B.s_neigh = a.take<int4>(b->tot_sphcap); B.s_key = a.take<int4>(b->tot_sphcap);
+        B.s_type = a.take<uint8_t>(b->tot_sphcap); B.s_cluster = a.take<int>(b->tot_sphcap);
+        B.cl_off = a.take<int>(b->tot_sphcap + 2 * (size_t)n + 2); B.cl_sph = a.take<int>(b->tot_sphcap);
+        B.counts = a.take<int>((size_t)n * CNT_STRIDE);
+        b->d_order = a.take<int>(n);
+        b->d_counters = a.take<int>(8);
+        B.tets_out = b->tot_tetcap ? a.take<int>(4 * b->tot_tetcap) : nullptr;
+        b->dDel = a.take<DelScratch>(b->nDel);
+        b->dClu = a.take<ClusterScratch>(b->nClu);
+        for (int i = 0; i < b->nDel; i++) del_scratch_layout(a, hDel[i], b->max_sites, b->max_sphcap, 256, true);
+        for (int i = 0; i < b->nClu; i++) {
+            hClu[i].cellcnt = a.take<int>(CELLMAX + 2); hClu[i].cellsph = a.take<int>(b->max_sphcap + 1);
+            hClu[i].tmp = a.take<int>(b->max_sphcap + 2); hClu[i].scap = b->max_sphcap;
+        }
+    });
+    if (rc) return rc;
+    B.nstruct = n; B.S = b->dS; B.prm = b->prm; B.work_order = b->d_order; B.work_counter = b->d_counters;
+    std::vector<char> stage;
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return b->S[x].nsites > b->S[y].nsites; });
+    CK(cudaMemcpy(b->dS, b->S.data(), sizeof(StructDev) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b->d_order, order.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b->dDel, hDel.data(), sizeof(DelScratch) * b->nDel, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b->dClu, hClu.data(), sizeof(ClusterScratch) * b->nClu, cudaMemcpyHostToDevice));
+    b->h2d += (long long)(sizeof(StructDev) + sizeof(int)) * n;
+    if (in) {
+#define UP(dst, field, cnt) if ((rc = h2d_gather(b, const_cast<std::remove_const<std::remove_pointer<decltype(B.dst)>::type>::type *>(B.dst), in, n, &fpk_structure::field, &fpk_structure::cnt, stage))) return rc;
+        UP(ax, x, natoms) UP(ay, y, natoms) UP(az, z, natoms) UP(arad, radius, natoms) UP(aen, electroneg, natoms) UP(abf, bfactor, natoms)
+        UP(aid, atom_id, natoms) UP(ares, res_id, natoms) UP(aaa, aa_idx, natoms) UP(afl, flags, natoms)
+        UP(wx, wx, natoms_w) UP(wy, wy, natoms_w) UP(wz, wz, natoms_w) UP(wrad, wradius, natoms_w) UP(wen, welectroneg, natoms_w) UP(wfl, wflags, natoms_w)
+#undef UP
+        // site map (voronoi.c:94-107 h_tr) and explicit-ligand coordinates
+        std::vector<int> s2a((size_t)b->tot_sites);
+        std::vector<float> xl(3 * (size_t)b->tot_xlig + 1);
+        size_t so = 0, xo = 0;
+        for (int k = 0; k < n; k++) {
+            for (int i = 0; i < in[k].natoms; i++) if (!(in[k].flags[i] & FPK_ATOM_H)) s2a[so++] = i;
+            if (in[k].n_xlig) { memcpy(&xl[3 * xo], in[k].xlig, sizeof(float) * 3 * in[k].n_xlig); xo += in[k].n_xlig; }
+        }
+        if (so) CK(cudaMemcpy(const_cast<int *>(B.site2atom), s2a.data(), sizeof(int) * so, cudaMemcpyHostToDevice));
+        if (xo) CK(cudaMemcpy(const_cast<float *>(B.xlig), xl.data(), sizeof(float) * 3 * xo, cudaMemcpyHostToDevice));
+        b->h2d += (long long)(sizeof(int) * so + sizeof(float) * 3 * xo);
+    }
+    if (!b->events) { for (auto &e : b->ev) CK(cudaEventCreate(&e)); b->events = true; }
+    return FPK_OK;
+}
+
+__global__ void k_compact(BatchDev B, const int *sbase, float4 *xyzr, float *bary, int4 *neigh, uint8_t *type, int *cluster, int *cl_sph,
+                          int *cl_off, const int *clbase)
+{
+    const int k = blockIdx.x;
+    const StructDev S = B.S[k];
+    const int *counts = B.counts + (size_t)k * CNT_STRIDE;
+    const int ns = (counts[CNT_STATUS] == FPK_OK || counts[CNT_STATUS] == FPK_ERR_NO_POCKETS || counts[CNT_STATUS] == FPK_ERR_NO_SPHERES) ? counts[CNT_SPHERES] : 0;
+    const int nc = counts[CNT_CLUSTERS];
+    const int d0 = sbase[k];
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+        const int s = S.sph_off + i;
+        xyzr[d0 + i] = B.s_xyzr[s]; neigh[d0 + i] = B.s_neigh[s]; type[d0 + i] = B.s_type[s]; cluster[d0 + i] = nc ? B.s_cluster[s] : 0;
+        bary[3 * (size_t)(d0 + i)] = B.s_bary[3 * (size_t)s]; bary[3 * (size_t)(d0 + i) + 1] = B.s_bary[3 * (size_t)s + 1];
+        bary[3 * (size_t)(d0 + i) + 2] = B.s_bary[3 * (size_t)s + 2];
+        cl_sph[d0 + i] = nc ? B.cl_sph[s] : 0;
+    }
+    for (int i = threadIdx.x; i <= nc; i += blockDim.x) cl_off[clbase[k] + k + i] = B.cl_off[S.sph_off + k + i];
+}
+
+static int batch_run(fpk_batch *b)
+{
+    const int n = b->n;
+    BatchDev &B = b->B;
+    b->launches = 0;
+    CK(cudaMemsetAsync(b->d_counters, 0, sizeof(int) * 8));
+    CK(cudaMemsetAsync(B.counts, 0, sizeof(int) * (size_t)n * CNT_STRIDE));
+    CK(cudaEventRecord(b->ev[0]));
+    k_delaunay_filter<<<b->nDel, 256>>>(B, b->dDel);
+    CK(cudaEventRecord(b->ev[1]));
+    k_cluster<<<b->nClu, 256>>>(B, b->dClu, b->d_counters + 1);
+    CK(cudaEventRecord(b->ev[2]));
+    b->launches += 2;
+    // ---- the one host round trip: per-structure counts -> exact sizes of the pocket-level arrays -----------------------
+    b->h_counts.resize((size_t)n * CNT_STRIDE);
+    CK(cudaMemcpy(b->h_counts.data(), B.counts, sizeof(int) * (size_t)n * CNT_STRIDE, cudaMemcpyDeviceToHost));
+    b->d2h += (long long)sizeof(int) * n * CNT_STRIDE;
+    b->h_clbase.assign(n + 1, 0); b->h_sbase.assign(n + 1, 0);
+    int max_ns = 1;
+    long long tt = 0;
+    for (int k = 0; k < n; k++) {
+        const int *c = &b->h_counts[(size_t)k * CNT_STRIDE];
+        bool have = c[CNT_STATUS] == FPK_OK || c[CNT_STATUS] == FPK_ERR_NO_SPHERES || c[CNT_STATUS] == FPK_ERR_NO_POCKETS;
+        int ns = have ? c[CNT_SPHERES] : 0;
+        b->h_clbase[k + 1] = b->h_clbase[k] + c[CNT_CLUSTERS];
+        b->h_sbase[k + 1] = b->h_sbase[k] + ns;
+        max_ns = std::max(max_ns, ns);
+        tt += c[CNT_TETS];
+    }
+    b->tot_clusters = b->h_clbase[n]; b->tot_spheres = b->h_sbase[n]; b->tot_tets = tt;
+    const long long NC = b->tot_clusters, NS = b->tot_spheres;
+    int occH = 8, occD = 8;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occH, k_hull_volume, HULL_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occD, k_descriptors, K4_THREADS, 0);
+    occH = std::max(1, std::min(occH, 8)); occD = std::max(1, std::min(occD, 8));
+    b->nHull = (int)std::max(1ll, std::min<long long>(NC, (long long)g_sms * occH));
+    b->nDesc = (int)std::max(1ll, std::min<long long>(NC, (long long)g_sms * occD));
+    std::vector<DelScratch> hHull(b->nHull);
+    std::vector<DescScratch> hDesc(b->nDesc);
+    PocketDev &Pk = b->Pk;
+    memset(&Pk, 0, sizeof Pk);
+    const bool full = b->prm.do_asa_and_volume != 0;
+    int rc = arena_build(b->A2, [&](Arena &a) {
+        b->d_clbase = a.take<int>(n + 1); b->d_sbase = a.take<int>(n + 1);
+        Pk.desc = a.take<fpk_desc>(NC + 1);
+        Pk.cl_atoms = a.take<int>(4 * NS + 4); Pk.ent_u = a.take<int>(4 * NS + 4); Pk.touch_off = a.take<int>(5 * NS + 5);
+        Pk.touch_list = a.take<int>(4 * NS + 4); Pk.acc = a.take<int>(16 * NS + 16); Pk.fx_val = a.take<float>(16 * NS + 16);
+        Pk.fx_who = a.take<int>(2 * b->tot_atoms + 2); Pk.atom_fx = a.take<float>(4 * b->tot_atoms + 4);
+        Pk.rank_to_cluster = a.take<int>(NS + n + 1);
+        b->c_xyzr = a.take<float4>(NS + 1); b->c_bary = a.take<float>(3 * NS + 3); b->c_neigh = a.take<int4>(NS + 1);
+        b->c_type = a.take<uint8_t>(NS + 1); b->c_cluster = a.take<int>(NS + 1); b->c_cl_sph = a.take<int>(NS + 1);
+        b->c_cl_off = a.take<int>(NC + n + 1);
+        b->dHull = a.take<DelScratch>(b->nHull); b->dDesc = a.take<DescScratch>(b->nDesc);
+        if (full) for (int i = 0; i < b->nHull; i++) del_scratch_layout(a, hHull[i], max_ns, 0, HULL_THREADS, false);
+        for (int i = 0; i < b->nDesc; i++) hDesc[i].sa = a.take<int>(b->max_w + 1);
+    });
+    if (rc) return rc;
+    Pk.clbase = b->d_clbase; Pk.sbase = b->d_sbase; Pk.total_clusters = (int)NC;
+    CK(cudaMemcpyAsync(b->d_clbase, b->h_clbase.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(b->d_sbase, b->h_sbase.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
+    if (full) CK(cudaMemcpyAsync(b->dHull, hHull.data(), sizeof(DelScratch) * b->nHull, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(b->dDesc, hDesc.data(), sizeof(DescScratch) * b->nDesc, cudaMemcpyHostToDevice));
+    CK(cudaMemsetAsync(Pk.desc, 0, sizeof(fpk_desc) * (size_t)(NC + 1)));
+    CK(cudaMemsetAsync(Pk.fx_who, 0xff, sizeof(int) * (2 * (size_t)b->tot_atoms + 2)));
+    CK(cudaMemsetAsync(Pk.atom_fx, 0, sizeof(float) * (4 * (size_t)b->tot_atoms + 4)));
+    // stage-2 arrays are addressed through the compact sphere base: rebase the per-structure offsets used by the pocket kernels
+    // (the kernels compute R = sph_off + cl_off[c]; with sph_off replaced by sbase for these arrays). See PocketDev.
+    CK(cudaEventRecord(b->ev[3]));
+    if (NC > 0) {
+        if (full) { k_hull_volume<<<b->nHull, HULL_THREADS>>>(B, Pk, b->dHull, b->d_counters + 2); b->launches++; }
+        CK(cudaEventRecord(b->ev[4]));
+        k_descriptors<<<b->nDesc, K4_THREADS>>>(B, Pk, b->dDesc, b->d_counters + 3);
+        CK(cudaEventRecord(b->ev[5]));
+        k_finalize<<<n, 128>>>(B, Pk);
+        if (full) { k_atom_fx<<<(unsigned)NC, 64>>>(B, Pk); b->launches++; }
+        b->launches += 2;
+    } else {
+        CK(cudaEventRecord(b->ev[4])); CK(cudaEventRecord(b->ev[5]));
+    }
+    k_compact<<<n, 128>>>(B, b->d_sbase, b->c_xyzr, b->c_bary, b->c_neigh, b->c_type, b->c_cluster, b->c_cl_sph, b->c_cl_off, b->d_clbase);
+    b->launches++;
+    CK(cudaEventRecord(b->ev[6]));
+    CK(cudaDeviceSynchronize());
+    CK(cudaGetLastError());
+    for (int i = 0; i < 6; i++) cudaEventElapsedTime(&b->ms[i], b->ev[i], b->ev[i + 1]);
+    cudaEventElapsedTime(&b->ms[7], b->ev[0], b->ev[6]);
+    // refresh counts (pockets / final status written by k_finalize)
+    CK(cudaMemcpy(b->h_counts.data(), B.counts, sizeof(int) * (size_t)n * CNT_STRIDE, cudaMemcpyDeviceToHost));
+    b->d2h += (long long)sizeof(int) * n * CNT_STRIDE;
+    return FPK_OK;
+}
+
+template <class T> static int d2h(fpk_batch *b, std::vector<T> &dst, const void *src, size_t count)
+{
+    dst.resize(count);
+    if (count) { CK(cudaMemcpy(dst.data(), src, count * sizeof(T), cudaMemcpyDeviceToHost)); b->d2h += (long long)(count * sizeof(T)); }
+    return FPK_OK;
+}
+
+static int batch_fetch(fpk_batch *b, fpk_result *out)
+{
+    const int n = b->n;
+    HostResults *H = new HostResults();
+    const long long NS = b->tot_spheres, NC = b->tot_clusters;
+    int rc;
+    std::vector<int> cl_atoms_sparse;
+    if ((rc = d2h(b, H->xyzr, b->c_xyzr, 4 * (size_t)NS)) || (rc = d2h(b, H->bary, b->c_bary, 3 * (size_t)NS)) ||
+        (rc = d2h(b, H->neigh, b->c_neigh, 4 * (size_t)NS)) || (rc = d2h(b, H->type, b->c_type, (size_t)NS)) ||
+        (rc = d2h(b, H->cluster, b->c_cluster, (size_t)NS)) || (rc = d2h(b, H->cl_sph, b->c_cl_sph, (size_t)NS)) ||
+        (rc = d2h(b, H->cl_off, b->c_cl_off, (size_t)(NC + n))) || (rc = d2h(b, H->desc, b->Pk.desc, (size_t)NC)) ||
+        (rc = d2h(b, cl_atoms_sparse, b->Pk.cl_atoms, 4 * (size_t)NS)) || (rc = d2h(b, H->rank, b->Pk.rank_to_cluster, (size_t)(NS + n))) ||
+        (rc = d2h(b, H->atom_fx, b->Pk.atom_fx, 4 * (size_t)b->tot_atoms))) { delete H; return rc; }
+    if (b->B.tets_out) {
+        H->tets.resize(4 * (size_t)b->tot_tets + 4);
+        size_t o = 0;
+        for (int k = 0; k < n; k++) {
+            int nt = b->h_counts[(size_t)k * CNT_STRIDE + CNT_TETS];
+            if (nt > b->S[k].tet_cap) nt = b->S[k].tet_cap;
+            if (nt) CK(cudaMemcpy(&H->tets[o], b->B.tets_out + 4 * (size_t)b->S[k].tet_off, sizeof(int) * 4 * nt, cudaMemcpyDeviceToHost));
+            // canonical order: lexicographic (each tet is already ascending)
+            struct T4 { int v[4]; };
+            T4 *t = reinterpret_cast<T4 *>(&H->tets[o]);
+            std::sort(t, t + nt, [](const T4 &x, const T4 &y) { return std::lexicographical_compare(x.v, x.v + 4, y.v, y.v + 4); });
+            o += 4 * (size_t)nt;
+            b->d2h += (long long)sizeof(int) * 4 * nt;
+        }
+    }
+    // compact the per-cluster atom lists (device layout: 4 slots per sphere of the cluster, first n_atoms used)
+    H->cl_atom_off.resize((size_t)(NC + n));
+    H->cl_atoms.reserve((size_t)NS);
+    size_t tetpos = 0;
+    for (int k = 0; k < n; k++) {
+        const int *c = &b->h_counts[(size_t)k * CNT_STRIDE];
+        fpk_result &r = out[k];
+        memset(&r, 0, sizeof r);
+        r.status = c[CNT_STATUS];
+        r.n_sites = b->S[k].nsites;
+        r.n_tets = c[CNT_TETS];
+        const int s0 = b->h_sbase[k], ns = b->h_sbase[k + 1] - s0, c0 = b->h_clbase[k], nc = b->h_clbase[k + 1] - c0;
+        r.n_spheres = ns; r.n_clusters = nc; r.n_pockets = c[CNT_POCKETS];
+        if (b->B.tets_out) { r.tets = &H->tets[tetpos]; tetpos += 4 * (size_t)std::min(r.n_tets, b->S[k].tet_cap); }
+        r.sph_xyzr = H->xyzr.data() + 4 * (size_t)s0; r.sph_bary = H->bary.data() + 3 * (size_t)s0;
+        r.sph_neigh = H->neigh.data() + 4 * (size_t)s0; r.sph_type = H->type.data() + s0; r.sph_cluster = H->cluster.data() + s0;
+        r.cl_off = H->cl_off.data() + c0 + k; r.cl_sph = H->cl_sph.data() + s0;
+        r.desc = H->desc.data() + c0;
+        r.rank_to_cluster = H->rank.data() + s0 + k;
+        r.atom_fx = H->atom_fx.data() + 4 * (size_t)b->S[k].atom_off;
+        int *ao = H->cl_atom_off.data() + c0 + k;
+        size_t abase = H->cl_atoms.size();
+        ao[0] = 0;
+        for (int q = 0; q < nc; q++) {
+            const int *src = &cl_atoms_sparse[4 * ((size_t)s0 + r.cl_off[q])];
+            int na = r.desc[q].n_atoms;
+            H->cl_atoms.insert(H->cl_atoms.end(), src, src + na);
+            ao[q + 1] = ao[q] + na;
+        }
+        r.cl_atom_off = ao;
+        r.cl_atoms = reinterpret_cast<int32_t *>(abase);     // fixed up below (vector may reallocate)
+        r._owner = H;
+        H->refs++;
+    }
+    for (int k = 0; k < n; k++) out[k].cl_atoms = H->cl_atoms.data() + reinterpret_cast<size_t>(out[k].cl_atoms);
+    if (H->refs == 0) delete H;
+    return FPK_OK;
+}
+
+extern "C" void fpk_result_free(fpk_result *r)
+{
+    if (!r || !r->_owner) return;
+    HostResults *H = static_cast<HostResults *>(r->_owner);
+    memset(r, 0, sizeof *r);
+    if (--H->refs == 0) delete H;
+}
+
+extern "C" fpk_batch *fpk_batch_create(const fpk_structure *in, int n, const fpk_params *p)
+{
+    if (ensure_init()) return nullptr;
+    if (!in || n <= 0 || !p) { fail(FPK_ERR_BAD_ARG, "fpk_batch_create: bad arguments"); return nullptr; }
+    fpk_batch *b = new fpk_batch();
+    if (batch_pack(b, in, n, p, 0.0) || batch_upload(b, in)) { delete b; return nullptr; }
+    return b;
+}
+extern "C" int fpk_batch_run(fpk_batch *b) { return b ? batch_run(b) : fail(FPK_ERR_BAD_ARG, "null batch"); }
+extern "C" int fpk_batch_fetch(fpk_batch *b, fpk_result *out) { return (b && out) ? batch_fetch(b, out) : fail(FPK_ERR_BAD_ARG, "null argument"); }
+extern "C" float fpk_batch_last_kernel_ms(const fpk_batch *b, int which) { return (b && which >= 0 && which < 8) ? b->ms[which] : -1.0f; }
+extern "C" long long fpk_batch_counter(const fpk_batch *b, int which)
+{
+    if (!b) return -1;
+    switch (which) {
+    case 0: return b->tot_sites;
+    case 1: return b->tot_tets;
+    case 2: return b->tot_spheres;
+    case 3: return b->tot_clusters;
+    case 4: { long long p = 0; for (int k = 0; k < b->n; k++) p += b->h_counts.empty() ? 0 : b->h_counts[(size_t)k * CNT_STRIDE + CNT_POCKETS]; return p; }
+    case 5: return b->launches;
+    case 6: return b->h2d;
+    case 7: return b->d2h;
+    case 8: { long long p = 0; for (int k = 0; k < b->n; k++) p += b->h_counts.empty() ? 0 : b->h_counts[(size_t)k * CNT_STRIDE + CNT_SUBROUNDS]; return p; }
+    case 9: { long long p = 0; for (int k = 0; k < b->n; k++) p += b->h_counts.empty() ? 0 : b->h_counts[(size_t)k * CNT_STRIDE + CNT_RETRIES]; return p; }
+    }
+    return -1;
+}
+extern "C" void fpk_batch_destroy(fpk_batch *b) { delete b; }
+
+extern "C" int fpk_detect_batch(const fpk_structure *in, int n, const fpk_params *p, fpk_result *out)
+{
+    if (!out) return fail(FPK_ERR_BAD_ARG, "null result array");
+    fpk_batch *b = fpk_batch_create(in, n, p);
+    if (!b) return FPK_ERR_BAD_ARG;
+    int rc = batch_run(b);
+    if (!rc) rc = batch_fetch(b, out);
+    // a structure whose sphere buffer overflowed is re-run alone with the worst-case capacity (7 tets per atom)
+    if (!rc) {
+        for (int k = 0; k < n; k++) {
+            if (out[k].status != FPK_ERR_CAPACITY) continue;
+            fpk_batch *b2 = new fpk_batch();
+            fpk_result r2;
+            if (!batch_pack(b2, in + k, 1, p, 7.5) && !batch_upload(b2, in + k) && !batch_run(b2) && !batch_fetch(b2, &r2)) {
+                fpk_result_free(&out[k]);
+                out[k] = r2;
+            }
+            delete b2;
+        }
+    }
+    delete b;
+    return rc;
+}
+
+extern "C" int fpk_detect(const fpk_structure *in, const fpk_params *p, fpk_result *out)
+{
+    int rc = fpk_detect_batch(in, 1, p, out);
+    return rc ? rc : out->status;
+}
+
+// =================================================== mdpocket =======================================================
+struct fpk_md {
+    fpk_batch *b = nullptr;            // re-used for every chunk of frames (geometry of the buffers is fixed)
+    fpk_structure topo;
+    std::vector<float> tx, ty, tz, trad, ten, tbf; std::vector<int> tid_, tres; std::vector<int8_t> taa; std::vector<uint8_t> tfl;
+    fpk_params prm;
+    int use_drug = 0;
+    int chunk = 0;
+    bool have_grid = false;
+    float origin[3]; int dims[3];
+    float *d_dens = nullptr, *d_freq = nullptr; unsigned *d_mask = nullptr; unsigned long long *d_nscat = nullptr;
+    float *d_geom = nullptr;
+    int nwords = 0, nblocks = 0;
+    long long frames = 0, launches = 0;
+    std::vector<float> stage;
+    ~fpk_md() { delete b; cudaFree(d_dens); cudaFree(d_freq); cudaFree(d_mask); cudaFree(d_nscat); cudaFree(d_geom); }
+};
+
+static int md_prepare(fpk_md *m, int nframes)
+{
+    // (re)build the batch skeleton for `nframes` frames: properties uploaded once, coordinates per push
+    if (m->b && m->b->n == nframes) return FPK_OK;
+    delete m->b;
+    m->b = new fpk_batch();
+    fpk_batch *b = m->b;
+    const fpk_structure &t = m->topo;
+    std::vector<fpk_structure> fr(nframes, t);
+    int rc = batch_pack(b, fr.data(), nframes, &m->prm, 0.0);
+    if (rc) return rc;
+    // all frames share one copy of the properties and of the site map
+    for (int k = 0; k < nframes; k++) { b->S[k].prop_off = 0; b->S[k].site_off = 0; b->S[k].w_off = 0; b->S[k].natoms_w = 0; b->S[k].same_pdb = 1; }
+    b->tot_w = 0; b->tot_sites = b->S[0].nsites;
+    rc = batch_upload(b, nullptr);
+    if (rc) return rc;
+    BatchDev &B = b->B;
+    const size_t na = (size_t)t.natoms;
+    CK(cudaMemcpy(const_cast<float *>(B.arad), t.radius, sizeof(float) * na, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(const_cast<float *>(B.aen), t.electroneg, sizeof(float) * na, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(const_cast<float *>(B.abf), t.bfactor, sizeof(float) * na, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(const_cast<int *>(B.aid), t.atom_id, sizeof(int) * na, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(const_cast<int *>(B.ares), t.res_id, sizeof(int) * na, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(const_cast<int8_t *>(B.aaa), t.aa_idx, na, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(const_cast<uint8_t *>(B.afl), t.flags, na, cudaMemcpyHostToDevice));
+    std::vector<int> s2a;
+    for (int i = 0; i < t.natoms; i++) if (!(t.flags[i] & FPK_ATOM_H)) s2a.push_back(i);
+    CK(cudaMemcpy(const_cast<int *>(B.site2atom), s2a.data(), sizeof(int) * s2a.size(), cudaMemcpyHostToDevice));
+    b->h2d += (long long)(na * 22 + s2a.size() * 4);
+    return FPK_OK;
+}
+
+static int md_upload_coords(fpk_md *m, const float *xyz, int nframes)
+{
+    // xyz is [frame][atom][3] (the molfile timestep layout, mdpocket.c:238-243): de-interleave into the SoA the kernels read
+    fpk_batch *b = m->b;
+    const size_t na = (size_t)m->topo.natoms, tot = na * nframes;
+    m->stage.resize(3 * tot);
+    float *hx = m->stage.data(), *hy = hx + tot, *hz = hy + tot;
+    for (size_t i = 0; i < tot; i++) { hx[i] = xyz[3 * i]; hy[i] = xyz[3 * i + 1]; hz[i] = xyz[3 * i + 2]; }
+    CK(cudaMemcpy(const_cast<float *>(b->B.ax), hx, sizeof(float) * tot, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(const_cast<float *>(b->B.ay), hy, sizeof(float) * tot, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(const_cast<float *>(b->B.az), hz, sizeof(float) * tot, cudaMemcpyHostToDevice));
+    b->h2d += (long long)(sizeof(float) * 3 * tot);
+    return FPK_OK;
+}
+
+extern "C" fpk_md *fpk_md_begin(const fpk_structure *topo, const fpk_params *p, int use_drug_score)
+{
+    if (ensure_init()) return nullptr;
+    if (!topo || !p || topo->natoms <= 0) { fail(FPK_ERR_BAD_ARG, "fpk_md_begin: bad arguments"); return nullptr; }
+    fpk_md *m = new fpk_md();
+    const int na = topo->natoms;
+    // own copies of the topology (the caller's arrays need not outlive this call)
+    m->tx.assign(na, 0.f); m->ty.assign(na, 0.f); m->tz.assign(na, 0.f);
+    m->trad.assign(topo->radius, topo->radius + na); m->ten.assign(topo->electroneg, topo->electroneg + na);
+    m->tbf.assign(topo->bfactor, topo->bfactor + na); m->tid_.assign(topo->atom_id, topo->atom_id + na);
+    m->tres.assign(topo->res_id, topo->res_id + na); m->taa.assign(topo->aa_idx, topo->aa_idx + na);
+    m->tfl.assign(topo->flags, topo->flags + na);
+    m->topo = *topo;
+    m->topo.x = m->tx.data(); m->topo.y = m->ty.data(); m->topo.z = m->tz.data(); m->topo.radius = m->trad.data();
+    m->topo.electroneg = m->ten.data(); m->topo.bfactor = m->tbf.data(); m->topo.atom_id = m->tid_.data();
+    m->topo.res_id = m->tres.data(); m->topo.aa_idx = m->taa.data(); m->topo.flags = m->tfl.data();
+    m->topo.natoms_w = 0; m->topo.same_pdb = 1; m->topo.n_xlig = 0; m->topo.xlig = nullptr;     // mdpocket.c:844 search_pocket(pdb, params, pdb)
+    m->prm = *p;
+    m->prm.do_asa_and_volume = 0;          // mdpocket.c:89
+    m->prm.want_tets = 0;
+    m->use_drug = use_drug_score;
+    return m;
+}
+
+extern "C" int fpk_md_set_grid(fpk_md *m, const float origin[3], const int dims[3])
+{
+    if (!m || !origin || !dims || dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return fail(FPK_ERR_BAD_ARG, "fpk_md_set_grid: bad arguments");
+    for (int q = 0; q < 3; q++) { m->origin[q] = origin[q]; m->dims[q] = dims[q]; }
+    size_t ncell = (size_t)dims[0] * dims[1] * dims[2];
+    cudaFree(m->d_dens); cudaFree(m->d_freq); cudaFree(m->d_mask); cudaFree(m->d_nscat);
+    m->nwords = (int)((ncell + 31) / 32);
+    m->nblocks = g_sms * 2;
+    CK(cudaMalloc(&m->d_dens, sizeof(float) * ncell)); CK(cudaMalloc(&m->d_freq, sizeof(float) * ncell));
+    CK(cudaMalloc(&m->d_mask, sizeof(unsigned) * (size_t)m->nwords * m->nblocks)); CK(cudaMalloc(&m->d_nscat, 8));
+    CK(cudaMemset(m->d_dens, 0, sizeof(float) * ncell)); CK(cudaMemset(m->d_freq, 0, sizeof(float) * ncell)); CK(cudaMemset(m->d_nscat, 0, 8));
+    m->have_grid = true;
+    return FPK_OK;
+}
+
+extern "C" int fpk_md_grid_from_frame(fpk_md *m, const float *xyz, float origin[3], int dims[3])
+{
+    if (!m || !xyz) return fail(FPK_ERR_BAD_ARG, "fpk_md_grid_from_frame: bad arguments");
+    int rc = md_prepare(m, 1);
+    if (!rc) rc = md_upload_coords(m, xyz, 1);
+    if (!rc) rc = batch_run(m->b);
+    if (rc) return rc;
+    m->launches += m->b->launches;
+    if (!m->d_geom) CK(cudaMalloc(&m->d_geom, sizeof(float) * 8));
+    k_md_geometry<<<1, 32>>>(m->b->B, 0, m->d_geom);
+    m->launches++;
+    float g[6];
+    CK(cudaMemcpy(g, m->d_geom, sizeof g, cudaMemcpyDeviceToHost));
+    for (int q = 0; q < 3; q++) { origin[q] = g[q]; dims[q] = (int)g[3 + q]; }
+    return FPK_OK;
+}
+
+extern "C" int fpk_md_push_frames(fpk_md *m, const float *xyz, int nframes)
+{
+    if (!m || !xyz || nframes <= 0) return fail(FPK_ERR_BAD_ARG, "fpk_md_push_frames: bad arguments");
+    if (!m->have_grid) return fail(FPK_ERR_BAD_ARG, "fpk_md_push_frames: set the grid first (fpk_md_set_grid)");
+    const size_t na = (size_t)m->topo.natoms;
+    const int chunk_max = 1024;
+    for (int f0 = 0; f0 < nframes; f0 += chunk_max) {
+        const int nf = std::min(chunk_max, nframes - f0);
+        int rc = md_prepare(m, nf);
+        if (!rc) rc = md_upload_coords(m, xyz + 3 * na * (size_t)f0, nf);
+        if (!rc) rc = batch_run(m->b);
+        if (rc) return rc;
+        MdGrid G;
+        for (int q = 0; q < 3; q++) G.origin[q] = m->origin[q];
+        G.nx = m->dims[0]; G.ny = m->dims[1]; G.nz = m->dims[2];
+        G.dens = m->d_dens; G.freq = m->d_freq; G.mask = m->d_mask; G.nwords = m->nwords; G.use_drug_score = m->use_drug;
+        k_md_scatter<<<std::min(m->nblocks, nf), 256>>>(m->b->B, m->b->Pk, G, m->d_nscat);
+        CK(cudaDeviceSynchronize());
+        m->launches += m->b->launches + 1;
+        m->frames += nf;
+    }
+    return FPK_OK;
+}
+
+extern "C" int fpk_md_device_grids(fpk_md *m, void **dens, void **freq, size_t *ncell)
+{
+    if (!m || !m->have_grid) return fail(FPK_ERR_BAD_ARG, "no grid");
+    if (dens) *dens = m->d_dens;
+    if (freq) *freq = m->d_freq;
+    if (ncell) *ncell = (size_t)m->dims[0] * m->dims[1] * m->dims[2];
+    return FPK_OK;
+}
+extern "C" int fpk_md_fetch_grids(fpk_md *m, float *dens, float *freq)
+{
+    if (!m || !m->have_grid) return fail(FPK_ERR_BAD_ARG, "no grid");
+    size_t ncell = (size_t)m->dims[0] * m->dims[1] * m->dims[2];
+    if (dens) CK(cudaMemcpy(dens, m->d_dens, sizeof(float) * ncell, cudaMemcpyDeviceToHost));
+    if (freq) CK(cudaMemcpy(freq, m->d_freq, sizeof(float) * ncell, cudaMemcpyDeviceToHost));
+    return FPK_OK;
+}
+extern "C" long long fpk_md_counter(const fpk_md *m, int which)
+{
+    if (!m) return -1;
+    if (which == 0) return m->frames;
+    if (which == 2) return m->launches;
+    if (which == 1 && m->d_nscat) { unsigned long long v = 0; cudaMemcpy(&v, m->d_nscat, 8, cudaMemcpyDeviceToHost); return (long long)v; }
+    return 0;
+}
+extern "C" void fpk_md_end(fpk_md *m) { delete m; }

@@ -1,0 +1,335 @@
+// K1: one thread block per structure (persistent blocks pulling structures from a queue):
+//   sites -> exact Delaunay triangulation (delaunay.cuh) -> fused alpha-sphere filter + typing -> canonical order.
+// The tetrahedra never leave the block's scratch (L2 resident); HBM sees atoms in and kept spheres out.
+//
+// Replaces reference src/voronoi.c:69-185 load_vvertices (text to qhull and back), :369-521 fill_vvertices,
+// :969-1087 testVvertice and :892-916 set_barycenter.
+#pragma once
+#include "common.cuh"
+#include "delaunay.cuh"
+
+namespace fpk {
+
+struct DelScratch {
+    double *P;                    // [3*nmax]
+    unsigned long long *keys;     // [npad]
+    int *order;                   // [nmax]
+    int *tv, *tn, *own, *rim, *mark, *cavpos, *free0, *free1;
+    int cap;
+    int *hint;                    // [32^3]
+    int *cav, *newid, *tinfo, *cursor;
+    int *bigcav, *bignewid;
+    int *cnt;                     // [C_COUNT]
+    int *rstart;                  // [32]
+    int4 *rawkey;                 // [scap]
+    float4 *rawxyzr;              // [scap]
+    int *sitecnt;                 // [nmax + 1]
+    int *bucket;                  // [scap]
+    int scap;
+};
+
+// qhull geom2.c:2012-2093 qh_voronoi_center (Cramer relative to the first point, f64), same operation order as the oracle
+__device__ __forceinline__ double det3d(const double *r0, const double *r1, const double *r2)
+{
+    return r0[0] * (r1[1] * r2[2] - r1[2] * r2[1]) - r1[0] * (r0[1] * r2[2] - r0[2] * r2[1]) +
+           r2[0] * (r0[1] * r1[2] - r0[2] * r1[1]);
+}
+__device__ __forceinline__ void circumcentre(const double *p0, const double *p1, const double *p2, const double *p3, double c[3])
+{
+    double m[3][3], s2[3];
+    const double *p[3] = {p1, p2, p3};
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) m[k][j] = p[j][k] - p0[k];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) s += m[k][j] * m[k][j];
+        s2[j] = s;
+    }
+    double det = det3d(m[0], m[1], m[2]);
+    double factor = 0.5 / det;
+    c[0] = det3d(s2, m[1], m[2]) * factor + p0[0];
+    c[1] = det3d(m[0], s2, m[2]) * factor + p0[1];
+    c[2] = det3d(m[0], m[1], s2) * factor + p0[2];
+}
+
+// voronoi.c:969-1087 testVvertice; ac[4] / ap[4] = indices of the 4 atoms into the packed coordinate / property arrays,
+// in the tet's vertex order
+__device__ float test_vvertice(const BatchDev &B, const StructDev &S, const float xyz[3], const int ac[4], const int ap[4])
+{
+    const fpk_params &p = B.prm;
+    float min_asph_size = p.asph_min_size, max_asph_size = p.asph_max_size;
+    float x = xyz[0] - 0.0f, y = xyz[1] - 0.0f, z = xyz[2] - 0.0f;
+    float baryx = 0.0f, baryy = 0.0f, baryz = 0.0f, barybf = 0.0f, sdbf = 0.0f;
+    if (p.xpocket_active) {
+        int ok = 0;
+        for (int k = 0; k < 4; k++)
+            if (B.afl[ap[k]] & FPK_ATOM_XPOCKET) ok++;
+        if (ok < p.min_n_explicit_pocket_atoms) return -3.0f;
+    }
+    int c = ac[0];
+    baryx += B.ax[c]; baryy += B.ay[c]; baryz += B.az[c]; barybf += B.abf[ap[0]];
+    float d1 = f_dist(x, y, z, B.ax[c], B.ay[c], B.az[c]), d2, d3, d4;
+    if ((double)min_asph_size <= (double)d1 + 1e-3 && (double)d1 - 1e-3 <= (double)max_asph_size) {
+        c = ac[1]; d2 = f_dist(x, y, z, B.ax[c], B.ay[c], B.az[c]);
+        baryx += B.ax[c]; baryy += B.ay[c]; baryz += B.az[c]; barybf += B.abf[ap[1]];
+        c = ac[2]; d3 = f_dist(x, y, z, B.ax[c], B.ay[c], B.az[c]);
+        baryx += B.ax[c]; baryy += B.ay[c]; baryz += B.az[c]; barybf += B.abf[ap[2]];
+        c = ac[3]; d4 = f_dist(x, y, z, B.ax[c], B.ay[c], B.az[c]);
+        baryx += B.ax[c]; baryy += B.ay[c]; baryz += B.az[c]; barybf += B.abf[ap[3]];
+        baryx = (float)((double)baryx * 0.25); baryy = (float)((double)baryy * 0.25);
+        baryz = (float)((double)baryz * 0.25); barybf = (float)((double)barybf * 0.25);
+        if (fabs((double)(d1 - d2)) < 1e-3 && fabs((double)(d1 - d3)) < 1e-3 && fabs((double)(d1 - d4)) < 1e-3) {
+            if (S.n_xlig) {
+                const float *xl = B.xlig + 3 * (size_t)S.xlig_off;
+                for (int i = 0; i < S.n_xlig; i++)
+                    if (f_dist(xl[3 * i], xl[3 * i + 1], xl[3 * i + 2], x, y, z) <= d1) return d1;
+                return -1.0f;
+            }
+            for (int k = 0; k < 4; k++) {
+                float b = B.abf[ap[k]];
+                sdbf += (b - barybf) * (b - barybf);
+            }
+            sdbf = (float)sqrt((double)(sdbf / 3));
+            if (((sdbf > S.avg_b) || (sdbf > ((S.max_b - S.min_b) / 4))) &&
+                (((double)S.avg_b > 0.0) && ((double)(barybf / S.avg_b) > 1.4)))
+                return -1.0f;
+            if ((double)f_dist(baryx, baryy, baryz, xyz[0], xyz[1], xyz[2]) > 1.0 && (double)d1 > ((double)max_asph_size - 1.5))
+                return -2.0f;
+            return d1;
+        }
+    }
+    return -3.0f;
+}
+
+__device__ __forceinline__ bool key_less(const int4 &a, const int4 &b)
+{
+    if (a.x != b.x) return a.x < b.x;
+    if (a.y != b.y) return a.y < b.y;
+    if (a.z != b.z) return a.z < b.z;
+    return a.w < b.w;
+}
+
+
+// bounding box of X.P[0..3n) by the whole block -> s_box[0..2]=min, [3..5]=max (s_box, s_bmin, s_bmax in shared memory)
+__device__ void block_bbox(const double *P, int n, double *s_box, double (*s_bmin)[3], double (*s_bmax)[3])
+{
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for (int i = tid; i < n; i += nt)
+        for (int c = 0; c < 3; c++) { double v = P[3 * (size_t)i + c]; mn[c] = fmin(mn[c], v); mx[c] = fmax(mx[c], v); }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            mn[c] = fmin(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], d));
+            mx[c] = fmax(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], d));
+        }
+    if (lane == 0) for (int c = 0; c < 3; c++) { s_bmin[wid][c] = mn[c]; s_bmax[wid][c] = mx[c]; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < ((nt + 31) >> 5); w++)
+            for (int c = 0; c < 3; c++) { mn[c] = fmin(mn[c], s_bmin[w][c]); mx[c] = fmax(mx[c], s_bmax[w][c]); }
+        for (int c = 0; c < 3; c++) { s_box[c] = mn[c]; s_box[3 + c] = mx[c]; }
+    }
+    __syncthreads();
+}
+
+// Delaunay triangulation of the n lattice points in X.P by the whole block. C = context in shared memory.
+// Returns 0 or a DERR_* code (uniform over the block). On return the mesh is in X.tv/X.tn, C.cnt[C_NTET] slots.
+__device__ int block_delaunay(DelaunayCtx &C, const DelScratch &X, int n, const double *s_box, int *s_first4)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double bmn[3] = {s_box[0], s_box[1], s_box[2]};
+    const double ext = fmax(1.0, fmax(s_box[3] - s_box[0], fmax(s_box[4] - s_box[1], s_box[5] - s_box[2])));
+    const int R = brio_nrounds(n);
+    int npad = 1;
+    while (npad < n) npad <<= 1;
+    for (int i = tid; i < npad; i += nt)
+        X.keys[i] = i < n ? brio_key(i, X.P + 3 * (size_t)i, bmn, 1023.999 / ext, R) : ~0ull;
+    __syncthreads();
+    block_bitonic_sort(X.keys, npad);
+    if (tid <= R) X.rstart[tid] = n;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+        unsigned long long key = X.keys[i];
+        X.order[i] = (int)(key & 0xffffffull);
+        int r = (int)(key >> 54);
+        if (i == 0 || (int)(X.keys[i - 1] >> 54) != r) X.rstart[r] = i;
+    }
+    int hgc = 2;
+    while (hgc < 32 && hgc * hgc * hgc * 2 < n) hgc++;
+    for (int i = tid; i < hgc * hgc * hgc; i += nt) X.hint[i] = -1;
+    X.tinfo[4 * tid] = -1;
+    __syncthreads();
+    if (tid == 0) {
+        for (int r = R - 1; r >= 0; r--) if (X.rstart[r] > X.rstart[r + 1]) X.rstart[r] = X.rstart[r + 1];
+        X.rstart[0] = 0;
+        C.n = n; C.P = X.P; C.tv = X.tv; C.tn = X.tn; C.own = X.own; C.rim = X.rim; C.mark = X.mark; C.cavpos = X.cavpos;
+        C.cap = X.cap; C.cnt = X.cnt; C.freest[0] = X.free0; C.freest[1] = X.free1; C.order = X.order;
+        C.hint = X.hint;
+        C.hg = hgc; C.hinv = hgc / (ext * 1.0001);
+        C.hmin[0] = bmn[0]; C.hmin[1] = bmn[1]; C.hmin[2] = bmn[2];
+        C.nthreads = nt; C.cav = X.cav; C.newid = X.newid; C.tinfo = X.tinfo; C.cursor = X.cursor;
+        C.bigcav = X.bigcav; C.bignewid = X.bignewid;
+        delaunay_init(C, s_first4);
+    }
+    __syncthreads();
+    bool failed = C.cnt[C_STATUS] != 0;
+    for (int r = 0; r < R && !failed; r++) {
+        round_chunk(X.rstart[r], X.rstart[r + 1], tid, nt, &X.cursor[2 * tid], &X.cursor[2 * tid + 1]);
+        for (;;) {
+            int work = phase_assign(C, tid) ? 1 : 0;
+            if (C.cnt[C_STATUS]) work = 0;
+            if (!__syncthreads_or(work)) break;
+            phase_claim(C, tid);
+            __syncthreads();
+            phase_verify(C, tid);
+            __syncthreads();
+            phase_reset(C, tid);
+            __syncthreads();
+            phase_commit(C, tid);
+            __syncthreads();
+            if (tid == 0) phase_serial(C);
+            __syncthreads();
+        }
+        failed = C.cnt[C_STATUS] != 0;
+    }
+    __syncthreads();
+    return C.cnt[C_STATUS];
+}
+
+#ifndef FPK_K1_MINBLOCKS
+#define FPK_K1_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(256, FPK_K1_MINBLOCKS) k_delaunay_filter(BatchDev B, const DelScratch *scratch)
+{
+    __shared__ DelaunayCtx C;
+    __shared__ int s_k, s_first4[4], s_red[40];
+    __shared__ double s_box[6];
+    __shared__ double s_bmin[8][3], s_bmax[8][3];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const DelScratch &X = scratch[blockIdx.x];
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_k = atomicAdd(B.work_counter, 1);
+        __syncthreads();
+        if (s_k >= B.nstruct) return;
+        const int k = B.work_order[s_k];
+        const StructDev S = B.S[k];
+        const int n = S.nsites;
+        int *counts = B.counts + (size_t)k * CNT_STRIDE;
+        if (n < 4) {
+            if (tid == 0) { counts[CNT_TETS] = 0; counts[CNT_SPHERES] = 0; counts[CNT_STATUS] = FPK_ERR_DEGENERATE; }
+            continue;
+        }
+        // ---- 1. lattice coordinates: what "%.6f" prints (voronoi.c:130), exact in double -----------------------
+        for (int i = tid; i < n; i += nt) {
+            int a = S.atom_off + B.site2atom[S.site_off + i];
+            X.P[3 * (size_t)i] = (double)__double2ll_rn(__dmul_rn((double)B.ax[a], 1e6));
+            X.P[3 * (size_t)i + 1] = (double)__double2ll_rn(__dmul_rn((double)B.ay[a], 1e6));
+            X.P[3 * (size_t)i + 2] = (double)__double2ll_rn(__dmul_rn((double)B.az[a], 1e6));
+        }
+        __syncthreads();
+        block_bbox(X.P, n, s_box, s_bmin, s_bmax);
+        // ---- 2.+3. insertion order, rounds of concurrent insertions --------------------------------------------------
+        const int err = block_delaunay(C, X, n, s_box, s_first4);
+        if (err) {
+            if (tid == 0) {
+                counts[CNT_TETS] = 0; counts[CNT_SPHERES] = 0;
+                counts[CNT_STATUS] = err == DERR_DEGENERATE ? FPK_ERR_DEGENERATE : FPK_ERR_CAPACITY;
+            }
+            continue;
+        }
+        // ---- 4. fused filter over the finite tets (circumcentre f64 -> f32, testVvertice) ----------------------------
+        const int ntet = C.cnt[C_NTET];
+        if (tid == 0) { s_red[0] = 0; s_red[1] = 0; }     // kept spheres, finite tets
+        for (int i = tid; i <= n; i += nt) X.sitecnt[i] = 0;
+        __syncthreads();
+        for (int t = tid; t < ntet; t += nt) {
+            int4 q = reinterpret_cast<const int4 *>(X.tv)[t];
+            if (q.x < 0 || q.y < 0 || q.z < 0 || q.w < 0) continue;
+            int v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 1; i < 4; i++) { int kk = v[i], j = i - 1; while (j >= 0 && v[j] > kk) { v[j + 1] = v[j]; j--; } v[j + 1] = kk; }
+            int ord = atomicAdd(&s_red[1], 1);
+            if (B.tets_out && ord < S.tet_cap)
+                reinterpret_cast<int4 *>(B.tets_out)[S.tet_off + ord] = make_int4(v[0], v[1], v[2], v[3]);
+            double p[4][3];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) p[i][c] = __ddiv_rn(X.P[3 * (size_t)v[i] + c], 1e6);   // strtod of the "%.6f" text
+            double cc[3];
+            circumcentre(p[0], p[1], p[2], p[3], cc);
+            float xyz[3] = {(float)cc[0], (float)cc[1], (float)cc[2]};
+            int ac[4], ap[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { int la = B.site2atom[S.site_off + v[i]]; ac[i] = S.atom_off + la; ap[i] = S.prop_off + la; }
+            float rad = test_vvertice(B, S, xyz, ac, ap);
+            if (rad > 0) {
+                int pos = atomicAdd(&s_red[0], 1);
+                if (pos < X.scap && pos < S.sph_cap) {
+                    X.rawkey[pos] = make_int4(v[0], v[1], v[2], v[3]);
+                    X.rawxyzr[pos] = make_float4(xyz[0], xyz[1], xyz[2], rad);
+                    atomicAdd(&X.sitecnt[v[0]], 1);
+                }
+            }
+        }
+        __syncthreads();
+        const int ns = s_red[0];
+        if (tid == 0) {
+            counts[CNT_TETS] = s_red[1];
+            counts[CNT_SUBROUNDS] = C.cnt[C_NSUB]; counts[CNT_RETRIES] = C.cnt[C_NRETRY]; counts[CNT_NBIG] = C.cnt[C_NBIG];
+        }
+        if (ns > S.sph_cap || ns > X.scap) {
+            if (tid == 0) { counts[CNT_SPHERES] = ns; counts[CNT_STATUS] = FPK_ERR_CAPACITY; }
+            continue;
+        }
+        // ---- 5. canonical order: ascending (a,b,c,d) of the sorted site tuple. Bucket by a, rank inside the bucket -----
+        block_exclusive_scan(X.sitecnt, n + 1, s_red + 2);
+        // sitecnt[a] = start of bucket a; reuse order[] (no longer needed) as the per-bucket fill cursor
+        for (int i = tid; i < n; i += nt) X.order[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < ns; i += nt) {
+            int a0 = X.rawkey[i].x;
+            int slot = atomicAdd(&X.order[a0], 1);
+            X.bucket[X.sitecnt[a0] + slot] = i;
+        }
+        __syncthreads();
+        for (int i = tid; i < ns; i += nt) {
+            int4 key = X.rawkey[i];
+            int b0 = X.sitecnt[key.x], b1 = X.sitecnt[key.x + 1], rank = 0;
+            for (int j = b0; j < b1; j++) {
+                int o = X.bucket[j];
+                if (o != i && key_less(X.rawkey[o], key)) rank++;
+            }
+            const int dst = S.sph_off + b0 + rank;
+            float4 xr = X.rawxyzr[i];
+            const int a[4] = {B.site2atom[S.site_off + key.x], B.site2atom[S.site_off + key.y],
+                              B.site2atom[S.site_off + key.z], B.site2atom[S.site_off + key.w]};
+            // typing (voronoi.c:467-495) and barycentre of the 4 contacted atoms (voronoi.c:892-916)
+            int apol = 0;
+            float xs = 0.0f, ys = 0.0f, zs = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if ((double)B.aen[S.prop_off + a[j]] < 2.8) apol++;
+                xs += B.ax[S.atom_off + a[j]]; ys += B.ay[S.atom_off + a[j]]; zs += B.az[S.atom_off + a[j]];
+            }
+            B.s_xyzr[dst] = xr;
+            B.s_key[dst] = key;
+            B.s_neigh[dst] = make_int4(a[0], a[1], a[2], a[3]);
+            B.s_type[dst] = (apol >= B.prm.min_apol_neigh) ? 0 : 1;
+            B.s_bary[3 * (size_t)dst] = (float)((double)xs * 0.25);
+            B.s_bary[3 * (size_t)dst + 1] = (float)((double)ys * 0.25);
+            B.s_bary[3 * (size_t)dst + 2] = (float)((double)zs * 0.25);
+        }
+        if (tid == 0) { counts[CNT_SPHERES] = ns; counts[CNT_STATUS] = FPK_OK; }
+    }
+}
+
+}  // namespace fpk

@@ -1,0 +1,708 @@
+// K3 (clustering), K4 (per-pocket descriptors) and K4c (normalise / score / drop / rank).
+//
+// K3 replaces reference src/clusterlib.c:3886 treecluster('s','e') -> :3514 pslcluster (O(S^2) SLINK),
+//    :3235 cuttree_distance, src/voronoi.c:260 transferClustersToVertices, src/pocket.c:77 assign_pockets,
+//    src/refine.c:58 apply_clustering and :192 reIndexPockets by ONE pass: uniform cell grid ->
+//    lock-free union-find over the  d <= clust_max_dist  graph (the single-linkage cut IS its connected
+//    components) -> numbering by lowest sphere index -> ordered segment fill.
+// K4 replaces src/pocket.c:575 set_pockets_descriptors: :1280 get_pocket_contacted_atms,
+//    src/descriptors.c:158-513, src/asa.c:84-454, src/voronoi.c:1150-1233 (Monte-Carlo volume).
+// K4c replaces src/pocket.c:664 set_normalized_descriptors, src/pscoring.c:241,325,
+//    src/refine.c:114 dropSmallNpolarPockets and src/psorting.c:64 sort_pockets.
+#pragma once
+#include "common.cuh"
+
+namespace fpk {
+
+struct PocketDev {            // cluster-level arrays, sized after K3 (exact number of clusters known)
+    const int *clbase;        // [nstruct + 1] exclusive scan of n_clusters
+    const int *sbase;         // [nstruct + 1] exclusive scan of n_spheres (compact sphere numbering)
+    fpk_desc *desc;           // [clbase[nstruct]]
+    // sphere-level scratch / outputs, region of cluster c of structure k: R = sph_off + cl_off[c]
+    int *cl_atoms;            // [4*R ...) unique contacted atoms (index inside the structure), first-seen order
+    int *ent_u;               // [4*R ...) entry (sphere i, slot j) -> position of its atom in cl_atoms
+    int *touch_off;           // [5*R ...) CSR offsets per unique atom
+    int *touch_list;          // [4*R ...) spheres (local index) touching the atom
+    int *acc;                 // [16*R ...) 4 int accumulators per unique atom: nn14, nn22, napol, npol
+    float *fx_val;            // [16*R ...) per unique atom: prob, a0, dA, flag(abpa)
+    int *fx_who;              // [2*natoms_total] per atom: highest cluster that wrote prob / abpa
+    float *atom_fx;           // [4*natoms_total] result
+    int *rank_to_cluster;     // [sph_off ...) per structure
+    int total_clusters;
+};
+
+struct ClusterScratch {       // per resident block of K3
+    int *cellcnt;             // [CELLMAX + 1]
+    int *cellsph;             // [scap]
+    int *tmp;                 // [scap + 1]
+    int scap;
+};
+enum { CELLMAX = 1 << 18 };
+
+__device__ __forceinline__ int uf_find(int *par, int i)
+{
+    int p = par[i];
+    while (p != i) {
+        int g = par[p];
+        if (g != p) par[i] = g;
+        i = p; p = g;
+    }
+    return i;
+}
+__device__ __forceinline__ void uf_union(int *par, int a, int b)
+{
+    for (;;) {
+        a = uf_find(par, a); b = uf_find(par, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        int old = atomicMin(&par[a], b);          // hook the larger root under the smaller one
+        if (old == a) return;
+        a = old;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_cluster(BatchDev B, const ClusterScratch *scratch, int *work_counter)
+{
+    __shared__ int s_k, s_sm[40], s_dims[4];
+    __shared__ float s_mn[8][3], s_mx[8][3], s_box[7];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const ClusterScratch &X = scratch[blockIdx.x];
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_k = atomicAdd(work_counter, 1);
+        __syncthreads();
+        if (s_k >= B.nstruct) return;
+        const int k = B.work_order[s_k];
+        const StructDev S = B.S[k];
+        int *counts = B.counts + (size_t)k * CNT_STRIDE;
+        if (counts[CNT_STATUS] != FPK_OK) { if (tid == 0) counts[CNT_CLUSTERS] = 0; continue; }
+        const int ns = counts[CNT_SPHERES];
+        const float4 *sx = B.s_xyzr + S.sph_off;
+        int *par = B.s_cluster + S.sph_off;
+        int *cl_off = B.cl_off + S.sph_off + k, *cl_sph = B.cl_sph + S.sph_off;
+        if (!B.prm.skip_clustering && ns < 2) {     // clusterlib.c:3969 -> fpocket.c:135-139
+            if (tid == 0) { counts[CNT_CLUSTERS] = 0; counts[CNT_STATUS] = FPK_ERR_NO_SPHERES; }
+            continue;
+        }
+        if (ns == 0) { if (tid == 0) { counts[CNT_CLUSTERS] = 0; counts[CNT_STATUS] = FPK_ERR_NO_POCKETS; } continue; }
+        if (B.prm.skip_clustering) {                 // explicit pocket: every sphere has the same resid -> one pocket
+            for (int i = tid; i < ns; i += nt) { par[i] = 0; cl_sph[i] = i; }
+            if (tid == 0) { cl_off[0] = 0; cl_off[1] = ns; counts[CNT_CLUSTERS] = 1; }
+            continue;
+        }
+        // ---- bounding box of the centres --------------------------------------------------------------
+        float mn[3] = {3e38f, 3e38f, 3e38f}, mx[3] = {-3e38f, -3e38f, -3e38f};
+        for (int i = tid; i < ns; i += nt) {
+            float4 v = sx[i];
+            mn[0] = fminf(mn[0], v.x); mn[1] = fminf(mn[1], v.y); mn[2] = fminf(mn[2], v.z);
+            mx[0] = fmaxf(mx[0], v.x); mx[1] = fmaxf(mx[1], v.y); mx[2] = fmaxf(mx[2], v.z);
+            par[i] = i;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], d));
+                mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], d));
+            }
+        if (lane == 0) for (int c = 0; c < 3; c++) { s_mn[wid][c] = mn[c]; s_mx[wid][c] = mx[c]; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < (nt >> 5); w++)
+                for (int c = 0; c < 3; c++) { mn[c] = fminf(mn[c], s_mn[w][c]); mx[c] = fmaxf(mx[c], s_mx[w][c]); }
+            float cell = B.prm.clust_max_dist * 1.001f + 1e-4f;      // >= cut, so neighbours are within +-1 cell
+            int d0, d1, d2;
+            for (;;) {
+                d0 = (int)((mx[0] - mn[0]) / cell) + 1; d1 = (int)((mx[1] - mn[1]) / cell) + 1; d2 = (int)((mx[2] - mn[2]) / cell) + 1;
+                if ((long long)d0 * d1 * d2 <= CELLMAX) break;
+                cell *= 1.26f;
+            }
+            s_dims[0] = d0; s_dims[1] = d1; s_dims[2] = d2;
+            s_box[0] = mn[0]; s_box[1] = mn[1]; s_box[2] = mn[2]; s_box[3] = cell;
+        }
+        __syncthreads();
+        const int d0 = s_dims[0], d1 = s_dims[1], d2 = s_dims[2], ncell = d0 * d1 * d2;
+        const float bx = s_box[0], by = s_box[1], bz = s_box[2], cell = s_box[3];
+        for (int i = tid; i <= ncell; i += nt) X.cellcnt[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < ns; i += nt) {
+            float4 v = sx[i];
+            int cx = min(d0 - 1, max(0, (int)((v.x - bx) / cell))), cy = min(d1 - 1, max(0, (int)((v.y - by) / cell))),
+                cz = min(d2 - 1, max(0, (int)((v.z - bz) / cell)));
+            int cid = (cx * d1 + cy) * d2 + cz;
+            X.tmp[i] = cid;
+            atomicAdd(&X.cellcnt[cid], 1);
+        }
+        __syncthreads();
+        block_exclusive_scan(X.cellcnt, ncell + 1, s_sm);
+        // fill (slot order inside a cell is irrelevant); cursor = the upper end walking down
+        for (int i = tid; i < ns; i += nt) {
+            int cid = X.tmp[i];
+            int slot = atomicAdd(&X.cellcnt[cid], 1);       // temporarily advances the start; restored below
+            X.cellsph[slot] = i;
+        }
+        __syncthreads();
+        // cellcnt[c] now holds the END of cell c (= old start of c+1); start of c = end of c-1
+        // ---- union over the  d <= cut  graph (clusterlib.c:933 euclid in f64 on the f32 centres) --------------------------
+        const double cut = (double)B.prm.clust_max_dist;
+        for (int i = tid; i < ns; i += nt) {
+            float4 v = sx[i];
+            int cid = X.tmp[i];
+            int cz = cid % d2, cy = (cid / d2) % d1, cx = cid / (d2 * d1);
+            double xi = (double)v.x, yi = (double)v.y, zi = (double)v.z;
+            for (int ax = max(cx - 1, 0); ax <= min(cx + 1, d0 - 1); ax++)
+                for (int ay = max(cy - 1, 0); ay <= min(cy + 1, d1 - 1); ay++)
+                    for (int az = max(cz - 1, 0); az <= min(cz + 1, d2 - 1); az++) {
+                        int c2 = (ax * d1 + ay) * d2 + az;
+                        int lo = c2 ? X.cellcnt[c2 - 1] : 0, hi = X.cellcnt[c2];
+                        for (int q = lo; q < hi; q++) {
+                            int j = X.cellsph[q];
+                            if (j >= i) continue;
+                            float4 w = sx[j];
+                            double result = 0.;
+                            double term = xi - (double)w.x; result += term * term;
+                            term = yi - (double)w.y; result += term * term;
+                            term = zi - (double)w.z; result += term * term;
+                            result = sqrt(result);
+                            if (!(result > cut)) uf_union(par, i, j);
+                        }
+                    }
+        }
+        __syncthreads();
+        // ---- flatten; number clusters by their lowest sphere (order apply_clustering leaves, refine.c:58-93) ------------------
+        for (int i = tid; i < ns; i += nt) { int r = uf_find(par, i); X.tmp[i] = (r == i) ? 1 : 0; X.cellsph[i] = r; }
+        __syncthreads();
+        if (tid == 0) X.tmp[ns] = 0;
+        __syncthreads();
+        const int nc = block_exclusive_scan(X.tmp, ns + 1, s_sm);
+        for (int i = tid; i < ns; i += nt) par[i] = X.tmp[X.cellsph[i]];     // cluster id of every sphere
+        for (int i = tid; i <= nc; i += nt) cl_off[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < ns; i += nt) atomicAdd(&cl_off[par[i]], 1);
+        __syncthreads();
+        block_exclusive_scan(cl_off, nc + 1, s_sm);
+        for (int i = tid; i < nc; i += nt) X.tmp[i] = 0;                    // per-cluster fill cursor
+        __syncthreads();
+        if (wid == 0) {                                                     // ordered fill: members ascending
+            for (int base = 0; base < ns; base += 32) {
+                int i = base + lane;
+                int c = i < ns ? par[i] : -1 - lane;
+                unsigned m = __match_any_sync(0xffffffffu, c);
+                int r = __popc(m & ((1u << lane) - 1u));
+                if (i < ns) {
+                    int cur = X.tmp[c];
+                    cl_sph[cl_off[c] + cur + r] = i;
+                }
+                __syncwarp();
+                if (i < ns && r == 0) X.tmp[c] += __popc(m);
+                __syncwarp();
+            }
+        }
+        if (tid == 0) counts[CNT_CLUSTERS] = nc;
+    }
+}
+
+// ============================================= K4: descriptors ===============================================================
+// aa.c:60-80 property table: volume score, hydrophobicity, charge, polarity
+__constant__ float c_aa_vol[20] = {2, 7, 3, 3, 3, 4, 4, 1, 4, 5, 5, 6, 5, 6, 3, 2, 3, 8, 7, 4};
+__constant__ float c_aa_hyd[20] = {41, -14, -28, -55, 49, -10, -31, 0, 8, 99, 97, -23, 74, 100, -46, -5, 13, 97, 63, 76};
+__constant__ int c_aa_chg[20] = {0, 1, 0, -1, 0, 0, -1, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0};
+__constant__ int c_aa_pol[20] = {0, 1, 1, 1, 0, 1, 1, 0, 1, 0, 0, 1, 0, 0, 0, 1, 1, 1, 1, 0};
+__constant__ float c_spiral[300];     // asa.c:438-454 get_points_on_sphere(100), computed on the host with libm
+
+// Philox4x32-10 (Salmon et al. SC'11): counter-based, so every sample of every pocket is independent of scheduling
+__device__ __forceinline__ void philox4x32(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        unsigned h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        unsigned h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        unsigned n0 = h1 ^ c1 ^ k0, n1 = l1, n2 = h0 ^ c3 ^ k1, n3 = l0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// utils.c:113-128 rand_uniform on a 31-bit draw
+__device__ __forceinline__ float unif_from_bits(unsigned r31, float mn, float mx)
+{
+    float rnd = ((float)(int)r31 / (float)2147483647) * (mx - mn);
+    return mn + rnd;
+}
+
+struct DescScratch {          // per resident block of K4
+    int *sa;                  // [natoms_w max] surrounding atoms of the current pocket (asa.c:84-112)
+};
+
+enum { K4_THREADS = 128, MC_SMEM_SPH = 1024 };
+
+__global__ void __launch_bounds__(K4_THREADS) k_descriptors(BatchDev B, PocketDev Pk, const DescScratch *scratch, int *work_counter)
+{
+    __shared__ int s_item, s_U, s_nsa, s_cnt[100], s_sm[40], s_wsum[K4_THREADS / 32];
+    __shared__ float s_mcbox[8];
+    __shared__ float4 s_sph[MC_SMEM_SPH];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const DescScratch &X = scratch[blockIdx.x];
+    const fpk_params &prm = B.prm;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= Pk.total_clusters) return;
+        // (structure, cluster) of this work item
+        int lo = 0, hi = B.nstruct;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (Pk.clbase[mid] <= item) lo = mid; else hi = mid; }
+        const int k = lo, c = item - Pk.clbase[k];
+        const StructDev S = B.S[k];
+        const int *cl_off = B.cl_off + S.sph_off + k;
+        const int off = cl_off[c], n = cl_off[c + 1] - off;
+        const int R = Pk.sbase[k] + off;                   // pocket-level arrays are addressed through the compact sphere base
+        const int *L = B.cl_sph + S.sph_off + off;         // sphere indices (inside the structure) of this pocket, ascending
+        const float4 *sx = B.s_xyzr + S.sph_off;
+        const int4 *sn = B.s_neigh + S.sph_off;
+        const uint8_t *sty = B.s_type + S.sph_off;
+        const float *sb = B.s_bary + 3 * (size_t)S.sph_off;
+        int *uat = Pk.cl_atoms + 4 * (size_t)R, *entu = Pk.ent_u + 4 * (size_t)R;
+        int *toff = Pk.touch_off + 5 * (size_t)R, *tlist = Pk.touch_list + 4 * (size_t)R;
+        int *acc = Pk.acc + 16 * (size_t)R;
+        float *fxv = Pk.fx_val + 16 * (size_t)R;
+        fpk_desc *D = Pk.desc + item;
+        const int A0 = S.atom_off, Q0 = S.prop_off;      // coordinates / properties of atom a: [A0 + a] / [Q0 + a]
+        const bool same = S.same_pdb != 0;
+        const int W0 = S.natoms_w ? S.w_off : S.atom_off, WQ0 = S.natoms_w ? S.w_off : S.prop_off, nw = S.natoms_w ? S.natoms_w : S.natoms;
+        const unsigned whmask = S.natoms_w ? FPK_ATOM_H : FPK_ATOM_H1;
+        const float *wx = S.natoms_w ? B.wx : B.ax, *wy = S.natoms_w ? B.wy : B.ay, *wz = S.natoms_w ? B.wz : B.az;
+        const float *wr = S.natoms_w ? B.wrad : B.arad, *we = S.natoms_w ? B.wen : B.aen;
+        const uint8_t *wf = S.natoms_w ? B.wfl : B.afl;
+
+        // ---- 1. unique contacted atoms by atom id, first-seen order (pocket.c:1280-1320) -- warp 0 -------------------------------
+        if (wid == 0) {
+            int U = 0;
+            for (int base = 0; base < 4 * n; base += 32) {
+                int e = base + lane;
+                bool valid = e < 4 * n;
+                int a = -1, id = -2 - lane;
+                if (valid) {
+                    int4 q = sn[L[e >> 2]];
+                    int j = e & 3;
+                    a = j == 0 ? q.x : (j == 1 ? q.y : (j == 2 ? q.z : q.w));
+                    id = B.aid[Q0 + a];
+                }
+                int dupidx = -1;
+                for (int u = 0; u < U; u++)
+                    if (B.aid[Q0 + uat[u]] == id) dupidx = u;
+                unsigned m = __match_any_sync(0xffffffffu, id);
+                int leader = __ffs(m) - 1;
+                bool isnew = valid && dupidx < 0 && lane == leader;
+                unsigned bal = __ballot_sync(0xffffffffu, isnew);
+                int pos = U + __popc(bal & ((1u << lane) - 1u));
+                if (isnew) uat[pos] = a;
+                int lp = __shfl_sync(0xffffffffu, pos, leader);
+                if (valid) entu[e] = dupidx >= 0 ? dupidx : lp;
+                U += __popc(bal);
+                __syncwarp();
+            }
+            if (lane == 0) s_U = U;
+        }
+        __syncthreads();
+        const int U = s_U;
+        // ---- 2. spheres touching each unique atom (CSR) ----------------------------------------------------------------------------
+        for (int u = tid; u <= U; u += nt) toff[u] = 0;
+        for (int u = tid; u < 4 * U; u += nt) acc[u] = 0;
+        __syncthreads();
+        for (int e = tid; e < 4 * n; e += nt) atomicAdd(&toff[entu[e]], 1);
+        __syncthreads();
+        block_exclusive_scan(toff, U + 1, s_sm);
+        for (int e = tid; e < 4 * n; e += nt) {
+            int u = entu[e];
+            int slot = atomicAdd(&acc[u], 1);               // acc[0..U) doubles as the fill cursor here
+            tlist[toff[u] + slot] = e >> 2;
+        }
+        __syncthreads();
+        for (int u = tid; u < 4 * U; u += nt) acc[u] = 0;
+        __syncthreads();
+
+        if (prm.do_asa_and_volume) {
+            // ---- 3. surrounding atoms (asa.c:84-112): heavy atoms of pdb_w_lig within ray+1 of a sphere, atom order ----------------
+            float bmn[3] = {3e38f, 3e38f, 3e38f}, bmx[3] = {-3e38f, -3e38f, -3e38f};
+            for (int i = tid; i < n; i += nt) {
+                float4 v = sx[L[i]];
+                float rp = v.w + 1.01f;
+                bmn[0] = fminf(bmn[0], v.x - rp); bmn[1] = fminf(bmn[1], v.y - rp); bmn[2] = fminf(bmn[2], v.z - rp);
+                bmx[0] = fmaxf(bmx[0], v.x + rp); bmx[1] = fmaxf(bmx[1], v.y + rp); bmx[2] = fmaxf(bmx[2], v.z + rp);
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1)
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    bmn[q] = fminf(bmn[q], __shfl_xor_sync(0xffffffffu, bmn[q], d));
+                    bmx[q] = fmaxf(bmx[q], __shfl_xor_sync(0xffffffffu, bmx[q], d));
+                }
+            __shared__ float s_bb[K4_THREADS / 32][6];
+            if (lane == 0) for (int q = 0; q < 3; q++) { s_bb[wid][q] = bmn[q]; s_bb[wid][3 + q] = bmx[q]; }
+            __syncthreads();
+            for (int w = 0; w < nt / 32; w++)
+                for (int q = 0; q < 3; q++) { bmn[q] = fminf(bmn[q], s_bb[w][q]); bmx[q] = fmaxf(bmx[q], s_bb[w][3 + q]); }
+            if (tid == 0) s_nsa = 0;
+            __syncthreads();
+            for (int base = 0; base < nw; base += nt) {
+                int i = base + tid;
+                bool in = false;
+                if (i < nw && !(wf[WQ0 + i] & whmask)) {
+                    float x = wx[W0 + i], y = wy[W0 + i], z = wz[W0 + i];
+                    if (x >= bmn[0] && x <= bmx[0] && y >= bmn[1] && y <= bmx[1] && z >= bmn[2] && z <= bmx[2]) {
+                        for (int q = 0; q < n && !in; q++) {
+                            float4 v = sx[L[q]];
+                            double rp = (double)v.w + 1.0;
+                            in = (double)f_ddist(x, y, z, v.x, v.y, v.z) < rp * rp;
+                        }
+                    }
+                }
+                unsigned bal = __ballot_sync(0xffffffffu, in);
+                if (lane == 0) s_wsum[wid] = __popc(bal);
+                __syncthreads();
+                int woff = s_nsa;
+                for (int w = 0; w < wid; w++) woff += s_wsum[w];
+                if (in) X.sa[woff + __popc(bal & ((1u << lane) - 1u))] = i;
+                __syncthreads();
+                if (tid == 0) { int t = 0; for (int w = 0; w < nt / 32; w++) t += s_wsum[w]; s_nsa += t; }
+                __syncthreads();
+            }
+            const int n_sa = s_nsa;
+            // ---- 4. 100-point spiral SASA, probes 1.4 and 2.2 (asa.c:240-419): one thread per (atom, point, probe) -----------
+            for (int it = tid; it < U * 200; it += nt) {
+                const int pass = it >= U * 100 ? 1 : 0;
+                const int r = it - pass * U * 100;
+                const int u = r / 100, kp = r - u * 100;
+                const double probe = pass == 0 ? 1.4 : 2.2;
+                const int cura = uat[u];
+                const float cx = B.ax[A0 + cura], cy = B.ay[A0 + cura], cz = B.az[A0 + cura], crad = B.arad[Q0 + cura];
+                const float tx = (float)((double)cx + (double)c_spiral[3 * kp] * ((double)crad + probe));
+                const float ty = (float)((double)cy + (double)c_spiral[3 * kp + 1] * ((double)crad + probe));
+                const float tz = (float)((double)cz + (double)c_spiral[3 * kp + 2] * ((double)crad + probe));
+                bool vref = true;                                   // "vrefburried": not inside any touching alpha sphere
+                for (int q = toff[u]; q < toff[u + 1] && vref; q++) {
+                    float4 v = sx[L[tlist[q]]];
+                    if (f_ddist(tx, ty, tz, v.x, v.y, v.z) <= v.w * v.w) vref = false;
+                }
+                if (vref) continue;
+                int hit = -1;
+                for (int j = 0; j < n_sa; j++) {
+                    int a = X.sa[j];
+                    if (same && a == cura) continue;                // asa.c:315 pointer inequality
+                    float dsq = f_ddist(tx, ty, tz, wx[W0 + a], wy[W0 + a], wz[W0 + a]);
+                    double rr = (double)wr[WQ0 + a] + probe;
+                    if ((double)dsq < rr * rr) { hit = a; break; }
+                }
+                if (hit < 0) atomicAdd(&acc[4 * u + pass], 1);
+                else if (pass == 0) atomicAdd(&acc[4 * u + ((double)we[WQ0 + hit] < 2.8 ? 2 : 3)], 1);
+            }
+            // ---- 5. Monte-Carlo volume (voronoi.c:1150-1233), radius ray-1.6, 100 x nb_mcv_iter samples ------------------------------
+            const float correct = -1.6f;
+            if (tid == 0) {
+                float xmin = 0, xmax = 0, ymin = 0, ymax = 0, zmin = 0, zmax = 0, xt, yt, zt;
+                for (int i = 0; i < n; i++) {
+                    float4 v = sx[L[i]];
+                    if (i == 0) {
+                        xmin = v.x - v.w + correct; xmax = v.x + v.w + correct;
+                        ymin = v.y - v.w + correct; ymax = v.y + v.w + correct;
+                        zmin = v.z - v.w + correct; zmax = v.z + v.w + correct;
+                    } else {
+                        if (xmin > (xt = v.x - v.w + correct)) xmin = xt; else if (xmax < (xt = v.x + v.w + correct)) xmax = xt;
+                        if (ymin > (yt = v.y - v.w + correct)) ymin = yt; else if (ymax < (yt = v.y + v.w + correct)) ymax = yt;
+                        if (zmin > (zt = v.z - v.w + correct)) zmin = zt; else if (zmax < (zt = v.z + v.w + correct)) zmax = zt;
+                    }
+                }
+                s_mcbox[0] = xmin; s_mcbox[1] = xmax; s_mcbox[2] = ymin; s_mcbox[3] = ymax; s_mcbox[4] = zmin; s_mcbox[5] = zmax;
+            }
+            for (int i = tid; i < 100; i += nt) s_cnt[i] = 0;
+            const bool insm = n <= MC_SMEM_SPH;
+            if (insm)
+                for (int i = tid; i < n; i += nt) { float4 v = sx[L[i]]; v.w = (correct + v.w) * (v.w + correct); s_sph[i] = v; }
+            __syncthreads();
+            {
+                const float xmin = s_mcbox[0], xmax = s_mcbox[1], ymin = s_mcbox[2], ymax = s_mcbox[3], zmin = s_mcbox[4], zmax = s_mcbox[5];
+                const int niter = prm.nb_mcv_iter;
+                const unsigned k0 = (unsigned)prm.mc_seed, k1 = (unsigned)(prm.mc_seed >> 32);
+                for (int s = tid; s < 100 * niter; s += nt) {
+                    const int li = s / niter, i = s - li * niter;
+                    unsigned o[4];
+                    philox4x32((unsigned)i, (unsigned)li, (unsigned)c, 0u, k0, k1, o);
+                    const float xr = unif_from_bits(o[0] >> 1, xmin, xmax), yr = unif_from_bits(o[1] >> 1, ymin, ymax),
+                                zr = unif_from_bits(o[2] >> 1, zmin, zmax);
+                    bool in = false;
+                    if (insm) {
+                        for (int j = 0; j < n && !in; j++) {
+                            float4 v = s_sph[j];
+                            float xt = v.x - xr, yt = v.y - yr, zt = v.z - zr;
+                            in = v.w > (xt * xt + yt * yt + zt * zt);
+                        }
+                    } else {
+                        for (int j = 0; j < n && !in; j++) {
+                            float4 v = sx[L[j]];
+                            float xt = v.x - xr, yt = v.y - yr, zt = v.z - zr;
+                            in = ((correct + v.w) * (v.w + correct)) > (xt * xt + yt * yt + zt * zt);
+                        }
+                    }
+                    if (in) atomicAdd(&s_cnt[li], 1);
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- 6. the sequential float sums, in the reference's order -- warp 0 -------------------------------------------------------
+        if (wid == 0) {
+            // sphere pair loop (descriptors.c:186-236): as_density accumulates dist(i,j), i<j, row-major, in ONE float
+            float as_density = 0.0f, as_max_dst = -1.0f;
+            int mlhd_cnt = 0, nAlphaApol = 0;
+            for (int i = 0; i < n; i++) {
+                const float4 vi = sx[L[i]];
+                const bool apol_i = sty[L[i]] == 0;
+                int napol = 0;
+                if (apol_i) {
+                    for (int j = lane; j < n; j += 32) {
+                        if (j == i || sty[L[j]] != 0) continue;
+                        float4 vj = sx[L[j]];
+                        if ((double)(f_dist(vi.x, vi.y, vi.z, vj.x, vj.y, vj.z) - (vj.w + vi.w)) <= 0.) napol++;
+                    }
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) napol += __shfl_xor_sync(0xffffffffu, napol, d);
+                    mlhd_cnt += napol;
+                    nAlphaApol++;
+                }
+                for (int base = i + 1; base < n; base += 32) {
+                    int j = base + lane;
+                    float dj = 0.0f;
+                    if (j < n) { float4 vj = sx[L[j]]; dj = f_dist(vi.x, vi.y, vi.z, vj.x, vj.y, vj.z); }
+                    const int cntj = min(32, n - base);
+                    for (int q = 0; q < cntj; q++) {
+                        float dq = __shfl_sync(0xffffffffu, dj, q);
+                        if (dq > as_max_dst) as_max_dst = dq;
+                        as_density += dq;
+                    }
+                }
+            }
+            if (lane == 0) {
+                float mean_r = 0.0f, masph = 0.0f, as_max_r = -1.0f, ps0 = 0.0f, ps1 = 0.0f, ps2 = 0.0f;
+                int napolc = 0;
+                for (int i = 0; i < n; i++) {
+                    const int si = L[i];
+                    const float4 v = sx[si];
+                    if (v.w > as_max_r) as_max_r = v.w;
+                    mean_r += v.w;
+                    float dd = f_dist(v.x, v.y, v.z, sb[3 * si], sb[3 * si + 1], sb[3 * si + 2]);
+                    masph += dd / v.w;
+                    ps0 += v.x; ps1 += v.y; ps2 += v.z;
+                    if (sty[si] == 0) napolc++;
+                }
+                fpk_desc d;
+                memset(&d, 0, sizeof d);
+                d.first_sphere = L[0];
+                d.nAlphaApol = napolc; d.nAlphaPol = n - napolc;
+                d.bary[0] = ps0 / (float)n; d.bary[1] = ps1 / (float)n; d.bary[2] = ps2 / (float)n;      // refine.c:192-240
+                d.n_atoms = U;
+                // atom based (descriptors.c:355-436, :453-513)
+                if (U > 1) {
+                    int nb_res = 0, nb_polar = 0;
+                    float flex = 0.0f, hyd = 0.0f, vol = 0.0f;
+                    for (int u = 0; u < U; u++) {
+                        const int a = Q0 + uat[u];
+                        const int rid = B.ares[a];
+                        bool seen = false;
+                        for (int q = 0; q < u && !seen; q++) seen = B.ares[Q0 + uat[q]] == rid;
+                        if (!seen) {
+                            int aa = B.aaa[a];
+                            if (aa >= 0) {
+                                d.aa_compo[aa]++;
+                                hyd += c_aa_hyd[aa]; d.polarity_score += c_aa_pol[aa]; vol += c_aa_vol[aa]; d.charge_score += c_aa_chg[aa];
+                            }
+                            nb_res++;
+                        }
+                        flex += B.abf[a];
+                        if ((double)B.aen[a] > 2.7) nb_polar++;
+                    }
+                    d.hydrophobicity_score = hyd / (float)nb_res;
+                    d.volume_score = vol / (float)nb_res;
+                    d.flex = flex / (float)U;
+                    d.prop_polar_atm = (float)((double)(((float)nb_polar) / ((float)U)) * 100.0);
+                }
+                d.mean_loc_hyd_dens = nAlphaApol > 0 ? (float)mlhd_cnt / (float)nAlphaApol : 0.0f;
+                if (prm.do_asa_and_volume) {
+                    for (int pass = 0; pass < 2; pass++) {
+                        const double probe = pass == 0 ? 1.4 : 2.2;
+                        for (int u = 0; u < U; u++) {
+                            const int a = Q0 + uat[u];
+                            const size_t ga = (size_t)A0 + uat[u];       // per-structure slot for the side effects
+                            const float crad = B.arad[a];
+                            const int nnb = acc[4 * u + pass];
+                            const float area = (float)((4 * 3.1415926535897932384626433832795 * ((double)crad + probe) * ((double)crad + probe) / (double)(float)100) * (double)nnb);
+                            const bool apolar_atom = (double)B.aen[a] < 2.8;
+                            if (pass == 0) {
+                                fxv[4 * u + 1] = area;              // abpatmp
+                                if (apolar_atom) d.surf_apol_vdw14 = d.surf_apol_vdw14 + area; else d.surf_pol_vdw14 = d.surf_pol_vdw14 + area;
+                                d.surf_vdw14 = d.surf_vdw14 + area;
+                                const float na = (float)acc[4 * u + 2], np = (float)acc[4 * u + 3];
+                                fxv[4 * u + 0] = na / (na + np);     // abpa_sourrounding_prob
+                                fxv[4 * u + 3] = 0.0f;
+                                atomicMax(&Pk.fx_who[2 * ga], c);
+                            } else {
+                                if (apolar_atom) d.surf_apol_vdw22 = d.surf_apol_vdw22 + area;
+                                else {
+                                    const float a14 = fxv[4 * u + 1];
+                                    if (area < a14 && (double)a14 <= 10.0 && (double)area >= 0.0) {
+                                        d.n_abpa += 1;
+                                        fxv[4 * u + 2] = area - a14;   // dA ; a0 = a14
+                                        fxv[4 * u + 3] = 1.0f;
+                                        atomicMax(&Pk.fx_who[2 * ga + 1], c);
+                                    }
+                                    d.surf_pol_vdw22 = d.surf_pol_vdw22 + area;
+                                }
+                                d.surf_vdw22 = d.surf_vdw22 + area;
+                            }
+                        }
+                    }
+                    const float vbox = (s_mcbox[1] - s_mcbox[0]) * (s_mcbox[3] - s_mcbox[2]) * (s_mcbox[5] - s_mcbox[4]);
+                    float sum_volume = 0.0f;
+                    for (int li = 0; li < 100; li++) sum_volume += ((float)s_cnt[li]) / ((float)prm.nb_mcv_iter) * vbox;
+                    d.volume = sum_volume / (float)100;
+                }
+                d.as_max_dst = as_max_dst;
+                d.apolar_asphere_prop = (float)nAlphaApol / (float)n;
+                d.masph_sacc = masph / (float)n;
+                d.mean_asph_ray = mean_r / (float)n;
+                d.nb_asph = n;
+                d.as_density = (float)((double)as_density / ((n * n - n) * 0.5));
+                d.as_max_r = as_max_r;
+                d.convex_hull_volume = D->convex_hull_volume;       // written by k_hull_volume before this kernel
+                *D = d;
+            }
+        }
+    }
+}
+
+// ============================================= K4c: finalize per structure ====================================================
+__global__ void __launch_bounds__(128) k_finalize(BatchDev B, PocketDev Pk)
+{
+    const int k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    if (k >= B.nstruct) return;
+    int *counts = B.counts + (size_t)k * CNT_STRIDE;
+    const StructDev S = B.S[k];
+    if (counts[CNT_STATUS] != FPK_OK) { if (tid == 0) counts[CNT_POCKETS] = 0; return; }
+    const int nc = counts[CNT_CLUSTERS];
+    fpk_desc *D = Pk.desc + Pk.clbase[k];
+    const fpk_params &prm = B.prm;
+    __shared__ float s_f[10];
+    __shared__ int s_i[6];
+    // ---- pocket.c:664-785: min/max with the reference's sequential-scan semantics (first value NaN poisons both bounds) ----------
+    if (tid < 7) {
+        // 0 as_max_dst 1 as_density 2 mean_loc_hyd_dens 3 flex 4 apolar_asphere_prop | 5 polarity_score 6 nb_asph (ints)
+        if (tid < 5) {
+            float M = 0, m = 0;
+            for (int i = 0; i < nc; i++) {
+                const fpk_desc &d = D[i];
+                float v = tid == 0 ? d.as_max_dst : tid == 1 ? d.as_density : tid == 2 ? d.mean_loc_hyd_dens : tid == 3 ? d.flex : d.apolar_asphere_prop;
+                if (i == 0) M = m = v;
+                else if (v > M) M = v;
+                else if (v < m) m = v;
+            }
+            s_f[2 * tid] = M; s_f[2 * tid + 1] = m;
+        } else {
+            int M = 0, m = 0;
+            for (int i = 0; i < nc; i++) {
+                int v = tid == 5 ? D[i].polarity_score : D[i].nb_asph;
+                if (i == 0) M = m = v;
+                else if (v > M) M = v;
+                else if (v < m) m = v;
+            }
+            s_i[2 * (tid - 5)] = M; s_i[2 * (tid - 5) + 1] = m;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < nc; i += nt) {
+        fpk_desc d = D[i];
+        if (nc > 1) {
+            if ((double)(s_f[0] - s_f[1]) != 0.0) d.as_max_dst_norm = (d.as_max_dst - s_f[1]) / (s_f[0] - s_f[1]);
+            if ((double)(s_f[2] - s_f[3]) != 0.0) d.as_density_norm = (d.as_density - s_f[3]) / (s_f[2] - s_f[3]);
+            if ((double)(s_i[0] - s_i[1]) != 0.0) d.polarity_score_norm = (float)(d.polarity_score - s_i[1]) / (float)(s_i[0] - s_i[1]);
+            if ((double)(s_f[4] - s_f[5]) != 0.0) d.mean_loc_hyd_dens_norm = (d.mean_loc_hyd_dens - s_f[5]) / (s_f[4] - s_f[5]);
+            if ((double)(s_f[6] - s_f[7]) != 0.0) d.flex = (d.flex - s_f[7]) / (s_f[6] - s_f[7]);
+            if ((double)(s_i[2] - s_i[3]) != 0.0) d.nas_norm = (float)(d.nb_asph - s_i[3]) / (float)(s_i[2] - s_i[3]);
+            if ((double)(s_f[8] - s_f[9]) != 0.0) d.prop_asapol_norm = (d.apolar_asphere_prop - s_f[9]) / (s_f[8] - s_f[9]);
+        } else {
+            d.polarity_score_norm = 0.0f; d.as_density_norm = 0.0f; d.as_max_dst_norm = 0.0f;
+            d.mean_loc_hyd_dens_norm = (float)(((double)d.mean_loc_hyd_dens - 8.23) / (24.20 - 8.23));
+            d.flex = 0.0f; d.nas_norm = 0.0f; d.prop_asapol_norm = 0.0f;
+        }
+        // pscoring.c:241-247 and :325-329
+        d.score = (float)(-0.03783394 + 0.48461469 * (double)d.nas_norm + 0.09093926 * (double)d.as_density +
+                          0.0004155899 * (double)d.convex_hull_volume - 0.003995233 * (double)d.surf_pol_vdw14 -
+                          0.004072336 * (double)d.surf_apol_vdw14);
+        const float b0 = (float)-9.5698768, b1 = (float)7.479844, b2 = (float)0.3696134, b3 = (float)-0.04671833;
+        d.drug_score = (float)(1.0 / (1.0 + exp((double)(-(b0 + b1 * d.mean_loc_hyd_dens_norm + b2 * d.as_max_dst + b3 * d.surf_pol_vdw22)))));
+        d.final_rank = 0;
+        D[i] = d;
+    }
+    __syncthreads();
+    // ---- refine.c:114-145 drop, psorting.c:64-165 first-pivot quicksort (same partition scheme => same tie order) -- one thread ----
+    if (tid == 0) {
+        int *keep = Pk.rank_to_cluster + Pk.sbase[k] + k, nk = 0;
+        for (int i = 0; i < nc; i++) {
+            const fpk_desc &d = D[i];
+            double pasph = (float)((float)d.nAlphaApol / (float)d.nb_asph);
+            int rhs = (prm.refine_min_apolar_asphere_prop != 0.0f) || (d.as_density < prm.min_as_density);
+            if (d.nb_asph < prm.min_pock_nb_asph || pasph < (double)rhs) continue;
+            keep[nk++] = i;
+        }
+        int stack[64][2], sp = 0;
+        if (nk > 1) { stack[0][0] = 0; stack[0][1] = nk - 1; sp = 1; }
+        while (sp > 0) {
+            sp--;
+            int start = stack[sp][0], end = stack[sp][1];
+            while (start < end) {
+                int cpos = start, piv = keep[start], tmp;
+                for (int i = start + 1; i <= end; i++) {
+                    int cp = keep[i];
+                    if (!(D[cp].score < D[piv].score)) {
+                        cpos++;
+                        if (cpos != i) { tmp = keep[cpos]; keep[cpos] = keep[i]; keep[i] = tmp; }
+                    }
+                }
+                if (cpos != start) { tmp = keep[cpos]; keep[cpos] = keep[start]; keep[start] = tmp; }
+                // recurse on the smaller half through the explicit stack, iterate on the other (order of the halves is immaterial)
+                int l0 = start, l1 = cpos - 1, r0 = cpos + 1, r1 = end;
+                if (l1 - l0 < r1 - r0) { if (l0 < l1 && sp < 64) { stack[sp][0] = l0; stack[sp][1] = l1; sp++; } start = r0; end = r1; }
+                else { if (r0 < r1 && sp < 64) { stack[sp][0] = r0; stack[sp][1] = r1; sp++; } start = l0; end = l1; }
+            }
+        }
+        for (int r = 0; r < nk; r++) D[keep[r]].final_rank = r + 1;
+        counts[CNT_POCKETS] = nk;
+        if (nk == 0) counts[CNT_STATUS] = FPK_ERR_NO_POCKETS;
+    }
+}
+
+// per-atom ASA side effects (asa.c:337,392-396): the LAST pocket (in list order) that wrote a field wins
+__global__ void k_atom_fx(BatchDev B, PocketDev Pk)
+{
+    const int item = blockIdx.x;
+    if (item >= Pk.total_clusters) return;
+    int lo = 0, hi = B.nstruct;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (Pk.clbase[mid] <= item) lo = mid; else hi = mid; }
+    const int k = lo, c = item - Pk.clbase[k];
+    const StructDev S = B.S[k];
+    if (B.counts[(size_t)k * CNT_STRIDE + CNT_CLUSTERS] <= c) return;
+    const int *cl_off = B.cl_off + S.sph_off + k;
+    const int R = Pk.sbase[k] + cl_off[c];
+    const int U = Pk.desc[item].n_atoms;
+    const int *uat = Pk.cl_atoms + 4 * (size_t)R;
+    const float *fxv = Pk.fx_val + 16 * (size_t)R;
+    for (int u = threadIdx.x; u < U; u += blockDim.x) {
+        const size_t a = (size_t)S.atom_off + uat[u];
+        if (Pk.fx_who[2 * a] == c) Pk.atom_fx[4 * a + 3] = fxv[4 * u + 0];
+        if (fxv[4 * u + 3] != 0.0f && Pk.fx_who[2 * a + 1] == c) {
+            Pk.atom_fx[4 * a + 0] = 1.0f; Pk.atom_fx[4 * a + 1] = fxv[4 * u + 1]; Pk.atom_fx[4 * a + 2] = fxv[4 * u + 2];
+        }
+    }
+}
+
+}  // namespace fpk

@@ -5,7 +5,7 @@ fpk_structure (include/fpocket_cuda.h).
 """
 import numpy as np
 
-from .capi import FPK_ATOM_H, Structure
+from .capi import FPK_ATOM_H, FPK_ATOM_H1, Structure
 
 # reference headers/aa.h:22-41
 _AA = {n: i for i, n in enumerate(
@@ -66,7 +66,8 @@ def structure_from_arrays(f, i, symbol, res_name, bfstat, w=None, same_pdb=0, xl
     w: optional (f_w, symbol_w) of the ligand-keeping copy (pdb_w_lig)."""
     n = len(f)
     sym = [_cstr(r) for r in symbol]
-    flags = np.array([FPK_ATOM_H if s == "H" else 0 for s in sym], dtype=np.uint8)     # voronoi.c:100
+    flags = np.array([(FPK_ATOM_H if s == "H" else 0) | (FPK_ATOM_H1 if s[:1] == "H" else 0) for s in sym],
+                     dtype=np.uint8)     # voronoi.c:100 / asa.c:89
     if extra_flags is not None:
         flags |= np.asarray(extra_flags, dtype=np.uint8)
     aa = np.array([aa_index(_cstr(r)) for r in res_name], dtype=np.int8) if n else np.zeros(0, np.int8)
@@ -75,11 +76,5 @@ def structure_from_arrays(f, i, symbol, res_name, bfstat, w=None, same_pdb=0, xl
         fw, symw = w
         wflags = np.array([FPK_ATOM_H if _cstr(r)[:1] == "H" else 0 for r in symw], dtype=np.uint8)  # asa.c:89
         wt = (fw[:, 0], fw[:, 1], fw[:, 2], fw[:, 3], fw[:, 4], wflags)
-    elif same_pdb:
-        # pdb_w_lig is pdb: the "surrounding atom" H test (symbol[0]=='H') differs from the site test
-        # (symbol=="H"); keep a separate flag array only if they differ
-        wflags = np.array([FPK_ATOM_H if s[:1] == "H" else 0 for s in sym], dtype=np.uint8)
-        if not np.array_equal(wflags, flags & FPK_ATOM_H):
-            wt = (f[:, 0], f[:, 1], f[:, 2], f[:, 3], f[:, 4], wflags)
     return Structure(f[:, 0], f[:, 1], f[:, 2], f[:, 3], f[:, 4], f[:, 5], i[:, 0], i[:, 1], aa, flags, bfstat,
                      w=wt, same_pdb=same_pdb, xlig=xlig)

@@ -41,6 +41,7 @@ extern "C" {
 #define FPK_ATOM_H          1u    /* pdb atoms:  strcmp(symbol,"H")==0  -> not a Delaunay site (voronoi.c:100,128)
                                      pdb_w_lig:  symbol[0]=='H'         -> not a "surrounding atom" (asa.c:89)   */
 #define FPK_ATOM_XPOCKET    2u    /* atom_in_explicit_pocket() is true (voronoi.c:934-949), -P option only      */
+#define FPK_ATOM_H1         4u    /* pdb atoms: symbol[0]=='H' (Hg, Ho, ...): the asa.c:89 test when pdb_w_lig is pdb itself */
 
 /* numeric subset of s_fparams (reference headers/fparams.h:182-227), defaults fparams.h:33-63 */
 typedef struct fpk_params {

@@ -320,7 +320,7 @@ static void set_asa(const fpk_structure *in, const sph_t *S, const int *idx, int
     d->n_abpa = 0;
     int *sa = malloc(sizeof(int) * (size_t)(nw + 1)), n_sa = 0;
     for (int i = 0; i < nw; i++) {
-        if (wf[i] & FPK_ATOM_H) continue;
+        if (wf[i] & (same ? FPK_ATOM_H1 : FPK_ATOM_H)) continue;
         for (int z = 0; z < n; z++) {
             const sph_t *v = S + idx[z];
             double rp = (double)v->ray + 1.0;
