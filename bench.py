@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Benchmark of the fpocket hot path on B200 (contract: one JSON line on stdout from rank 0).
+
+Workload (BASELINE.json configs[1]): a batch of 10,000 synthetic protein-like structures of 2,000-5,000 heavy atoms
+(tests/synth, seeds 20260000+k), default fpocket parameters, every stage of search_pocket() per structure.
+A "step" is one pass of the whole pipeline over the batch. `value` = structures/s with the batch already resident
+in HBM (kernels + the one 32-byte-per-structure count read-back the pipeline needs); `e2e` = the same metric through
+fpk_detect_batch() with host buffers (pack, H2D, kernels, D2H, unpack inside the timed region).
+With N > 1 (torchrun) every rank processes its own batch (independent structures, no collective): weak scaling.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--structures B] [--impl reference] [--md-frames F]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+SEED0 = 20260000
+
+
+def _gen_one(k):
+    import synth
+    rng = np.random.default_rng(SEED0 + k)
+    n = int(rng.integers(2000, 5001))
+    return synth.generate(SEED0 + k, n, 0.065)
+
+
+def make_batch(nstruct, workers, first=0):
+    import synth
+    synth.lib()                                   # compile once before forking
+    ids = list(range(first, first + nstruct))
+    if workers > 1 and nstruct >= 64:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            raw = pool.map(_gen_one, ids, chunksize=16)
+    else:
+        raw = [_gen_one(k) for k in ids]
+    return raw
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop = False
+        self.proc = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop:
+                    break
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, nme in enumerate(names):
+                if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def reference_fpocket_rate(raw, nsample, cores, keep_dir=None):
+    """Times the UNMODIFIED reference binary (oracle/_ref/fpocket, built from /root/reference by oracle/Makefile) on the first
+    `nsample` structures of the workload, one process per structure (the reference is single-threaded and not re-entrant),
+    `cores` processes at a time, files on tmpfs. Returns structures/s."""
+    import synth
+    exe = os.path.join(ROOT, "oracle", "_ref", "fpocket")
+    if not os.path.exists(exe):
+        return None, "oracle/_ref/fpocket missing"
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    tmp = tempfile.mkdtemp(prefix="fpkref", dir=base)
+    files = []
+    for k in range(nsample):
+        f = os.path.join(tmp, "s%05d.pdb" % k)
+        synth.to_pdb(raw[k], f)
+        files.append(f)
+    t0 = time.time()
+    procs = []
+    it = iter(files)
+    done = 0
+    env = dict(os.environ, TMPDIR=tmp)
+    while True:
+        while len(procs) < cores:
+            f = next(it, None)
+            if f is None:
+                break
+            procs.append(subprocess.Popen([exe, "-f", f], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=tmp, env=env))
+        if not procs:
+            break
+        procs[0].wait()
+        procs.pop(0)
+        done += 1
+    dt = time.time() - t0
+    subprocess.call(["rm", "-rf", tmp])
+    return nsample / dt, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--structures", type=int, default=10000, help="structures per GPU (BASELINE configs[1]: 10,000)")
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--ref-sample", type=int, default=0)
+    ap.add_argument("--md-frames", type=int, default=0, help="also measure mdpocket frames/s on a synthetic trajectory of this many frames per GPU")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    ncores = os.cpu_count() or 1
+    workers = max(1, ncores // max(1, world))
+
+    cfg = {"workload": "batch of %d synthetic protein-like structures of 2k-5k heavy atoms per GPU (BASELINE configs[1]), default fpocket "
+                       "parameters, full search_pocket() per structure" % args.structures,
+           "structures_per_gpu": args.structures, "generator": "tests/synth/synth.c seeds 20260000+k, density 0.065",
+           "l2": "inputs + per-block scratch (> 1 GB) exceed the 126 MB L2; nothing is reused between steps",
+           "parallelism": "structures sharded per GPU, no collective"}
+
+    # ------------------------------------------------------------------ reference arm -----------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        nsample = args.ref_sample or max(ncores * 3, 48)
+        raw = make_batch(nsample, ncores)
+        for _ in range(max(0, min(args.warmup, 1))):
+            reference_fpocket_rate(raw, min(nsample, ncores), ncores)
+        rates = []
+        for _ in range(max(1, args.steps)):
+            r, dt = reference_fpocket_rate(raw, nsample, ncores)
+            if r is None:
+                print(json.dumps({"impl": "reference", "unavailable": dt}))
+                return
+            rates.append((r, dt))
+        v = float(np.mean([r for r, _ in rates]))
+        ms = float(np.mean([dt for _, dt in rates])) * 1e3
+        sample = "first %d structures of the workload per step, one `fpocket -f` process each, %d at a time, tmpfs" % (nsample, ncores)
+        print(json.dumps({"impl": "reference", "metric": "structures/sec", "value": v, "unit": "structures/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32/f64", "data": "synthetic", "config": cfg,
+                          "cpu_baseline": {"value": v, "unit": "structures/s", "cores": ncores, "kind": "reference", "sample": sample},
+                          "e2e": {"value": v, "unit": "structures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------ B200 arm ----------------------------------------------------
+    import torch
+    import synth
+    from fpocket_b200 import api
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    api.init(local)
+
+    t0 = time.time()
+    raw = make_batch(args.structures, workers)
+    structs = [synth.to_structure(s) for s in raw]
+    t_gen = time.time() - t0
+    p = api.default_params()
+    batch = api.Batch(structs, p)                      # pack + H2D: inputs now resident in HBM
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        batch.run()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    kms = np.zeros(8)
+    t1 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        batch.run()                                    # returns after the device finished; per-stage CUDA-event times inside
+        for i in range(8):
+            kms[i] += batch.kernel_ms(i)
+        dev_ms += batch.kernel_ms(7)
+    barrier()
+    wall = time.perf_counter() - t1
+    clocks = sampler.finish() if sampler else None
+    launches = batch.counter(5) * args.steps
+    tot = {k: batch.counter(i) for i, k in enumerate(["sites", "tets", "spheres", "clusters", "pockets"])}
+    subrounds, retries = batch.counter(8), batch.counter(9)
+    # max over ranks of the timed region (device-timed whole steps; wall kept for the record)
+    tt = torch.tensor([dev_ms / 1e3, wall], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev, t_wall = float(tt[0]), float(tt[1])
+    value = args.structures * world * args.steps / t_dev        # device-timed (CUDA events around every step), max over ranks
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------------------------------
+    peak, peak_src = measured_peak()
+    stage_names = ["k_delaunay_filter", "k_cluster", "host_count_roundtrip+alloc", "k_hull_volume", "k_descriptors", "k_finalize+k_atom_fx+k_compact"]
+    per_stage = {stage_names[i]: kms[i] / args.steps for i in range(6)}
+    dom = max(("k_delaunay_filter", "k_hull_volume", "k_descriptors", "k_cluster"), key=lambda k: per_stage[k])
+    # algorithmic bytes: B = 32 N + 32 T + 108 S + 160 P0 per structure; split per kernel in DESIGN.md
+    N, T, S, P0 = tot["sites"], tot["tets"], tot["spheres"], tot["clusters"]
+    alg = {"k_delaunay_filter": 32 * N + 32 * T + 36 * S, "k_cluster": 36 * S + 8 * S, "k_descriptors": 36 * S + 160 * P0 + 32 * N,
+           "k_hull_volume": 16 * S + 4 * P0}
+    ach = alg[dom] / (per_stage[dom] * 1e-3) / 1e9
+    whole = (32 * N + 32 * T + 108 * S + 160 * P0)
+    roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": per_stage[dom],
+            "whole_path": {"algorithmic_bytes_per_step": whole, "achieved_gbs": whole / (t_dev / args.steps) / 1e9,
+                           "frac": whole / (t_dev / args.steps) / 1e9 / peak}}
+    out = {"metric": "structures/sec", "value": value, "unit": "structures/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64 predicates/circumcentres + f32 descriptors (the reference's own mix)", "data": "synthetic", "config": cfg,
+           "wall_ms_per_step": t_wall / args.steps * 1e3, "stage_ms_per_step": per_stage, "roofline": roof, "gpu_launches": int(launches),
+           "totals_per_gpu": tot, "delaunay_subrounds_per_structure": subrounds / max(1, args.structures),
+           "delaunay_retries_per_site": retries / max(1, N), "clocks": clocks, "gen_s": t_gen}
+
+    # ---- e2e: the public call with host buffers ---------------------------------------------------------------------------------
+    if not args.no_e2e:
+        ne2e = min(args.structures, 4096)
+        sub = structs[:ne2e]
+        api.detect_batch(sub[: min(256, ne2e)], p)         # warm the allocator / page-lock paths
+        barrier()
+        te = time.perf_counter()
+        b2 = api.Batch(sub, p)
+        h2d = b2.counter(6)
+        b2.run()
+        res = b2.fetch(as_dicts=False)
+        d2h = b2.counter(7)
+        barrier()
+        te = time.perf_counter() - te
+        b2.close()
+        ee = torch.tensor([te], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(ee, op=dist.ReduceOp.MAX)
+        out["e2e"] = {"value": ne2e * world / float(ee[0]), "unit": "structures/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                      "structures_per_call": ne2e, "ok": int(sum(1 for s in res if s[0] == 0)),
+                      "note": "fpk_batch_create + run + fetch on host arrays (what fpk_detect_batch does), one call"}
+
+    # ---- optional: mdpocket frames/s with the grids summed over ranks (NCCL) ------------------------------------------------------
+    if args.md_frames > 0:
+        s5 = synth.generate(20260301, 5000, 0.065)
+        st5 = synth.to_structure(s5)
+        rng = np.random.default_rng(20260301 + rank)
+        F = args.md_frames
+        modes = rng.normal(size=(8, s5.n, 3)).astype(np.float32) * 0.25
+        amp = np.cumsum(rng.normal(size=(F, 8)).astype(np.float32) * 0.15, 0)
+        amp -= amp.mean(0)
+        xyz = (s5.xyz[None] + np.tensordot(np.clip(amp, -1.2, 1.2), modes, 1)).astype(np.float32)
+        xyz = np.round(xyz, 3)
+        md = api.MdPocket(st5, p)
+        org, dims = md.grid_from_frame(s5.xyz[None])             # frame 1 defines the grid (mdpocket.c:151-154); same on every rank
+        md.set_grid(org, dims)
+        md.push_frames(xyz[: min(F, 64)])                        # warm-up
+        md.set_grid(org, dims)
+        barrier()
+        tm = time.perf_counter()
+        md.push_frames(xyz)
+        if dist is not None:
+            gd, gf = md.torch_grids()
+            dist.all_reduce(gd)                                  # the only collective of the whole design
+            dist.all_reduce(gf)
+        barrier()
+        tm = time.perf_counter() - tm
+        mm = torch.tensor([tm], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(mm, op=dist.ReduceOp.MAX)
+        out["mdpocket"] = {"metric": "frames/sec", "value": F * world / float(mm[0]), "frames_per_gpu": F, "atoms": int(s5.n),
+                           "grid": [int(v) for v in dims], "includes": "H2D of every frame, detection, grid scatter, NCCL all-reduce of both grids"}
+        md.close()
+
+    # ---- CPU baseline: the unmodified reference on this box's cores, bounded sample ------------------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu:
+        nsample = args.ref_sample or max(ncores * 3, 48)
+        r, dt = reference_fpocket_rate(raw, min(nsample, len(raw)), ncores)
+        if r is not None:
+            out["cpu_baseline"] = {"value": r, "unit": "structures/s", "cores": ncores, "kind": "reference",
+                                   "sample": "first %d structures of the workload, one `fpocket -f` process each (oracle/_ref/fpocket, "
+                                             "the unmodified reference built with -O2), %d at a time, tmpfs; %.1f s" % (min(nsample, len(raw)), ncores, dt)}
+        else:
+            out["cpu_baseline"] = {"value": None, "unit": "structures/s", "cores": ncores, "kind": "reference", "sample": str(dt)}
+    batch.close()
+    if rank == 0:
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -487,6 +487,7 @@ FPK_HDN void phase_serial(DelaunayCtx &c)
     if (c.cnt[C_NFREE0 + popstack] < 0) c.cnt[C_NFREE0 + popstack] = 0;
     c.cnt[C_SUBROUND]++;
     c.cnt[C_NSUB]++;
+    if (c.cnt[C_NSUB] > 64 * c.n + 4096) c.cnt[C_STATUS] = DERR_WALK;     // cannot happen (the best-ranked point always wins); never spin
 }
 
 // chunk [lo,hi) of `order` handed to thread tid for a round [r0,r1)
