@@ -228,14 +228,14 @@ static size_t del_scratch_layout(Arena &a, DelScratch &x, int nmax, int scap, in
     x.P = a.take<double>(3 * (size_t)nmax);
     x.keys = a.take<unsigned long long>(npad);
     x.order = a.take<int>(nmax);
-    x.tv = a.take<int>(4 * (size_t)cap); x.tn = a.take<int>(4 * (size_t)cap);
-    x.own = a.take<int>(cap); x.rim = a.take<int>(cap); x.mark = a.take<int>(cap); x.cavpos = a.take<int>(cap);
+    x.tet = a.take<int>(8 * (size_t)cap); x.claim = a.take<int>(2 * (size_t)cap); x.mark = a.take<int>(2 * (size_t)cap);
     x.free0 = a.take<int>(cap); x.free1 = a.take<int>(cap);
     x.hint = a.take<int>(32 * 32 * 32);
-    x.cav = a.take<int>((size_t)nthreads * CAVMAX); x.newid = a.take<int>((size_t)nthreads * CAVMAX * 4);
-    x.tinfo = a.take<int>(4 * (size_t)nthreads); x.cursor = a.take<int>(2 * (size_t)nthreads);
+    const int nwarps = (nthreads + 31) / 32;
+    x.cav = a.take<int>((size_t)nwarps * CAVMAX); x.newid = a.take<int>((size_t)nwarps * CAVMAX * 4);
+    x.tinfo = a.take<int>(4 * (size_t)nwarps); x.cursor = a.take<int>(2 * (size_t)nwarps);
     x.bigcav = a.take<int>(cap); x.bignewid = a.take<int>(4 * (size_t)cap);
-    x.cnt = a.take<int>(C_COUNT); x.rstart = a.take<int>(40);
+    x.cnt = a.take<int>(C_COUNT); x.rstart = a.take<int>(40); x.rep = a.take<int>(nmax);
     x.scap = with_filter ? scap : 0;
     x.rawkey = a.take<int4>(with_filter ? scap : 1); x.rawxyzr = a.take<float4>(with_filter ? scap : 1);
     x.sitecnt = a.take<int>(with_filter ? nmax + 1 : 1); x.bucket = a.take<int>(with_filter ? scap : 1);
@@ -555,6 +555,7 @@ extern "C" long long fpk_batch_counter(const fpk_batch *b, int which)
     case 7: return b->d2h;
     case 8: { long long p = 0; for (int k = 0; k < b->n; k++) p += b->h_counts.empty() ? 0 : b->h_counts[(size_t)k * CNT_STRIDE + CNT_SUBROUNDS]; return p; }
     case 9: { long long p = 0; for (int k = 0; k < b->n; k++) p += b->h_counts.empty() ? 0 : b->h_counts[(size_t)k * CNT_STRIDE + CNT_RETRIES]; return p; }
+    case 10: { long long p = 0; for (int k = 0; k < b->n; k++) p += b->h_counts.empty() ? 0 : b->h_counts[(size_t)k * CNT_STRIDE + CNT_NBIG]; return p; }
     }
     return -1;
 }

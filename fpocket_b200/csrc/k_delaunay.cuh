@@ -14,12 +14,13 @@ struct DelScratch {
     double *P;                    // [3*nmax]
     unsigned long long *keys;     // [npad]
     int *order;                   // [nmax]
-    int *tv, *tn, *own, *rim, *mark, *cavpos, *free0, *free1;
+    int *tet, *claim, *mark, *free0, *free1;     // [8*cap], [2*cap], [2*cap], [cap], [cap]
     int cap;
     int *hint;                    // [32^3]
     int *cav, *newid, *tinfo, *cursor;
     int *bigcav, *bignewid;
     int *cnt;                     // [C_COUNT]
+    int *rep;                     // [nmax]
     int *rstart;                  // [32]
     int4 *rawkey;                 // [scap]
     float4 *rawxyzr;              // [scap]
@@ -163,37 +164,41 @@ __device__ int block_delaunay(DelaunayCtx &C, const DelScratch &X, int n, const 
     int hgc = 2;
     while (hgc < 32 && hgc * hgc * hgc * 2 < n) hgc++;
     for (int i = tid; i < hgc * hgc * hgc; i += nt) X.hint[i] = -1;
-    X.tinfo[4 * tid] = -1;
+    for (int i = tid; i < n; i += nt) X.rep[i] = i;
+    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    if (lane == 0) { X.tinfo[4 * wid] = -1; X.tinfo[4 * wid + 3] = -1; }
     __syncthreads();
     if (tid == 0) {
         for (int r = R - 1; r >= 0; r--) if (X.rstart[r] > X.rstart[r + 1]) X.rstart[r] = X.rstart[r + 1];
         X.rstart[0] = 0;
-        C.n = n; C.P = X.P; C.tv = X.tv; C.tn = X.tn; C.own = X.own; C.rim = X.rim; C.mark = X.mark; C.cavpos = X.cavpos;
+        C.n = n; C.P = X.P; C.tet = X.tet; C.claim = X.claim; C.mark = X.mark;
         C.cap = X.cap; C.cnt = X.cnt; C.freest[0] = X.free0; C.freest[1] = X.free1; C.order = X.order;
         C.hint = X.hint;
         C.hg = hgc; C.hinv = hgc / (ext * 1.0001);
         C.hmin[0] = bmn[0]; C.hmin[1] = bmn[1]; C.hmin[2] = bmn[2];
-        C.nthreads = nt; C.cav = X.cav; C.newid = X.newid; C.tinfo = X.tinfo; C.cursor = X.cursor;
-        C.bigcav = X.bigcav; C.bignewid = X.bignewid;
+        C.nworkers = nw; C.cav = X.cav; C.newid = X.newid; C.tinfo = X.tinfo; C.cursor = X.cursor;
+        C.bigcav = X.bigcav; C.bignewid = X.bignewid; C.rep = X.rep;
         delaunay_init(C, s_first4);
     }
     __syncthreads();
+    // rounds of concurrent insertions: one pending point per warp, phases separated by block barriers
     bool failed = C.cnt[C_STATUS] != 0;
     for (int r = 0; r < R && !failed; r++) {
-        round_chunk(X.rstart[r], X.rstart[r + 1], tid, nt, &X.cursor[2 * tid], &X.cursor[2 * tid + 1]);
+        if (lane == 0) round_chunk(X.rstart[r], X.rstart[r + 1], wid, nw, &X.cursor[2 * wid], &X.cursor[2 * wid + 1]);
+        __syncwarp();
         for (;;) {
-            int work = phase_assign(C, tid) ? 1 : 0;
+            int work = w_phase_assign(C, wid) ? 1 : 0;
             if (C.cnt[C_STATUS]) work = 0;
             if (!__syncthreads_or(work)) break;
-            phase_claim(C, tid);
+            w_phase_claim(C, wid);
             __syncthreads();
-            phase_verify(C, tid);
+            w_phase_verify(C, wid);
             __syncthreads();
-            phase_reset(C, tid);
+            w_phase_reset(C, wid);
             __syncthreads();
-            phase_commit(C, tid);
+            w_phase_commit(C, wid);
             __syncthreads();
-            if (tid == 0) phase_serial(C);
+            if (wid == 0) w_phase_serial(C);
             __syncthreads();
         }
         failed = C.cnt[C_STATUS] != 0;
@@ -242,6 +247,7 @@ __global__ void __launch_bounds__(256, FPK_K1_MINBLOCKS) k_delaunay_filter(Batch
             if (tid == 0) {
                 counts[CNT_TETS] = 0; counts[CNT_SPHERES] = 0;
                 counts[CNT_STATUS] = err == DERR_DEGENERATE ? FPK_ERR_DEGENERATE : FPK_ERR_CAPACITY;
+                counts[CNT_SUBROUNDS] = C.cnt[C_NSUB]; counts[CNT_RETRIES] = C.cnt[C_NRETRY]; counts[CNT_NBIG] = 1000 * err + C.cnt[C_NBIG];
             }
             continue;
         }
@@ -251,9 +257,9 @@ __global__ void __launch_bounds__(256, FPK_K1_MINBLOCKS) k_delaunay_filter(Batch
         for (int i = tid; i <= n; i += nt) X.sitecnt[i] = 0;
         __syncthreads();
         for (int t = tid; t < ntet; t += nt) {
-            int4 q = reinterpret_cast<const int4 *>(X.tv)[t];
+            int4 q = reinterpret_cast<const int4 *>(X.tet)[2 * (size_t)t];
             if (q.x < 0 || q.y < 0 || q.z < 0 || q.w < 0) continue;
-            int v[4] = {q.x, q.y, q.z, q.w};
+            int v[4] = {X.rep[q.x], X.rep[q.y], X.rep[q.z], X.rep[q.w]};       // coincident sites: lowest index
 #pragma unroll
             for (int i = 1; i < 4; i++) { int kk = v[i], j = i - 1; while (j >= 0 && v[j] > kk) { v[j + 1] = v[j]; j--; } v[j + 1] = kk; }
             int ord = atomicAdd(&s_red[1], 1);

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(HULL_THREADS, 8) k_hull_volume(BatchDev B, Poc
         i128 sum = 0;
         const int ntet = C.cnt[C_NTET];
         for (int t = tid; t < ntet; t += nt) {
-            int4 q = reinterpret_cast<const int4 *>(X.tv)[t];
+            int4 q = reinterpret_cast<const int4 *>(X.tet)[2 * (size_t)t];
             if (q.x < 0 || q.y < 0 || q.z < 0 || q.w < 0) continue;
             sum += orient3d_exact_det(X.P + 3 * (size_t)q.x, X.P + 3 * (size_t)q.y, X.P + 3 * (size_t)q.z, X.P + 3 * (size_t)q.w);
         }

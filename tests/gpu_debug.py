@@ -6,6 +6,7 @@ import golden_cases as G, oracle_lib as O
 from fpocket_b200 import api, capi
 case = sys.argv[1] if len(sys.argv) > 1 else "5WA6"
 d = G.load(case); st, p = G.inputs(d, want_tets=1)
+b = api.Batch([st], p); b.run(); print("counters: sub %d retries %d nbig/err %d" % (b.counter(8), b.counter(9), b.counter(10))); b.close()
 t0 = time.time(); r = api.detect(st, p); print("detect %.3fs status %d sites %d tets %d spheres %d clusters %d pockets %d" % (time.time()-t0, r["status"], r["n_sites"], r["n_tets"], r["n_spheres"], r["n_clusters"], r["n_pockets"]))
 q = O.canonicalize(d["qh.tets"]); print("tets equal qhull:", r["tets"] is not None and np.array_equal(r["tets"], q), len(q))
 o = O.search_pocket(st, p, tets=None, rng_mode=O.RNG_PHILOX)
