@@ -259,7 +259,8 @@ def main():
            "dtype": "f64 predicates/circumcentres + f32 descriptors (the reference's own mix)", "data": "synthetic", "config": cfg,
            "wall_ms_per_step": t_wall / args.steps * 1e3, "stage_ms_per_step": per_stage, "roofline": roof, "gpu_launches": int(launches),
            "totals_per_gpu": tot, "delaunay_subrounds_per_structure": subrounds / max(1, args.structures),
-           "delaunay_retries_per_site": retries / max(1, N), "clocks": clocks, "gen_s": t_gen}
+           "delaunay_retries_per_site": retries / max(1, N),
+           "delaunay_debug": {"attempts": batch.counter(13), "walk_steps_per_attempt": batch.counter(11) / max(1, batch.counter(13)), "bfs_levels_per_attempt": batch.counter(12) / max(1, batch.counter(13)), "dead_hops_per_attempt": batch.counter(14) / max(1, batch.counter(13)), "big": batch.counter(10)}, "clocks": clocks, "gen_s": t_gen}
 
     # ---- e2e: the public call with host buffers ---------------------------------------------------------------------------------
     if not args.no_e2e:

@@ -146,6 +146,7 @@ struct fpk_batch {
     BatchDev B;
     StructDev *dS = nullptr;
     DelScratch *dDel = nullptr; int nDel = 0;
+    int k1_picap = 0, hull_picap = 0; size_t k1_dsm = 0, hull_dsm = 0;   // shared-memory plan of the two Delaunay kernels
     ClusterScratch *dClu = nullptr; int nClu = 0;
     int *d_counters = nullptr;         // [8] work counters
     int *d_order = nullptr;
@@ -235,7 +236,7 @@ static size_t del_scratch_layout(Arena &a, DelScratch &x, int nmax, int scap, in
     x.cav = a.take<int>((size_t)nwarps * CAVMAX); x.newid = a.take<int>((size_t)nwarps * CAVMAX * 4);
     x.tinfo = a.take<int>(4 * (size_t)nwarps); x.cursor = a.take<int>(2 * (size_t)nwarps);
     x.bigcav = a.take<int>(cap); x.bignewid = a.take<int>(4 * (size_t)cap);
-    x.cnt = a.take<int>(C_COUNT); x.rstart = a.take<int>(40); x.rep = a.take<int>(nmax);
+    x.cnt = a.take<int>(C_COUNT); x.rstart = a.take<int>(40); x.rep = a.take<int>(nmax); x.Pi = a.take<int>(3 * (size_t)nmax);
     x.scap = with_filter ? scap : 0;
     x.rawkey = a.take<int4>(with_filter ? scap : 1); x.rawxyzr = a.take<float4>(with_filter ? scap : 1);
     x.sitecnt = a.take<int>(with_filter ? nmax + 1 : 1); x.bucket = a.take<int>(with_filter ? scap : 1);
@@ -265,9 +266,21 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
 {
     const int n = b->n;
     int occ1 = 2, occ3 = 4;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_delaunay_filter, 256, 0);
+    // K1 shared-memory plan: WarpCav records + the sites as int32 lattice offsets. Two blocks per SM when the largest
+    // structure fits in half an SM's shared memory, else one block, else the sites stay in global memory (pi_cap 0).
+    {
+        const size_t fixed = 8 * sizeof(WarpCav), stat = 2048, sm_total = 227 * 1024, per_block_reserved = 1024;
+        const size_t need = fixed + 12 * (size_t)b->max_sites + 16;
+        const size_t half = (sm_total - 2 * per_block_reserved) / 2 - stat, full = sm_total - per_block_reserved - stat;
+        if (need <= half) { b->k1_picap = b->max_sites; b->k1_dsm = need; }
+        else if (need <= full) { b->k1_picap = b->max_sites; b->k1_dsm = need; }
+        else { b->k1_picap = 0; b->k1_dsm = fixed; }
+        CK(cudaFuncSetAttribute(k_delaunay_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->k1_dsm));
+    }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_delaunay_filter, 256, b->k1_dsm);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_cluster, 256, 0);
     occ1 = std::max(1, std::min(occ1, 4)); occ3 = std::max(1, std::min(occ3, 4));
+    if (const char *e = getenv("FPK_K1_BLOCKS_PER_SM")) occ1 = std::max(1, std::min(occ1, atoi(e)));     // tuning knob (profiles/)
     b->nDel = std::max(1, std::min(n, g_sms * occ1));
     b->nClu = std::max(1, std::min(n, g_sms * occ3));
     std::vector<DelScratch> hDel(b->nDel);
@@ -364,7 +377,7 @@ static int batch_run(fpk_batch *b)
     CK(cudaMemsetAsync(b->d_counters, 0, sizeof(int) * 8));
     CK(cudaMemsetAsync(B.counts, 0, sizeof(int) * (size_t)n * CNT_STRIDE));
     CK(cudaEventRecord(b->ev[0]));
-    k_delaunay_filter<<<b->nDel, 256>>>(B, b->dDel);
+    k_delaunay_filter<<<b->nDel, 256, b->k1_dsm>>>(B, b->dDel, b->k1_picap);
     CK(cudaEventRecord(b->ev[1]));
     k_cluster<<<b->nClu, 256>>>(B, b->dClu, b->d_counters + 1);
     CK(cudaEventRecord(b->ev[2]));
@@ -388,7 +401,10 @@ static int batch_run(fpk_batch *b)
     b->tot_clusters = b->h_clbase[n]; b->tot_spheres = b->h_sbase[n]; b->tot_tets = tt;
     const long long NC = b->tot_clusters, NS = b->tot_spheres;
     int occH = 8, occD = 8;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occH, k_hull_volume, HULL_THREADS, 0);
+    b->hull_picap = std::min(max_ns, 1024);
+    b->hull_dsm = (HULL_THREADS / 32) * sizeof(WarpCav) + 12 * (size_t)b->hull_picap + 16;
+    CK(cudaFuncSetAttribute(k_hull_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->hull_dsm));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occH, k_hull_volume, HULL_THREADS, b->hull_dsm);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occD, k_descriptors, K4_THREADS, 0);
     occH = std::max(1, std::min(occH, 8)); occD = std::max(1, std::min(occD, 8));
     b->nHull = (int)std::max(1ll, std::min<long long>(NC, (long long)g_sms * occH));
@@ -425,7 +441,7 @@ static int batch_run(fpk_batch *b)
     // (the kernels compute R = sph_off + cl_off[c]; with sph_off replaced by sbase for these arrays). See PocketDev.
     CK(cudaEventRecord(b->ev[3]));
     if (NC > 0) {
-        if (full) { k_hull_volume<<<b->nHull, HULL_THREADS>>>(B, Pk, b->dHull, b->d_counters + 2); b->launches++; }
+        if (full) { k_hull_volume<<<b->nHull, HULL_THREADS, b->hull_dsm>>>(B, Pk, b->dHull, b->d_counters + 2, b->hull_picap); b->launches++; }
         CK(cudaEventRecord(b->ev[4]));
         k_descriptors<<<b->nDesc, K4_THREADS>>>(B, Pk, b->dDesc, b->d_counters + 3);
         CK(cudaEventRecord(b->ev[5]));
@@ -555,6 +571,7 @@ extern "C" long long fpk_batch_counter(const fpk_batch *b, int which)
     case 7: return b->d2h;
     case 8: { long long p = 0; for (int k = 0; k < b->n; k++) p += b->h_counts.empty() ? 0 : b->h_counts[(size_t)k * CNT_STRIDE + CNT_SUBROUNDS]; return p; }
     case 9: { long long p = 0; for (int k = 0; k < b->n; k++) p += b->h_counts.empty() ? 0 : b->h_counts[(size_t)k * CNT_STRIDE + CNT_RETRIES]; return p; }
+    case 11: case 12: case 13: case 14: { long long p = 0; for (int k = 0; k < b->n; k++) p += b->h_counts.empty() ? 0 : b->h_counts[(size_t)k * CNT_STRIDE + CNT_WALK + (which - 11)]; return p; }
     case 10: { long long p = 0; for (int k = 0; k < b->n; k++) p += b->h_counts.empty() ? 0 : b->h_counts[(size_t)k * CNT_STRIDE + CNT_NBIG]; return p; }
     }
     return -1;

@@ -20,7 +20,7 @@ struct StructDev {
 };
 
 enum { CNT_TETS = 0, CNT_SPHERES = 1, CNT_CLUSTERS = 2, CNT_POCKETS = 3, CNT_STATUS = 4, CNT_SUBROUNDS = 5, CNT_RETRIES = 6,
-       CNT_NBIG = 7, CNT_STRIDE = 8 };
+       CNT_NBIG = 7, CNT_WALK = 8, CNT_LEVELS = 9, CNT_ATTEMPTS = 10, CNT_HOPS = 11, CNT_STRIDE = 12 };
 
 struct BatchDev {
     int nstruct;

@@ -22,7 +22,7 @@ namespace fpk {
 enum { T_DEAD = -2, V_INF = -1, OWN_FREE = 0x7fffffff, CAVMAX = 192 };
 enum { ST_IDLE = 0, ST_CLAIMED = 1, ST_LOST = 2, ST_BIG = 3, ST_DUP = 4, ST_WIN = 5, ST_ERR = 6 };
 enum { C_NTET = 0, C_NFREE0 = 1, C_NFREE1 = 2, C_RECENT = 3, C_STATUS = 4, C_SUBROUND = 5, C_NDUP = 6, C_NBIG = 7,
-       C_NSUB = 8, C_NRETRY = 9, C_NEXACT = 10, C_COUNT = 16 };
+       C_NSUB = 8, C_NRETRY = 9, C_NEXACT = 10, C_NWALK = 11, C_NLEVEL = 12, C_NATTEMPT = 13, C_NHOP = 14, C_COUNT = 16 };
 enum { DERR_NONE = 0, DERR_DEGENERATE = 1, DERR_CAPACITY = 2, DERR_WALK = 3, DERR_ROTATE = 4 };
 
 struct DelaunayCtx {
@@ -46,6 +46,7 @@ struct DelaunayCtx {
     int *bigcav, *bignewid;   // [cap], [4*cap]: serial path for cavities > CAVMAX
     int first4[4];      // sites of the initial simplex (skipped by phase_assign)
     int *rep;           // [n] representative of every site: lowest index among coincident sites (identity when all distinct)
+    const int *Pi;      // [3n] lattice offsets from the bounding-box corner (shared memory when they fit): fast path of delaunay_warp.cuh
 };
 
 #define FPK_TV(c, t) ((c).tet + 8 * (size_t)(t))

@@ -1,0 +1,396 @@
+// Warp-cooperative fast path of the block Delaunay (device only): same claim / verify / commit protocol as
+// delaunay.cuh, laid out for the SM:
+//   * sites live in SHARED memory as int32 lattice offsets from the bounding-box corner (12 B/site; exact: the
+//     "%.6f" lattice of reference src/voronoi.c:130 in units of 1e-6 A), so a predicate costs LDS, not L2 trips;
+//   * the cavity of a warp's point (tet id, 4 vertices, 4 neighbours, rim-face mask) lives in shared memory; one
+//     BFS level = one round trip (claim pair + the 32-byte tet record of 8 x 4 neighbours, issued together);
+//   * the winners' new tets are linked to each other through a per-warp edge hash in shared memory (each internal
+//     face (p,a,b) is met by exactly two new tets) instead of rotating around rim edges through global memory;
+//   * counters, per-warp state and chunk cursors live in shared memory.
+// Cavities larger than WCAV tets take the serial path of delaunay.cuh (w_locate_and_claim / w_commit_insertion).
+#pragma once
+#include "delaunay.cuh"
+
+namespace fpk {
+
+enum { WCAV = 64, WHASH = 256 };
+#define FPK_HEMPTY 0xffffffffffffffffull
+
+struct WarpCav {                        // one per warp, shared memory
+    int4 v[WCAV];                       // vertices of cavity tet i
+    int4 n[WCAV];                       // neighbours of cavity tet i; after pass A of the commit, component q of a rim face holds the NEW tet
+    unsigned long long hkey[WHASH];     // edge hash: (lo+1) << 32 | (hi+1)
+    int hval[WHASH];                    // 4 * new tet + slot of the face waiting for its twin
+    int id[WCAV];
+    unsigned char rim[WCAV];            // bit q: face q of cavity tet i is on the rim (its neighbour stays)
+    unsigned short rl[2 * WCAV + 8];    // compact list of rim faces (4 * i + q), filled by pass A of the commit
+};
+
+struct P3 { double x, y, z; };
+__device__ __forceinline__ P3 ldp(const int *Pi, int i)
+{
+    // 2^52 + offset, built by placing the (non-negative) offset in the low word: no conversion instruction. Predicates only
+    // use DIFFERENCES of coordinates, and (2^52 + a) - (2^52 + b) = a - b exactly.
+    const int *q = Pi + 3 * (size_t)i;
+    P3 r; r.x = __hiloint2double(0x43300000, q[0]); r.y = __hiloint2double(0x43300000, q[1]); r.z = __hiloint2double(0x43300000, q[2]);
+    return r;
+}
+__device__ __forceinline__ int comp4(const int4 &a, int q) { return q == 0 ? a.x : (q == 1 ? a.y : (q == 2 ? a.z : a.w)); }
+
+// ---- exact slow paths (rare): reload the lattice offsets, integer determinants ----------------------------------------
+__device__ __noinline__ int orient3d_slow(const int *Pi, int ia, int ib, int ic, int id)
+{
+    const int *a = Pi + 3 * (size_t)ia, *b = Pi + 3 * (size_t)ib, *c = Pi + 3 * (size_t)ic, *d = Pi + 3 * (size_t)id;
+    i128 adx = (long long)a[0] - d[0], ady = (long long)a[1] - d[1], adz = (long long)a[2] - d[2];
+    i128 bdx = (long long)b[0] - d[0], bdy = (long long)b[1] - d[1], bdz = (long long)b[2] - d[2];
+    i128 cdx = (long long)c[0] - d[0], cdy = (long long)c[1] - d[1], cdz = (long long)c[2] - d[2];
+    i128 e = adx * (bdy * cdz - bdz * cdy) + bdx * (cdy * adz - cdz * ady) + cdx * (ady * bdz - adz * bdy);
+    return e > 0 ? 1 : (e < 0 ? -1 : 0);
+}
+// same sign convention, filter and error bound as predicates.cuh orient3d (differences of lattice offsets are exact)
+__device__ __forceinline__ int orient3d_v(const int *Pi, int ia, int ib, int ic, int id, const P3 &a, const P3 &b, const P3 &c, const P3 &d)
+{
+    double adx = a.x - d.x, ady = a.y - d.y, adz = a.z - d.z;
+    double bdx = b.x - d.x, bdy = b.y - d.y, bdz = b.z - d.z;
+    double cdx = c.x - d.x, cdy = c.y - d.y, cdz = c.z - d.z;
+    double bdxcdy = bdx * cdy, cdxbdy = cdx * bdy, cdxady = cdx * ady, adxcdy = adx * cdy, adxbdy = adx * bdy, bdxady = bdx * ady;
+    double det = adz * (bdxcdy - cdxbdy) + bdz * (cdxady - adxcdy) + cdz * (adxbdy - bdxady);
+    double permanent = (fabs(bdxcdy) + fabs(cdxbdy)) * fabs(adz) + (fabs(cdxady) + fabs(adxcdy)) * fabs(bdz) +
+                       (fabs(adxbdy) + fabs(bdxady)) * fabs(cdz);
+    double errbound = 1.6e-15 * permanent;
+    if (det > errbound) return 1;
+    if (-det > errbound) return -1;
+    return orient3d_slow(Pi, ia, ib, ic, id);
+}
+
+// exact insphere with the symbolic perturbation of delaunay.cuh insphere_sos (points ordered by site index)
+__device__ __noinline__ int insphere_sos_slow(const int *Pi, int v0, int v1, int v2, int v3, int p)
+{
+    const int *a = Pi + 3 * (size_t)v0, *b = Pi + 3 * (size_t)v1, *c = Pi + 3 * (size_t)v2, *d = Pi + 3 * (size_t)v3, *e = Pi + 3 * (size_t)p;
+    i128 aex = (long long)a[0] - e[0], aey = (long long)a[1] - e[1], aez = (long long)a[2] - e[2];
+    i128 bex = (long long)b[0] - e[0], bey = (long long)b[1] - e[1], bez = (long long)b[2] - e[2];
+    i128 cex = (long long)c[0] - e[0], cey = (long long)c[1] - e[1], cez = (long long)c[2] - e[2];
+    i128 dex = (long long)d[0] - e[0], dey = (long long)d[1] - e[1], dez = (long long)d[2] - e[2];
+    i128 ab = aex * bey - bex * aey, bc = bex * cey - cex * bey, cd = cex * dey - dex * cey;
+    i128 da = dex * aey - aex * dey, ac = aex * cey - cex * aey, bd = bex * dey - dex * bey;
+    i128 abc = aez * bc - bez * ac + cez * ab;
+    i128 bcd = bez * cd - cez * bd + dez * bc;
+    i128 cda = cez * da + dez * ac + aez * cd;
+    i128 dab = dez * ab + aez * bd + bez * da;
+    i128 alift = aex * aex + aey * aey + aez * aez, blift = bex * bex + bey * bey + bez * bez;
+    i128 clift = cex * cex + cey * cey + cez * cez, dlift = dex * dex + dey * dey + dez * dez;
+    I256 acc;
+    acc.w[0] = acc.w[1] = acc.w[2] = acc.w[3] = 0;
+    i256_add_prod(acc, dlift, abc, false);
+    i256_add_prod(acc, clift, dab, true);
+    i256_add_prod(acc, blift, cda, false);
+    i256_add_prod(acc, alift, bcd, true);
+    int r = i256_sign(acc);
+    if (r) return r;
+    int v[4] = {v0, v1, v2, v3};
+    int idx[5] = {v0, v1, v2, v3, p};
+    for (int i = 1; i < 5; i++) {
+        int k = idx[i], j = i - 1;
+        while (j >= 0 && idx[j] > k) { idx[j + 1] = idx[j]; j--; }
+        idx[j + 1] = k;
+    }
+    for (int i = 4; i > 0; i--) {
+        int q = idx[i], o;
+        if (q == p) return -1;
+        if (q == v[3] && (o = orient3d_slow(Pi, v[0], v[1], v[2], p)) != 0) return o;
+        if (q == v[2] && (o = orient3d_slow(Pi, v[0], v[1], p, v[3])) != 0) return o;
+        if (q == v[1] && (o = orient3d_slow(Pi, v[0], p, v[2], v[3])) != 0) return o;
+        if (q == v[0] && (o = orient3d_slow(Pi, p, v[1], v[2], v[3])) != 0) return o;
+    }
+    return -1;
+}
+
+// > 0: p strictly inside the (perturbed) circumsphere of the positively oriented finite tet v
+__device__ __forceinline__ int insphere_sos_v(const int *Pi, const int4 &v, int p, const P3 &e)
+{
+    const P3 a = ldp(Pi, v.x), b = ldp(Pi, v.y), c = ldp(Pi, v.z), d = ldp(Pi, v.w);
+    double aex = a.x - e.x, aey = a.y - e.y, aez = a.z - e.z;
+    double bex = b.x - e.x, bey = b.y - e.y, bez = b.z - e.z;
+    double cex = c.x - e.x, cey = c.y - e.y, cez = c.z - e.z;
+    double dex = d.x - e.x, dey = d.y - e.y, dez = d.z - e.z;
+    double aexbey = aex * bey, bexaey = bex * aey, ab = aexbey - bexaey;
+    double bexcey = bex * cey, cexbey = cex * bey, bc = bexcey - cexbey;
+    double cexdey = cex * dey, dexcey = dex * cey, cd = cexdey - dexcey;
+    double dexaey = dex * aey, aexdey = aex * dey, da = dexaey - aexdey;
+    double aexcey = aex * cey, cexaey = cex * aey, ac = aexcey - cexaey;
+    double bexdey = bex * dey, dexbey = dex * bey, bd = bexdey - dexbey;
+    double abc = aez * bc - bez * ac + cez * ab;
+    double bcd = bez * cd - cez * bd + dez * bc;
+    double cda = cez * da + dez * ac + aez * cd;
+    double dab = dez * ab + aez * bd + bez * da;
+    double alift = aex * aex + aey * aey + aez * aez, blift = bex * bex + bey * bey + bez * bez;
+    double clift = cex * cex + cey * cey + cez * cez, dlift = dex * dex + dey * dey + dez * dez;
+    double det = (dlift * abc - clift * dab) + (blift * cda - alift * bcd);
+    double az = fabs(aez), bz = fabs(bez), cz = fabs(cez), dz = fabs(dez);
+    double pab = fabs(aexbey) + fabs(bexaey), pbc = fabs(bexcey) + fabs(cexbey), pcd = fabs(cexdey) + fabs(dexcey);
+    double pda = fabs(dexaey) + fabs(aexdey), pac = fabs(aexcey) + fabs(cexaey), pbd = fabs(bexdey) + fabs(dexbey);
+    double permanent = (pcd * bz + pbd * cz + pbc * dz) * alift + (pda * cz + pac * dz + pcd * az) * blift +
+                       (pab * dz + pbd * az + pda * bz) * clift + (pbc * az + pac * bz + pab * cz) * dlift;
+    double errbound = 3.6e-15 * permanent;
+    if (det > errbound) return 1;
+    if (-det > errbound) return -1;
+    return insphere_sos_slow(Pi, v.x, v.y, v.z, v.w, p);
+}
+
+// orientation of tet v with the vertex in `slot` replaced by p (all four of v finite except possibly v[slot])
+__device__ __forceinline__ int orient_sub_v(const int *Pi, const int4 &v, int slot, int p, const P3 &pp)
+{
+    const int i0 = slot == 0 ? p : v.x, i1 = slot == 1 ? p : v.y, i2 = slot == 2 ? p : v.z, i3 = slot == 3 ? p : v.w;
+    const P3 a = slot == 0 ? pp : ldp(Pi, i0), b = slot == 1 ? pp : ldp(Pi, i1), c = slot == 2 ? pp : ldp(Pi, i2), d = slot == 3 ? pp : ldp(Pi, i3);
+    return orient3d_v(Pi, i0, i1, i2, i3, a, b, c, d);
+}
+
+__device__ __forceinline__ int inf_slot4(const int4 &v) { return v.x < 0 ? 0 : (v.y < 0 ? 1 : (v.z < 0 ? 2 : (v.w < 0 ? 3 : -1))); }
+
+// in_conflict of delaunay.cuh on the shared-memory sites; xn = neighbours of the tet (needed for a ghost whose facet plane holds p)
+__device__ __forceinline__ bool in_conflict_v(const DelaunayCtx &c, const int *Pi, const int4 &v, const int4 &xn, int p, const P3 &pp)
+{
+    const int k = inf_slot4(v);
+    if (k < 0) return insphere_sos_v(Pi, v, p, pp) > 0;
+    const int o = orient_sub_v(Pi, v, k, p, pp);
+    if (o) return o > 0;
+    const int4 w = *reinterpret_cast<const int4 *>(FPK_TV(c, comp4(xn, k)));
+    return insphere_sos_v(Pi, w, p, pp) > 0;
+}
+
+__device__ __forceinline__ int2 ldcg2(const int *p) { return __ldcg(reinterpret_cast<const int2 *>(p)); }
+
+// ---- claim phase: locate the point, flood its cavity while claiming it (all 32 lanes, identical arguments) ------------------------
+__device__ __noinline__ int w2_locate_and_claim(DelaunayCtx &c, WarpCav &W, const int *Pi, int rank, int own_hint, int *ncav_out)
+{
+    const int lane = threadIdx.x & 31;
+    const int p = c.order[rank];
+    const int prio = prio_of(rank);
+    const P3 pp = ldp(Pi, p);
+    *ncav_out = 0;
+    int t = own_hint;
+    if (t < 0) {
+        const int g = c.hg;
+        const int *e = Pi + 3 * (size_t)p;
+        int ix = (int)((double)e[0] * c.hinv), iy = (int)((double)e[1] * c.hinv), iz = (int)((double)e[2] * c.hinv);
+        ix = ix < 0 ? 0 : (ix >= g ? g - 1 : ix); iy = iy < 0 ? 0 : (iy >= g ? g - 1 : iy); iz = iz < 0 ? 0 : (iz >= g ? g - 1 : iz);
+        t = c.hint[(ix * g + iy) * g + iz];
+    }
+    if (t < 0) t = c.cnt[C_RECENT];
+    int hops = 0;
+    for (int hop = 0; hop < 64 && FPK_TV(c, t)[0] == T_DEAD; hop++) { t = FPK_TN(c, t)[0]; hops++; }
+    if (hops && lane == 0) atomicAdd(&c.cnt[C_NHOP], hops);
+    if (FPK_TV(c, t)[0] == T_DEAD) {
+        t = c.cnt[C_RECENT];
+        for (int hop = 0; hop < 64 && FPK_TV(c, t)[0] == T_DEAD; hop++) t = FPK_TN(c, t)[0];
+        if (FPK_TV(c, t)[0] == T_DEAD) return ST_ERR;
+    }
+    int4 v, nb;
+    const int maxsteps = c.cnt[C_NTET] + 64;
+    for (int steps = 0;; steps++) {         // visibility walk: the four face tests of a step run on four lanes
+        if (steps > maxsteps) return ST_ERR;
+        v = *reinterpret_cast<const int4 *>(FPK_TV(c, t));
+        nb = *reinterpret_cast<const int4 *>(FPK_TN(c, t));
+        const int k = inf_slot4(v);
+        if (k >= 0) {
+            if (in_conflict_v(c, Pi, v, nb, p, pp)) break;
+            t = comp4(nb, k);
+            continue;
+        }
+        int o = 1;
+        bool dup = false;
+        if (lane < 4) {
+            const int *q = Pi + 3 * (size_t)comp4(v, lane), *e = Pi + 3 * (size_t)p;
+            dup = q[0] == e[0] && q[1] == e[1] && q[2] == e[2];
+            o = orient_sub_v(Pi, v, lane, p, pp);
+        }
+        const unsigned dupm = __ballot_sync(FPK_FULL, dup) & 0xfu, neg = __ballot_sync(FPK_FULL, o < 0) & 0xfu;
+        if (dupm) { *ncav_out = comp4(v, __ffs(dupm) - 1); return ST_DUP; }      // coincident site: reports the vertex it duplicates
+        if (!neg) { if (lane == 0) { atomicAdd(&c.cnt[C_NWALK], steps + 1); atomicAdd(&c.cnt[C_NATTEMPT], 1); } break; }
+        t = comp4(nb, __ffs(neg) - 1);
+    }
+    int st = ST_CLAIMED;
+    if (lane == 0) {
+        if (__ldcg(FPK_RIM(c, t)) < prio) st = ST_LOST;
+        else if (atomicMin(FPK_OWN(c, t), prio) < prio) st = ST_LOST;
+        else { W.id[0] = t; W.v[0] = v; W.n[0] = nb; }
+    }
+    st = __shfl_sync(FPK_FULL, st, 0);
+    if (st == ST_LOST) return ST_LOST;
+    __syncwarp();
+    int ncav = 1, nlev = 0;
+    for (int head = 0; head < ncav;) {      // breadth-first: 8 frontier tets x 4 faces per step
+        const int room = (WCAV - ncav) >> 2;                            // every claimed tet must fit in the list (the reset walks it)
+        if (room < 1) { *ncav_out = ncav; return ST_BIG; }
+        const int f = head + (lane >> 2), q = lane & 3;
+        head = min(head + min(8, room), ncav);
+        const bool active = f < head;
+        bool lost = false, add = false, isrim = false;
+        int x = -1;
+        int4 xv, xn;
+        if (active) {
+            x = reinterpret_cast<const int *>(&W.n[f])[q];
+            const int2 cl = ldcg2(FPK_OWN(c, x));                       // one round trip: claim pair and the tet record together
+            xv = *reinterpret_cast<const int4 *>(FPK_TV(c, x));
+            xn = *reinterpret_cast<const int4 *>(FPK_TN(c, x));
+            if (cl.x < prio) lost = true;                               // in (or next to) a stronger cavity
+            else if (cl.x == prio) isrim = false;                       // already in my cavity: interior face
+            else if (cl.y == prio) isrim = true;                        // already known as my rim
+            else if (in_conflict_v(c, Pi, xv, xn, p, pp)) {
+                if (cl.y < prio) lost = true;                           // a stronger insertion rewrites x's adjacency
+                else {
+                    const int old = atomicMin(FPK_OWN(c, x), prio);
+                    if (old < prio) lost = true;
+                    else if (old != prio) add = true;                   // exactly one lane sees the transition to prio
+                }
+            } else {
+                atomicMin(FPK_RIM(c, x), prio);
+                isrim = true;
+            }
+        }
+        const unsigned addm = __ballot_sync(FPK_FULL, add), lostm = __ballot_sync(FPK_FULL, lost), rimm = __ballot_sync(FPK_FULL, isrim);
+        if (add) {
+            const int pos = ncav + __popc(addm & ((1u << lane) - 1u));
+            W.id[pos] = x; W.v[pos] = xv; W.n[pos] = xn;
+        }
+        if (active && q == 0) W.rim[f] = (unsigned char)((rimm >> lane) & 0xfu);
+        ncav += __popc(addm);
+        nlev++;
+        __syncwarp();
+        if (lostm) { *ncav_out = ncav; return ST_LOST; }
+    }
+    if (lane == 0) atomicAdd(&c.cnt[C_NLEVEL], nlev);
+    *ncav_out = ncav;
+    return ST_CLAIMED;
+}
+
+__device__ __forceinline__ bool w2_verify_claims(const DelaunayCtx &c, const WarpCav &W, int rank, int ncav)
+{
+    const int lane = threadIdx.x & 31, prio = prio_of(rank), q = lane & 3;
+    bool ok = true;
+    for (int base = 0; base < ncav; base += 8) {
+        const int f = base + (lane >> 2);
+        if (f < ncav) {
+            if (__ldcg(FPK_OWN(c, reinterpret_cast<const int *>(&W.n[f])[q])) < prio) ok = false;           // rim tet inside a stronger cavity
+            if (q == 0) { const int2 cl = ldcg2(FPK_OWN(c, W.id[f])); if (cl.x != prio || cl.y < prio) ok = false; }
+        }
+    }
+    return __all_sync(FPK_FULL, ok);
+}
+
+__device__ __forceinline__ void w2_reset_claims(DelaunayCtx &c, const WarpCav &W, int ncav)
+{
+    const int lane = threadIdx.x & 31, q = lane & 3;
+    for (int base = 0; base < ncav; base += 8) {
+        const int f = base + (lane >> 2);
+        if (f < ncav) {
+            *reinterpret_cast<int2 *>(FPK_OWN(c, reinterpret_cast<const int *>(&W.n[f])[q])) = make_int2(OWN_FREE, OWN_FREE);
+            if (q == 0) *reinterpret_cast<int2 *>(FPK_OWN(c, W.id[f])) = make_int2(OWN_FREE, OWN_FREE);
+        }
+    }
+}
+
+// a winner replaces its cavity (in W) by the star of p. Returns a new tet (the warp's next walk starts there) or -1.
+__device__ __noinline__ int w2_commit_insertion(DelaunayCtx &c, WarpCav &W, int rank, int ncav, int popstack)
+{
+    const int lane = threadIdx.x & 31;
+    const int p = c.order[rank];
+    for (int i = lane; i < WHASH; i += 32) { W.hkey[i] = FPK_HEMPTY; W.hval[i] = -1; }
+    __syncwarp();
+    int mynew = 0x7fffffff, nrim = 0;
+    bool bad = false;
+    // ---- pass A: one new tet per rim face (slots allocated warp-wide), outside adjacency both ways ----------------------------------
+    for (int base = 0; base < 4 * ncav; base += 32) {
+        const int e = base + lane, f = e >> 2, q = e & 3;
+        const bool isrim = e < 4 * ncav && ((W.rim[f] >> q) & 1);
+        const unsigned m = __ballot_sync(FPK_FULL, isrim);
+        if (!m) continue;
+        const int cnt = __popc(m), my = __popc(m & ((1u << lane) - 1u));
+        int fb = 0;
+        if (lane == 0) fb = atomicAdd(&c.cnt[C_NFREE0 + popstack], -cnt);
+        fb = __shfl_sync(FPK_FULL, fb, 0);
+        const int fi = fb - 1 - my;                                          // index into the free stack, < 0: take a fresh slot
+        const unsigned fresh = __ballot_sync(FPK_FULL, isrim && fi < 0);
+        int nbase = 0;
+        if (fresh && lane == 0) nbase = atomicAdd(&c.cnt[C_NTET], __popc(fresh));
+        nbase = __shfl_sync(FPK_FULL, nbase, 0);
+        if (isrim) {
+            int nt = fi >= 0 ? c.freest[popstack][fi] : nbase + __popc(fresh & ((1u << lane) - 1u));
+            if (nt >= c.cap) { bad = true; nt = -1; }
+            if (nt >= 0) {
+                const int cur = W.id[f];
+                const int4 v = W.v[f];
+                const int o = reinterpret_cast<const int *>(&W.n[f])[q];
+                int4 nv = v;
+                if (q == 0) nv.x = p; else if (q == 1) nv.y = p; else if (q == 2) nv.z = p; else nv.w = p;
+                *reinterpret_cast<int4 *>(FPK_TV(c, nt)) = nv;
+                FPK_TN(c, nt)[q] = o;
+                *reinterpret_cast<int2 *>(FPK_OWN(c, nt)) = make_int2(OWN_FREE, OWN_FREE);
+                const int4 ov = *reinterpret_cast<const int4 *>(FPK_TV(c, o)), on = *reinterpret_cast<const int4 *>(FPK_TN(c, o));
+                // the slot of o that faced cur through this face: its vertex there is the one of o that is not on the face
+                const int vq = reinterpret_cast<const int *>(&W.v[f])[q];
+                int r = -1;
+                if (on.x == cur && ov.x != v.x && ov.x != v.y && ov.x != v.z && ov.x != v.w) r = 0;
+                else if (on.y == cur && ov.y != v.x && ov.y != v.y && ov.y != v.z && ov.y != v.w) r = 1;
+                else if (on.z == cur && ov.z != v.x && ov.z != v.y && ov.z != v.z && ov.z != v.w) r = 2;
+                else if (on.w == cur && ov.w != v.x && ov.w != v.y && ov.w != v.z && ov.w != v.w) r = 3;
+                if (r < 0) {                                                    // o's apex coincides with v[q] only in the 5-tet start complex
+                    if (on.x == cur && ov.x == vq) r = 0; else if (on.y == cur && ov.y == vq) r = 1;
+                    else if (on.z == cur && ov.z == vq) r = 2; else if (on.w == cur && ov.w == vq) r = 3;
+                }
+                if (r >= 0) FPK_TN(c, o)[r] = nt; else bad = true;
+                reinterpret_cast<int *>(&W.n[f])[q] = nt;
+                W.rl[nrim + my] = (unsigned short)e;
+                mynew = min(mynew, nt);
+            }
+        }
+        nrim += cnt;
+    }
+    if (__any_sync(FPK_FULL, bad)) { if (lane == 0) c.cnt[C_STATUS] = DERR_CAPACITY; return -1; }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mynew = min(mynew, __shfl_xor_sync(FPK_FULL, mynew, d));
+    const int firstnew = mynew;
+    __syncwarp();
+    // ---- pass B: one lane per (new tet, face through p): twins meet through the edge hash ---------------------------------------------
+    for (int it = lane; it < 3 * nrim; it += 32) {
+        const int ri = it / 3, jj = it - 3 * ri;
+        const int e = W.rl[ri], f = e >> 2, q = e & 3;
+        const int *vv = reinterpret_cast<const int *>(&W.v[f]);
+        const int j = (q + 1 + jj) & 3;                                         // slot of the new tet whose opposite face holds p
+        const int a = vv[(q + 1 + ((jj + 1) % 3)) & 3], b = vv[(q + 1 + ((jj + 2) % 3)) & 3];      // the rim edge of that face
+        const int nt = reinterpret_cast<const int *>(&W.n[f])[q];
+        const unsigned lo = (unsigned)(min(a, b) + 1), hi = (unsigned)(max(a, b) + 1);
+        const unsigned long long key = ((unsigned long long)lo << 32) | hi;
+        unsigned slot = (lo * 0x9E3779B1u ^ hi * 0x85EBCA77u) >> 11;
+        for (int probe = 0; probe < WHASH; probe++, slot++) {
+            slot &= WHASH - 1;
+            const unsigned long long old = atomicCAS(&W.hkey[slot], FPK_HEMPTY, key);
+            if (old == FPK_HEMPTY || old == key) break;
+        }
+        const int prev = atomicExch(&W.hval[slot], 4 * nt + j);
+        if (prev >= 0) { FPK_TN(c, nt)[j] = prev >> 2; FPK_TN(c, prev >> 2)[prev & 3] = nt; }
+    }
+    __syncwarp();
+    // ---- pass C: the cavity dies; its slots go to the stack the NEXT sub-round pops ---------------------------------------------------
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&c.cnt[C_NFREE0 + (popstack ^ 1)], ncav);
+    base = __shfl_sync(FPK_FULL, base, 0);
+    int *pushst = c.freest[popstack ^ 1];
+    for (int i = lane; i < ncav; i += 32) {
+        const int cur = W.id[i];
+        FPK_TV(c, cur)[0] = T_DEAD;
+        FPK_TN(c, cur)[0] = firstnew;
+        pushst[base + i] = cur;
+    }
+    if (lane == 0) {
+        const int g = c.hg;
+        const int *e = c.Pi + 3 * (size_t)p;
+        int ix = (int)((double)e[0] * c.hinv), iy = (int)((double)e[1] * c.hinv), iz = (int)((double)e[2] * c.hinv);
+        ix = ix < 0 ? 0 : (ix >= g ? g - 1 : ix); iy = iy < 0 ? 0 : (iy >= g ? g - 1 : iy); iz = iz < 0 ? 0 : (iz >= g ? g - 1 : iz);
+        c.hint[(ix * g + iy) * g + iz] = firstnew;
+        c.cnt[C_RECENT] = firstnew;
+    }
+    return firstnew;
+}
+
+}  // namespace fpk

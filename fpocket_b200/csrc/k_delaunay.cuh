@@ -6,7 +6,7 @@
 // :969-1087 testVvertice and :892-916 set_barycenter.
 #pragma once
 #include "common.cuh"
-#include "delaunay.cuh"
+#include "delaunay_warp.cuh"
 
 namespace fpk {
 
@@ -21,6 +21,7 @@ struct DelScratch {
     int *bigcav, *bignewid;
     int *cnt;                     // [C_COUNT]
     int *rep;                     // [nmax]
+    int *Pi;                      // [3*nmax] lattice offsets when they do not fit in shared memory
     int *rstart;                  // [32]
     int4 *rawkey;                 // [scap]
     float4 *rawxyzr;              // [scap]
@@ -139,18 +140,55 @@ __device__ void block_bbox(const double *P, int n, double *s_box, double (*s_bmi
     __syncthreads();
 }
 
-// Delaunay triangulation of the n lattice points in X.P by the whole block. C = context in shared memory.
-// Returns 0 or a DERR_* code (uniform over the block). On return the mesh is in X.tv/X.tn, C.cnt[C_NTET] slots.
-__device__ int block_delaunay(DelaunayCtx &C, const DelScratch &X, int n, const double *s_box, int *s_first4)
+// Shared-memory state of one block's triangulation (static part; the WarpCav records and the sites are dynamic)
+enum { FPK_MAXWARPS = 8 };
+struct BlockDel {
+    DelaunayCtx C;
+    int cnt[C_COUNT];
+    int tinfo[4 * FPK_MAXWARPS], cursor[2 * FPK_MAXWARPS];
+    int first4[4];
+    int bigw;
+};
+
+// the serial path for one over-sized cavity (warp w alone, the rest of the block waits): global lists, delaunay.cuh
+__device__ __forceinline__ void w_big_insert(DelaunayCtx &c, int w)
 {
+    const int lane = threadIdx.x & 31;
+    const int popstack = c.cnt[C_SUBROUND] & 1;
+    int *ti = c.tinfo + 4 * w;
+    int ncav = 0;
+    int st = w_locate_and_claim(c, ti[0], ti[3], c.bigcav, c.cap, &ncav);
+    __syncwarp();
+    w_reset_claims(c, c.bigcav, ncav);
+    __syncwarp();
+    int nt = -1;
+    if (st == ST_CLAIMED) nt = w_commit_insertion(c, ti[0], c.bigcav, c.bignewid, ncav, popstack);
+    __syncwarp();
+    if (lane == 0) {
+        if (st == ST_CLAIMED) ti[3] = nt;
+        else if (st != ST_DUP) c.cnt[C_STATUS] = DERR_CAPACITY;
+        c.cnt[C_NBIG]++;
+        ti[0] = -1;
+    }
+    __syncwarp();
+}
+
+// Delaunay triangulation of the n lattice points in X.P by the whole block (blockDim.x / 32 <= FPK_MAXWARPS warps).
+// S = static shared state, Wall = one WarpCav per warp (shared), Pi_sm / pi_cap = shared buffer for the sites.
+// Returns 0 or a DERR_* code (uniform over the block). On return the mesh is in X.tet, S.cnt[C_NTET] slots.
+__device__ int block_delaunay(BlockDel &S, WarpCav *Wall, int *Pi_sm, int pi_cap, const DelScratch &X, int n, const double *s_box)
+{
+    DelaunayCtx &C = S.C;
     const int tid = threadIdx.x, nt = blockDim.x;
     const double bmn[3] = {s_box[0], s_box[1], s_box[2]};
     const double ext = fmax(1.0, fmax(s_box[3] - s_box[0], fmax(s_box[4] - s_box[1], s_box[5] - s_box[2])));
     const int R = brio_nrounds(n);
     int npad = 1;
     while (npad < n) npad <<= 1;
+    int *Pi = n <= pi_cap ? Pi_sm : X.Pi;
     for (int i = tid; i < npad; i += nt)
         X.keys[i] = i < n ? brio_key(i, X.P + 3 * (size_t)i, bmn, 1023.999 / ext, R) : ~0ull;
+    for (int i = tid; i < 3 * n; i += nt) Pi[i] = (int)(X.P[i] - bmn[i % 3]);        // exact: integers, extent checked below
     __syncthreads();
     block_bitonic_sort(X.keys, npad);
     if (tid <= R) X.rstart[tid] = n;
@@ -166,56 +204,81 @@ __device__ int block_delaunay(DelaunayCtx &C, const DelScratch &X, int n, const 
     for (int i = tid; i < hgc * hgc * hgc; i += nt) X.hint[i] = -1;
     for (int i = tid; i < n; i += nt) X.rep[i] = i;
     const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-    if (lane == 0) { X.tinfo[4 * wid] = -1; X.tinfo[4 * wid + 3] = -1; }
+    if (lane == 0) { S.tinfo[4 * wid] = -1; S.tinfo[4 * wid + 3] = -1; }
     __syncthreads();
     if (tid == 0) {
         for (int r = R - 1; r >= 0; r--) if (X.rstart[r] > X.rstart[r + 1]) X.rstart[r] = X.rstart[r + 1];
         X.rstart[0] = 0;
-        C.n = n; C.P = X.P; C.tet = X.tet; C.claim = X.claim; C.mark = X.mark;
-        C.cap = X.cap; C.cnt = X.cnt; C.freest[0] = X.free0; C.freest[1] = X.free1; C.order = X.order;
+        C.n = n; C.P = X.P; C.Pi = Pi; C.tet = X.tet; C.claim = X.claim; C.mark = X.mark;
+        C.cap = X.cap; C.cnt = S.cnt; C.freest[0] = X.free0; C.freest[1] = X.free1; C.order = X.order;
         C.hint = X.hint;
         C.hg = hgc; C.hinv = hgc / (ext * 1.0001);
         C.hmin[0] = bmn[0]; C.hmin[1] = bmn[1]; C.hmin[2] = bmn[2];
-        C.nworkers = nw; C.cav = X.cav; C.newid = X.newid; C.tinfo = X.tinfo; C.cursor = X.cursor;
+        C.nworkers = nw; C.cav = X.cav; C.newid = X.newid; C.tinfo = S.tinfo; C.cursor = S.cursor;
         C.bigcav = X.bigcav; C.bignewid = X.bignewid; C.rep = X.rep;
-        delaunay_init(C, s_first4);
+        delaunay_init(C, S.first4);
+        if (ext > 2.0e9) S.cnt[C_STATUS] = DERR_CAPACITY;          // lattice offsets must fit in 31 bits (> 2000 A across: not a molecule)
+        S.bigw = 1 << 30;
     }
     __syncthreads();
-    // rounds of concurrent insertions: one pending point per warp, phases separated by block barriers
-    bool failed = C.cnt[C_STATUS] != 0;
+    // rounds of concurrent insertions: one pending point per warp, four block barriers per sub-round
+    WarpCav &W = Wall[wid];
+    int *ti = S.tinfo + 4 * wid;
+    bool failed = S.cnt[C_STATUS] != 0;
     for (int r = 0; r < R && !failed; r++) {
-        if (lane == 0) round_chunk(X.rstart[r], X.rstart[r + 1], wid, nw, &X.cursor[2 * wid], &X.cursor[2 * wid + 1]);
+        if (lane == 0) round_chunk(X.rstart[r], X.rstart[r + 1], wid, nw, &S.cursor[2 * wid], &S.cursor[2 * wid + 1]);
         __syncwarp();
         for (;;) {
             int work = w_phase_assign(C, wid) ? 1 : 0;
-            if (C.cnt[C_STATUS]) work = 0;
+            if (S.cnt[C_STATUS]) work = 0;
             if (!__syncthreads_or(work)) break;
-            w_phase_claim(C, wid);
+            // ---- claim: walk + cavity flood on a read-only mesh ----------------------------------------------------------
+            const int rank = work ? ti[0] : -1;
+            int st = ST_IDLE, ncav = 0;
+            if (rank >= 0) st = w2_locate_and_claim(C, W, Pi, rank, ti[3], &ncav);
             __syncthreads();
-            w_phase_verify(C, wid);
+            // ---- verify: a claimant wins iff nothing stronger touched its cavity or rim ---------------------------------
+            if (st == ST_CLAIMED) st = w2_verify_claims(C, W, rank, ncav) ? ST_WIN : ST_LOST;
             __syncthreads();
-            w_phase_reset(C, wid);
+            // ---- release the claims; winners rewrite the mesh concurrently --------------------------------------------
+            if (rank >= 0) {
+                if (st == ST_WIN || st == ST_LOST || st == ST_BIG) w2_reset_claims(C, W, ncav);
+                int newtet = -1;
+                if (st == ST_WIN) newtet = w2_commit_insertion(C, W, rank, ncav, S.cnt[C_SUBROUND] & 1);
+                __syncwarp();
+                if (lane == 0) {
+                    ti[1] = st; ti[2] = ncav;
+                    after_attempt(C, wid, newtet);
+                    if (st == ST_BIG) atomicMin(&S.bigw, wid);
+                }
+            }
             __syncthreads();
-            w_phase_commit(C, wid);
-            __syncthreads();
-            if (wid == 0) w_phase_serial(C);
-            __syncthreads();
+            if (S.bigw < nw) {                     // rare: at most one over-sized cavity per sub-round goes through the serial path
+                if (wid == S.bigw) w_big_insert(C, wid);
+                __syncthreads();
+                if (tid == 0) S.bigw = 1 << 30;
+            }
+            if (tid == 0) end_subround(C);
         }
-        failed = C.cnt[C_STATUS] != 0;
+        failed = S.cnt[C_STATUS] != 0;
     }
     __syncthreads();
-    return C.cnt[C_STATUS];
+    return S.cnt[C_STATUS];
 }
 
 #ifndef FPK_K1_MINBLOCKS
 #define FPK_K1_MINBLOCKS 2
 #endif
-__global__ void __launch_bounds__(256, FPK_K1_MINBLOCKS) k_delaunay_filter(BatchDev B, const DelScratch *scratch)
+__global__ void __launch_bounds__(256, FPK_K1_MINBLOCKS) k_delaunay_filter(BatchDev B, const DelScratch *scratch, int pi_cap)
 {
-    __shared__ DelaunayCtx C;
-    __shared__ int s_k, s_first4[4], s_red[40];
+    __shared__ BlockDel BD;
+    __shared__ int s_k, s_red[40];
     __shared__ double s_box[6];
     __shared__ double s_bmin[8][3], s_bmax[8][3];
+    extern __shared__ __align__(16) unsigned char fpk_dsm[];
+    WarpCav *Wall = reinterpret_cast<WarpCav *>(fpk_dsm);
+    int *Pi_sm = reinterpret_cast<int *>(fpk_dsm + (blockDim.x >> 5) * sizeof(WarpCav));
+    DelaunayCtx &C = BD.C;
     const int tid = threadIdx.x, nt = blockDim.x;
     const DelScratch &X = scratch[blockIdx.x];
 
@@ -242,7 +305,7 @@ __global__ void __launch_bounds__(256, FPK_K1_MINBLOCKS) k_delaunay_filter(Batch
         __syncthreads();
         block_bbox(X.P, n, s_box, s_bmin, s_bmax);
         // ---- 2.+3. insertion order, rounds of concurrent insertions --------------------------------------------------
-        const int err = block_delaunay(C, X, n, s_box, s_first4);
+        const int err = block_delaunay(BD, Wall, Pi_sm, pi_cap, X, n, s_box);
         if (err) {
             if (tid == 0) {
                 counts[CNT_TETS] = 0; counts[CNT_SPHERES] = 0;
@@ -291,6 +354,7 @@ __global__ void __launch_bounds__(256, FPK_K1_MINBLOCKS) k_delaunay_filter(Batch
         if (tid == 0) {
             counts[CNT_TETS] = s_red[1];
             counts[CNT_SUBROUNDS] = C.cnt[C_NSUB]; counts[CNT_RETRIES] = C.cnt[C_NRETRY]; counts[CNT_NBIG] = C.cnt[C_NBIG];
+            counts[CNT_WALK] = C.cnt[C_NWALK]; counts[CNT_LEVELS] = C.cnt[C_NLEVEL]; counts[CNT_ATTEMPTS] = C.cnt[C_NATTEMPT]; counts[CNT_HOPS] = C.cnt[C_NHOP];
         }
         if (ns > S.sph_cap || ns > X.scap) {
             if (tid == 0) { counts[CNT_SPHERES] = ns; counts[CNT_STATUS] = FPK_ERR_CAPACITY; }

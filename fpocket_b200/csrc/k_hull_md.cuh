@@ -11,10 +11,14 @@ namespace fpk {
 // (on the 1e-6 lattice the reference's "%.6f" text puts them on, voronoi.c:1256-1262); tet volumes are summed EXACTLY
 // (128-bit integers), so the result does not depend on thread timing.
 enum { HULL_THREADS = 64 };
-__global__ void __launch_bounds__(HULL_THREADS, 8) k_hull_volume(BatchDev B, PocketDev Pk, const DelScratch *scratch, int *work_counter)
+__global__ void __launch_bounds__(HULL_THREADS, 8) k_hull_volume(BatchDev B, PocketDev Pk, const DelScratch *scratch, int *work_counter, int pi_cap)
 {
-    __shared__ DelaunayCtx C;
-    __shared__ int s_item, s_first4[4];
+    __shared__ BlockDel BD;
+    __shared__ int s_item;
+    extern __shared__ __align__(16) unsigned char fpk_dsm[];
+    WarpCav *Wall = reinterpret_cast<WarpCav *>(fpk_dsm);
+    int *Pi_sm = reinterpret_cast<int *>(fpk_dsm + (HULL_THREADS / 32) * sizeof(WarpCav));
+    DelaunayCtx &C = BD.C;
     __shared__ double s_box[6];
     __shared__ double s_bmin[HULL_THREADS / 32][3], s_bmax[HULL_THREADS / 32][3];
     __shared__ long long s_hi[HULL_THREADS];
@@ -33,7 +37,7 @@ __global__ void __launch_bounds__(HULL_THREADS, 8) k_hull_volume(BatchDev B, Poc
         const StructDev S = B.S[k];
         const int *cl_off = B.cl_off + S.sph_off + k;
         const int off = cl_off[c], n = cl_off[c + 1] - off;
-        if (n < 10) continue;                                   // voronoi.c:1244: volume 0 (desc is zero-initialised)
+        if (n < 10 || n < B.prm.min_pock_nb_asph) continue;     // voronoi.c:1244: volume 0 (desc is zero-initialised); always-dropped clusters (refine.c:124) too
         const int *L = B.cl_sph + S.sph_off + off;
         const float4 *sx = B.s_xyzr + S.sph_off;
         for (int i = tid; i < n; i += nt) {
@@ -44,7 +48,7 @@ __global__ void __launch_bounds__(HULL_THREADS, 8) k_hull_volume(BatchDev B, Poc
         }
         __syncthreads();
         block_bbox(X.P, n, s_box, s_bmin, s_bmax);
-        const int err = block_delaunay(C, X, n, s_box, s_first4);
+        const int err = block_delaunay(BD, Wall, Pi_sm, pi_cap, X, n, s_box);
         if (err) { if (tid == 0) Pk.desc[item].convex_hull_volume = -1.0f; continue; }      // voronoi.c:1276-1279
         i128 sum = 0;
         const int ntet = C.cnt[C_NTET];

@@ -417,6 +417,8 @@ __global__ void __launch_bounds__(K4_THREADS) k_descriptors(BatchDev B, PocketDe
                 s_mcbox[0] = xmin; s_mcbox[1] = xmax; s_mcbox[2] = ymin; s_mcbox[3] = ymax; s_mcbox[4] = zmin; s_mcbox[5] = zmax;
             }
             for (int i = tid; i < 100; i += nt) s_cnt[i] = 0;
+            // a cluster below min_pock_nb_asph is always dropped (refine.c:124) and never written: no samples are spent on it
+            const bool observable = n >= prm.min_pock_nb_asph;
             const bool insm = n <= MC_SMEM_SPH;
             if (insm)
                 for (int i = tid; i < n; i += nt) { float4 v = sx[L[i]]; v.w = (correct + v.w) * (v.w + correct); s_sph[i] = v; }
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(K4_THREADS) k_descriptors(BatchDev B, PocketDe
                 const float xmin = s_mcbox[0], xmax = s_mcbox[1], ymin = s_mcbox[2], ymax = s_mcbox[3], zmin = s_mcbox[4], zmax = s_mcbox[5];
                 const int niter = prm.nb_mcv_iter;
                 const unsigned k0 = (unsigned)prm.mc_seed, k1 = (unsigned)(prm.mc_seed >> 32);
-                for (int s = tid; s < 100 * niter; s += nt) {
+                for (int s = tid; observable && s < 100 * niter; s += nt) {
                     const int li = s / niter, i = s - li * niter;
                     unsigned o[4];
                     philox4x32((unsigned)i, (unsigned)li, (unsigned)c, 0u, k0, k1, o);
@@ -565,7 +567,7 @@ __global__ void __launch_bounds__(K4_THREADS) k_descriptors(BatchDev B, PocketDe
                     const float vbox = (s_mcbox[1] - s_mcbox[0]) * (s_mcbox[3] - s_mcbox[2]) * (s_mcbox[5] - s_mcbox[4]);
                     float sum_volume = 0.0f;
                     for (int li = 0; li < 100; li++) sum_volume += ((float)s_cnt[li]) / ((float)prm.nb_mcv_iter) * vbox;
-                    d.volume = sum_volume / (float)100;
+                    d.volume = n >= prm.min_pock_nb_asph ? sum_volume / (float)100 : 0.0f;
                 }
                 d.as_max_dst = as_max_dst;
                 d.apolar_asphere_prop = (float)nAlphaApol / (float)n;

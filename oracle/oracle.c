@@ -464,8 +464,13 @@ static void set_descriptors(const fpk_structure *in, const fpk_params *p, const 
     else d->mean_loc_hyd_dens = 0.0f;
     if (p->do_asa_and_volume) {
         set_asa(in, S, idx, nvert, d, atom_fx, pts);
-        d->volume = mc_volume(S, idx, nvert, p->nb_mcv_iter, -1.6f, rng_mode, p->mc_seed, cluster);
-        d->convex_hull_volume = hull_volume(S, idx, nvert);
+        /* A cluster with fewer than min_pock_nb_asph spheres is always dropped (refine.c:124) and nothing of it is ever
+         * written, so the product (ORC_RNG_PHILOX semantics) does not spend 30,000 Monte-Carlo samples and a hull on it:
+         * volume = convex_hull_volume = 0 there. ORC_RNG_LIBC keeps the reference's behaviour exactly (it must: the libc
+         * rand() stream is consumed by every cluster, fpocket.c:183), which is what pins this file to the reference. */
+        int observable = rng_mode == ORC_RNG_LIBC || nvert >= p->min_pock_nb_asph;
+        d->volume = observable ? mc_volume(S, idx, nvert, p->nb_mcv_iter, -1.6f, rng_mode, p->mc_seed, cluster) : 0.0f;
+        d->convex_hull_volume = observable ? hull_volume(S, idx, nvert) : 0.0f;
     }
     d->as_max_dst = as_max_dst;
     d->apolar_asphere_prop = (float)nAlphaApol / (float)nvert;
