@@ -59,6 +59,24 @@ def detect_batch(structures, params=None):
     return out
 
 
+def detect_batch_raw(structures, params=None, c_array=None):
+    """fpk_detect_batch without copying the results into numpy: returns (ctypes fpk_result array, free()). The arrays behind
+    each fpk_result stay owned by the library until free() is called. `c_array` = a prebuilt (FpkStructure * n) array."""
+    lib = _lib()
+    p = params if params is not None else default_params()
+    n = len(structures)
+    arr = c_array if c_array is not None else (FpkStructure * n)(*[s.c_struct() for s in structures])
+    res = (FpkResult * n)()
+    rc = lib.fpk_detect_batch(arr, n, C.byref(p), res)
+    if rc != capi.FPK_OK:
+        raise FpkError("fpk_detect_batch failed (%d): %s" % (rc, (lib.fpk_last_error() or b"").decode()))
+
+    def free():
+        for k in range(n):
+            lib.fpk_result_free(C.byref(res[k]))
+    return res, free
+
+
 class Batch:
     """Staged form (inputs stay resident in HBM between runs): create -> run()* -> fetch()."""
 

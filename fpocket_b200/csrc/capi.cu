@@ -9,7 +9,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <chrono>
 #include <mutex>
+#include <thread>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -20,6 +23,7 @@ using namespace fpk;
 
 // ------------------------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
+static std::atomic<long long> g_tot_h2d(0), g_tot_d2h(0);      // bytes moved by fpk_detect_batch since load (fpk_batch_counter(NULL, 6 / 7))
 static int g_dev = -1, g_sms = 0;
 static bool g_init = false;
 
@@ -84,10 +88,21 @@ extern "C" int fpk_init(const int *devices, int ndev)
     float pts[300];
     spiral_points(pts);
     CK(cudaMemcpyToSymbol(c_spiral, pts, sizeof pts));
+    // dynamic shared memory of the two Delaunay kernels: opted in ONCE to the device maximum (a per-batch setting would race between
+    // the host threads of fpk_detect_batch); each launch then asks for what its batch needs
+    {
+        cudaFuncAttributes fa;
+        CK(cudaFuncGetAttributes(&fa, k_delaunay_filter));
+        CK(cudaFuncSetAttribute(k_delaunay_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pr.sharedMemPerBlockOptin - fa.sharedSizeBytes)));
+        CK(cudaFuncGetAttributes(&fa, k_hull_volume));
+        CK(cudaFuncSetAttribute(k_hull_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pr.sharedMemPerBlockOptin - fa.sharedSizeBytes)));
+    }
     g_init = true;
     return FPK_OK;
 }
-extern "C" void fpk_shutdown(void) { g_init = false; }
+static void pool_clear();
+static void pin_clear();
+extern "C" void fpk_shutdown(void) { pool_clear(); pin_clear(); g_init = false; }
 
 static int ensure_init()
 {
@@ -115,6 +130,7 @@ template <class F> static int arena_build(Arena &A, F layout)
     layout(m);
     size_t need = m.used + 4096;
     if (need > A.cap) {
+        need += need / 4;                  // headroom: pooled contexts see chunks of slightly different sizes
         A.release();
         cudaError_t e = cudaMalloc(&A.base, need);
         if (e != cudaSuccess) return fail(FPK_ERR_CUDA, "cudaMalloc(%zu bytes): %s", need, cudaGetErrorString(e));
@@ -125,12 +141,67 @@ template <class F> static int arena_build(Arena &A, F layout)
     return FPK_OK;
 }
 
-struct HostResults {            // owner of the unpacked host arrays of one fetch
-    int refs = 0;
-    std::vector<float> xyzr, bary, atom_fx;
-    std::vector<int> neigh, cluster, cl_off, cl_sph, cl_atom_off, cl_atoms, rank, tets;
-    std::vector<uint8_t> type;
-    std::vector<fpk_desc> desc;
+// std::vector that does not zero-fill on resize (the arrays are overwritten by a D2H copy right away)
+template <class T> struct NoInit : std::allocator<T> {
+    template <class U> struct rebind { using other = NoInit<U>; };
+    template <class U, class... A> void construct(U *p, A &&...a)
+    {
+        if constexpr (sizeof...(A) == 0) ::new ((void *)p) U; else ::new ((void *)p) U(std::forward<A>(a)...);
+    }
+};
+template <class T> using rawvec = std::vector<T, NoInit<T>>;
+
+// Pinned host blocks for results, recycled across fetches: a D2H copy into pinned memory is a plain DMA (no driver staging, no
+// page faults on fresh pages), and allocating pinned memory is far too slow to do per chunk.
+static std::mutex g_pin_mu;
+static std::vector<std::pair<char *, size_t>> g_pin_pool;
+static char *pin_get(size_t need, size_t *cap)
+{
+    {
+        std::lock_guard<std::mutex> g(g_pin_mu);
+        int best = -1;
+        for (int i = 0; i < (int)g_pin_pool.size(); i++)
+            if (g_pin_pool[i].second >= need && (best < 0 || g_pin_pool[i].second < g_pin_pool[best].second)) best = i;
+        if (best >= 0) {
+            char *p = g_pin_pool[best].first; *cap = g_pin_pool[best].second;
+            g_pin_pool.erase(g_pin_pool.begin() + best);
+            return p;
+        }
+    }
+    char *p = nullptr;
+    size_t want = need + need / 4 + 4096;
+    if (cudaHostAlloc((void **)&p, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    *cap = want;
+    return p;
+}
+static void pin_put(char *p, size_t cap)
+{
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> g(g_pin_mu);
+        if (g_pin_pool.size() < 24) { g_pin_pool.emplace_back(p, cap); return; }
+    }
+    cudaFreeHost(p);
+}
+static void pin_clear()
+{
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    for (auto &x : g_pin_pool) cudaFreeHost(x.first);
+    g_pin_pool.clear();
+}
+
+struct HostResults {            // owner of the host arrays of one fetch: one pinned block, carved up
+    std::atomic<int> refs{0};
+    char *blk = nullptr; size_t cap = 0, used = 0;
+    std::vector<int> tets;      // only with want_tets
+    template <class T> T *take(size_t n)
+    {
+        used = (used + 255) & ~(size_t)255;
+        T *p = reinterpret_cast<T *>(blk + used);
+        used += n * sizeof(T);
+        return p;
+    }
+    ~HostResults() { pin_put(blk, cap); }
 };
 
 struct fpk_batch {
@@ -149,6 +220,7 @@ struct fpk_batch {
     int k1_picap = 0, hull_picap = 0; size_t k1_dsm = 0, hull_dsm = 0;   // shared-memory plan of the two Delaunay kernels
     ClusterScratch *dClu = nullptr; int nClu = 0;
     int *d_counters = nullptr;         // [8] work counters
+    char *hin = nullptr; size_t hin_cap = 0, in_bytes = 0;     // pinned host mirror of the arena's input prefix (one H2D copy)
     int *d_order = nullptr;
     // stage 2
     PocketDev Pk;
@@ -165,7 +237,7 @@ struct fpk_batch {
     float ms[8] = {0};
     long long launches = 0, h2d = 0, d2h = 0;
     bool events = false;
-    ~fpk_batch() { A1.release(); A2.release(); if (events) for (auto &e : ev) cudaEventDestroy(e); }
+    ~fpk_batch() { A1.release(); A2.release(); if (hin) cudaFreeHost(hin); if (events) for (auto &e : ev) cudaEventDestroy(e); }
 };
 
 static inline size_t sph_cap_for(const fpk_params &p, int nsites, double factor_override)
@@ -179,6 +251,7 @@ static int batch_pack(fpk_batch *b, const fpk_structure *in, int n, const fpk_pa
 {
     b->n = n; b->prm = *p;
     b->S.resize(n); b->natoms.resize(n);
+    b->max_sites = b->max_w = b->max_sphcap = 0; b->h2d = b->d2h = 0;
     long long ao = 0, wo = 0, so = 0, xo = 0, sc = 0, tc = 0;
     for (int k = 0; k < n; k++) {
         const fpk_structure &s = in[k];
@@ -243,25 +316,6 @@ static size_t del_scratch_layout(Arena &a, DelScratch &x, int nmax, int scap, in
     return a.used;
 }
 
-template <class T> static int h2d_gather(fpk_batch *b, T *dst, const fpk_structure *in, int n, const T *const fpk_structure::*field,
-                                         const int fpk_structure::*count, std::vector<char> &stage)
-{
-    size_t tot = 0;
-    for (int k = 0; k < n; k++) tot += (size_t)(in[k].*count);
-    if (!tot) return FPK_OK;
-    stage.resize(tot * sizeof(T));
-    T *h = reinterpret_cast<T *>(stage.data());
-    size_t o = 0;
-    for (int k = 0; k < n; k++) {
-        size_t c = (size_t)(in[k].*count);
-        if (c) memcpy(h + o, in[k].*field, c * sizeof(T));
-        o += c;
-    }
-    CK(cudaMemcpy(dst, h, tot * sizeof(T), cudaMemcpyHostToDevice));
-    b->h2d += (long long)(tot * sizeof(T));
-    return FPK_OK;
-}
-
 static int batch_upload(fpk_batch *b, const fpk_structure *in)
 {
     const int n = b->n;
@@ -275,7 +329,6 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
         if (need <= half) { b->k1_picap = b->max_sites; b->k1_dsm = need; }
         else if (need <= full) { b->k1_picap = b->max_sites; b->k1_dsm = need; }
         else { b->k1_picap = 0; b->k1_dsm = fixed; }
-        CK(cudaFuncSetAttribute(k_delaunay_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->k1_dsm));
     }
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_delaunay_filter, 256, b->k1_dsm);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_cluster, 256, 0);
@@ -301,16 +354,18 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
         float *xl = a.take<float>(3 * b->tot_xlig + 1);
         B.ax = ax; B.ay = ay; B.az = az; B.arad = ar; B.aen = ae; B.abf = ab; B.aid = aid; B.ares = ares; B.aaa = aaa; B.afl = afl;
         B.wx = wx; B.wy = wy; B.wz = wz; B.wrad = wr; B.wen = we; B.wfl = wfl; B.site2atom = s2a; B.xlig = xl;
+        b->d_order = a.take<int>(n);
+        b->dDel = a.take<DelScratch>(b->nDel);
+        b->dClu = a.take<ClusterScratch>(b->nClu);
+        a.take<char>(0);
+        b->in_bytes = a.used;                      // everything above is input: mirrored in pinned host memory, one copy
         B.s_xyzr = a.take<float4>(b->tot_sphcap); B.s_bary = a.take<float>(3 * b->tot_sphcap);
         B.s_neigh = a.take<int4>(b->tot_sphcap); B.s_key = a.take<int4>(b->tot_sphcap);
         B.s_type = a.take<uint8_t>(b->tot_sphcap); B.s_cluster = a.take<int>(b->tot_sphcap);
         B.cl_off = a.take<int>(b->tot_sphcap + 2 * (size_t)n + 2); B.cl_sph = a.take<int>(b->tot_sphcap);
         B.counts = a.take<int>((size_t)n * CNT_STRIDE);
-        b->d_order = a.take<int>(n);
         b->d_counters = a.take<int>(8);
         B.tets_out = b->tot_tetcap ? a.take<int>(4 * b->tot_tetcap) : nullptr;
-        b->dDel = a.take<DelScratch>(b->nDel);
-        b->dClu = a.take<ClusterScratch>(b->nClu);
         for (int i = 0; i < b->nDel; i++) del_scratch_layout(a, hDel[i], b->max_sites, b->max_sphcap, 256, true);
         for (int i = 0; i < b->nClu; i++) {
             hClu[i].cellcnt = a.take<int>(CELLMAX + 2); hClu[i].cellsph = a.take<int>(b->max_sphcap + 1);
@@ -319,32 +374,60 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
     });
     if (rc) return rc;
     B.nstruct = n; B.S = b->dS; B.prm = b->prm; B.work_order = b->d_order; B.work_counter = b->d_counters;
-    std::vector<char> stage;
     std::vector<int> order(n);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return b->S[x].nsites > b->S[y].nsites; });
-    CK(cudaMemcpy(b->dS, b->S.data(), sizeof(StructDev) * n, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(b->d_order, order.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(b->dDel, hDel.data(), sizeof(DelScratch) * b->nDel, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(b->dClu, hClu.data(), sizeof(ClusterScratch) * b->nClu, cudaMemcpyHostToDevice));
-    b->h2d += (long long)(sizeof(StructDev) + sizeof(int)) * n;
-    if (in) {
-#define UP(dst, field, cnt) if ((rc = h2d_gather(b, const_cast<std::remove_const<std::remove_pointer<decltype(B.dst)>::type>::type *>(B.dst), in, n, &fpk_structure::field, &fpk_structure::cnt, stage))) return rc;
-        UP(ax, x, natoms) UP(ay, y, natoms) UP(az, z, natoms) UP(arad, radius, natoms) UP(aen, electroneg, natoms) UP(abf, bfactor, natoms)
-        UP(aid, atom_id, natoms) UP(ares, res_id, natoms) UP(aaa, aa_idx, natoms) UP(afl, flags, natoms)
-        UP(wx, wx, natoms_w) UP(wy, wy, natoms_w) UP(wz, wz, natoms_w) UP(wrad, wradius, natoms_w) UP(wen, welectroneg, natoms_w) UP(wfl, wflags, natoms_w)
-#undef UP
-        // site map (voronoi.c:94-107 h_tr) and explicit-ligand coordinates
-        std::vector<int> s2a((size_t)b->tot_sites);
-        std::vector<float> xl(3 * (size_t)b->tot_xlig + 1);
-        size_t so = 0, xo = 0;
-        for (int k = 0; k < n; k++) {
-            for (int i = 0; i < in[k].natoms; i++) if (!(in[k].flags[i] & FPK_ATOM_H)) s2a[so++] = i;
-            if (in[k].n_xlig) { memcpy(&xl[3 * xo], in[k].xlig, sizeof(float) * 3 * in[k].n_xlig); xo += in[k].n_xlig; }
+    if (!in) {          // mdpocket skeleton: descriptors only; properties and coordinates are uploaded by the caller
+        CK(cudaMemcpy(b->dS, b->S.data(), sizeof(StructDev) * n, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(b->d_order, order.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(b->dDel, hDel.data(), sizeof(DelScratch) * b->nDel, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(b->dClu, hClu.data(), sizeof(ClusterScratch) * b->nClu, cudaMemcpyHostToDevice));
+        b->h2d += (long long)(sizeof(StructDev) + sizeof(int)) * n;
+    } else {
+        // fill the pinned mirror at the arena's own offsets, then ONE asynchronous copy of the whole input prefix
+        if (b->in_bytes > b->hin_cap) {
+            if (b->hin) cudaFreeHost(b->hin);
+            b->hin = nullptr; b->hin_cap = 0;
+            const size_t want = b->in_bytes + b->in_bytes / 8 + 4096;
+            cudaError_t e = cudaHostAlloc((void **)&b->hin, want, cudaHostAllocDefault);
+            if (e != cudaSuccess) return fail(FPK_ERR_CUDA, "cudaHostAlloc(%zu bytes): %s", want, cudaGetErrorString(e));
+            b->hin_cap = want;
         }
-        if (so) CK(cudaMemcpy(const_cast<int *>(B.site2atom), s2a.data(), sizeof(int) * so, cudaMemcpyHostToDevice));
-        if (xo) CK(cudaMemcpy(const_cast<float *>(B.xlig), xl.data(), sizeof(float) * 3 * xo, cudaMemcpyHostToDevice));
-        b->h2d += (long long)(sizeof(int) * so + sizeof(float) * 3 * xo);
+        char *H = b->hin;
+        const char *D0 = b->A1.base;
+        auto mir = [&](const void *dev) { return H + (reinterpret_cast<const char *>(dev) - D0); };
+        memcpy(mir(b->dS), b->S.data(), sizeof(StructDev) * n);
+        memcpy(mir(b->d_order), order.data(), sizeof(int) * n);
+        memcpy(mir(b->dDel), hDel.data(), sizeof(DelScratch) * b->nDel);
+        memcpy(mir(b->dClu), hClu.data(), sizeof(ClusterScratch) * b->nClu);
+        float *hx = (float *)mir(B.ax), *hy = (float *)mir(B.ay), *hz = (float *)mir(B.az), *hr = (float *)mir(B.arad), *he = (float *)mir(B.aen),
+              *hb = (float *)mir(B.abf);
+        int *hid = (int *)mir(B.aid), *hres = (int *)mir(B.ares), *hs2a = (int *)mir(B.site2atom);
+        int8_t *haa = (int8_t *)mir(B.aaa);
+        uint8_t *hfl = (uint8_t *)mir(B.afl), *hwf = (uint8_t *)mir(B.wfl);
+        float *hwx = (float *)mir(B.wx), *hwy = (float *)mir(B.wy), *hwz = (float *)mir(B.wz), *hwr = (float *)mir(B.wrad), *hwe = (float *)mir(B.wen);
+        float *hxl = (float *)mir(B.xlig);
+        for (int k = 0; k < n; k++) {
+            const fpk_structure &q = in[k];
+            const StructDev &d = b->S[k];
+            const size_t na = (size_t)q.natoms, nw = (size_t)q.natoms_w;
+            if (na) {
+                memcpy(hx + d.atom_off, q.x, 4 * na); memcpy(hy + d.atom_off, q.y, 4 * na); memcpy(hz + d.atom_off, q.z, 4 * na);
+                memcpy(hr + d.atom_off, q.radius, 4 * na); memcpy(he + d.atom_off, q.electroneg, 4 * na); memcpy(hb + d.atom_off, q.bfactor, 4 * na);
+                memcpy(hid + d.atom_off, q.atom_id, 4 * na); memcpy(hres + d.atom_off, q.res_id, 4 * na);
+                memcpy(haa + d.atom_off, q.aa_idx, na); memcpy(hfl + d.atom_off, q.flags, na);
+            }
+            if (nw) {
+                memcpy(hwx + d.w_off, q.wx, 4 * nw); memcpy(hwy + d.w_off, q.wy, 4 * nw); memcpy(hwz + d.w_off, q.wz, 4 * nw);
+                memcpy(hwr + d.w_off, q.wradius, 4 * nw); memcpy(hwe + d.w_off, q.welectroneg, 4 * nw); memcpy(hwf + d.w_off, q.wflags, nw);
+            }
+            int *s2 = hs2a + d.site_off;                                      // site map (voronoi.c:94-107 h_tr)
+            int so = 0;
+            for (int i = 0; i < q.natoms; i++) if (!(q.flags[i] & FPK_ATOM_H)) s2[so++] = i;
+            if (q.n_xlig) memcpy(hxl + 3 * (size_t)d.xlig_off, q.xlig, sizeof(float) * 3 * q.n_xlig);
+        }
+        CK(cudaMemcpyAsync(b->A1.base, H, b->in_bytes, cudaMemcpyHostToDevice, cudaStreamPerThread));
+        b->h2d += (long long)b->in_bytes;
     }
     if (!b->events) { for (auto &e : b->ev) CK(cudaEventCreate(&e)); b->events = true; }
     return FPK_OK;
@@ -403,7 +486,6 @@ static int batch_run(fpk_batch *b)
     int occH = 8, occD = 8;
     b->hull_picap = std::min(max_ns, 1024);
     b->hull_dsm = (HULL_THREADS / 32) * sizeof(WarpCav) + 12 * (size_t)b->hull_picap + 16;
-    CK(cudaFuncSetAttribute(k_hull_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->hull_dsm));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occH, k_hull_volume, HULL_THREADS, b->hull_dsm);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occD, k_descriptors, K4_THREADS, 0);
     occH = std::max(1, std::min(occH, 8)); occD = std::max(1, std::min(occD, 8));
@@ -454,7 +536,7 @@ static int batch_run(fpk_batch *b)
     k_compact<<<n, 128>>>(B, b->d_sbase, b->c_xyzr, b->c_bary, b->c_neigh, b->c_type, b->c_cluster, b->c_cl_sph, b->c_cl_off, b->d_clbase);
     b->launches++;
     CK(cudaEventRecord(b->ev[6]));
-    CK(cudaDeviceSynchronize());
+    CK(cudaStreamSynchronize(cudaStreamPerThread));
     CK(cudaGetLastError());
     for (int i = 0; i < 6; i++) cudaEventElapsedTime(&b->ms[i], b->ev[i], b->ev[i + 1]);
     cudaEventElapsedTime(&b->ms[7], b->ev[0], b->ev[6]);
@@ -464,10 +546,9 @@ static int batch_run(fpk_batch *b)
     return FPK_OK;
 }
 
-template <class T> static int d2h(fpk_batch *b, std::vector<T> &dst, const void *src, size_t count)
+template <class T> static int d2h(fpk_batch *b, T *dst, const void *src, size_t count)
 {
-    dst.resize(count);
-    if (count) { CK(cudaMemcpy(dst.data(), src, count * sizeof(T), cudaMemcpyDeviceToHost)); b->d2h += (long long)(count * sizeof(T)); }
+    if (count) { CK(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyDeviceToHost, cudaStreamPerThread)); b->d2h += (long long)(count * sizeof(T)); }
     return FPK_OK;
 }
 
@@ -475,15 +556,22 @@ static int batch_fetch(fpk_batch *b, fpk_result *out)
 {
     const int n = b->n;
     HostResults *H = new HostResults();
-    const long long NS = b->tot_spheres, NC = b->tot_clusters;
+    const size_t NS = (size_t)b->tot_spheres, NC = (size_t)b->tot_clusters, NA = (size_t)b->tot_atoms;
+    const size_t need = 16 * NS + 12 * NS + 16 * NS + NS + 4 * NS + 4 * NS + 4 * (NC + n) + sizeof(fpk_desc) * NC + 16 * NS + 4 * (NS + n) + 16 * NA +
+                        4 * (NC + n) + 16 * NS + 256 * 16;
+    H->blk = pin_get(need, &H->cap);
+    if (!H->blk) { delete H; return fail(FPK_ERR_CUDA, "cudaHostAlloc(%zu bytes) for the results failed", need); }
+    float *xyzr = H->take<float>(4 * NS), *bary = H->take<float>(3 * NS), *atom_fx = H->take<float>(4 * NA);
+    int *neigh = H->take<int>(4 * NS), *cluster = H->take<int>(NS), *cl_sph = H->take<int>(NS), *cl_off = H->take<int>(NC + n);
+    int *sparse = H->take<int>(4 * NS), *rank = H->take<int>(NS + n), *cl_atom_off = H->take<int>(NC + n), *cl_atoms = H->take<int>(4 * NS);
+    uint8_t *type = H->take<uint8_t>(NS);
+    fpk_desc *desc = H->take<fpk_desc>(NC);
     int rc;
-    std::vector<int> cl_atoms_sparse;
-    if ((rc = d2h(b, H->xyzr, b->c_xyzr, 4 * (size_t)NS)) || (rc = d2h(b, H->bary, b->c_bary, 3 * (size_t)NS)) ||
-        (rc = d2h(b, H->neigh, b->c_neigh, 4 * (size_t)NS)) || (rc = d2h(b, H->type, b->c_type, (size_t)NS)) ||
-        (rc = d2h(b, H->cluster, b->c_cluster, (size_t)NS)) || (rc = d2h(b, H->cl_sph, b->c_cl_sph, (size_t)NS)) ||
-        (rc = d2h(b, H->cl_off, b->c_cl_off, (size_t)(NC + n))) || (rc = d2h(b, H->desc, b->Pk.desc, (size_t)NC)) ||
-        (rc = d2h(b, cl_atoms_sparse, b->Pk.cl_atoms, 4 * (size_t)NS)) || (rc = d2h(b, H->rank, b->Pk.rank_to_cluster, (size_t)(NS + n))) ||
-        (rc = d2h(b, H->atom_fx, b->Pk.atom_fx, 4 * (size_t)b->tot_atoms))) { delete H; return rc; }
+    if ((rc = d2h(b, xyzr, b->c_xyzr, 4 * NS)) || (rc = d2h(b, bary, b->c_bary, 3 * NS)) || (rc = d2h(b, neigh, b->c_neigh, 4 * NS)) ||
+        (rc = d2h(b, type, b->c_type, NS)) || (rc = d2h(b, cluster, b->c_cluster, NS)) || (rc = d2h(b, cl_sph, b->c_cl_sph, NS)) ||
+        (rc = d2h(b, cl_off, b->c_cl_off, NC + n)) || (rc = d2h(b, desc, b->Pk.desc, NC)) || (rc = d2h(b, sparse, b->Pk.cl_atoms, 4 * NS)) ||
+        (rc = d2h(b, rank, b->Pk.rank_to_cluster, NS + n)) || (rc = d2h(b, atom_fx, b->Pk.atom_fx, 4 * NA))) { delete H; return rc; }
+    CK(cudaStreamSynchronize(cudaStreamPerThread));
     if (b->B.tets_out) {
         H->tets.resize(4 * (size_t)b->tot_tets + 4);
         size_t o = 0;
@@ -500,9 +588,7 @@ static int batch_fetch(fpk_batch *b, fpk_result *out)
         }
     }
     // compact the per-cluster atom lists (device layout: 4 slots per sphere of the cluster, first n_atoms used)
-    H->cl_atom_off.resize((size_t)(NC + n));
-    H->cl_atoms.reserve((size_t)NS);
-    size_t tetpos = 0;
+    size_t tetpos = 0, apos = 0;
     for (int k = 0; k < n; k++) {
         const int *c = &b->h_counts[(size_t)k * CNT_STRIDE];
         fpk_result &r = out[k];
@@ -513,27 +599,26 @@ static int batch_fetch(fpk_batch *b, fpk_result *out)
         const int s0 = b->h_sbase[k], ns = b->h_sbase[k + 1] - s0, c0 = b->h_clbase[k], nc = b->h_clbase[k + 1] - c0;
         r.n_spheres = ns; r.n_clusters = nc; r.n_pockets = c[CNT_POCKETS];
         if (b->B.tets_out) { r.tets = &H->tets[tetpos]; tetpos += 4 * (size_t)std::min(r.n_tets, b->S[k].tet_cap); }
-        r.sph_xyzr = H->xyzr.data() + 4 * (size_t)s0; r.sph_bary = H->bary.data() + 3 * (size_t)s0;
-        r.sph_neigh = H->neigh.data() + 4 * (size_t)s0; r.sph_type = H->type.data() + s0; r.sph_cluster = H->cluster.data() + s0;
-        r.cl_off = H->cl_off.data() + c0 + k; r.cl_sph = H->cl_sph.data() + s0;
-        r.desc = H->desc.data() + c0;
-        r.rank_to_cluster = H->rank.data() + s0 + k;
-        r.atom_fx = H->atom_fx.data() + 4 * (size_t)b->S[k].atom_off;
-        int *ao = H->cl_atom_off.data() + c0 + k;
-        size_t abase = H->cl_atoms.size();
+        r.sph_xyzr = xyzr + 4 * (size_t)s0; r.sph_bary = bary + 3 * (size_t)s0;
+        r.sph_neigh = neigh + 4 * (size_t)s0; r.sph_type = type + s0; r.sph_cluster = cluster + s0;
+        r.cl_off = cl_off + c0 + k; r.cl_sph = cl_sph + s0;
+        r.desc = desc + c0;
+        r.rank_to_cluster = rank + s0 + k;
+        r.atom_fx = atom_fx + 4 * (size_t)b->S[k].atom_off;
+        int *ao = cl_atom_off + c0 + k;
+        r.cl_atoms = cl_atoms + apos;
         ao[0] = 0;
         for (int q = 0; q < nc; q++) {
-            const int *src = &cl_atoms_sparse[4 * ((size_t)s0 + r.cl_off[q])];
-            int na = r.desc[q].n_atoms;
-            H->cl_atoms.insert(H->cl_atoms.end(), src, src + na);
+            const int *src = sparse + 4 * ((size_t)s0 + r.cl_off[q]);
+            const int na = r.desc[q].n_atoms;
+            memcpy(cl_atoms + apos, src, sizeof(int) * (size_t)na);
+            apos += (size_t)na;
             ao[q + 1] = ao[q] + na;
         }
         r.cl_atom_off = ao;
-        r.cl_atoms = reinterpret_cast<int32_t *>(abase);     // fixed up below (vector may reallocate)
         r._owner = H;
         H->refs++;
     }
-    for (int k = 0; k < n; k++) out[k].cl_atoms = H->cl_atoms.data() + reinterpret_cast<size_t>(out[k].cl_atoms);
     if (H->refs == 0) delete H;
     return FPK_OK;
 }
@@ -543,7 +628,7 @@ extern "C" void fpk_result_free(fpk_result *r)
     if (!r || !r->_owner) return;
     HostResults *H = static_cast<HostResults *>(r->_owner);
     memset(r, 0, sizeof *r);
-    if (--H->refs == 0) delete H;
+    if (H->refs.fetch_sub(1) == 1) delete H;
 }
 
 extern "C" fpk_batch *fpk_batch_create(const fpk_structure *in, int n, const fpk_params *p)
@@ -559,7 +644,7 @@ extern "C" int fpk_batch_fetch(fpk_batch *b, fpk_result *out) { return (b && out
 extern "C" float fpk_batch_last_kernel_ms(const fpk_batch *b, int which) { return (b && which >= 0 && which < 8) ? b->ms[which] : -1.0f; }
 extern "C" long long fpk_batch_counter(const fpk_batch *b, int which)
 {
-    if (!b) return -1;
+    if (!b) return which == 6 ? g_tot_h2d.load() : (which == 7 ? g_tot_d2h.load() : -1);
     switch (which) {
     case 0: return b->tot_sites;
     case 1: return b->tot_tets;
@@ -578,13 +663,85 @@ extern "C" long long fpk_batch_counter(const fpk_batch *b, int which)
 }
 extern "C" void fpk_batch_destroy(fpk_batch *b) { delete b; }
 
+// ---- fpk_detect_batch: the batch is cut into chunks that a few host threads push through pack -> H2D -> kernels -> D2H ->
+// unpack, each on its own CUDA stream (the library is compiled with --default-stream per-thread), so that one chunk's copies and
+// host-side packing overlap another chunk's kernels. Worker contexts (device arenas, pinned mirrors) are pooled across calls.
+static std::mutex g_pool_mu;
+static std::vector<fpk_batch *> g_pool;
+static fpk_batch *pool_get()
+{
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    if (!g_pool.empty()) { fpk_batch *b = g_pool.back(); g_pool.pop_back(); return b; }
+    return new fpk_batch();
+}
+static void pool_put(fpk_batch *b)
+{
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    if (g_pool.size() < 4) g_pool.push_back(b); else delete b;
+}
+static void pool_clear()
+{
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    for (fpk_batch *b : g_pool) delete b;
+    g_pool.clear();
+}
+
+static std::atomic<long long> g_t_pack(0), g_t_up(0), g_t_run(0), g_t_fetch(0);     // host wall time per stage, ns (FPK_TRACE=1 prints them)
+static int detect_chunk(fpk_batch *b, const fpk_structure *in, int n, const fpk_params *p, fpk_result *out)
+{
+    typedef std::chrono::steady_clock clk;
+    auto t0 = clk::now();
+    int rc = batch_pack(b, in, n, p, 0.0);
+    auto t1 = clk::now();
+    if (!rc) rc = batch_upload(b, in);
+    auto t2 = clk::now();
+    if (!rc) rc = batch_run(b);
+    auto t3 = clk::now();
+    if (!rc) rc = batch_fetch(b, out);
+    auto t4 = clk::now();
+    g_t_pack += (t1 - t0).count(); g_t_up += (t2 - t1).count(); g_t_run += (t3 - t2).count(); g_t_fetch += (t4 - t3).count();
+    g_tot_h2d += b->h2d; g_tot_d2h += b->d2h;
+    return rc;
+}
+
 extern "C" int fpk_detect_batch(const fpk_structure *in, int n, const fpk_params *p, fpk_result *out)
 {
     if (!out) return fail(FPK_ERR_BAD_ARG, "null result array");
-    fpk_batch *b = fpk_batch_create(in, n, p);
-    if (!b) return FPK_ERR_BAD_ARG;
-    int rc = batch_run(b);
-    if (!rc) rc = batch_fetch(b, out);
+    if (!in || n <= 0 || !p) return fail(FPK_ERR_BAD_ARG, "fpk_detect_batch: bad arguments");
+    int rc = ensure_init();
+    if (rc) return rc;
+    int chunk = 512, nthreads = 4;
+    if (const char *e = getenv("FPK_CHUNK")) chunk = std::max(1, atoi(e));
+    if (const char *e = getenv("FPK_HOST_THREADS")) nthreads = std::max(1, std::min(8, atoi(e)));
+    const int nchunks = (n + chunk - 1) / chunk;
+    nthreads = std::min(nthreads, nchunks);
+    if (nthreads <= 1) {
+        fpk_batch *b = pool_get();
+        for (int c = 0; c < nchunks && !rc; c++) rc = detect_chunk(b, in + (size_t)c * chunk, std::min(chunk, n - c * chunk), p, out + (size_t)c * chunk);
+        pool_put(b);
+    } else {
+        std::atomic<int> next(0), err(0);
+        std::vector<std::string> msgs(nthreads);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; t++)
+            th.emplace_back([&, t]() {
+                cudaSetDevice(g_dev);
+                fpk_batch *b = pool_get();
+                for (;;) {
+                    const int c = next.fetch_add(1);
+                    if (c >= nchunks || err.load()) break;
+                    int r = detect_chunk(b, in + (size_t)c * chunk, std::min(chunk, n - c * chunk), p, out + (size_t)c * chunk);
+                    if (r) { msgs[t] = g_err; err.store(r); break; }
+                }
+                pool_put(b);
+            });
+        for (auto &x : th) x.join();
+        rc = err.load();
+        if (rc) for (auto &m : msgs) if (!m.empty()) g_err = m;
+    }
+    if (getenv("FPK_TRACE"))
+        fprintf(stderr, "fpk_detect_batch: %d structures, %d chunks, %d threads; cumulative host ms: pack %.1f upload %.1f run %.1f fetch %.1f\n", n, nchunks,
+                nthreads, g_t_pack.load() / 1e6, g_t_up.load() / 1e6, g_t_run.load() / 1e6, g_t_fetch.load() / 1e6);
     // a structure whose sphere buffer overflowed is re-run alone with the worst-case capacity (7 tets per atom)
     if (!rc) {
         for (int k = 0; k < n; k++) {
@@ -598,7 +755,6 @@ extern "C" int fpk_detect_batch(const fpk_structure *in, int n, const fpk_params
             delete b2;
         }
     }
-    delete b;
     return rc;
 }
 

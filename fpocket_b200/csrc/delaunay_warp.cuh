@@ -326,6 +326,7 @@ __device__ __noinline__ int w2_commit_insertion(DelaunayCtx &c, WarpCav &W, int 
                 *reinterpret_cast<int4 *>(FPK_TV(c, nt)) = nv;
                 FPK_TN(c, nt)[q] = o;
                 *reinterpret_cast<int2 *>(FPK_OWN(c, nt)) = make_int2(OWN_FREE, OWN_FREE);
+                FPK_MARK(c, nt) = -1;                       // the serial path (delaunay.cuh) tests marks of live tets
                 const int4 ov = *reinterpret_cast<const int4 *>(FPK_TV(c, o)), on = *reinterpret_cast<const int4 *>(FPK_TN(c, o));
                 // the slot of o that faced cur through this face: its vertex there is the one of o that is not on the face
                 const int vq = reinterpret_cast<const int *>(&W.v[f])[q];

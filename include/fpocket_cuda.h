@@ -151,7 +151,7 @@ fpk_batch *fpk_batch_create(const fpk_structure *in, int n, const fpk_params *p)
 int fpk_batch_run(fpk_batch *b);                                                   /* kernels only, returns after sync */
 int fpk_batch_fetch(fpk_batch *b, fpk_result *out);                                /* D2H + unpack */
 float fpk_batch_last_kernel_ms(const fpk_batch *b, int which);                     /* CUDA-event time of stage `which` in the last run */
-long long fpk_batch_counter(const fpk_batch *b, int which);                        /* 0 sites,1 tets,2 spheres,3 clusters,4 pockets,5 launches,6 h2d bytes,7 d2h bytes */
+long long fpk_batch_counter(const fpk_batch *b, int which);                        /* 0 sites,1 tets,2 spheres,3 clusters,4 pockets,5 launches,6 h2d bytes,7 d2h bytes; b == NULL: 6/7 = bytes moved by fpk_detect_batch so far */
 void fpk_batch_destroy(fpk_batch *b);
 
 /* ---- mdpocket: replaces the per-frame body of mdpocket_detect (mdpocket.c:142-175,235-271) --- */

@@ -102,6 +102,20 @@ def test_batch_equals_single():
         assert_same_result(r, o, c)
 
 
+def test_scratch_reuse_across_batches_of_different_shape():
+    """The per-block Delaunay scratch and the pooled host contexts are reused by later calls whose layout differs: nothing may
+    depend on what an earlier batch left behind (regression: stale cavity marks read by the serial big-cavity path)."""
+    api = _api()
+    ds = [G.load(c) for c in ("7TAA_m28_M74", "5WA6", "1UYD", "3LKF")]
+    p = G.inputs(ds[1])[1]
+    sts = [G.inputs(d)[0] for d in ds]
+    want = [O.search_pocket(st, p, tets=None, rng_mode=O.RNG_PHILOX) for st in sts]
+    for order in ([0, 1, 2, 3, 0, 1], [3, 2], [1, 1, 1, 0, 2, 3, 3], [2]):
+        got = api.detect_batch([sts[i] for i in order], p)
+        for i, r in zip(order, got):
+            assert_same_result(r, want[i], "reuse %d" % i)
+
+
 def test_edge_cases():
     from fpocket_b200 import capi
     api = _api()
