@@ -231,16 +231,27 @@ __device__ __forceinline__ float unif_from_bits(unsigned r31, float mn, float mx
 }
 
 struct DescScratch {          // per resident block of K4
-    int *sa;                  // [natoms_w max] surrounding atoms of the current pocket (asa.c:84-112)
+    int *sa;                  // [natoms_w max] surrounding atoms of the current pocket (asa.c:84-112), three ordered segments
 };
 
-enum { K4_THREADS = 128, MC_SMEM_SPH = 1024 };
+enum { K4_THREADS = 128, K4_WORKERS = 96, MC_SMEM_SPH = 1024, MC_CELLS = 512, MC_ENTRIES = 8192, ASA_CAND = 128 };
 
+// barrier among warps 1..3 only (warp 0 runs the reference-order sequential sums meanwhile)
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
+
+// K4: one block per cluster. After the contacted-atom lists are built the block splits:
+//   warp 0     - the reference's sequential float sums (pair loop of descriptors.c:186-236 etc.), in the reference's order;
+//   warps 1..3 - surrounding atoms, the two SASA passes and the Monte-Carlo volume (integer counts: order-free).
 __global__ void __launch_bounds__(K4_THREADS) k_descriptors(BatchDev B, PocketDev Pk, const DescScratch *scratch, int *work_counter)
 {
-    __shared__ int s_item, s_U, s_nsa, s_cnt[100], s_sm[40], s_wsum[K4_THREADS / 32];
-    __shared__ float s_mcbox[8];
-    __shared__ float4 s_sph[MC_SMEM_SPH];
+    __shared__ int s_item, s_U, s_cnt[100], s_sm[40], s_segcnt[3], s_mcdim[4], s_mcmode;
+    __shared__ float s_mcbox[6], s_mch[3], s_bb[3][6];
+    __shared__ float4 s_sph[MC_SMEM_SPH];                  // (x, y, z, (ray-1.6)^2) of the pocket's spheres
+    __shared__ int s_cell[MC_CELLS + 1];
+    __shared__ unsigned short s_ent[MC_ENTRIES];
+    __shared__ float4 s_cand[3][ASA_CAND];                 // per worker warp: burial candidates of the current atom (x, y, z, radius)
+    __shared__ unsigned char s_candapol[3][ASA_CAND];
+    __shared__ fpk_desc s_desc;                            // warp 0's part of the record (everything but ASA / volume)
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
     const DescScratch &X = scratch[blockIdx.x];
     const fpk_params &prm = B.prm;
@@ -275,8 +286,12 @@ __global__ void __launch_bounds__(K4_THREADS) k_descriptors(BatchDev B, PocketDe
         const float *wx = S.natoms_w ? B.wx : B.ax, *wy = S.natoms_w ? B.wy : B.ay, *wz = S.natoms_w ? B.wz : B.az;
         const float *wr = S.natoms_w ? B.wrad : B.arad, *we = S.natoms_w ? B.wen : B.aen;
         const uint8_t *wf = S.natoms_w ? B.wfl : B.afl;
+        const bool full = prm.do_asa_and_volume != 0;
+        const bool observable = n >= prm.min_pock_nb_asph;      // below it the cluster is always dropped (refine.c:124): no MC samples
+        const bool insm = n <= MC_SMEM_SPH;
+        const float correct = -1.6f;
 
-        // ---- 1. unique contacted atoms by atom id, first-seen order (pocket.c:1280-1320) -- warp 0 -------------------------------
+        // ---- 1. warp 0: unique contacted atoms by atom id, first-seen order (pocket.c:1280-1320); warps 1..3: MC sphere tile ----------
         if (wid == 0) {
             int U = 0;
             for (int base = 0; base < 4 * n; base += 32) {
@@ -304,6 +319,26 @@ __global__ void __launch_bounds__(K4_THREADS) k_descriptors(BatchDev B, PocketDe
                 __syncwarp();
             }
             if (lane == 0) s_U = U;
+        } else if (full) {
+            if (insm)
+                for (int i = tid - 32; i < n; i += K4_WORKERS) { float4 v = sx[L[i]]; v.w = (correct + v.w) * (v.w + correct); s_sph[i] = v; }
+            if (tid == 32) {        // MC box (voronoi.c:1172-1195: +correct on both sides, else-if updates), one thread, reference order
+                float xmin = 0, xmax = 0, ymin = 0, ymax = 0, zmin = 0, zmax = 0, xt, yt, zt;
+                for (int i = 0; i < n; i++) {
+                    float4 v = sx[L[i]];
+                    if (i == 0) {
+                        xmin = v.x - v.w + correct; xmax = v.x + v.w + correct;
+                        ymin = v.y - v.w + correct; ymax = v.y + v.w + correct;
+                        zmin = v.z - v.w + correct; zmax = v.z + v.w + correct;
+                    } else {
+                        if (xmin > (xt = v.x - v.w + correct)) xmin = xt; else if (xmax < (xt = v.x + v.w + correct)) xmax = xt;
+                        if (ymin > (yt = v.y - v.w + correct)) ymin = yt; else if (ymax < (yt = v.y + v.w + correct)) ymax = yt;
+                        if (zmin > (zt = v.z - v.w + correct)) zmin = zt; else if (zmax < (zt = v.z + v.w + correct)) zmax = zt;
+                    }
+                }
+                s_mcbox[0] = xmin; s_mcbox[1] = xmax; s_mcbox[2] = ymin; s_mcbox[3] = ymax; s_mcbox[4] = zmin; s_mcbox[5] = zmax;
+            }
+            for (int i = tid - 32; i < 100; i += K4_WORKERS) s_cnt[i] = 0;
         }
         __syncthreads();
         const int U = s_U;
@@ -323,138 +358,8 @@ __global__ void __launch_bounds__(K4_THREADS) k_descriptors(BatchDev B, PocketDe
         for (int u = tid; u < 4 * U; u += nt) acc[u] = 0;
         __syncthreads();
 
-        if (prm.do_asa_and_volume) {
-            // ---- 3. surrounding atoms (asa.c:84-112): heavy atoms of pdb_w_lig within ray+1 of a sphere, atom order ----------------
-            float bmn[3] = {3e38f, 3e38f, 3e38f}, bmx[3] = {-3e38f, -3e38f, -3e38f};
-            for (int i = tid; i < n; i += nt) {
-                float4 v = sx[L[i]];
-                float rp = v.w + 1.01f;
-                bmn[0] = fminf(bmn[0], v.x - rp); bmn[1] = fminf(bmn[1], v.y - rp); bmn[2] = fminf(bmn[2], v.z - rp);
-                bmx[0] = fmaxf(bmx[0], v.x + rp); bmx[1] = fmaxf(bmx[1], v.y + rp); bmx[2] = fmaxf(bmx[2], v.z + rp);
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1)
-#pragma unroll
-                for (int q = 0; q < 3; q++) {
-                    bmn[q] = fminf(bmn[q], __shfl_xor_sync(0xffffffffu, bmn[q], d));
-                    bmx[q] = fmaxf(bmx[q], __shfl_xor_sync(0xffffffffu, bmx[q], d));
-                }
-            __shared__ float s_bb[K4_THREADS / 32][6];
-            if (lane == 0) for (int q = 0; q < 3; q++) { s_bb[wid][q] = bmn[q]; s_bb[wid][3 + q] = bmx[q]; }
-            __syncthreads();
-            for (int w = 0; w < nt / 32; w++)
-                for (int q = 0; q < 3; q++) { bmn[q] = fminf(bmn[q], s_bb[w][q]); bmx[q] = fmaxf(bmx[q], s_bb[w][3 + q]); }
-            if (tid == 0) s_nsa = 0;
-            __syncthreads();
-            for (int base = 0; base < nw; base += nt) {
-                int i = base + tid;
-                bool in = false;
-                if (i < nw && !(wf[WQ0 + i] & whmask)) {
-                    float x = wx[W0 + i], y = wy[W0 + i], z = wz[W0 + i];
-                    if (x >= bmn[0] && x <= bmx[0] && y >= bmn[1] && y <= bmx[1] && z >= bmn[2] && z <= bmx[2]) {
-                        for (int q = 0; q < n && !in; q++) {
-                            float4 v = sx[L[q]];
-                            double rp = (double)v.w + 1.0;
-                            in = (double)f_ddist(x, y, z, v.x, v.y, v.z) < rp * rp;
-                        }
-                    }
-                }
-                unsigned bal = __ballot_sync(0xffffffffu, in);
-                if (lane == 0) s_wsum[wid] = __popc(bal);
-                __syncthreads();
-                int woff = s_nsa;
-                for (int w = 0; w < wid; w++) woff += s_wsum[w];
-                if (in) X.sa[woff + __popc(bal & ((1u << lane) - 1u))] = i;
-                __syncthreads();
-                if (tid == 0) { int t = 0; for (int w = 0; w < nt / 32; w++) t += s_wsum[w]; s_nsa += t; }
-                __syncthreads();
-            }
-            const int n_sa = s_nsa;
-            // ---- 4. 100-point spiral SASA, probes 1.4 and 2.2 (asa.c:240-419): one thread per (atom, point, probe) -----------
-            for (int it = tid; it < U * 200; it += nt) {
-                const int pass = it >= U * 100 ? 1 : 0;
-                const int r = it - pass * U * 100;
-                const int u = r / 100, kp = r - u * 100;
-                const double probe = pass == 0 ? 1.4 : 2.2;
-                const int cura = uat[u];
-                const float cx = B.ax[A0 + cura], cy = B.ay[A0 + cura], cz = B.az[A0 + cura], crad = B.arad[Q0 + cura];
-                const float tx = (float)((double)cx + (double)c_spiral[3 * kp] * ((double)crad + probe));
-                const float ty = (float)((double)cy + (double)c_spiral[3 * kp + 1] * ((double)crad + probe));
-                const float tz = (float)((double)cz + (double)c_spiral[3 * kp + 2] * ((double)crad + probe));
-                bool vref = true;                                   // "vrefburried": not inside any touching alpha sphere
-                for (int q = toff[u]; q < toff[u + 1] && vref; q++) {
-                    float4 v = sx[L[tlist[q]]];
-                    if (f_ddist(tx, ty, tz, v.x, v.y, v.z) <= v.w * v.w) vref = false;
-                }
-                if (vref) continue;
-                int hit = -1;
-                for (int j = 0; j < n_sa; j++) {
-                    int a = X.sa[j];
-                    if (same && a == cura) continue;                // asa.c:315 pointer inequality
-                    float dsq = f_ddist(tx, ty, tz, wx[W0 + a], wy[W0 + a], wz[W0 + a]);
-                    double rr = (double)wr[WQ0 + a] + probe;
-                    if ((double)dsq < rr * rr) { hit = a; break; }
-                }
-                if (hit < 0) atomicAdd(&acc[4 * u + pass], 1);
-                else if (pass == 0) atomicAdd(&acc[4 * u + ((double)we[WQ0 + hit] < 2.8 ? 2 : 3)], 1);
-            }
-            // ---- 5. Monte-Carlo volume (voronoi.c:1150-1233), radius ray-1.6, 100 x nb_mcv_iter samples ------------------------------
-            const float correct = -1.6f;
-            if (tid == 0) {
-                float xmin = 0, xmax = 0, ymin = 0, ymax = 0, zmin = 0, zmax = 0, xt, yt, zt;
-                for (int i = 0; i < n; i++) {
-                    float4 v = sx[L[i]];
-                    if (i == 0) {
-                        xmin = v.x - v.w + correct; xmax = v.x + v.w + correct;
-                        ymin = v.y - v.w + correct; ymax = v.y + v.w + correct;
-                        zmin = v.z - v.w + correct; zmax = v.z + v.w + correct;
-                    } else {
-                        if (xmin > (xt = v.x - v.w + correct)) xmin = xt; else if (xmax < (xt = v.x + v.w + correct)) xmax = xt;
-                        if (ymin > (yt = v.y - v.w + correct)) ymin = yt; else if (ymax < (yt = v.y + v.w + correct)) ymax = yt;
-                        if (zmin > (zt = v.z - v.w + correct)) zmin = zt; else if (zmax < (zt = v.z + v.w + correct)) zmax = zt;
-                    }
-                }
-                s_mcbox[0] = xmin; s_mcbox[1] = xmax; s_mcbox[2] = ymin; s_mcbox[3] = ymax; s_mcbox[4] = zmin; s_mcbox[5] = zmax;
-            }
-            for (int i = tid; i < 100; i += nt) s_cnt[i] = 0;
-            // a cluster below min_pock_nb_asph is always dropped (refine.c:124) and never written: no samples are spent on it
-            const bool observable = n >= prm.min_pock_nb_asph;
-            const bool insm = n <= MC_SMEM_SPH;
-            if (insm)
-                for (int i = tid; i < n; i += nt) { float4 v = sx[L[i]]; v.w = (correct + v.w) * (v.w + correct); s_sph[i] = v; }
-            __syncthreads();
-            {
-                const float xmin = s_mcbox[0], xmax = s_mcbox[1], ymin = s_mcbox[2], ymax = s_mcbox[3], zmin = s_mcbox[4], zmax = s_mcbox[5];
-                const int niter = prm.nb_mcv_iter;
-                const unsigned k0 = (unsigned)prm.mc_seed, k1 = (unsigned)(prm.mc_seed >> 32);
-                for (int s = tid; observable && s < 100 * niter; s += nt) {
-                    const int li = s / niter, i = s - li * niter;
-                    unsigned o[4];
-                    philox4x32((unsigned)i, (unsigned)li, (unsigned)c, 0u, k0, k1, o);
-                    const float xr = unif_from_bits(o[0] >> 1, xmin, xmax), yr = unif_from_bits(o[1] >> 1, ymin, ymax),
-                                zr = unif_from_bits(o[2] >> 1, zmin, zmax);
-                    bool in = false;
-                    if (insm) {
-                        for (int j = 0; j < n && !in; j++) {
-                            float4 v = s_sph[j];
-                            float xt = v.x - xr, yt = v.y - yr, zt = v.z - zr;
-                            in = v.w > (xt * xt + yt * yt + zt * zt);
-                        }
-                    } else {
-                        for (int j = 0; j < n && !in; j++) {
-                            float4 v = sx[L[j]];
-                            float xt = v.x - xr, yt = v.y - yr, zt = v.z - zr;
-                            in = ((correct + v.w) * (v.w + correct)) > (xt * xt + yt * yt + zt * zt);
-                        }
-                    }
-                    if (in) atomicAdd(&s_cnt[li], 1);
-                }
-            }
-            __syncthreads();
-        }
-
-        // ---- 6. the sequential float sums, in the reference's order -- warp 0 -------------------------------------------------------
         if (wid == 0) {
+            // ---- 3a. warp 0: the sequential float sums, in the reference's order ---------------------------------------------------
             // sphere pair loop (descriptors.c:186-236): as_density accumulates dist(i,j), i<j, row-major, in ONE float
             float as_density = 0.0f, as_max_dst = -1.0f;
             int mlhd_cnt = 0, nAlphaApol = 0;
@@ -485,6 +390,14 @@ __global__ void __launch_bounds__(K4_THREADS) k_descriptors(BatchDev B, PocketDe
                     }
                 }
             }
+            // first occurrence of every residue id among the contacted atoms (descriptors.c:408 in_tab), one lane per atom
+            for (int u = lane; u < U; u += 32) {
+                const int rid = B.ares[Q0 + uat[u]];
+                bool seen = false;
+                for (int q = 0; q < u && !seen; q++) seen = B.ares[Q0 + uat[q]] == rid;
+                entu[u] = seen ? 0 : 1;                     // ent_u is free once the CSR is built
+            }
+            __syncwarp();
             if (lane == 0) {
                 float mean_r = 0.0f, masph = 0.0f, as_max_r = -1.0f, ps0 = 0.0f, ps1 = 0.0f, ps2 = 0.0f;
                 int napolc = 0;
@@ -510,10 +423,7 @@ __global__ void __launch_bounds__(K4_THREADS) k_descriptors(BatchDev B, PocketDe
                     float flex = 0.0f, hyd = 0.0f, vol = 0.0f;
                     for (int u = 0; u < U; u++) {
                         const int a = Q0 + uat[u];
-                        const int rid = B.ares[a];
-                        bool seen = false;
-                        for (int q = 0; q < u && !seen; q++) seen = B.ares[Q0 + uat[q]] == rid;
-                        if (!seen) {
+                        if (entu[u]) {
                             int aa = B.aaa[a];
                             if (aa >= 0) {
                                 d.aa_compo[aa]++;
@@ -530,45 +440,6 @@ __global__ void __launch_bounds__(K4_THREADS) k_descriptors(BatchDev B, PocketDe
                     d.prop_polar_atm = (float)((double)(((float)nb_polar) / ((float)U)) * 100.0);
                 }
                 d.mean_loc_hyd_dens = nAlphaApol > 0 ? (float)mlhd_cnt / (float)nAlphaApol : 0.0f;
-                if (prm.do_asa_and_volume) {
-                    for (int pass = 0; pass < 2; pass++) {
-                        const double probe = pass == 0 ? 1.4 : 2.2;
-                        for (int u = 0; u < U; u++) {
-                            const int a = Q0 + uat[u];
-                            const size_t ga = (size_t)A0 + uat[u];       // per-structure slot for the side effects
-                            const float crad = B.arad[a];
-                            const int nnb = acc[4 * u + pass];
-                            const float area = (float)((4 * 3.1415926535897932384626433832795 * ((double)crad + probe) * ((double)crad + probe) / (double)(float)100) * (double)nnb);
-                            const bool apolar_atom = (double)B.aen[a] < 2.8;
-                            if (pass == 0) {
-                                fxv[4 * u + 1] = area;              // abpatmp
-                                if (apolar_atom) d.surf_apol_vdw14 = d.surf_apol_vdw14 + area; else d.surf_pol_vdw14 = d.surf_pol_vdw14 + area;
-                                d.surf_vdw14 = d.surf_vdw14 + area;
-                                const float na = (float)acc[4 * u + 2], np = (float)acc[4 * u + 3];
-                                fxv[4 * u + 0] = na / (na + np);     // abpa_sourrounding_prob
-                                fxv[4 * u + 3] = 0.0f;
-                                atomicMax(&Pk.fx_who[2 * ga], c);
-                            } else {
-                                if (apolar_atom) d.surf_apol_vdw22 = d.surf_apol_vdw22 + area;
-                                else {
-                                    const float a14 = fxv[4 * u + 1];
-                                    if (area < a14 && (double)a14 <= 10.0 && (double)area >= 0.0) {
-                                        d.n_abpa += 1;
-                                        fxv[4 * u + 2] = area - a14;   // dA ; a0 = a14
-                                        fxv[4 * u + 3] = 1.0f;
-                                        atomicMax(&Pk.fx_who[2 * ga + 1], c);
-                                    }
-                                    d.surf_pol_vdw22 = d.surf_pol_vdw22 + area;
-                                }
-                                d.surf_vdw22 = d.surf_vdw22 + area;
-                            }
-                        }
-                    }
-                    const float vbox = (s_mcbox[1] - s_mcbox[0]) * (s_mcbox[3] - s_mcbox[2]) * (s_mcbox[5] - s_mcbox[4]);
-                    float sum_volume = 0.0f;
-                    for (int li = 0; li < 100; li++) sum_volume += ((float)s_cnt[li]) / ((float)prm.nb_mcv_iter) * vbox;
-                    d.volume = n >= prm.min_pock_nb_asph ? sum_volume / (float)100 : 0.0f;
-                }
                 d.as_max_dst = as_max_dst;
                 d.apolar_asphere_prop = (float)nAlphaApol / (float)n;
                 d.masph_sacc = masph / (float)n;
@@ -576,9 +447,261 @@ __global__ void __launch_bounds__(K4_THREADS) k_descriptors(BatchDev B, PocketDe
                 d.nb_asph = n;
                 d.as_density = (float)((double)as_density / ((n * n - n) * 0.5));
                 d.as_max_r = as_max_r;
-                d.convex_hull_volume = D->convex_hull_volume;       // written by k_hull_volume before this kernel
-                *D = d;
+                s_desc = d;
             }
+        } else if (full) {
+            // ---- 3b. warps 1..3: surrounding atoms (asa.c:84-112): heavy atoms of pdb_w_lig within ray+1 of a sphere, atom order ----
+            const int wt = tid - 32, ww = wid - 1;
+            float bmn[3] = {3e38f, 3e38f, 3e38f}, bmx[3] = {-3e38f, -3e38f, -3e38f};
+            for (int i = wt; i < n; i += K4_WORKERS) {
+                float4 v = sx[L[i]];
+                float rp = v.w + 1.01f;
+                bmn[0] = fminf(bmn[0], v.x - rp); bmn[1] = fminf(bmn[1], v.y - rp); bmn[2] = fminf(bmn[2], v.z - rp);
+                bmx[0] = fmaxf(bmx[0], v.x + rp); bmx[1] = fmaxf(bmx[1], v.y + rp); bmx[2] = fmaxf(bmx[2], v.z + rp);
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1)
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    bmn[q] = fminf(bmn[q], __shfl_xor_sync(0xffffffffu, bmn[q], d));
+                    bmx[q] = fmaxf(bmx[q], __shfl_xor_sync(0xffffffffu, bmx[q], d));
+                }
+            if (lane == 0) for (int q = 0; q < 3; q++) { s_bb[ww][q] = bmn[q]; s_bb[ww][3 + q] = bmx[q]; }
+            workers_sync();
+            for (int w = 0; w < 3; w++)
+                for (int q = 0; q < 3; q++) { bmn[q] = fminf(bmn[q], s_bb[w][q]); bmx[q] = fmaxf(bmx[q], s_bb[w][3 + q]); }
+            // every worker warp scans one contiguous third of the atoms and appends, in order, to its own segment of X.sa
+            const int seg = (nw + 2) / 3, a_lo = min(nw, ww * seg), a_hi = min(nw, a_lo + seg);
+            int nseg = 0;
+            for (int base = a_lo; base < a_hi; base += 32) {
+                const int i = base + lane;
+                bool in = false;
+                if (i < a_hi && !(wf[WQ0 + i] & whmask)) {
+                    const float x = wx[W0 + i], y = wy[W0 + i], z = wz[W0 + i];
+                    if (x >= bmn[0] && x <= bmx[0] && y >= bmn[1] && y <= bmx[1] && z >= bmn[2] && z <= bmx[2]) {
+                        for (int q = 0; q < n && !in; q++) {
+                            const float4 v = sx[L[q]];
+                            const double rp = (double)v.w + 1.0;
+                            in = (double)f_ddist(x, y, z, v.x, v.y, v.z) < rp * rp;
+                        }
+                    }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, in);
+                if (in) X.sa[a_lo + nseg + __popc(bal & ((1u << lane) - 1u))] = i;
+                nseg += __popc(bal);
+            }
+            if (lane == 0) s_segcnt[ww] = nseg;
+            workers_sync();
+            // ---- 4. 100-point spiral SASA, probes 1.4 and 2.2 (asa.c:240-419): one warp per contacted atom ----------------------------
+            for (int u = ww; u < U; u += 3) {
+                const int cura = uat[u];
+                const float cx = B.ax[A0 + cura], cy = B.ay[A0 + cura], cz = B.az[A0 + cura], crad = B.arad[Q0 + cura];
+                // burial candidates: surrounding atoms close enough to bury a point of this atom at either probe, in sa order
+                const float reach = crad + 2.2f + 2.2f + 0.01f;
+                int ncand = 0;
+                bool overflow = false;
+                for (int sg = 0; sg < 3 && !overflow; sg++) {
+                    const int s0 = min(nw, sg * seg), cnt = s_segcnt[sg];
+                    for (int base = 0; base < cnt && !overflow; base += 32) {
+                        const int j = base + lane;
+                        bool take = false;
+                        int a = -1;
+                        float ax_ = 0, ay_ = 0, az_ = 0, ar_ = 0;
+                        if (j < cnt) {
+                            a = X.sa[s0 + j];
+                            if (!(same && a == cura)) {                 // asa.c:315 pointer inequality
+                                ax_ = wx[W0 + a]; ay_ = wy[W0 + a]; az_ = wz[W0 + a]; ar_ = wr[WQ0 + a];
+                                const float dx = ax_ - cx, dy = ay_ - cy, dz = az_ - cz, rr = reach + ar_;
+                                take = dx * dx + dy * dy + dz * dz <= rr * rr;
+                            }
+                        }
+                        const unsigned bal = __ballot_sync(0xffffffffu, take);
+                        if (ncand + __popc(bal) > ASA_CAND) { overflow = true; break; }
+                        if (take) {
+                            const int pos = ncand + __popc(bal & ((1u << lane) - 1u));
+                            s_cand[ww][pos] = make_float4(ax_, ay_, az_, ar_);
+                            s_candapol[ww][pos] = (double)we[WQ0 + a] < 2.8 ? 1 : 0;
+                        }
+                        ncand += __popc(bal);
+                    }
+                }
+                __syncwarp();
+                for (int it = lane; it < 200; it += 32) {
+                    const int pass = it >= 100 ? 1 : 0, kp = it - 100 * pass;
+                    const double probe = pass == 0 ? 1.4 : 2.2;
+                    const float tx = (float)((double)cx + (double)c_spiral[3 * kp] * ((double)crad + probe));
+                    const float ty = (float)((double)cy + (double)c_spiral[3 * kp + 1] * ((double)crad + probe));
+                    const float tz = (float)((double)cz + (double)c_spiral[3 * kp + 2] * ((double)crad + probe));
+                    bool vref = true;                                   // "vrefburried": not inside any touching alpha sphere
+                    for (int q = toff[u]; q < toff[u + 1] && vref; q++) {
+                        float4 v = sx[L[tlist[q]]];
+                        if (f_ddist(tx, ty, tz, v.x, v.y, v.z) <= v.w * v.w) vref = false;
+                    }
+                    if (vref) continue;
+                    int hit = -1;       // -1 none, 0 polar burying atom, 1 apolar burying atom
+                    if (!overflow) {
+                        for (int j = 0; j < ncand; j++) {
+                            const float4 q = s_cand[ww][j];
+                            const float dsq = f_ddist(tx, ty, tz, q.x, q.y, q.z);
+                            const double rr = (double)q.w + probe;
+                            if ((double)dsq < rr * rr) { hit = s_candapol[ww][j]; break; }
+                        }
+                    } else {
+                        for (int sg = 0; sg < 3 && hit < 0; sg++) {
+                            const int s0 = min(nw, sg * seg), cnt = s_segcnt[sg];
+                            for (int j = 0; j < cnt; j++) {
+                                const int a = X.sa[s0 + j];
+                                if (same && a == cura) continue;
+                                const float dsq = f_ddist(tx, ty, tz, wx[W0 + a], wy[W0 + a], wz[W0 + a]);
+                                const double rr = (double)wr[WQ0 + a] + probe;
+                                if ((double)dsq < rr * rr) { hit = (double)we[WQ0 + a] < 2.8 ? 1 : 0; break; }
+                            }
+                        }
+                    }
+                    if (hit < 0) atomicAdd(&acc[4 * u + pass], 1);
+                    else if (pass == 0) atomicAdd(&acc[4 * u + (hit ? 2 : 3)], 1);
+                }
+                __syncwarp();
+            }
+            // ---- 5. Monte-Carlo volume (voronoi.c:1150-1233), radius ray-1.6, 100 x nb_mcv_iter samples ------------------------------
+            if (observable) {
+                const float xmin = s_mcbox[0], xmax = s_mcbox[1], ymin = s_mcbox[2], ymax = s_mcbox[3], zmin = s_mcbox[4], zmax = s_mcbox[5];
+                // cell grid over the box: a sample only meets the spheres registered in its cell (the test is an OR: order-free)
+                if (wt == 0) {
+                    int mode = 0;
+                    if (insm && n >= 24) {
+                        const float ex = xmax - xmin, ey = ymax - ymin, ez = zmax - zmin;
+                        const int dx = max(1, min(8, (int)(ex / 4.5f))), dy = max(1, min(8, (int)(ey / 4.5f))), dz = max(1, min(8, (int)(ez / 4.5f)));
+                        s_mcdim[0] = dx; s_mcdim[1] = dy; s_mcdim[2] = dz;
+                        s_mch[0] = (float)dx / ex; s_mch[1] = (float)dy / ey; s_mch[2] = (float)dz / ez;
+                        mode = (ex > 0 && ey > 0 && ez > 0) ? 1 : 0;
+                    }
+                    s_mcmode = mode;
+                }
+                workers_sync();
+                if (s_mcmode) {
+                    const int dx = s_mcdim[0], dy = s_mcdim[1], dz = s_mcdim[2], ncell = dx * dy * dz;
+                    const float hx = s_mch[0], hy = s_mch[1], hz = s_mch[2];
+                    for (int i = wt; i <= ncell; i += K4_WORKERS) s_cell[i] = 0;
+                    workers_sync();
+                    for (int pass = 0; pass < 2; pass++) {
+                        for (int i = wt; i < n; i += K4_WORKERS) {
+                            const float4 v = s_sph[i];
+                            const float r = sqrtf(fmaxf(v.w, 0.0f)) + 2e-3f;
+                            const int x0 = max(0, min(dx - 1, (int)floorf((v.x - r - xmin) * hx))), x1 = max(0, min(dx - 1, (int)floorf((v.x + r - xmin) * hx)));
+                            const int y0 = max(0, min(dy - 1, (int)floorf((v.y - r - ymin) * hy))), y1 = max(0, min(dy - 1, (int)floorf((v.y + r - ymin) * hy)));
+                            const int z0 = max(0, min(dz - 1, (int)floorf((v.z - r - zmin) * hz))), z1 = max(0, min(dz - 1, (int)floorf((v.z + r - zmin) * hz)));
+                            for (int a = x0; a <= x1; a++) for (int b = y0; b <= y1; b++) for (int d = z0; d <= z1; d++) {
+                                const int cid = (a * dy + b) * dz + d;
+                                if (pass == 0) atomicAdd(&s_cell[cid], 1);
+                                else { const int slot = atomicAdd(&s_cell[cid], 1); if (slot < MC_ENTRIES) s_ent[slot] = (unsigned short)i; }
+                            }
+                        }
+                        workers_sync();
+                        if (pass == 0) {
+                            if (ww == 0) {          // exclusive scan of the cell counts by one warp
+                                int run = 0;
+                                for (int base = 0; base <= ncell; base += 32) {
+                                    const int i = base + lane;
+                                    const int v = i <= ncell ? s_cell[i] : 0;
+                                    const int inc = warp_incl_scan(v);
+                                    if (i <= ncell) s_cell[i] = run + inc - v;
+                                    run += __shfl_sync(0xffffffffu, inc, 31);
+                                }
+                                if (lane == 0 && run > MC_ENTRIES) s_mcmode = 0;       // does not fit: every sample meets every sphere
+                            }
+                            workers_sync();
+                            if (!s_mcmode) break;
+                        }
+                    }
+                    // after the fill, s_cell[c] = END of cell c; start = end of cell c-1
+                }
+                workers_sync();
+                const int mode = s_mcmode;
+                const int dx = s_mcdim[0], dy = s_mcdim[1], dz = s_mcdim[2];
+                const float hx = s_mch[0], hy = s_mch[1], hz = s_mch[2];
+                const int niter = prm.nb_mcv_iter;
+                const unsigned k0 = (unsigned)prm.mc_seed, k1 = (unsigned)(prm.mc_seed >> 32);
+                for (int s = wt; s < 100 * niter; s += K4_WORKERS) {
+                    const int li = s / niter, i = s - li * niter;
+                    unsigned o[4];
+                    philox4x32((unsigned)i, (unsigned)li, (unsigned)c, 0u, k0, k1, o);
+                    const float xr = unif_from_bits(o[0] >> 1, xmin, xmax), yr = unif_from_bits(o[1] >> 1, ymin, ymax),
+                                zr = unif_from_bits(o[2] >> 1, zmin, zmax);
+                    bool in = false;
+                    if (mode) {
+                        const int a = max(0, min(dx - 1, (int)floorf((xr - xmin) * hx))), b = max(0, min(dy - 1, (int)floorf((yr - ymin) * hy))),
+                                  d = max(0, min(dz - 1, (int)floorf((zr - zmin) * hz)));
+                        const int cid = (a * dy + b) * dz + d;
+                        const int e0 = cid ? s_cell[cid - 1] : 0, e1 = s_cell[cid];
+                        for (int j = e0; j < e1 && !in; j++) {
+                            const float4 v = s_sph[s_ent[j]];
+                            const float xt = v.x - xr, yt = v.y - yr, zt = v.z - zr;
+                            in = v.w > (xt * xt + yt * yt + zt * zt);
+                        }
+                    } else if (insm) {
+                        for (int j = 0; j < n && !in; j++) {
+                            const float4 v = s_sph[j];
+                            const float xt = v.x - xr, yt = v.y - yr, zt = v.z - zr;
+                            in = v.w > (xt * xt + yt * yt + zt * zt);
+                        }
+                    } else {
+                        for (int j = 0; j < n && !in; j++) {
+                            const float4 v = sx[L[j]];
+                            const float xt = v.x - xr, yt = v.y - yr, zt = v.z - zr;
+                            in = ((correct + v.w) * (v.w + correct)) > (xt * xt + yt * yt + zt * zt);
+                        }
+                    }
+                    if (in) atomicAdd(&s_cnt[li], 1);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- 6. the ASA / volume part of the record (needs the workers' counts) -- one thread ----------------------------------------
+        if (tid == 0) {
+            fpk_desc d = s_desc;
+            if (full) {
+                for (int pass = 0; pass < 2; pass++) {
+                    const double probe = pass == 0 ? 1.4 : 2.2;
+                    for (int u = 0; u < U; u++) {
+                        const int a = Q0 + uat[u];
+                        const size_t ga = (size_t)A0 + uat[u];       // per-structure slot for the side effects
+                        const float crad = B.arad[a];
+                        const int nnb = acc[4 * u + pass];
+                        const float area = (float)((4 * 3.1415926535897932384626433832795 * ((double)crad + probe) * ((double)crad + probe) / (double)(float)100) * (double)nnb);
+                        const bool apolar_atom = (double)B.aen[a] < 2.8;
+                        if (pass == 0) {
+                            fxv[4 * u + 1] = area;              // abpatmp
+                            if (apolar_atom) d.surf_apol_vdw14 = d.surf_apol_vdw14 + area; else d.surf_pol_vdw14 = d.surf_pol_vdw14 + area;
+                            d.surf_vdw14 = d.surf_vdw14 + area;
+                            const float na = (float)acc[4 * u + 2], np = (float)acc[4 * u + 3];
+                            fxv[4 * u + 0] = na / (na + np);     // abpa_sourrounding_prob
+                            fxv[4 * u + 3] = 0.0f;
+                            atomicMax(&Pk.fx_who[2 * ga], c);
+                        } else {
+                            if (apolar_atom) d.surf_apol_vdw22 = d.surf_apol_vdw22 + area;
+                            else {
+                                const float a14 = fxv[4 * u + 1];
+                                if (area < a14 && (double)a14 <= 10.0 && (double)area >= 0.0) {
+                                    d.n_abpa += 1;
+                                    fxv[4 * u + 2] = area - a14;   // dA ; a0 = a14
+                                    fxv[4 * u + 3] = 1.0f;
+                                    atomicMax(&Pk.fx_who[2 * ga + 1], c);
+                                }
+                                d.surf_pol_vdw22 = d.surf_pol_vdw22 + area;
+                            }
+                            d.surf_vdw22 = d.surf_vdw22 + area;
+                        }
+                    }
+                }
+                const float vbox = (s_mcbox[1] - s_mcbox[0]) * (s_mcbox[3] - s_mcbox[2]) * (s_mcbox[5] - s_mcbox[4]);
+                float sum_volume = 0.0f;
+                for (int li = 0; li < 100; li++) sum_volume += ((float)s_cnt[li]) / ((float)prm.nb_mcv_iter) * vbox;
+                d.volume = observable ? sum_volume / (float)100 : 0.0f;
+            }
+            d.convex_hull_volume = D->convex_hull_volume;       // written by k_hull_volume before this kernel
+            *D = d;
         }
     }
 }
