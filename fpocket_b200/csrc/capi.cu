@@ -323,7 +323,7 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
     // K1 shared-memory plan: WarpCav records + the sites as int32 lattice offsets. Two blocks per SM when the largest
     // structure fits in half an SM's shared memory, else one block, else the sites stay in global memory (pi_cap 0).
     {
-        const size_t fixed = 8 * sizeof(WarpCav), stat = 2048, sm_total = 227 * 1024, per_block_reserved = 1024;
+        const size_t fixed = FPK_BD_BYTES + 8 * sizeof(WarpCav), stat = 2048, sm_total = 227 * 1024, per_block_reserved = 1024;
         const size_t need = fixed + 12 * (size_t)b->max_sites + 16;
         const size_t half = (sm_total - 2 * per_block_reserved) / 2 - stat, full = sm_total - per_block_reserved - stat;
         if (need <= half) { b->k1_picap = b->max_sites; b->k1_dsm = need; }
@@ -485,7 +485,7 @@ static int batch_run(fpk_batch *b)
     const long long NC = b->tot_clusters, NS = b->tot_spheres;
     int occH = 8, occD = 8;
     b->hull_picap = std::min(max_ns, 1024);
-    b->hull_dsm = (HULL_THREADS / 32) * sizeof(WarpCav) + 12 * (size_t)b->hull_picap + 16;
+    b->hull_dsm = FPK_BD_BYTES + (HULL_THREADS / 32) * sizeof(WarpCav) + 12 * (size_t)b->hull_picap + 16;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occH, k_hull_volume, HULL_THREADS, b->hull_dsm);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occD, k_descriptors, K4_THREADS, 0);
     occH = std::max(1, std::min(occH, 8)); occD = std::max(1, std::min(occD, 8));

@@ -26,6 +26,26 @@ struct WarpCav {                        // one per warp, shared memory
     unsigned short rl[2 * WCAV + 8];    // compact list of rim faces (4 * i + q), filled by pass A of the commit
 };
 
+// Shared-memory state of one block's triangulation. Dynamic shared memory = [BlockDel][WarpCav x warps][sites]; every function
+// reaches it through the accessors below so that the compiler sees SHARED addresses (LDS/STS/ATOMS), not generic ones.
+enum { FPK_MAXWARPS = 8 };
+struct BlockDel {
+    DelaunayCtx C;
+    int cnt[C_COUNT];
+    int tinfo[4 * FPK_MAXWARPS], cursor[2 * FPK_MAXWARPS];
+    int first4[4];
+    int bigw;
+};
+#define FPK_BD_BYTES ((sizeof(BlockDel) + 15) & ~(size_t)15)
+__device__ __forceinline__ unsigned char *dsm_base() { extern __shared__ __align__(16) unsigned char fpk_dsm[]; return fpk_dsm; }
+__device__ __forceinline__ BlockDel &blk() { return *reinterpret_cast<BlockDel *>(dsm_base()); }
+__device__ __forceinline__ WarpCav &my_cav() { return reinterpret_cast<WarpCav *>(dsm_base() + FPK_BD_BYTES)[threadIdx.x >> 5]; }
+__device__ __forceinline__ int *sm_sites() { return reinterpret_cast<int *>(dsm_base() + FPK_BD_BYTES + (blockDim.x >> 5) * sizeof(WarpCav)); }
+#define TVp(t) (tet + 8 * (size_t)(t))
+#define TNp(t) (tet + 8 * (size_t)(t) + 4)
+#define OWNp(t) (claim + 2 * (size_t)(t))
+#define RIMp(t) (claim + 2 * (size_t)(t) + 1)
+
 struct P3 { double x, y, z; };
 __device__ __forceinline__ P3 ldp(const int *Pi, int i)
 {
@@ -148,23 +168,31 @@ __device__ __forceinline__ int orient_sub_v(const int *Pi, const int4 &v, int sl
 __device__ __forceinline__ int inf_slot4(const int4 &v) { return v.x < 0 ? 0 : (v.y < 0 ? 1 : (v.z < 0 ? 2 : (v.w < 0 ? 3 : -1))); }
 
 // in_conflict of delaunay.cuh on the shared-memory sites; xn = neighbours of the tet (needed for a ghost whose facet plane holds p)
-__device__ __forceinline__ bool in_conflict_v(const DelaunayCtx &c, const int *Pi, const int4 &v, const int4 &xn, int p, const P3 &pp)
+__device__ __forceinline__ bool in_conflict_v(const int *tet, const int *Pi, const int4 &v, const int4 &xn, int p, const P3 &pp)
 {
     const int k = inf_slot4(v);
     if (k < 0) return insphere_sos_v(Pi, v, p, pp) > 0;
     const int o = orient_sub_v(Pi, v, k, p, pp);
     if (o) return o > 0;
-    const int4 w = *reinterpret_cast<const int4 *>(FPK_TV(c, comp4(xn, k)));
+    const int4 w = *reinterpret_cast<const int4 *>(TVp(comp4(xn, k)));
     return insphere_sos_v(Pi, w, p, pp) > 0;
 }
 
 __device__ __forceinline__ int2 ldcg2(const int *p) { return __ldcg(reinterpret_cast<const int2 *>(p)); }
 
 // ---- claim phase: locate the point, flood its cavity while claiming it (all 32 lanes, identical arguments) ------------------------
-__device__ __noinline__ int w2_locate_and_claim(DelaunayCtx &c, WarpCav &W, const int *Pi, int rank, int own_hint, int *ncav_out)
+template <bool SM> __device__ __noinline__ int w2_locate_and_claim(int rank, int own_hint, int *ncav_out)
 {
+    BlockDel &S = blk();
+    DelaunayCtx &c = S.C;
+    WarpCav &W = my_cav();
+    const int *Pi = SM ? sm_sites() : c.Pi;
+    int *const tet = c.tet, *const claim = c.claim, *const hint = c.hint;
+    const int *const order = c.order;
+    __builtin_assume(__isGlobal(tet)); __builtin_assume(__isGlobal(claim)); __builtin_assume(__isGlobal(hint)); __builtin_assume(__isGlobal(order));
+    if (!SM) __builtin_assume(__isGlobal(Pi));
     const int lane = threadIdx.x & 31;
-    const int p = c.order[rank];
+    const int p = order[rank];
     const int prio = prio_of(rank);
     const P3 pp = ldp(Pi, p);
     *ncav_out = 0;
@@ -174,26 +202,26 @@ __device__ __noinline__ int w2_locate_and_claim(DelaunayCtx &c, WarpCav &W, cons
         const int *e = Pi + 3 * (size_t)p;
         int ix = (int)((double)e[0] * c.hinv), iy = (int)((double)e[1] * c.hinv), iz = (int)((double)e[2] * c.hinv);
         ix = ix < 0 ? 0 : (ix >= g ? g - 1 : ix); iy = iy < 0 ? 0 : (iy >= g ? g - 1 : iy); iz = iz < 0 ? 0 : (iz >= g ? g - 1 : iz);
-        t = c.hint[(ix * g + iy) * g + iz];
+        t = hint[(ix * g + iy) * g + iz];
     }
-    if (t < 0) t = c.cnt[C_RECENT];
+    if (t < 0) t = S.cnt[C_RECENT];
     int hops = 0;
-    for (int hop = 0; hop < 64 && FPK_TV(c, t)[0] == T_DEAD; hop++) { t = FPK_TN(c, t)[0]; hops++; }
-    if (hops && lane == 0) atomicAdd(&c.cnt[C_NHOP], hops);
-    if (FPK_TV(c, t)[0] == T_DEAD) {
-        t = c.cnt[C_RECENT];
-        for (int hop = 0; hop < 64 && FPK_TV(c, t)[0] == T_DEAD; hop++) t = FPK_TN(c, t)[0];
-        if (FPK_TV(c, t)[0] == T_DEAD) return ST_ERR;
+    for (int hop = 0; hop < 64 && TVp(t)[0] == T_DEAD; hop++) { t = TNp(t)[0]; hops++; }
+    if (hops && lane == 0) atomicAdd(&S.cnt[C_NHOP], hops);
+    if (TVp(t)[0] == T_DEAD) {
+        t = S.cnt[C_RECENT];
+        for (int hop = 0; hop < 64 && TVp(t)[0] == T_DEAD; hop++) t = TNp(t)[0];
+        if (TVp(t)[0] == T_DEAD) return ST_ERR;
     }
     int4 v, nb;
-    const int maxsteps = c.cnt[C_NTET] + 64;
+    const int maxsteps = S.cnt[C_NTET] + 64;
     for (int steps = 0;; steps++) {         // visibility walk: the four face tests of a step run on four lanes
         if (steps > maxsteps) return ST_ERR;
-        v = *reinterpret_cast<const int4 *>(FPK_TV(c, t));
-        nb = *reinterpret_cast<const int4 *>(FPK_TN(c, t));
+        v = *reinterpret_cast<const int4 *>(TVp(t));
+        nb = *reinterpret_cast<const int4 *>(TNp(t));
         const int k = inf_slot4(v);
         if (k >= 0) {
-            if (in_conflict_v(c, Pi, v, nb, p, pp)) break;
+            if (in_conflict_v(tet, Pi, v, nb, p, pp)) break;
             t = comp4(nb, k);
             continue;
         }
@@ -206,13 +234,13 @@ __device__ __noinline__ int w2_locate_and_claim(DelaunayCtx &c, WarpCav &W, cons
         }
         const unsigned dupm = __ballot_sync(FPK_FULL, dup) & 0xfu, neg = __ballot_sync(FPK_FULL, o < 0) & 0xfu;
         if (dupm) { *ncav_out = comp4(v, __ffs(dupm) - 1); return ST_DUP; }      // coincident site: reports the vertex it duplicates
-        if (!neg) { if (lane == 0) { atomicAdd(&c.cnt[C_NWALK], steps + 1); atomicAdd(&c.cnt[C_NATTEMPT], 1); } break; }
+        if (!neg) { if (lane == 0) { atomicAdd(&S.cnt[C_NWALK], steps + 1); atomicAdd(&S.cnt[C_NATTEMPT], 1); } break; }
         t = comp4(nb, __ffs(neg) - 1);
     }
     int st = ST_CLAIMED;
     if (lane == 0) {
-        if (__ldcg(FPK_RIM(c, t)) < prio) st = ST_LOST;
-        else if (atomicMin(FPK_OWN(c, t), prio) < prio) st = ST_LOST;
+        if (__ldcg(RIMp(t)) < prio) st = ST_LOST;
+        else if (atomicMin(OWNp(t), prio) < prio) st = ST_LOST;
         else { W.id[0] = t; W.v[0] = v; W.n[0] = nb; }
     }
     st = __shfl_sync(FPK_FULL, st, 0);
@@ -230,21 +258,21 @@ __device__ __noinline__ int w2_locate_and_claim(DelaunayCtx &c, WarpCav &W, cons
         int4 xv, xn;
         if (active) {
             x = reinterpret_cast<const int *>(&W.n[f])[q];
-            const int2 cl = ldcg2(FPK_OWN(c, x));                       // one round trip: claim pair and the tet record together
-            xv = *reinterpret_cast<const int4 *>(FPK_TV(c, x));
-            xn = *reinterpret_cast<const int4 *>(FPK_TN(c, x));
+            const int2 cl = ldcg2(OWNp(x));                       // one round trip: claim pair and the tet record together
+            xv = *reinterpret_cast<const int4 *>(TVp(x));
+            xn = *reinterpret_cast<const int4 *>(TNp(x));
             if (cl.x < prio) lost = true;                               // in (or next to) a stronger cavity
             else if (cl.x == prio) isrim = false;                       // already in my cavity: interior face
             else if (cl.y == prio) isrim = true;                        // already known as my rim
-            else if (in_conflict_v(c, Pi, xv, xn, p, pp)) {
+            else if (in_conflict_v(tet, Pi, xv, xn, p, pp)) {
                 if (cl.y < prio) lost = true;                           // a stronger insertion rewrites x's adjacency
                 else {
-                    const int old = atomicMin(FPK_OWN(c, x), prio);
+                    const int old = atomicMin(OWNp(x), prio);
                     if (old < prio) lost = true;
                     else if (old != prio) add = true;                   // exactly one lane sees the transition to prio
                 }
             } else {
-                atomicMin(FPK_RIM(c, x), prio);
+                atomicMin(RIMp(x), prio);
                 isrim = true;
             }
         }
@@ -259,40 +287,53 @@ __device__ __noinline__ int w2_locate_and_claim(DelaunayCtx &c, WarpCav &W, cons
         __syncwarp();
         if (lostm) { *ncav_out = ncav; return ST_LOST; }
     }
-    if (lane == 0) atomicAdd(&c.cnt[C_NLEVEL], nlev);
+    if (lane == 0) atomicAdd(&S.cnt[C_NLEVEL], nlev);
     *ncav_out = ncav;
     return ST_CLAIMED;
 }
 
-__device__ __forceinline__ bool w2_verify_claims(const DelaunayCtx &c, const WarpCav &W, int rank, int ncav)
+__device__ __forceinline__ bool w2_verify_claims(int rank, int ncav)
 {
+    const WarpCav &W = my_cav();
+    const int *const claim = blk().C.claim;
+    __builtin_assume(__isGlobal(claim));
     const int lane = threadIdx.x & 31, prio = prio_of(rank), q = lane & 3;
     bool ok = true;
     for (int base = 0; base < ncav; base += 8) {
         const int f = base + (lane >> 2);
         if (f < ncav) {
-            if (__ldcg(FPK_OWN(c, reinterpret_cast<const int *>(&W.n[f])[q])) < prio) ok = false;           // rim tet inside a stronger cavity
-            if (q == 0) { const int2 cl = ldcg2(FPK_OWN(c, W.id[f])); if (cl.x != prio || cl.y < prio) ok = false; }
+            if (__ldcg(OWNp(reinterpret_cast<const int *>(&W.n[f])[q])) < prio) ok = false;           // rim tet inside a stronger cavity
+            if (q == 0) { const int2 cl = ldcg2(OWNp(W.id[f])); if (cl.x != prio || cl.y < prio) ok = false; }
         }
     }
     return __all_sync(FPK_FULL, ok);
 }
 
-__device__ __forceinline__ void w2_reset_claims(DelaunayCtx &c, const WarpCav &W, int ncav)
+__device__ __forceinline__ void w2_reset_claims(int ncav)
 {
+    const WarpCav &W = my_cav();
+    int *const claim = blk().C.claim;
+    __builtin_assume(__isGlobal(claim));
     const int lane = threadIdx.x & 31, q = lane & 3;
     for (int base = 0; base < ncav; base += 8) {
         const int f = base + (lane >> 2);
         if (f < ncav) {
-            *reinterpret_cast<int2 *>(FPK_OWN(c, reinterpret_cast<const int *>(&W.n[f])[q])) = make_int2(OWN_FREE, OWN_FREE);
-            if (q == 0) *reinterpret_cast<int2 *>(FPK_OWN(c, W.id[f])) = make_int2(OWN_FREE, OWN_FREE);
+            *reinterpret_cast<int2 *>(OWNp(reinterpret_cast<const int *>(&W.n[f])[q])) = make_int2(OWN_FREE, OWN_FREE);
+            if (q == 0) *reinterpret_cast<int2 *>(OWNp(W.id[f])) = make_int2(OWN_FREE, OWN_FREE);
         }
     }
 }
 
 // a winner replaces its cavity (in W) by the star of p. Returns a new tet (the warp's next walk starts there) or -1.
-__device__ __noinline__ int w2_commit_insertion(DelaunayCtx &c, WarpCav &W, int rank, int ncav, int popstack)
+__device__ __noinline__ int w2_commit_insertion(int rank, int ncav, int popstack)
 {
+    BlockDel &S = blk();
+    DelaunayCtx &c = S.C;
+    WarpCav &W = my_cav();
+    int *const tet = c.tet, *const claim = c.claim, *const mark = c.mark, *const hint = c.hint;
+    int *const popst = c.freest[popstack], *const pushst = c.freest[popstack ^ 1];
+    __builtin_assume(__isGlobal(tet)); __builtin_assume(__isGlobal(claim)); __builtin_assume(__isGlobal(mark)); __builtin_assume(__isGlobal(hint));
+    __builtin_assume(__isGlobal(popst)); __builtin_assume(__isGlobal(pushst)); __builtin_assume(__isGlobal(c.order));
     const int lane = threadIdx.x & 31;
     const int p = c.order[rank];
     for (int i = lane; i < WHASH; i += 32) { W.hkey[i] = FPK_HEMPTY; W.hval[i] = -1; }
@@ -307,15 +348,15 @@ __device__ __noinline__ int w2_commit_insertion(DelaunayCtx &c, WarpCav &W, int 
         if (!m) continue;
         const int cnt = __popc(m), my = __popc(m & ((1u << lane) - 1u));
         int fb = 0;
-        if (lane == 0) fb = atomicAdd(&c.cnt[C_NFREE0 + popstack], -cnt);
+        if (lane == 0) fb = atomicAdd(&S.cnt[C_NFREE0 + popstack], -cnt);
         fb = __shfl_sync(FPK_FULL, fb, 0);
         const int fi = fb - 1 - my;                                          // index into the free stack, < 0: take a fresh slot
         const unsigned fresh = __ballot_sync(FPK_FULL, isrim && fi < 0);
         int nbase = 0;
-        if (fresh && lane == 0) nbase = atomicAdd(&c.cnt[C_NTET], __popc(fresh));
+        if (fresh && lane == 0) nbase = atomicAdd(&S.cnt[C_NTET], __popc(fresh));
         nbase = __shfl_sync(FPK_FULL, nbase, 0);
         if (isrim) {
-            int nt = fi >= 0 ? c.freest[popstack][fi] : nbase + __popc(fresh & ((1u << lane) - 1u));
+            int nt = fi >= 0 ? popst[fi] : nbase + __popc(fresh & ((1u << lane) - 1u));
             if (nt >= c.cap) { bad = true; nt = -1; }
             if (nt >= 0) {
                 const int cur = W.id[f];
@@ -323,11 +364,11 @@ __device__ __noinline__ int w2_commit_insertion(DelaunayCtx &c, WarpCav &W, int 
                 const int o = reinterpret_cast<const int *>(&W.n[f])[q];
                 int4 nv = v;
                 if (q == 0) nv.x = p; else if (q == 1) nv.y = p; else if (q == 2) nv.z = p; else nv.w = p;
-                *reinterpret_cast<int4 *>(FPK_TV(c, nt)) = nv;
-                FPK_TN(c, nt)[q] = o;
-                *reinterpret_cast<int2 *>(FPK_OWN(c, nt)) = make_int2(OWN_FREE, OWN_FREE);
-                FPK_MARK(c, nt) = -1;                       // the serial path (delaunay.cuh) tests marks of live tets
-                const int4 ov = *reinterpret_cast<const int4 *>(FPK_TV(c, o)), on = *reinterpret_cast<const int4 *>(FPK_TN(c, o));
+                *reinterpret_cast<int4 *>(TVp(nt)) = nv;
+                TNp(nt)[q] = o;
+                *reinterpret_cast<int2 *>(OWNp(nt)) = make_int2(OWN_FREE, OWN_FREE);
+                mark[2 * (size_t)nt] = -1;                       // the serial path (delaunay.cuh) tests marks of live tets
+                const int4 ov = *reinterpret_cast<const int4 *>(TVp(o)), on = *reinterpret_cast<const int4 *>(TNp(o));
                 // the slot of o that faced cur through this face: its vertex there is the one of o that is not on the face
                 const int vq = reinterpret_cast<const int *>(&W.v[f])[q];
                 int r = -1;
@@ -339,7 +380,7 @@ __device__ __noinline__ int w2_commit_insertion(DelaunayCtx &c, WarpCav &W, int 
                     if (on.x == cur && ov.x == vq) r = 0; else if (on.y == cur && ov.y == vq) r = 1;
                     else if (on.z == cur && ov.z == vq) r = 2; else if (on.w == cur && ov.w == vq) r = 3;
                 }
-                if (r >= 0) FPK_TN(c, o)[r] = nt; else bad = true;
+                if (r >= 0) TNp(o)[r] = nt; else bad = true;
                 reinterpret_cast<int *>(&W.n[f])[q] = nt;
                 W.rl[nrim + my] = (unsigned short)e;
                 mynew = min(mynew, nt);
@@ -347,7 +388,7 @@ __device__ __noinline__ int w2_commit_insertion(DelaunayCtx &c, WarpCav &W, int 
         }
         nrim += cnt;
     }
-    if (__any_sync(FPK_FULL, bad)) { if (lane == 0) c.cnt[C_STATUS] = DERR_CAPACITY; return -1; }
+    if (__any_sync(FPK_FULL, bad)) { if (lane == 0) S.cnt[C_STATUS] = DERR_CAPACITY; return -1; }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) mynew = min(mynew, __shfl_xor_sync(FPK_FULL, mynew, d));
     const int firstnew = mynew;
@@ -369,18 +410,17 @@ __device__ __noinline__ int w2_commit_insertion(DelaunayCtx &c, WarpCav &W, int 
             if (old == FPK_HEMPTY || old == key) break;
         }
         const int prev = atomicExch(&W.hval[slot], 4 * nt + j);
-        if (prev >= 0) { FPK_TN(c, nt)[j] = prev >> 2; FPK_TN(c, prev >> 2)[prev & 3] = nt; }
+        if (prev >= 0) { TNp(nt)[j] = prev >> 2; TNp(prev >> 2)[prev & 3] = nt; }
     }
     __syncwarp();
     // ---- pass C: the cavity dies; its slots go to the stack the NEXT sub-round pops ---------------------------------------------------
     int base = 0;
-    if (lane == 0) base = atomicAdd(&c.cnt[C_NFREE0 + (popstack ^ 1)], ncav);
+    if (lane == 0) base = atomicAdd(&S.cnt[C_NFREE0 + (popstack ^ 1)], ncav);
     base = __shfl_sync(FPK_FULL, base, 0);
-    int *pushst = c.freest[popstack ^ 1];
     for (int i = lane; i < ncav; i += 32) {
         const int cur = W.id[i];
-        FPK_TV(c, cur)[0] = T_DEAD;
-        FPK_TN(c, cur)[0] = firstnew;
+        TVp(cur)[0] = T_DEAD;
+        TNp(cur)[0] = firstnew;
         pushst[base + i] = cur;
     }
     if (lane == 0) {
@@ -388,8 +428,8 @@ __device__ __noinline__ int w2_commit_insertion(DelaunayCtx &c, WarpCav &W, int 
         const int *e = c.Pi + 3 * (size_t)p;
         int ix = (int)((double)e[0] * c.hinv), iy = (int)((double)e[1] * c.hinv), iz = (int)((double)e[2] * c.hinv);
         ix = ix < 0 ? 0 : (ix >= g ? g - 1 : ix); iy = iy < 0 ? 0 : (iy >= g ? g - 1 : iy); iz = iz < 0 ? 0 : (iz >= g ? g - 1 : iz);
-        c.hint[(ix * g + iy) * g + iz] = firstnew;
-        c.cnt[C_RECENT] = firstnew;
+        hint[(ix * g + iy) * g + iz] = firstnew;
+        S.cnt[C_RECENT] = firstnew;
     }
     return firstnew;
 }

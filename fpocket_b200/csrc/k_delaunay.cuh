@@ -140,16 +140,6 @@ __device__ void block_bbox(const double *P, int n, double *s_box, double (*s_bmi
     __syncthreads();
 }
 
-// Shared-memory state of one block's triangulation (static part; the WarpCav records and the sites are dynamic)
-enum { FPK_MAXWARPS = 8 };
-struct BlockDel {
-    DelaunayCtx C;
-    int cnt[C_COUNT];
-    int tinfo[4 * FPK_MAXWARPS], cursor[2 * FPK_MAXWARPS];
-    int first4[4];
-    int bigw;
-};
-
 // the serial path for one over-sized cavity (warp w alone, the rest of the block waits): global lists, delaunay.cuh
 __device__ __forceinline__ void w_big_insert(DelaunayCtx &c, int w)
 {
@@ -176,9 +166,11 @@ __device__ __forceinline__ void w_big_insert(DelaunayCtx &c, int w)
 // Delaunay triangulation of the n lattice points in X.P by the whole block (blockDim.x / 32 <= FPK_MAXWARPS warps).
 // S = static shared state, Wall = one WarpCav per warp (shared), Pi_sm / pi_cap = shared buffer for the sites.
 // Returns 0 or a DERR_* code (uniform over the block). On return the mesh is in X.tet, S.cnt[C_NTET] slots.
-__device__ int block_delaunay(BlockDel &S, WarpCav *Wall, int *Pi_sm, int pi_cap, const DelScratch &X, int n, const double *s_box)
+__device__ int block_delaunay(int pi_cap, const DelScratch &X, int n, const double *s_box)
 {
+    BlockDel &S = blk();
     DelaunayCtx &C = S.C;
+    int *Pi_sm = sm_sites();
     const int tid = threadIdx.x, nt = blockDim.x;
     const double bmn[3] = {s_box[0], s_box[1], s_box[2]};
     const double ext = fmax(1.0, fmax(s_box[3] - s_box[0], fmax(s_box[4] - s_box[1], s_box[5] - s_box[2])));
@@ -222,7 +214,7 @@ __device__ int block_delaunay(BlockDel &S, WarpCav *Wall, int *Pi_sm, int pi_cap
     }
     __syncthreads();
     // rounds of concurrent insertions: one pending point per warp, four block barriers per sub-round
-    WarpCav &W = Wall[wid];
+    const bool sm_pts = n <= pi_cap;
     int *ti = S.tinfo + 4 * wid;
     bool failed = S.cnt[C_STATUS] != 0;
     for (int r = 0; r < R && !failed; r++) {
@@ -235,16 +227,16 @@ __device__ int block_delaunay(BlockDel &S, WarpCav *Wall, int *Pi_sm, int pi_cap
             // ---- claim: walk + cavity flood on a read-only mesh ----------------------------------------------------------
             const int rank = work ? ti[0] : -1;
             int st = ST_IDLE, ncav = 0;
-            if (rank >= 0) st = w2_locate_and_claim(C, W, Pi, rank, ti[3], &ncav);
+            if (rank >= 0) st = sm_pts ? w2_locate_and_claim<true>(rank, ti[3], &ncav) : w2_locate_and_claim<false>(rank, ti[3], &ncav);
             __syncthreads();
             // ---- verify: a claimant wins iff nothing stronger touched its cavity or rim ---------------------------------
-            if (st == ST_CLAIMED) st = w2_verify_claims(C, W, rank, ncav) ? ST_WIN : ST_LOST;
+            if (st == ST_CLAIMED) st = w2_verify_claims(rank, ncav) ? ST_WIN : ST_LOST;
             __syncthreads();
             // ---- release the claims; winners rewrite the mesh concurrently --------------------------------------------
             if (rank >= 0) {
-                if (st == ST_WIN || st == ST_LOST || st == ST_BIG) w2_reset_claims(C, W, ncav);
+                if (st == ST_WIN || st == ST_LOST || st == ST_BIG) w2_reset_claims(ncav);
                 int newtet = -1;
-                if (st == ST_WIN) newtet = w2_commit_insertion(C, W, rank, ncav, S.cnt[C_SUBROUND] & 1);
+                if (st == ST_WIN) newtet = w2_commit_insertion(rank, ncav, S.cnt[C_SUBROUND] & 1);
                 __syncwarp();
                 if (lane == 0) {
                     ti[1] = st; ti[2] = ncav;
@@ -271,13 +263,10 @@ __device__ int block_delaunay(BlockDel &S, WarpCav *Wall, int *Pi_sm, int pi_cap
 #endif
 __global__ void __launch_bounds__(256, FPK_K1_MINBLOCKS) k_delaunay_filter(BatchDev B, const DelScratch *scratch, int pi_cap)
 {
-    __shared__ BlockDel BD;
     __shared__ int s_k, s_red[40];
     __shared__ double s_box[6];
     __shared__ double s_bmin[8][3], s_bmax[8][3];
-    extern __shared__ __align__(16) unsigned char fpk_dsm[];
-    WarpCav *Wall = reinterpret_cast<WarpCav *>(fpk_dsm);
-    int *Pi_sm = reinterpret_cast<int *>(fpk_dsm + (blockDim.x >> 5) * sizeof(WarpCav));
+    BlockDel &BD = blk();
     DelaunayCtx &C = BD.C;
     const int tid = threadIdx.x, nt = blockDim.x;
     const DelScratch &X = scratch[blockIdx.x];
@@ -305,7 +294,7 @@ __global__ void __launch_bounds__(256, FPK_K1_MINBLOCKS) k_delaunay_filter(Batch
         __syncthreads();
         block_bbox(X.P, n, s_box, s_bmin, s_bmax);
         // ---- 2.+3. insertion order, rounds of concurrent insertions --------------------------------------------------
-        const int err = block_delaunay(BD, Wall, Pi_sm, pi_cap, X, n, s_box);
+        const int err = block_delaunay(pi_cap, X, n, s_box);
         if (err) {
             if (tid == 0) {
                 counts[CNT_TETS] = 0; counts[CNT_SPHERES] = 0;

@@ -13,11 +13,8 @@ namespace fpk {
 enum { HULL_THREADS = 64 };
 __global__ void __launch_bounds__(HULL_THREADS, 8) k_hull_volume(BatchDev B, PocketDev Pk, const DelScratch *scratch, int *work_counter, int pi_cap)
 {
-    __shared__ BlockDel BD;
     __shared__ int s_item;
-    extern __shared__ __align__(16) unsigned char fpk_dsm[];
-    WarpCav *Wall = reinterpret_cast<WarpCav *>(fpk_dsm);
-    int *Pi_sm = reinterpret_cast<int *>(fpk_dsm + (HULL_THREADS / 32) * sizeof(WarpCav));
+    BlockDel &BD = blk();
     DelaunayCtx &C = BD.C;
     __shared__ double s_box[6];
     __shared__ double s_bmin[HULL_THREADS / 32][3], s_bmax[HULL_THREADS / 32][3];
@@ -48,7 +45,7 @@ __global__ void __launch_bounds__(HULL_THREADS, 8) k_hull_volume(BatchDev B, Poc
         }
         __syncthreads();
         block_bbox(X.P, n, s_box, s_bmin, s_bmax);
-        const int err = block_delaunay(BD, Wall, Pi_sm, pi_cap, X, n, s_box);
+        const int err = block_delaunay(pi_cap, X, n, s_box);
         if (err) { if (tid == 0) Pk.desc[item].convex_hull_volume = -1.0f; continue; }      // voronoi.c:1276-1279
         i128 sum = 0;
         const int ntet = C.cnt[C_NTET];
