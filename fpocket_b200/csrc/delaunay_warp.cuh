@@ -13,7 +13,7 @@
 
 namespace fpk {
 
-enum { WCAV = 64, WHASH = 256 };
+enum { WCAV = 64, WHASH = 256, WALK_CAP = 20 };
 #define FPK_HEMPTY 0xffffffffffffffffull
 
 struct WarpCav {                        // one per warp, shared memory
@@ -35,6 +35,7 @@ struct BlockDel {
     int tinfo[4 * FPK_MAXWARPS], cursor[2 * FPK_MAXWARPS];
     int first4[4];
     int bigw;
+    int resume[FPK_MAXWARPS];      // tet at which the warp's capped walk stopped (-1: none)
 };
 #define FPK_BD_BYTES ((sizeof(BlockDel) + 15) & ~(size_t)15)
 __device__ __forceinline__ unsigned char *dsm_base() { extern __shared__ __align__(16) unsigned char fpk_dsm[]; return fpk_dsm; }
@@ -196,29 +197,34 @@ template <bool SM> __device__ __noinline__ int w2_locate_and_claim(int rank, int
     const int prio = prio_of(rank);
     const P3 pp = ldp(Pi, p);
     *ncav_out = 0;
-    int t = own_hint;
+    const int *pe = Pi + 3 * (size_t)p;
+    const int pe0 = pe[0], pe1 = pe[1], pe2 = pe[2];
+    // start of the walk: where an earlier attempt on this point stopped, else the warp's last new tet (the previous point of its
+    // Morton-ordered chunk), else the hint grid's tet for the point's cell, else the most recent tet of the block
+    int t = S.resume[threadIdx.x >> 5];
+    if (t < 0) t = own_hint;
     if (t < 0) {
         const int g = c.hg;
-        const int *e = Pi + 3 * (size_t)p;
-        int ix = (int)((double)e[0] * c.hinv), iy = (int)((double)e[1] * c.hinv), iz = (int)((double)e[2] * c.hinv);
+        int ix = (int)((double)pe0 * c.hinv), iy = (int)((double)pe1 * c.hinv), iz = (int)((double)pe2 * c.hinv);
         ix = ix < 0 ? 0 : (ix >= g ? g - 1 : ix); iy = iy < 0 ? 0 : (iy >= g ? g - 1 : iy); iz = iz < 0 ? 0 : (iz >= g ? g - 1 : iz);
         t = hint[(ix * g + iy) * g + iz];
     }
     if (t < 0) t = S.cnt[C_RECENT];
-    int hops = 0;
-    for (int hop = 0; hop < 64 && TVp(t)[0] == T_DEAD; hop++) { t = TNp(t)[0]; hops++; }
-    if (hops && lane == 0) atomicAdd(&S.cnt[C_NHOP], hops);
-    if (TVp(t)[0] == T_DEAD) {
-        t = S.cnt[C_RECENT];
-        for (int hop = 0; hop < 64 && TVp(t)[0] == T_DEAD; hop++) t = TNp(t)[0];
-        if (TVp(t)[0] == T_DEAD) return ST_ERR;
-    }
     int4 v, nb;
-    const int maxsteps = S.cnt[C_NTET] + 64;
+    int dead = 0;
     for (int steps = 0;; steps++) {         // visibility walk: the four face tests of a step run on four lanes
-        if (steps > maxsteps) return ST_ERR;
         v = *reinterpret_cast<const int4 *>(TVp(t));
         nb = *reinterpret_cast<const int4 *>(TNp(t));
+        if (v.x == T_DEAD) {                // a dead tet forwards to a tet of the star that replaced it
+            dead++;
+            if (dead > 200) return ST_ERR;
+            t = dead == 64 ? S.cnt[C_RECENT] : nb.x;
+            continue;
+        }
+        if (steps - dead >= WALK_CAP) {     // bound the claim phase: go on from here in the next sub-round
+            if (lane == 0) { S.resume[threadIdx.x >> 5] = t; atomicAdd(&S.cnt[C_NWALK], steps - dead); atomicAdd(&S.cnt[C_NHOP], dead); }
+            return ST_LOST;
+        }
         const int k = inf_slot4(v);
         if (k >= 0) {
             if (in_conflict_v(tet, Pi, v, nb, p, pp)) break;
@@ -228,15 +234,22 @@ template <bool SM> __device__ __noinline__ int w2_locate_and_claim(int rank, int
         int o = 1;
         bool dup = false;
         if (lane < 4) {
-            const int *q = Pi + 3 * (size_t)comp4(v, lane), *e = Pi + 3 * (size_t)p;
-            dup = q[0] == e[0] && q[1] == e[1] && q[2] == e[2];
-            o = orient_sub_v(Pi, v, lane, p, pp);
+            // orient(v with slot q := p) = -+ orient(v[q+1], v[q+2], v[q+3], p): the cyclic shift is an even permutation for odd q
+            const int iq = comp4(v, lane), i1 = comp4(v, (lane + 1) & 3), i2 = comp4(v, (lane + 2) & 3), i3 = comp4(v, (lane + 3) & 3);
+            const int *q = Pi + 3 * (size_t)iq;
+            dup = q[0] == pe0 && q[1] == pe1 && q[2] == pe2;
+            o = orient3d_v(Pi, i1, i2, i3, p, ldp(Pi, i1), ldp(Pi, i2), ldp(Pi, i3), pp);
+            if (!(lane & 1)) o = -o;
         }
         const unsigned dupm = __ballot_sync(FPK_FULL, dup) & 0xfu, neg = __ballot_sync(FPK_FULL, o < 0) & 0xfu;
-        if (dupm) { *ncav_out = comp4(v, __ffs(dupm) - 1); return ST_DUP; }      // coincident site: reports the vertex it duplicates
-        if (!neg) { if (lane == 0) { atomicAdd(&S.cnt[C_NWALK], steps + 1); atomicAdd(&S.cnt[C_NATTEMPT], 1); } break; }
+        if (dupm) { if (lane == 0) S.resume[threadIdx.x >> 5] = -1; *ncav_out = comp4(v, __ffs(dupm) - 1); return ST_DUP; }      // coincident site: reports the vertex it duplicates
+        if (!neg) {
+            if (lane == 0) { atomicAdd(&S.cnt[C_NWALK], steps - dead + 1); atomicAdd(&S.cnt[C_NATTEMPT], 1); atomicAdd(&S.cnt[C_NHOP], dead); }
+            break;
+        }
         t = comp4(nb, __ffs(neg) - 1);
     }
+    if (lane == 0) S.resume[threadIdx.x >> 5] = t;      // a lost attempt starts again here; cleared when the point is done
     int st = ST_CLAIMED;
     if (lane == 0) {
         if (__ldcg(RIMp(t)) < prio) st = ST_LOST;

@@ -159,6 +159,7 @@ __device__ __forceinline__ void w_big_insert(DelaunayCtx &c, int w)
         else if (st != ST_DUP) c.cnt[C_STATUS] = DERR_CAPACITY;
         c.cnt[C_NBIG]++;
         ti[0] = -1;
+        blk().resume[w] = -1;
     }
     __syncwarp();
 }
@@ -196,7 +197,7 @@ __device__ int block_delaunay(int pi_cap, const DelScratch &X, int n, const doub
     for (int i = tid; i < hgc * hgc * hgc; i += nt) X.hint[i] = -1;
     for (int i = tid; i < n; i += nt) X.rep[i] = i;
     const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-    if (lane == 0) { S.tinfo[4 * wid] = -1; S.tinfo[4 * wid + 3] = -1; }
+    if (lane == 0) { S.tinfo[4 * wid] = -1; S.tinfo[4 * wid + 3] = -1; S.resume[wid] = -1; }
     __syncthreads();
     if (tid == 0) {
         for (int r = R - 1; r >= 0; r--) if (X.rstart[r] > X.rstart[r + 1]) X.rstart[r] = X.rstart[r + 1];
@@ -240,6 +241,7 @@ __device__ int block_delaunay(int pi_cap, const DelScratch &X, int n, const doub
                 __syncwarp();
                 if (lane == 0) {
                     ti[1] = st; ti[2] = ncav;
+                    if (st != ST_LOST && st != ST_BIG) S.resume[wid] = -1;
                     after_attempt(C, wid, newtet);
                     if (st == ST_BIG) atomicMin(&S.bigw, wid);
                 }
