@@ -35,10 +35,15 @@ def _gen_one(k):
     return synth.generate(SEED0 + k, n, 0.065)
 
 
-def make_batch(nstruct, workers, first=0):
+def size_of(k):
+    """heavy-atom count of workload structure k (what _gen_one draws first)"""
+    return int(np.random.default_rng(SEED0 + k).integers(2000, 5001))
+
+
+def make_batch(nstruct, workers, first=0, ids=None):
     import synth
     synth.lib()                                   # compile once before forking
-    ids = list(range(first, first + nstruct))
+    ids = list(range(first, first + nstruct)) if ids is None else [int(i) for i in ids]
     if workers > 1 and nstruct >= 64:
         import multiprocessing as mp
         with mp.get_context("fork").Pool(workers) as pool:
@@ -200,7 +205,15 @@ def main():
     api.init(local)
 
     t0 = time.time()
-    raw = make_batch(args.structures, workers)
+    if world > 1:       # weak scaling: the global workload is world x structures; ranks take balanced shares without communication
+        from fpocket_b200 import sharding
+        sizes = [size_of(k) for k in range(args.structures * world)]
+        mine = sharding.shard_structures(sizes, rank, world)[: args.structures]
+        if len(mine) < args.structures:
+            mine = list(mine) + [int(mine[-1])] * (args.structures - len(mine))
+        raw = make_batch(args.structures, workers, ids=mine)
+    else:
+        raw = make_batch(args.structures, workers)
     structs = [synth.to_structure(s) for s in raw]
     t_gen = time.time() - t0
     p = api.default_params()

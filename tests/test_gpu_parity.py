@@ -116,6 +116,70 @@ def test_scratch_reuse_across_batches_of_different_shape():
             assert_same_result(r, want[i], "reuse %d" % i)
 
 
+def _synth(seed, n):
+    import synth
+    return synth.to_structure(synth.generate(seed, n, 0.065))
+
+
+def test_synthetic_structures_equal_oracle():
+    """BASELINE configs[1] sizes (2k-5k heavy atoms, the bench generator): the whole result, bit for bit, against the oracle."""
+    api = _api()
+    sts = [_synth(20269100 + i, n) for i, n in enumerate((2000, 3517, 5000, 4242))]
+    p = api.default_params()
+    p.want_tets = 1
+    got = api.detect_batch(sts, p)
+    for st, r in zip(sts, got):
+        o = O.search_pocket(st, p, tets=None, rng_mode=O.RNG_PHILOX)
+        assert r["status"] == 0 and r["n_pockets"] >= 5
+        _, ki, _ = O.sites(st)
+        rc, tets, _ = O.delaunay(ki)
+        assert rc == 0 and np.array_equal(r["tets"], tets)
+        assert_same_result(r, o, "synthetic")
+
+
+def test_empty_sphere_property_at_bench_size():
+    """Size-independent property of the whole K1 stage on a bench-like batch: every kept alpha sphere touches its four contact atoms
+    (f32 distances agree within 1e-3, voronoi.c:1042) and holds no heavy atom (the Delaunay property), its radius is inside the window,
+    and clustering is the connected-component partition of the <= 2.4 A graph (pocket sets closed under the cut)."""
+    api = _api()
+    sts = [_synth(20269200 + i, 2000 + 97 * i) for i in range(24)]
+    p = api.default_params()
+    got = api.detect_batch(sts, p)
+    rng = np.random.default_rng(1)
+    for st, r in zip(sts, got):
+        assert r["status"] == 0
+        ns = r["n_spheres"]
+        assert 0.4 * st.natoms < ns < 0.75 * st.natoms          # SURVEY 8d sanity gate of the generator
+        xyz = np.stack([st.x, st.y, st.z], -1).astype(np.float64)
+        pick = rng.choice(ns, size=min(300, ns), replace=False)
+        c, rad = r["sph_xyzr"][pick, :3].astype(np.float64), r["sph_xyzr"][pick, 3].astype(np.float64)
+        d = np.linalg.norm(xyz[None] - c[:, None], axis=2)
+        dn = np.take_along_axis(d, r["sph_neigh"][pick].astype(np.int64), 1)
+        assert np.all(np.abs(dn - rad[:, None]) < 1.5e-3)
+        assert np.all(d.min(1) > rad - 1.5e-3)
+        assert np.all((rad >= 3.4 - 1e-3) & (rad <= 6.2 + 1e-3))
+        # single-linkage cut: no two spheres of different clusters within the cut
+        cx = r["sph_xyzr"][:, :3].astype(np.float64)
+        sub = rng.choice(ns, size=min(400, ns), replace=False)
+        dd = np.linalg.norm(cx[sub][:, None] - cx[None], axis=2)
+        close = dd <= float(np.float32(2.4)) - 1e-6
+        same = r["sph_cluster"][sub][:, None] == r["sph_cluster"][None]
+        assert not np.any(close & ~same)
+
+
+def test_large_structure_sites_in_global_memory():
+    """20k heavy atoms do not fit the shared-memory site buffer: K1 takes the global-memory instantiation of the same code."""
+    api = _api()
+    st = _synth(20269300, 20000)
+    p = api.default_params()
+    p.want_tets = 1
+    r = api.detect(st, p)
+    assert r["status"] == 0
+    _, ki, _ = O.sites(st)
+    rc, tets, _ = O.delaunay(ki)
+    assert rc == 0 and np.array_equal(r["tets"], tets)
+
+
 def test_edge_cases():
     from fpocket_b200 import capi
     api = _api()
