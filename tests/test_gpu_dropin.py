@@ -1,0 +1,93 @@
+"""GPU: the reference's OWN fpocket program with one translation unit swapped - src/fpocket.c (search_pocket) replaced by
+fpocket_b200/shim/search_pocket_cuda.c - built by fpocket_b200/shim/Makefile into build/fpocket_cuda (CLI, PDB reader and
+writers are the reference's objects, unchanged). Checks
+  * it runs and writes the reference's file set;
+  * what it prints in <name>_info.txt IS the C-ABI result for the same structure (the shim maps every field correctly);
+  * against the unmodified reference binary on the same file: same pockets up to the spheres the reference loses in its
+    unflushed qhull tail (DESIGN.md par. 3) - pocket count within 2, and every top reference pocket has a CUDA twin sharing
+    most of its atoms."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+ROOT = O.ROOT
+EXE = os.path.join(ROOT, "build", "fpocket_cuda")
+REF = os.path.join(ROOT, "oracle", "_ref", "fpocket")
+SEED = 424242
+
+
+def _info(path):
+    pockets, cur = [], None
+    for line in open(path):
+        m = re.match(r"Pocket (\d+) :", line)
+        if m:
+            cur = {}
+            pockets.append(cur)
+        elif ":" in line and cur is not None:
+            k, v = line.rsplit(":", 1)
+            cur[k.strip()] = float(v)
+    return pockets
+
+
+def _atoms(dirpath, k):
+    ids = set()
+    for line in open(os.path.join(dirpath, "pockets", "pocket%d_atm.pdb" % k)):
+        if line.startswith("ATOM"):
+            ids.add(int(line[6:11]))
+    return ids
+
+
+@pytest.mark.parametrize("n", [2300, 4100])
+def test_reference_program_with_cuda_search_pocket(tmp_path, n):
+    if not os.path.exists(EXE):
+        pytest.skip("build/fpocket_cuda not built (needs the reference tree: make -C fpocket_b200/shim)")
+    import synth
+    from fpocket_b200 import api
+    s = synth.generate(20269400 + n, n, 0.065)
+    dg, dr = tmp_path / "gpu", tmp_path / "ref"
+    for d in (dg, dr):
+        d.mkdir()
+        synth.to_pdb(s, str(d / "x.pdb"))
+    env = dict(os.environ, FPOCKET_MC_SEED=str(SEED), TMPDIR=str(tmp_path))
+    subprocess.check_call([EXE, "-f", "x.pdb"], cwd=str(dg), env=env, stdout=subprocess.DEVNULL)
+    out = dg / "x_out"
+    assert (out / "x_info.txt").exists() and (out / "x_out.pdb").exists() and (out / "x_pockets.pqr").exists()
+    got = _info(str(out / "x_info.txt"))
+    # ---- the file is the C-ABI result ----------------------------------------------------------------------------------
+    st = synth.to_structure(s)
+    # fpmain.c:143-164 reads the file twice: pdb and pdb_w_lig are two objects with the same atoms here (asa.c:315 pointer test is always true)
+    st.wx, st.wy, st.wz, st.wradius, st.welectroneg = st.x, st.y, st.z, st.radius, st.electroneg
+    st.wflags = np.zeros(st.natoms, np.uint8)
+    st.natoms_w, st.same_pdb = st.natoms, 0
+    p = api.default_params()
+    p.mc_seed = SEED
+    r = api.detect(st, p)
+    assert r["status"] == 0 and len(got) == r["n_pockets"]
+    D = r["desc"]
+    fields = {"Score": "score", "Druggability Score": "drug_score", "Number of Alpha Spheres": "nb_asph", "Total SASA": "surf_vdw14",
+              "Polar SASA": "surf_pol_vdw14", "Apolar SASA": "surf_apol_vdw14", "Volume": "volume", "Mean local hydrophobic density": "mean_loc_hyd_dens",
+              "Mean alpha sphere radius": "mean_asph_ray", "Mean alp. sph. solvent access": "masph_sacc",
+              "Apolar alpha sphere proportion": "apolar_asphere_prop", "Hydrophobicity score": "hydrophobicity_score", "Volume score": "volume_score",
+              "Polarity score": "polarity_score", "Charge score": "charge_score", "Proportion of polar atoms": "prop_polar_atm",
+              "Alpha sphere density": "as_density", "Cent. of mass - Alpha Sphere max dist": "as_max_dst", "Flexibility": "flex"}
+    for k, c in enumerate(r["rank_to_cluster"]):
+        for label, name in fields.items():
+            assert abs(got[k][label] - float(D[name][c])) <= 5.1e-4 + 1e-6 * abs(float(D[name][c])), (k, label, got[k][label], D[name][c])
+        atoms = {int(st.atom_id[a]) for a in r["cl_atoms"][r["cl_atom_off"][c]:r["cl_atom_off"][c + 1]]}
+        assert _atoms(str(out), k + 1) == atoms
+    # ---- against the unmodified reference on the same file -------------------------------------------------------------------
+    if os.path.exists(REF):
+        subprocess.check_call([REF, "-f", "x.pdb"], cwd=str(dr), env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        ref = _info(str(dr / "x_out" / "x_info.txt"))
+        assert abs(len(ref) - len(got)) <= 2
+        ours = [_atoms(str(out), k + 1) for k in range(len(got))]
+        for k in range(min(5, len(ref))):
+            a = _atoms(str(dr / "x_out"), k + 1)
+            best = max(len(a & b) / float(len(a | b)) for b in ours)
+            assert best >= 0.8, (k, best)
