@@ -22,7 +22,8 @@ struct WarpCav {                        // one per warp, shared memory
     unsigned long long hkey[WHASH];     // edge hash: (lo+1) << 32 | (hi+1)
     int hval[WHASH];                    // 4 * new tet + slot of the face waiting for its twin
     int id[WCAV];
-    unsigned char rim[WCAV];            // bit q: face q of cavity tet i is on the rim (its neighbour stays)
+    unsigned char rf[4 * WCAV];         // per face 4 * i + q of cavity tet i: 1 = on the rim (its neighbour stays), 0 = interior
+    unsigned char fq[4 * WCAV];         // frontier queue of the flood: faces still to be tested
     unsigned short rl[2 * WCAV + 8];    // compact list of rim faces (4 * i + q), filled by pass A of the commit
 };
 
@@ -235,7 +236,9 @@ template <bool SM> __device__ __noinline__ int w2_locate_and_claim(int rank, int
         bool dup = false;
         if (lane < 4) {
             // orient(v with slot q := p) = -+ orient(v[q+1], v[q+2], v[q+3], p): the cyclic shift is an even permutation for odd q
-            const int iq = comp4(v, lane), i1 = comp4(v, (lane + 1) & 3), i2 = comp4(v, (lane + 2) & 3), i3 = comp4(v, (lane + 3) & 3);
+            int iq = v.x, i1 = v.y, i2 = v.z, i3 = v.w;                       // rotate left by `lane`
+            if (lane & 1) { const int t0 = iq; iq = i1; i1 = i2; i2 = i3; i3 = t0; }
+            if (lane & 2) { int t0 = iq; iq = i2; i2 = t0; t0 = i1; i1 = i3; i3 = t0; }
             const int *q = Pi + 3 * (size_t)iq;
             dup = q[0] == pe0 && q[1] == pe1 && q[2] == pe2;
             o = orient3d_v(Pi, i1, i2, i3, p, ldp(Pi, i1), ldp(Pi, i2), ldp(Pi, i3), pp);
@@ -259,18 +262,20 @@ template <bool SM> __device__ __noinline__ int w2_locate_and_claim(int rank, int
     st = __shfl_sync(FPK_FULL, st, 0);
     if (st == ST_LOST) return ST_LOST;
     __syncwarp();
-    int ncav = 1, nlev = 0;
-    for (int head = 0; head < ncav;) {      // breadth-first: 8 frontier tets x 4 faces per step
-        const int room = (WCAV - ncav) >> 2;                            // every claimed tet must fit in the list (the reset walks it)
+    int ncav = 1, nlev = 0, qhead = 0, qtail = 4;
+    if (lane < 4) W.fq[lane] = (unsigned char)lane;
+    __syncwarp();
+    while (qhead < qtail) {                 // breadth-first over FACES: up to 32 untested faces of the cavity per step, one per lane
+        const int room = WCAV - ncav;                                   // every claimed tet must fit in the list (the reset walks it)
         if (room < 1) { *ncav_out = ncav; return ST_BIG; }
-        const int f = head + (lane >> 2), q = lane & 3;
-        head = min(head + min(8, room), ncav);
-        const bool active = f < head;
+        const int nproc = min(min(32, room), qtail - qhead);
+        const bool active = lane < nproc;
         bool lost = false, add = false, isrim = false;
-        int x = -1;
+        int x = -1, e = 0;
         int4 xv, xn;
         if (active) {
-            x = reinterpret_cast<const int *>(&W.n[f])[q];
+            e = W.fq[qhead + lane];
+            x = reinterpret_cast<const int *>(W.n)[e];
             const int2 cl = ldcg2(OWNp(x));                       // one round trip: claim pair and the tet record together
             xv = *reinterpret_cast<const int4 *>(TVp(x));
             xn = *reinterpret_cast<const int4 *>(TNp(x));
@@ -288,13 +293,20 @@ template <bool SM> __device__ __noinline__ int w2_locate_and_claim(int rank, int
                 atomicMin(RIMp(x), prio);
                 isrim = true;
             }
+            W.rf[e] = isrim ? 1 : 0;
         }
-        const unsigned addm = __ballot_sync(FPK_FULL, add), lostm = __ballot_sync(FPK_FULL, lost), rimm = __ballot_sync(FPK_FULL, isrim);
+        qhead += nproc;
+        const unsigned addm = __ballot_sync(FPK_FULL, add), lostm = __ballot_sync(FPK_FULL, lost);
         if (add) {
-            const int pos = ncav + __popc(addm & ((1u << lane) - 1u));
+            const int rk = __popc(addm & ((1u << lane) - 1u)), pos = ncav + rk;
             W.id[pos] = x; W.v[pos] = xv; W.n[pos] = xn;
+            const int cur = W.id[e >> 2];                               // the face of x back to its parent is interior; the other three join the queue
+            const int r = xn.x == cur ? 0 : (xn.y == cur ? 1 : (xn.z == cur ? 2 : 3));
+            W.rf[4 * pos + r] = 0;
+            unsigned char *qq = W.fq + qtail + 3 * rk;
+            qq[0] = (unsigned char)(4 * pos + ((r + 1) & 3)); qq[1] = (unsigned char)(4 * pos + ((r + 2) & 3)); qq[2] = (unsigned char)(4 * pos + ((r + 3) & 3));
         }
-        if (active && q == 0) W.rim[f] = (unsigned char)((rimm >> lane) & 0xfu);
+        qtail += 3 * __popc(addm);
         ncav += __popc(addm);
         nlev++;
         __syncwarp();
@@ -356,7 +368,7 @@ __device__ __noinline__ int w2_commit_insertion(int rank, int ncav, int popstack
     // ---- pass A: one new tet per rim face (slots allocated warp-wide), outside adjacency both ways ----------------------------------
     for (int base = 0; base < 4 * ncav; base += 32) {
         const int e = base + lane, f = e >> 2, q = e & 3;
-        const bool isrim = e < 4 * ncav && ((W.rim[f] >> q) & 1);
+        const bool isrim = e < 4 * ncav && W.rf[e];
         const unsigned m = __ballot_sync(FPK_FULL, isrim);
         if (!m) continue;
         const int cnt = __popc(m), my = __popc(m & ((1u << lane) - 1u));
