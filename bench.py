@@ -149,7 +149,8 @@ def main():
     ap.add_argument("--structures", type=int, default=10000, help="structures per GPU (BASELINE configs[1]: 10,000)")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--ref-sample", type=int, default=0)
-    ap.add_argument("--md-frames", type=int, default=0, help="also measure mdpocket frames/s on a synthetic trajectory of this many frames per GPU")
+    ap.add_argument("--md-frames", type=int, default=2048, help="also measure mdpocket frames/s on a synthetic trajectory of this many frames per GPU (0: skip)")
+    ap.add_argument("--large", type=int, default=0, help="also time ONE synthetic complex of this many heavy atoms (BASELINE configs[3]: 150000) on rank 0")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -201,6 +202,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (the version banner goes to stdout)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     api.init(local)
 
@@ -347,6 +350,17 @@ def main():
         out["mdpocket"] = {"metric": "frames/sec", "value": F * world / float(mm[0]), "frames_per_gpu": F, "atoms": int(s5.n),
                            "grid": [int(v) for v in dims], "includes": "H2D of every frame, detection, grid scatter, NCCL all-reduce of both grids"}
         md.close()
+
+    # ---- optional: one large complex (configs[3]); a single Delaunay does not shard: one block of one GPU ------------------------------
+    if args.large > 0 and rank == 0:
+        big = synth.to_structure(synth.generate(20260401, args.large, 0.065))
+        bb = api.Batch([big], p)
+        bb.run()
+        bb.run()
+        out["large_complex"] = {"heavy_atoms": int(big.n_sites), "seconds": bb.kernel_ms(7) / 1e3, "tets": bb.counter(1), "spheres": bb.counter(2),
+                                "pockets": bb.counter(4), "tets_per_s": bb.counter(1) / max(1e-9, bb.kernel_ms(0) / 1e3),
+                                "stage_ms": {"k_delaunay_filter": bb.kernel_ms(0), "k_cluster": bb.kernel_ms(1), "k_hull_volume": bb.kernel_ms(3), "k_descriptors": bb.kernel_ms(4)}}
+        bb.close()
 
     # ---- CPU baseline: the unmodified reference on this box's cores, bounded sample ------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
