@@ -141,6 +141,40 @@ def reference_fpocket_rate(raw, nsample, cores, keep_dir=None):
     return nsample / dt, dt
 
 
+def reference_mdpocket_rate(base, frames, cores):
+    """Times the UNMODIFIED reference mdpocket (oracle/_ref/mdpocket --pdb_list) on `frames` ([F, n, 3]) of the workload: the program
+    is sequential over frames (one grid, mdpocket.c:235-271), so the frames are cut into `cores` chunks, one process per chunk
+    (the fair host-cores figure of SURVEY 8d). Returns (frames/s, seconds) or (None, reason)."""
+    import copy
+    import synth
+    exe = os.path.join(ROOT, "oracle", "_ref", "mdpocket")
+    if not os.path.exists(exe):
+        return None, "oracle/_ref/mdpocket missing"
+    tmp = tempfile.mkdtemp(prefix="fpkmd", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    F = len(frames)
+    per = max(1, (F + cores - 1) // cores)
+    lists = []
+    for c0 in range(0, F, per):
+        d = os.path.join(tmp, "c%03d" % (c0 // per))
+        os.makedirs(d)
+        names = []
+        for f in range(c0, min(F, c0 + per)):
+            s = copy.copy(base)
+            s.xyz = frames[f]
+            fn = os.path.join(d, "f%05d.pdb" % f)
+            synth.to_pdb(s, fn)
+            names.append(fn)
+        open(os.path.join(d, "list.txt"), "w").write("\n".join(names) + "\n")
+        lists.append(d)
+    t0 = time.time()
+    procs = [subprocess.Popen([exe, "--pdb_list", os.path.join(d, "list.txt")], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for d in lists]
+    for pr in procs:
+        pr.wait()
+    dt = time.time() - t0
+    subprocess.call(["rm", "-rf", tmp])
+    return F / dt, dt
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -359,6 +393,12 @@ def main():
         out["mdpocket"] = {"metric": "frames/sec", "value": F * world / float(mm[0]), "frames_per_gpu": F, "atoms": int(s5.n),
                            "grid": [int(v) for v in dims], "includes": "H2D of every frame, detection, grid scatter, NCCL all-reduce of both grids"}
         md.close()
+        if rank == 0 and world == 1 and not args.no_cpu:
+            nfr = 2 * ncores
+            r, dt = reference_mdpocket_rate(s5, xyz[:nfr], ncores)
+            out["mdpocket"]["cpu_baseline"] = {"value": r, "unit": "frames/s", "cores": ncores, "kind": "reference",
+                                               "sample": "first %d frames, oracle/_ref/mdpocket --pdb_list (the unmodified reference), %d processes of %d frames each, tmpfs; %s s"
+                                                         % (nfr, ncores, 2, ("%.1f" % dt) if r else dt)}
 
     # ---- optional: one large complex (configs[3]); a single Delaunay does not shard: one block of one GPU ------------------------------
     if args.large > 0 and rank == 0:
