@@ -257,3 +257,41 @@ def test_md_trajectory_of_distinct_frames_equals_oracle():
         freq += ff
     assert np.array_equal(gd, dens) and np.array_equal(gf, freq)
     assert gd.sum() > 0 and gf.sum() > 0
+
+
+def _points_structure(xyz):
+    """a bare point set as a structure (carbon atoms, one residue each): only the Delaunay stage is of interest"""
+    from fpocket_b200 import capi
+    n = len(xyz)
+    one = np.ones(n, np.float32)
+    return capi.Structure(xyz[:, 0], xyz[:, 1], xyz[:, 2], 1.7 * one, 2.5 * one, 20 * one, np.arange(1, n + 1), np.arange(1, n + 1),
+                          np.zeros(n, np.int8), np.zeros(n, np.uint8), (np.float32(20), np.float32(0), np.float32(20)), w=None, same_pdb=1)
+
+
+def test_delaunay_on_degenerate_and_random_point_sets():
+    """The shared-memory fast path has its own exact predicates and symbolic perturbation (delaunay_warp.cuh): cubic lattices (every
+    point cospherical / coplanar with many others), duplicated sites, thin slabs and random clouds of many sizes, all in ONE batch,
+    must give exactly the oracle's tetrahedra (same perturbation scheme, so the same triangulation of the degenerate sets)."""
+    api = _api()
+    rng = np.random.default_rng(11)
+    sets = []
+    g = np.stack(np.meshgrid(*[np.arange(6)] * 3, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    sets.append(g * 1.5)                                                  # 216-point cubic lattice
+    sets.append(np.concatenate([g * 2.0, g * 2.0 + 1.0]))                 # body-centred lattice, 432 points
+    slab = rng.random((500, 3)).astype(np.float32) * np.array([40, 40, 0.004], np.float32)
+    sets.append(np.round(slab, 3))                                        # thin slab on the 1e-3 grid: coplanar quadruples galore
+    dup = np.round(rng.random((300, 3)).astype(np.float32) * 25, 3)
+    dup[100] = dup[7]; dup[101] = dup[7]; dup[250] = dup[3]
+    sets.append(dup)                                                      # coincident sites
+    for n in (5, 9, 33, 120, 700, 1900, 3300, 5200):
+        sets.append(np.round(rng.random((n, 3)).astype(np.float32) * (n ** (1 / 3.0)) * 2.7, 3))
+    sts = [_points_structure(x) for x in sets]
+    p = api.default_params()
+    p.want_tets = 1
+    got = api.detect_batch(sts, p)
+    for st, r in zip(sts, got):
+        _, ki, _ = O.sites(st)
+        rc, tets, _ = O.delaunay(ki)
+        assert rc == 0
+        assert r["n_tets"] == len(tets), (st.natoms, r["status"], r["n_tets"], len(tets))
+        assert np.array_equal(r["tets"], tets), st.natoms
