@@ -34,13 +34,14 @@ class FpkParams(C.Structure):
         ("min_apol_neigh", C.c_int32), ("nb_mcv_iter", C.c_int32), ("min_pock_nb_asph", C.c_int32),
         ("do_asa_and_volume", C.c_int32), ("skip_clustering", C.c_int32), ("xpocket_active", C.c_int32),
         ("min_n_explicit_pocket_atoms", C.c_int32), ("want_tets", C.c_int32), ("mc_seed", C.c_uint64),
+        ("lig_interface_dist", C.c_float), ("lig_crit_dist", C.c_float),
     ]
 
 
 def default_params(**kw):
     """init_def_fparams (reference src/fparams.c:63-95, headers/fparams.h:33-63)."""
     p = FpkParams(np.float32(3.4), np.float32(6.2), np.float32(2.4), 0.0, np.float32(0.7),
-                  3, 300, 15, 1, 0, 0, 4, 0, 20260101)
+                  3, 300, 15, 1, 0, 0, 4, 0, 20260101, np.float32(4.0), np.float32(3.0))
     for k, v in kw.items():
         setattr(p, k, v)
     return p
@@ -56,6 +57,7 @@ class FpkStructure(C.Structure):
         ("wx", _fp), ("wy", _fp), ("wz", _fp), ("wradius", _fp), ("welectroneg", _fp), ("wflags", _bp),
         ("same_pdb", C.c_int32),
         ("n_xlig", C.c_int32), ("xlig", _fp),
+        ("n_lig", C.c_int32), ("lig_atoms", _ip), ("lig_mol", _ip), ("atom_name_key", _ip),
     ]
 
 
@@ -85,6 +87,8 @@ class FpkResult(C.Structure):
         ("sph_cluster", _ip), ("n_clusters", C.c_int32), ("cl_off", _ip), ("cl_sph", _ip), ("cl_atom_off", _ip),
         ("cl_atoms", _ip), ("desc", C.POINTER(FpkDesc)), ("n_pockets", C.c_int32), ("rank_to_cluster", _ip),
         ("atom_fx", _fp), ("_owner", C.c_void_p),
+        ("n_xspheres", C.c_int32), ("xspheres", _ip), ("n_iface", C.c_int32), ("iface_atoms", _ip),
+        ("pk_ovlp", _fp), ("pk_dst", _fp), ("pk_c4", _fp), ("pk_c5", _fp),
     ]
 
 
@@ -114,6 +118,11 @@ def result_to_dict(r, natoms):
     }
     na = int(d["cl_atom_off"][-1]) if nc else 0
     d["cl_atoms"] = _arr(r.cl_atoms, (na,), np.int32)
+    if r.xspheres or r.pk_dst:                       # dpocket ligand queries
+        d["xspheres"] = _arr(r.xspheres, (r.n_xspheres,), np.int32)
+        d["iface_atoms"] = _arr(r.iface_atoms, (r.n_iface,), np.int32)
+        for k in ("pk_ovlp", "pk_dst", "pk_c4", "pk_c5"):
+            d[k] = _arr(getattr(r, k), (npk,), np.float32)
     return d
 
 
@@ -139,6 +148,14 @@ class Structure:
         else:
             self.natoms_w = 0
         self.xlig = f32(xlig).reshape(-1, 3) if xlig is not None and len(xlig) else None
+        self.lig_atoms = self.lig_mol = self.atom_name_key = None
+
+    def set_ligand(self, lig_atoms, lig_mol=None, atom_name_key=None):
+        """dpocket: the known ligand as indices into the pdb_w_lig atoms (into the pdb atoms when there is no separate copy)."""
+        self.lig_atoms = np.ascontiguousarray(lig_atoms, dtype=np.int32)
+        self.lig_mol = np.ascontiguousarray(lig_mol if lig_mol is not None else np.zeros(len(self.lig_atoms)), dtype=np.int32)
+        self.atom_name_key = None if atom_name_key is None else np.ascontiguousarray(atom_name_key, dtype=np.int32)
+        return self
 
     @property
     def n_sites(self):
@@ -161,6 +178,11 @@ class Structure:
         if self.xlig is not None:
             s.n_xlig = len(self.xlig)
             s.xlig = p(self.xlig, _fp)
+        if getattr(self, "lig_atoms", None) is not None and len(self.lig_atoms):
+            s.n_lig = len(self.lig_atoms)
+            s.lig_atoms, s.lig_mol = p(self.lig_atoms, _ip), p(self.lig_mol, _ip)
+            if self.atom_name_key is not None:
+                s.atom_name_key = p(self.atom_name_key, _ip)
         return s
 
 

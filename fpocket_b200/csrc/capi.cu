@@ -53,6 +53,7 @@ extern "C" void fpk_default_params(fpk_params *p)
     p->refine_min_apolar_asphere_prop = (float)0.0; p->min_as_density = (float)0.7;
     p->min_apol_neigh = 3; p->nb_mcv_iter = 300; p->min_pock_nb_asph = 15;
     p->do_asa_and_volume = 1; p->min_n_explicit_pocket_atoms = 4; p->mc_seed = 20260101ull;
+    p->lig_interface_dist = (float)4.0; p->lig_crit_dist = (float)3.0;
 }
 
 // asa.c:438-454 get_points_on_sphere(100): computed with the host libm exactly as the reference does
@@ -209,7 +210,11 @@ struct fpk_batch {
     fpk_params prm;
     std::vector<StructDev> S;
     std::vector<int> natoms;
-    long long tot_atoms = 0, tot_w = 0, tot_sites = 0, tot_xlig = 0, tot_sphcap = 0, tot_tetcap = 0;
+    long long tot_atoms = 0, tot_w = 0, tot_sites = 0, tot_xlig = 0, tot_sphcap = 0, tot_tetcap = 0, tot_lig = 0;
+    bool has_names = false;
+    std::vector<int> lig_n;
+    LigDev Lg;                         // dpocket ligand queries (tot_lig > 0)
+    std::vector<int> h_nx, h_ni;
     int max_sites = 0, max_w = 0, max_sphcap = 0;
     int md_shared_props = 0;           // mdpocket: all frames share the property arrays
     // stage 1 device
@@ -250,9 +255,10 @@ static inline size_t sph_cap_for(const fpk_params &p, int nsites, double factor_
 static int batch_pack(fpk_batch *b, const fpk_structure *in, int n, const fpk_params *p, double cap_factor)
 {
     b->n = n; b->prm = *p;
-    b->S.resize(n); b->natoms.resize(n);
+    b->S.resize(n); b->natoms.resize(n); b->lig_n.assign(n, 0);
     b->max_sites = b->max_w = b->max_sphcap = 0; b->h2d = b->d2h = 0;
-    long long ao = 0, wo = 0, so = 0, xo = 0, sc = 0, tc = 0;
+    long long ao = 0, wo = 0, so = 0, xo = 0, sc = 0, tc = 0, lo = 0;
+    b->has_names = false;
     for (int k = 0; k < n; k++) {
         const fpk_structure &s = in[k];
         if (s.natoms < 0 || (s.natoms > 0 && (!s.x || !s.y || !s.z || !s.radius || !s.electroneg || !s.bfactor || !s.atom_id || !s.res_id || !s.aa_idx || !s.flags)))
@@ -261,6 +267,12 @@ static int batch_pack(fpk_batch *b, const fpk_structure *in, int n, const fpk_pa
             return fail(FPK_ERR_BAD_ARG, "structure %d: NULL pdb_w_lig array", k);
         if (s.natoms_w == 0 && !s.same_pdb)
             return fail(FPK_ERR_BAD_ARG, "structure %d: natoms_w == 0 requires same_pdb = 1", k);
+        if (s.n_lig < 0 || (s.n_lig > 0 && (!s.lig_atoms || !s.lig_mol))) return fail(FPK_ERR_BAD_ARG, "structure %d: NULL ligand array", k);
+        for (int i = 0; i < s.n_lig; i++)
+            if (s.lig_atoms[i] < 0 || s.lig_atoms[i] >= (s.natoms_w ? s.natoms_w : s.natoms)) return fail(FPK_ERR_BAD_ARG, "structure %d: ligand atom index out of range", k);
+        lo += s.n_lig;
+        b->lig_n[k] = s.n_lig;
+        if (s.n_lig > 0 && s.atom_name_key) b->has_names = true;
         StructDev &d = b->S[k];
         memset(&d, 0, sizeof d);
         int ns = 0;
@@ -289,7 +301,7 @@ static int batch_pack(fpk_batch *b, const fpk_structure *in, int n, const fpk_pa
         b->max_sphcap = std::max(b->max_sphcap, d.sph_cap);
         if (ao > 2000000000ll || sc + n > 2000000000ll || tc > 500000000ll) return fail(FPK_ERR_BAD_ARG, "batch too large for 32-bit offsets; split it");
     }
-    b->tot_atoms = ao; b->tot_w = wo; b->tot_sites = so; b->tot_xlig = xo; b->tot_sphcap = sc; b->tot_tetcap = tc;
+    b->tot_atoms = ao; b->tot_w = wo; b->tot_sites = so; b->tot_xlig = xo; b->tot_sphcap = sc; b->tot_tetcap = tc; b->tot_lig = lo;
     return FPK_OK;
 }
 
@@ -357,6 +369,8 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
         b->d_order = a.take<int>(n);
         b->dDel = a.take<DelScratch>(b->nDel);
         b->dClu = a.take<ClusterScratch>(b->nClu);
+        b->Lg.lig_off = a.take<int>(n + 1); b->Lg.lig_idx = a.take<int>(b->tot_lig + 1); b->Lg.lig_mol = a.take<int>(b->tot_lig + 1);
+        b->Lg.name_key = b->has_names ? a.take<int>(b->tot_atoms + 1) : nullptr;
         a.take<char>(0);
         b->in_bytes = a.used;                      // everything above is input: mirrored in pinned host memory, one copy
         B.s_xyzr = a.take<float4>(b->tot_sphcap); B.s_bary = a.take<float>(3 * b->tot_sphcap);
@@ -425,6 +439,20 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
             int so = 0;
             for (int i = 0; i < q.natoms; i++) if (!(q.flags[i] & FPK_ATOM_H)) s2[so++] = i;
             if (q.n_xlig) memcpy(hxl + 3 * (size_t)d.xlig_off, q.xlig, sizeof(float) * 3 * q.n_xlig);
+        }
+        {
+            int *hlo = (int *)mir(b->Lg.lig_off), *hli = (int *)mir(b->Lg.lig_idx), *hlm = (int *)mir(b->Lg.lig_mol);
+            int *hnk = b->has_names ? (int *)mir(b->Lg.name_key) : nullptr;
+            int lo = 0;
+            for (int k = 0; k < n; k++) {
+                hlo[k] = lo;
+                if (in[k].n_lig > 0) { memcpy(hli + lo, in[k].lig_atoms, 4 * (size_t)in[k].n_lig); memcpy(hlm + lo, in[k].lig_mol, 4 * (size_t)in[k].n_lig); lo += in[k].n_lig; }
+                if (hnk) {
+                    if (in[k].atom_name_key) memcpy(hnk + b->S[k].atom_off, in[k].atom_name_key, 4 * (size_t)in[k].natoms);
+                    else for (int i = 0; i < in[k].natoms; i++) hnk[b->S[k].atom_off + i] = -1 - i;      // no names: never equal
+                }
+            }
+            hlo[n] = lo;
         }
         CK(cudaMemcpyAsync(b->A1.base, H, b->in_bytes, cudaMemcpyHostToDevice, cudaStreamPerThread));
         b->h2d += (long long)b->in_bytes;
@@ -507,6 +535,11 @@ static int batch_run(fpk_batch *b)
         b->c_type = a.take<uint8_t>(NS + 1); b->c_cluster = a.take<int>(NS + 1); b->c_cl_sph = a.take<int>(NS + 1);
         b->c_cl_off = a.take<int>(NC + n + 1);
         b->dHull = a.take<DelScratch>(b->nHull); b->dDesc = a.take<DescScratch>(b->nDesc);
+        if (b->tot_lig > 0) {
+            b->Lg.xpos = a.take<int>(NS + n + 1); b->Lg.xlist = a.take<int>(NS + n + 1);
+            b->Lg.ipos = a.take<int>(b->tot_atoms + n + 1); b->Lg.ilist = a.take<int>(b->tot_atoms + n + 1);
+            b->Lg.nx = a.take<int>(n); b->Lg.ni = a.take<int>(n); b->Lg.crit = a.take<float>(4 * NC + 4);
+        }
         if (full) for (int i = 0; i < b->nHull; i++) del_scratch_layout(a, hHull[i], max_ns, 0, HULL_THREADS, false);
         for (int i = 0; i < b->nDesc; i++) hDesc[i].sa = a.take<int>(b->max_w + 1);
     });
@@ -533,6 +566,7 @@ static int batch_run(fpk_batch *b)
     } else {
         CK(cudaEventRecord(b->ev[4])); CK(cudaEventRecord(b->ev[5]));
     }
+    if (b->tot_lig > 0 && b->prm.skip_clustering == 0) { k_ligand<<<n, 256>>>(B, Pk, b->Lg); b->launches++; }
     k_compact<<<n, 128>>>(B, b->d_sbase, b->c_xyzr, b->c_bary, b->c_neigh, b->c_type, b->c_cluster, b->c_cl_sph, b->c_cl_off, b->d_clbase);
     b->launches++;
     CK(cudaEventRecord(b->ev[6]));
@@ -552,13 +586,15 @@ template <class T> static int d2h(fpk_batch *b, T *dst, const void *src, size_t 
     return FPK_OK;
 }
 
+static inline bool in_has_lig(const fpk_batch *b, int k) { return b->lig_n[k] > 0; }
+
 static int batch_fetch(fpk_batch *b, fpk_result *out)
 {
     const int n = b->n;
     HostResults *H = new HostResults();
     const size_t NS = (size_t)b->tot_spheres, NC = (size_t)b->tot_clusters, NA = (size_t)b->tot_atoms;
     const size_t need = 16 * NS + 12 * NS + 16 * NS + NS + 4 * NS + 4 * NS + 4 * (NC + n) + sizeof(fpk_desc) * NC + 16 * NS + 4 * (NS + n) + 16 * NA +
-                        4 * (NC + n) + 16 * NS + 256 * 16;
+                        4 * (NC + n) + 16 * NS + 256 * 24 + (b->tot_lig > 0 ? 4 * (NS + n + 1) + 4 * (NA + n + 1) + 32 * (NC + 1) : 0);
     H->blk = pin_get(need, &H->cap);
     if (!H->blk) { delete H; return fail(FPK_ERR_CUDA, "cudaHostAlloc(%zu bytes) for the results failed", need); }
     float *xyzr = H->take<float>(4 * NS), *bary = H->take<float>(3 * NS), *atom_fx = H->take<float>(4 * NA);
@@ -571,6 +607,15 @@ static int batch_fetch(fpk_batch *b, fpk_result *out)
         (rc = d2h(b, type, b->c_type, NS)) || (rc = d2h(b, cluster, b->c_cluster, NS)) || (rc = d2h(b, cl_sph, b->c_cl_sph, NS)) ||
         (rc = d2h(b, cl_off, b->c_cl_off, NC + n)) || (rc = d2h(b, desc, b->Pk.desc, NC)) || (rc = d2h(b, sparse, b->Pk.cl_atoms, 4 * NS)) ||
         (rc = d2h(b, rank, b->Pk.rank_to_cluster, NS + n)) || (rc = d2h(b, atom_fx, b->Pk.atom_fx, 4 * NA))) { delete H; return rc; }
+    const bool lig = b->tot_lig > 0 && b->prm.skip_clustering == 0;
+    int *xlist = nullptr, *ilist = nullptr;
+    float *crit = nullptr, *pk4 = nullptr;
+    if (lig) {
+        xlist = H->take<int>(NS + n + 1); ilist = H->take<int>(NA + n + 1); crit = H->take<float>(4 * NC + 4); pk4 = H->take<float>(4 * NC + 4);
+        b->h_nx.resize(n); b->h_ni.resize(n);
+        if ((rc = d2h(b, xlist, b->Lg.xlist, NS + n)) || (rc = d2h(b, ilist, b->Lg.ilist, NA + n)) || (rc = d2h(b, crit, b->Lg.crit, 4 * NC)) ||
+            (rc = d2h(b, b->h_nx.data(), b->Lg.nx, (size_t)n)) || (rc = d2h(b, b->h_ni.data(), b->Lg.ni, (size_t)n))) { delete H; return rc; }
+    }
     CK(cudaStreamSynchronize(cudaStreamPerThread));
     if (b->B.tets_out) {
         H->tets.resize(4 * (size_t)b->tot_tets + 4);
@@ -616,6 +661,14 @@ static int batch_fetch(fpk_batch *b, fpk_result *out)
             ao[q + 1] = ao[q] + na;
         }
         r.cl_atom_off = ao;
+        if (lig && in_has_lig(b, k)) {
+            r.n_xspheres = b->h_nx[k]; r.xspheres = xlist + s0 + k;
+            r.n_iface = b->h_ni[k]; r.iface_atoms = ilist + b->S[k].atom_off + k;
+            float *o = pk4 + 4 * (size_t)c0;
+            const int np = r.n_pockets;
+            r.pk_ovlp = o; r.pk_dst = o + np; r.pk_c4 = o + 2 * np; r.pk_c5 = o + 3 * np;
+            for (int q = 0; q < np; q++) for (int z = 0; z < 4; z++) o[z * np + q] = crit[4 * ((size_t)c0 + q) + z];
+        }
         r._owner = H;
         H->refs++;
     }
@@ -845,7 +898,7 @@ extern "C" fpk_md *fpk_md_begin(const fpk_structure *topo, const fpk_params *p, 
     m->topo.x = m->tx.data(); m->topo.y = m->ty.data(); m->topo.z = m->tz.data(); m->topo.radius = m->trad.data();
     m->topo.electroneg = m->ten.data(); m->topo.bfactor = m->tbf.data(); m->topo.atom_id = m->tid_.data();
     m->topo.res_id = m->tres.data(); m->topo.aa_idx = m->taa.data(); m->topo.flags = m->tfl.data();
-    m->topo.natoms_w = 0; m->topo.same_pdb = 1; m->topo.n_xlig = 0; m->topo.xlig = nullptr;     // mdpocket.c:844 search_pocket(pdb, params, pdb)
+    m->topo.natoms_w = 0; m->topo.same_pdb = 1; m->topo.n_xlig = 0; m->topo.xlig = nullptr; m->topo.n_lig = 0; m->topo.lig_atoms = nullptr; m->topo.lig_mol = nullptr; m->topo.atom_name_key = nullptr;     // mdpocket.c:844 search_pocket(pdb, params, pdb)
     m->prm = *p;
     m->prm.do_asa_and_volume = 0;          // mdpocket.c:89
     m->prm.want_tets = 0;

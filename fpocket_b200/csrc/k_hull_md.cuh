@@ -181,4 +181,139 @@ __global__ void k_md_geometry(BatchDev B, int k, float *out /* origin[3], dims[3
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// K6: dpocket's ligand queries. Replaces reference src/neighbor.c:192 get_mol_vert_neigh, :313 get_mol_ctd_atm_neigh (interface
+// search), :490 count_pocket_lig_vert_ovlp, :598 count_atm_prop_vert_neigh, src/atom.c:264 atm_corsp and the barycentre distance of
+// src/dpocket.c:253-261. The reference finds the pairs by sweeping an x-sorted merged array (sort.c:86 get_sorted_list); the RESULTS
+// are sets and counts of the strict "dist < d" relation (calc.c:51 dist in f32), which is what is computed here, one block per
+// structure: lanes over spheres x ligand atoms, lists in ascending index order.
+struct LigDev {
+    const int *lig_off;        // [nstruct + 1] offsets into lig_idx / lig_mol
+    const int *lig_idx;        // indices into the pdb_w_lig atom arrays (pdb arrays when there is no separate copy)
+    const int *lig_mol;
+    const int *name_key;       // [natoms_total] or nullptr
+    int *xpos;                 // [sbase[nstruct] + nstruct + 1] scratch -> explicit-pocket sphere list per structure at sbase[k] + k
+    int *ipos;                 // [natoms_total + nstruct + 1]   scratch -> interface atom list per structure at atom_off + k
+    int *xlist, *ilist;        // compact lists (same bases as xpos / ipos)
+    int *nx, *ni;              // [nstruct]
+    float *crit;               // [4 * total_clusters]: ovlp, dst, c4, c5 of the pocket ranked r of structure k at 4 * (clbase[k] + r)
+};
+enum { LIG_MAXMOL = 64 };
+
+__global__ void __launch_bounds__(256) k_ligand(BatchDev B, PocketDev Pk, LigDev G)
+{
+    __shared__ int s_sm[40], s_hit[8][LIG_MAXMOL], s_tot[8][LIG_MAXMOL];
+    const int k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nt >> 5;
+    const StructDev S = B.S[k];
+    const int *counts = B.counts + (size_t)k * CNT_STRIDE;
+    const int L0 = G.lig_off[k], nl = G.lig_off[k + 1] - L0;
+    if (tid == 0) { G.nx[k] = 0; G.ni[k] = 0; }
+    if (nl <= 0) return;
+    const int st = counts[CNT_STATUS];
+    if (st != FPK_OK && st != FPK_ERR_NO_POCKETS) return;
+    const int ns = counts[CNT_SPHERES], na = S.natoms;
+    const int W0 = S.natoms_w ? S.w_off : S.atom_off;
+    const float *wx = S.natoms_w ? B.wx : B.ax, *wy = S.natoms_w ? B.wy : B.ay, *wz = S.natoms_w ? B.wz : B.az;
+    const int *lig = G.lig_idx + L0, *mol = G.lig_mol + L0;
+    const float4 *sx = B.s_xyzr + S.sph_off;
+    const int4 *sn = B.s_neigh + S.sph_off;
+    int *xpos = G.xpos + Pk.sbase[k] + k, *ipos = G.ipos + S.atom_off + k;
+    int *xlist = G.xlist + Pk.sbase[k] + k, *ilist = G.ilist + S.atom_off + k;
+    const float dcrit = B.prm.lig_interface_dist, ccrit = B.prm.lig_crit_dist;
+    for (int i = tid; i <= na; i += nt) ipos[i] = 0;
+    __syncthreads();
+    // ---- explicit pocket spheres and interface atoms -------------------------------------------------------------------------
+    for (int s = tid; s <= ns; s += nt) {
+        int near = 0;
+        if (s < ns) {
+            const float4 v = sx[s];
+            const int4 q = sn[s];
+            for (int l = 0; l < nl; l++) {
+                const float lx = wx[W0 + lig[l]], ly = wy[W0 + lig[l]], lz = wz[W0 + lig[l]];
+                if (f_dist(v.x, v.y, v.z, lx, ly, lz) < dcrit) {
+                    near = 1;
+                    const int a[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int j = 0; j < 4; j++)         // neighbor.h:30 M_INTERFACE_SEARCH_DIST 8.0
+                        if ((double)f_dist(B.ax[S.atom_off + a[j]], B.ay[S.atom_off + a[j]], B.az[S.atom_off + a[j]], lx, ly, lz) < 8.0) ipos[a[j]] = 1;
+                }
+            }
+        }
+        xpos[s] = near;
+    }
+    __syncthreads();
+    const int nx = block_exclusive_scan(xpos, ns + 1, s_sm);
+    const int ni = block_exclusive_scan(ipos, na + 1, s_sm);
+    for (int s = tid; s < ns; s += nt) if (xpos[s + 1] != xpos[s]) xlist[xpos[s]] = s;
+    for (int a = tid; a < na; a += nt) if (ipos[a + 1] != ipos[a]) ilist[ipos[a]] = a;
+    if (tid == 0) { G.nx[k] = nx; G.ni[k] = ni; }
+    __syncthreads();
+    // ---- per surviving pocket: ovlp, dst, c4, c5 (one warp per pocket) ----------------------------------------------------------
+    const int npk = st == FPK_OK ? counts[CNT_POCKETS] : 0;
+    const int *cl_off = B.cl_off + S.sph_off + k, *cl_sph = B.cl_sph + S.sph_off;
+    const int *rank = Pk.rank_to_cluster + Pk.sbase[k] + k;
+    const fpk_desc *D = Pk.desc + Pk.clbase[k];
+    int nmol = 0;
+    for (int l = 0; l < nl; l++) nmol = max(nmol, mol[l] + 1);
+    nmol = min(nmol, LIG_MAXMOL);
+    for (int r = wid; r < npk; r += nwarp) {
+        const int c = rank[r], off = cl_off[c], n = cl_off[c + 1] - off;
+        const int *Lp = cl_sph + off;
+        // c5 (neighbor.c:490): share of the pocket's spheres within ccrit of some ligand atom
+        int c5n = 0;
+        for (int i = lane; i < n; i += 32) {
+            const float4 v = sx[Lp[i]];
+            bool hit = false;
+            for (int l = 0; l < nl && !hit; l++) hit = f_dist(v.x, v.y, v.z, wx[W0 + lig[l]], wy[W0 + lig[l]], wz[W0 + lig[l]]) < ccrit;
+            c5n += hit;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c5n += __shfl_xor_sync(0xffffffffu, c5n, d);
+        // c4 (neighbor.c:598): per ligand molecule, share of its atoms with a sphere of the pocket within ccrit; the best molecule counts
+        for (int m = lane; m < nmol; m += 32) { s_hit[wid][m] = 0; s_tot[wid][m] = 0; }
+        __syncwarp();
+        float dmin = 3e38f;
+        for (int l = lane; l < nl; l += 32) {
+            const float lx = wx[W0 + lig[l]], ly = wy[W0 + lig[l]], lz = wz[W0 + lig[l]];
+            bool hit = false;
+            for (int i = 0; i < n && !hit; i++) { const float4 v = sx[Lp[i]]; hit = f_dist(v.x, v.y, v.z, lx, ly, lz) < ccrit; }
+            const int m = min(mol[l], LIG_MAXMOL - 1);
+            atomicAdd(&s_tot[wid][m], 1);
+            if (hit) atomicAdd(&s_hit[wid][m], 1);
+            dmin = fminf(dmin, f_dist(lx, ly, lz, D[c].bary[0], D[c].bary[1], D[c].bary[2]));      // dpocket.c:253-261
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, d));
+        __syncwarp();
+        // ovlp (atom.c:264 atm_corsp): % of the interface atoms found among the pocket's atoms (same res_id and same id or name)
+        const int *uat = Pk.cl_atoms + 4 * (size_t)(Pk.sbase[k] + off);
+        const int U = D[c].n_atoms;
+        int found = 0;
+        for (int i = lane; i < ni; i += 32) {
+            const int a = S.prop_off + ilist[i];
+            bool f = false;
+            for (int j = 0; j < U && !f; j++) {
+                const int b = S.prop_off + uat[j];
+                f = B.ares[b] == B.ares[a] && (B.aid[b] == B.aid[a] || (G.name_key && G.name_key[b] == G.name_key[a]));
+            }
+            found += f;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) found += __shfl_xor_sync(0xffffffffu, found, d);
+        if (lane == 0) {
+            float c4 = 0.0f;
+            for (int m = 0; m < nmol; m++) {
+                const float t = (float)s_hit[wid][m] / (float)s_tot[wid][m];
+                if (t > c4) c4 = t;
+            }
+            float *o = G.crit + 4 * (size_t)(Pk.clbase[k] + r);
+            o[0] = (ni <= 0 || U <= 0) ? 0.0f : (float)((double)(((float)found) / ((float)ni)) * 100.0);
+            o[1] = dmin;
+            o[2] = c4;
+            o[3] = (float)c5n / (float)n;
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace fpk

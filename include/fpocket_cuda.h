@@ -60,6 +60,9 @@ typedef struct fpk_params {
     int32_t want_tets;                    /* also return the Delaunay tetrahedra (parity checks; costs a D2H copy)     */
     uint64_t mc_seed;                     /* Monte-Carlo volume: Philox key. The reference seeds libc rand() with
                                              time(NULL) (voronoi.c:87), so there is no reference stream to copy.       */
+    /* dpocket ligand queries (only read when a structure carries ligand atoms, fpk_structure.n_lig > 0) */
+    float lig_interface_dist;             /* dparams.h:42 M_VERT_LIG_NEIG_DIST 4.0: spheres within it of a ligand atom define the explicit pocket */
+    float lig_crit_dist;                  /* tpocket.h:32-33 M_CRIT4_D = M_CRIT5_D = 3.0                                                        */
 } fpk_params;
 
 /* flattened s_pdb pair (reference headers/rpdb.h:69-98, atom.h:29-77). Arrays are caller-owned, read-only. */
@@ -82,6 +85,15 @@ typedef struct fpk_structure {
 
     int32_t n_xlig;            /* pdb->n_xlig_atoms (explicit ligand, -r / -a), 0 if none */
     const float *xlig;         /* xyz triplets */
+
+    /* dpocket (reference src/dpocket.c:171-300): the known ligand, as indices into the pdb_w_lig atom arrays (pdb_cplx_l->latm_lig);
+     * n_lig = 0 for plain fpocket. lig_mol = 0,1,.. per ligand atom: consecutive runs of equal (chain, res_id), as
+     * count_atm_prop_vert_neigh groups them (neighbor.c:619-637). atom_name_key = the atom name of every pdb atom packed into an int
+     * (atm_corsp compares names, atom.c:281); NULL: atoms match by id only. */
+    int32_t n_lig;
+    const int32_t *lig_atoms;
+    const int32_t *lig_mol;
+    const int32_t *atom_name_key;
 } fpk_structure;
 
 /* numeric part of s_desc (reference headers/descriptors.h:34-88) + s_pocket scalars (pocket.h:37-52) */
@@ -130,6 +142,15 @@ typedef struct fpk_result {
     int32_t *rank_to_cluster;  /* [n_pockets] cluster index of the pocket ranked k+1 (psorting.c:64-165) */
     float *atom_fx;            /* [natoms*4] per-atom ASA side effects: abpa, a0, dA, abpa_sourrounding_prob (asa.c:337,392-396) */
     void *_owner;              /* library bookkeeping */
+    /* ---- dpocket ligand queries (neighbor.c), filled when the structure carried ligand atoms; sets in ascending index order ---- */
+    int32_t n_xspheres;        /* get_mol_vert_neigh (neighbor.c:192): spheres with dist(centre, some ligand atom) < lig_interface_dist */
+    int32_t *xspheres;         /* [n_xspheres] sphere indices: the explicit pocket of dpocket.c:341-349 */
+    int32_t n_iface;           /* get_mol_ctd_atm_neigh(.., M_INTERFACE_SEARCH) (neighbor.c:313): atoms contacted by such a sphere and */
+    int32_t *iface_atoms;      /* within 8.0 A (neighbor.h:30) of the ligand atom that reaches the sphere; indices into the pdb atoms   */
+    float *pk_ovlp;            /* [n_pockets] rank order: atm_corsp(interface, pocket atoms) in % (atom.c:264, dpocket.c:249)           */
+    float *pk_dst;             /* [n_pockets] min distance ligand atom - pocket barycentre (dpocket.c:253-261)                           */
+    float *pk_c4;              /* [n_pockets] count_atm_prop_vert_neigh(.., lig_crit_dist) (neighbor.c:598, dpocket.c:266)               */
+    float *pk_c5;              /* [n_pockets] count_pocket_lig_vert_ovlp(.., lig_crit_dist) (neighbor.c:490, dpocket.c:268)              */
 } fpk_result;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */

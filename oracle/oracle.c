@@ -563,6 +563,7 @@ void orc_result_free(fpk_result *r)
 {
     free(r->tets); free(r->sph_xyzr); free(r->sph_bary); free(r->sph_neigh); free(r->sph_type); free(r->sph_cluster);
     free(r->cl_off); free(r->cl_sph); free(r->cl_atom_off); free(r->cl_atoms); free(r->desc); free(r->rank_to_cluster); free(r->atom_fx);
+    free(r->xspheres); free(r->iface_atoms); free(r->pk_ovlp);
     memset(r, 0, sizeof *r);
 }
 
@@ -663,7 +664,84 @@ int orc_search_pocket(const fpk_structure *in, const fpk_params *p, const int *t
     for (int k = 0; k < nk; k++) out->desc[keep[k]].final_rank = k + 1;
     free(S);
     out->status = nk > 0 ? FPK_OK : FPK_ERR_NO_POCKETS;
+    if (in->n_lig > 0 && !p->skip_clustering) orc_ligand_queries(in, p, out);
     return out->status;
+}
+
+/* ---------------------------------------- dpocket ligand queries ---------------------------------------- */
+/* neighbor.c:192 get_mol_vert_neigh, :313 get_mol_ctd_atm_neigh(M_INTERFACE_SEARCH), :490 count_pocket_lig_vert_ovlp,
+ * :598 count_atm_prop_vert_neigh, atom.c:264 atm_corsp, dpocket.c:246-270. The reference finds the pairs by sweeping an x-sorted
+ * merged array outwards from every ligand atom until the x-gap exceeds the criterion; what it returns are the SETS / counts of the
+ * strict relation dist() < d, restated here directly (pinned against the reference's own functions by tests/golden, the _dpocket fixture). */
+void orc_ligand_queries(const fpk_structure *in, const fpk_params *p, fpk_result *out)
+{
+    const int nl = in->n_lig, ns = out->n_spheres, na = in->natoms, np = out->n_pockets;
+    const float *wx = in->natoms_w ? in->wx : in->x, *wy = in->natoms_w ? in->wy : in->y, *wz = in->natoms_w ? in->wz : in->z;
+    const float dcrit = p->lig_interface_dist, ccrit = p->lig_crit_dist;
+    unsigned char *xf = calloc((size_t)ns + 1, 1), *af = calloc((size_t)na + 1, 1);
+    for (int s = 0; s < ns; s++) {
+        const float *v = out->sph_xyzr + 4 * s;
+        for (int l = 0; l < nl; l++) {
+            int a = in->lig_atoms[l];
+            if (f_dist(v[0], v[1], v[2], wx[a], wy[a], wz[a]) < dcrit) {
+                xf[s] = 1;
+                for (int j = 0; j < 4; j++) {
+                    int c = out->sph_neigh[4 * s + j];
+                    if ((double)f_dist(in->x[c], in->y[c], in->z[c], wx[a], wy[a], wz[a]) < 8.0) af[c] = 1;     /* neighbor.h:30 */
+                }
+            }
+        }
+    }
+    out->xspheres = malloc(sizeof(int) * ((size_t)ns + 1));
+    out->iface_atoms = malloc(sizeof(int) * ((size_t)na + 1));
+    out->n_xspheres = out->n_iface = 0;
+    for (int s = 0; s < ns; s++) if (xf[s]) out->xspheres[out->n_xspheres++] = s;
+    for (int a = 0; a < na; a++) if (af[a]) out->iface_atoms[out->n_iface++] = a;
+    free(xf); free(af);
+    float *o = malloc(sizeof(float) * (4 * (size_t)np + 4));
+    out->pk_ovlp = o; out->pk_dst = o + np; out->pk_c4 = o + 2 * np; out->pk_c5 = o + 3 * np;
+    int nmol = 0;
+    for (int l = 0; l < nl; l++) if (in->lig_mol[l] + 1 > nmol) nmol = in->lig_mol[l] + 1;
+    int *hit = malloc(sizeof(int) * ((size_t)nmol + 1)), *tot = malloc(sizeof(int) * ((size_t)nmol + 1));
+    for (int r = 0; r < np; r++) {
+        const int c = out->rank_to_cluster[r], off = out->cl_off[c], n = out->cl_off[c + 1] - off;
+        const fpk_desc *d = out->desc + c;
+        int c5n = 0;
+        for (int i = 0; i < n; i++) {
+            const float *v = out->sph_xyzr + 4 * out->cl_sph[off + i];
+            for (int l = 0; l < nl; l++) {
+                int a = in->lig_atoms[l];
+                if (f_dist(v[0], v[1], v[2], wx[a], wy[a], wz[a]) < ccrit) { c5n++; break; }
+            }
+        }
+        for (int m = 0; m < nmol; m++) hit[m] = tot[m] = 0;
+        float dst = 0.0f;
+        for (int l = 0; l < nl; l++) {
+            int a = in->lig_atoms[l], m = in->lig_mol[l];
+            tot[m]++;
+            for (int i = 0; i < n; i++) {
+                const float *v = out->sph_xyzr + 4 * out->cl_sph[off + i];
+                if (f_dist(v[0], v[1], v[2], wx[a], wy[a], wz[a]) < ccrit) { hit[m]++; break; }
+            }
+            float t = f_dist(wx[a], wy[a], wz[a], d->bary[0], d->bary[1], d->bary[2]);
+            if (l == 0) dst = t;
+            else if (t < dst) dst = t;
+        }
+        float c4 = 0.0f;
+        for (int m = 0; m < nmol; m++) { float t = (float)hit[m] / (float)tot[m]; if (t > c4) c4 = t; }
+        const int *pa = out->cl_atoms + out->cl_atom_off[c], npa = out->cl_atom_off[c + 1] - out->cl_atom_off[c];
+        int found = 0;
+        for (int i = 0; i < out->n_iface; i++) {
+            int a = out->iface_atoms[i];
+            for (int j = 0; j < npa; j++) {
+                int b = pa[j];
+                if (in->res_id[b] == in->res_id[a] && (in->atom_id[b] == in->atom_id[a] || (in->atom_name_key && in->atom_name_key[b] == in->atom_name_key[a]))) { found++; break; }
+            }
+        }
+        out->pk_ovlp[r] = (out->n_iface <= 0 || npa <= 0) ? 0.0f : (float)((double)(((float)found) / ((float)out->n_iface)) * 100.0);
+        out->pk_dst[r] = dst; out->pk_c4[r] = c4; out->pk_c5[r] = (float)c5n / (float)n;
+    }
+    free(hit); free(tot);
 }
 
 /* ---------------------------------------- mdpocket grids ---------------------------------------- */

@@ -49,6 +49,8 @@ void orc_canonicalize_tets(int *tets, int ntets);
 int orc_search_pocket(const fpk_structure *in, const fpk_params *p, const int *tets, int ntets,
                       int rng_mode, fpk_result *out);
 void orc_result_free(fpk_result *r);
+/* dpocket ligand queries on a finished result (called by orc_search_pocket when in->n_lig > 0): fills xspheres, iface_atoms, pk_* */
+void orc_ligand_queries(const fpk_structure *in, const fpk_params *p, fpk_result *out);
 
 /* mdpocket grids (mdpbase.c). Spheres of surviving pockets in final pocket order. */
 void orc_md_grid_geometry(const fpk_result *r, float origin[3], int dims[3]);           /* init_md_grid :444-502 */

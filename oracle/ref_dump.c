@@ -17,7 +17,10 @@
  *   per-atom ASA side effects                                          (asa.c:337,392-396)
  *   optional: mdpocket grids for this single frame                     (mdpbase.c:108-262,444-502)
  *
- * Usage:  ref_dump <out.dump> [--md] [--seed S] <fpocket options, e.g. -f X.pdb -m 3.0>
+ *   optional: dpocket's ligand queries (--lig NAME: the structure is loaded as dpocket.c:186-203 does, and the
+ *             reference's own neighbor.c / atom.c functions are called on the final pockets)            (dpocket.c:228-290)
+ *
+ * Usage:  ref_dump <out.dump> [--md] [--seed S] [--lig NAME] <fpocket options, e.g. -f X.pdb -m 3.0>
  *   --md    mimic mdpocket's call (mdpocket.c:833-846): search_pocket(pdb,params,pdb),
  *           ASA/volume/hull off (mdpocket.c:89), then the three grids of frame 1.
  *
@@ -35,6 +38,9 @@
 #include "mdpbase.h"
 #include "mdparams.h"
 #include "read_mmcif.h"
+#include "neighbor.h"
+#include "dparams.h"
+#include "tpocket.h"
 
 extern int run_qvoronoi(FILE *fin, FILE *fout);
 
@@ -298,7 +304,9 @@ int main(int argc, char **argv)
     const char *outp = argv[1];
     int md = 0, md_score = 0, a = 2;
     long seed = -1;
+    char *ligname = NULL;
     for (;;) {
+        if (a + 1 < argc && !strcmp(argv[a], "--lig")) { ligname = argv[a + 1]; a += 2; continue; }
         if (a < argc && !strcmp(argv[a], "--md")) { md = 1; a++; }
         else if (a < argc && !strcmp(argv[a], "--score")) { md_score = 1; a++; }
         else if (a + 1 < argc && !strcmp(argv[a], "--seed")) { seed = atol(argv[a + 1]); a += 2; }
@@ -323,11 +331,12 @@ int main(int argc, char **argv)
         read_mmcif(pdb, NULL, M_DONT_KEEP_LIG, params->model_number, params);
         if (!md) read_mmcif(pdb_w_lig, NULL, M_KEEP_LIG, params->model_number, params);
     } else {
-        pdb = rpdb_open(pdbname, NULL, M_DONT_KEEP_LIG, params->model_number, params);
-        pdb_w_lig = md ? pdb : rpdb_open(pdbname, NULL, M_KEEP_LIG, params->model_number, params);
+        /* with --lig: dpocket.c:186-203 (pdb_cplx_nl / pdb_cplx_l) */
+        pdb = rpdb_open(pdbname, ligname, M_DONT_KEEP_LIG, ligname ? 0 : params->model_number, params);
+        pdb_w_lig = md ? pdb : rpdb_open(pdbname, ligname, M_KEEP_LIG, ligname ? 0 : params->model_number, params);
         if (!pdb) return 3;
-        rpdb_read(pdb, NULL, M_DONT_KEEP_LIG, params->model_number, params);
-        if (!md) rpdb_read(pdb_w_lig, NULL, M_KEEP_LIG, params->model_number, params);
+        rpdb_read(pdb, ligname, M_DONT_KEEP_LIG, ligname ? 0 : params->model_number, params);
+        if (!md) rpdb_read(pdb_w_lig, ligname, M_KEEP_LIG, ligname ? 0 : params->model_number, params);
     }
 
     OUT = fopen(outp, "wb");
@@ -411,6 +420,50 @@ int main(int argc, char **argv)
         rec1("grid.origin", 'f', 4, org);
         dump_grid("grid.dens", dens);
         dump_grid("grid.freq", freq);
+    }
+    if (ligname && pdb_w_lig->natm_lig > 0 && pockets->n_pockets > 0) {
+        /* dpocket.c:204-290 on the final pockets, with the reference's own functions */
+        s_atm **lig = pdb_w_lig->latm_lig;
+        int nal = pdb_w_lig->natm_lig, j, nvn = 0, nai = 0, nmol = 1;
+        int *la = malloc(sizeof(int) * nal), *lm = malloc(sizeof(int) * nal);
+        char chain_tmp[2];
+        int resnumber_tmp = lig[0]->res_id;
+        strncpy(chain_tmp, lig[0]->chain, 2);
+        for (j = 0; j < nal; j++) {
+            if (strncmp(chain_tmp, lig[j]->chain, 2) != 0 || resnumber_tmp != lig[j]->res_id) {
+                nmol++; strncpy(chain_tmp, lig[j]->chain, 2); resnumber_tmp = lig[j]->res_id;
+            }
+            la[j] = (int)(lig[j] - pdb_w_lig->latoms); lm[j] = nmol - 1;
+        }
+        rec1("lig.atoms", 'i', nal, la);
+        rec1("lig.mol", 'i', nal, lm);
+        s_atm **interface = get_mol_ctd_atm_neigh(lig, nal, lvert->pvertices, lvert->nvert, M_VERT_LIG_NEIG_DIST, M_INTERFACE_SEARCH, &nai);
+        s_vvertice **tpverts = get_mol_vert_neigh(lig, nal, lvert->pvertices, lvert->nvert, M_VERT_LIG_NEIG_DIST, &nvn);
+        int *ia = malloc(sizeof(int) * (nai + 1)), *xs = malloc(sizeof(int) * (nvn + 1));
+        for (j = 0; j < nai; j++) ia[j] = (int)(interface[j] - pdb->latoms);       /* discovery order of the sweep */
+        for (j = 0; j < nvn; j++) xs[j] = (int)(tpverts[j] - lvert->vertices);
+        rec1("lig.iface", 'i', nai, ia);
+        rec1("lig.xspheres", 'i', nvn, xs);
+        float *crit = malloc(sizeof(float) * 4 * pockets->n_pockets);
+        node_pocket *cur = pockets->first;
+        int q = 0;
+        while (cur) {
+            int nbpa = 0;
+            s_atm **patoms = get_vert_contacted_atms(cur->pocket->v_lst, &nbpa);
+            float ovlp = atm_corsp(interface, nai, patoms, nbpa), dst = 0, tmp;
+            for (j = 0; j < nal; j++) {
+                tmp = dist(lig[j]->x, lig[j]->y, lig[j]->z, cur->pocket->bary[0], cur->pocket->bary[1], cur->pocket->bary[2]);
+                if (j == 0) dst = tmp; else if (tmp < dst) dst = tmp;
+            }
+            s_vvertice **pvert = get_pocket_pvertices(cur->pocket);
+            float c4 = count_atm_prop_vert_neigh(lig, nal, pvert, cur->pocket->size, M_CRIT4_D, nmol);
+            float c5 = count_pocket_lig_vert_ovlp(lig, nal, pvert, cur->pocket->size, M_CRIT5_D);
+            crit[4 * q] = ovlp; crit[4 * q + 1] = dst; crit[4 * q + 2] = c4; crit[4 * q + 3] = c5;
+            q++;
+            cur = cur->next;
+        }
+        int d2[2] = {q, 4};
+        rec("lig.crit", 'f', 2, d2, crit);
     }
     rec_i("status", 0);
     fclose(OUT);

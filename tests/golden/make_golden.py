@@ -31,6 +31,7 @@ CASES = [
     ("1UYD_explicit", "1UYD.pdb", ["--seed", "16"], ["-r", "1224:PU8:A"]),       # test_fpocket.py:117
     ("2P0R_mod_aD", "2P0R_mod.pdb", ["--seed", "17"], ["-a", "D"]),              # test_fpocket.py:125
     ("5RGF_cif", "5RGF.cif", ["--seed", "18"], []),                              # test_mmcif.py:77
+    ("1UYD_dpocket", "1UYD.pdb", ["--seed", "19", "--lig", "PU8"], []),            # dpocket.c:186-290 with the known ligand
     ("md_2yex", "mdpocket/2yex.pdb", ["--md"], []),                           # mdpocket.c:833 call shape
     ("md_3ot3_S", "mdpocket/3ot3.pdb", ["--md", "--score"], []),              # -S drug-score increments
 ]
@@ -38,7 +39,10 @@ CASES = [
 
 def main():
     tmp = tempfile.mkdtemp(prefix="fpkgold")
+    only = set(sys.argv[1:])            # optional: names of the fixtures to (re)generate
     for name, fn, dflags, opts in CASES:
+        if only and name not in only:
+            continue
         src = os.path.join(REF, "data", "sample", fn)
         if not os.path.exists(src):
             print("skip", name, "(no", src, ")")
@@ -52,7 +56,8 @@ def main():
         d = read_dump(out)
         d["seed"] = np.array([int(dflags[dflags.index("--seed") + 1]) if "--seed" in dflags else 0])
         for k in ("pdb.name", "pdb.type", "pdbw.name", "pdbw.type", "qh.centres", "sph1.f"):
-            d.pop(k, None)
+            if not (k == "pdb.name" and "--lig" in dflags):          # atm_corsp compares atom names (atom.c:281)
+                d.pop(k, None)
         # the reference reads only the flushed part of qhull's output (see oracle/ref_dump.c): keep the full
         # tet list, how many lines were visible and the (possibly cut) last visible line
         seen = d.pop("qh.tets_seen")

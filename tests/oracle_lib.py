@@ -138,8 +138,12 @@ def structure_from_dump(d):
             for (xr, xc, xi) in xp:
                 if xr == rid and xc == ch and (xi == ins or (xi == ord("-") and ins in (ord(" "), 0))):
                     extra[k] |= capi.FPK_ATOM_XPOCKET
-    return structure_from_arrays(d["pdb.f"], d["pdb.i"], d["pdb.symbol"], d["pdb.res_name"], d["pdb.bfstat"], w=w,
-                                 same_pdb=md, xlig=xlig, extra_flags=extra)
+    st = structure_from_arrays(d["pdb.f"], d["pdb.i"], d["pdb.symbol"], d["pdb.res_name"], d["pdb.bfstat"], w=w,
+                               same_pdb=md, xlig=xlig, extra_flags=extra)
+    if "lig.atoms" in d:            # dpocket fixture: the known ligand (indices into pdb_w_lig), atom names packed for atm_corsp
+        nk = np.ascontiguousarray(d["pdb.name"][:, :4]).view(np.int32).reshape(-1) if "pdb.name" in d else None
+        st.set_ligand(d["lig.atoms"], d["lig.mol"], nk)
+    return st
 
 
 def params_from_dump(d, **kw):

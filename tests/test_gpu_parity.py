@@ -43,6 +43,9 @@ def assert_same_result(r, o, what=""):
     assert np.array_equal(D["aa_compo"], E["aa_compo"]) and np.array_equal(D["bary"], E["bary"]), what
     assert r["n_pockets"] == o["n_pockets"] and np.array_equal(r["rank_to_cluster"], o["rank_to_cluster"]), what
     assert G.eq_nan(r["atom_fx"], o["atom_fx"]), what
+    if "xspheres" in o:             # dpocket ligand queries (K6)
+        for k in ("xspheres", "iface_atoms", "pk_ovlp", "pk_dst", "pk_c4", "pk_c5"):
+            assert k in r and np.array_equal(r[k], o[k]), (what, k)
 
 
 @pytest.mark.parametrize("case", G.ALL)

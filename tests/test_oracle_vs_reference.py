@@ -70,3 +70,23 @@ def test_reference_tail_loss_is_real():
     d = G.load("1UYD")
     assert int(d["qh.out_len"][1]) == (int(d["qh.out_len"][0]) // 4096) * 4096
     assert int(d["qh.n_seen"][0]) < len(d["qh.tets"])
+
+
+def test_oracle_ligand_queries_equal_the_reference_functions():
+    """dpocket (dpocket.c:228-290): fed the reference's tets, the oracle's restatement of the ligand queries - sets and counts of the
+    strict dist() < d relation - must equal what the reference's own x-sorted sweeps returned (neighbor.c:192,313,490,598, atom.c:264),
+    element for element once sorted, and the per-pocket criteria bit for bit."""
+    d = G.load("1UYD_dpocket")
+    st, p = G.inputs(d)
+    r = O.search_pocket(st, p, tets=d["qh.tets_seen"], rng_mode=O.RNG_LIBC)
+    assert r["n_pockets"] == len(d["lig.crit"]) and r["n_spheres"] == len(d["sph0.f"])
+    assert np.array_equal(r["iface_atoms"], np.sort(d["lig.iface"]))
+    # get_mol_vert_neigh drops a sphere whose v->id was "already seen" (neighbor.c:244 is_in_lst_vert), and v->id is NOT unique: it is
+    # natoms + qhull index + 1 - kept-so-far (voronoi.c:488), constant over runs of consecutive kept tets. The reference's explicit pocket
+    # is therefore an order-dependent subset of the relation; ours is the relation itself. Every sphere it lacks is such a collision.
+    ours, ref, ids = set(r["xspheres"].tolist()), set(d["lig.xspheres"].tolist()), d["sph0.i"][:, 7]
+    assert ref <= ours
+    assert {int(ids[s]) for s in ours - ref} <= {int(ids[s]) for s in ref}
+    assert len({int(ids[s]) for s in ours}) == len(ref) == len({int(ids[s]) for s in ref})
+    got = np.stack([r["pk_ovlp"], r["pk_dst"], r["pk_c4"], r["pk_c5"]], 1)
+    assert np.array_equal(got, d["lig.crit"])
