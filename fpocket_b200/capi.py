@@ -87,7 +87,7 @@ class FpkResult(C.Structure):
         ("sph_cluster", _ip), ("n_clusters", C.c_int32), ("cl_off", _ip), ("cl_sph", _ip), ("cl_atom_off", _ip),
         ("cl_atoms", _ip), ("desc", C.POINTER(FpkDesc)), ("n_pockets", C.c_int32), ("rank_to_cluster", _ip),
         ("atom_fx", _fp), ("_owner", C.c_void_p),
-        ("n_xspheres", C.c_int32), ("xspheres", _ip), ("n_iface", C.c_int32), ("iface_atoms", _ip),
+        ("n_xspheres", C.c_int32), ("xspheres", _ip), ("xdesc", C.POINTER(FpkDesc)), ("n_iface", C.c_int32), ("iface_atoms", _ip),
         ("pk_ovlp", _fp), ("pk_dst", _fp), ("pk_c4", _fp), ("pk_c5", _fp),
     ]
 
@@ -120,6 +120,7 @@ def result_to_dict(r, natoms):
     d["cl_atoms"] = _arr(r.cl_atoms, (na,), np.int32)
     if r.xspheres or r.pk_dst:                       # dpocket ligand queries
         d["xspheres"] = _arr(r.xspheres, (r.n_xspheres,), np.int32)
+        d["xdesc"] = _arr(r.xdesc, (1,), DESC_DTYPE) if r.xdesc else None
         d["iface_atoms"] = _arr(r.iface_atoms, (r.n_iface,), np.int32)
         for k in ("pk_ovlp", "pk_dst", "pk_c4", "pk_c5"):
             d[k] = _arr(getattr(r, k), (npk,), np.float32)

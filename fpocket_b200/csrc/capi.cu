@@ -214,7 +214,7 @@ struct fpk_batch {
     bool has_names = false;
     std::vector<int> lig_n;
     LigDev Lg;                         // dpocket ligand queries (tot_lig > 0)
-    std::vector<int> h_nx, h_ni;
+    std::vector<int> h_ni;
     int max_sites = 0, max_w = 0, max_sphcap = 0;
     int md_shared_props = 0;           // mdpocket: all frames share the property arrays
     // stage 1 device
@@ -373,6 +373,10 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
         b->Lg.name_key = b->has_names ? a.take<int>(b->tot_atoms + 1) : nullptr;
         a.take<char>(0);
         b->in_bytes = a.used;                      // everything above is input: mirrored in pinned host memory, one copy
+        if (b->tot_lig > 0) {
+            b->Lg.xpos = a.take<int>(b->tot_sphcap + n + 1); b->Lg.ipos = a.take<int>(b->tot_atoms + n + 1);
+            b->Lg.ilist = a.take<int>(b->tot_atoms + n + 1); b->Lg.ni = a.take<int>(n);
+        }
         B.s_xyzr = a.take<float4>(b->tot_sphcap); B.s_bary = a.take<float>(3 * b->tot_sphcap);
         B.s_neigh = a.take<int4>(b->tot_sphcap); B.s_key = a.take<int4>(b->tot_sphcap);
         B.s_type = a.take<uint8_t>(b->tot_sphcap); B.s_cluster = a.take<int>(b->tot_sphcap);
@@ -477,6 +481,8 @@ __global__ void k_compact(BatchDev B, const int *sbase, float4 *xyzr, float *bar
         bary[3 * (size_t)(d0 + i) + 2] = B.s_bary[3 * (size_t)s + 2];
         cl_sph[d0 + i] = nc ? B.cl_sph[s] : 0;
     }
+    if (counts[CNT_XP] == 1)        // dpocket's explicit pocket: its sphere list sits after the partition
+        for (int i = threadIdx.x; i < counts[CNT_NX]; i += blockDim.x) cl_sph[d0 + ns + i] = B.cl_sph[S.sph_off + ns + i];
     for (int i = threadIdx.x; i <= nc; i += blockDim.x) cl_off[clbase[k] + k + i] = B.cl_off[S.sph_off + k + i];
 }
 
@@ -491,6 +497,8 @@ static int batch_run(fpk_batch *b)
     k_delaunay_filter<<<b->nDel, 256, b->k1_dsm>>>(B, b->dDel, b->k1_picap);
     CK(cudaEventRecord(b->ev[1]));
     k_cluster<<<b->nClu, 256>>>(B, b->dClu, b->d_counters + 1);
+    const bool lig = b->tot_lig > 0 && b->prm.skip_clustering == 0;
+    if (lig) { k_ligand_select<<<n, 256>>>(B, b->Lg); b->launches++; }
     CK(cudaEventRecord(b->ev[2]));
     b->launches += 2;
     // ---- the one host round trip: per-structure counts -> exact sizes of the pocket-level arrays -----------------------
@@ -505,7 +513,7 @@ static int batch_run(fpk_batch *b)
         bool have = c[CNT_STATUS] == FPK_OK || c[CNT_STATUS] == FPK_ERR_NO_SPHERES || c[CNT_STATUS] == FPK_ERR_NO_POCKETS;
         int ns = have ? c[CNT_SPHERES] : 0;
         b->h_clbase[k + 1] = b->h_clbase[k] + c[CNT_CLUSTERS];
-        b->h_sbase[k + 1] = b->h_sbase[k] + ns;
+        b->h_sbase[k + 1] = b->h_sbase[k] + ns + (have && c[CNT_XP] == 1 ? c[CNT_NX] : 0);      // room for the explicit pocket's pocket-level arrays
         max_ns = std::max(max_ns, ns);
         tt += c[CNT_TETS];
     }
@@ -535,16 +543,13 @@ static int batch_run(fpk_batch *b)
         b->c_type = a.take<uint8_t>(NS + 1); b->c_cluster = a.take<int>(NS + 1); b->c_cl_sph = a.take<int>(NS + 1);
         b->c_cl_off = a.take<int>(NC + n + 1);
         b->dHull = a.take<DelScratch>(b->nHull); b->dDesc = a.take<DescScratch>(b->nDesc);
-        if (b->tot_lig > 0) {
-            b->Lg.xpos = a.take<int>(NS + n + 1); b->Lg.xlist = a.take<int>(NS + n + 1);
-            b->Lg.ipos = a.take<int>(b->tot_atoms + n + 1); b->Lg.ilist = a.take<int>(b->tot_atoms + n + 1);
-            b->Lg.nx = a.take<int>(n); b->Lg.ni = a.take<int>(n); b->Lg.crit = a.take<float>(4 * NC + 4);
-        }
+        if (b->tot_lig > 0) b->Lg.crit = a.take<float>(4 * NC + 4);
         if (full) for (int i = 0; i < b->nHull; i++) del_scratch_layout(a, hHull[i], max_ns, 0, HULL_THREADS, false);
         for (int i = 0; i < b->nDesc; i++) hDesc[i].sa = a.take<int>(b->max_w + 1);
     });
     if (rc) return rc;
     Pk.clbase = b->d_clbase; Pk.sbase = b->d_sbase; Pk.total_clusters = (int)NC;
+    Pk.xp_ilist = lig ? b->Lg.ilist : nullptr; Pk.xp_ni = lig ? b->Lg.ni : nullptr;
     CK(cudaMemcpyAsync(b->d_clbase, b->h_clbase.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
     CK(cudaMemcpyAsync(b->d_sbase, b->h_sbase.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
     if (full) CK(cudaMemcpyAsync(b->dHull, hHull.data(), sizeof(DelScratch) * b->nHull, cudaMemcpyHostToDevice));
@@ -566,7 +571,7 @@ static int batch_run(fpk_batch *b)
     } else {
         CK(cudaEventRecord(b->ev[4])); CK(cudaEventRecord(b->ev[5]));
     }
-    if (b->tot_lig > 0 && b->prm.skip_clustering == 0) { k_ligand<<<n, 256>>>(B, Pk, b->Lg); b->launches++; }
+    if (lig && NC > 0) { k_ligand<<<n, 256>>>(B, Pk, b->Lg); b->launches++; }
     k_compact<<<n, 128>>>(B, b->d_sbase, b->c_xyzr, b->c_bary, b->c_neigh, b->c_type, b->c_cluster, b->c_cl_sph, b->c_cl_off, b->d_clbase);
     b->launches++;
     CK(cudaEventRecord(b->ev[6]));
@@ -608,13 +613,13 @@ static int batch_fetch(fpk_batch *b, fpk_result *out)
         (rc = d2h(b, cl_off, b->c_cl_off, NC + n)) || (rc = d2h(b, desc, b->Pk.desc, NC)) || (rc = d2h(b, sparse, b->Pk.cl_atoms, 4 * NS)) ||
         (rc = d2h(b, rank, b->Pk.rank_to_cluster, NS + n)) || (rc = d2h(b, atom_fx, b->Pk.atom_fx, 4 * NA))) { delete H; return rc; }
     const bool lig = b->tot_lig > 0 && b->prm.skip_clustering == 0;
-    int *xlist = nullptr, *ilist = nullptr;
+    int *ilist = nullptr;
     float *crit = nullptr, *pk4 = nullptr;
     if (lig) {
-        xlist = H->take<int>(NS + n + 1); ilist = H->take<int>(NA + n + 1); crit = H->take<float>(4 * NC + 4); pk4 = H->take<float>(4 * NC + 4);
-        b->h_nx.resize(n); b->h_ni.resize(n);
-        if ((rc = d2h(b, xlist, b->Lg.xlist, NS + n)) || (rc = d2h(b, ilist, b->Lg.ilist, NA + n)) || (rc = d2h(b, crit, b->Lg.crit, 4 * NC)) ||
-            (rc = d2h(b, b->h_nx.data(), b->Lg.nx, (size_t)n)) || (rc = d2h(b, b->h_ni.data(), b->Lg.ni, (size_t)n))) { delete H; return rc; }
+        ilist = H->take<int>(NA + n + 1); crit = H->take<float>(4 * NC + 4); pk4 = H->take<float>(4 * NC + 4);
+        b->h_ni.resize(n);
+        if ((rc = d2h(b, ilist, b->Lg.ilist, NA + n)) || (rc = d2h(b, crit, b->Lg.crit, 4 * NC)) ||
+            (rc = d2h(b, b->h_ni.data(), b->Lg.ni, (size_t)n))) { delete H; return rc; }
     }
     CK(cudaStreamSynchronize(cudaStreamPerThread));
     if (b->B.tets_out) {
@@ -641,8 +646,10 @@ static int batch_fetch(fpk_batch *b, fpk_result *out)
         r.status = c[CNT_STATUS];
         r.n_sites = b->S[k].nsites;
         r.n_tets = c[CNT_TETS];
-        const int s0 = b->h_sbase[k], ns = b->h_sbase[k + 1] - s0, c0 = b->h_clbase[k], nc = b->h_clbase[k + 1] - c0;
-        r.n_spheres = ns; r.n_clusters = nc; r.n_pockets = c[CNT_POCKETS];
+        const bool have = c[CNT_STATUS] == FPK_OK || c[CNT_STATUS] == FPK_ERR_NO_SPHERES || c[CNT_STATUS] == FPK_ERR_NO_POCKETS;
+        const int xp = (have && c[CNT_XP] == 1) ? 1 : 0;
+        const int s0 = b->h_sbase[k], ns = have ? c[CNT_SPHERES] : 0, c0 = b->h_clbase[k], nc = b->h_clbase[k + 1] - c0;
+        r.n_spheres = ns; r.n_clusters = nc - xp; r.n_pockets = c[CNT_POCKETS];
         if (b->B.tets_out) { r.tets = &H->tets[tetpos]; tetpos += 4 * (size_t)std::min(r.n_tets, b->S[k].tet_cap); }
         r.sph_xyzr = xyzr + 4 * (size_t)s0; r.sph_bary = bary + 3 * (size_t)s0;
         r.sph_neigh = neigh + 4 * (size_t)s0; r.sph_type = type + s0; r.sph_cluster = cluster + s0;
@@ -662,7 +669,7 @@ static int batch_fetch(fpk_batch *b, fpk_result *out)
         }
         r.cl_atom_off = ao;
         if (lig && in_has_lig(b, k)) {
-            r.n_xspheres = b->h_nx[k]; r.xspheres = xlist + s0 + k;
+            if (xp) { r.n_xspheres = c[CNT_NX]; r.xspheres = r.cl_sph + r.cl_off[nc - 1]; r.xdesc = r.desc + (nc - 1); }
             r.n_iface = b->h_ni[k]; r.iface_atoms = ilist + b->S[k].atom_off + k;
             float *o = pk4 + 4 * (size_t)c0;
             const int np = r.n_pockets;

@@ -20,7 +20,10 @@ struct StructDev {
 };
 
 enum { CNT_TETS = 0, CNT_SPHERES = 1, CNT_CLUSTERS = 2, CNT_POCKETS = 3, CNT_STATUS = 4, CNT_SUBROUNDS = 5, CNT_RETRIES = 6,
-       CNT_NBIG = 7, CNT_WALK = 8, CNT_LEVELS = 9, CNT_ATTEMPTS = 10, CNT_HOPS = 11, CNT_STRIDE = 12 };
+       CNT_NBIG = 7, CNT_WALK = 8, CNT_LEVELS = 9, CNT_ATTEMPTS = 10, CNT_HOPS = 11,
+       CNT_XP = 12,      // 1: the last cluster is dpocket's explicit pocket (spheres near the known ligand), not a pocket of the partition
+       CNT_NX = 13,      // its number of spheres
+       CNT_STRIDE = 16 };
 
 struct BatchDev {
     int nstruct;

@@ -34,7 +34,9 @@ __global__ void __launch_bounds__(HULL_THREADS, 8) k_hull_volume(BatchDev B, Poc
         const StructDev S = B.S[k];
         const int *cl_off = B.cl_off + S.sph_off + k;
         const int off = cl_off[c], n = cl_off[c + 1] - off;
-        if (n < 10 || n < B.prm.min_pock_nb_asph) continue;     // voronoi.c:1244: volume 0 (desc is zero-initialised); always-dropped clusters (refine.c:124) too
+        const int *kc = B.counts + (size_t)k * CNT_STRIDE;
+        const bool xp = kc[CNT_XP] == 1 && c == kc[CNT_CLUSTERS] - 1;      // dpocket's explicit pocket: always described
+        if (n < 10 || (n < B.prm.min_pock_nb_asph && !xp)) continue;     // voronoi.c:1244: volume 0 (desc is zero-initialised); always-dropped clusters (refine.c:124) too
         const int *L = B.cl_sph + S.sph_off + off;
         const float4 *sx = B.s_xyzr + S.sph_off;
         for (int i = tid; i < n; i += nt) {
@@ -192,37 +194,36 @@ struct LigDev {
     const int *lig_idx;        // indices into the pdb_w_lig atom arrays (pdb arrays when there is no separate copy)
     const int *lig_mol;
     const int *name_key;       // [natoms_total] or nullptr
-    int *xpos;                 // [sbase[nstruct] + nstruct + 1] scratch -> explicit-pocket sphere list per structure at sbase[k] + k
-    int *ipos;                 // [natoms_total + nstruct + 1]   scratch -> interface atom list per structure at atom_off + k
-    int *xlist, *ilist;        // compact lists (same bases as xpos / ipos)
-    int *nx, *ni;              // [nstruct]
+    int *xpos;                 // [sphcap_total + nstruct + 1] scratch of the selection, per structure at sph_off + k
+    int *ipos;                 // [natoms_total + nstruct + 1] scratch, per structure at atom_off + k
+    int *ilist;                // interface atoms (ascending) per structure at atom_off + k
+    int *ni;                   // [nstruct]
     float *crit;               // [4 * total_clusters]: ovlp, dst, c4, c5 of the pocket ranked r of structure k at 4 * (clbase[k] + r)
 };
 enum { LIG_MAXMOL = 64 };
 
-__global__ void __launch_bounds__(256) k_ligand(BatchDev B, PocketDev Pk, LigDev G)
+// K6a (after K3): the explicit pocket = spheres within lig_interface_dist of a ligand atom, appended to the structure's cluster list as
+// one more cluster (K4 / K4b then give it a descriptor record like any pocket, dpocket.c:350 set_descriptors), and the interface atoms.
+__global__ void __launch_bounds__(256) k_ligand_select(BatchDev B, LigDev G)
 {
-    __shared__ int s_sm[40], s_hit[8][LIG_MAXMOL], s_tot[8][LIG_MAXMOL];
-    const int k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nt >> 5;
+    __shared__ int s_sm[40];
+    const int k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     const StructDev S = B.S[k];
-    const int *counts = B.counts + (size_t)k * CNT_STRIDE;
+    int *counts = B.counts + (size_t)k * CNT_STRIDE;
     const int L0 = G.lig_off[k], nl = G.lig_off[k + 1] - L0;
-    if (tid == 0) { G.nx[k] = 0; G.ni[k] = 0; }
-    if (nl <= 0) return;
-    const int st = counts[CNT_STATUS];
-    if (st != FPK_OK && st != FPK_ERR_NO_POCKETS) return;
-    const int ns = counts[CNT_SPHERES], na = S.natoms;
+    if (tid == 0) { G.ni[k] = 0; counts[CNT_XP] = 0; counts[CNT_NX] = 0; }
+    if (nl <= 0 || counts[CNT_STATUS] != FPK_OK || B.prm.skip_clustering) return;
+    const int ns = counts[CNT_SPHERES], na = S.natoms, nc = counts[CNT_CLUSTERS];
     const int W0 = S.natoms_w ? S.w_off : S.atom_off;
     const float *wx = S.natoms_w ? B.wx : B.ax, *wy = S.natoms_w ? B.wy : B.ay, *wz = S.natoms_w ? B.wz : B.az;
-    const int *lig = G.lig_idx + L0, *mol = G.lig_mol + L0;
+    const int *lig = G.lig_idx + L0;
     const float4 *sx = B.s_xyzr + S.sph_off;
     const int4 *sn = B.s_neigh + S.sph_off;
-    int *xpos = G.xpos + Pk.sbase[k] + k, *ipos = G.ipos + S.atom_off + k;
-    int *xlist = G.xlist + Pk.sbase[k] + k, *ilist = G.ilist + S.atom_off + k;
-    const float dcrit = B.prm.lig_interface_dist, ccrit = B.prm.lig_crit_dist;
+    int *xpos = G.xpos + S.sph_off + k, *ipos = G.ipos + S.atom_off + k, *ilist = G.ilist + S.atom_off + k;
+    int *cl_off = B.cl_off + S.sph_off + k, *cl_sph = B.cl_sph + S.sph_off;
+    const float dcrit = B.prm.lig_interface_dist;
     for (int i = tid; i <= na; i += nt) ipos[i] = 0;
     __syncthreads();
-    // ---- explicit pocket spheres and interface atoms -------------------------------------------------------------------------
     for (int s = tid; s <= ns; s += nt) {
         int near = 0;
         if (s < ns) {
@@ -244,12 +245,32 @@ __global__ void __launch_bounds__(256) k_ligand(BatchDev B, PocketDev Pk, LigDev
     __syncthreads();
     const int nx = block_exclusive_scan(xpos, ns + 1, s_sm);
     const int ni = block_exclusive_scan(ipos, na + 1, s_sm);
-    for (int s = tid; s < ns; s += nt) if (xpos[s + 1] != xpos[s]) xlist[xpos[s]] = s;
+    const bool fits = nx > 0 && ns + nx <= S.sph_cap;
+    if (fits) for (int s = tid; s < ns; s += nt) if (xpos[s + 1] != xpos[s]) cl_sph[ns + xpos[s]] = s;
     for (int a = tid; a < na; a += nt) if (ipos[a + 1] != ipos[a]) ilist[ipos[a]] = a;
-    if (tid == 0) { G.nx[k] = nx; G.ni[k] = ni; }
-    __syncthreads();
-    // ---- per surviving pocket: ovlp, dst, c4, c5 (one warp per pocket) ----------------------------------------------------------
-    const int npk = st == FPK_OK ? counts[CNT_POCKETS] : 0;
+    if (tid == 0) {
+        G.ni[k] = ni;
+        if (fits) { cl_off[nc + 1] = ns + nx; counts[CNT_CLUSTERS] = nc + 1; counts[CNT_XP] = 1; counts[CNT_NX] = nx; }
+    }
+}
+
+// K6b (after K4c): per surviving pocket ovlp, dst, c4, c5 (one warp per pocket)
+__global__ void __launch_bounds__(256) k_ligand(BatchDev B, PocketDev Pk, LigDev G)
+{
+    __shared__ int s_hit[8][LIG_MAXMOL], s_tot[8][LIG_MAXMOL];
+    const int k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nt >> 5;
+    const StructDev S = B.S[k];
+    const int *counts = B.counts + (size_t)k * CNT_STRIDE;
+    const int L0 = G.lig_off[k], nl = G.lig_off[k + 1] - L0;
+    if (nl <= 0 || counts[CNT_STATUS] != FPK_OK) return;
+    const int W0 = S.natoms_w ? S.w_off : S.atom_off;
+    const float *wx = S.natoms_w ? B.wx : B.ax, *wy = S.natoms_w ? B.wy : B.ay, *wz = S.natoms_w ? B.wz : B.az;
+    const int *lig = G.lig_idx + L0, *mol = G.lig_mol + L0;
+    const float4 *sx = B.s_xyzr + S.sph_off;
+    const int *ilist = G.ilist + S.atom_off + k;
+    const int ni = G.ni[k];
+    const float ccrit = B.prm.lig_crit_dist;
+    const int npk = counts[CNT_POCKETS];
     const int *cl_off = B.cl_off + S.sph_off + k, *cl_sph = B.cl_sph + S.sph_off;
     const int *rank = Pk.rank_to_cluster + Pk.sbase[k] + k;
     const fpk_desc *D = Pk.desc + Pk.clbase[k];

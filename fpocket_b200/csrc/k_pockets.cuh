@@ -29,6 +29,8 @@ struct PocketDev {            // cluster-level arrays, sized after K3 (exact num
     float *atom_fx;           // [4*natoms_total] result
     int *rank_to_cluster;     // [sph_off ...) per structure
     int total_clusters;
+    const int *xp_ilist;      // dpocket: interface atoms of structure k at atom_off + k (ascending), count xp_ni[k]; nullptr without ligands
+    const int *xp_ni;
 };
 
 struct ClusterScratch {       // per resident block of K3
@@ -287,7 +289,9 @@ __global__ void __launch_bounds__(K4_THREADS) k_descriptors(BatchDev B, PocketDe
         const float *wr = S.natoms_w ? B.wrad : B.arad, *we = S.natoms_w ? B.wen : B.aen;
         const uint8_t *wf = S.natoms_w ? B.wfl : B.afl;
         const bool full = prm.do_asa_and_volume != 0;
-        const bool observable = n >= prm.min_pock_nb_asph;      // below it the cluster is always dropped (refine.c:124): no MC samples
+        const int *kcnt = B.counts + (size_t)k * CNT_STRIDE;
+        const bool explicit_pocket = kcnt[CNT_XP] == 1 && c == kcnt[CNT_CLUSTERS] - 1;     // dpocket.c:350: described from the interface atoms
+        const bool observable = explicit_pocket || n >= prm.min_pock_nb_asph;      // below it the cluster is always dropped (refine.c:124): no MC samples
         const bool insm = n <= MC_SMEM_SPH;
         const float correct = -1.6f;
 
@@ -390,11 +394,14 @@ __global__ void __launch_bounds__(K4_THREADS) k_descriptors(BatchDev B, PocketDe
                     }
                 }
             }
-            // first occurrence of every residue id among the contacted atoms (descriptors.c:408 in_tab), one lane per atom
-            for (int u = lane; u < U; u += 32) {
-                const int rid = B.ares[Q0 + uat[u]];
+            // atoms of the atom-based descriptors: the contacted atoms; for dpocket's explicit pocket the interface atoms (dpocket.c:350)
+            const int *alist = explicit_pocket ? Pk.xp_ilist + S.atom_off + k : uat;
+            const int UA = explicit_pocket ? Pk.xp_ni[k] : U;
+            // first occurrence of every residue id among them (descriptors.c:408 in_tab), one lane per atom
+            for (int u = lane; u < UA; u += 32) {
+                const int rid = B.ares[Q0 + alist[u]];
                 bool seen = false;
-                for (int q = 0; q < u && !seen; q++) seen = B.ares[Q0 + uat[q]] == rid;
+                for (int q = 0; q < u && !seen; q++) seen = B.ares[Q0 + alist[q]] == rid;
                 entu[u] = seen ? 0 : 1;                     // ent_u is free once the CSR is built
             }
             __syncwarp();
@@ -418,11 +425,11 @@ __global__ void __launch_bounds__(K4_THREADS) k_descriptors(BatchDev B, PocketDe
                 d.bary[0] = ps0 / (float)n; d.bary[1] = ps1 / (float)n; d.bary[2] = ps2 / (float)n;      // refine.c:192-240
                 d.n_atoms = U;
                 // atom based (descriptors.c:355-436, :453-513)
-                if (U > 1) {
+                if (UA > 1) {
                     int nb_res = 0, nb_polar = 0;
                     float flex = 0.0f, hyd = 0.0f, vol = 0.0f;
-                    for (int u = 0; u < U; u++) {
-                        const int a = Q0 + uat[u];
+                    for (int u = 0; u < UA; u++) {
+                        const int a = Q0 + alist[u];
                         if (entu[u]) {
                             int aa = B.aaa[a];
                             if (aa >= 0) {
@@ -436,8 +443,8 @@ __global__ void __launch_bounds__(K4_THREADS) k_descriptors(BatchDev B, PocketDe
                     }
                     d.hydrophobicity_score = hyd / (float)nb_res;
                     d.volume_score = vol / (float)nb_res;
-                    d.flex = flex / (float)U;
-                    d.prop_polar_atm = (float)((double)(((float)nb_polar) / ((float)U)) * 100.0);
+                    d.flex = flex / (float)UA;
+                    d.prop_polar_atm = (float)((double)(((float)nb_polar) / ((float)UA)) * 100.0);
                 }
                 d.mean_loc_hyd_dens = nAlphaApol > 0 ? (float)mlhd_cnt / (float)nAlphaApol : 0.0f;
                 d.as_max_dst = as_max_dst;
@@ -678,7 +685,7 @@ __global__ void __launch_bounds__(K4_THREADS) k_descriptors(BatchDev B, PocketDe
                             const float na = (float)acc[4 * u + 2], np = (float)acc[4 * u + 3];
                             fxv[4 * u + 0] = na / (na + np);     // abpa_sourrounding_prob
                             fxv[4 * u + 3] = 0.0f;
-                            atomicMax(&Pk.fx_who[2 * ga], c);
+                            if (!explicit_pocket) atomicMax(&Pk.fx_who[2 * ga], c);
                         } else {
                             if (apolar_atom) d.surf_apol_vdw22 = d.surf_apol_vdw22 + area;
                             else {
@@ -687,7 +694,7 @@ __global__ void __launch_bounds__(K4_THREADS) k_descriptors(BatchDev B, PocketDe
                                     d.n_abpa += 1;
                                     fxv[4 * u + 2] = area - a14;   // dA ; a0 = a14
                                     fxv[4 * u + 3] = 1.0f;
-                                    atomicMax(&Pk.fx_who[2 * ga + 1], c);
+                                    if (!explicit_pocket) atomicMax(&Pk.fx_who[2 * ga + 1], c);
                                 }
                                 d.surf_pol_vdw22 = d.surf_pol_vdw22 + area;
                             }
@@ -714,7 +721,7 @@ __global__ void __launch_bounds__(128) k_finalize(BatchDev B, PocketDev Pk)
     int *counts = B.counts + (size_t)k * CNT_STRIDE;
     const StructDev S = B.S[k];
     if (counts[CNT_STATUS] != FPK_OK) { if (tid == 0) counts[CNT_POCKETS] = 0; return; }
-    const int nc = counts[CNT_CLUSTERS];
+    const int nc = counts[CNT_CLUSTERS] - (counts[CNT_XP] == 1 ? 1 : 0);        // dpocket's explicit pocket is not one of the pockets
     fpk_desc *D = Pk.desc + Pk.clbase[k];
     const fpk_params &prm = B.prm;
     __shared__ float s_f[10];
@@ -815,7 +822,7 @@ __global__ void k_atom_fx(BatchDev B, PocketDev Pk)
     while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (Pk.clbase[mid] <= item) lo = mid; else hi = mid; }
     const int k = lo, c = item - Pk.clbase[k];
     const StructDev S = B.S[k];
-    if (B.counts[(size_t)k * CNT_STRIDE + CNT_CLUSTERS] <= c) return;
+    if (B.counts[(size_t)k * CNT_STRIDE + CNT_CLUSTERS] - (B.counts[(size_t)k * CNT_STRIDE + CNT_XP] == 1 ? 1 : 0) <= c) return;
     const int *cl_off = B.cl_off + S.sph_off + k;
     const int R = Pk.sbase[k] + cl_off[c];
     const int U = Pk.desc[item].n_atoms;

@@ -145,6 +145,8 @@ typedef struct fpk_result {
     /* ---- dpocket ligand queries (neighbor.c), filled when the structure carried ligand atoms; sets in ascending index order ---- */
     int32_t n_xspheres;        /* get_mol_vert_neigh (neighbor.c:192): spheres with dist(centre, some ligand atom) < lig_interface_dist */
     int32_t *xspheres;         /* [n_xspheres] sphere indices: the explicit pocket of dpocket.c:341-349 */
+    fpk_desc *xdesc;           /* its descriptor record: set_descriptors(interface atoms, these spheres) (dpocket.c:350); NULL if no sphere qualifies.
+                                  Not normalised, not scored, exactly like the reference's edesc */
     int32_t n_iface;           /* get_mol_ctd_atm_neigh(.., M_INTERFACE_SEARCH) (neighbor.c:313): atoms contacted by such a sphere and */
     int32_t *iface_atoms;      /* within 8.0 A (neighbor.h:30) of the ligand atom that reaches the sphere; indices into the pdb atoms   */
     float *pk_ovlp;            /* [n_pockets] rank order: atm_corsp(interface, pocket atoms) in % (atom.c:264, dpocket.c:249)           */

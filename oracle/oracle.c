@@ -392,6 +392,7 @@ static void set_asa(const fpk_structure *in, const sph_t *S, const int *idx, int
     free(sa); free(ua); free(abpatmp);
 }
 
+static int g_force_observable = 0;      /* dpocket's explicit pocket always gets its volume and hull (dpocket.c:350) */
 /* descriptors.c:158-265 set_descriptors + :355-436 set_atom_based_descriptors + :453-513 set_aa_desc */
 static void set_descriptors(const fpk_structure *in, const fpk_params *p, const sph_t *S, const int *idx, int nvert,
                             const int *atoms, int natoms, fpk_desc *d, float *atom_fx, const float *pts,
@@ -468,7 +469,7 @@ static void set_descriptors(const fpk_structure *in, const fpk_params *p, const 
          * written, so the product (ORC_RNG_PHILOX semantics) does not spend 30,000 Monte-Carlo samples and a hull on it:
          * volume = convex_hull_volume = 0 there. ORC_RNG_LIBC keeps the reference's behaviour exactly (it must: the libc
          * rand() stream is consumed by every cluster, fpocket.c:183), which is what pins this file to the reference. */
-        int observable = rng_mode == ORC_RNG_LIBC || nvert >= p->min_pock_nb_asph;
+        int observable = g_force_observable || rng_mode == ORC_RNG_LIBC || nvert >= p->min_pock_nb_asph;
         d->volume = observable ? mc_volume(S, idx, nvert, p->nb_mcv_iter, -1.6f, rng_mode, p->mc_seed, cluster) : 0.0f;
         d->convex_hull_volume = observable ? hull_volume(S, idx, nvert) : 0.0f;
     }
@@ -563,7 +564,7 @@ void orc_result_free(fpk_result *r)
 {
     free(r->tets); free(r->sph_xyzr); free(r->sph_bary); free(r->sph_neigh); free(r->sph_type); free(r->sph_cluster);
     free(r->cl_off); free(r->cl_sph); free(r->cl_atom_off); free(r->cl_atoms); free(r->desc); free(r->rank_to_cluster); free(r->atom_fx);
-    free(r->xspheres); free(r->iface_atoms); free(r->pk_ovlp);
+    free(r->xspheres); free(r->iface_atoms); free(r->pk_ovlp); free(r->xdesc);
     memset(r, 0, sizeof *r);
 }
 
@@ -662,9 +663,38 @@ int orc_search_pocket(const fpk_structure *in, const fpk_params *p, const int *t
     out->n_pockets = nk;
     out->rank_to_cluster = keep;
     for (int k = 0; k < nk; k++) out->desc[keep[k]].final_rank = k + 1;
-    free(S);
     out->status = nk > 0 ? FPK_OK : FPK_ERR_NO_POCKETS;
-    if (in->n_lig > 0 && !p->skip_clustering) orc_ligand_queries(in, p, out);
+    if (in->n_lig > 0 && !p->skip_clustering) {
+        orc_ligand_queries(in, p, out);
+        if (out->n_xspheres > 0) {
+            /* dpocket.c:341-350 get_explicit_desc: set_descriptors(interface atoms, explicit-pocket spheres) - one more record, computed
+             * like a pocket's (canonical = ascending order of both lists) but from the interface atoms, never normalised or scored */
+            const int *idx = out->xspheres, n = out->n_xspheres;
+            fpk_desc *d = out->xdesc = calloc(1, sizeof(fpk_desc));
+            d->first_sphere = idx[0];
+            float ps[3] = {0, 0, 0};
+            for (int i = 0; i < n; i++) {
+                ps[0] += S[idx[i]].x; ps[1] += S[idx[i]].y; ps[2] += S[idx[i]].z;
+                if (S[idx[i]].type == 0) d->nAlphaApol++; else d->nAlphaPol++;
+            }
+            d->bary[0] = ps[0] / (float)n; d->bary[1] = ps[1] / (float)n; d->bary[2] = ps[2] / (float)n;
+            int *atoms = malloc(sizeof(int) * 4 * (size_t)(n + 1)), na = 0;
+            for (int i = 0; i < n; i++)
+                for (int k = 0; k < 4; k++) {
+                    int a = S[idx[i]].neigh[k], seen = 0;
+                    for (int q = 0; q < na; q++) if (in->atom_id[atoms[q]] == in->atom_id[a]) { seen = 1; break; }
+                    if (!seen) atoms[na++] = a;
+                }
+            d->n_atoms = na;
+            free(atoms);
+            float *fx = calloc((size_t)natoms * 4 + 4, sizeof(float));         /* the explicit call's side effects reach no output */
+            g_force_observable = 1;
+            set_descriptors(in, p, S, idx, n, out->iface_atoms, out->n_iface, d, fx, pts, rng_mode, nc);
+            g_force_observable = 0;
+            free(fx);
+        }
+    }
+    free(S);
     return out->status;
 }
 

@@ -46,6 +46,11 @@ def assert_same_result(r, o, what=""):
     if "xspheres" in o:             # dpocket ligand queries (K6)
         for k in ("xspheres", "iface_atoms", "pk_ovlp", "pk_dst", "pk_c4", "pk_c5"):
             assert k in r and np.array_equal(r[k], o[k]), (what, k)
+        assert (r["xdesc"] is None) == (o["xdesc"] is None), what
+        if o["xdesc"] is not None:      # the explicit pocket's own record (dpocket.c:350), bit for bit
+            for n in r["xdesc"].dtype.names:
+                assert G.eq_nan(r["xdesc"][n], o["xdesc"][n]), (what, "xdesc", n, r["xdesc"][n], o["xdesc"][n])
+            assert r["xdesc"]["volume"][0] > 0 and r["xdesc"]["nb_asph"][0] == len(r["xspheres"])
 
 
 @pytest.mark.parametrize("case", G.ALL)
