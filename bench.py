@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--md-frames", type=int, default=2048, help="also measure mdpocket frames/s on a synthetic trajectory of this many frames per GPU (0: skip)")
+    ap.add_argument("--dpocket", type=int, default=1000, help="also measure dpocket (BASELINE configs[4]): this many ligand-bound synthetic structures per GPU (0: skip)")
     ap.add_argument("--large", type=int, default=0, help="also time ONE synthetic complex of this many heavy atoms (BASELINE configs[3]: 150000) on rank 0")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -399,6 +400,62 @@ def main():
             out["mdpocket"]["cpu_baseline"] = {"value": r, "unit": "frames/s", "cores": ncores, "kind": "reference",
                                                "sample": "first %d frames, oracle/_ref/mdpocket --pdb_list (the unmodified reference), %d processes of %d frames each, tmpfs; %s s"
                                                          % (nfr, ncores, 2, ("%.1f" % dt) if r else dt)}
+
+    # ---- dpocket (configs[4]): ligand-bound structures; detection + ligand queries + the explicit pocket's record, one call -----------
+    if args.dpocket > 0:
+        from fpocket_b200 import capi
+        nd = min(args.dpocket, len(structs))
+        res, free = api.detect_batch_raw(structs[:nd], p)                  # first pass: where is the best pocket? the ligand goes there
+        cents = []
+        for k in range(nd):
+            r = res[k]
+            cents.append([r.desc[r.rank_to_cluster[0]].bary[q] for q in range(3)] if r.status == 0 and r.n_pockets > 0 else None)
+        free()
+        rngl = np.random.default_rng(20260501 + rank)
+        ligs = [synth.make_ligand(rngl, c if c is not None else raw[k].xyz.mean(0)) for k, c in enumerate(cents)]
+        cplx = [synth.with_ligand(raw[k], ligs[k]) for k in range(nd)]
+        carr = (capi.FpkStructure * nd)(*[s.c_struct() for s in cplx])
+        _, free = api.detect_batch_raw(cplx, p, c_array=carr)
+        free()
+        barrier()
+        td = time.perf_counter()
+        res, free = api.detect_batch_raw(cplx, p, c_array=carr)
+        okd = sum(1 for k in range(nd) if res[k].status == 0 and res[k].n_xspheres > 0)
+        mean_ovlp = float(np.mean([res[k].pk_ovlp[0] for k in range(nd) if res[k].status == 0 and res[k].n_pockets > 0]))
+        free()
+        barrier()
+        td = time.perf_counter() - td
+        dd = torch.tensor([td], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(dd, op=dist.ReduceOp.MAX)
+        out["dpocket"] = {"metric": "structures/sec", "value": nd * world / float(dd[0]), "structures_per_gpu": nd, "with_explicit_pocket": int(okd),
+                          "mean_overlap_of_top_pocket_pct": mean_ovlp,
+                          "includes": "fpk_detect_batch on host arrays with the known ligand: detection, ligand queries (K6), the explicit pocket's descriptor "
+                                      "record; H2D/D2H inside; 28-atom ligand placed in the best pocket of a first pass"}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            exe = os.path.join(ROOT, "oracle", "_ref", "dpocket")
+            if os.path.exists(exe):
+                nsm = min(nd, 2 * ncores)
+                tmp = tempfile.mkdtemp(prefix="fpkdp", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+                jobs = []
+                per = max(1, (nsm + ncores - 1) // ncores)
+                for c0 in range(0, nsm, per):
+                    d = os.path.join(tmp, "j%03d" % (c0 // per))
+                    os.makedirs(d)
+                    with open(os.path.join(d, "list.txt"), "w") as f:
+                        for k in range(c0, min(nsm, c0 + per)):
+                            fn = os.path.join(d, "c%05d.pdb" % k)
+                            synth.to_pdb(raw[k], fn, ligs[k])
+                            f.write("%s LIG\n" % fn)
+                    jobs.append(d)
+                t0 = time.time()
+                procs = [subprocess.Popen([exe, "-f", os.path.join(d, "list.txt")], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for d in jobs]
+                for pr in procs:
+                    pr.wait()
+                dt = time.time() - t0
+                subprocess.call(["rm", "-rf", tmp])
+                out["dpocket"]["cpu_baseline"] = {"value": nsm / dt, "unit": "structures/s", "cores": ncores, "kind": "reference",
+                                                  "sample": "first %d complexes, oracle/_ref/dpocket -f list (the unmodified reference), %d processes, tmpfs; %.1f s" % (nsm, len(jobs), dt)}
 
     # ---- optional: one large complex (configs[3]); a single Delaunay does not shard: one block of one GPU ------------------------------
     if args.large > 0 and rank == 0:

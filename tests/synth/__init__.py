@@ -68,7 +68,45 @@ def to_structure(s, same_pdb=1):
                      s.aa, np.zeros(n, np.uint8), stat, w=None, same_pdb=same_pdb)
 
 
-def to_pdb(s, path):
+def atom_names(s):
+    names = ["N", "CA", "C", "O"]
+    return [names[int(sl)] if sl < 4 else (ELEM[int(e)] + "%d" % (int(sl) - 3)) for sl, e in zip(s.slot, s.elem)]
+
+
+def name_keys(s):
+    """atom names packed into an int32 each (fpk_structure.atom_name_key), as a C char[4] would be"""
+    out = np.zeros(s.n, np.int32)
+    for i, nm in enumerate(atom_names(s)):
+        out[i] = int.from_bytes(nm.encode()[:4].ljust(4, b"\0"), "little", signed=True)
+    return out
+
+
+def make_ligand(rng, centre, natoms=28, step=1.5, reach=4.5):
+    """a blob of carbon atoms around `centre`: a random walk of bonded steps kept within `reach` of it (3-decimal coordinates)"""
+    pts = [np.asarray(centre, np.float64)]
+    while len(pts) < natoms:
+        d = rng.normal(size=3)
+        q = pts[rng.integers(len(pts))] + step * d / np.linalg.norm(d)
+        if np.linalg.norm(q - pts[0]) <= reach and min(np.linalg.norm(q - p) for p in pts) > 1.2:
+            pts.append(q)
+    return np.round(np.array(pts), 3).astype(np.float32)
+
+
+def with_ligand(s, lig_xyz):
+    """Structure of the complex as dpocket loads it (dpocket.c:186-203): pdb = protein, pdb_w_lig = protein + HETATM LIG."""
+    st = to_structure(s, same_pdb=0)
+    nl = len(lig_xyz)
+    one = np.ones(nl, np.float32)
+    st.wx, st.wy, st.wz = (np.ascontiguousarray(np.concatenate([a, lig_xyz[:, k]])) for k, a in enumerate((st.x, st.y, st.z)))
+    st.wradius = np.ascontiguousarray(np.concatenate([st.radius, RVDW[0] * one]))
+    st.welectroneg = np.ascontiguousarray(np.concatenate([st.electroneg, ENEG[0] * one]))
+    st.wflags = np.zeros(st.natoms + nl, np.uint8)
+    st.natoms_w = st.natoms + nl
+    st.set_ligand(np.arange(st.natoms, st.natoms + nl), np.zeros(nl, np.int32), name_keys(s))
+    return st
+
+
+def to_pdb(s, path, lig_xyz=None):
     names = ["N", "CA", "C", "O"]
     with open(path, "w") as f:
         for i in range(s.n):
@@ -78,4 +116,8 @@ def to_pdb(s, path):
             f.write("ATOM  %5d %-4s %3s A%4d    %8.3f%8.3f%8.3f%6.2f%6.2f          %2s\n" %
                     ((i + 1) % 100000, (" " + nm) if len(nm) < 4 else nm, AA[int(s.aa[i])], int(s.res[i]) % 10000,
                      s.xyz[i, 0], s.xyz[i, 1], s.xyz[i, 2], 1.0, s.bf[i], el))
+        if lig_xyz is not None:
+            for j, q in enumerate(lig_xyz):
+                f.write("HETATM%5d %-4s LIG A9001    %8.3f%8.3f%8.3f%6.2f%6.2f          %2s\n" %
+                        ((s.n + j + 1) % 100000, " C%d" % (j + 1) if j < 99 else "C%d" % (j + 1), q[0], q[1], q[2], 1.0, 20.0, "C"))
         f.write("END\n")

@@ -303,3 +303,26 @@ def test_delaunay_on_degenerate_and_random_point_sets():
         assert rc == 0
         assert r["n_tets"] == len(tets), (st.natoms, r["status"], r["n_tets"], len(tets))
         assert np.array_equal(r["tets"], tets), st.natoms
+
+
+def test_dpocket_synthetic_complexes_equal_oracle():
+    """BASELINE configs[4] shape: ligand-bound synthetic structures (and ligand-free ones in the same batch). Ligand queries, the explicit
+    pocket's record and everything else equal the oracle bit for bit; a ligand far from the protein gives an empty explicit pocket."""
+    import synth
+    api = _api()
+    rng = np.random.default_rng(5)
+    sts = []
+    for i, n in enumerate((2100, 3300, 2600)):
+        s = synth.generate(20269600 + i, n, 0.065)
+        first = api.detect(synth.to_structure(s), api.default_params())
+        c = first["desc"]["bary"][first["rank_to_cluster"][0]] if i < 2 else s.xyz.max(0) + 60.0        # third ligand: nowhere near
+        sts.append(synth.with_ligand(s, synth.make_ligand(rng, c)))
+    sts.insert(1, _synth(20269650, 2400))                                   # no ligand
+    p = api.default_params()
+    got = api.detect_batch(sts, p)
+    for k, (st, r) in enumerate(zip(sts, got)):
+        o = O.search_pocket(st, p, tets=None, rng_mode=O.RNG_PHILOX)
+        assert_same_result(r, o, "dpocket %d" % k)
+    assert "xspheres" not in got[1]
+    assert len(got[0]["xspheres"]) > 10 and got[0]["pk_ovlp"].max() > 30 and got[0]["pk_c4"].max() > 0.5
+    assert len(got[3]["xspheres"]) == 0 and got[3]["xdesc"] is None and np.all(got[3]["pk_c5"] == 0)
