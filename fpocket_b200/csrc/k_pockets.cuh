@@ -236,7 +236,7 @@ struct DescScratch {          // per resident block of K4
     int *sa;                  // [natoms_w max] surrounding atoms of the current pocket (asa.c:84-112), three ordered segments
 };
 
-enum { K4_THREADS = 128, K4_WORKERS = 96, MC_SMEM_SPH = 1024, MC_CELLS = 512, MC_ENTRIES = 8192, ASA_CAND = 128 };
+enum { K4_THREADS = 128, K4_WORKERS = 96, MC_SMEM_SPH = 512, MC_CELLS = 512, MC_ENTRIES = 4096, ASA_CAND = 128 };
 
 // barrier among warps 1..3 only (warp 0 runs the reference-order sequential sums meanwhile)
 __device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
@@ -244,7 +244,7 @@ __device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 96;" 
 // K4: one block per cluster. After the contacted-atom lists are built the block splits:
 //   warp 0     - the reference's sequential float sums (pair loop of descriptors.c:186-236 etc.), in the reference's order;
 //   warps 1..3 - surrounding atoms, the two SASA passes and the Monte-Carlo volume (integer counts: order-free).
-__global__ void __launch_bounds__(K4_THREADS) k_descriptors(BatchDev B, PocketDev Pk, const DescScratch *scratch, int *work_counter)
+__global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, PocketDev Pk, const DescScratch *scratch, int *work_counter)
 {
     __shared__ int s_item, s_U, s_cnt[100], s_sm[40], s_segcnt[3], s_mcdim[4], s_mcmode;
     __shared__ float s_mcbox[6], s_mch[3], s_bb[3][6];
