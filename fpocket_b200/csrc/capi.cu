@@ -335,14 +335,14 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
     // K1 shared-memory plan: WarpCav records + the sites as int32 lattice offsets. Two blocks per SM when the largest
     // structure fits in half an SM's shared memory, else one block, else the sites stay in global memory (pi_cap 0).
     {
-        const size_t fixed = FPK_BD_BYTES + 8 * sizeof(WarpCav), stat = 2048, sm_total = 227 * 1024, per_block_reserved = 1024;
+        const size_t fixed = FPK_BD_BYTES + (FPK_K1_THREADS / 32) * sizeof(WarpCav), stat = 2048, sm_total = 227 * 1024, per_block_reserved = 1024;
         const size_t need = fixed + 12 * (size_t)b->max_sites + 16;
         const size_t half = (sm_total - 2 * per_block_reserved) / 2 - stat, full = sm_total - per_block_reserved - stat;
         if (need <= half) { b->k1_picap = b->max_sites; b->k1_dsm = need; }
         else if (need <= full) { b->k1_picap = b->max_sites; b->k1_dsm = need; }
         else { b->k1_picap = 0; b->k1_dsm = fixed; }
     }
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_delaunay_filter, 256, b->k1_dsm);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_delaunay_filter, FPK_K1_THREADS, b->k1_dsm);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_cluster, 256, 0);
     occ1 = std::max(1, std::min(occ1, 4)); occ3 = std::max(1, std::min(occ3, 4));
     if (const char *e = getenv("FPK_K1_BLOCKS_PER_SM")) occ1 = std::max(1, std::min(occ1, atoi(e)));     // tuning knob (profiles/)
@@ -384,7 +384,7 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
         B.counts = a.take<int>((size_t)n * CNT_STRIDE);
         b->d_counters = a.take<int>(8);
         B.tets_out = b->tot_tetcap ? a.take<int>(4 * b->tot_tetcap) : nullptr;
-        for (int i = 0; i < b->nDel; i++) del_scratch_layout(a, hDel[i], b->max_sites, b->max_sphcap, 256, true);
+        for (int i = 0; i < b->nDel; i++) del_scratch_layout(a, hDel[i], b->max_sites, b->max_sphcap, FPK_K1_THREADS, true);
         for (int i = 0; i < b->nClu; i++) {
             hClu[i].cellcnt = a.take<int>(CELLMAX + 2); hClu[i].cellsph = a.take<int>(b->max_sphcap + 1);
             hClu[i].tmp = a.take<int>(b->max_sphcap + 2); hClu[i].scap = b->max_sphcap;
@@ -494,7 +494,7 @@ static int batch_run(fpk_batch *b)
     CK(cudaMemsetAsync(b->d_counters, 0, sizeof(int) * 8));
     CK(cudaMemsetAsync(B.counts, 0, sizeof(int) * (size_t)n * CNT_STRIDE));
     CK(cudaEventRecord(b->ev[0]));
-    k_delaunay_filter<<<b->nDel, 256, b->k1_dsm>>>(B, b->dDel, b->k1_picap);
+    k_delaunay_filter<<<b->nDel, FPK_K1_THREADS, b->k1_dsm>>>(B, b->dDel, b->k1_picap);
     CK(cudaEventRecord(b->ev[1]));
     k_cluster<<<b->nClu, 256>>>(B, b->dClu, b->d_counters + 1);
     const bool lig = b->tot_lig > 0 && b->prm.skip_clustering == 0;

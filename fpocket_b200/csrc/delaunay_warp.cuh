@@ -29,7 +29,10 @@ struct WarpCav {                        // one per warp, shared memory
 
 // Shared-memory state of one block's triangulation. Dynamic shared memory = [BlockDel][WarpCav x warps][sites]; every function
 // reaches it through the accessors below so that the compiler sees SHARED addresses (LDS/STS/ATOMS), not generic ones.
-enum { FPK_MAXWARPS = 8 };
+#ifndef FPK_MAXWARPS_N
+#define FPK_MAXWARPS_N 8
+#endif
+enum { FPK_MAXWARPS = FPK_MAXWARPS_N };
 struct BlockDel {
     DelaunayCtx C;
     int cnt[C_COUNT];

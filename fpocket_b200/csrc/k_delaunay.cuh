@@ -263,11 +263,14 @@ __device__ int block_delaunay(int pi_cap, const DelScratch &X, int n, const doub
 #ifndef FPK_K1_MINBLOCKS
 #define FPK_K1_MINBLOCKS 2
 #endif
-__global__ void __launch_bounds__(256, FPK_K1_MINBLOCKS) k_delaunay_filter(BatchDev B, const DelScratch *scratch, int pi_cap)
+#ifndef FPK_K1_THREADS
+#define FPK_K1_THREADS 256
+#endif
+__global__ void __launch_bounds__(FPK_K1_THREADS, FPK_K1_MINBLOCKS) k_delaunay_filter(BatchDev B, const DelScratch *scratch, int pi_cap)
 {
     __shared__ int s_k, s_red[40];
     __shared__ double s_box[6];
-    __shared__ double s_bmin[8][3], s_bmax[8][3];
+    __shared__ double s_bmin[FPK_MAXWARPS][3], s_bmax[FPK_MAXWARPS][3];
     BlockDel &BD = blk();
     DelaunayCtx &C = BD.C;
     const int tid = threadIdx.x, nt = blockDim.x;
