@@ -336,7 +336,7 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
     // structure fits in half an SM's shared memory, else one block, else the sites stay in global memory (pi_cap 0).
     {
         const size_t fixed = FPK_BD_BYTES + (FPK_K1_THREADS / 32) * sizeof(WarpCav), stat = 2048, sm_total = 227 * 1024, per_block_reserved = 1024;
-        const size_t need = fixed + 12 * (size_t)b->max_sites + 16;
+        const size_t need = fixed + 12 * (size_t)b->max_sites + 128;          // + slack for the 16-byte aligned TMA window
         const size_t half = (sm_total - 2 * per_block_reserved) / 2 - stat, full = sm_total - per_block_reserved - stat;
         if (need <= half) { b->k1_picap = b->max_sites; b->k1_dsm = need; }
         else if (need <= full) { b->k1_picap = b->max_sites; b->k1_dsm = need; }

@@ -260,6 +260,36 @@ __device__ int block_delaunay(int pi_cap, const DelScratch &X, int n, const doub
     return S.cnt[C_STATUS];
 }
 
+// ---- TMA (bulk async copy) staging of a structure's coordinate tile into shared memory ------------------------------------------------
+// The x / y / z arrays of one structure are contiguous in the batch arena; when every atom is a site (no hydrogens) the tile is brought
+// into the shared site buffer by three cp.async.bulk copies completing on an mbarrier (SASS: UBLKCP), instead of per-thread gathers.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(__cvta_generic_to_global(src_gmem)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// bounded wait (never spins forever: a failed copy is reported, not hung on)
+__device__ __forceinline__ bool mbar_wait(unsigned long long *bar, unsigned phase)
+{
+    const unsigned a = smem_u32(bar);
+    for (int it = 0; it < (1 << 22); it++) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(phase) : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+
 #ifndef FPK_K1_MINBLOCKS
 #define FPK_K1_MINBLOCKS 2
 #endif
@@ -271,10 +301,14 @@ __global__ void __launch_bounds__(FPK_K1_THREADS, FPK_K1_MINBLOCKS) k_delaunay_f
     __shared__ int s_k, s_red[40];
     __shared__ double s_box[6];
     __shared__ double s_bmin[FPK_MAXWARPS][3], s_bmax[FPK_MAXWARPS][3];
+    __shared__ __align__(8) unsigned long long s_mbar;
     BlockDel &BD = blk();
     DelaunayCtx &C = BD.C;
     const int tid = threadIdx.x, nt = blockDim.x;
     const DelScratch &X = scratch[blockIdx.x];
+    unsigned tma_phase = 0;
+    if (tid == 0) mbar_init(&s_mbar, 1);
+    __syncthreads();
 
     for (;;) {
         __syncthreads();
@@ -290,13 +324,35 @@ __global__ void __launch_bounds__(FPK_K1_THREADS, FPK_K1_MINBLOCKS) k_delaunay_f
             continue;
         }
         // ---- 1. lattice coordinates: what "%.6f" prints (voronoi.c:130), exact in double -----------------------
-        for (int i = tid; i < n; i += nt) {
-            int a = S.atom_off + B.site2atom[S.site_off + i];
-            X.P[3 * (size_t)i] = (double)__double2ll_rn(__dmul_rn((double)B.ax[a], 1e6));
-            X.P[3 * (size_t)i + 1] = (double)__double2ll_rn(__dmul_rn((double)B.ay[a], 1e6));
-            X.P[3 * (size_t)i + 2] = (double)__double2ll_rn(__dmul_rn((double)B.az[a], 1e6));
+        const int lead = S.atom_off & 3, tile = (n + lead + 3) & ~3;             // 16-byte aligned window around the structure's atoms
+        bool staged = false;
+        if (n == S.natoms && 3 * tile <= 3 * pi_cap + 24) {                     // every atom is a site: the tile is contiguous
+            float *stg = reinterpret_cast<float *>(sm_sites());
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // earlier generic-proxy accesses to the buffer come first
+                mbar_expect_tx(&s_mbar, 3u * (unsigned)tile * 4u);
+                tma_load_1d(stg, B.ax + S.atom_off - lead, (unsigned)tile * 4u, &s_mbar);
+                tma_load_1d(stg + tile, B.ay + S.atom_off - lead, (unsigned)tile * 4u, &s_mbar);
+                tma_load_1d(stg + 2 * tile, B.az + S.atom_off - lead, (unsigned)tile * 4u, &s_mbar);
+            }
+            staged = mbar_wait(&s_mbar, tma_phase);
+            tma_phase ^= 1u;
+            if (staged)
+                for (int i = tid; i < n; i += nt) {
+                    X.P[3 * (size_t)i] = (double)__double2ll_rn(__dmul_rn((double)stg[lead + i], 1e6));
+                    X.P[3 * (size_t)i + 1] = (double)__double2ll_rn(__dmul_rn((double)stg[tile + lead + i], 1e6));
+                    X.P[3 * (size_t)i + 2] = (double)__double2ll_rn(__dmul_rn((double)stg[2 * tile + lead + i], 1e6));
+                }
         }
-        __syncthreads();
+        if (!__syncthreads_and(staged ? 1 : 0)) {                                // hydrogens present (sites are a subset) or a tile too large
+            for (int i = tid; i < n; i += nt) {
+                int a = S.atom_off + B.site2atom[S.site_off + i];
+                X.P[3 * (size_t)i] = (double)__double2ll_rn(__dmul_rn((double)B.ax[a], 1e6));
+                X.P[3 * (size_t)i + 1] = (double)__double2ll_rn(__dmul_rn((double)B.ay[a], 1e6));
+                X.P[3 * (size_t)i + 2] = (double)__double2ll_rn(__dmul_rn((double)B.az[a], 1e6));
+            }
+            __syncthreads();
+        }
         block_bbox(X.P, n, s_box, s_bmin, s_bmax);
         // ---- 2.+3. insertion order, rounds of concurrent insertions --------------------------------------------------
         const int err = block_delaunay(pi_cap, X, n, s_box);
