@@ -326,3 +326,22 @@ def test_dpocket_synthetic_complexes_equal_oracle():
     assert "xspheres" not in got[1]
     assert len(got[0]["xspheres"]) > 10 and got[0]["pk_ovlp"].max() > 30 and got[0]["pk_c4"].max() > 0.5
     assert len(got[3]["xspheres"]) == 0 and got[3]["xdesc"] is None and np.all(got[3]["pk_c5"] == 0)
+
+
+def test_hydrogens_are_not_sites():
+    """Atoms flagged as hydrogens are not Delaunay sites (voronoi.c:100,128) nor surrounding atoms (asa.c:89): the site gather path
+    (no contiguous TMA tile) against the oracle, in a batch with a hydrogen-free structure (TMA path)."""
+    from fpocket_b200 import capi
+    api = _api()
+    a, b = _synth(20269700, 2300), _synth(20269701, 2500)
+    rng = np.random.default_rng(9)
+    h = rng.random(a.natoms) < 0.15
+    a.flags = np.where(h, capi.FPK_ATOM_H | capi.FPK_ATOM_H1, 0).astype(np.uint8)
+    p = api.default_params()
+    p.want_tets = 1
+    got = api.detect_batch([a, b, a], p)
+    for st, r in zip([a, b, a], got):
+        o = O.search_pocket(st, p, tets=None, rng_mode=O.RNG_PHILOX)
+        assert r["n_sites"] == o["n_sites"] == int(np.count_nonzero((st.flags & capi.FPK_ATOM_H) == 0))
+        assert_same_result(r, o, "hydrogens")
+    assert got[0]["n_sites"] < a.natoms and got[1]["n_sites"] == b.natoms
