@@ -838,8 +838,8 @@ struct fpk_md {
     float *d_geom = nullptr;
     int nwords = 0, nblocks = 0;
     long long frames = 0, launches = 0;
-    std::vector<float> stage;
-    ~fpk_md() { delete b; cudaFree(d_dens); cudaFree(d_freq); cudaFree(d_mask); cudaFree(d_nscat); cudaFree(d_geom); }
+    float *pin[2] = {nullptr, nullptr}, *d_xyz[2] = {nullptr, nullptr}; size_t stage_cap = 0;     // double-buffered frame staging
+    ~fpk_md() { for (int q = 0; q < 2; q++) { if (pin[q]) cudaFreeHost(pin[q]); if (d_xyz[q]) cudaFree(d_xyz[q]); } delete b; cudaFree(d_dens); cudaFree(d_freq); cudaFree(d_mask); cudaFree(d_nscat); cudaFree(d_geom); }
 };
 
 static int md_prepare(fpk_md *m, int nframes)
@@ -874,18 +874,37 @@ static int md_prepare(fpk_md *m, int nframes)
     return FPK_OK;
 }
 
-static int md_upload_coords(fpk_md *m, const float *xyz, int nframes)
+// xyz is [frame][atom][3] (the molfile timestep layout, mdpocket.c:238-243): split into the SoA the kernels read, on the device
+__global__ void k_md_deinterleave(const float *xyz, size_t tot, float *ax, float *ay, float *az)
 {
-    // xyz is [frame][atom][3] (the molfile timestep layout, mdpocket.c:238-243): de-interleave into the SoA the kernels read
-    fpk_batch *b = m->b;
-    const size_t na = (size_t)m->topo.natoms, tot = na * nframes;
-    m->stage.resize(3 * tot);
-    float *hx = m->stage.data(), *hy = hx + tot, *hz = hy + tot;
-    for (size_t i = 0; i < tot; i++) { hx[i] = xyz[3 * i]; hy[i] = xyz[3 * i + 1]; hz[i] = xyz[3 * i + 2]; }
-    CK(cudaMemcpy(const_cast<float *>(b->B.ax), hx, sizeof(float) * tot, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(const_cast<float *>(b->B.ay), hy, sizeof(float) * tot, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(const_cast<float *>(b->B.az), hz, sizeof(float) * tot, cudaMemcpyHostToDevice));
-    b->h2d += (long long)(sizeof(float) * 3 * tot);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
+        ax[i] = xyz[3 * i]; ay[i] = xyz[3 * i + 1]; az[i] = xyz[3 * i + 2];
+    }
+}
+
+// host -> pinned bounce buffer -> device staging buffer `slot`, on the calling thread's stream (returns after the copy has landed)
+static int md_stage_chunk(fpk_md *m, int slot, const float *xyz, int nframes)
+{
+    const size_t bytes = sizeof(float) * 3 * (size_t)m->topo.natoms * nframes;
+    if (bytes > m->stage_cap) return fail(FPK_ERR_BAD_ARG, "md staging buffer too small");
+    memcpy(m->pin[slot], xyz, bytes);
+    CK(cudaMemcpyAsync(m->d_xyz[slot], m->pin[slot], bytes, cudaMemcpyHostToDevice, cudaStreamPerThread));
+    CK(cudaStreamSynchronize(cudaStreamPerThread));
+    return FPK_OK;
+}
+
+static int md_ensure_staging(fpk_md *m, int chunk_frames)
+{
+    const size_t need = sizeof(float) * 3 * (size_t)m->topo.natoms * chunk_frames;
+    if (need <= m->stage_cap) return FPK_OK;
+    for (int q = 0; q < 2; q++) {
+        if (m->pin[q]) cudaFreeHost(m->pin[q]);
+        if (m->d_xyz[q]) cudaFree(m->d_xyz[q]);
+        m->pin[q] = nullptr; m->d_xyz[q] = nullptr;
+        CK(cudaHostAlloc((void **)&m->pin[q], need, cudaHostAllocDefault));
+        CK(cudaMalloc((void **)&m->d_xyz[q], need));
+    }
+    m->stage_cap = need;
     return FPK_OK;
 }
 
@@ -932,7 +951,12 @@ extern "C" int fpk_md_grid_from_frame(fpk_md *m, const float *xyz, float origin[
 {
     if (!m || !xyz) return fail(FPK_ERR_BAD_ARG, "fpk_md_grid_from_frame: bad arguments");
     int rc = md_prepare(m, 1);
-    if (!rc) rc = md_upload_coords(m, xyz, 1);
+    if (!rc) rc = md_ensure_staging(m, 1);
+    if (!rc) rc = md_stage_chunk(m, 0, xyz, 1);
+    if (!rc) {
+        const size_t tot = (size_t)m->topo.natoms;
+        k_md_deinterleave<<<64, 256>>>(m->d_xyz[0], tot, const_cast<float *>(m->b->B.ax), const_cast<float *>(m->b->B.ay), const_cast<float *>(m->b->B.az));
+    }
     if (!rc) rc = batch_run(m->b);
     if (rc) return rc;
     m->launches += m->b->launches;
@@ -950,22 +974,58 @@ extern "C" int fpk_md_push_frames(fpk_md *m, const float *xyz, int nframes)
     if (!m || !xyz || nframes <= 0) return fail(FPK_ERR_BAD_ARG, "fpk_md_push_frames: bad arguments");
     if (!m->have_grid) return fail(FPK_ERR_BAD_ARG, "fpk_md_push_frames: set the grid first (fpk_md_set_grid)");
     const size_t na = (size_t)m->topo.natoms;
-    const int chunk_max = 1024;
-    for (int f0 = 0; f0 < nframes; f0 += chunk_max) {
-        const int nf = std::min(chunk_max, nframes - f0);
-        int rc = md_prepare(m, nf);
-        if (!rc) rc = md_upload_coords(m, xyz + 3 * na * (size_t)f0, nf);
-        if (!rc) rc = batch_run(m->b);
+    const int chunk_max = std::max(256, g_sms * 2 * 8);         // a whole number of structures per resident K1 block (2 per SM)
+    int rc = md_ensure_staging(m, std::min(chunk_max, nframes));
+    typedef std::chrono::steady_clock clk;
+    double t_run = 0, t_scatter = 0, t_prep = 0;
+    if (rc) return rc;
+    // chunk k+1 is staged (host copy into pinned memory + H2D) by a helper thread on its own stream while chunk k is detected
+    const int nchunks = (nframes + chunk_max - 1) / chunk_max;
+    rc = md_stage_chunk(m, 0, xyz, std::min(chunk_max, nframes));
+    if (rc) return rc;
+    for (int c = 0; c < nchunks; c++) {
+        const int f0 = c * chunk_max, nf = std::min(chunk_max, nframes - f0);
+        std::thread pre;
+        int pre_rc = FPK_OK;
+        std::string pre_err;
+        if (c + 1 < nchunks) {
+            const int f1 = f0 + chunk_max, nf1 = std::min(chunk_max, nframes - f1);
+            pre = std::thread([&, f1, nf1, c]() {
+                cudaSetDevice(g_dev);
+                pre_rc = md_stage_chunk(m, (c + 1) & 1, xyz + 3 * na * (size_t)f1, nf1);
+                if (pre_rc) pre_err = g_err;
+            });
+        }
+        auto t0 = clk::now();
+        rc = md_prepare(m, nf);
+        auto t1 = clk::now();
+        t_prep += std::chrono::duration<double, std::milli>(t1 - t0).count();
+        if (!rc) {
+            const size_t tot = na * (size_t)nf;
+            k_md_deinterleave<<<g_sms * 4, 256>>>(m->d_xyz[c & 1], tot, const_cast<float *>(m->b->B.ax), const_cast<float *>(m->b->B.ay), const_cast<float *>(m->b->B.az));
+            m->b->h2d += (long long)(sizeof(float) * 3 * tot);
+            rc = batch_run(m->b);
+            t_run += std::chrono::duration<double, std::milli>(clk::now() - t1).count();
+        }
+        if (!rc) {
+            auto t2 = clk::now();
+            MdGrid G;
+            for (int q = 0; q < 3; q++) G.origin[q] = m->origin[q];
+            G.nx = m->dims[0]; G.ny = m->dims[1]; G.nz = m->dims[2];
+            G.dens = m->d_dens; G.freq = m->d_freq; G.mask = m->d_mask; G.nwords = m->nwords; G.use_drug_score = m->use_drug;
+            k_md_scatter<<<std::min(m->nblocks, nf), 256>>>(m->b->B, m->b->Pk, G, m->d_nscat);
+            cudaError_t e = cudaStreamSynchronize(cudaStreamPerThread);
+            if (e != cudaSuccess) rc = fail(FPK_ERR_CUDA, "k_md_scatter: %s", cudaGetErrorString(e));
+            m->launches += m->b->launches + 2;
+            m->frames += nf;
+            t_scatter += std::chrono::duration<double, std::milli>(clk::now() - t2).count();
+        }
+        if (pre.joinable()) pre.join();
         if (rc) return rc;
-        MdGrid G;
-        for (int q = 0; q < 3; q++) G.origin[q] = m->origin[q];
-        G.nx = m->dims[0]; G.ny = m->dims[1]; G.nz = m->dims[2];
-        G.dens = m->d_dens; G.freq = m->d_freq; G.mask = m->d_mask; G.nwords = m->nwords; G.use_drug_score = m->use_drug;
-        k_md_scatter<<<std::min(m->nblocks, nf), 256>>>(m->b->B, m->b->Pk, G, m->d_nscat);
-        CK(cudaDeviceSynchronize());
-        m->launches += m->b->launches + 1;
-        m->frames += nf;
+        if (pre_rc) { g_err = pre_err; return pre_rc; }
     }
+    CK(cudaDeviceSynchronize());
+    if (getenv("FPK_TRACE")) fprintf(stderr, "fpk_md_push_frames: %d frames, %d chunks; host ms: prepare %.1f detect %.1f scatter %.1f\n", nframes, nchunks, t_prep, t_run, t_scatter);
     return FPK_OK;
 }
 
