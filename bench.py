@@ -377,7 +377,7 @@ def main():
         md = api.MdPocket(st5, p)
         org, dims = md.grid_from_frame(s5.xyz[None])             # frame 1 defines the grid (mdpocket.c:151-154); same on every rank
         md.set_grid(org, dims)
-        md.push_frames(xyz[: min(F, 64)])                        # warm-up
+        md.push_frames(xyz)                                      # warm-up with the same chunk shapes (arenas, pinned staging), then reset the grids
         md.set_grid(org, dims)
         barrier()
         tm = time.perf_counter()
