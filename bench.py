@@ -228,8 +228,19 @@ def main():
         return
 
     # ------------------------------------------------------------------ B200 arm ----------------------------------------------------
-    import torch
+    # the synthetic workload first: worker processes are forked before any CUDA / NCCL state exists in this process
     import synth
+    t0 = time.time()
+    if world > 1:       # weak scaling: the global workload is world x structures; ranks take balanced shares without communication
+        from fpocket_b200 import sharding
+        sizes = [size_of(k) for k in range(args.structures * world)]
+        mine = sharding.shard_structures(sizes, rank, world)[: args.structures]
+        if len(mine) < args.structures:
+            mine = list(mine) + [int(mine[-1])] * (args.structures - len(mine))
+        raw = make_batch(args.structures, workers, ids=mine)
+    else:
+        raw = make_batch(args.structures, workers)
+    import torch
     from fpocket_b200 import api
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
@@ -250,17 +261,6 @@ def main():
             os.dup2(saved, 1)
             os.close(saved)
     api.init(local)
-
-    t0 = time.time()
-    if world > 1:       # weak scaling: the global workload is world x structures; ranks take balanced shares without communication
-        from fpocket_b200 import sharding
-        sizes = [size_of(k) for k in range(args.structures * world)]
-        mine = sharding.shard_structures(sizes, rank, world)[: args.structures]
-        if len(mine) < args.structures:
-            mine = list(mine) + [int(mine[-1])] * (args.structures - len(mine))
-        raw = make_batch(args.structures, workers, ids=mine)
-    else:
-        raw = make_batch(args.structures, workers)
     structs = [synth.to_structure(s) for s in raw]
     t_gen = time.time() - t0
     p = api.default_params()
