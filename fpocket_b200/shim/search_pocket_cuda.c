@@ -22,6 +22,36 @@
 
 #include "fpocket.h"            /* the reference's header: s_pdb, s_fparams, c_lst_pockets, allocators */
 #include "fpocket_cuda.h"
+#include "shim.h"
+
+/* The reference's writers shell out for "mkdir [-p] <dir>" and "chmod +x <file>" (fpout.c:83,127, write_visu.c:115,185,266). A fork()
+ * of a process that holds a CUDA context (pinned buffers, GPU mappings) costs ~100 ms, five times per structure, so every program linked with this shim
+ * answers those three commands in-process; anything else still goes to the shell. */
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <errno.h>
+extern int __libc_system(const char *cmd);
+static int mkdir_p(const char *path)
+{
+    char tmp[4096];
+    snprintf(tmp, sizeof tmp, "%s", path);
+    for (char *q = tmp + 1; *q; q++)
+        if (*q == '/') { *q = 0; if (mkdir(tmp, 0777) && errno != EEXIST) return 1; *q = '/'; }
+    return (mkdir(tmp, 0777) && errno != EEXIST) ? 1 : 0;
+}
+int system(const char *cmd)
+{
+    if (!cmd) return 1;
+    if (!strncmp(cmd, "mkdir -p ", 9) && !strpbrk(cmd + 9, " ;&|<>$`\"'*?")) return mkdir_p(cmd + 9) ? 256 : 0;
+    if (!strncmp(cmd, "mkdir ", 6) && !strpbrk(cmd + 6, " ;&|<>$`\"'*?")) return (mkdir(cmd + 6, 0777) && errno != EEXIST) ? 256 : 0;
+    if (!strncmp(cmd, "chmod +x ", 9) && !strpbrk(cmd + 9, " ;&|<>$`\"'*?")) {
+        struct stat st;
+        if (stat(cmd + 9, &st)) return 256;
+        return chmod(cmd + 9, st.st_mode | S_IXUSR | S_IXGRP | S_IXOTH) ? 256 : 0;
+    }
+    return __libc_system(cmd);
+}
+
 
 /* set_aa_desc's decision on the first three letters of the residue name (descriptors.c:453-507), as an index 0..19 in the
  * order of aa.h (ALA ARG ASN ASP CYS GLN GLU GLY HIS ILE LEU LYS MET PHE PRO SER THR TRP TYR VAL), -1 when it updates nothing */
@@ -43,13 +73,6 @@ static int shim_aa_index(const char *n)
     }
     return -1;
 }
-
-typedef struct {
-    float *f;        /* 6 arrays of n floats: x y z radius electroneg bfactor */
-    int32_t *i;      /* 2 arrays of n ints: id res_id */
-    int8_t *aa;
-    uint8_t *fl;
-} shim_atoms;
 
 static int shim_flatten(const s_pdb *pdb, const s_fparams *params, int with_props, shim_atoms *o)
 {
@@ -133,56 +156,68 @@ static void shim_fill_desc(s_desc *d, const fpk_desc *g)
     d->as_max_r = g->as_max_r; d->drug_score = g->drug_score;
 }
 
-c_lst_pockets *search_pocket(s_pdb *pdb, s_fparams *params, s_pdb *pdb_w_lig)
+/* ---- the three steps, exposed so that a batch driver (fpocket_batch.c) can put many structures into ONE fpk_detect_batch call ---- */
+void shim_params(const s_fparams *params, fpk_params *P)
 {
-    if (!pdb || !params) return NULL;
+    fpk_default_params(P);
+    P->asph_min_size = params->asph_min_size; P->asph_max_size = params->asph_max_size; P->clust_max_dist = params->clust_max_dist;
+    P->refine_min_apolar_asphere_prop = params->refine_min_apolar_asphere_prop; P->min_as_density = params->min_as_density;
+    P->min_apol_neigh = params->min_apol_neigh; P->nb_mcv_iter = params->nb_mcv_iter; P->min_pock_nb_asph = params->min_pock_nb_asph;
+    P->do_asa_and_volume = params->flag_do_asa_and_volume_calculations;
+    P->skip_clustering = (params->xlig_resnumber != -1 || params->xpocket_n > 0);      /* fpocket.c:114 */
+    P->xpocket_active = params->xpocket_n > 0;
+    P->min_n_explicit_pocket_atoms = params->min_n_explicit_pocket_atoms;
+    P->mc_seed = (uint64_t)time(NULL);                                                    /* voronoi.c:87 srand(time(NULL)) */
+    if (getenv("FPOCKET_MC_SEED")) P->mc_seed = strtoull(getenv("FPOCKET_MC_SEED"), NULL, 10);
+}
+
+int shim_supported(const s_fparams *params)
+{
     if (params->clustering_method != 's' || params->distance_measure != 'e') {
         fprintf(stderr, "! libfpocket_cuda implements single linkage on euclidean distances only (-C s -e e); got -C %c -e %c\n",
                 params->clustering_method, params->distance_measure);
-        return NULL;
+        return 0;
     }
+    return 1;
+}
+
+/* step 1: flatten (the arrays stay alive inside `job` until shim_job_release) */
+int shim_job_prepare(shim_job *job, s_pdb *pdb, s_fparams *params, s_pdb *pdb_w_lig)
+{
+    memset(job, 0, sizeof *job);
     const int same = (pdb_w_lig == pdb || pdb_w_lig == NULL);
-    shim_atoms A, W;
-    memset(&W, 0, sizeof W);
-    if (shim_flatten(pdb, params, 1, &A) || (!same && shim_flatten(pdb_w_lig, params, 0, &W))) {
+    if (shim_flatten(pdb, params, 1, &job->A) || (!same && shim_flatten(pdb_w_lig, params, 0, &job->W))) {
         fprintf(stderr, "! search_pocket: out of memory\n");
-        return NULL;
+        return -1;
     }
     const int n = pdb->natoms;
-    fpk_structure st;
-    memset(&st, 0, sizeof st);
-    st.natoms = n;
-    st.x = A.f; st.y = A.f + n; st.z = A.f + 2 * n; st.radius = A.f + 3 * n; st.electroneg = A.f + 4 * n; st.bfactor = A.f + 5 * n;
-    st.atom_id = A.i; st.res_id = A.i + n; st.aa_idx = A.aa; st.flags = A.fl;
-    st.avg_bfactor = pdb->avg_bfactor; st.min_bfactor = pdb->min_bfactor; st.max_bfactor = pdb->max_bfactor;
-    st.same_pdb = pdb_w_lig == pdb;                   /* asa.c:315 compares pointers: effective only when both are one object */
+    shim_atoms *A = &job->A, *W = &job->W;
+    fpk_structure *st = &job->st;
+    st->natoms = n;
+    st->x = A->f; st->y = A->f + n; st->z = A->f + 2 * n; st->radius = A->f + 3 * n; st->electroneg = A->f + 4 * n; st->bfactor = A->f + 5 * n;
+    st->atom_id = A->i; st->res_id = A->i + n; st->aa_idx = A->aa; st->flags = A->fl;
+    st->avg_bfactor = pdb->avg_bfactor; st->min_bfactor = pdb->min_bfactor; st->max_bfactor = pdb->max_bfactor;
+    st->same_pdb = pdb_w_lig == pdb;                  /* asa.c:315 compares pointers: effective only when both are one object */
     if (!same) {
         const int nw = pdb_w_lig->natoms;
-        st.natoms_w = nw;
-        st.wx = W.f; st.wy = W.f + nw; st.wz = W.f + 2 * nw; st.wradius = W.f + 3 * nw; st.welectroneg = W.f + 4 * nw; st.wflags = W.fl;
-    } else if (!st.same_pdb) st.same_pdb = 1;
-    float *xl = NULL;
+        st->natoms_w = nw;
+        st->wx = W->f; st->wy = W->f + nw; st->wz = W->f + 2 * nw; st->wradius = W->f + 3 * nw; st->welectroneg = W->f + 4 * nw; st->wflags = W->fl;
+    } else if (!st->same_pdb) st->same_pdb = 1;
     if (pdb->n_xlig_atoms > 0) {
-        xl = (float *)malloc(sizeof(float) * 3 * (size_t)pdb->n_xlig_atoms);
-        for (int k = 0; k < pdb->n_xlig_atoms; k++) { xl[3 * k] = pdb->xlig_x[k]; xl[3 * k + 1] = pdb->xlig_y[k]; xl[3 * k + 2] = pdb->xlig_z[k]; }
-        st.n_xlig = pdb->n_xlig_atoms; st.xlig = xl;
+        job->xl = (float *)malloc(sizeof(float) * 3 * (size_t)pdb->n_xlig_atoms);
+        for (int k = 0; k < pdb->n_xlig_atoms; k++) { job->xl[3 * k] = pdb->xlig_x[k]; job->xl[3 * k + 1] = pdb->xlig_y[k]; job->xl[3 * k + 2] = pdb->xlig_z[k]; }
+        st->n_xlig = pdb->n_xlig_atoms; st->xlig = job->xl;
     }
-    fpk_params P;
-    fpk_default_params(&P);
-    P.asph_min_size = params->asph_min_size; P.asph_max_size = params->asph_max_size; P.clust_max_dist = params->clust_max_dist;
-    P.refine_min_apolar_asphere_prop = params->refine_min_apolar_asphere_prop; P.min_as_density = params->min_as_density;
-    P.min_apol_neigh = params->min_apol_neigh; P.nb_mcv_iter = params->nb_mcv_iter; P.min_pock_nb_asph = params->min_pock_nb_asph;
-    P.do_asa_and_volume = params->flag_do_asa_and_volume_calculations;
-    P.skip_clustering = (params->xlig_resnumber != -1 || params->xpocket_n > 0);      /* fpocket.c:114 */
-    P.xpocket_active = params->xpocket_n > 0;
-    P.min_n_explicit_pocket_atoms = params->min_n_explicit_pocket_atoms;
-    P.mc_seed = (uint64_t)time(NULL);                                                    /* voronoi.c:87 srand(time(NULL)) */
-    if (getenv("FPOCKET_MC_SEED")) P.mc_seed = strtoull(getenv("FPOCKET_MC_SEED"), NULL, 10);
+    return 0;
+}
+void shim_job_release(shim_job *job) { shim_free_atoms(&job->A); shim_free_atoms(&job->W); free(job->xl); memset(job, 0, sizeof *job); }
 
-    fpk_result R;
-    memset(&R, 0, sizeof R);
-    int rc = fpk_detect(&st, &P, &R);
-    shim_free_atoms(&A); shim_free_atoms(&W); free(xl);
+/* step 3: rebuild the reference's lists from a finished result (R is consumed) */
+c_lst_pockets *shim_rebuild(s_pdb *pdb, s_fparams *params, s_pdb *pdb_w_lig, fpk_result *Rp, int rc, int do_asa)
+{
+    fpk_result R = *Rp;
+    const int n = pdb->natoms;
+    memset(Rp, 0, sizeof *Rp);
     if (rc == FPK_ERR_NO_SPHERES) {
         fprintf(stderr, "Error in creating clustering tree, return NULL pointer...breaking up");      /* fpocket.c:137 */
         fpk_result_free(&R);
@@ -193,7 +228,6 @@ c_lst_pockets *search_pocket(s_pdb *pdb, s_fparams *params, s_pdb *pdb_w_lig)
         fpk_result_free(&R);
         return NULL;
     }
-
     /* ---- s_lst_vvertice: ALL kept spheres, also those of dropped pockets (mdpbase.c:403-416, dpocket.c:239 rely on it) ---------- */
     s_lst_vvertice *lv = (s_lst_vvertice *)my_malloc(sizeof(s_lst_vvertice));
     const int ns = R.n_spheres;
@@ -239,7 +273,7 @@ c_lst_pockets *search_pocket(s_pdb *pdb, s_fparams *params, s_pdb *pdb_w_lig)
         shim_chain_info(p, pdb_w_lig ? pdb_w_lig : pdb);                /* pocket.c:617 hands pdb_w_lig to set_descriptors */
     }
     /* ---- per-atom ASA side effects (asa.c:337,392-396), printed by writepocket.c:664-669 ------------------------------------------- */
-    if (P.do_asa_and_volume && R.atom_fx)
+    if (do_asa && R.atom_fx)
         for (int k = 0; k < n; k++) {
             s_atm *a = pdb->latoms + k;
             a->abpa = (int)R.atom_fx[4 * k]; a->a0 = R.atom_fx[4 * k + 1]; a->dA = R.atom_fx[4 * k + 2];
@@ -249,4 +283,19 @@ c_lst_pockets *search_pocket(s_pdb *pdb, s_fparams *params, s_pdb *pdb_w_lig)
     if (params->fpocket_running && params->flag_do_grid_calculations && params->topology_path[0])
         calculate_pocket_energy_grids(pockets, params, pdb);               /* fpocket.c:219: stays the reference's code */
     return pockets;
+}
+
+c_lst_pockets *search_pocket(s_pdb *pdb, s_fparams *params, s_pdb *pdb_w_lig)
+{
+    if (!pdb || !params) return NULL;
+    if (!shim_supported(params)) return NULL;
+    shim_job job;
+    if (shim_job_prepare(&job, pdb, params, pdb_w_lig)) return NULL;
+    fpk_params P;
+    shim_params(params, &P);
+    fpk_result R;
+    memset(&R, 0, sizeof R);
+    int rc = fpk_detect(&job.st, &P, &R);
+    shim_job_release(&job);
+    return shim_rebuild(pdb, params, pdb_w_lig, &R, rc, P.do_asa_and_volume);
 }

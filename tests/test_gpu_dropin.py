@@ -91,3 +91,36 @@ def test_reference_program_with_cuda_search_pocket(tmp_path, n):
             a = _atoms(str(dr / "x_out"), k + 1)
             best = max(len(a & b) / float(len(a | b)) for b in ours)
             assert best >= 0.8, (k, best)
+
+
+def test_batch_driver_writes_what_the_single_file_program_writes(tmp_path):
+    """build/fpocket_cuda_batch (the -F list loop as ONE fpk_detect_batch call; reader and writers are the reference's) must leave the
+    same <name>_out/<name>_info.txt and pocket atom files as build/fpocket_cuda -f <name> run file by file (same Monte-Carlo seed)."""
+    bexe = os.path.join(ROOT, "build", "fpocket_cuda_batch")
+    if not (os.path.exists(EXE) and os.path.exists(bexe)):
+        pytest.skip("build/fpocket_cuda_batch not built (needs the reference tree: make -C fpocket_b200/shim)")
+    import synth
+    env = dict(os.environ, FPOCKET_MC_SEED=str(SEED), TMPDIR=str(tmp_path))
+    da, db = tmp_path / "single", tmp_path / "batch"
+    names = []
+    for d in (da, db):
+        d.mkdir()
+    for i, n in enumerate((2050, 3100, 2500)):
+        s = synth.generate(20269800 + i, n, 0.065)
+        names.append("s%d" % i)
+        for d in (da, db):
+            synth.to_pdb(s, str(d / (names[-1] + ".pdb")))
+    for nm in names:
+        subprocess.check_call([EXE, "-f", nm + ".pdb"], cwd=str(da), env=env, stdout=subprocess.DEVNULL)
+    (db / "list.txt").write_text("".join(nm + ".pdb\n" for nm in names))
+    out = subprocess.check_output([bexe, "list.txt"], cwd=str(db), env=env).decode()
+    assert "3 structures" in out and "0 failed" in out
+    for nm in names:
+        a = (da / (nm + "_out") / (nm + "_info.txt")).read_text()
+        b = (db / (nm + "_out") / (nm + "_info.txt")).read_text()
+        assert a == b and a.count("Pocket") >= 5
+        k = a.count("Pocket ")
+        for q in (1, k):
+            fa = (da / (nm + "_out") / "pockets" / ("pocket%d_atm.pdb" % q)).read_text()
+            fb = (db / (nm + "_out") / "pockets" / ("pocket%d_atm.pdb" % q)).read_text()
+            assert fa == fb
