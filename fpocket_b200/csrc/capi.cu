@@ -341,6 +341,7 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
         if (need <= half) { b->k1_picap = b->max_sites; b->k1_dsm = need; }
         else if (need <= full) { b->k1_picap = b->max_sites; b->k1_dsm = need; }
         else { b->k1_picap = 0; b->k1_dsm = fixed; }
+        if (getenv("FPK_K1_SITES_GLOBAL")) { b->k1_picap = 0; b->k1_dsm = fixed; }     // tuning knob (profiles/): sites read through L1 instead of shared memory
     }
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_delaunay_filter, FPK_K1_THREADS, b->k1_dsm);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_cluster, 256, 0);
