@@ -124,3 +124,63 @@ def test_batch_driver_writes_what_the_single_file_program_writes(tmp_path):
             fa = (da / (nm + "_out") / "pockets" / ("pocket%d_atm.pdb" % q)).read_text()
             fb = (db / (nm + "_out") / "pockets" / ("pocket%d_atm.pdb" % q)).read_text()
             assert fa == fb
+
+
+def _read_dx(path):
+    vals, dims, org = [], None, None
+    for line in open(path):
+        if line.startswith("object 1"):
+            dims = [int(v) for v in line.split()[-3:]]
+        elif line.startswith("origin"):
+            org = [float(v) for v in line.split()[1:4]]
+        elif line and (line[0].isdigit() or line[0] == "-") :
+            vals += [float(v) for v in line.split()]
+    return np.array(vals, np.float32).reshape(dims), np.array(org, np.float32)
+
+
+def test_mdpocket_program_on_the_library(tmp_path):
+    """build/mdpocket_cuda = the reference's mdpocket program with mdpocket_detect() replaced by the fpk_md_* driver
+    (fpocket_b200/shim/mdpocket_cuda.c); reading of the snapshots, normalize_grid, project_grid_on_atoms and the DX / PDB writers are
+    the reference's. Its DX grids must be the library's grids (fpk_md API called directly), and close to the unmodified reference's
+    (which loses the spheres of its unflushed qhull tail, DESIGN.md par. 3)."""
+    exe = os.path.join(ROOT, "build", "mdpocket_cuda")
+    ref = os.path.join(ROOT, "oracle", "_ref", "mdpocket")
+    if not os.path.exists(exe):
+        pytest.skip("build/mdpocket_cuda not built (needs the reference tree: make -C fpocket_b200/shim)")
+    import copy
+    import synth
+    from fpocket_b200 import api
+    s = synth.generate(20269900, 2400, 0.065)
+    rng = np.random.default_rng(2)
+    frames = [s.xyz] + [np.round(s.xyz + rng.normal(scale=0.2, size=s.xyz.shape).astype(np.float32), 3) for _ in range(5)]
+    dg, dr = tmp_path / "gpu", tmp_path / "ref"
+    for d in (dg, dr):
+        d.mkdir()
+        with open(d / "list.txt", "w") as f:
+            for i, x in enumerate(frames):
+                sf = copy.copy(s)
+                sf.xyz = x
+                synth.to_pdb(sf, str(d / ("f%02d.pdb" % i)))
+                f.write(str(d / ("f%02d.pdb" % i)) + "\n")
+    subprocess.check_call([exe, "--pdb_list", "list.txt"], cwd=str(dg), stdout=subprocess.DEVNULL)
+    dens, org = _read_dx(str(dg / "mdpout_dens_grid.dx"))
+    freq, _ = _read_dx(str(dg / "mdpout_freq_grid.dx"))
+    # ---- the same through the C ABI ----------------------------------------------------------------------------------------
+    st = synth.to_structure(s)
+    m = api.MdPocket(st, api.default_params())
+    xyz = np.stack(frames).astype(np.float32)
+    o, dims = m.grid_from_frame(xyz[:1])
+    m.set_grid(o, dims)
+    m.push_frames(xyz)
+    gd, gf = m.fetch_grids()
+    m.close()
+    assert list(dens.shape) == [int(v) for v in dims] and np.allclose(org, np.round(o, 2), atol=0.0051)
+    assert np.allclose(dens, gd / len(frames), atol=5.1e-4) and np.allclose(freq, gf / len(frames), atol=5.1e-4)
+    assert (dg / "mdpout_all_atom_pdensities.pdb").stat().st_size > 1000
+    # ---- against the unmodified reference ---------------------------------------------------------------------------------------
+    if os.path.exists(ref):
+        subprocess.check_call([ref, "--pdb_list", "list.txt"], cwd=str(dr), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        rd, ro = _read_dx(str(dr / "mdpout_dens_grid.dx"))
+        if rd.shape == dens.shape and np.allclose(ro, org, atol=0.011):
+            cc = np.corrcoef(rd.ravel(), dens.ravel())[0, 1]
+            assert cc > 0.97, cc
