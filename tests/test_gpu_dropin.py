@@ -184,3 +184,47 @@ def test_mdpocket_program_on_the_library(tmp_path):
         if rd.shape == dens.shape and np.allclose(ro, org, atol=0.011):
             cc = np.corrcoef(rd.ravel(), dens.ravel())[0, 1]
             assert cc > 0.97, cc
+
+
+def test_dpocket_program_on_the_library(tmp_path):
+    """build/dpocket_cuda = the reference's dpocket program with desc_pocket() replaced (fpocket_b200/shim/dpocket_cuda.c): loading,
+    write_out_fpocket and the three dpout_*.txt writers are the reference's; pockets, the explicit pocket's record, interface atoms
+    and the per-pocket criteria come from ONE fpk_detect call with the ligand attached. The rows it prints must be the C-ABI result,
+    and agree with the unmodified reference dpocket on what does not depend on the reference's order-dependent explicit-pocket
+    subset: the pocket that holds the ligand and its overlap criteria."""
+    exe = os.path.join(ROOT, "build", "dpocket_cuda")
+    ref = os.path.join(ROOT, "oracle", "_ref", "dpocket")
+    if not os.path.exists(exe):
+        pytest.skip("build/dpocket_cuda not built (needs the reference tree: make -C fpocket_b200/shim)")
+    import synth
+    from fpocket_b200 import api
+    s = synth.generate(20269950, 2700, 0.065)
+    first = api.detect(synth.to_structure(s), api.default_params())
+    lig = synth.make_ligand(np.random.default_rng(4), first["desc"]["bary"][first["rank_to_cluster"][0]])
+    rows = {}
+    for d, prog in ((tmp_path / "gpu", exe), (tmp_path / "ref", ref)):
+        if not os.path.exists(prog):
+            continue
+        d.mkdir()
+        synth.to_pdb(s, str(d / "c.pdb"), lig)
+        (d / "list.txt").write_text("%s LIG\n" % (d / "c.pdb"))
+        env = dict(os.environ, FPOCKET_MC_SEED=str(SEED), TMPDIR=str(tmp_path))
+        subprocess.check_call([prog, "-f", "list.txt"], cwd=str(d), env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        rows[prog] = {k: [l.split() for l in open(d / ("dpout_%s.txt" % k)).read().splitlines()[1:]] for k in ("explicitp", "fpocketp", "fpocketnp")}
+    g = rows[exe]
+    assert len(g["explicitp"]) == 1 and len(g["fpocketp"]) >= 1
+    # ---- the rows are the C-ABI result -------------------------------------------------------------------------------------------
+    st = synth.with_ligand(s, lig)
+    p = api.default_params()
+    p.mc_seed = SEED
+    r = api.detect(st, p)
+    assert len(g["fpocketp"]) + len(g["fpocketnp"]) == r["n_pockets"]
+    e = g["explicitp"][0]
+    assert int(e[11]) == len(r["xspheres"]) and abs(float(e[10]) - float(r["xdesc"]["volume"][0])) <= 0.0051      # nb_AS, pock_vol
+    best = int(np.argmax(r["pk_ovlp"]))
+    top = g["fpocketp"][0]
+    assert abs(float(top[2]) - float(r["pk_ovlp"][best])) <= 0.0051 and abs(float(top[4]) - float(r["pk_dst"][best])) <= 0.0051
+    # ---- the unmodified reference finds the same ligand pocket -----------------------------------------------------------------------
+    if ref in rows:
+        rt = rows[ref]["fpocketp"][0]
+        assert abs(float(rt[2]) - float(top[2])) <= 15.0 and abs(float(rt[4]) - float(top[4])) <= 1.0 and rt[5] == top[5]
