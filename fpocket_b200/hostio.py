@@ -1,0 +1,182 @@
+"""ctypes binding of libfpocket_hostio (include/fpocket_hostio.h): the native PDB reader, the writers of the reference's
+output directory and the -F pipeline. The library has no CUDA dependency; the detection call is handed in
+(`capi.load_library().fpk_detect_batch` in the product)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import capi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfpocket_hostio.so")
+
+FPKIO_OK, FPKIO_ERR_OPEN, FPKIO_ERR_NO_ATOMS, FPKIO_ERR_UNSUPPORTED, FPKIO_ERR_WRITE, FPKIO_ERR_BAD_ARG = 0, -1, -2, -3, -4, -5
+
+
+class ReadOpts(C.Structure):
+    _fields_ = [("n_chains", C.c_int32), ("chains", (C.c_char * 21) * 20), ("chains_are_kept", C.c_int32)]
+
+    @classmethod
+    def make(cls, drop=None, keep=None):
+        o = cls()
+        names = keep if keep is not None else (drop or [])
+        o.n_chains = len(names)
+        o.chains_are_kept = 1 if keep is not None else 0
+        for i, nm in enumerate(names):
+            o.chains[i].value = nm.encode()
+        return o
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_files", C.c_int32), ("n_written", C.c_int32), ("n_read_failed", C.c_int32), ("n_no_pockets", C.c_int32),
+                ("n_detect_failed", C.c_int32), ("n_pockets", C.c_longlong), ("n_atoms", C.c_longlong), ("bytes_in", C.c_longlong),
+                ("bytes_out", C.c_longlong), ("wall_s", C.c_double), ("read_cpu_s", C.c_double), ("write_cpu_s", C.c_double),
+                ("detect_s", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+DETECT_FN = C.CFUNCTYPE(C.c_int, C.POINTER(capi.FpkStructure), C.c_int, C.POINTER(capi.FpkParams), C.POINTER(capi.FpkResult))
+FREE_FN = C.CFUNCTYPE(None, C.POINTER(capi.FpkResult))
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libfpocket_hostio.so is not built: run python __graft_entry__.py")
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.fpkio_read_pdb.argtypes = [C.c_char_p, C.POINTER(ReadOpts), C.POINTER(vp)]
+        L.fpkio_read_pdb.restype = C.c_int
+        L.fpkio_read_pdb_mem.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(ReadOpts), C.POINTER(vp)]
+        L.fpkio_read_pdb_mem.restype = C.c_int
+        L.fpkio_file_free.argtypes = [vp]
+        L.fpkio_file_free.restype = None
+        L.fpkio_structure.argtypes = [vp]
+        L.fpkio_structure.restype = C.POINTER(capi.FpkStructure)
+        L.fpkio_natoms.argtypes = [vp, C.c_int]
+        L.fpkio_natoms.restype = C.c_int
+        L.fpkio_nhetatm.argtypes = [vp, C.c_int]
+        L.fpkio_nhetatm.restype = C.c_int
+        L.fpkio_atom_text.argtypes = [vp, C.c_int, C.c_int] + [C.c_char_p] * 5 + [C.POINTER(C.c_int32), C.c_char_p]
+        L.fpkio_atom_text.restype = C.c_int
+        L.fpkio_write_output.argtypes = [vp, C.c_char_p, C.POINTER(capi.FpkResult), C.POINTER(C.c_longlong)]
+        L.fpkio_write_output.restype = C.c_int
+        L.fpkio_run_list.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.POINTER(ReadOpts), C.POINTER(capi.FpkParams), DETECT_FN, FREE_FN,
+                                     C.c_int, C.c_int, C.c_int, C.POINTER(Stats)]
+        L.fpkio_run_list.restype = C.c_int
+        L.fpkio_version.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+class PdbFile:
+    """One parsed PDB file (fpkio_file). `.structure` is the ctypes fpk_structure the library would be handed."""
+
+    def __init__(self, path=None, data=None, opts=None):
+        L = lib()
+        h = C.c_void_p()
+        o = C.byref(opts) if opts is not None else None
+        if data is not None:
+            rc = L.fpkio_read_pdb_mem((path or "<memory>").encode(), data, len(data), o, C.byref(h))
+        else:
+            rc = L.fpkio_read_pdb(path.encode(), o, C.byref(h))
+        if rc != FPKIO_OK:
+            raise IOError("fpkio_read_pdb(%s) failed: %d" % (path, rc))
+        self.h = h
+        self.path = path
+
+    @property
+    def structure(self):
+        return lib().fpkio_structure(self.h).contents
+
+    def natoms(self, with_lig=0):
+        return lib().fpkio_natoms(self.h, with_lig)
+
+    def nhetatm(self, with_lig=0):
+        return lib().fpkio_nhetatm(self.h, with_lig)
+
+    def arrays(self):
+        """The flat arrays as numpy copies, keyed like oracle/ref_io.c's dump."""
+        s = self.structure
+        n, nw = s.natoms, s.natoms_w
+
+        def arr(p, k, dt):
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(dt)), (k,)).copy() if k else np.zeros(0, dt)
+        d = {"n": n, "nw": nw, "same_pdb": s.same_pdb,
+             "bfstat": np.array([s.avg_bfactor, s.min_bfactor, s.max_bfactor], np.float32)}
+        for nm in ("x", "y", "z", "radius", "electroneg", "bfactor"):
+            d[nm] = arr(getattr(s, nm), n, C.c_float)
+        d["atom_id"], d["res_id"] = arr(s.atom_id, n, C.c_int32), arr(s.res_id, n, C.c_int32)
+        d["aa_idx"], d["flags"] = arr(s.aa_idx, n, C.c_int8), arr(s.flags, n, C.c_uint8)
+        for nm in ("wx", "wy", "wz", "wradius", "welectroneg"):
+            d[nm] = arr(getattr(s, nm), nw, C.c_float)
+        d["wflags"] = arr(s.wflags, nw, C.c_uint8)
+        return d
+
+    def atom_text(self, with_lig=0):
+        """[n, 40] uint8 rows laid out as ref_io.c dumps them + [n, 3] ints (id, res_id, charge)."""
+        L = lib()
+        n = self.natoms(with_lig)
+        t = np.zeros((n, 40), np.uint8)
+        iv = np.zeros((n, 3), np.int32)
+        ty, nm, rn, ch, sy = (C.create_string_buffer(8) for _ in range(5))
+        ia = C.create_string_buffer(2)
+        irc = (C.c_int32 * 3)()
+        for k in range(n):
+            L.fpkio_atom_text(self.h, with_lig, k, ty, nm, rn, ch, sy, irc, ia)
+            t[k, 0:7] = np.frombuffer(ty.raw[:7], np.uint8)
+            t[k, 8:13] = np.frombuffer(nm.raw[:5], np.uint8)
+            t[k, 16:24] = np.frombuffer(rn.raw[:8], np.uint8)
+            t[k, 24:28] = np.frombuffer(ch.raw[:4], np.uint8)
+            t[k, 28:31] = np.frombuffer(sy.raw[:3], np.uint8)
+            t[k, 32], t[k, 33] = ia.raw[0], ia.raw[1]
+            iv[k] = irc[0], irc[1], irc[2]
+        return t, iv
+
+    def write_output(self, pdb_path, result):
+        """result: a ctypes capi.FpkResult. Returns (pockets written, bytes written)."""
+        nb = C.c_longlong(0)
+        rc = lib().fpkio_write_output(self.h, pdb_path.encode(), C.byref(result), C.byref(nb))
+        if rc < 0:
+            raise IOError("fpkio_write_output(%s) failed: %d" % (pdb_path, rc))
+        return rc, nb.value
+
+    def close(self):
+        if self.h:
+            lib().fpkio_file_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def run_list(paths, params, detect=None, free_result=None, group=0, io_threads=0, quiet=1, opts=None):
+    """The -F loop: reader pool -> detect -> writer pool. detect / free_result default to libfpocket_cuda's
+    fpk_detect_batch / fpk_result_free (needs a B200); the CPU tests pass oracle-backed callbacks."""
+    L = lib()
+    keep = []
+    if detect is None:
+        cl = capi.load_library()
+        if cl.fpk_init(None, 0) != 0:
+            raise RuntimeError("fpk_init failed: %s" % cl.fpk_last_error().decode())
+        detect = C.cast(cl.fpk_detect_batch, DETECT_FN)
+        free_result = C.cast(cl.fpk_result_free, FREE_FN)
+    else:
+        detect, free_result = DETECT_FN(detect), FREE_FN(free_result)
+    keep += [detect, free_result]
+    arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+    st = Stats()
+    rc = L.fpkio_run_list(arr, len(paths), C.byref(opts) if opts is not None else None, C.byref(params), detect, free_result,
+                          group, io_threads, quiet, C.byref(st))
+    if rc != FPKIO_OK:
+        raise RuntimeError("fpkio_run_list failed: %d" % rc)
+    return st.as_dict()

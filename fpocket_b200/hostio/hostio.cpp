@@ -1,0 +1,875 @@
+// libfpocket_hostio: native, re-entrant host I/O either side of libfpocket_cuda (include/fpocket_hostio.h).
+//
+//   reader  : reference src/rpdb.c:785-1478 (rpdb_open + rpdb_read, both atom lists) in ONE pass over the file's bytes, followed by the
+//             flattening the C shim does (fpocket_b200/shim/search_pocket_cuda.c: shim_flatten / shim_job_prepare)
+//   writers : reference src/fpout.c:55-213, src/writepocket.c:262-640, src/write_visu.c:56-290, src/writepdb.c:78-216,
+//             src/voronoi.c:1437-1557, fed from fpk_result instead of c_lst_pockets
+//   pipeline: the -F loop of src/fpmain.c:61-76 as reader pool -> detect callback (fpk_detect_batch) -> writer pool
+//
+// Everything the reference's parser does with its fixed 83-byte line buffer is kept, including what it reads from a PREVIOUS line when a
+// record is short (the buffer is never cleared, rpdb.c:1064), because that decides which bytes land in the output files.
+#include "fpocket_hostio.h"
+
+#include <atomic>
+#include <cerrno>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <unistd.h>
+
+namespace {
+
+#include "tables.inc"
+#include "viz_templates.inc"
+
+constexpr int LINE_MAX_CHARS = 81;      // fgets(buf, M_PDB_LINE_LEN + 2, f) hands out at most 81 characters (rpdb.h:32, rpdb.c:832)
+
+struct AtomRec {                        // the fields of s_atm (headers/atom.h:29-77) the path and the writers use
+    char type[8], name[8], res_name[8], chain[4], symbol[4];
+    int32_t id, res_id, charge;
+    char insert, aloc;
+    float x, y, z, occ, bf, radius, en;
+};
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// ---- the C library calls the reference makes on slices of its line buffer ------------------------------------------------------------
+// atoi(p) with a NUL planted at p[len] (rpdb.c:283-287): leading blanks, sign, digits; stops at the slice end or an earlier NUL
+int slice_atoi(const char *p, int len)
+{
+    int i = 0;
+    while (i < len && p[i] && (p[i] == ' ' || (p[i] >= '\t' && p[i] <= '\r'))) i++;
+    bool neg = false;
+    if (i < len && (p[i] == '-' || p[i] == '+')) { neg = p[i] == '-'; i++; }
+    long long v = 0;
+    while (i < len && p[i] >= '0' && p[i] <= '9') { v = v * 10 + (p[i] - '0'); if (v > 0x7fffffffLL + 1) { v = 0x7fffffffLL + 1; } i++; }
+    if (neg) v = -v;
+    if (v > 0x7fffffffLL) v = 0x7fffffffLL;
+    if (v < -0x80000000LL) v = -0x80000000LL;
+    return (int)v;
+}
+// (float)atof(p) with a NUL planted at p[len] (rpdb.c:632-660). Plain decimals with <= 15 digits take the exact route
+// (integer mantissa / power of ten is the correctly rounded double); anything else goes to strtod on a copy of the slice.
+float slice_atof(const char *p, int len)
+{
+    int i = 0;
+    while (i < len && p[i] && (p[i] == ' ' || (p[i] >= '\t' && p[i] <= '\r'))) i++;
+    int j = i;
+    bool neg = false;
+    if (j < len && (p[j] == '-' || p[j] == '+')) { neg = p[j] == '-'; j++; }
+    unsigned long long m = 0;
+    int nd = 0, frac = 0;
+    bool dot = false, simple = true;
+    int k = j;
+    for (; k < len && p[k]; k++) {
+        const char c = p[k];
+        if (c >= '0' && c <= '9') { m = m * 10 + (unsigned)(c - '0'); nd++; if (dot) frac++; }
+        else if (c == '.' && !dot) dot = true;
+        else break;
+    }
+    if (nd == 0 || nd > 15) simple = false;
+    if (simple && k < len && p[k]) {
+        const char c = p[k];            // what follows the digits must not continue a number strtod would accept (exponent, hex, inf/nan)
+        if (c == 'e' || c == 'E' || c == 'x' || c == 'X' || c == 'p' || c == 'P') simple = false;
+    }
+    if (simple) {
+        static const double P10[16] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15};
+        double d = (double)m / P10[frac];
+        return (float)(neg ? -d : d);
+    }
+    char tmp[24];
+    int n = 0;
+    while (n < len && n < 23 && p[n]) { tmp[n] = p[n]; n++; }
+    tmp[n] = 0;
+    return (float)atof(tmp);
+}
+// strncpy(dst, p, len); dst[len] = 0 (dst zero-filled beyond the copied bytes, as strncpy does)
+void slice_strncpy(char *dst, const char *p, int len)
+{
+    int i = 0;
+    for (; i < len && p[i]; i++) dst[i] = p[i];
+    for (; i <= len; i++) dst[i] = 0;
+}
+void str_trim(char *s)                  // utils.c:518-531: blanks only
+{
+    int len = (int)strlen(s);
+    while (len > 0 && s[len - 1] == ' ') s[--len] = 0;
+    int lead = 0;
+    while (lead < len && s[lead] == ' ') lead++;
+    if (lead) { memmove(s, s + lead, (size_t)(len - lead) + 1); memset(s + (len - lead) + 1, 0, (size_t)lead); }   // the bytes behind the terminator end up NUL there too
+}
+
+// ---- element tables (pertable.c) ------------------------------------------------------------------------------------------------------
+const ElemRow *elem_lookup(const char *symbol)         // pte_get_vdw_ray / pte_get_enegativity: first row matching (upper, lower)
+{
+    const char a0 = (char)toupper((unsigned char)symbol[0]), a1 = (char)tolower((unsigned char)symbol[1]);
+    for (const ElemRow &e : ELEMENTS) if (e.c0 == a0 && e.c1 == a1) return &e;
+    return nullptr;
+}
+bool in_std_res(const char *r)          // pertable.c element_in_std_res: strncmp(res_name, X, 3)
+{
+    static const char *N[26] = {"GLY", "LEU", "ILE", "TRP", "MET", "SER", "THR", "LYS", "ARG", "ASN", "GLN", "GLU", "ASP", "CYS", "PRO", "HIS",
+                                "TYR", "PHE", "VAL", "ALA", "HIE", "HID", "HIP", "HSD", "HSE", "HSP"};
+    for (const char *n : N) if (!strncmp(r, n, 3)) return true;
+    return false;
+}
+bool in_nucl_acid(const char *r)
+{
+    static const char *N[9] = {"dG", "dC", "dT", "dA", "A", "C", "T", "G", "U"};
+    for (const char *n : N) if (!strncmp(r, n, 3)) return true;
+    return false;
+}
+bool first_letter_in(const char *s, const char *letters)      // is_valid_prot_element / is_valid_nucl_acid_element with ignore_case
+{
+    if (!s[0]) return false;
+    char t[8];
+    snprintf(t, sizeof t, "%s", s);
+    str_trim(t);
+    const char c = (char)tolower((unsigned char)t[0]);
+    for (const char *q = letters; *q; q++) if (c == (char)tolower((unsigned char)*q)) return true;
+    return false;
+}
+bool is_element_name(const char *s)                           // is_valid_element(str, 1): the whole trimmed string is a symbol
+{
+    if (!s[0]) return false;
+    char t[8];
+    snprintf(t, sizeof t, "%s", s);
+    str_trim(t);
+    t[0] = (char)tolower((unsigned char)t[0]);
+    if (t[0]) t[1] = (char)tolower((unsigned char)t[1]);
+    for (const ElemRow &e : ELEMENTS) {
+        const char u[3] = {(char)tolower((unsigned char)e.c0), (char)tolower((unsigned char)e.c1), 0};
+        if (!strcmp(t, u)) return true;
+    }
+    return false;
+}
+void guess_element(const char *aname, char *element, const char *res_name)      // rpdb.c:410-461
+{
+    char tmp[8];
+    snprintf(tmp, sizeof tmp, "%s", aname);
+    str_trim(tmp);
+    const char *pt = tmp;
+    if (isdigit((unsigned char)tmp[0])) pt++;
+    if (in_std_res(res_name)) {
+        if (first_letter_in(pt, "HCNOSP")) { element[0] = pt[0]; element[1] = 0; return; }
+    } else if (in_nucl_acid(res_name)) {
+        if (first_letter_in(pt, "HCNOP")) { element[0] = pt[0]; element[1] = 0; return; }
+    } else if (is_element_name(pt)) {
+        element[0] = pt[0]; element[1] = pt[0] ? pt[1] : 0; element[2] = 0;       // strcpy of a one- or two-letter symbol
+        return;
+    }
+    element[0] = pt[0];
+    element[1] = pt[0] ? pt[1] : 0;
+    element[2] = 0;
+}
+bool keep_hetatm(const char *resb)      // rpdb.c:952-961: first three bytes equal to an entry of ST_keep_hetatm
+{
+    if (!resb[0] || !resb[1]) return false;     // the one-letter entries never match: the byte the reference compares lies beyond their terminator
+    const uint32_t key = ((uint32_t)(unsigned char)resb[0] << 16) | ((uint32_t)(unsigned char)resb[1] << 8) | (uint32_t)(unsigned char)resb[2];
+    int lo = 0, hi = (int)(sizeof KEEP_HETATM / sizeof KEEP_HETATM[0]) - 1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        if (KEEP_HETATM[mid] == key) return true;
+        if (KEEP_HETATM[mid] < key) lo = mid + 1; else hi = mid - 1;
+    }
+    return false;
+}
+bool is_water3(const char *r) { return !strncmp(r, "HOH", 3) || !strncmp(r, "WAT", 3) || !strncmp(r, "TIP", 3); }
+
+int aa_index(const char *n)             // set_aa_desc's switch (descriptors.c:453-507), as the shim's shim_aa_index
+{
+    const char a = n[0], b = n[0] ? n[1] : 0, c = (n[0] && n[1]) ? n[2] : 0;
+    switch (a) {
+    case 'A': return b == 'L' ? 0 : b == 'R' ? 1 : (b == 'S' && c == 'P') ? 3 : 2;
+    case 'C': return 4;
+    case 'G': return c == 'U' ? 6 : c == 'Y' ? 7 : 5;
+    case 'H': return 8;
+    case 'I': return 9;
+    case 'L': return b == 'Y' ? 11 : 10;
+    case 'M': return 12;
+    case 'P': return b == 'H' ? 13 : 14;
+    case 'S': return 15;
+    case 'T': return b == 'H' ? 16 : b == 'R' ? 17 : 18;
+    case 'V': return 19;
+    }
+    return -1;
+}
+
+}  // namespace
+
+struct fpkio_file {
+    std::string path;
+    std::vector<AtomRec> watoms;        // pdb_w_lig->latoms (keep_lig = 1): a superset of pdb->latoms on the restated route
+    std::vector<int32_t> nolig;         // pdb->latoms[k] = watoms[nolig[k]]
+    int nhet[2] = {0, 0};
+    std::vector<float> f, wf;           // 6 x n: x y z radius electroneg bfactor;  5 x nw: x y z radius electroneg
+    std::vector<int32_t> iv;            // 2 x n: id res_id
+    std::vector<int8_t> aa;
+    std::vector<uint8_t> fl, wfl;
+    fpk_structure st;
+    long long bytes = 0;
+};
+
+namespace {
+
+// rpdb_extract_pdb_atom (rpdb.c:262-352) on the persistent line buffer L
+void extract_atom(const char *L, AtomRec &a)
+{
+    memset(&a, 0, sizeof a);
+    const int rlen = (int)strlen(L);
+    slice_strncpy(a.type, L, 6);
+    a.id = slice_atoi(L + 6, 5);
+    slice_strncpy(a.name, L + 12, 4);
+    str_trim(a.name);
+    a.aloc = L[16];
+    slice_strncpy(a.res_name, L + 17, 4);
+    str_trim(a.res_name);
+    a.chain[0] = L[21];
+    a.res_id = slice_atoi(L + 22, 4);
+    a.insert = L[26];
+    a.x = slice_atof(L + 30, 8); a.y = slice_atof(L + 38, 8); a.z = slice_atof(L + 46, 8);
+    a.occ = slice_atof(L + 54, 6); a.bf = slice_atof(L + 60, 6);
+    if (rlen >= 77) {
+        slice_strncpy(a.symbol, L + 76, 2);
+        str_trim(a.symbol);
+        if (!a.symbol[0]) guess_element(a.name, a.symbol, a.res_name);
+    } else guess_element(a.name, a.symbol, a.res_name);
+    str_trim(a.symbol);
+    if (rlen >= 79) {
+        if ((L[78] == ' ' && L[79] == ' ') || L[78] == '\n') a.charge = 0;
+        else { const char b[3] = {L[78], L[79], 0}; a.charge = slice_atoi(b, 2); }
+    } else a.charge = 0;
+    const ElemRow *e = elem_lookup(a.symbol);
+    a.radius = e ? e->rvdw : -1.0f;
+    a.en = e ? e->en : -1.0f;
+}
+
+bool chain_passes(const fpkio_read_opts *o, char c)     // chains_to_delete (rpdb.c:1561-1591)
+{
+    if (!o || o->n_chains <= 0) return !(o && o->chains_are_kept);
+    bool hit = false;
+    for (int i = 0; i < o->n_chains && i < 20; i++) if (o->chains[i][0] == c && o->chains[i][1] == 0) hit = true;
+    return o->chains_are_kept ? hit : !hit;
+}
+
+int parse_pdb(const char *path, const char *data, size_t size, const fpkio_read_opts *opts, fpkio_file **out)
+{
+    fpkio_file *F = new fpkio_file();
+    F->path = path ? path : "";
+    F->bytes = (long long)size;
+    F->watoms.reserve(size / 81 + 8);
+    char L[LINE_MAX_CHARS + 3];
+    memset(L, 0, sizeof L);
+    const char *p = data, *end = data + size;
+    float x = 0, y = 0, z = 0;
+    while (p < end) {
+        int n = 0;
+        while (n < LINE_MAX_CHARS && p < end) { const char c = *p++; L[n++] = c; if (c == '\n') break; }
+        L[n] = 0;
+        const bool is_atom = !strncmp(L, "ATOM ", 5), is_het = !is_atom && !strncmp(L, "HETATM", 6);
+        if (is_atom || is_het) {
+            if (!chain_passes(opts, L[21])) continue;
+            x = slice_atof(L + 30, 8); y = slice_atof(L + 38, 8); z = slice_atof(L + 46, 8);
+            if (!((L[16] == ' ' || L[16] == 'A') && x < 9990 && y < 9990 && z < 9990)) continue;
+            bool in_lig = true, in_nolig = true;
+            if (is_het) {
+                char resb[8];
+                slice_strncpy(resb, L + 17, 4);
+                str_trim(resb);
+                const bool listed = keep_hetatm(resb);
+                in_nolig = listed;                               // rpdb.c:947-961 with keep_lig = 0
+                in_lig = !is_water3(resb) || listed;             // rpdb.c:941-946 with keep_lig = 1, ligan = NULL
+                if (!in_lig) continue;
+            }
+            F->watoms.emplace_back();
+            extract_atom(L, F->watoms.back());
+            if (is_het) { F->nhet[1]++; if (in_nolig) F->nhet[0]++; }
+            if (in_nolig) F->nolig.push_back((int32_t)F->watoms.size() - 1);
+        } else if (!strncmp(L, "END", 3)) break;                 // rpdb.c:975, :1420 (model_flag == 0): ENDMDL ends the file too
+    }
+    if (F->nolig.empty()) { delete F; return FPKIO_ERR_NO_ATOMS; }
+    // ---- the flat arrays of fpk_structure (shim_flatten / shim_job_prepare) + the s_pdb B-factor statistics (rpdb.c:1429-1454) ----
+    const int n = (int)F->nolig.size(), nw = (int)F->watoms.size();
+    F->f.resize((size_t)6 * n); F->iv.resize((size_t)2 * n); F->aa.resize(n); F->fl.resize(n);
+    F->wf.resize((size_t)5 * nw); F->wfl.resize(nw);
+    float avg = 0.0f, mn = 0.0f, mx = 0.0f;
+    int nh = 0;
+    for (int k = 0; k < n; k++) {
+        const AtomRec &a = F->watoms[F->nolig[k]];
+        F->f[k] = a.x; F->f[(size_t)n + k] = a.y; F->f[(size_t)2 * n + k] = a.z;
+        F->f[(size_t)3 * n + k] = a.radius; F->f[(size_t)4 * n + k] = a.en; F->f[(size_t)5 * n + k] = a.bf;
+        F->iv[k] = a.id; F->iv[(size_t)n + k] = a.res_id;
+        F->aa[k] = (int8_t)aa_index(a.res_name);
+        uint8_t fl = 0;
+        if (!strcmp(a.symbol, "H")) { fl |= FPK_ATOM_H; nh++; }
+        if (a.symbol[0] == 'H') fl |= FPK_ATOM_H1;
+        F->fl[k] = fl;
+        avg += a.bf;
+        if (a.bf < mn) mn = a.bf;
+        if (a.bf > mx) mx = a.bf;
+    }
+    avg /= (n - nh);
+    for (int k = 0; k < nw; k++) {
+        const AtomRec &a = F->watoms[k];
+        F->wf[k] = a.x; F->wf[(size_t)nw + k] = a.y; F->wf[(size_t)2 * nw + k] = a.z; F->wf[(size_t)3 * nw + k] = a.radius; F->wf[(size_t)4 * nw + k] = a.en;
+        F->wfl[k] = a.symbol[0] == 'H' ? FPK_ATOM_H : 0;
+    }
+    fpk_structure &s = F->st;
+    memset(&s, 0, sizeof s);
+    s.natoms = n;
+    s.x = F->f.data(); s.y = s.x + n; s.z = s.x + 2 * (size_t)n; s.radius = s.x + 3 * (size_t)n; s.electroneg = s.x + 4 * (size_t)n; s.bfactor = s.x + 5 * (size_t)n;
+    s.atom_id = F->iv.data(); s.res_id = s.atom_id + n; s.aa_idx = F->aa.data(); s.flags = F->fl.data();
+    s.avg_bfactor = avg; s.min_bfactor = mn; s.max_bfactor = mx;
+    s.natoms_w = nw;
+    s.wx = F->wf.data(); s.wy = s.wx + nw; s.wz = s.wx + 2 * (size_t)nw; s.wradius = s.wx + 3 * (size_t)nw; s.welectroneg = s.wx + 4 * (size_t)nw;
+    s.wflags = F->wfl.data();
+    s.same_pdb = 0;                     // fpmain.c:143-144: two objects
+    *out = F;
+    return FPKIO_OK;
+}
+
+bool read_whole(const char *path, std::string &buf)
+{
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st)) { close(fd); return false; }
+    buf.resize((size_t)st.st_size);
+    size_t got = 0;
+    while (got < buf.size()) {
+        ssize_t r = read(fd, &buf[got], buf.size() - got);
+        if (r <= 0) break;
+        got += (size_t)r;
+    }
+    close(fd);
+    buf.resize(got);
+    return true;
+}
+
+// ====================================================== writers =========================================================================
+struct Out {                            // one output file assembled in memory, written with one write()
+    std::string s;
+    void put(const char *t) { s.append(t); }
+    void put(const char *t, size_t n) { s.append(t, n); }
+    void ch(char c) { s.push_back(c); }
+    void pad(int n) { if (n > 0) s.append((size_t)n, ' '); }
+    void str_left(const char *t, int w) { const int l = (int)strlen(t); s.append(t, (size_t)l); pad(w - l); }       // %-Ns
+    void str_right(const char *t, int w) { const int l = (int)strlen(t); pad(w - l); s.append(t, (size_t)l); }      // %Ns
+    void integer(long long v, int w)                                                                                 // %Nd
+    {
+        char b[24];
+        int n = 0;
+        const bool neg = v < 0;
+        unsigned long long u = neg ? (unsigned long long)(-v) : (unsigned long long)v;
+        do { b[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+        if (neg) b[n++] = '-';
+        pad(w - n);
+        while (n) s.push_back(b[--n]);
+    }
+    // %W.Pf of a float-valued double. v * 10^P is exact in double for a 24-bit mantissa and P <= 4, so rounding it to the nearest integer
+    // (ties to even) is what printf's exact decimal conversion prints; everything else goes through snprintf.
+    void fixed(double v, int w, int prec)
+    {
+        static const double P10[5] = {1.0, 10.0, 100.0, 1000.0, 10000.0};
+        const double av = std::fabs(v);
+        if (!(av < 1e9) || prec > 4 || (double)(float)v != v) {
+            char b[64];
+            const int n = snprintf(b, sizeof b, "%*.*f", w, prec, v);
+            s.append(b, (size_t)n);
+            return;
+        }
+        unsigned long long q = (unsigned long long)std::nearbyint(av * P10[prec]);
+        char b[32];
+        int n = 0;
+        for (int i = 0; i < prec; i++) { b[n++] = (char)('0' + q % 10); q /= 10; }
+        if (prec) b[n++] = '.';
+        do { b[n++] = (char)('0' + q % 10); q /= 10; } while (q);
+        if (std::signbit(v)) b[n++] = '-';
+        pad(w - n);
+        while (n) s.push_back(b[--n]);
+    }
+    void fmt(const char *f, ...) __attribute__((format(printf, 2, 3)))
+    {
+        char b[512];
+        va_list ap;
+        va_start(ap, f);
+        const int n = vsnprintf(b, sizeof b, f, ap);
+        va_end(ap);
+        if (n > 0) s.append(b, (size_t)(n < (int)sizeof b ? n : (int)sizeof b - 1));
+    }
+};
+
+bool write_file(const std::string &path, const std::string &data, mode_t mode, long long *bytes)
+{
+    int fd = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, mode);
+    if (fd < 0) return false;
+    size_t done = 0;
+    while (done < data.size()) {
+        ssize_t r = write(fd, data.data() + done, data.size() - done);
+        if (r < 0) { if (errno == EINTR) continue; close(fd); return false; }
+        done += (size_t)r;
+    }
+    close(fd);
+    if (bytes) *bytes += (long long)data.size();
+    return true;
+}
+bool mkdir_p(const std::string &path)
+{
+    std::string t = path;
+    for (size_t i = 1; i < t.size(); i++)
+        if (t[i] == '/') { t[i] = 0; if (mkdir(t.c_str(), 0777) && errno != EEXIST) return false; t[i] = '/'; }
+    return !(mkdir(t.c_str(), 0777) && errno != EEXIST);
+}
+
+void id_field(Out &o, int id) { if (id < 100000) o.integer(id, 5); else o.fmt("%05x", id); }                 // writepdb.c:101-104
+void resid_field(Out &o, int r) { if (r < 10000) o.integer(r, 4); else if (r < 65536) o.fmt("%04x", r); else o.put("****"); }
+
+// write_pdb_atom_line (writepdb.c:78-135): the occupancy column carries abpa ? abpa_sourrounding_prob : 0, the B-factor column a0
+void pdb_line(Out &o, const char *rec, int id, const char *name, char aloc, const char *res, const char *chain, int res_id, char ins,
+              float x, float y, float z, float a0, int abpa, const char *sym, int charge, float prob)
+{
+    o.str_left(rec, 6);
+    id_field(o, id);
+    o.ch(' ');
+    o.str_right(name, 4);
+    o.ch(aloc ? aloc : ' ');
+    o.str_left(res, 4);
+    o.put(chain);
+    resid_field(o, res_id);
+    o.ch(ins ? ins : ' ');
+    o.pad(3);
+    o.fixed(x, 8, 3); o.fixed(y, 8, 3); o.fixed(z, 8, 3);
+    o.fixed(abpa ? prob : 0.0f, 6, 2);
+    o.fixed(a0, 6, 2);
+    o.pad(10);
+    o.str_right(sym, 2);
+    if (charge == -1) o.put("  "); else o.integer(charge, 2);
+    o.ch('\n');
+}
+void atom_line(Out &o, const AtomRec &a, const float *fx)
+{
+    const int abpa = fx ? (int)fx[0] : 0;
+    pdb_line(o, a.type, a.id, a.name, a.aloc, a.res_name, a.chain, a.res_id, a.insert, a.x, a.y, a.z, fx ? fx[1] : 0.0f, abpa, a.symbol, a.charge,
+             fx ? fx[3] : 0.0f);
+}
+// write_pqr_vert (voronoi.c:1536-1557) -> write_pqr_atom_line (writepdb.c:168-199); electrostatic_energy is 0 on this path
+void pqr_sphere(Out &o, int i, bool apolar, int resid, const float *c)
+{
+    o.put("ATOM  ");
+    id_field(o, i);
+    o.put(apolar ? "    C STP  " : "    O STP  ");
+    resid_field(o, resid);
+    o.pad(4);
+    o.fixed(c[0], 8, 3); o.fixed(c[1], 8, 3); o.fixed(c[2], 8, 3);
+    o.pad(2); o.fixed(0.0, 6, 2); o.pad(3); o.fixed(c[3], 6, 2);
+    o.ch('\n');
+}
+
+void substitute(Out &o, const char *tpl, const std::string &code)
+{
+    for (const char *q = tpl; *q; q++) if (*q == '\001') o.s.append(code); else o.s.push_back(*q);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *fpkio_version(void) { return "fpocket_hostio 0.1 (PDB reader + PDB-mode writers of the -F loop)"; }
+
+int fpkio_read_pdb_mem(const char *path, const char *data, size_t size, const fpkio_read_opts *opts, fpkio_file **out)
+{
+    if (!data || !out) return FPKIO_ERR_BAD_ARG;
+    *out = nullptr;
+    return parse_pdb(path, data, size, opts, out);
+}
+
+int fpkio_read_pdb(const char *path, const fpkio_read_opts *opts, fpkio_file **out)
+{
+    if (!path || !out) return FPKIO_ERR_BAD_ARG;
+    *out = nullptr;
+    if (strstr(path, ".cif")) return FPKIO_ERR_UNSUPPORTED;         // fpmain.c:229: mmCIF goes to read_mmcif, which is not restated
+    std::string buf;
+    if (!read_whole(path, buf)) return FPKIO_ERR_OPEN;
+    return parse_pdb(path, buf.data(), buf.size(), opts, out);
+}
+
+void fpkio_file_free(fpkio_file *f) { delete f; }
+const fpk_structure *fpkio_structure(const fpkio_file *f) { return f ? &f->st : nullptr; }
+int fpkio_natoms(const fpkio_file *f, int with_lig) { return !f ? 0 : with_lig ? (int)f->watoms.size() : (int)f->nolig.size(); }
+int fpkio_nhetatm(const fpkio_file *f, int with_lig) { return !f ? 0 : f->nhet[with_lig ? 1 : 0]; }
+
+int fpkio_atom_text(const fpkio_file *f, int with_lig, int k, char *type, char *name, char *res_name, char *chain, char *symbol,
+                    int32_t *irc, char *insert_aloc)
+{
+    if (!f || k < 0 || k >= fpkio_natoms(f, with_lig)) return FPKIO_ERR_BAD_ARG;
+    const AtomRec &a = f->watoms[with_lig ? k : f->nolig[k]];
+    if (type) memcpy(type, a.type, 8);
+    if (name) memcpy(name, a.name, 8);
+    if (res_name) memcpy(res_name, a.res_name, 8);
+    if (chain) memcpy(chain, a.chain, 4);
+    if (symbol) memcpy(symbol, a.symbol, 4);
+    if (irc) { irc[0] = a.id; irc[1] = a.res_id; irc[2] = a.charge; }
+    if (insert_aloc) { insert_aloc[0] = a.insert; insert_aloc[1] = a.aloc; }
+    return FPKIO_OK;
+}
+
+int fpkio_write_output(const fpkio_file *F, const char *pdb_path, const fpk_result *R, long long *bytes_out)
+{
+    if (!F || !pdb_path || !R) return FPKIO_ERR_BAD_ARG;
+    // ---- names (fpout.c:71-80): remove_ext on the whole path, then remove_path ----
+    std::string code = pdb_path, dir;
+    { const size_t sl = code.rfind('/'); if (sl != std::string::npos) dir = code.substr(0, sl); }
+    { const size_t dot = code.rfind('.'); if (dot != std::string::npos) code.erase(dot); }
+    { const size_t sl = code.rfind('/'); if (sl != std::string::npos) code.erase(0, sl + 1); }
+    const std::string out_dir = dir.empty() ? code + "_out" : dir + "/" + code + "_out";
+    if (!mkdir_p(out_dir)) return FPKIO_ERR_WRITE;
+    const std::string base = out_dir + "/" + code;
+    const int n = (int)F->nolig.size();
+    const float *fx = R->atom_fx;
+    bool ok = true;
+    Out o;
+    // ---- write_visualization (write_visu.c:56-290) ----
+    o.s.clear(); substitute(o, TPL_VMD_SH, code);   ok &= write_file(base + "_VMD.sh", o.s, 0777, bytes_out);
+    o.s.clear(); substitute(o, TPL_TCL, code);      ok &= write_file(base + ".tcl", o.s, 0666, bytes_out);
+    o.s.clear(); substitute(o, TPL_PYMOL_SH, code); ok &= write_file(base + "_PYMOL.sh", o.s, 0777, bytes_out);
+    o.s.clear(); substitute(o, TPL_PML, code);      ok &= write_file(base + ".pml", o.s, 0666, bytes_out);
+    // ---- <code>_out.pdb: every atom of pdb, then the spheres pocket by pocket (writepocket.c:262-305, voronoi.c:1437-1482) ----
+    o.s.clear();
+    o.s.reserve((size_t)(n + R->n_spheres) * 82 + 256);
+    for (int k = 0; k < n; k++) atom_line(o, F->watoms[F->nolig[k]], fx ? fx + 4 * (size_t)k : nullptr);
+    for (int r = 0; r < R->n_pockets; r++) {
+        const int c = R->rank_to_cluster[r];
+        int i = 0;
+        for (int q = R->cl_off[c]; q < R->cl_off[c + 1]; q++) {
+            const int s = R->cl_sph[q];
+            const float *xyz = R->sph_xyzr + 4 * (size_t)s;
+            i++;
+            if (R->sph_type[s] == 0) pdb_line(o, "HETATM", i, "APOL", ' ', "STP", "C", r + 1, ' ', xyz[0], xyz[1], xyz[2], 0.0f, 0, "Ve", -1, 0.0f);
+            else pdb_line(o, "HETATM", n + 1 + s, " POL", ' ', "STP", "C", r + 1, ' ', xyz[0], xyz[1], xyz[2], 0.0f, 0, "Ve", -1, 0.0f);   // s_vvertice.id as the shim numbers it
+        }
+    }
+    ok &= write_file(base + "_out.pdb", o.s, 0666, bytes_out);
+    // ---- <code>_info.txt (fpout.c:151-213) ----
+    o.s.clear();
+    for (int r = 0; r < R->n_pockets; r++) {
+        const int c = R->rank_to_cluster[r];
+        const fpk_desc &d = R->desc[c];
+        o.fmt("Pocket %d :\n", r + 1);
+        o.put("\tScore : \t"); o.fixed(d.score, 0, 3); o.ch('\n');
+        o.put("\tDruggability Score : \t"); o.fixed(d.drug_score, 0, 3); o.ch('\n');
+        o.fmt("\tNumber of Alpha Spheres : \t%d\n", R->cl_off[c + 1] - R->cl_off[c]);
+        o.put("\tTotal SASA : \t"); o.fixed(d.surf_vdw14, 0, 3); o.ch('\n');
+        o.put("\tPolar SASA : \t"); o.fixed(d.surf_pol_vdw14, 0, 3); o.ch('\n');
+        o.put("\tApolar SASA : \t"); o.fixed(d.surf_apol_vdw14, 0, 3); o.ch('\n');
+        o.put("\tVolume : \t"); o.fixed(d.volume, 0, 3); o.ch('\n');
+        o.put("\tMean local hydrophobic density : \t"); o.fixed(d.mean_loc_hyd_dens, 0, 3); o.ch('\n');
+        o.put("\tMean alpha sphere radius :\t"); o.fixed(d.mean_asph_ray, 0, 3); o.ch('\n');
+        o.put("\tMean alp. sph. solvent access : \t"); o.fixed(d.masph_sacc, 0, 3); o.ch('\n');
+        o.put("\tApolar alpha sphere proportion : \t"); o.fixed(d.apolar_asphere_prop, 0, 3); o.ch('\n');
+        o.put("\tHydrophobicity score:\t"); o.fixed(d.hydrophobicity_score, 0, 3); o.ch('\n');
+        o.put("\tVolume score: \t "); o.fixed(d.volume_score, 0, 3); o.ch('\n');
+        o.fmt("\tPolarity score:\t %d\n", d.polarity_score);
+        o.fmt("\tCharge score :\t %d\n", d.charge_score);
+        o.put("\tProportion of polar atoms: \t"); o.fixed(d.prop_polar_atm, 0, 3); o.ch('\n');
+        o.put("\tAlpha sphere density : \t"); o.fixed(d.as_density, 0, 3); o.ch('\n');
+        o.put("\tCent. of mass - Alpha Sphere max dist: \t"); o.fixed(d.as_max_dst, 0, 3); o.ch('\n');
+        o.put("\tFlexibility : \t"); o.fixed(d.flex, 0, 3); o.ch('\n');
+        o.ch('\n');
+    }
+    ok &= write_file(base + "_info.txt", o.s, 0666, bytes_out);
+    // ---- <code>_pockets.pqr (writepocket.c:381-416): one running index over all pockets ----
+    o.s.clear();
+    o.put("HEADER\n"
+          "HEADER This is a pqr format file writen by the programm fpocket.                 \n"
+          "HEADER It contains all the pocket vertices found by fpocket.                    \n");
+    {
+        int i = 0;
+        for (int r = 0; r < R->n_pockets; r++) {
+            const int c = R->rank_to_cluster[r];
+            for (int q = R->cl_off[c]; q < R->cl_off[c + 1]; q++) { const int s = R->cl_sph[q]; pqr_sphere(o, ++i, R->sph_type[s] == 0, r + 1, R->sph_xyzr + 4 * (size_t)s); }
+        }
+    }
+    o.put("TER\nEND\n");
+    ok &= write_file(base + "_pockets.pqr", o.s, 0666, bytes_out);
+    // ---- pockets/pocketK_vert.pqr, pockets/pocketK_atm.pdb (writepocket.c:475-640) ----
+    const std::string pdir = out_dir + "/pockets";
+    if (mkdir(pdir.c_str(), 0777) && errno != EEXIST) return FPKIO_ERR_WRITE;
+    std::vector<int32_t> uniq;
+    char nm[64];
+    for (int r = 0; r < R->n_pockets; r++) {
+        const int c = R->rank_to_cluster[r];
+        const fpk_desc &d = R->desc[c];
+        const int first = R->cl_off[c], last = R->cl_off[c + 1];
+        o.s.clear();
+        o.put("HEADER\n"
+              "HEADER This is a pqr format file writen by the programm fpocket.                 \n"
+              "HEADER It represent the voronoi vertices of a single pocket found by the         \n"
+              "HEADER algorithm.                                                                \n"
+              "HEADER                                                                           \n");
+        o.fmt("HEADER Information about the pocket %5d:\n", r + 1);
+        o.put("HEADER 0  - Pocket Score                      : "); o.fixed(d.score, 0, 4); o.ch('\n');
+        o.put("HEADER 1  - Drug Score                        : "); o.fixed(d.drug_score, 0, 4); o.ch('\n');
+        o.fmt("HEADER 2  - Number of V. Vertices             : %5d\n", d.nb_asph);
+        o.put("HEADER 3  - Mean alpha-sphere radius          : "); o.fixed(d.mean_asph_ray, 0, 4); o.ch('\n');
+        o.put("HEADER 4  - Mean alpha-sphere SA              : "); o.fixed(d.masph_sacc, 0, 4); o.ch('\n');
+        o.put("HEADER 5  - Mean B-factor                     : "); o.fixed(d.flex, 0, 4); o.ch('\n');
+        o.put("HEADER 6  - Hydrophobicity Score              : "); o.fixed(d.hydrophobicity_score, 0, 4); o.ch('\n');
+        o.fmt("HEADER 7  - Polarity Score                    : %5d\n", d.polarity_score);
+        o.put("HEADER 8  - Volume Score                      : "); o.fixed(d.volume_score, 0, 4); o.ch('\n');
+        o.put("HEADER 9  - Real volume (approximation)       : "); o.fixed(d.volume, 0, 4); o.ch('\n');
+        o.fmt("HEADER 10 - Charge Score                      : %5d\n", d.charge_score);
+        o.put("HEADER 11 - Local hydrophobic density Score   : "); o.fixed(d.mean_loc_hyd_dens, 0, 4); o.ch('\n');
+        o.fmt("HEADER 12 - Number of apolar alpha sphere     : %5d\n", d.nAlphaApol);
+        o.put("HEADER 13 - Proportion of apolar alpha sphere : "); o.fixed(d.apolar_asphere_prop, 0, 4); o.ch('\n');
+        {
+            int i = 0;
+            for (int q = first; q < last; q++) { const int s = R->cl_sph[q]; pqr_sphere(o, ++i, R->sph_type[s] == 0, r + 1, R->sph_xyzr + 4 * (size_t)s); }
+        }
+        o.put("TER\nEND\n");
+        snprintf(nm, sizeof nm, "/pocket%d_vert.pqr", r + 1);
+        ok &= write_file(pdir + nm, o.s, 0666, bytes_out);
+
+        o.s.clear();
+        o.put("HEADER\n"
+              "HEADER This is a pdb format file writen by the programm fpocket.                 \n"
+              "HEADER It represents the atoms contacted by the voronoi vertices of the pocket.  \n"
+              "HEADER                                                                           \n");
+        o.fmt("HEADER Information about the pocket %5d:\n", r + 1);
+        o.put("HEADER 0  - Pocket Score                      : "); o.fixed(d.score, 0, 4); o.ch('\n');
+        o.put("HEADER 1  - Drug Score                        : "); o.fixed(d.drug_score, 0, 4); o.ch('\n');
+        o.fmt("HEADER 2  - Number of alpha spheres           : %5d\n", d.nb_asph);
+        o.put("HEADER 3  - Mean alpha-sphere radius          : "); o.fixed(d.mean_asph_ray, 0, 4); o.ch('\n');
+        o.put("HEADER 4  - Mean alpha-sphere Solvent Acc.    : "); o.fixed(d.masph_sacc, 0, 4); o.ch('\n');
+        o.put("HEADER 5  - Mean B-factor of pocket residues  : "); o.fixed(d.flex, 0, 4); o.ch('\n');
+        o.put("HEADER 6  - Hydrophobicity Score              : "); o.fixed(d.hydrophobicity_score, 0, 4); o.ch('\n');
+        o.fmt("HEADER 7  - Polarity Score                    : %5d\n", d.polarity_score);
+        o.put("HEADER 8  - Amino Acid based volume Score     : "); o.fixed(d.volume_score, 0, 4); o.ch('\n');
+        o.put("HEADER 9  - Pocket volume (Monte Carlo)       : "); o.fixed(d.volume, 0, 4); o.ch('\n');
+        o.put("HEADER 10 - Pocket volume (convex hull)       : "); o.fixed(d.convex_hull_volume, 0, 4); o.ch('\n');
+        o.fmt("HEADER 11 - Charge Score                      : %5d\n", d.charge_score);
+        o.put("HEADER 12 - Local hydrophobic density Score   : "); o.fixed(d.mean_loc_hyd_dens, 0, 4); o.ch('\n');
+        o.fmt("HEADER 13 - Number of apolar alpha sphere     : %5d\n", d.nAlphaApol);
+        o.put("HEADER 14 - Proportion of apolar alpha sphere : "); o.fixed(d.apolar_asphere_prop, 0, 4); o.ch('\n');
+        // atoms contacted by the pocket's spheres, unique by atom id, first seen first (writepocket.c:604-617, is_in_lst_atm compares ids)
+        uniq.clear();
+        for (int q = first; q < last; q++) {
+            const int32_t *ng = R->sph_neigh + 4 * (size_t)R->cl_sph[q];
+            for (int j = 0; j < 4; j++) {
+                const int id = F->watoms[F->nolig[ng[j]]].id;
+                bool seen = false;
+                for (const int32_t u : uniq) if (F->watoms[F->nolig[u]].id == id) { seen = true; break; }
+                if (!seen) uniq.push_back(ng[j]);
+            }
+        }
+        for (const int32_t k : uniq) atom_line(o, F->watoms[F->nolig[k]], fx ? fx + 4 * (size_t)k : nullptr);
+        o.put("TER\nEND\n");
+        snprintf(nm, sizeof nm, "/pocket%d_atm.pdb", r + 1);
+        ok &= write_file(pdir + nm, o.s, 0666, bytes_out);
+    }
+    return ok ? R->n_pockets : FPKIO_ERR_WRITE;
+}
+
+}  // extern "C"
+
+// ====================================================== the -F loop =====================================================================
+namespace {
+
+class Pool {                            // fixed pool, two priorities: writes first (they release memory), then reads
+public:
+    explicit Pool(int n) { for (int i = 0; i < n; i++) th_.emplace_back([this] { run(); }); }
+    ~Pool()
+    {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    void submit(std::function<void()> fn, bool urgent)
+    {
+        { std::lock_guard<std::mutex> g(m_); (urgent ? hi_ : lo_).push_back(std::move(fn)); }
+        cv_.notify_one();
+    }
+private:
+    void run()
+    {
+        for (;;) {
+            std::function<void()> fn;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [this] { return stop_ || !hi_.empty() || !lo_.empty(); });
+                if (!hi_.empty()) { fn = std::move(hi_.front()); hi_.pop_front(); }
+                else if (!lo_.empty()) { fn = std::move(lo_.front()); lo_.pop_front(); }
+                else if (stop_) return;
+            }
+            if (fn) fn();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::deque<std::function<void()>> hi_, lo_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    bool stop_ = false;
+};
+
+struct Group {
+    int first = 0, n = 0;
+    std::vector<fpkio_file *> files;
+    std::vector<int> rc;
+    std::vector<fpk_structure> in;
+    std::vector<int> idx;
+    std::vector<fpk_result> out;
+    std::atomic<int> pending{0};
+};
+
+}  // namespace
+
+extern "C" int fpkio_run_list(const char *const *paths, int n, const fpkio_read_opts *ropts, const fpk_params *p, fpkio_detect_fn detect,
+                              fpkio_free_fn free_result, int group, int io_threads, int quiet, fpkio_stats *stats)
+{
+    if (!paths || n < 0 || !p || !detect || !free_result) return FPKIO_ERR_BAD_ARG;
+    if (group <= 0) group = 1024;
+    if (io_threads <= 0) io_threads = (int)std::thread::hardware_concurrency();
+    if (io_threads <= 0) io_threads = 4;
+    const double t0 = now_s();
+    fpkio_stats S;
+    memset(&S, 0, sizeof S);
+    S.n_files = n;
+    std::mutex sm;                       // guards S, the ready queue and the in-flight count
+    std::condition_variable scv;
+    std::deque<Group *> ready;
+    int in_flight = 0, finished = 0;
+    const int ngroups = (n + group - 1) / group;
+    bool detect_error = false;
+    {
+        Pool pool(io_threads);
+        // ---- detect thread: one fpk_detect_batch per group, in order of readiness; hands every structure to the writer pool ----
+        std::thread det([&] {
+            for (int done = 0; done < ngroups; done++) {
+                Group *g;
+                {
+                    std::unique_lock<std::mutex> lk(sm);
+                    scv.wait(lk, [&] { return !ready.empty(); });
+                    g = ready.front();
+                    ready.pop_front();
+                }
+                for (int k = 0; k < g->n; k++)
+                    if (g->rc[k] == FPKIO_OK) { g->in.push_back(*fpkio_structure(g->files[k])); g->idx.push_back(k); }
+                    else {
+                        if (!quiet) {
+                            if (g->rc[k] == FPKIO_ERR_OPEN) fprintf(stderr, "! File %s does not exist\n", paths[g->first + k]);
+                            else if (g->rc[k] == FPKIO_ERR_NO_ATOMS) fprintf(stderr, "! File '%s' contains no atoms...\n", paths[g->first + k]);
+                            else fprintf(stderr, "! %s: not a PDB file this reader handles (mmCIF input goes through build/fpocket_cuda_batch)\n", paths[g->first + k]);
+                            fprintf(stderr, "! Structure reading failed!\n");
+                        }
+                        std::lock_guard<std::mutex> lk(sm);
+                        S.n_read_failed++;
+                    }
+                const int nb = (int)g->in.size();
+                g->out.assign((size_t)nb, fpk_result());
+                for (auto &r : g->out) memset(&r, 0, sizeof r);
+                int rc = 0;
+                if (nb > 0) {
+                    const double td = now_s();
+                    rc = detect(g->in.data(), nb, p, g->out.data());
+                    const double dt = now_s() - td;
+                    std::lock_guard<std::mutex> lk(sm);
+                    S.detect_s += dt;
+                    if (rc) { detect_error = true; S.n_detect_failed += nb; }
+                }
+                g->pending = nb;
+                auto retire = [&, g] {
+                    for (fpkio_file *f : g->files) fpkio_file_free(f);
+                    delete g;
+                    std::lock_guard<std::mutex> lk(sm);
+                    in_flight--;
+                    finished++;
+                    scv.notify_all();
+                };
+                if (nb == 0 || rc) { if (rc) for (auto &r : g->out) free_result(&r); retire(); continue; }
+                for (int q = 0; q < nb; q++)
+                    pool.submit([&, g, q, retire] {
+                        const int k = g->idx[q];
+                        const double tw = now_s();
+                        long long bytes = 0;
+                        fpk_result *R = &g->out[q];
+                        int w = 0;
+                        // search_pocket returns a list (possibly with no pocket left, fpocket.c:225) unless the clustering tree failed (:135-139)
+                        const bool have_list = (R->status == FPK_OK || R->status == FPK_ERR_NO_POCKETS);
+                        if (have_list) w = fpkio_write_output(g->files[k], paths[g->first + k], R, &bytes);
+                        else {
+                            if (!quiet && R->status == FPK_ERR_NO_SPHERES) fprintf(stderr, "Error in creating clustering tree, return NULL pointer...breaking up");
+                            if (!quiet) printf("no pockets found\n");                            // fpmain.c:204
+                        }
+                        if (w < 0 && !quiet) fprintf(stderr, "! could not write the results of %s\n", paths[g->first + k]);
+                        const long long natoms = fpkio_natoms(g->files[k], 0);
+                        const int st = R->status;
+                        free_result(R);
+                        fpkio_file_free(g->files[k]);
+                        g->files[k] = nullptr;
+                        const double dt = now_s() - tw;
+                        {
+                            std::lock_guard<std::mutex> lk(sm);
+                            S.write_cpu_s += dt;
+                            S.bytes_out += bytes;
+                            S.n_atoms += natoms;
+                            if (have_list && w >= 0) { S.n_written++; S.n_pockets += w; if (!w) S.n_no_pockets++; }
+                            else if (st == FPK_ERR_NO_SPHERES) S.n_no_pockets++;
+                            else S.n_detect_failed++;
+                        }
+                        if (g->pending.fetch_sub(1) == 1) retire();
+                    }, true);
+            }
+        });
+        // ---- this thread: keeps at most three groups in flight (one being read, one on the GPU, one being written) ----
+        for (int gi = 0; gi < ngroups; gi++) {
+            {
+                std::unique_lock<std::mutex> lk(sm);
+                scv.wait(lk, [&] { return in_flight < 3; });
+                in_flight++;
+            }
+            Group *g = new Group();
+            g->first = gi * group;
+            g->n = std::min(group, n - g->first);
+            g->files.assign((size_t)g->n, nullptr);
+            g->rc.assign((size_t)g->n, FPKIO_ERR_OPEN);
+            g->pending = g->n;
+            for (int k = 0; k < g->n; k++)
+                pool.submit([&, g, k] {
+                    const double tr = now_s();
+                    g->rc[k] = fpkio_read_pdb(paths[g->first + k], ropts, &g->files[k]);
+                    const double dt = now_s() - tr;
+                    {
+                        std::lock_guard<std::mutex> lk(sm);
+                        S.read_cpu_s += dt;
+                        if (g->files[k]) S.bytes_in += g->files[k]->bytes;
+                    }
+                    if (g->pending.fetch_sub(1) == 1) {
+                        std::lock_guard<std::mutex> lk(sm);
+                        ready.push_back(g);
+                        scv.notify_all();
+                    }
+                }, false);
+        }
+        det.join();
+        {
+            std::unique_lock<std::mutex> lk(sm);
+            scv.wait(lk, [&] { return finished == ngroups; });
+        }
+    }
+    S.wall_s = now_s() - t0;
+    if (stats) *stats = S;
+    return detect_error ? FPKIO_ERR_BAD_ARG : FPKIO_OK;
+}

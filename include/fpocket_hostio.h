@@ -1,0 +1,89 @@
+/*
+ * libfpocket_hostio — native host I/O either side of the CUDA hot path (SURVEY.md par. 8 row f1: "batched host I/O").
+ *
+ * The reference reads every input four times (rpdb_open + rpdb_read for pdb and for pdb_w_lig, src/fpmain.c:143-164) and
+ * writes ~2P+9 small files per structure through stdio and system() (src/fpout.c:55-134); neither is thread-safe
+ * (globals in memhandler.c, fparams.c:60). Once detection costs ~0.1 ms per structure that host code is the whole
+ * wall time (21 structures/s per process with the reference's reader and writers around libfpocket_cuda).
+ * This library restates the two ends for the default PDB route, re-entrantly, so that a pool of host threads keeps a GPU fed:
+ *
+ *   fpkio_read_pdb      = rpdb_open + rpdb_read, for BOTH atom lists in one pass over the file (src/rpdb.c:785-1478),
+ *                         + the flattening of s_pdb into fpk_structure (fpocket_b200/shim/search_pocket_cuda.c shim_job_prepare)
+ *   fpkio_write_output  = write_out_fpocket (src/fpout.c:55-134) with everything it calls: write_visualization
+ *                         (src/write_visu.c:56-290), write_pockets_single_pdb / _pqr, write_each_pocket, write_pocket_pqr / _pdb
+ *                         (src/writepocket.c:262-305,381-416,475-640), write_out_fpocket_info_file (src/fpout.c:151-213),
+ *                         the record formats of src/writepdb.c:78-216 and src/voronoi.c:1437-1557
+ *   fpkio_run_list      = the "-F list" loop (src/fpmain.c:61-76) as a three-stage pipeline: reader pool -> one
+ *                         fpk_detect_batch call per group of files -> writer pool
+ *
+ * Scope: PDB input, PDB-mode output (the reference's default for a .pdb input, fparams.c:397-407), chain filters -c / -k.
+ * Not restated (use build/fpocket_cuda_batch, which keeps the reference's reader and writers): mmCIF in or out, -a, -r, -P,
+ * -l, -d, -x. fpkio_* refuse those explicitly (FPKIO_ERR_UNSUPPORTED); nothing falls back silently.
+ *
+ * The library has no CUDA dependency of its own: the detection call is handed in (fpk_detect_batch in the product,
+ * build/fpocket_fast), so the CPU tests can drive the same pipeline with the oracle as the detector.
+ */
+#ifndef FPOCKET_HOSTIO_H
+#define FPOCKET_HOSTIO_H
+#include "fpocket_cuda.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPKIO_OK               0
+#define FPKIO_ERR_OPEN        (-1)   /* "! File %s does not exist" (rpdb.c:813) */
+#define FPKIO_ERR_NO_ATOMS    (-2)   /* "! File '%s' contains no atoms..." (rpdb.c:983) */
+#define FPKIO_ERR_UNSUPPORTED (-3)   /* input or option outside the restated route (see above) */
+#define FPKIO_ERR_WRITE       (-4)   /* an output directory or file could not be created */
+#define FPKIO_ERR_BAD_ARG     (-5)
+
+/* what the reference's s_fparams carries for the reader (fparams.h:182-227); zero-initialise for the defaults */
+typedef struct fpkio_read_opts {
+    int32_t n_chains;            /* -c / -k: number of chain names (<= 20)                     */
+    char chains[20][21];         /* chain names (compared with the one-character chain column) */
+    int32_t chains_are_kept;     /* 0: -c (drop these chains), 1: -k (keep only these)         */
+} fpkio_read_opts;
+
+typedef struct fpkio_file fpkio_file;      /* one parsed input: both atom lists + the flat arrays handed to the library */
+
+int  fpkio_read_pdb(const char *path, const fpkio_read_opts *opts, fpkio_file **out);
+/* same, from a buffer holding the file's bytes (the path is only kept for messages) */
+int  fpkio_read_pdb_mem(const char *path, const char *data, size_t size, const fpkio_read_opts *opts, fpkio_file **out);
+void fpkio_file_free(fpkio_file *f);
+const fpk_structure *fpkio_structure(const fpkio_file *f);       /* valid until fpkio_file_free */
+int  fpkio_natoms(const fpkio_file *f, int with_lig);            /* pdb->natoms / pdb_w_lig->natoms */
+int  fpkio_nhetatm(const fpkio_file *f, int with_lig);           /* pdb->nhetatm */
+/* text fields of atom k of pdb (with_lig = 0) or pdb_w_lig (1), as the reference's s_atm holds them; for tests.
+ * type[8] name[8] res_name[8] chain[4] symbol[4]; ints: id res_id charge; chars: insert aloc */
+int  fpkio_atom_text(const fpkio_file *f, int with_lig, int k, char *type, char *name, char *res_name, char *chain, char *symbol,
+                     int32_t *id_resid_charge, char *insert_aloc);
+
+/* write_out_fpocket(pockets, pdb, pdbname): <dir>/<code>_out/{<code>_out.pdb, _info.txt, _pockets.pqr, _VMD.sh, .tcl, _PYMOL.sh,
+ * .pml, pockets/pocketK_vert.pqr, pockets/pocketK_atm.pdb}. A result with no pocket left (FPK_ERR_NO_POCKETS) is written too, as the
+ * reference does with the empty list search_pocket returns (fpocket.c:225); only a failed clustering tree (FPK_ERR_NO_SPHERES) makes the
+ * caller print "no pockets found" (fpmain.c:204). Returns the number of pockets written or FPKIO_ERR_*. bytes_out (may be NULL) += bytes. */
+int  fpkio_write_output(const fpkio_file *f, const char *pdb_path, const fpk_result *r, long long *bytes_out);
+
+/* ---- the -F loop ------------------------------------------------------------------------------------------------------- */
+typedef int  (*fpkio_detect_fn)(const fpk_structure *in, int n, const fpk_params *p, fpk_result *out);   /* fpk_detect_batch */
+typedef void (*fpkio_free_fn)(fpk_result *r);                                                             /* fpk_result_free  */
+
+typedef struct fpkio_stats {
+    int32_t n_files, n_written, n_read_failed, n_no_pockets, n_detect_failed;
+    long long n_pockets, n_atoms, bytes_in, bytes_out;
+    double wall_s;                 /* whole call */
+    double read_cpu_s, write_cpu_s;/* summed over the pool's threads */
+    double detect_s;               /* wall time inside the detect callback, summed over groups */
+} fpkio_stats;
+
+/* paths[n]: PDB files. group: files per detect call (0 = 1024). io_threads: pool size (0 = hardware threads).
+ * quiet = 0 prints the reference's per-file messages. Per-file failures never abort the list. */
+int  fpkio_run_list(const char *const *paths, int n, const fpkio_read_opts *ropts, const fpk_params *p,
+                    fpkio_detect_fn detect, fpkio_free_fn free_result, int group, int io_threads, int quiet, fpkio_stats *stats);
+
+const char *fpkio_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
