@@ -53,6 +53,32 @@ def make_batch(nstruct, workers, first=0, ids=None):
     return raw
 
 
+_RAW = None
+
+
+def _pdb_one(job):
+    import synth
+    i, path = job
+    synth.to_pdb(_RAW[i], path)
+    return os.path.getsize(path)
+
+
+def write_pdb_files(raw, n, workers, tag):
+    """PDB files of the first n workload structures on tmpfs (before any CUDA state exists: the writers are forked)."""
+    global _RAW
+    d = tempfile.mkdtemp(prefix="fpkf2f_%s_" % tag, dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    jobs = [(i, os.path.join(d, "s%05d.pdb" % i)) for i in range(min(n, len(raw)))]
+    _RAW = raw
+    if workers > 1 and len(jobs) >= 64:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            sizes = pool.map(_pdb_one, jobs, chunksize=16)
+    else:
+        sizes = [_pdb_one(j) for j in jobs]
+    _RAW = None
+    return d, [j[1] for j in jobs], int(sum(sizes))
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -186,6 +212,7 @@ def main():
     ap.add_argument("--md-frames", type=int, default=2048, help="also measure mdpocket frames/s on a synthetic trajectory of this many frames per GPU (0: skip)")
     ap.add_argument("--dpocket", type=int, default=1000, help="also measure dpocket (BASELINE configs[4]): this many ligand-bound synthetic structures per GPU (0: skip)")
     ap.add_argument("--large", type=int, default=0, help="also time ONE synthetic complex of this many heavy atoms (BASELINE configs[3]: 150000) on rank 0")
+    ap.add_argument("--files", type=int, default=2000, help="also measure the file-to-file -F loop (native PDB reader -> fpk_detect_batch -> native writers) on this many workload structures per GPU (0: skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -240,6 +267,9 @@ def main():
         raw = make_batch(args.structures, workers, ids=mine)
     else:
         raw = make_batch(args.structures, workers)
+    f2f_dir = None
+    if args.files > 0:
+        f2f_dir, f2f_paths, f2f_bytes = write_pdb_files(raw, args.files, workers, "r%d" % rank)
     import torch
     from fpocket_b200 import api
     if not torch.cuda.is_available():
@@ -362,6 +392,42 @@ def main():
                       "structures_per_call": ne2e, "ok": int(ok), "steps": e2e_steps,
                       "note": "fpk_detect_batch() on host arrays: chunks of 512 structures through pack -> pinned H2D -> kernels -> pinned D2H -> unpack on 4 host "
                               "threads / CUDA streams; wall clock around the call, results freed inside the timed region"}
+
+    # ---- file to file: the -F loop on PDB files, native reader pool -> fpk_detect_batch -> native writer pool ---------
+    if f2f_dir is not None:
+        from fpocket_b200 import hostio
+        nf = len(f2f_paths)
+        io_threads = max(2, workers)
+        hostio.run_list(f2f_paths[: min(nf, 256)], p, group=128, io_threads=io_threads, quiet=1)       # warm-up (page cache, arenas, pool)
+        subprocess.call("rm -rf %s/*_out" % f2f_dir, shell=True)
+        barrier()
+        tf = time.perf_counter()
+        st = hostio.run_list(f2f_paths, p, group=1024, io_threads=io_threads, quiet=1)
+        barrier()
+        tf = time.perf_counter() - tf
+        ff = torch.tensor([tf], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(ff, op=dist.ReduceOp.MAX)
+        out["file_to_file"] = {"metric": "structures/sec", "value": nf * world / float(ff[0]), "files_per_gpu": nf, "written": st["n_written"],
+                               "pockets": st["n_pockets"], "io_threads": io_threads, "MB_in": st["bytes_in"] / 1e6, "MB_out": st["bytes_out"] / 1e6,
+                               "read_cpu_s": st["read_cpu_s"], "write_cpu_s": st["write_cpu_s"], "detect_s": st["detect_s"], "wall_s": tf,
+                               "includes": "PDB files on tmpfs -> fpkio_run_list (libfpocket_hostio: one-pass reader of both atom lists, groups of 1024 "
+                                           "through fpk_detect_batch, writers of the reference's <code>_out/ directory: _out.pdb, _info.txt, _pockets.pqr, "
+                                           "4 scripts, 2 files per pocket), byte-identical to the reference's writers (tests/test_hostio.py)"}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            bexe = os.path.join(ROOT, "build", "fpocket_cuda_batch")
+            if os.path.exists(bexe):
+                nb = min(nf, 64)
+                subprocess.call("rm -rf %s/*_out" % f2f_dir, shell=True)
+                with open(os.path.join(f2f_dir, "list64.txt"), "w") as f:
+                    f.write("".join(os.path.basename(q) + "\n" for q in f2f_paths[:nb]))
+                tb = time.time()
+                rcb = subprocess.call([bexe, "list64.txt"], cwd=f2f_dir, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                tb = time.time() - tb
+                out["file_to_file"]["reference_host_io"] = {"value": nb / tb if rcb == 0 else None, "unit": "structures/s",
+                                                            "sample": "first %d files through build/fpocket_cuda_batch: the reference's own reader and writers "
+                                                                      "(one thread, not re-entrant) around the same fpk_detect_batch; %.1f s incl. CUDA start-up" % (nb, tb)}
+        subprocess.call(["rm", "-rf", f2f_dir])
 
     # ---- optional: mdpocket frames/s with the grids summed over ranks (NCCL) ------------------------------------------------------
     if args.md_frames > 0:

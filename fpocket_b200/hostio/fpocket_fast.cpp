@@ -1,0 +1,93 @@
+// build/fpocket_fast: the reference's `fpocket -f X.pdb` / `fpocket -F list.txt` (src/fpmain.c:52-103) with NO reference object in it:
+// native PDB reader and writers (libfpocket_hostio) around libfpocket_cuda, as a three-stage pipeline
+//     reader pool  ->  one fpk_detect_batch per group of files  ->  writer pool.
+// It leaves, next to every input, the <code>_out/ directory `fpocket -f` writes (PDB mode, fparams.c:403-407).
+//
+//   fpocket_fast -f X.pdb | -F list.txt  [-m f] [-M f] [-D f] [-i n] [-A n] [-p f] [-v n] [-c A,B | -k A,B]
+//                [--threads T] [--group G] [--quiet] [--stats]
+//
+// Options outside the restated route (mmCIF input or -w m/b, -a, -r, -P, -l, -d, -x, -C != s, -e != e) are refused with a pointer to
+// build/fpocket_cuda_batch (reference reader / writers around the same library). There is no CPU detection path.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <string>
+#include <vector>
+
+#include "fpocket_hostio.h"
+
+static int refuse(const char *what)
+{
+    fprintf(stderr, "! fpocket_fast does not handle %s: use build/fpocket_cuda_batch (the reference's reader and writers on the same library)\n", what);
+    return 3;
+}
+
+int main(int argc, char **argv)
+{
+    fpk_params P;
+    fpk_default_params(&P);
+    fpkio_read_opts ro;
+    memset(&ro, 0, sizeof ro);
+    std::vector<std::string> files;
+    int threads = 0, group = 0, quiet = 0, want_stats = 0;
+    auto chains = [&](const char *arg, int kept) {                 // fparams.c:203-240: names separated by ',' or ':'
+        char tmp[512];
+        snprintf(tmp, sizeof tmp, "%s", arg);
+        ro.n_chains = 0;
+        for (char *t = strtok(tmp, ",:"); t && ro.n_chains < 20; t = strtok(nullptr, ",:")) snprintf(ro.chains[ro.n_chains++], 21, "%s", t);
+        ro.chains_are_kept = kept;
+    };
+    for (int a = 1; a < argc; a++) {
+        const std::string o = argv[a];
+        auto val = [&]() -> const char * { if (a + 1 >= argc) { fprintf(stderr, "! option %s needs a value\n", o.c_str()); exit(2); } return argv[++a]; };
+        if (o == "-f" || o == "--file") files.push_back(val());
+        else if (o == "-F" || o == "--fileList") {
+            const char *lp = val();
+            FILE *fl = fopen(lp, "r");
+            if (!fl) { fprintf(stderr, "! File %s doesn't exist\n", lp); return 2; }
+            char line[4096];
+            while (fgets(line, sizeof line, fl)) {
+                size_t L = strlen(line);
+                while (L && (line[L - 1] == '\n' || line[L - 1] == '\r' || line[L - 1] == ' ')) line[--L] = 0;
+                if (L) files.push_back(line);
+            }
+            fclose(fl);
+        }
+        else if (o == "-m" || o == "--min_alpha_size") P.asph_min_size = (float)atof(val());
+        else if (o == "-M" || o == "--max_alpha_size") P.asph_max_size = (float)atof(val());
+        else if (o == "-D" || o == "--clustering_distance") P.clust_max_dist = (float)atof(val());
+        else if (o == "-i" || o == "--min_spheres_per_pocket") P.min_pock_nb_asph = atoi(val());
+        else if (o == "-A" || o == "--number_apol_asph_pocket") P.min_apol_neigh = atoi(val());
+        else if (o == "-p" || o == "--ratio_apol_spheres_pocket") P.refine_min_apolar_asphere_prop = (float)atof(val());
+        else if (o == "-v" || o == "--iterations_volume_mc") P.nb_mcv_iter = atoi(val());
+        else if (o == "-c" || o == "--drop_chains") chains(val(), 0);
+        else if (o == "-k" || o == "--keep_chains") chains(val(), 1);
+        else if (o == "-C" || o == "--clustering_method") { if (val()[0] != 's') return refuse("-C other than s (single linkage)"); }
+        else if (o == "-e" || o == "--clustering_measure") { if (val()[0] != 'e') return refuse("-e other than e (euclidean)"); }
+        else if (o == "-w" || o == "--write_mode") { const char *w = val(); if (w[0] != 'p' && w[0] != 'd') return refuse("-w other than pdb"); }
+        else if (o == "--threads") threads = atoi(val());
+        else if (o == "--group") group = atoi(val());
+        else if (o == "--quiet") quiet = 1;
+        else if (o == "--stats") want_stats = 1;
+        else if (o == "-a" || o == "-r" || o == "-P" || o == "-l" || o == "-d" || o == "-x" || o == "-y" || o == "-u" || o == "-b") return refuse(o.c_str());
+        else { fprintf(stderr, "! unknown option %s\n", o.c_str()); return 2; }
+    }
+    if (files.empty()) { fprintf(stderr, "usage: %s -f X.pdb | -F list.txt [fpocket detection options] [--threads T] [--group G] [--quiet] [--stats]\n", argv[0]); return 2; }
+    for (const auto &f : files) if (strstr(f.c_str(), ".cif")) return refuse("mmCIF input");
+    P.mc_seed = (uint64_t)time(nullptr);                                       // voronoi.c:87 srand(time(NULL))
+    if (getenv("FPOCKET_MC_SEED")) P.mc_seed = strtoull(getenv("FPOCKET_MC_SEED"), nullptr, 10);
+    if (fpk_init(nullptr, 0) != FPK_OK) { fprintf(stderr, "! %s\n", fpk_last_error()); return 4; }
+    std::vector<const char *> paths;
+    for (const auto &f : files) paths.push_back(f.c_str());
+    fpkio_stats S;
+    const int rc = fpkio_run_list(paths.data(), (int)paths.size(), &ro, &P, fpk_detect_batch, fpk_result_free, group, threads, quiet, &S);
+    if (rc != FPKIO_OK) fprintf(stderr, "! fpk_detect_batch: %s\n", fpk_last_error());
+    if (want_stats)
+        printf("fpocket_fast: %d files, %d written (%lld pockets), %d unreadable, %d without pockets, %d failed | %.3f s wall, %.1f structures/s | "
+               "read %.3f cpu-s, detect %.3f s, write %.3f cpu-s | %.1f MB in, %.1f MB out\n",
+               S.n_files, S.n_written, S.n_pockets, S.n_read_failed, S.n_no_pockets, S.n_detect_failed, S.wall_s,
+               S.wall_s > 0 ? S.n_files / S.wall_s : 0.0, S.read_cpu_s, S.detect_s, S.write_cpu_s, S.bytes_in / 1e6, S.bytes_out / 1e6);
+    fpk_shutdown();
+    return (rc != FPKIO_OK || S.n_read_failed || S.n_detect_failed) ? 1 : 0;
+}

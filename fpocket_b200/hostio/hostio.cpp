@@ -117,6 +117,16 @@ void str_trim(char *s)                  // utils.c:518-531: blanks only
 const ElemRow *elem_lookup(const char *symbol)         // pte_get_vdw_ray / pte_get_enegativity: first row matching (upper, lower)
 {
     const char a0 = (char)toupper((unsigned char)symbol[0]), a1 = (char)tolower((unsigned char)symbol[1]);
+    if (a1 == 0) {                                     // the one-letter symbols, in table order (first match wins there too)
+        switch (a0) {
+        case 'C': return &ELEMENTS[6];
+        case 'N': return &ELEMENTS[7];
+        case 'O': return &ELEMENTS[8];
+        case 'S': return &ELEMENTS[16];
+        case 'H': return &ELEMENTS[1];
+        case 'P': return &ELEMENTS[15];
+        }
+    }
     for (const ElemRow &e : ELEMENTS) if (e.c0 == a0 && e.c1 == a1) return &e;
     return nullptr;
 }
@@ -227,10 +237,9 @@ struct fpkio_file {
 namespace {
 
 // rpdb_extract_pdb_atom (rpdb.c:262-352) on the persistent line buffer L
-void extract_atom(const char *L, AtomRec &a)
+void extract_atom(const char *L, int rlen, float x, float y, float z, AtomRec &a)
 {
     memset(&a, 0, sizeof a);
-    const int rlen = (int)strlen(L);
     slice_strncpy(a.type, L, 6);
     a.id = slice_atoi(L + 6, 5);
     slice_strncpy(a.name, L + 12, 4);
@@ -241,7 +250,7 @@ void extract_atom(const char *L, AtomRec &a)
     a.chain[0] = L[21];
     a.res_id = slice_atoi(L + 22, 4);
     a.insert = L[26];
-    a.x = slice_atof(L + 30, 8); a.y = slice_atof(L + 38, 8); a.z = slice_atof(L + 46, 8);
+    a.x = x; a.y = y; a.z = z;                        // the same slices parsed by the caller (rpdb_extract_atom_values, rpdb.c:632-648)
     a.occ = slice_atof(L + 54, 6); a.bf = slice_atof(L + 60, 6);
     if (rlen >= 77) {
         slice_strncpy(a.symbol, L + 76, 2);
@@ -277,9 +286,11 @@ int parse_pdb(const char *path, const char *data, size_t size, const fpkio_read_
     const char *p = data, *end = data + size;
     float x = 0, y = 0, z = 0;
     while (p < end) {
-        int n = 0;
-        while (n < LINE_MAX_CHARS && p < end) { const char c = *p++; L[n++] = c; if (c == '\n') break; }
+        size_t n = (size_t)(end - p) < (size_t)LINE_MAX_CHARS ? (size_t)(end - p) : (size_t)LINE_MAX_CHARS;
+        if (const void *nl = memchr(p, '\n', n)) n = (size_t)((const char *)nl - p) + 1;
+        memcpy(L, p, n);
         L[n] = 0;
+        p += n;
         const bool is_atom = !strncmp(L, "ATOM ", 5), is_het = !is_atom && !strncmp(L, "HETATM", 6);
         if (is_atom || is_het) {
             if (!chain_passes(opts, L[21])) continue;
@@ -296,7 +307,7 @@ int parse_pdb(const char *path, const char *data, size_t size, const fpkio_read_
                 if (!in_lig) continue;
             }
             F->watoms.emplace_back();
-            extract_atom(L, F->watoms.back());
+            extract_atom(L, (int)strlen(L), x, y, z, F->watoms.back());
             if (is_het) { F->nhet[1]++; if (in_nolig) F->nhet[0]++; }
             if (in_nolig) F->nolig.push_back((int32_t)F->watoms.size() - 1);
         } else if (!strncmp(L, "END", 3)) break;                 // rpdb.c:975, :1420 (model_flag == 0): ENDMDL ends the file too
@@ -362,23 +373,29 @@ bool read_whole(const char *path, std::string &buf)
 
 // ====================================================== writers =========================================================================
 struct Out {                            // one output file assembled in memory, written with one write()
-    std::string s;
-    void put(const char *t) { s.append(t); }
-    void put(const char *t, size_t n) { s.append(t, n); }
-    void ch(char c) { s.push_back(c); }
-    void pad(int n) { if (n > 0) s.append((size_t)n, ' '); }
-    void str_left(const char *t, int w) { const int l = (int)strlen(t); s.append(t, (size_t)l); pad(w - l); }       // %-Ns
-    void str_right(const char *t, int w) { const int l = (int)strlen(t); pad(w - l); s.append(t, (size_t)l); }      // %Ns
-    void integer(long long v, int w)                                                                                 // %Nd
+    std::vector<char> buf;
+    size_t n = 0;
+    char *room(size_t k) { if (n + k > buf.size()) buf.resize((n + k) * 2 + 4096); return buf.data() + n; }
+    void clear() { n = 0; }
+    const char *data() const { return buf.data(); }
+    size_t size() const { return n; }
+    void put(const char *t, size_t k) { memcpy(room(k), t, k); n += k; }
+    void put(const char *t) { put(t, strlen(t)); }
+    void put(const std::string &t) { put(t.data(), t.size()); }
+    void ch(char c) { *room(1) = c; n++; }
+    void pad(int k) { if (k > 0) { memset(room((size_t)k), ' ', (size_t)k); n += (size_t)k; } }
+    void str_left(const char *t, int w) { const int l = (int)strlen(t); put(t, (size_t)l); pad(w - l); }       // %-Ns
+    void str_right(const char *t, int w) { const int l = (int)strlen(t); pad(w - l); put(t, (size_t)l); }      // %Ns
+    void reversed(const char *b, int k, int w) { char *q = room((size_t)(k > w ? k : w)); int o = 0; for (; o < w - k; o++) q[o] = ' '; while (k) q[o++] = b[--k]; n += (size_t)o; }
+    void integer(long long v, int w)                                                                            // %Nd
     {
         char b[24];
-        int n = 0;
+        int k = 0;
         const bool neg = v < 0;
         unsigned long long u = neg ? (unsigned long long)(-v) : (unsigned long long)v;
-        do { b[n++] = (char)('0' + u % 10); u /= 10; } while (u);
-        if (neg) b[n++] = '-';
-        pad(w - n);
-        while (n) s.push_back(b[--n]);
+        do { b[k++] = (char)('0' + u % 10); u /= 10; } while (u);
+        if (neg) b[k++] = '-';
+        reversed(b, k, w);
     }
     // %W.Pf of a float-valued double. v * 10^P is exact in double for a 24-bit mantissa and P <= 4, so rounding it to the nearest integer
     // (ties to even) is what printf's exact decimal conversion prints; everything else goes through snprintf.
@@ -388,32 +405,31 @@ struct Out {                            // one output file assembled in memory, 
         const double av = std::fabs(v);
         if (!(av < 1e9) || prec > 4 || (double)(float)v != v) {
             char b[64];
-            const int n = snprintf(b, sizeof b, "%*.*f", w, prec, v);
-            s.append(b, (size_t)n);
+            const int k = snprintf(b, sizeof b, "%*.*f", w, prec, v);
+            put(b, (size_t)k);
             return;
         }
         unsigned long long q = (unsigned long long)std::nearbyint(av * P10[prec]);
         char b[32];
-        int n = 0;
-        for (int i = 0; i < prec; i++) { b[n++] = (char)('0' + q % 10); q /= 10; }
-        if (prec) b[n++] = '.';
-        do { b[n++] = (char)('0' + q % 10); q /= 10; } while (q);
-        if (std::signbit(v)) b[n++] = '-';
-        pad(w - n);
-        while (n) s.push_back(b[--n]);
+        int k = 0;
+        for (int i = 0; i < prec; i++) { b[k++] = (char)('0' + q % 10); q /= 10; }
+        if (prec) b[k++] = '.';
+        do { b[k++] = (char)('0' + q % 10); q /= 10; } while (q);
+        if (std::signbit(v)) b[k++] = '-';
+        reversed(b, k, w);
     }
     void fmt(const char *f, ...) __attribute__((format(printf, 2, 3)))
     {
         char b[512];
         va_list ap;
         va_start(ap, f);
-        const int n = vsnprintf(b, sizeof b, f, ap);
+        const int k = vsnprintf(b, sizeof b, f, ap);
         va_end(ap);
-        if (n > 0) s.append(b, (size_t)(n < (int)sizeof b ? n : (int)sizeof b - 1));
+        if (k > 0) put(b, (size_t)(k < (int)sizeof b ? k : (int)sizeof b - 1));
     }
 };
 
-bool write_file(const std::string &path, const std::string &data, mode_t mode, long long *bytes)
+bool write_file(const std::string &path, const Out &data, mode_t mode, long long *bytes)
 {
     int fd = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, mode);
     if (fd < 0) return false;
@@ -481,7 +497,7 @@ void pqr_sphere(Out &o, int i, bool apolar, int resid, const float *c)
 
 void substitute(Out &o, const char *tpl, const std::string &code)
 {
-    for (const char *q = tpl; *q; q++) if (*q == '\001') o.s.append(code); else o.s.push_back(*q);
+    for (const char *q = tpl; *q; q++) if (*q == '\001') o.put(code); else o.ch(*q);
 }
 
 }  // namespace
@@ -543,13 +559,13 @@ int fpkio_write_output(const fpkio_file *F, const char *pdb_path, const fpk_resu
     bool ok = true;
     Out o;
     // ---- write_visualization (write_visu.c:56-290) ----
-    o.s.clear(); substitute(o, TPL_VMD_SH, code);   ok &= write_file(base + "_VMD.sh", o.s, 0777, bytes_out);
-    o.s.clear(); substitute(o, TPL_TCL, code);      ok &= write_file(base + ".tcl", o.s, 0666, bytes_out);
-    o.s.clear(); substitute(o, TPL_PYMOL_SH, code); ok &= write_file(base + "_PYMOL.sh", o.s, 0777, bytes_out);
-    o.s.clear(); substitute(o, TPL_PML, code);      ok &= write_file(base + ".pml", o.s, 0666, bytes_out);
+    o.clear(); substitute(o, TPL_VMD_SH, code);   ok &= write_file(base + "_VMD.sh", o, 0777, bytes_out);
+    o.clear(); substitute(o, TPL_TCL, code);      ok &= write_file(base + ".tcl", o, 0666, bytes_out);
+    o.clear(); substitute(o, TPL_PYMOL_SH, code); ok &= write_file(base + "_PYMOL.sh", o, 0777, bytes_out);
+    o.clear(); substitute(o, TPL_PML, code);      ok &= write_file(base + ".pml", o, 0666, bytes_out);
     // ---- <code>_out.pdb: every atom of pdb, then the spheres pocket by pocket (writepocket.c:262-305, voronoi.c:1437-1482) ----
-    o.s.clear();
-    o.s.reserve((size_t)(n + R->n_spheres) * 82 + 256);
+    o.clear();
+    o.room((size_t)(n + R->n_spheres) * 82 + 256);
     for (int k = 0; k < n; k++) atom_line(o, F->watoms[F->nolig[k]], fx ? fx + 4 * (size_t)k : nullptr);
     for (int r = 0; r < R->n_pockets; r++) {
         const int c = R->rank_to_cluster[r];
@@ -562,9 +578,9 @@ int fpkio_write_output(const fpkio_file *F, const char *pdb_path, const fpk_resu
             else pdb_line(o, "HETATM", n + 1 + s, " POL", ' ', "STP", "C", r + 1, ' ', xyz[0], xyz[1], xyz[2], 0.0f, 0, "Ve", -1, 0.0f);   // s_vvertice.id as the shim numbers it
         }
     }
-    ok &= write_file(base + "_out.pdb", o.s, 0666, bytes_out);
+    ok &= write_file(base + "_out.pdb", o, 0666, bytes_out);
     // ---- <code>_info.txt (fpout.c:151-213) ----
-    o.s.clear();
+    o.clear();
     for (int r = 0; r < R->n_pockets; r++) {
         const int c = R->rank_to_cluster[r];
         const fpk_desc &d = R->desc[c];
@@ -590,9 +606,9 @@ int fpkio_write_output(const fpkio_file *F, const char *pdb_path, const fpk_resu
         o.put("\tFlexibility : \t"); o.fixed(d.flex, 0, 3); o.ch('\n');
         o.ch('\n');
     }
-    ok &= write_file(base + "_info.txt", o.s, 0666, bytes_out);
+    ok &= write_file(base + "_info.txt", o, 0666, bytes_out);
     // ---- <code>_pockets.pqr (writepocket.c:381-416): one running index over all pockets ----
-    o.s.clear();
+    o.clear();
     o.put("HEADER\n"
           "HEADER This is a pqr format file writen by the programm fpocket.                 \n"
           "HEADER It contains all the pocket vertices found by fpocket.                    \n");
@@ -604,7 +620,7 @@ int fpkio_write_output(const fpkio_file *F, const char *pdb_path, const fpk_resu
         }
     }
     o.put("TER\nEND\n");
-    ok &= write_file(base + "_pockets.pqr", o.s, 0666, bytes_out);
+    ok &= write_file(base + "_pockets.pqr", o, 0666, bytes_out);
     // ---- pockets/pocketK_vert.pqr, pockets/pocketK_atm.pdb (writepocket.c:475-640) ----
     const std::string pdir = out_dir + "/pockets";
     if (mkdir(pdir.c_str(), 0777) && errno != EEXIST) return FPKIO_ERR_WRITE;
@@ -614,7 +630,7 @@ int fpkio_write_output(const fpkio_file *F, const char *pdb_path, const fpk_resu
         const int c = R->rank_to_cluster[r];
         const fpk_desc &d = R->desc[c];
         const int first = R->cl_off[c], last = R->cl_off[c + 1];
-        o.s.clear();
+        o.clear();
         o.put("HEADER\n"
               "HEADER This is a pqr format file writen by the programm fpocket.                 \n"
               "HEADER It represent the voronoi vertices of a single pocket found by the         \n"
@@ -641,9 +657,9 @@ int fpkio_write_output(const fpkio_file *F, const char *pdb_path, const fpk_resu
         }
         o.put("TER\nEND\n");
         snprintf(nm, sizeof nm, "/pocket%d_vert.pqr", r + 1);
-        ok &= write_file(pdir + nm, o.s, 0666, bytes_out);
+        ok &= write_file(pdir + nm, o, 0666, bytes_out);
 
-        o.s.clear();
+        o.clear();
         o.put("HEADER\n"
               "HEADER This is a pdb format file writen by the programm fpocket.                 \n"
               "HEADER It represents the atoms contacted by the voronoi vertices of the pocket.  \n"
@@ -678,7 +694,7 @@ int fpkio_write_output(const fpkio_file *F, const char *pdb_path, const fpk_resu
         for (const int32_t k : uniq) atom_line(o, F->watoms[F->nolig[k]], fx ? fx + 4 * (size_t)k : nullptr);
         o.put("TER\nEND\n");
         snprintf(nm, sizeof nm, "/pocket%d_atm.pdb", r + 1);
-        ok &= write_file(pdir + nm, o.s, 0666, bytes_out);
+        ok &= write_file(pdir + nm, o, 0666, bytes_out);
     }
     return ok ? R->n_pockets : FPKIO_ERR_WRITE;
 }
@@ -755,15 +771,21 @@ extern "C" int fpkio_run_list(const char *const *paths, int n, const fpkio_read_
     bool detect_error = false;
     {
         Pool pool(io_threads);
-        // ---- detect thread: one fpk_detect_batch per group, in order of readiness; hands every structure to the writer pool ----
-        std::thread det([&] {
-            for (int done = 0; done < ngroups; done++) {
+        // ---- detect threads: one fpk_detect_batch per group, in order of readiness; every structure then goes to the writer pool.
+        // Two of them (fpk_detect_batch is re-entrant: pooled per-call contexts): while one call drains its last chunk the other one has
+        // its first chunks on the device, so the GPU does not idle at group boundaries.
+        int n_det = 2, taken = 0;
+        if (const char *e = getenv("FPKIO_DETECT_THREADS")) n_det = std::max(1, std::min(4, atoi(e)));
+        auto det_loop = [&] {
+            for (;;) {
                 Group *g;
                 {
                     std::unique_lock<std::mutex> lk(sm);
-                    scv.wait(lk, [&] { return !ready.empty(); });
+                    scv.wait(lk, [&] { return !ready.empty() || taken == ngroups; });
+                    if (ready.empty()) return;
                     g = ready.front();
                     ready.pop_front();
+                    if (++taken == ngroups) scv.notify_all();
                 }
                 for (int k = 0; k < g->n; k++)
                     if (g->rc[k] == FPKIO_OK) { g->in.push_back(*fpkio_structure(g->files[k])); g->idx.push_back(k); }
@@ -832,12 +854,14 @@ extern "C" int fpkio_run_list(const char *const *paths, int n, const fpkio_read_
                         if (g->pending.fetch_sub(1) == 1) retire();
                     }, true);
             }
-        });
-        // ---- this thread: keeps at most three groups in flight (one being read, one on the GPU, one being written) ----
+        };
+        std::vector<std::thread> det;
+        for (int t = 0; t < n_det; t++) det.emplace_back(det_loop);
+        // ---- this thread: bounds the groups in flight (being read, on the GPU, being written) ----
         for (int gi = 0; gi < ngroups; gi++) {
             {
                 std::unique_lock<std::mutex> lk(sm);
-                scv.wait(lk, [&] { return in_flight < 3; });
+                scv.wait(lk, [&] { return in_flight < 2 + n_det; });
                 in_flight++;
             }
             Group *g = new Group();
@@ -863,7 +887,7 @@ extern "C" int fpkio_run_list(const char *const *paths, int n, const fpkio_read_
                     }
                 }, false);
         }
-        det.join();
+        for (auto &t : det) t.join();
         {
             std::unique_lock<std::mutex> lk(sm);
             scv.wait(lk, [&] { return finished == ngroups; });

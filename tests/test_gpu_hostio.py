@@ -1,0 +1,82 @@
+"""GPU: build/fpocket_fast (native reader + libfpocket_cuda + native writers, fpocket_b200/hostio) must leave, file for file and byte
+for byte, what build/fpocket_cuda_batch leaves (the reference's OWN reader and writers around the same library) for the same list and
+the same Monte-Carlo seed; and the in-process pipeline (hostio.run_list on fpk_detect_batch) must equal both."""
+import os
+import subprocess
+
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+ROOT = O.ROOT
+FAST = os.path.join(ROOT, "build", "fpocket_fast")
+BATCH = os.path.join(ROOT, "build", "fpocket_cuda_batch")
+SEED = 515151
+
+
+def _tree(d):
+    out = {}
+    for root, _, files in os.walk(d):
+        for fn in files:
+            p = os.path.join(root, fn)
+            out[os.path.relpath(p, d)] = (open(p, "rb").read(), os.stat(p).st_mode & 0o777)
+    return out
+
+
+def _files(dirs, with_ligand=False):
+    import numpy as np
+    import synth
+    names = []
+    for i, n in enumerate((2050, 3300, 2600, 4100, 2200, 2900)):
+        s = synth.generate(20267700 + i, n, 0.065)
+        names.append("q%d.pdb" % i)
+        lig = None
+        if with_ligand and i % 2 == 0:          # HETATM records: kept in pdb_w_lig only (they shield surface points in the ASA pass)
+            rng = np.random.default_rng(i)
+            lig = s.xyz[rng.integers(0, s.n, 20)] + rng.normal(scale=2.5, size=(20, 3)).astype(np.float32)
+        for d in dirs:
+            synth.to_pdb(s, str(d / names[-1]), lig_xyz=lig)
+    return names
+
+
+@pytest.mark.parametrize("extra", [(), ("-m", "3.0", "-M", "6.5", "-D", "2.0", "-i", "20")])
+def test_fpocket_fast_equals_reference_io_around_the_library(tmp_path, extra):
+    if not os.path.exists(FAST):
+        pytest.skip("build/fpocket_fast not built")
+    if not os.path.exists(BATCH):
+        pytest.skip("build/fpocket_cuda_batch not built (needs the reference tree)")
+    da, db = tmp_path / "fast", tmp_path / "refio"
+    da.mkdir(), db.mkdir()
+    names = _files((da, db), with_ligand=True)
+    env = dict(os.environ, FPOCKET_MC_SEED=str(SEED), TMPDIR=str(tmp_path))
+    for d in (da, db):
+        (d / "list.txt").write_text("".join(nm + "\n" for nm in names))
+    out = subprocess.check_output([FAST, "-F", "list.txt", "--group", "4", "--threads", "3", "--stats", *extra], cwd=str(da), env=env).decode()
+    assert "6 files, 6 written" in out, out
+    subprocess.check_call([BATCH, "list.txt", *extra], cwd=str(db), env=env, stdout=subprocess.DEVNULL)
+    for nm in names:
+        code = nm[:-4]
+        a, b = _tree(str(da / (code + "_out"))), _tree(str(db / (code + "_out")))
+        assert sorted(a) == sorted(b) and len(a) >= 17, (code, sorted(set(a) ^ set(b)))
+        for k in a:
+            assert a[k][0] == b[k][0], "%s/%s differs" % (code, k)
+            assert a[k][1] == b[k][1], "%s/%s mode" % (code, k)
+
+
+def test_in_process_pipeline_on_the_library(tmp_path):
+    from fpocket_b200 import api, hostio
+    if not os.path.exists(FAST):
+        pytest.skip("build/fpocket_fast not built")
+    da, db = tmp_path / "exe", tmp_path / "inproc"
+    da.mkdir(), db.mkdir()
+    names = _files((da, db))
+    env = dict(os.environ, FPOCKET_MC_SEED=str(SEED))
+    subprocess.check_call([FAST] + sum((["-f", nm] for nm in names), []) + ["--quiet"], cwd=str(da), env=env)
+    p = api.default_params()
+    p.mc_seed = SEED
+    st = hostio.run_list([str(db / nm) for nm in names] + [str(db / "absent.pdb")], p, group=3, io_threads=4, quiet=1)
+    assert st["n_files"] == 7 and st["n_written"] == 6 and st["n_read_failed"] == 1 and st["n_pockets"] >= 60
+    for nm in names:
+        code = nm[:-4]
+        assert _tree(str(da / (code + "_out"))) == _tree(str(db / (code + "_out")))

