@@ -213,6 +213,7 @@ def main():
     ap.add_argument("--dpocket", type=int, default=1000, help="also measure dpocket (BASELINE configs[4]): this many ligand-bound synthetic structures per GPU (0: skip)")
     ap.add_argument("--large", type=int, default=0, help="also time ONE synthetic complex of this many heavy atoms (BASELINE configs[3]: 150000) on rank 0")
     ap.add_argument("--files", type=int, default=2000, help="also measure the file-to-file -F loop (native PDB reader -> fpk_detect_batch -> native writers) on this many workload structures per GPU (0: skip)")
+    ap.add_argument("--cores", type=int, default=0, help="after the workload is generated, pin this process to the first N cores (emulates the per-rank share of a busy multi-GPU box)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -270,6 +271,8 @@ def main():
     f2f_dir = None
     if args.files > 0:
         f2f_dir, f2f_paths, f2f_bytes = write_pdb_files(raw, args.files, workers, "r%d" % rank)
+    if args.cores > 0:
+        os.sched_setaffinity(0, set(range(args.cores)))
     import torch
     from fpocket_b200 import api
     if not torch.cuda.is_available():

@@ -111,6 +111,25 @@ static int ensure_init()
     return fpk_init(nullptr, 0);
 }
 
+// ---- how a host thread waits for its stream ---------------------------------------------------------------------------------------
+// cudaStreamSynchronize spins on a core until the device is done; FPK_SYNC=block waits on a cudaEventBlockingSync event instead (the
+// thread sleeps). Measured on one B200 with the process pinned to 2, 4 and 16 cores (4 library threads; profiles/README.md): e2e
+// 7,102 / 7,191 / 7,218 structures/s spinning, 7,191 / 7,233 / 7,239 blocking - the host threads are not what bounds the call, so
+// spinning stays the default and blocking is a knob for boxes where the cores are needed elsewhere.
+static bool block_sync()
+{
+    const char *e = getenv("FPK_SYNC");
+    return e && !strcmp(e, "block");
+}
+static cudaError_t wait_stream()
+{
+    if (!block_sync()) return cudaStreamSynchronize(cudaStreamPerThread);
+    static thread_local cudaEvent_t ev = nullptr;
+    if (!ev) { cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+    cudaError_t e = cudaEventRecord(ev, cudaStreamPerThread);
+    return e != cudaSuccess ? e : cudaEventSynchronize(ev);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 struct Arena {
     char *base = nullptr;
@@ -236,13 +255,14 @@ struct fpk_batch {
     float4 *c_xyzr = nullptr; float *c_bary = nullptr; int4 *c_neigh = nullptr; uint8_t *c_type = nullptr; int *c_cluster = nullptr;
     int *c_cl_sph = nullptr, *c_cl_off = nullptr;
     std::vector<int> h_counts, h_clbase, h_sbase;
+    int *pin_counts = nullptr; size_t pin_counts_cap = 0;      // pinned staging of the per-structure counts (read back without spinning)
     long long tot_spheres = 0, tot_clusters = 0, tot_tets = 0;
     // timing / accounting
     cudaEvent_t ev[8];
     float ms[8] = {0};
     long long launches = 0, h2d = 0, d2h = 0;
     bool events = false;
-    ~fpk_batch() { A1.release(); A2.release(); if (hin) cudaFreeHost(hin); if (events) for (auto &e : ev) cudaEventDestroy(e); }
+    ~fpk_batch() { A1.release(); A2.release(); if (hin) cudaFreeHost(hin); if (pin_counts) cudaFreeHost(pin_counts); if (events) for (auto &e : ev) cudaEventDestroy(e); }
 };
 
 static inline size_t sph_cap_for(const fpk_params &p, int nsites, double factor_override)
@@ -487,6 +507,7 @@ __global__ void k_compact(BatchDev B, const int *sbase, float4 *xyzr, float *bar
     for (int i = threadIdx.x; i <= nc; i += blockDim.x) cl_off[clbase[k] + k + i] = B.cl_off[S.sph_off + k + i];
 }
 
+static int fetch_counts(fpk_batch *b);
 static int batch_run(fpk_batch *b)
 {
     const int n = b->n;
@@ -503,9 +524,7 @@ static int batch_run(fpk_batch *b)
     CK(cudaEventRecord(b->ev[2]));
     b->launches += 2;
     // ---- the one host round trip: per-structure counts -> exact sizes of the pocket-level arrays -----------------------
-    b->h_counts.resize((size_t)n * CNT_STRIDE);
-    CK(cudaMemcpy(b->h_counts.data(), B.counts, sizeof(int) * (size_t)n * CNT_STRIDE, cudaMemcpyDeviceToHost));
-    b->d2h += (long long)sizeof(int) * n * CNT_STRIDE;
+    { int rcq = fetch_counts(b); if (rcq) return rcq; }
     b->h_clbase.assign(n + 1, 0); b->h_sbase.assign(n + 1, 0);
     int max_ns = 1;
     long long tt = 0;
@@ -576,13 +595,28 @@ static int batch_run(fpk_batch *b)
     k_compact<<<n, 128>>>(B, b->d_sbase, b->c_xyzr, b->c_bary, b->c_neigh, b->c_type, b->c_cluster, b->c_cl_sph, b->c_cl_off, b->d_clbase);
     b->launches++;
     CK(cudaEventRecord(b->ev[6]));
-    CK(cudaStreamSynchronize(cudaStreamPerThread));
+    // refresh counts (pockets / final status written by k_finalize); the wait inside is the end of the run
+    { int rcq = fetch_counts(b); if (rcq) return rcq; }
     CK(cudaGetLastError());
     for (int i = 0; i < 6; i++) cudaEventElapsedTime(&b->ms[i], b->ev[i], b->ev[i + 1]);
     cudaEventElapsedTime(&b->ms[7], b->ev[0], b->ev[6]);
-    // refresh counts (pockets / final status written by k_finalize)
-    CK(cudaMemcpy(b->h_counts.data(), B.counts, sizeof(int) * (size_t)n * CNT_STRIDE, cudaMemcpyDeviceToHost));
-    b->d2h += (long long)sizeof(int) * n * CNT_STRIDE;
+    return FPK_OK;
+}
+
+static int fetch_counts(fpk_batch *b)
+{
+    const size_t cnt = (size_t)b->n * CNT_STRIDE;
+    b->h_counts.resize(cnt);
+    if (cnt > b->pin_counts_cap) {
+        if (b->pin_counts) cudaFreeHost(b->pin_counts);
+        b->pin_counts = nullptr; b->pin_counts_cap = 0;
+        CK(cudaHostAlloc((void **)&b->pin_counts, sizeof(int) * (cnt + cnt / 4 + 64), cudaHostAllocDefault));
+        b->pin_counts_cap = cnt + cnt / 4 + 64;
+    }
+    CK(cudaMemcpyAsync(b->pin_counts, b->B.counts, sizeof(int) * cnt, cudaMemcpyDeviceToHost, cudaStreamPerThread));
+    CK(wait_stream());
+    memcpy(b->h_counts.data(), b->pin_counts, sizeof(int) * cnt);
+    b->d2h += (long long)(sizeof(int) * cnt);
     return FPK_OK;
 }
 
@@ -622,7 +656,7 @@ static int batch_fetch(fpk_batch *b, fpk_result *out)
         if ((rc = d2h(b, ilist, b->Lg.ilist, NA + n)) || (rc = d2h(b, crit, b->Lg.crit, 4 * NC)) ||
             (rc = d2h(b, b->h_ni.data(), b->Lg.ni, (size_t)n))) { delete H; return rc; }
     }
-    CK(cudaStreamSynchronize(cudaStreamPerThread));
+    CK(wait_stream());
     if (b->B.tets_out) {
         H->tets.resize(4 * (size_t)b->tot_tets + 4);
         size_t o = 0;
@@ -890,7 +924,7 @@ static int md_stage_chunk(fpk_md *m, int slot, const float *xyz, int nframes)
     if (bytes > m->stage_cap) return fail(FPK_ERR_BAD_ARG, "md staging buffer too small");
     memcpy(m->pin[slot], xyz, bytes);
     CK(cudaMemcpyAsync(m->d_xyz[slot], m->pin[slot], bytes, cudaMemcpyHostToDevice, cudaStreamPerThread));
-    CK(cudaStreamSynchronize(cudaStreamPerThread));
+    CK(wait_stream());
     return FPK_OK;
 }
 
