@@ -229,7 +229,7 @@ def load_library(path=None):
     """dlopen libfpocket_cuda.so. No fallback: a missing library is an error."""
     global _lib
     if _lib is None or path is not None:
-        p = path or LIB_PATH
+        p = path or os.environ.get("FPK_LIB") or LIB_PATH        # FPK_LIB: A/B experiments with kernel variants (scripts/)
         if not os.path.exists(p):
             raise RuntimeError(
                 "libfpocket_cuda.so not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'`. "

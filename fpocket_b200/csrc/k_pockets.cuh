@@ -246,11 +246,11 @@ __device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 96;" 
 //   warps 1..3 - surrounding atoms, the two SASA passes and the Monte-Carlo volume (integer counts: order-free).
 __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, PocketDev Pk, const DescScratch *scratch, int *work_counter)
 {
-    __shared__ int s_item, s_U, s_cnt[100], s_sm[40], s_segcnt[3], s_mcdim[4], s_mcmode;
+    __shared__ int s_item, s_U, s_cnt[100], s_sm[40], s_segcnt[3], s_mcdim[4], s_mcmode, s_asanext, s_mcnext;
     __shared__ float s_mcbox[6], s_mch[3], s_bb[3][6];
     __shared__ float4 s_sph[MC_SMEM_SPH];                  // (x, y, z, (ray-1.6)^2) of the pocket's spheres
     __shared__ int s_cell[MC_CELLS + 1];
-    __shared__ unsigned short s_ent[MC_ENTRIES];
+    __shared__ __align__(16) unsigned short s_ent[MC_ENTRIES];   // MC cell entries; in clusters without MC samples: warp 0's SASA candidates
     __shared__ float4 s_cand[3][ASA_CAND];                 // per worker warp: burial candidates of the current atom (x, y, z, radius)
     __shared__ unsigned char s_candapol[3][ASA_CAND];
     __shared__ fpk_desc s_desc;                            // warp 0's part of the record (everything but ASA / volume)
@@ -343,6 +343,7 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                 s_mcbox[0] = xmin; s_mcbox[1] = xmax; s_mcbox[2] = ymin; s_mcbox[3] = ymax; s_mcbox[4] = zmin; s_mcbox[5] = zmax;
             }
             for (int i = tid - 32; i < 100; i += K4_WORKERS) s_cnt[i] = 0;
+            if (tid == 33) { s_asanext = 0; s_mcnext = 0; }
         }
         __syncthreads();
         const int U = s_U;
@@ -362,10 +363,131 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
         for (int u = tid; u < 4 * U; u += nt) acc[u] = 0;
         __syncthreads();
 
+        // ---- work shared by all four warps once warp 0 is through with its sequential sums (3a): contacted atoms of the SASA pass and
+        // chunks of Monte-Carlo samples are handed out through two counters in shared memory; both only add integers, so who does what is free
+        const int seg = (nw + 2) / 3;                       // the three ordered segments of X.sa (one per worker warp)
+        auto asa_atom = [&](const int u, float4 *cand, unsigned char *candapol) {
+            const int cura = uat[u];
+            const float cx = B.ax[A0 + cura], cy = B.ay[A0 + cura], cz = B.az[A0 + cura], crad = B.arad[Q0 + cura];
+            // burial candidates: surrounding atoms close enough to bury a point of this atom at either probe, in sa order
+            const float reach = crad + 2.2f + 2.2f + 0.01f;
+            int ncand = 0;
+            bool overflow = false;
+            for (int sg = 0; sg < 3 && !overflow; sg++) {
+                const int s0 = min(nw, sg * seg), cnt = s_segcnt[sg];
+                for (int base = 0; base < cnt && !overflow; base += 32) {
+                    const int j = base + lane;
+                    bool take = false;
+                    int a = -1;
+                    float ax_ = 0, ay_ = 0, az_ = 0, ar_ = 0;
+                    if (j < cnt) {
+                        a = X.sa[s0 + j];
+                        if (!(same && a == cura)) {                 // asa.c:315 pointer inequality
+                            ax_ = wx[W0 + a]; ay_ = wy[W0 + a]; az_ = wz[W0 + a]; ar_ = wr[WQ0 + a];
+                            const float dx = ax_ - cx, dy = ay_ - cy, dz = az_ - cz, rr = reach + ar_;
+                            take = dx * dx + dy * dy + dz * dz <= rr * rr;
+                        }
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, take);
+                    if (ncand + __popc(bal) > ASA_CAND) { overflow = true; break; }
+                    if (take) {
+                        const int pos = ncand + __popc(bal & ((1u << lane) - 1u));
+                        cand[pos] = make_float4(ax_, ay_, az_, ar_);
+                        candapol[pos] = (double)we[WQ0 + a] < 2.8 ? 1 : 0;
+                    }
+                    ncand += __popc(bal);
+                }
+            }
+            __syncwarp();
+            for (int it = lane; it < 200; it += 32) {
+                const int pass = it >= 100 ? 1 : 0, kp = it - 100 * pass;
+                const double probe = pass == 0 ? 1.4 : 2.2;
+                const float tx = (float)((double)cx + (double)c_spiral[3 * kp] * ((double)crad + probe));
+                const float ty = (float)((double)cy + (double)c_spiral[3 * kp + 1] * ((double)crad + probe));
+                const float tz = (float)((double)cz + (double)c_spiral[3 * kp + 2] * ((double)crad + probe));
+                bool vref = true;                                   // "vrefburried": not inside any touching alpha sphere
+                for (int q = toff[u]; q < toff[u + 1] && vref; q++) {
+                    float4 v = sx[L[tlist[q]]];
+                    if (f_ddist(tx, ty, tz, v.x, v.y, v.z) <= v.w * v.w) vref = false;
+                }
+                if (vref) continue;
+                int hit = -1;       // -1 none, 0 polar burying atom, 1 apolar burying atom
+                if (!overflow) {
+                    for (int j = 0; j < ncand; j++) {
+                        const float4 q = cand[j];
+                        const float dsq = f_ddist(tx, ty, tz, q.x, q.y, q.z);
+                        const double rr = (double)q.w + probe;
+                        if ((double)dsq < rr * rr) { hit = candapol[j]; break; }
+                    }
+                } else {
+                    for (int sg = 0; sg < 3 && hit < 0; sg++) {
+                        const int s0 = min(nw, sg * seg), cnt = s_segcnt[sg];
+                        for (int j = 0; j < cnt; j++) {
+                            const int a = X.sa[s0 + j];
+                            if (same && a == cura) continue;
+                            const float dsq = f_ddist(tx, ty, tz, wx[W0 + a], wy[W0 + a], wz[W0 + a]);
+                            const double rr = (double)wr[WQ0 + a] + probe;
+                            if ((double)dsq < rr * rr) { hit = (double)we[WQ0 + a] < 2.8 ? 1 : 0; break; }
+                        }
+                    }
+                }
+                if (hit < 0) atomicAdd(&acc[4 * u + pass], 1);
+                else if (pass == 0) atomicAdd(&acc[4 * u + (hit ? 2 : 3)], 1);
+            }
+            __syncwarp();
+        };
+        auto mc_samples = [&]() {
+            const float xmin = s_mcbox[0], xmax = s_mcbox[1], ymin = s_mcbox[2], ymax = s_mcbox[3], zmin = s_mcbox[4], zmax = s_mcbox[5];
+            const int mode = s_mcmode;
+            const int dx = s_mcdim[0], dy = s_mcdim[1], dz = s_mcdim[2];
+            const float hx = s_mch[0], hy = s_mch[1], hz = s_mch[2];
+            const int niter = prm.nb_mcv_iter;
+            const unsigned k0 = (unsigned)prm.mc_seed, k1 = (unsigned)(prm.mc_seed >> 32);
+            const int total = 100 * niter;
+            for (;;) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_mcnext, 256);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= total) break;
+                const int stop = min(total, base + 256);
+                for (int s = base + lane; s < stop; s += 32) {
+                    const int li = s / niter, i = s - li * niter;
+                    unsigned o[4];
+                    philox4x32((unsigned)i, (unsigned)li, (unsigned)c, 0u, k0, k1, o);
+                    const float xr = unif_from_bits(o[0] >> 1, xmin, xmax), yr = unif_from_bits(o[1] >> 1, ymin, ymax),
+                                zr = unif_from_bits(o[2] >> 1, zmin, zmax);
+                    bool in = false;
+                    if (mode) {
+                        const int a = max(0, min(dx - 1, (int)floorf((xr - xmin) * hx))), b = max(0, min(dy - 1, (int)floorf((yr - ymin) * hy))),
+                                  d = max(0, min(dz - 1, (int)floorf((zr - zmin) * hz)));
+                        const int cid = (a * dy + b) * dz + d;
+                        const int e0 = cid ? s_cell[cid - 1] : 0, e1 = s_cell[cid];
+                        for (int j = e0; j < e1 && !in; j++) {
+                            const float4 v = s_sph[s_ent[j]];
+                            const float xt = v.x - xr, yt = v.y - yr, zt = v.z - zr;
+                            in = v.w > (xt * xt + yt * yt + zt * zt);
+                        }
+                    } else if (insm) {
+                        for (int j = 0; j < n && !in; j++) {
+                            const float4 v = s_sph[j];
+                            const float xt = v.x - xr, yt = v.y - yr, zt = v.z - zr;
+                            in = v.w > (xt * xt + yt * yt + zt * zt);
+                        }
+                    } else {
+                        for (int j = 0; j < n && !in; j++) {
+                            const float4 v = sx[L[j]];
+                            const float xt = v.x - xr, yt = v.y - yr, zt = v.z - zr;
+                            in = ((correct + v.w) * (v.w + correct)) > (xt * xt + yt * yt + zt * zt);
+                        }
+                    }
+                    if (in) atomicAdd(&s_cnt[li], 1);
+                }
+            }
+        };
         if (wid == 0) {
             // ---- 3a. warp 0: the sequential float sums, in the reference's order ---------------------------------------------------
             // sphere pair loop (descriptors.c:186-236): as_density accumulates dist(i,j), i<j, row-major, in ONE float
-            float as_density = 0.0f, as_max_dst = -1.0f;
+            float as_density = 0.0f, as_max_dst = -1.0f, lane_max = -1.0f;
             int mlhd_cnt = 0, nAlphaApol = 0;
             for (int i = 0; i < n; i++) {
                 const float4 vi = sx[L[i]];
@@ -385,15 +507,24 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                 for (int base = i + 1; base < n; base += 32) {
                     int j = base + lane;
                     float dj = 0.0f;
-                    if (j < n) { float4 vj = sx[L[j]]; dj = f_dist(vi.x, vi.y, vi.z, vj.x, vj.y, vj.z); }
-                    const int cntj = min(32, n - base);
-                    for (int q = 0; q < cntj; q++) {
-                        float dq = __shfl_sync(0xffffffffu, dj, q);
-                        if (dq > as_max_dst) as_max_dst = dq;
-                        as_density += dq;
+                    if (j < n) {
+                        float4 vj = sx[L[j]];
+                        dj = f_dist(vi.x, vi.y, vi.z, vj.x, vj.y, vj.z);
+                        lane_max = fmaxf(lane_max, dj);       // the maximum does not depend on the order: kept per lane, reduced once
+                    }
+                    // only the SUM is order-bound: one float, pairs in row-major order (descriptors.c:214)
+                    if (n - base >= 32) {
+#pragma unroll
+                        for (int q = 0; q < 32; q++) as_density += __shfl_sync(0xffffffffu, dj, q);
+                    } else {
+                        const int cntj = n - base;
+                        for (int q = 0; q < cntj; q++) as_density += __shfl_sync(0xffffffffu, dj, q);
                     }
                 }
             }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) lane_max = fmaxf(lane_max, __shfl_xor_sync(0xffffffffu, lane_max, d));
+            if (lane_max > as_max_dst) as_max_dst = lane_max;
             // atoms of the atom-based descriptors: the contacted atoms; for dpocket's explicit pocket the interface atoms (dpocket.c:350)
             const int *alist = explicit_pocket ? Pk.xp_ilist + S.atom_off + k : uat;
             const int UA = explicit_pocket ? Pk.xp_ni[k] : U;
@@ -456,121 +587,14 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                 d.as_max_r = as_max_r;
                 s_desc = d;
             }
+            if (full) {
+                // the workers have ARRIVED at barrier 2 once the surrounding atoms (X.sa) and the Monte-Carlo cell grid are in place; warp 0 waits for
+                // that only now, then takes samples (observable clusters) or contacted atoms (the rest: s_ent is idle there and holds its candidates)
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+            }
         } else if (full) {
-            // ---- 3b. warps 1..3: surrounding atoms (asa.c:84-112): heavy atoms of pdb_w_lig within ray+1 of a sphere, atom order ----
             const int wt = tid - 32, ww = wid - 1;
-            float bmn[3] = {3e38f, 3e38f, 3e38f}, bmx[3] = {-3e38f, -3e38f, -3e38f};
-            for (int i = wt; i < n; i += K4_WORKERS) {
-                float4 v = sx[L[i]];
-                float rp = v.w + 1.01f;
-                bmn[0] = fminf(bmn[0], v.x - rp); bmn[1] = fminf(bmn[1], v.y - rp); bmn[2] = fminf(bmn[2], v.z - rp);
-                bmx[0] = fmaxf(bmx[0], v.x + rp); bmx[1] = fmaxf(bmx[1], v.y + rp); bmx[2] = fmaxf(bmx[2], v.z + rp);
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1)
-#pragma unroll
-                for (int q = 0; q < 3; q++) {
-                    bmn[q] = fminf(bmn[q], __shfl_xor_sync(0xffffffffu, bmn[q], d));
-                    bmx[q] = fmaxf(bmx[q], __shfl_xor_sync(0xffffffffu, bmx[q], d));
-                }
-            if (lane == 0) for (int q = 0; q < 3; q++) { s_bb[ww][q] = bmn[q]; s_bb[ww][3 + q] = bmx[q]; }
-            workers_sync();
-            for (int w = 0; w < 3; w++)
-                for (int q = 0; q < 3; q++) { bmn[q] = fminf(bmn[q], s_bb[w][q]); bmx[q] = fmaxf(bmx[q], s_bb[w][3 + q]); }
-            // every worker warp scans one contiguous third of the atoms and appends, in order, to its own segment of X.sa
-            const int seg = (nw + 2) / 3, a_lo = min(nw, ww * seg), a_hi = min(nw, a_lo + seg);
-            int nseg = 0;
-            for (int base = a_lo; base < a_hi; base += 32) {
-                const int i = base + lane;
-                bool in = false;
-                if (i < a_hi && !(wf[WQ0 + i] & whmask)) {
-                    const float x = wx[W0 + i], y = wy[W0 + i], z = wz[W0 + i];
-                    if (x >= bmn[0] && x <= bmx[0] && y >= bmn[1] && y <= bmx[1] && z >= bmn[2] && z <= bmx[2]) {
-                        for (int q = 0; q < n && !in; q++) {
-                            const float4 v = sx[L[q]];
-                            const double rp = (double)v.w + 1.0;
-                            in = (double)f_ddist(x, y, z, v.x, v.y, v.z) < rp * rp;
-                        }
-                    }
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, in);
-                if (in) X.sa[a_lo + nseg + __popc(bal & ((1u << lane) - 1u))] = i;
-                nseg += __popc(bal);
-            }
-            if (lane == 0) s_segcnt[ww] = nseg;
-            workers_sync();
-            // ---- 4. 100-point spiral SASA, probes 1.4 and 2.2 (asa.c:240-419): one warp per contacted atom ----------------------------
-            for (int u = ww; u < U; u += 3) {
-                const int cura = uat[u];
-                const float cx = B.ax[A0 + cura], cy = B.ay[A0 + cura], cz = B.az[A0 + cura], crad = B.arad[Q0 + cura];
-                // burial candidates: surrounding atoms close enough to bury a point of this atom at either probe, in sa order
-                const float reach = crad + 2.2f + 2.2f + 0.01f;
-                int ncand = 0;
-                bool overflow = false;
-                for (int sg = 0; sg < 3 && !overflow; sg++) {
-                    const int s0 = min(nw, sg * seg), cnt = s_segcnt[sg];
-                    for (int base = 0; base < cnt && !overflow; base += 32) {
-                        const int j = base + lane;
-                        bool take = false;
-                        int a = -1;
-                        float ax_ = 0, ay_ = 0, az_ = 0, ar_ = 0;
-                        if (j < cnt) {
-                            a = X.sa[s0 + j];
-                            if (!(same && a == cura)) {                 // asa.c:315 pointer inequality
-                                ax_ = wx[W0 + a]; ay_ = wy[W0 + a]; az_ = wz[W0 + a]; ar_ = wr[WQ0 + a];
-                                const float dx = ax_ - cx, dy = ay_ - cy, dz = az_ - cz, rr = reach + ar_;
-                                take = dx * dx + dy * dy + dz * dz <= rr * rr;
-                            }
-                        }
-                        const unsigned bal = __ballot_sync(0xffffffffu, take);
-                        if (ncand + __popc(bal) > ASA_CAND) { overflow = true; break; }
-                        if (take) {
-                            const int pos = ncand + __popc(bal & ((1u << lane) - 1u));
-                            s_cand[ww][pos] = make_float4(ax_, ay_, az_, ar_);
-                            s_candapol[ww][pos] = (double)we[WQ0 + a] < 2.8 ? 1 : 0;
-                        }
-                        ncand += __popc(bal);
-                    }
-                }
-                __syncwarp();
-                for (int it = lane; it < 200; it += 32) {
-                    const int pass = it >= 100 ? 1 : 0, kp = it - 100 * pass;
-                    const double probe = pass == 0 ? 1.4 : 2.2;
-                    const float tx = (float)((double)cx + (double)c_spiral[3 * kp] * ((double)crad + probe));
-                    const float ty = (float)((double)cy + (double)c_spiral[3 * kp + 1] * ((double)crad + probe));
-                    const float tz = (float)((double)cz + (double)c_spiral[3 * kp + 2] * ((double)crad + probe));
-                    bool vref = true;                                   // "vrefburried": not inside any touching alpha sphere
-                    for (int q = toff[u]; q < toff[u + 1] && vref; q++) {
-                        float4 v = sx[L[tlist[q]]];
-                        if (f_ddist(tx, ty, tz, v.x, v.y, v.z) <= v.w * v.w) vref = false;
-                    }
-                    if (vref) continue;
-                    int hit = -1;       // -1 none, 0 polar burying atom, 1 apolar burying atom
-                    if (!overflow) {
-                        for (int j = 0; j < ncand; j++) {
-                            const float4 q = s_cand[ww][j];
-                            const float dsq = f_ddist(tx, ty, tz, q.x, q.y, q.z);
-                            const double rr = (double)q.w + probe;
-                            if ((double)dsq < rr * rr) { hit = s_candapol[ww][j]; break; }
-                        }
-                    } else {
-                        for (int sg = 0; sg < 3 && hit < 0; sg++) {
-                            const int s0 = min(nw, sg * seg), cnt = s_segcnt[sg];
-                            for (int j = 0; j < cnt; j++) {
-                                const int a = X.sa[s0 + j];
-                                if (same && a == cura) continue;
-                                const float dsq = f_ddist(tx, ty, tz, wx[W0 + a], wy[W0 + a], wz[W0 + a]);
-                                const double rr = (double)wr[WQ0 + a] + probe;
-                                if ((double)dsq < rr * rr) { hit = (double)we[WQ0 + a] < 2.8 ? 1 : 0; break; }
-                            }
-                        }
-                    }
-                    if (hit < 0) atomicAdd(&acc[4 * u + pass], 1);
-                    else if (pass == 0) atomicAdd(&acc[4 * u + (hit ? 2 : 3)], 1);
-                }
-                __syncwarp();
-            }
-            // ---- 5. Monte-Carlo volume (voronoi.c:1150-1233), radius ray-1.6, 100 x nb_mcv_iter samples ------------------------------
+            // ---- 5a. Monte-Carlo cell grid first (voronoi.c:1150-1233 samples come later): warp 0 may start sampling while the workers are in the SASA pass ----
             if (observable) {
                 const float xmin = s_mcbox[0], xmax = s_mcbox[1], ymin = s_mcbox[2], ymax = s_mcbox[3], zmin = s_mcbox[4], zmax = s_mcbox[5];
                 // cell grid over the box: a sample only meets the spheres registered in its cell (the test is an OR: order-free)
@@ -624,83 +648,111 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                     // after the fill, s_cell[c] = END of cell c; start = end of cell c-1
                 }
                 workers_sync();
-                const int mode = s_mcmode;
-                const int dx = s_mcdim[0], dy = s_mcdim[1], dz = s_mcdim[2];
-                const float hx = s_mch[0], hy = s_mch[1], hz = s_mch[2];
-                const int niter = prm.nb_mcv_iter;
-                const unsigned k0 = (unsigned)prm.mc_seed, k1 = (unsigned)(prm.mc_seed >> 32);
-                for (int s = wt; s < 100 * niter; s += K4_WORKERS) {
-                    const int li = s / niter, i = s - li * niter;
-                    unsigned o[4];
-                    philox4x32((unsigned)i, (unsigned)li, (unsigned)c, 0u, k0, k1, o);
-                    const float xr = unif_from_bits(o[0] >> 1, xmin, xmax), yr = unif_from_bits(o[1] >> 1, ymin, ymax),
-                                zr = unif_from_bits(o[2] >> 1, zmin, zmax);
-                    bool in = false;
-                    if (mode) {
-                        const int a = max(0, min(dx - 1, (int)floorf((xr - xmin) * hx))), b = max(0, min(dy - 1, (int)floorf((yr - ymin) * hy))),
-                                  d = max(0, min(dz - 1, (int)floorf((zr - zmin) * hz)));
-                        const int cid = (a * dy + b) * dz + d;
-                        const int e0 = cid ? s_cell[cid - 1] : 0, e1 = s_cell[cid];
-                        for (int j = e0; j < e1 && !in; j++) {
-                            const float4 v = s_sph[s_ent[j]];
-                            const float xt = v.x - xr, yt = v.y - yr, zt = v.z - zr;
-                            in = v.w > (xt * xt + yt * yt + zt * zt);
-                        }
-                    } else if (insm) {
-                        for (int j = 0; j < n && !in; j++) {
-                            const float4 v = s_sph[j];
-                            const float xt = v.x - xr, yt = v.y - yr, zt = v.z - zr;
-                            in = v.w > (xt * xt + yt * yt + zt * zt);
-                        }
-                    } else {
-                        for (int j = 0; j < n && !in; j++) {
-                            const float4 v = sx[L[j]];
-                            const float xt = v.x - xr, yt = v.y - yr, zt = v.z - zr;
-                            in = ((correct + v.w) * (v.w + correct)) > (xt * xt + yt * yt + zt * zt);
+            }
+            // ---- 3b. warps 1..3: surrounding atoms (asa.c:84-112): heavy atoms of pdb_w_lig within ray+1 of a sphere, atom order ----
+            float bmn[3] = {3e38f, 3e38f, 3e38f}, bmx[3] = {-3e38f, -3e38f, -3e38f};
+            for (int i = wt; i < n; i += K4_WORKERS) {
+                float4 v = sx[L[i]];
+                float rp = v.w + 1.01f;
+                bmn[0] = fminf(bmn[0], v.x - rp); bmn[1] = fminf(bmn[1], v.y - rp); bmn[2] = fminf(bmn[2], v.z - rp);
+                bmx[0] = fmaxf(bmx[0], v.x + rp); bmx[1] = fmaxf(bmx[1], v.y + rp); bmx[2] = fmaxf(bmx[2], v.z + rp);
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1)
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    bmn[q] = fminf(bmn[q], __shfl_xor_sync(0xffffffffu, bmn[q], d));
+                    bmx[q] = fmaxf(bmx[q], __shfl_xor_sync(0xffffffffu, bmx[q], d));
+                }
+            if (lane == 0) for (int q = 0; q < 3; q++) { s_bb[ww][q] = bmn[q]; s_bb[ww][3 + q] = bmx[q]; }
+            workers_sync();
+            for (int w = 0; w < 3; w++)
+                for (int q = 0; q < 3; q++) { bmn[q] = fminf(bmn[q], s_bb[w][q]); bmx[q] = fmaxf(bmx[q], s_bb[w][3 + q]); }
+            // every worker warp scans one contiguous third of the atoms and appends, in order, to its own segment of X.sa
+            const int a_lo = min(nw, ww * seg), a_hi = min(nw, a_lo + seg);
+            int nseg = 0;
+            for (int base = a_lo; base < a_hi; base += 32) {
+                const int i = base + lane;
+                bool in = false;
+                if (i < a_hi && !(wf[WQ0 + i] & whmask)) {
+                    const float x = wx[W0 + i], y = wy[W0 + i], z = wz[W0 + i];
+                    if (x >= bmn[0] && x <= bmx[0] && y >= bmn[1] && y <= bmx[1] && z >= bmn[2] && z <= bmx[2]) {
+                        for (int q = 0; q < n && !in; q++) {
+                            const float4 v = sx[L[q]];
+                            const double rp = (double)v.w + 1.0;
+                            in = (double)f_ddist(x, y, z, v.x, v.y, v.z) < rp * rp;
                         }
                     }
-                    if (in) atomicAdd(&s_cnt[li], 1);
                 }
+                const unsigned bal = __ballot_sync(0xffffffffu, in);
+                if (in) X.sa[a_lo + nseg + __popc(bal & ((1u << lane) - 1u))] = i;
+                nseg += __popc(bal);
             }
+            if (lane == 0) s_segcnt[ww] = nseg;
+            workers_sync();
+            __threadfence_block();
+            asm volatile("bar.arrive 2, 128;" ::: "memory");          // lets warp 0 in (it may still be busy with its sums: nobody waits for it here)
+        }
+        if (full) {
+            // all four warps from here (warp 0 as soon as its sums are done and the workers have arrived at barrier 2)
+            // ---- 4. 100-point spiral SASA, probes 1.4 and 2.2 (asa.c:240-419): one warp per contacted atom ----------------------------
+            // warp 0 keeps its candidates in s_ent, which is idle in clusters without Monte-Carlo samples; in the others it goes straight to the samples
+            float4 *cand = wid ? s_cand[wid - 1] : reinterpret_cast<float4 *>(s_ent);
+            unsigned char *candapol = wid ? s_candapol[wid - 1] : reinterpret_cast<unsigned char *>(s_ent) + sizeof(float4) * ASA_CAND;
+            if (wid || !observable)
+                for (;;) {
+                    int u = 0;
+                    if (lane == 0) u = atomicAdd(&s_asanext, 1);
+                    u = __shfl_sync(0xffffffffu, u, 0);
+                    if (u >= U) break;
+                    asa_atom(u, cand, candapol);
+                }
+            // ---- 5. Monte-Carlo volume (voronoi.c:1150-1233), radius ray-1.6, 100 x nb_mcv_iter samples ------------------------------
+            if (observable) mc_samples();
         }
         __syncthreads();
 
-        // ---- 6. the ASA / volume part of the record (needs the workers' counts) -- one thread ----------------------------------------
+        // ---- 6. the ASA / volume part of the record (needs the counts of all four warps) ----------------------------------------------
+        // 6a. per contacted atom, all threads: the two areas (asa.c:330,384: an f64 expression rounded to f32) and the per-atom side effects
+        //     (abpa_sourrounding_prob, a0, dA, abpa: asa.c:337,392-396). The areas replace the counts in acc[4u], acc[4u+1] (as float bits);
+        //     acc[4u+2] keeps the polarity of the atom for 6b.
+        if (full) {
+            for (int u = tid; u < U; u += nt) {
+                const int a = Q0 + uat[u];
+                const size_t ga = (size_t)A0 + uat[u];       // per-structure slot for the side effects
+                const float crad = B.arad[a];
+                const bool apolar_atom = (double)B.aen[a] < 2.8;
+                const float a14 = (float)((4 * 3.1415926535897932384626433832795 * ((double)crad + 1.4) * ((double)crad + 1.4) / (double)(float)100) * (double)acc[4 * u]);
+                const float a22 = (float)((4 * 3.1415926535897932384626433832795 * ((double)crad + 2.2) * ((double)crad + 2.2) / (double)(float)100) * (double)acc[4 * u + 1]);
+                const float na = (float)acc[4 * u + 2], np = (float)acc[4 * u + 3];
+                fxv[4 * u + 0] = na / (na + np);             // abpa_sourrounding_prob
+                fxv[4 * u + 1] = a14;                        // abpatmp
+                float flag = 0.0f;
+                if (!explicit_pocket) atomicMax(&Pk.fx_who[2 * ga], c);
+                if (!apolar_atom && a22 < a14 && (double)a14 <= 10.0 && (double)a22 >= 0.0) {
+                    fxv[4 * u + 2] = a22 - a14;              // dA ; a0 = a14
+                    flag = 1.0f;
+                    if (!explicit_pocket) atomicMax(&Pk.fx_who[2 * ga + 1], c);
+                }
+                fxv[4 * u + 3] = flag;
+                acc[4 * u] = __float_as_int(a14); acc[4 * u + 1] = __float_as_int(a22); acc[4 * u + 2] = apolar_atom ? 1 : 0; acc[4 * u + 3] = (int)flag;
+            }
+        }
+        __syncthreads();
+        // 6b. one thread: only the float sums whose order is the reference's (atoms in first-seen order, probe 1.4 then 2.2)
         if (tid == 0) {
             fpk_desc d = s_desc;
             if (full) {
-                for (int pass = 0; pass < 2; pass++) {
-                    const double probe = pass == 0 ? 1.4 : 2.2;
-                    for (int u = 0; u < U; u++) {
-                        const int a = Q0 + uat[u];
-                        const size_t ga = (size_t)A0 + uat[u];       // per-structure slot for the side effects
-                        const float crad = B.arad[a];
-                        const int nnb = acc[4 * u + pass];
-                        const float area = (float)((4 * 3.1415926535897932384626433832795 * ((double)crad + probe) * ((double)crad + probe) / (double)(float)100) * (double)nnb);
-                        const bool apolar_atom = (double)B.aen[a] < 2.8;
-                        if (pass == 0) {
-                            fxv[4 * u + 1] = area;              // abpatmp
-                            if (apolar_atom) d.surf_apol_vdw14 = d.surf_apol_vdw14 + area; else d.surf_pol_vdw14 = d.surf_pol_vdw14 + area;
-                            d.surf_vdw14 = d.surf_vdw14 + area;
-                            const float na = (float)acc[4 * u + 2], np = (float)acc[4 * u + 3];
-                            fxv[4 * u + 0] = na / (na + np);     // abpa_sourrounding_prob
-                            fxv[4 * u + 3] = 0.0f;
-                            if (!explicit_pocket) atomicMax(&Pk.fx_who[2 * ga], c);
-                        } else {
-                            if (apolar_atom) d.surf_apol_vdw22 = d.surf_apol_vdw22 + area;
-                            else {
-                                const float a14 = fxv[4 * u + 1];
-                                if (area < a14 && (double)a14 <= 10.0 && (double)area >= 0.0) {
-                                    d.n_abpa += 1;
-                                    fxv[4 * u + 2] = area - a14;   // dA ; a0 = a14
-                                    fxv[4 * u + 3] = 1.0f;
-                                    if (!explicit_pocket) atomicMax(&Pk.fx_who[2 * ga + 1], c);
-                                }
-                                d.surf_pol_vdw22 = d.surf_pol_vdw22 + area;
-                            }
-                            d.surf_vdw22 = d.surf_vdw22 + area;
-                        }
-                    }
+                for (int u = 0; u < U; u++) {
+                    const float area = __int_as_float(acc[4 * u]);
+                    if (acc[4 * u + 2]) d.surf_apol_vdw14 = d.surf_apol_vdw14 + area; else d.surf_pol_vdw14 = d.surf_pol_vdw14 + area;
+                    d.surf_vdw14 = d.surf_vdw14 + area;
+                }
+                for (int u = 0; u < U; u++) {
+                    const float area = __int_as_float(acc[4 * u + 1]);
+                    if (acc[4 * u + 2]) d.surf_apol_vdw22 = d.surf_apol_vdw22 + area;
+                    else { d.n_abpa += acc[4 * u + 3]; d.surf_pol_vdw22 = d.surf_pol_vdw22 + area; }
+                    d.surf_vdw22 = d.surf_vdw22 + area;
                 }
                 const float vbox = (s_mcbox[1] - s_mcbox[0]) * (s_mcbox[3] - s_mcbox[2]) * (s_mcbox[5] - s_mcbox[4]);
                 float sum_volume = 0.0f;
