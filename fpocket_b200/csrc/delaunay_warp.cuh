@@ -114,11 +114,14 @@ __device__ __noinline__ int insphere_sos_slow(const int *Pi, int v0, int v1, int
     if (r) return r;
     int v[4] = {v0, v1, v2, v3};
     int idx[5] = {v0, v1, v2, v3, p};
+#pragma unroll 1   // measured: the compiler's own unrolling of this loop costs the hull kernel 14 % (profiles/README.md)
     for (int i = 1; i < 5; i++) {
         int k = idx[i], j = i - 1;
+#pragma unroll 1
         while (j >= 0 && idx[j] > k) { idx[j + 1] = idx[j]; j--; }
         idx[j + 1] = k;
     }
+#pragma unroll 1
     for (int i = 4; i > 0; i--) {
         int q = idx[i], o;
         if (q == p) return -1;
@@ -216,6 +219,7 @@ template <bool SM> __device__ __noinline__ int w2_locate_and_claim(int rank, int
     if (t < 0) t = S.cnt[C_RECENT];
     int4 v, nb;
     int dead = 0;
+#pragma unroll 1
     for (int steps = 0;; steps++) {         // visibility walk: the four face tests of a step run on four lanes
         v = *reinterpret_cast<const int4 *>(TVp(t));
         nb = *reinterpret_cast<const int4 *>(TNp(t));
@@ -268,6 +272,7 @@ template <bool SM> __device__ __noinline__ int w2_locate_and_claim(int rank, int
     int ncav = 1, nlev = 0, qhead = 0, qtail = 4;
     if (lane < 4) W.fq[lane] = (unsigned char)lane;
     __syncwarp();
+#pragma unroll 1
     while (qhead < qtail) {                 // breadth-first over FACES: up to 32 untested faces of the cavity per step, one per lane
         const int room = WCAV - ncav;                                   // every claimed tet must fit in the list (the reset walks it)
         if (room < 1) { *ncav_out = ncav; return ST_BIG; }
@@ -327,6 +332,7 @@ __device__ __forceinline__ bool w2_verify_claims(int rank, int ncav)
     __builtin_assume(__isGlobal(claim));
     const int lane = threadIdx.x & 31, prio = prio_of(rank), q = lane & 3;
     bool ok = true;
+#pragma unroll 1
     for (int base = 0; base < ncav; base += 8) {
         const int f = base + (lane >> 2);
         if (f < ncav) {
@@ -343,6 +349,7 @@ __device__ __forceinline__ void w2_reset_claims(int ncav)
     int *const claim = blk().C.claim;
     __builtin_assume(__isGlobal(claim));
     const int lane = threadIdx.x & 31, q = lane & 3;
+#pragma unroll 1
     for (int base = 0; base < ncav; base += 8) {
         const int f = base + (lane >> 2);
         if (f < ncav) {
@@ -364,11 +371,13 @@ __device__ __noinline__ int w2_commit_insertion(int rank, int ncav, int popstack
     __builtin_assume(__isGlobal(popst)); __builtin_assume(__isGlobal(pushst)); __builtin_assume(__isGlobal(c.order));
     const int lane = threadIdx.x & 31;
     const int p = c.order[rank];
+#pragma unroll 1
     for (int i = lane; i < WHASH; i += 32) { W.hkey[i] = FPK_HEMPTY; W.hval[i] = -1; }
     __syncwarp();
     int mynew = 0x7fffffff, nrim = 0;
     bool bad = false;
     // ---- pass A: one new tet per rim face (slots allocated warp-wide), outside adjacency both ways ----------------------------------
+#pragma unroll 1
     for (int base = 0; base < 4 * ncav; base += 32) {
         const int e = base + lane, f = e >> 2, q = e & 3;
         const bool isrim = e < 4 * ncav && W.rf[e];
@@ -422,6 +431,7 @@ __device__ __noinline__ int w2_commit_insertion(int rank, int ncav, int popstack
     const int firstnew = mynew;
     __syncwarp();
     // ---- pass B: one lane per (new tet, face through p): twins meet through the edge hash ---------------------------------------------
+#pragma unroll 1
     for (int it = lane; it < 3 * nrim; it += 32) {
         const int ri = it / 3, jj = it - 3 * ri;
         const int e = W.rl[ri], f = e >> 2, q = e & 3;
@@ -432,6 +442,7 @@ __device__ __noinline__ int w2_commit_insertion(int rank, int ncav, int popstack
         const unsigned lo = (unsigned)(min(a, b) + 1), hi = (unsigned)(max(a, b) + 1);
         const unsigned long long key = ((unsigned long long)lo << 32) | hi;
         unsigned slot = (lo * 0x9E3779B1u ^ hi * 0x85EBCA77u) >> 11;
+#pragma unroll 1
         for (int probe = 0; probe < WHASH; probe++, slot++) {
             slot &= WHASH - 1;
             const unsigned long long old = atomicCAS(&W.hkey[slot], FPK_HEMPTY, key);
@@ -445,6 +456,7 @@ __device__ __noinline__ int w2_commit_insertion(int rank, int ncav, int popstack
     int base = 0;
     if (lane == 0) base = atomicAdd(&S.cnt[C_NFREE0 + (popstack ^ 1)], ncav);
     base = __shfl_sync(FPK_FULL, base, 0);
+#pragma unroll 1
     for (int i = lane; i < ncav; i += 32) {
         const int cur = W.id[i];
         TVp(cur)[0] = T_DEAD;
