@@ -35,3 +35,6 @@ print("\n# warp stall samples (all warps): " + ", ".join("%s %.1f%%" % (k, 100.0
 print("# hottest source lines: %samples  %instructions  active lanes  file:line  source")
 for o in sorted(out, key=lambda o: -o[0])[:18]:
     print("%5.1f%% %5.1f%% %5.1f  %s:%s  %s" % (100.0 * o[0] / ts, 100.0 * o[1] / ti, o[2] / max(1, o[1]), o[3], o[4], o[5]))
+print("# most executed source lines: %instructions  %samples  active lanes  file:line  source")
+for o in sorted(out, key=lambda o: -o[1])[:24]:
+    print("%5.1f%% %5.1f%% %5.1f  %s:%s  %s" % (100.0 * o[1] / ti, 100.0 * o[0] / ts, o[2] / max(1, o[1]), o[3], o[4], o[5]))
