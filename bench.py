@@ -405,7 +405,7 @@ def main():
         subprocess.call("rm -rf %s/*_out" % f2f_dir, shell=True)
         barrier()
         tf = time.perf_counter()
-        st = hostio.run_list(f2f_paths, p, group=1024, io_threads=io_threads, quiet=1)
+        st = hostio.run_list(f2f_paths, p, group=512, io_threads=io_threads, quiet=1)
         barrier()
         tf = time.perf_counter() - tf
         ff = torch.tensor([tf], device="cuda", dtype=torch.float64)
@@ -414,18 +414,18 @@ def main():
         out["file_to_file"] = {"metric": "structures/sec", "value": nf * world / float(ff[0]), "files_per_gpu": nf, "written": st["n_written"],
                                "pockets": st["n_pockets"], "io_threads": io_threads, "MB_in": st["bytes_in"] / 1e6, "MB_out": st["bytes_out"] / 1e6,
                                "read_cpu_s": st["read_cpu_s"], "write_cpu_s": st["write_cpu_s"], "detect_s": st["detect_s"], "wall_s": tf,
-                               "includes": "PDB files on tmpfs -> fpkio_run_list (libfpocket_hostio: one-pass reader of both atom lists, groups of 1024 "
+                               "includes": "PDB files on tmpfs -> fpkio_run_list (libfpocket_hostio: one-pass reader of both atom lists, groups of 512 "
                                            "through fpk_detect_batch, writers of the reference's <code>_out/ directory: _out.pdb, _info.txt, _pockets.pqr, "
                                            "4 scripts, 2 files per pocket), byte-identical to the reference's writers (tests/test_hostio.py)"}
         if rank == 0 and world == 1 and not args.no_cpu:
             bexe = os.path.join(ROOT, "build", "fpocket_cuda_batch")
             if os.path.exists(bexe):
-                nb = min(nf, 64)
+                nb = min(nf, 128)
                 subprocess.call("rm -rf %s/*_out" % f2f_dir, shell=True)
-                with open(os.path.join(f2f_dir, "list64.txt"), "w") as f:
+                with open(os.path.join(f2f_dir, "list_ref.txt"), "w") as f:
                     f.write("".join(os.path.basename(q) + "\n" for q in f2f_paths[:nb]))
                 tb = time.time()
-                rcb = subprocess.call([bexe, "list64.txt"], cwd=f2f_dir, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                rcb = subprocess.call([bexe, "list_ref.txt"], cwd=f2f_dir, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
                 tb = time.time() - tb
                 out["file_to_file"]["reference_host_io"] = {"value": nb / tb if rcb == 0 else None, "unit": "structures/s",
                                                             "sample": "first %d files through build/fpocket_cuda_batch: the reference's own reader and writers "
