@@ -352,20 +352,22 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
 {
     const int n = b->n;
     int occ1 = 2, occ3 = 4;
-    // K1 shared-memory plan: WarpCav records + the sites as int32 lattice offsets. Two blocks per SM when the largest
-    // structure fits in half an SM's shared memory, else one block, else the sites stay in global memory (pi_cap 0).
+    // K1 shared-memory plan. The kernel is bound by the latency of dependent tet / claim loads, so what counts is the number of
+    // resident warps: three blocks of eight warps per SM at 80 registers (launch bounds) beat two blocks at 128 by 11 % even though
+    // the sites then come through L1 / L2 instead of shared memory (profiles/README.md: 192 -> 171.5 ms per 3,000 structures; at two
+    // blocks per SM the shared-memory tile made no difference: 193.6 vs 192.1). The tile (int32 lattice offsets, brought in by TMA
+    // bulk copies) is kept when it fits beside the WarpCav records at three blocks per SM, i.e. for structures up to ~2,000 sites.
     {
         const size_t fixed = FPK_BD_BYTES + (FPK_K1_THREADS / 32) * sizeof(WarpCav), stat = 2048, sm_total = 227 * 1024, per_block_reserved = 1024;
         const size_t need = fixed + 12 * (size_t)b->max_sites + 128;          // + slack for the 16-byte aligned TMA window
-        const size_t half = (sm_total - 2 * per_block_reserved) / 2 - stat, full = sm_total - per_block_reserved - stat;
-        if (need <= half) { b->k1_picap = b->max_sites; b->k1_dsm = need; }
-        else if (need <= full) { b->k1_picap = b->max_sites; b->k1_dsm = need; }
+        const size_t share = (sm_total - FPK_K1_MINBLOCKS * per_block_reserved) / FPK_K1_MINBLOCKS - stat;
+        if (need <= share) { b->k1_picap = b->max_sites; b->k1_dsm = need; }
         else { b->k1_picap = 0; b->k1_dsm = fixed; }
-        if (getenv("FPK_K1_SITES_GLOBAL")) { b->k1_picap = 0; b->k1_dsm = fixed; }     // tuning knob (profiles/): sites read through L1 instead of shared memory
+        if (getenv("FPK_K1_SITES_GLOBAL")) { b->k1_picap = 0; b->k1_dsm = fixed; }     // tuning knob (profiles/): never stage the sites
     }
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_delaunay_filter, FPK_K1_THREADS, b->k1_dsm);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_cluster, 256, 0);
-    occ1 = std::max(1, std::min(occ1, 4)); occ3 = std::max(1, std::min(occ3, 4));
+    occ1 = std::max(1, std::min(occ1, 16)); occ3 = std::max(1, std::min(occ3, 4));
     if (const char *e = getenv("FPK_K1_BLOCKS_PER_SM")) occ1 = std::max(1, std::min(occ1, atoi(e)));     // tuning knob (profiles/)
     b->nDel = std::max(1, std::min(n, g_sms * occ1));
     b->nClu = std::max(1, std::min(n, g_sms * occ3));
@@ -541,10 +543,11 @@ static int batch_run(fpk_batch *b)
     const long long NC = b->tot_clusters, NS = b->tot_spheres;
     int occH = 8, occD = 8;
     b->hull_picap = std::min(max_ns, 1024);
+    if (getenv("FPK_HULL_SITES_GLOBAL")) b->hull_picap = 0;          // tuning knob (profiles/)
     b->hull_dsm = FPK_BD_BYTES + (HULL_THREADS / 32) * sizeof(WarpCav) + 12 * (size_t)b->hull_picap + 16;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occH, k_hull_volume, HULL_THREADS, b->hull_dsm);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occD, k_descriptors, K4_THREADS, 0);
-    occH = std::max(1, std::min(occH, 8)); occD = std::max(1, std::min(occD, 8));
+    occH = std::max(1, std::min(occH, FPK_HULL_MINBLOCKS)); occD = std::max(1, std::min(occD, 8));
     b->nHull = (int)std::max(1ll, std::min<long long>(NC, (long long)g_sms * occH));
     b->nDesc = (int)std::max(1ll, std::min<long long>(NC, (long long)g_sms * occD));
     std::vector<DelScratch> hHull(b->nHull);

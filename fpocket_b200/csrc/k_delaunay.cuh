@@ -291,7 +291,7 @@ __device__ __forceinline__ bool mbar_wait(unsigned long long *bar, unsigned phas
 }
 
 #ifndef FPK_K1_MINBLOCKS
-#define FPK_K1_MINBLOCKS 2
+#define FPK_K1_MINBLOCKS 3        // 3 x 8 warps at 80 registers: more resident warps beat more registers (profiles/README.md)
 #endif
 #ifndef FPK_K1_THREADS
 #define FPK_K1_THREADS 256
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(FPK_K1_THREADS, FPK_K1_MINBLOCKS) k_delaunay_f
         // ---- 1. lattice coordinates: what "%.6f" prints (voronoi.c:130), exact in double -----------------------
         const int lead = S.atom_off & 3, tile = (n + lead + 3) & ~3;             // 16-byte aligned window around the structure's atoms
         bool staged = false;
-        if (n == S.natoms && 3 * tile <= 3 * pi_cap + 24) {                     // every atom is a site: the tile is contiguous
+        if (pi_cap > 0 && n == S.natoms && 3 * tile <= 3 * pi_cap + 24) {       // every atom is a site: the tile is contiguous (pi_cap 0: no site buffer at all)
             float *stg = reinterpret_cast<float *>(sm_sites());
             if (tid == 0) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // earlier generic-proxy accesses to the buffer come first

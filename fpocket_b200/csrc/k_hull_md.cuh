@@ -10,8 +10,11 @@ namespace fpk {
 // tetrahedra of the same points, so the block-parallel exact Delaunay of delaunay.cuh is reused on the pocket's centres
 // (on the 1e-6 lattice the reference's "%.6f" text puts them on, voronoi.c:1256-1262); tet volumes are summed EXACTLY
 // (128-bit integers), so the result does not depend on thread timing.
+#ifndef FPK_HULL_MINBLOCKS
+#define FPK_HULL_MINBLOCKS 8
+#endif
 enum { HULL_THREADS = 64 };
-__global__ void __launch_bounds__(HULL_THREADS, 8) k_hull_volume(BatchDev B, PocketDev Pk, const DelScratch *scratch, int *work_counter, int pi_cap)
+__global__ void __launch_bounds__(HULL_THREADS, FPK_HULL_MINBLOCKS) k_hull_volume(BatchDev B, PocketDev Pk, const DelScratch *scratch, int *work_counter, int pi_cap)
 {
     __shared__ int s_item;
     BlockDel &BD = blk();
