@@ -80,3 +80,32 @@ def test_in_process_pipeline_on_the_library(tmp_path):
     for nm in names:
         code = nm[:-4]
         assert _tree(str(da / (code + "_out"))) == _tree(str(db / (code + "_out")))
+
+
+def test_real_pdb_files_equal_reference_io(tmp_path):
+    """The reference's own sample structures (HETATM groups, alternate locations, several chains, up to 27k atoms), staged under
+    build/samples by build(): build/fpocket_fast must leave byte for byte what the reference's reader and writers leave around the
+    same library (build/fpocket_cuda_batch), for the whole list in one call."""
+    import shutil
+    src = os.path.join(ROOT, "build", "samples")
+    if not (os.path.isdir(src) and os.path.exists(FAST) and os.path.exists(BATCH)):
+        pytest.skip("build/samples, build/fpocket_fast or build/fpocket_cuda_batch missing (built where the reference tree is present)")
+    names = sorted(f for f in os.listdir(src) if f.endswith(".pdb"))
+    assert len(names) >= 10
+    da, db = tmp_path / "fast", tmp_path / "refio"
+    for d in (da, db):
+        d.mkdir()
+        for nm in names:
+            shutil.copy(os.path.join(src, nm), str(d / nm))
+        (d / "list.txt").write_text("".join(nm + "\n" for nm in names))
+    env = dict(os.environ, FPOCKET_MC_SEED=str(SEED), TMPDIR=str(tmp_path))
+    out = subprocess.check_output([FAST, "-F", "list.txt", "--stats", "--quiet"], cwd=str(da), env=env).decode()
+    assert "%d files, %d written" % (len(names), len(names)) in out, out
+    subprocess.check_call([BATCH, "list.txt"], cwd=str(db), env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    total = 0
+    for nm in names:
+        code = nm[:-4]
+        a, b = _tree(str(da / (code + "_out"))), _tree(str(db / (code + "_out")))
+        assert a == b, (code, sorted(k for k in set(a) | set(b) if a.get(k) != b.get(k))[:5])
+        total += len(a)
+    assert total > 500
