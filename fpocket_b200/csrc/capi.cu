@@ -808,9 +808,18 @@ extern "C" int fpk_detect_batch(const fpk_structure *in, int n, const fpk_params
     if (!in || n <= 0 || !p) return fail(FPK_ERR_BAD_ARG, "fpk_detect_batch: bad arguments");
     int rc = ensure_init();
     if (rc) return rc;
-    int chunk = 512, nthreads = 4;
+    // Chunking: K1 keeps 3 x 148 = 444 blocks resident, so a launch wants well over that many structures, and the last round of chunks
+    // should keep every host thread busy: ~1,200 structures per chunk, the number of chunks a multiple of the thread count when the batch
+    // allows (measured on 6,144 structures, 4 threads: 512 -> 7,668, 1,024 -> 7,867, 1,536 -> 8,268 structures/s end to end).
+    int chunk = 0, nthreads = 4;
     if (const char *e = getenv("FPK_CHUNK")) chunk = std::max(1, atoi(e));
     if (const char *e = getenv("FPK_HOST_THREADS")) nthreads = std::max(1, std::min(8, atoi(e)));
+    if (chunk <= 0) {
+        int nc = (n + 1199) / 1200;
+        if (n >= 600 * nthreads) nc = std::max(nthreads, (nc / nthreads) * nthreads);
+        else nc = std::max(1, std::min(nthreads, (n + 599) / 600));
+        chunk = (n + nc - 1) / nc;
+    }
     const int nchunks = (n + chunk - 1) / chunk;
     nthreads = std::min(nthreads, nchunks);
     if (nthreads <= 1) {
