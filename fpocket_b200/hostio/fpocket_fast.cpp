@@ -4,7 +4,10 @@
 // It leaves, next to every input, the <code>_out/ directory `fpocket -f` writes (PDB mode, fparams.c:403-407).
 //
 //   fpocket_fast -f X.pdb | -F list.txt  [-m f] [-M f] [-D f] [-i n] [-A n] [-p f] [-v n] [-c A,B | -k A,B]
-//                [--threads T] [--group G] [--quiet] [--stats]
+//                [--threads T] [--group G] [--quiet] [--stats] [--devices 0,1,..]
+//
+// --devices: one worker process per listed GPU (independent structures: no collective), file k of the list goes to worker k mod N; each
+// worker is this same program restricted to its device through CUDA_VISIBLE_DEVICES, with the I/O pool divided among them.
 //
 // Options outside the restated route (mmCIF input or -w m/b, -a, -r, -P, -l, -d, -x, -C != s, -e != e) are refused with a pointer to
 // build/fpocket_cuda_batch (reference reader / writers around the same library). There is no CPU detection path.
@@ -13,7 +16,11 @@
 #include <cstring>
 #include <ctime>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <sys/wait.h>
+#include <unistd.h>
 
 #include "fpocket_hostio.h"
 
@@ -30,7 +37,8 @@ int main(int argc, char **argv)
     fpkio_read_opts ro;
     memset(&ro, 0, sizeof ro);
     std::vector<std::string> files;
-    int threads = 0, group = 0, quiet = 0, want_stats = 0;
+    int threads = 0, group = 0, quiet = 0, want_stats = 0, slice_k = 0, slice_n = 1;
+    std::vector<std::string> devices;
     auto chains = [&](const char *arg, int kept) {                 // fparams.c:203-240: names separated by ',' or ':'
         char tmp[512];
         snprintf(tmp, sizeof tmp, "%s", arg);
@@ -68,13 +76,55 @@ int main(int argc, char **argv)
         else if (o == "-w" || o == "--write_mode") { const char *w = val(); if (w[0] != 'p' && w[0] != 'd') return refuse("-w other than pdb"); }
         else if (o == "--threads") threads = atoi(val());
         else if (o == "--group") group = atoi(val());
+        else if (o == "--devices") { char tmp[256]; snprintf(tmp, sizeof tmp, "%s", val()); for (char *t = strtok(tmp, ","); t; t = strtok(nullptr, ",")) devices.push_back(t); }
+        else if (o == "--slice") { if (sscanf(val(), "%d/%d", &slice_k, &slice_n) != 2 || slice_n < 1 || slice_k < 0 || slice_k >= slice_n) { fprintf(stderr, "! bad --slice\n"); return 2; } }
         else if (o == "--quiet") quiet = 1;
         else if (o == "--stats") want_stats = 1;
         else if (o == "-a" || o == "-r" || o == "-P" || o == "-l" || o == "-d" || o == "-x" || o == "-y" || o == "-u" || o == "-b") return refuse(o.c_str());
         else { fprintf(stderr, "! unknown option %s\n", o.c_str()); return 2; }
     }
-    if (files.empty()) { fprintf(stderr, "usage: %s -f X.pdb | -F list.txt [fpocket detection options] [--threads T] [--group G] [--quiet] [--stats]\n", argv[0]); return 2; }
+    if (files.empty()) { fprintf(stderr, "usage: %s -f X.pdb | -F list.txt [fpocket detection options] [--threads T] [--group G] [--quiet] [--stats] [--devices 0,1,..]\n", argv[0]); return 2; }
     for (const auto &f : files) if (strstr(f.c_str(), ".cif")) return refuse("mmCIF input");
+    if (devices.size() > 1) {
+        // one worker per GPU: re-run this command line with --slice k/N under CUDA_VISIBLE_DEVICES=<device k>
+        const int nd = (int)devices.size();
+        int hw = (int)std::thread::hardware_concurrency();
+        if (threads <= 0) threads = hw > 0 ? std::max(2, hw / nd) : 4;
+        std::vector<pid_t> kids;
+        for (int k = 0; k < nd; k++) {
+            pid_t pid = fork();
+            if (pid < 0) { perror("fork"); return 4; }
+            if (pid == 0) {
+                setenv("CUDA_VISIBLE_DEVICES", devices[k].c_str(), 1);
+                std::vector<std::string> av;
+                for (int a = 0; a < argc; a++) {
+                    if (!strcmp(argv[a], "--devices") || !strcmp(argv[a], "--threads")) { a++; continue; }
+                    av.push_back(argv[a]);
+                }
+                char sl[32], th[16];
+                snprintf(sl, sizeof sl, "%d/%d", k, nd);
+                snprintf(th, sizeof th, "%d", threads);
+                av.push_back("--slice"); av.push_back(sl); av.push_back("--threads"); av.push_back(th);
+                std::vector<char *> cav;
+                for (auto &x : av) cav.push_back(const_cast<char *>(x.c_str()));
+                cav.push_back(nullptr);
+                execv("/proc/self/exe", cav.data());
+                perror("execv");
+                _exit(127);
+            }
+            kids.push_back(pid);
+        }
+        int worst = 0;
+        for (pid_t pid : kids) { int st = 0; waitpid(pid, &st, 0); const int rc = WIFEXITED(st) ? WEXITSTATUS(st) : 128; if (rc > worst) worst = rc; }
+        return worst;
+    }
+    if (devices.size() == 1) setenv("CUDA_VISIBLE_DEVICES", devices[0].c_str(), 1);
+    if (slice_n > 1) {
+        std::vector<std::string> mine;
+        for (size_t k = 0; k < files.size(); k++) if ((int)(k % (size_t)slice_n) == slice_k) mine.push_back(files[k]);
+        files.swap(mine);
+        if (files.empty()) return 0;
+    }
     P.mc_seed = (uint64_t)time(nullptr);                                       // voronoi.c:87 srand(time(NULL))
     if (getenv("FPOCKET_MC_SEED")) P.mc_seed = strtoull(getenv("FPOCKET_MC_SEED"), nullptr, 10);
     if (fpk_init(nullptr, 0) != FPK_OK) { fprintf(stderr, "! %s\n", fpk_last_error()); return 4; }

@@ -14,6 +14,9 @@ with open(os.path.join(tmp, "list64.txt"), "w") as f:
     f.write("".join(os.path.basename(p) + "\n" for p in paths[:64]))
 fast = os.path.join(ROOT, "build", "fpocket_fast")
 configs = [({}, [])]
+if "--devices" in sys.argv:
+    dv = sys.argv[sys.argv.index("--devices") + 1]
+    configs = [({}, []), ({}, ["--devices", dv])]
 if "--sweep" in sys.argv:
     configs = [({"FPKIO_DETECT_THREADS": d}, ["--group", g, "--threads", t]) for d, g, t in
                [("1", "1024", "16"), ("2", "1024", "16"), ("2", "512", "16"), ("2", "2048", "16"), ("3", "1024", "16"), ("2", "1024", "12"), ("2", "1024", "24"),
