@@ -13,7 +13,10 @@ namespace fpk {
 #ifndef FPK_HULL_MINBLOCKS
 #define FPK_HULL_MINBLOCKS 8
 #endif
-enum { HULL_THREADS = 64 };
+#ifndef FPK_HULL_THREADS
+#define FPK_HULL_THREADS 64
+#endif
+enum { HULL_THREADS = FPK_HULL_THREADS };
 __global__ void __launch_bounds__(HULL_THREADS, FPK_HULL_MINBLOCKS) k_hull_volume(BatchDev B, PocketDev Pk, const DelScratch *scratch, int *work_counter, int pi_cap)
 {
     __shared__ int s_item;
