@@ -355,6 +355,18 @@ def main():
             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": per_stage[dom],
             "whole_path": {"algorithmic_bytes_per_step": whole, "achieved_gbs": whole / (t_dev / args.steps) / 1e9,
                            "frac": whole / (t_dev / args.steps) / 1e9 / peak}}
+    # compute-side figure for K4 (the explanatory second number): executed thread instructions per second against the FP32 lane
+    # rate of the chip; the instruction count per structure comes from the committed ncu capture, the time is this run's CUDA-event time
+    try:
+        kj = json.load(open(os.path.join(ROOT, "profiles", "k4_compute.json")))
+        sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
+        tinst = kj["warp_inst"] * kj["active_lanes"] / kj["structures"] * args.structures
+        peak_lanes = torch.cuda.get_device_properties(local).multi_processor_count * 128 * sm_hz * 1e6
+        roof["k_descriptors_compute"] = {"thread_inst_per_launch": tinst, "achieved_Tinst_s": tinst / (per_stage["k_descriptors"] * 1e-3) / 1e12,
+                                         "peak_fp32_lane_Tinst_s": peak_lanes / 1e12, "frac": tinst / (per_stage["k_descriptors"] * 1e-3) / peak_lanes,
+                                         "issue_slots_active_pct_ncu": kj["issue_active_pct"], "source": "profiles/k4_compute.json (" + kj["capture"] + ")"}
+    except Exception:
+        pass
     out = {"metric": "structures/sec", "value": value, "unit": "structures/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64 predicates/circumcentres + f32 descriptors (the reference's own mix)", "data": "synthetic", "config": cfg,
