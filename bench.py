@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--md-frames", type=int, default=2048, help="also measure mdpocket frames/s on a synthetic trajectory of this many frames per GPU (0: skip)")
+    ap.add_argument("--md-file-frames", type=int, default=8192, help="also run build/mdpocket_cuda file to file on a DCD trajectory of this many frames (0: skip)")
     ap.add_argument("--dpocket", type=int, default=1000, help="also measure dpocket (BASELINE configs[4]): this many ligand-bound synthetic structures per GPU (0: skip)")
     ap.add_argument("--large", type=int, default=0, help="also time ONE synthetic complex of this many heavy atoms (BASELINE configs[3]: 150000) on rank 0")
     ap.add_argument("--files", type=int, default=2000, help="also measure the file-to-file -F loop (native PDB reader -> fpk_detect_batch -> native writers) on this many workload structures per GPU (0: skip)")
@@ -475,6 +476,27 @@ def main():
         out["mdpocket"] = {"metric": "frames/sec", "value": F * world / float(mm[0]), "frames_per_gpu": F, "atoms": int(s5.n),
                            "grid": [int(v) for v in dims], "includes": "H2D of every frame, detection, grid scatter, NCCL all-reduce of both grids"}
         md.close()
+        # file to file: the reference's mdpocket program on the fpk_md_* API (build/mdpocket_cuda, fpocket_b200/shim/mdpocket_cuda.c): DCD
+        # trajectory in through the reference's molfile reader (double-buffered against the GPU), DX grids / PDB files out through its writers
+        mexe = os.path.join(ROOT, "build", "mdpocket_cuda")
+        if rank == 0 and world == 1 and os.path.exists(mexe) and args.md_file_frames > 0:
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import gpu_md_file_to_file as mdf
+            Ff = args.md_file_frames
+            reps = (Ff + F - 1) // F
+            traj = np.concatenate([xyz] * reps)[:Ff]
+            tmpd = tempfile.mkdtemp(prefix="fpkmdf", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+            synth.to_pdb(s5, os.path.join(tmpd, "top.pdb"))
+            mdf.write_dcd(os.path.join(tmpd, "traj.dcd"), traj)
+            del traj
+            tq = time.time()
+            rcm = subprocess.call([mexe, "--trajectory_file", "traj.dcd", "--trajectory_format", "dcd", "-f", "top.pdb"], cwd=tmpd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            tq = time.time() - tq
+            okf = rcm == 0 and os.path.exists(os.path.join(tmpd, "mdpout_dens_grid.dx"))
+            out["mdpocket"]["file_to_file"] = {"value": Ff / tq if okf else None, "unit": "frames/s", "frames": Ff, "process_wall_s": tq,
+                                               "includes": "one process: CUDA start-up, topology PDB, %d-frame DCD through the molfile reader, detection, grid scatter, "
+                                                           "the reference's normalize / project / DX / PDB writers" % Ff}
+            subprocess.call(["rm", "-rf", tmpd])
         if rank == 0 and world == 1 and not args.no_cpu:
             nfr = 2 * ncores
             r, dt = reference_mdpocket_rate(s5, xyz[:nfr], ncores)

@@ -16,6 +16,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
 
 #include "mdpocket.h"
 #include "fpocket_cuda.h"
@@ -46,22 +47,43 @@ static s_mdgrid *grid_from_array(const float *vals, const float origin[3], const
     return g;
 }
 
-typedef struct { fpk_md *md; int natoms, have_grid, nframes; float origin[3]; int dims[3]; float *buf; int nbuf; const int *slot; } md_run;
+/* Two frame buffers: while the library works on one block (fpk_md_push_frames blocks until the GPU is done), the reader fills the other. */
+typedef struct { fpk_md *md; int natoms, have_grid, nframes; float origin[3]; int dims[3]; float *buf, *bufs[2]; int cur, nbuf; const int *slot;
+                 pthread_t th; int th_live, th_rc, push_n; float *push_buf; } md_run;
 
+static void *md_push_thread(void *arg)
+{
+    md_run *r = (md_run *)arg;
+    r->th_rc = fpk_md_push_frames(r->md, r->push_buf, r->push_n);
+    return NULL;
+}
+static int md_wait(md_run *r)
+{
+    if (!r->th_live) return 0;
+    pthread_join(r->th, NULL);
+    r->th_live = 0;
+    if (r->th_rc) fprintf(stderr, "! libfpocket_cuda (%d): %s\n", r->th_rc, fpk_last_error());
+    return r->th_rc;
+}
 static int md_flush(md_run *r)
 {
-    if (!r->nbuf) return 0;
-    int rc = 0, first = 0;
-    if (!r->have_grid) {        /* frame 1 defines the grid (mdpocket.c:151-154) */
+    if (!r->nbuf) return md_wait(r);
+    int rc = md_wait(r);                     /* the previous block is done: its buffer is the one the reader gets next */
+    if (!rc && !r->have_grid) {              /* frame 1 defines the grid (mdpocket.c:151-154) */
         rc = fpk_md_grid_from_frame(r->md, r->buf, r->origin, r->dims);
         if (!rc) rc = fpk_md_set_grid(r->md, r->origin, r->dims);
         r->have_grid = 1;
-        (void)first;
+        if (rc) fprintf(stderr, "! libfpocket_cuda (%d): %s\n", rc, fpk_last_error());
     }
-    if (!rc) rc = fpk_md_push_frames(r->md, r->buf, r->nbuf);
-    if (rc) fprintf(stderr, "! libfpocket_cuda (%d): %s\n", rc, fpk_last_error());
+    if (!rc) {
+        r->push_buf = r->buf; r->push_n = r->nbuf; r->th_rc = 0;
+        if (pthread_create(&r->th, NULL, md_push_thread, r) == 0) r->th_live = 1;
+        else rc = fpk_md_push_frames(r->md, r->buf, r->nbuf);
+    }
     r->nframes += r->nbuf;
     r->nbuf = 0;
+    r->cur ^= 1;
+    r->buf = r->bufs[r->cur];                /* the reader goes on in the other buffer */
     return rc;
 }
 
@@ -115,7 +137,9 @@ void mdpocket_detect(s_mdparams *par)
     R.md = fpk_md_begin(&job.st, &P, par->flag_scoring);
     if (!R.md) { fprintf(stderr, "! libfpocket_cuda: %s\n", fpk_last_error()); return; }
     R.natoms = na;
-    R.buf = (float *)malloc(sizeof(float) * 3 * (size_t)na * MD_BLOCK);
+    R.bufs[0] = (float *)malloc(sizeof(float) * 3 * (size_t)na * MD_BLOCK);
+    R.bufs[1] = (float *)malloc(sizeof(float) * 3 * (size_t)na * MD_BLOCK);
+    R.buf = R.bufs[0];
     int failed = 0;
 
     /* ---- the frames ------------------------------------------------------------------------------------------------------------- */
@@ -144,6 +168,7 @@ void mdpocket_detect(s_mdparams *par)
         md_api->close_file_read(h_in);
     }
     if (!failed) failed = md_flush(&R);
+    if (md_wait(&R)) failed = 1;
     const int n_snapshots = R.nframes;
     fprintf(stdout, "<mdpocket> %d snapshots analysed on the GPU\n", n_snapshots);
     if (failed || !R.have_grid || n_snapshots == 0) { fpk_md_end(R.md); return; }
@@ -154,7 +179,7 @@ void mdpocket_detect(s_mdparams *par)
     if (fpk_md_fetch_grids(R.md, dens, freq)) { fprintf(stderr, "! libfpocket_cuda: %s\n", fpk_last_error()); return; }
     fpk_md_end(R.md);
     s_mdgrid *freqgrid = grid_from_array(freq, R.origin, R.dims), *densgrid = grid_from_array(dens, R.origin, R.dims);
-    free(dens); free(freq); free(R.buf);
+    free(dens); free(freq); free(R.bufs[0]); free(R.bufs[1]);
     freqgrid->n_snapshots = n_snapshots;
     densgrid->n_snapshots = n_snapshots;
     normalize_grid(freqgrid, n_snapshots);
