@@ -775,7 +775,7 @@ static fpk_batch *pool_get()
 static void pool_put(fpk_batch *b)
 {
     std::lock_guard<std::mutex> g(g_pool_mu);
-    if (g_pool.size() < 4) g_pool.push_back(b); else delete b;
+    if (g_pool.size() < 8) g_pool.push_back(b); else delete b;      // two concurrent callers x four threads (libfpocket_hostio) keep their contexts: a cudaFree here would serialise the device
 }
 static void pool_clear()
 {
