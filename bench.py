@@ -535,6 +535,32 @@ def main():
                           "mean_overlap_of_top_pocket_pct": mean_ovlp,
                           "includes": "fpk_detect_batch on host arrays with the known ligand: detection, ligand queries (K6), the explicit pocket's descriptor "
                                       "record; H2D/D2H inside; 28-atom ligand placed in the best pocket of a first pass"}
+        # file to file (SURVEY 8 f1 for configs[4]): PDB complexes + ligand names -> fpkio_run_dpocket (native reader in ligand mode, one
+        # fpk_detect_batch per group, native writers of every <code>_out/ directory and of the three dpocket tables)
+        if args.files > 0:
+            from fpocket_b200 import hostio
+            ndf = min(nd, args.files)
+            tmpd = tempfile.mkdtemp(prefix="fpkdpf_r%d_" % rank, dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+            dpaths = [os.path.join(tmpd, "c%05d.pdb" % k) for k in range(ndf)]
+            for k in range(ndf):
+                synth.to_pdb(raw[k], dpaths[k], ligs[k])
+            outs = [os.path.join(tmpd, nm) for nm in ("dpout_explicitp.txt", "dpout_fpocketp.txt", "dpout_fpocketnp.txt")]
+            io_threads = max(2, workers)
+            hostio.run_dpocket(dpaths[: min(ndf, 128)], ["LIG"] * min(ndf, 128), p, outs, group=128, io_threads=io_threads)     # warm-up
+            subprocess.call("rm -rf %s/*_out" % tmpd, shell=True)
+            barrier()
+            tq = time.perf_counter()
+            sd = hostio.run_dpocket(dpaths, ["LIG"] * ndf, p, outs, group=512, io_threads=io_threads)
+            barrier()
+            tq = time.perf_counter() - tq
+            qq = torch.tensor([tq], device="cuda", dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(qq, op=dist.ReduceOp.MAX)
+            out["dpocket"]["file_to_file"] = {"value": ndf * world / float(qq[0]), "unit": "structures/s", "complexes_per_gpu": ndf, "written": sd["n_written"],
+                                              "pockets": sd["n_pockets"], "table_rows": sum(max(0, len(open(o).read().splitlines()) - 1) for o in outs),
+                                              "includes": "PDB complexes on tmpfs -> fpkio_run_dpocket: reader in ligand mode, detection + ligand queries + explicit pocket "
+                                                          "(one fpk_detect_batch per 512 complexes), <code>_out/ directories and the three dpocket tables"}
+            subprocess.call(["rm", "-rf", tmpd])
         if rank == 0 and world == 1 and not args.no_cpu:
             exe = os.path.join(ROOT, "oracle", "_ref", "dpocket")
             if os.path.exists(exe):

@@ -11,15 +11,17 @@ from . import capi
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfpocket_hostio.so")
 
-FPKIO_OK, FPKIO_ERR_OPEN, FPKIO_ERR_NO_ATOMS, FPKIO_ERR_UNSUPPORTED, FPKIO_ERR_WRITE, FPKIO_ERR_BAD_ARG = 0, -1, -2, -3, -4, -5
+FPKIO_OK, FPKIO_ERR_OPEN, FPKIO_ERR_NO_ATOMS, FPKIO_ERR_UNSUPPORTED, FPKIO_ERR_WRITE, FPKIO_ERR_BAD_ARG, FPKIO_ERR_NO_LIGAND = 0, -1, -2, -3, -4, -5, -6
 
 
 class ReadOpts(C.Structure):
-    _fields_ = [("n_chains", C.c_int32), ("chains", (C.c_char * 21) * 20), ("chains_are_kept", C.c_int32)]
+    _fields_ = [("n_chains", C.c_int32), ("chains", (C.c_char * 21) * 20), ("chains_are_kept", C.c_int32), ("ligand", C.c_char * 8)]
 
     @classmethod
-    def make(cls, drop=None, keep=None):
+    def make(cls, drop=None, keep=None, ligand=None):
         o = cls()
+        if ligand:
+            o.ligand = ligand.encode()
         names = keep if keep is not None else (drop or [])
         o.n_chains = len(names)
         o.chains_are_kept = 1 if keep is not None else 0
@@ -71,6 +73,17 @@ def lib():
                                      C.c_int, C.c_int, C.c_int, C.POINTER(Stats)]
         L.fpkio_run_list.restype = C.c_int
         L.fpkio_version.restype = C.c_char_p
+        L.fpkio_nligand.argtypes = [vp]
+        L.fpkio_nligand.restype = C.c_int
+        L.fpkio_ligand_volume.argtypes = [vp, C.c_int, C.c_uint64]
+        L.fpkio_ligand_volume.restype = C.c_float
+        L.fpkio_dpocket_rows.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(capi.FpkResult), C.c_float, C.POINTER(C.c_void_p)]
+        L.fpkio_dpocket_rows.restype = C.c_int
+        L.fpkio_free_rows.argtypes = [C.POINTER(C.c_void_p)]
+        L.fpkio_free_rows.restype = None
+        L.fpkio_run_dpocket.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int, C.POINTER(capi.FpkParams), DETECT_FN, FREE_FN,
+                                        C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.POINTER(Stats)]
+        L.fpkio_run_dpocket.restype = C.c_int
         _lib = L
     return _lib
 
@@ -147,6 +160,22 @@ class PdbFile:
             raise IOError("fpkio_write_output(%s) failed: %d" % (pdb_path, rc))
         return rc, nb.value
 
+    def nligand(self):
+        return lib().fpkio_nligand(self.h)
+
+    def ligand_volume(self, niter, seed):
+        return float(lib().fpkio_ligand_volume(self.h, niter, seed))
+
+    def dpocket_rows(self, complex_path, ligand, result, lig_vol):
+        """The rows desc_pocket appends to the three dpocket tables for this complex (bytes x 3)."""
+        rows = (C.c_void_p * 3)()
+        rc = lib().fpkio_dpocket_rows(self.h, complex_path.encode(), ligand.encode(), C.byref(result), lig_vol, rows)
+        if rc < 0:
+            raise IOError("fpkio_dpocket_rows failed: %d" % rc)
+        out = [C.string_at(rows[k]) for k in range(3)]
+        lib().fpkio_free_rows(rows)
+        return out
+
     def close(self):
         if self.h:
             lib().fpkio_file_free(self.h)
@@ -179,4 +208,26 @@ def run_list(paths, params, detect=None, free_result=None, group=0, io_threads=0
                           group, io_threads, quiet, C.byref(st))
     if rc != FPKIO_OK:
         raise RuntimeError("fpkio_run_list failed: %d" % rc)
+    return st.as_dict()
+
+
+def run_dpocket(paths, ligands, params, out_paths, detect=None, free_result=None, group=0, io_threads=0, quiet=1):
+    """dpocket's loop (dpocket.c:83-130): complexes + ligand residue names in, <code>_out/ directories and the three tables out."""
+    L = lib()
+    if detect is None:
+        cl = capi.load_library()
+        if cl.fpk_init(None, 0) != 0:
+            raise RuntimeError("fpk_init failed: %s" % cl.fpk_last_error().decode())
+        detect = C.cast(cl.fpk_detect_batch, DETECT_FN)
+        free_result = C.cast(cl.fpk_result_free, FREE_FN)
+    else:
+        detect, free_result = DETECT_FN(detect), FREE_FN(free_result)
+    n = len(paths)
+    pa = (C.c_char_p * n)(*[p.encode() for p in paths])
+    la = (C.c_char_p * n)(*[l.encode() for l in ligands])
+    oa = (C.c_char_p * 3)(*[o.encode() for o in out_paths])
+    st = Stats()
+    rc = L.fpkio_run_dpocket(pa, la, n, C.byref(params), detect, free_result, oa, group, io_threads, quiet, C.byref(st))
+    if rc != FPKIO_OK:
+        raise RuntimeError("fpkio_run_dpocket failed: %d" % rc)
     return st.as_dict()

@@ -230,6 +230,7 @@ struct fpkio_file {
     std::vector<int32_t> iv;            // 2 x n: id res_id
     std::vector<int8_t> aa;
     std::vector<uint8_t> fl, wfl;
+    std::vector<int32_t> lig_idx, lig_mol, name_key;   // dpocket: the known ligand (indices into watoms), its molecules, atom names of pdb packed
     fpk_structure st;
     long long bytes = 0;
 };
@@ -285,6 +286,7 @@ int parse_pdb(const char *path, const char *data, size_t size, const fpkio_read_
     memset(L, 0, sizeof L);
     const char *p = data, *end = data + size;
     float x = 0, y = 0, z = 0;
+    const bool ligmode = opts && opts->ligand[0] && opts->ligand[1];
     while (p < end) {
         size_t n = (size_t)(end - p) < (size_t)LINE_MAX_CHARS ? (size_t)(end - p) : (size_t)LINE_MAX_CHARS;
         if (const void *nl = memchr(p, '\n', n)) n = (size_t)((const char *)nl - p) + 1;
@@ -296,19 +298,24 @@ int parse_pdb(const char *path, const char *data, size_t size, const fpkio_read_
             if (!chain_passes(opts, L[21])) continue;
             x = slice_atof(L + 30, 8); y = slice_atof(L + 38, 8); z = slice_atof(L + 46, 8);
             if (!((L[16] == ' ' || L[16] == 'A') && x < 9990 && y < 9990 && z < 9990)) continue;
-            bool in_lig = true, in_nolig = true;
+            bool in_lig = true, in_nolig = true, is_ligand_atom = false;
+            char resb[8];
+            slice_strncpy(resb, L + 17, 4);
+            str_trim(resb);
+            // dpocket: rpdb_open / rpdb_read with ligan = the ligand's residue name (rpdb.c:872-885,925-936,1131-1160,1250-1273)
+            const bool lig_match = ligmode && resb[0] == opts->ligand[0] && resb[1] == opts->ligand[1] && resb[2] == opts->ligand[2];
             if (is_het) {
-                char resb[8];
-                slice_strncpy(resb, L + 17, 4);
-                str_trim(resb);
                 const bool listed = keep_hetatm(resb);
-                in_nolig = listed;                               // rpdb.c:947-961 with keep_lig = 0
-                in_lig = !is_water3(resb) || listed;             // rpdb.c:941-946 with keep_lig = 1, ligan = NULL
+                in_nolig = listed;                               // rpdb.c:947-961 with keep_lig = 0 (also for the ligand's own name)
+                if (ligmode) { is_ligand_atom = lig_match; in_lig = lig_match || listed; }      // keep_lig = 1, ligan != NULL: nothing else is kept
+                else in_lig = !is_water3(resb) || listed;        // rpdb.c:941-946 with keep_lig = 1, ligan = NULL
                 if (!in_lig) continue;
-            }
+            } else if (lig_match) { is_ligand_atom = true; in_nolig = false; }      // an ATOM record of the ligand: only in pdb_w_lig
             F->watoms.emplace_back();
             extract_atom(L, (int)strlen(L), x, y, z, F->watoms.back());
-            if (is_het) { F->nhet[1]++; if (in_nolig) F->nhet[0]++; }
+            if (is_het && !is_ligand_atom) F->nhet[1]++;
+            if (is_het && in_nolig) F->nhet[0]++;
+            if (is_ligand_atom) F->lig_idx.push_back((int32_t)F->watoms.size() - 1);
             if (in_nolig) F->nolig.push_back((int32_t)F->watoms.size() - 1);
         } else if (!strncmp(L, "END", 3)) break;                 // rpdb.c:975, :1420 (model_flag == 0): ENDMDL ends the file too
     }
@@ -349,6 +356,24 @@ int parse_pdb(const char *path, const char *data, size_t size, const fpkio_read_
     s.wx = F->wf.data(); s.wy = s.wx + nw; s.wz = s.wx + 2 * (size_t)nw; s.wradius = s.wx + 3 * (size_t)nw; s.welectroneg = s.wx + 4 * (size_t)nw;
     s.wflags = F->wfl.data();
     s.same_pdb = 0;                     // fpmain.c:143-144: two objects
+    if (ligmode) {
+        if (F->lig_idx.empty()) { delete F; return FPKIO_ERR_NO_LIGAND; }
+        // ligand molecules: runs of equal (chain, res_id) in file order (dpocket.c:211-222, neighbor.c:619-637)
+        int mol = 0;
+        for (size_t j = 0; j < F->lig_idx.size(); j++) {
+            const AtomRec &a = F->watoms[F->lig_idx[j]];
+            if (j > 0) { const AtomRec &q = F->watoms[F->lig_idx[j - 1]]; if (q.chain[0] != a.chain[0] || q.res_id != a.res_id) mol++; }
+            F->lig_mol.push_back(mol);
+        }
+        F->name_key.resize(n);
+        for (int k = 0; k < n; k++) {                          // atm_corsp compares atom names (atom.c:281): four bytes packed
+            const char *nm = F->watoms[F->nolig[k]].name;
+            unsigned char b[4] = {0, 0, 0, 0};
+            for (int i = 0; i < 4 && nm[i]; i++) b[i] = (unsigned char)nm[i];
+            F->name_key[k] = (int)((unsigned)b[0] | ((unsigned)b[1] << 8) | ((unsigned)b[2] << 16) | ((unsigned)b[3] << 24));
+        }
+        s.n_lig = (int32_t)F->lig_idx.size(); s.lig_atoms = F->lig_idx.data(); s.lig_mol = F->lig_mol.data(); s.atom_name_key = F->name_key.data();
+    }
     *out = F;
     return FPKIO_OK;
 }
@@ -752,8 +777,14 @@ struct Group {
 
 }  // namespace
 
-extern "C" int fpkio_run_list(const char *const *paths, int n, const fpkio_read_opts *ropts, const fpk_params *p, fpkio_detect_fn detect,
-                              fpkio_free_fn free_result, int group, int io_threads, int quiet, fpkio_stats *stats)
+namespace {
+// what happens to one structure once its result is there: writes files (and, for dpocket, keeps the table rows); returns the number of pockets
+// written or FPKIO_ERR_*
+typedef std::function<int(int k, const fpkio_file *f, const fpk_result *r, long long *bytes)> Sink;
+typedef std::function<const fpkio_read_opts *(int k)> OptsOf;
+
+int run_pipeline(const char *const *paths, int n, const OptsOf &opts_of, const fpk_params *p, fpkio_detect_fn detect,
+                 fpkio_free_fn free_result, int group, int io_threads, int quiet, fpkio_stats *stats, const Sink &sink)
 {
     if (!paths || n < 0 || !p || !detect || !free_result) return FPKIO_ERR_BAD_ARG;
     if (group <= 0) group = 1024;
@@ -793,6 +824,7 @@ extern "C" int fpkio_run_list(const char *const *paths, int n, const fpkio_read_
                         if (!quiet) {
                             if (g->rc[k] == FPKIO_ERR_OPEN) fprintf(stderr, "! File %s does not exist\n", paths[g->first + k]);
                             else if (g->rc[k] == FPKIO_ERR_NO_ATOMS) fprintf(stderr, "! File '%s' contains no atoms...\n", paths[g->first + k]);
+                            else if (g->rc[k] == FPKIO_ERR_NO_LIGAND) fprintf(stdout, "ERROR - No ligand %s found in %s.\n", opts_of(g->first + k)->ligand, paths[g->first + k]);
                             else fprintf(stderr, "! %s: not a PDB file this reader handles (mmCIF input goes through build/fpocket_cuda_batch)\n", paths[g->first + k]);
                             fprintf(stderr, "! Structure reading failed!\n");
                         }
@@ -830,7 +862,7 @@ extern "C" int fpkio_run_list(const char *const *paths, int n, const fpkio_read_
                         int w = 0;
                         // search_pocket returns a list (possibly with no pocket left, fpocket.c:225) unless the clustering tree failed (:135-139)
                         const bool have_list = (R->status == FPK_OK || R->status == FPK_ERR_NO_POCKETS);
-                        if (have_list) w = fpkio_write_output(g->files[k], paths[g->first + k], R, &bytes);
+                        if (have_list) w = sink(g->first + k, g->files[k], R, &bytes);
                         else {
                             if (!quiet && R->status == FPK_ERR_NO_SPHERES) fprintf(stderr, "Error in creating clustering tree, return NULL pointer...breaking up");
                             if (!quiet) printf("no pockets found\n");                            // fpmain.c:204
@@ -873,7 +905,7 @@ extern "C" int fpkio_run_list(const char *const *paths, int n, const fpkio_read_
             for (int k = 0; k < g->n; k++)
                 pool.submit([&, g, k] {
                     const double tr = now_s();
-                    g->rc[k] = fpkio_read_pdb(paths[g->first + k], ropts, &g->files[k]);
+                    g->rc[k] = fpkio_read_pdb(paths[g->first + k], opts_of(g->first + k), &g->files[k]);
                     const double dt = now_s() - tr;
                     {
                         std::lock_guard<std::mutex> lk(sm);
@@ -897,3 +929,132 @@ extern "C" int fpkio_run_list(const char *const *paths, int n, const fpkio_read_
     if (stats) *stats = S;
     return detect_error ? FPKIO_ERR_BAD_ARG : FPKIO_OK;
 }
+
+// Philox4x32-10 (Salmon et al., SC'11), the generator of the library's Monte-Carlo volume
+void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+float unif31(uint32_t r31, float mn, float mx) { const float rnd = ((float)(int)r31 / (float)2147483647) * (mx - mn); return mn + rnd; }   // utils.c:113-128
+
+// write_pocket_desc (dpocket.c:387-402): one row of a dpocket table
+void dpocket_row(std::string &o, const char *fc, const char *l, const fpk_desc *d, float lv, float ovlp, float dst, float c4, float c5)
+{
+    static const fpk_desc zero = fpk_desc();
+    if (!d) d = &zero;
+    const int status = dst < 4.0 ? 1 : 0;
+    const int c6 = (c4 >= 0.5 && c5 >= 0.20) ? 1 : 0;                                      // tpocket.h:38-39 M_CRIT4_VAL, M_CRIT5_VAL
+    const float c6_c = ((c4 - 0.5) / (1 - 0.5)) + ((c5 - 0.20) / (1 - 0.20));
+    char b[1024];
+    int k = snprintf(b, sizeof b, "%s %s %6.2f %2d %6.2f %4.2f %4.2f %2d %5.2f %8.2f %10.2f %5d %4.2f %6.2f %6.2f %5.2f %4.2f %7.2f %4.2f %9.2f %7.2f %5d %5.2f %5d "
+                                  "%6.2f %7.2f %5.2f %5.2f %5.2f %5.2f %5.2f %5.2f %5.2f %5.2f %5.2f %5.2f %5d",
+                     fc, l, ovlp, status, dst, c4, c5, c6, c6_c, lv, d->volume, d->nb_asph, d->nas_norm, d->mean_asph_ray, d->masph_sacc, d->apolar_asphere_prop,
+                     d->prop_asapol_norm, d->mean_loc_hyd_dens, d->mean_loc_hyd_dens_norm, d->hydrophobicity_score, d->volume_score, d->polarity_score,
+                     d->polarity_score_norm, d->charge_score, d->flex, d->prop_polar_atm, d->as_density, d->as_density_norm, d->as_max_dst, d->as_max_dst_norm,
+                     d->drug_score, d->convex_hull_volume, d->surf_pol_vdw14, d->surf_pol_vdw22, d->surf_apol_vdw14, d->surf_apol_vdw22, d->n_abpa);
+    if (k < 0) k = 0;
+    if (k > (int)sizeof b - 1) k = (int)sizeof b - 1;
+    o.append(b, (size_t)k);
+    for (int i = 0; i < 20; i++) { k = snprintf(b, sizeof b, " %3d", d->aa_compo[i]); o.append(b, (size_t)k); }
+    o.push_back('\n');
+}
+const char *const DP_HEADER =                                                              // dpocket.h:42 + the residue names of aa.c:60-80 (dpocket.c:99-103)
+    "pdb lig overlap PP-crit PP-dst crit4 crit5 crit6 crit6_continue lig_vol pock_vol nb_AS nb_AS_norm mean_as_ray mean_as_solv_acc apol_as_prop "
+    "apol_as_prop_norm mean_loc_hyd_dens mean_loc_hyd_dens_norm hydrophobicity_score volume_score polarity_score polarity_score_norm charge_score flex "
+    "prop_polar_atm as_density as_density_norm as_max_dst as_max_dst_norm drug_score convex_hull_volume surf_pol_vdw14 surf_pol_vdw22 surf_apol_vdw14 "
+    "surf_apol_vdw22 n_abpa ALA ARG ASN ASP CYS GLN GLU GLY HIS ILE LEU LYS MET PHE PRO SER THR TRP TYR VAL\n";
+}  // namespace
+
+extern "C" {
+
+int fpkio_run_list(const char *const *paths, int n, const fpkio_read_opts *ropts, const fpk_params *p, fpkio_detect_fn detect,
+                   fpkio_free_fn free_result, int group, int io_threads, int quiet, fpkio_stats *stats)
+{
+    if (ropts && ropts->ligand[0]) return FPKIO_ERR_UNSUPPORTED;          // a known ligand is dpocket's business: fpkio_run_dpocket
+    return run_pipeline(paths, n, [ropts](int) { return ropts; }, p, detect, free_result, group, io_threads, quiet, stats,
+                        [paths](int k, const fpkio_file *f, const fpk_result *r, long long *bytes) { return fpkio_write_output(f, paths[k], r, bytes); });
+}
+
+int fpkio_nligand(const fpkio_file *f) { return f ? (int)f->lig_idx.size() : 0; }
+
+float fpkio_ligand_volume(const fpkio_file *f, int niter, uint64_t seed)
+{
+    if (!f || f->lig_idx.empty() || niter <= 0) return 0.0f;
+    float xmin = 0, xmax = 0, ymin = 0, ymax = 0, zmin = 0, zmax = 0, t;
+    for (size_t i = 0; i < f->lig_idx.size(); i++) {                  // atom.c:171-190, with its else-if updates
+        const AtomRec &a = f->watoms[f->lig_idx[i]];
+        if (i == 0) { xmin = a.x - a.radius; xmax = a.x + a.radius; ymin = a.y - a.radius; ymax = a.y + a.radius; zmin = a.z - a.radius; zmax = a.z + a.radius; }
+        else {
+            if (xmin > (t = a.x - a.radius)) xmin = t; else if (xmax < (t = a.x + a.radius)) xmax = t;
+            if (ymin > (t = a.y - a.radius)) ymin = t; else if (ymax < (t = a.y + a.radius)) ymax = t;
+            if (zmin > (t = a.z - a.radius)) zmin = t; else if (zmax < (t = a.z + a.radius)) zmax = t;
+        }
+    }
+    const float vbox = (xmax - xmin) * (ymax - ymin) * (zmax - zmin);
+    int nb_in = 0;
+    for (int i = 0; i < niter; i++) {
+        uint32_t o[4];
+        philox4x32((uint32_t)i, 0x11Au, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+        const float xr = unif31(o[0] >> 1, xmin, xmax), yr = unif31(o[1] >> 1, ymin, ymax), zr = unif31(o[2] >> 1, zmin, zmax);
+        for (size_t j = 0; j < f->lig_idx.size(); j++) {
+            const AtomRec &a = f->watoms[f->lig_idx[j]];
+            const float xt = a.x - xr, yt = a.y - yr, zt = a.z - zr;
+            if ((a.radius * a.radius) > (xt * xt + yt * yt + zt * zt)) { nb_in++; break; }
+        }
+    }
+    return ((float)nb_in) / ((float)niter) * vbox;
+}
+
+int fpkio_dpocket_rows(const fpkio_file *f, const char *fc, const char *lig, const fpk_result *r, float lig_vol, char *rows[3])
+{
+    if (!f || !fc || !lig || !r || !rows) return FPKIO_ERR_BAD_ARG;
+    std::string t[3];
+    dpocket_row(t[0], fc, lig, r->xdesc, lig_vol, 100.0f, 0.0f, 1.0f, 1.0f);               // dpocket.c:245: the explicit pocket
+    for (int q = 0; q < r->n_pockets; q++) {                                              // dpocket.c:247-287
+        const float ovlp = r->pk_ovlp ? r->pk_ovlp[q] : 0.0f, dst = r->pk_dst ? r->pk_dst[q] : 0.0f, c4 = r->pk_c4 ? r->pk_c4[q] : 0.0f,
+                    c5 = r->pk_c5 ? r->pk_c5[q] : 0.0f;
+        dpocket_row(t[(ovlp > 40.0 || dst < 4.0) ? 1 : 2], fc, lig, &r->desc[r->rank_to_cluster[q]], lig_vol, ovlp, dst, c4, c5);
+    }
+    for (int k = 0; k < 3; k++) { rows[k] = (char *)malloc(t[k].size() + 1); if (!rows[k]) return FPKIO_ERR_BAD_ARG; memcpy(rows[k], t[k].c_str(), t[k].size() + 1); }
+    return r->n_pockets;
+}
+void fpkio_free_rows(char *rows[3]) { if (rows) for (int k = 0; k < 3; k++) { free(rows[k]); rows[k] = nullptr; } }
+
+int fpkio_run_dpocket(const char *const *paths, const char *const *ligands, int n, const fpk_params *p, fpkio_detect_fn detect,
+                      fpkio_free_fn free_result, const char *const out_paths[3], int group, int io_threads, int quiet, fpkio_stats *stats)
+{
+    if (!paths || !ligands || n < 0 || !p || !out_paths) return FPKIO_ERR_BAD_ARG;
+    std::vector<fpkio_read_opts> ro((size_t)n);
+    for (int k = 0; k < n; k++) { memset(&ro[k], 0, sizeof ro[k]); snprintf(ro[k].ligand, sizeof ro[k].ligand, "%s", ligands[k] ? ligands[k] : ""); if (!ro[k].ligand[0] || !ro[k].ligand[1]) return FPKIO_ERR_BAD_ARG; }
+    std::vector<std::string> rows((size_t)3 * n);                    // kept per complex: the tables are written in list order at the end
+    const uint64_t seed = p->mc_seed;
+    const int niter = p->nb_mcv_iter;
+    const int rc = run_pipeline(paths, n, [&ro](int k) { return &ro[k]; }, p, detect, free_result, group, io_threads, quiet, stats,
+                                [&](int k, const fpkio_file *f, const fpk_result *r, long long *bytes) {
+                                    const int w = fpkio_write_output(f, paths[k], r, bytes);                 // dpocket.c:233
+                                    if (w < 0) return w;
+                                    char *t[3] = {nullptr, nullptr, nullptr};
+                                    const float vol = fpkio_ligand_volume(f, niter, seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(k + 1)));
+                                    if (fpkio_dpocket_rows(f, paths[k], ligands[k], r, vol, t) >= 0)
+                                        for (int q = 0; q < 3; q++) rows[(size_t)3 * k + q] = t[q];
+                                    fpkio_free_rows(t);
+                                    return w;
+                                });
+    long long bytes = 0;
+    for (int q = 0; q < 3; q++) {
+        Out o;
+        o.put(DP_HEADER);
+        for (int k = 0; k < n; k++) o.put(rows[(size_t)3 * k + q]);
+        if (!write_file(out_paths[q], o, 0666, &bytes)) return FPKIO_ERR_WRITE;
+    }
+    if (stats) stats->bytes_out += bytes;
+    return rc;
+}
+
+}  // extern "C"

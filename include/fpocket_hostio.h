@@ -36,12 +36,15 @@ extern "C" {
 #define FPKIO_ERR_UNSUPPORTED (-3)   /* input or option outside the restated route (see above) */
 #define FPKIO_ERR_WRITE       (-4)   /* an output directory or file could not be created */
 #define FPKIO_ERR_BAD_ARG     (-5)
+#define FPKIO_ERR_NO_LIGAND   (-6)   /* dpocket: "ERROR - No ligand %s found in %s." (dpocket.c:189) */
 
 /* what the reference's s_fparams carries for the reader (fparams.h:182-227); zero-initialise for the defaults */
 typedef struct fpkio_read_opts {
     int32_t n_chains;            /* -c / -k: number of chain names (<= 20)                     */
     char chains[20][21];         /* chain names (compared with the one-character chain column) */
     int32_t chains_are_kept;     /* 0: -c (drop these chains), 1: -k (keep only these)         */
+    char ligand[8];              /* dpocket: residue name of the known ligand (rpdb_open/rpdb_read with ligan != NULL, dpocket.c:186-203): its atoms
+                                    are kept in pdb_w_lig only and flagged as the ligand; other HETATM groups count only when listed. "" = fpocket */
 } fpkio_read_opts;
 
 typedef struct fpkio_file fpkio_file;      /* one parsed input: both atom lists + the flat arrays handed to the library */
@@ -64,10 +67,24 @@ int  fpkio_atom_text(const fpkio_file *f, int with_lig, int k, char *type, char 
  * caller print "no pockets found" (fpmain.c:204). Returns the number of pockets written or FPKIO_ERR_*. bytes_out (may be NULL) += bytes. */
 int  fpkio_write_output(const fpkio_file *f, const char *pdb_path, const fpk_result *r, long long *bytes_out);
 
-/* ---- the -F loop ------------------------------------------------------------------------------------------------------- */
-typedef int  (*fpkio_detect_fn)(const fpk_structure *in, int n, const fpk_params *p, fpk_result *out);   /* fpk_detect_batch */
-typedef void (*fpkio_free_fn)(fpk_result *r);                                                             /* fpk_result_free  */
+/* ---- dpocket (dpocket.c:166-300) ------------------------------------------------------------------------------------------ */
+int  fpkio_nligand(const fpkio_file *f);                          /* pdb_cplx_l->natm_lig (the structure then carries n_lig / lig_atoms / lig_mol / atom_name_key) */
+/* get_mol_volume_ptr (atom.c:156-217) on the ligand atoms: niter samples in the bounding box, counter-based stream keyed by seed (the reference
+ * draws from libc rand() seeded with the time: no stream to copy) */
+float fpkio_ligand_volume(const fpkio_file *f, int niter, uint64_t seed);
+/* the rows desc_pocket appends to dpout_explicitp / dpout_fpocketp / dpout_fpocketnp for one complex (write_pocket_desc, dpocket.c:387-402);
+ * rows[k] is malloc'd (release with fpkio_free_rows), "" when the complex has no row for that table */
+int  fpkio_dpocket_rows(const fpkio_file *f, const char *complex_path, const char *ligand, const fpk_result *r, float lig_vol, char *rows[3]);
+void fpkio_free_rows(char *rows[3]);
+/* the whole loop of dpocket() (dpocket.c:83-130): paths[k] + ligands[k]; writes every <code>_out/ directory and the three tables
+ * (header + rows in list order) to out_paths[0..2]; detection, ligand queries and the explicit pocket come from ONE detect call per group */
+typedef int  (*fpkio_detect_fn)(const fpk_structure *in, int n, const fpk_params *p, fpk_result *out);
+typedef void (*fpkio_free_fn)(fpk_result *r);
+struct fpkio_stats;
+int  fpkio_run_dpocket(const char *const *paths, const char *const *ligands, int n, const fpk_params *p, fpkio_detect_fn detect,
+                       fpkio_free_fn free_result, const char *const out_paths[3], int group, int io_threads, int quiet, struct fpkio_stats *stats);
 
+/* ---- the -F loop ------------------------------------------------------------------------------------------------------- */
 typedef struct fpkio_stats {
     int32_t n_files, n_written, n_read_failed, n_no_pockets, n_detect_failed;
     long long n_pockets, n_atoms, bytes_in, bytes_out;

@@ -6,7 +6,8 @@
  * (fpocket_b200/shim/search_pocket_cuda.c: shim_job_prepare / shim_rebuild), with the fpk_* entry points the shim calls
  * stubbed here (no GPU, no library).
  *
- *   ref_io atoms <out.dump> <fpocket options, -f X.pdb ...>
+ *   ref_io atoms <out.dump> [--lig NAME] <fpocket options, -f X.pdb ...>
+ *        (--lig: the structure is loaded as dpocket does, dpocket.c:186-203: ligan = NAME, model 0; the ligand atom list is dumped too)
  *        rpdb_open + rpdb_read for pdb and pdb_w_lig exactly as process_pdb does (src/fpmain.c:143-164), then the shim's flattening;
  *        dumps the flat arrays of fpk_structure and the text fields of every atom (FPKDUMP1 records, tests/dumpio.py)
  *   ref_io write <result.bin> <fpocket options, -f X.pdb ...>
@@ -87,21 +88,26 @@ int main(int argc, char **argv)
 {
     if (argc < 4) { fprintf(stderr, "usage: ref_io atoms out.dump <fpocket args> | ref_io write result.bin <fpocket args>\n"); return 2; }
     const int do_write = !strcmp(argv[1], "write");
-    int nargs = argc - 2;
+    const char *ligname = NULL;
+    int first = 3;
+    if (argc > 5 && !strcmp(argv[3], "--lig")) { ligname = argv[4]; first = 5; }
+    int nargs = argc - first + 1;
     char **args = malloc(sizeof(char *) * (nargs + 1));
     args[0] = argv[0];
-    for (int i = 3; i < argc; i++) args[i - 2] = argv[i];
+    for (int i = first; i < argc; i++) args[i - first + 1] = argv[i];
     args[nargs] = NULL;
     s_fparams *params = get_fpocket_args(nargs, args);
     if (!params) { fprintf(stderr, "bad fpocket args\n"); return 2; }
     params->fpocket_running = 1;
     char *pdbname = params->pdb_path;
     /* process_pdb, fpmain.c:143-164 (PDB route) */
-    s_pdb *pdb = rpdb_open(pdbname, NULL, M_DONT_KEEP_LIG, params->model_number, params);
-    s_pdb *pdbw = rpdb_open(pdbname, NULL, M_KEEP_LIG, params->model_number, params);
+    const int model = ligname ? 0 : params->model_number;
+    s_pdb *pdbw = rpdb_open(pdbname, ligname, M_KEEP_LIG, model, params);
+    s_pdb *pdb = rpdb_open(pdbname, ligname, M_DONT_KEEP_LIG, model, params);
     if (!pdb || !pdbw) { fprintf(stderr, "! Structure reading failed!\n"); return 3; }
-    rpdb_read(pdb, NULL, M_DONT_KEEP_LIG, params->model_number, params);
-    rpdb_read(pdbw, NULL, M_KEEP_LIG, params->model_number, params);
+    if (ligname && pdbw->natm_lig <= 0) { fprintf(stdout, "ERROR - No ligand %s found in %s.\n", ligname, pdbname); return 6; }
+    rpdb_read(pdbw, ligname, M_KEEP_LIG, model, params);
+    rpdb_read(pdb, ligname, M_DONT_KEEP_LIG, model, params);
     shim_job job;
     if (shim_job_prepare(&job, pdb, params, pdbw)) return 4;
     if (!do_write) {
@@ -123,6 +129,12 @@ int main(int argc, char **argv)
         rec1("same_pdb", 'i', 1, &sp);
         dump_text("pdb", pdb);
         dump_text("pdbw", pdbw);
+        if (ligname) {
+            int nl = pdbw->natm_lig, *li = malloc(sizeof(int) * (nl + 1));
+            for (int i = 0; i < nl; i++) li[i] = (int)(pdbw->latm_lig[i] - pdbw->latoms);
+            rec1("lig", 'i', nl, li);
+            free(li);
+        }
         fclose(OUT);
         return 0;
     }

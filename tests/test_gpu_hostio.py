@@ -109,3 +109,47 @@ def test_real_pdb_files_equal_reference_io(tmp_path):
         assert a == b, (code, sorted(k for k in set(a) | set(b) if a.get(k) != b.get(k))[:5])
         total += len(a)
     assert total > 500
+
+
+def test_dpocket_fast_equals_reference_io_around_the_library(tmp_path):
+    """build/dpocket_fast (native reader in ligand mode + ONE fpk_detect_batch per group + native writers) against build/dpocket_cuda (the
+    reference's dpocket program: its reader, write_out_fpocket and write_pocket_desc around fpk_detect): the same <code>_out/ directories and
+    the same three tables, byte for byte, except column lig_vol (the ligand's own Monte-Carlo volume: libc rand() seeded with the time in the
+    reference, a counter-based stream here - compared statistically)."""
+    import numpy as np
+    import synth
+    dfast, dref = os.path.join(ROOT, "build", "dpocket_fast"), os.path.join(ROOT, "build", "dpocket_cuda")
+    if not (os.path.exists(dfast) and os.path.exists(dref)):
+        pytest.skip("build/dpocket_fast or build/dpocket_cuda not built")
+    da, db = tmp_path / "fast", tmp_path / "refio"
+    da.mkdir(), db.mkdir()
+    names = []
+    for i, n in enumerate((2100, 2600, 3200, 2300)):
+        s = synth.generate(20267900 + i, n, 0.065)
+        rng = np.random.default_rng(40 + i)
+        c = s.xyz[rng.integers(0, s.n)] * 0.6 + s.xyz.mean(0) * 0.4
+        lig = (c + rng.normal(scale=2.2, size=(26, 3))).astype(np.float32)
+        names.append("d%d.pdb" % i)
+        for d in (da, db):
+            synth.to_pdb(s, str(d / names[-1]), lig_xyz=lig)
+    for d in (da, db):
+        (d / "list.txt").write_text("".join("%s\tLIG\n" % nm for nm in names))
+    env = dict(os.environ, FPOCKET_MC_SEED=str(SEED), TMPDIR=str(tmp_path))
+    out = subprocess.check_output([dfast, "-f", "list.txt", "--group", "3", "--threads", "3", "--stats", "--quiet"], cwd=str(da), env=env).decode()
+    assert "4 complexes, 4 written" in out, out
+    subprocess.check_call([dref, "-f", "list.txt"], cwd=str(db), env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    for nm in names:
+        code = nm[:-4]
+        a, b = _tree(str(da / (code + "_out"))), _tree(str(db / (code + "_out")))
+        assert a == b and len(a) >= 15, (code, sorted(k for k in set(a) | set(b) if a.get(k) != b.get(k))[:5])
+    nrows = 0
+    for tab in ("dpout_explicitp.txt", "dpout_fpocketp.txt", "dpout_fpocketnp.txt"):
+        ta, tb = (da / tab).read_text().splitlines(), (db / tab).read_text().splitlines()
+        assert ta[0] == tb[0] and len(ta) == len(tb), tab
+        for x, y in zip(ta[1:], tb[1:]):
+            fx, fy = x.split(), y.split()
+            assert fx[:9] == fy[:9] and fx[10:] == fy[10:], (tab, x, y)
+            vx, vy = float(fx[9]), float(fy[9])
+            assert abs(vx - vy) <= 0.25 * max(vx, vy) + 5.0, (tab, vx, vy)           # 300 samples each: a few percent of the box
+            nrows += 1
+    assert nrows >= 4 + 40

@@ -266,3 +266,117 @@ def test_pipeline_equals_one_by_one(tmp_path):
         code = nm[:-4]
         a, b = _tree(str(tmp_path / "single" / (code + "_out"))), _tree(str(tmp_path / "pipe" / (code + "_out")))
         assert a == b and len(a) >= 9
+
+
+# ---- dpocket: reader in ligand mode, table rows, the loop --------------------------------------------------------------------------------
+def _complex(tmp_path, name, seed, n, nlig=24, hetatm_extra=False):
+    import synth
+    s = synth.generate(seed, n, 0.065)
+    rng = np.random.default_rng(seed)
+    c = s.xyz[rng.integers(0, s.n)]
+    lig = (c + rng.normal(scale=2.0, size=(nlig, 3))).astype(np.float32)
+    path = str(tmp_path / name)
+    synth.to_pdb(s, path, lig_xyz=lig)
+    if hetatm_extra:        # a water, a listed cofactor (kept as protein) and an unlisted group (dropped in ligand mode) before END
+        txt = open(path).read().replace("END\n", "")
+        txt += "HETATM90001  O   HOH A9100    %8.3f%8.3f%8.3f  1.00 20.00           O\n" % tuple(c + 9)
+        txt += "HETATM90002 ZN    ZN A9101    %8.3f%8.3f%8.3f  1.00 20.00          ZN\n" % tuple(c - 7)
+        txt += "HETATM90003  C1  XYZ A9102    %8.3f%8.3f%8.3f  1.00 20.00           C\nEND\n" % tuple(c + 6)
+        open(path, "w").write(txt)
+    return path, s
+
+
+@needs_ref_io
+def test_reader_ligand_mode_equals_reference(tmp_path):
+    """dpocket loads a complex with rpdb_open / rpdb_read(ligan = residue name) (dpocket.c:186-203): ligand atoms only in pdb_w_lig, other
+    HETATM groups only when listed. Same arrays, same ligand atom list as the reference's reader."""
+    path, s = _complex(tmp_path, "c.pdb", 20268201, 800, hetatm_extra=True)
+    dump = path + ".dump"
+    r = subprocess.run([REF_IO, "atoms", dump, "--lig", "LIG", "-f", path], capture_output=True)
+    assert r.returncode == 0, r.stderr[-200:]
+    d = dumpio.read_dump(dump)
+    p = hostio.PdbFile(path, opts=hostio.ReadOpts.make(ligand="LIG"))
+    a = p.arrays()
+    assert a["n"] == int(d["n"][0]) == s.n + 1 and a["nw"] == int(d["nw"][0]) == s.n + 1 + 24          # + ZN; + ZN + ligand
+    for k in ("x", "y", "z", "radius", "electroneg", "bfactor", "bfstat", "wx", "wy", "wz", "wradius", "welectroneg"):
+        assert np.array_equal(a[k].view(np.uint32), d[k].view(np.uint32)), k
+    for k in ("atom_id", "res_id", "flags", "wflags"):
+        assert np.array_equal(a[k], d[k]), k
+    st = p.structure
+    assert p.nligand() == st.n_lig == 24
+    assert np.array_equal(np.ctypeslib.as_array(st.lig_atoms, (24,)), d["lig"])
+    assert list(np.ctypeslib.as_array(st.lig_mol, (24,))) == [0] * 24
+    for wl, pfx in ((0, "pdb"), (1, "pdbw")):
+        t, iv = p.atom_text(wl)
+        assert np.array_equal(iv, d[pfx + ".irc"]) and np.array_equal(t, d[pfx + ".text"])
+        assert p.nhetatm(wl) == int(d[pfx + ".nhetatm"][0])
+    p.close()
+    # no such ligand: dpocket.c:189 "ERROR - No ligand"
+    h = C.c_void_p()
+    o = hostio.ReadOpts.make(ligand="QQQ")
+    assert hostio.lib().fpkio_read_pdb(path.encode(), C.byref(o), C.byref(h)) == hostio.FPKIO_ERR_NO_LIGAND
+
+
+@needs_ref_io
+@needs_sample
+def test_reader_ligand_mode_on_1uyd(tmp_path):
+    dst = str(tmp_path / "1UYD.pdb")
+    shutil.copy(os.path.join(SAMPLE, "1UYD.pdb"), dst)
+    r = subprocess.run([REF_IO, "atoms", dst + ".dump", "--lig", "PU8", "-f", dst], capture_output=True)
+    assert r.returncode == 0
+    d = dumpio.read_dump(dst + ".dump")
+    p = hostio.PdbFile(dst, opts=hostio.ReadOpts.make(ligand="PU8"))
+    a = p.arrays()
+    assert a["n"] == int(d["n"][0]) and a["nw"] == int(d["nw"][0])
+    for k in ("x", "y", "z", "radius", "electroneg", "bfactor", "wx", "wy", "wz", "wradius"):
+        assert np.array_equal(a[k].view(np.uint32), d[k].view(np.uint32)), k
+    st = p.structure
+    assert st.n_lig == len(d["lig"]) > 10 and np.array_equal(np.ctypeslib.as_array(st.lig_atoms, (st.n_lig,)), d["lig"])
+
+
+def test_dpocket_loop_with_the_oracle_as_detector(tmp_path):
+    """fpkio_run_dpocket: complexes + ligand names in, <code>_out/ directories and the three tables out (header of dpocket.h:42, one
+    explicit-pocket row per complex in list order, every pocket in exactly one of the two other tables by the rule of dpocket.c:277)."""
+    L = O.lib()
+    prm = api.default_params()
+    prm.mc_seed = 5
+    paths, ligs = [], []
+    for i, n in enumerate((700, 900, 800)):
+        pth, _ = _complex(tmp_path, "c%d.pdb" % i, 20268300 + i, n)
+        paths.append(pth)
+        ligs.append("LIG")
+    npk = []
+
+    def detect(inp, n, pp, out):
+        for k in range(n):
+            assert inp[k].n_lig == 24
+            L.orc_search_pocket(C.byref(inp[k]), pp, None, 0, O.RNG_PHILOX, C.byref(out[k]))
+            npk.append(out[k].n_pockets)
+        return 0
+
+    def free_result(r):
+        L.orc_result_free(r)
+
+    outs = [str(tmp_path / nm) for nm in ("exp.txt", "fp.txt", "fpn.txt")]
+    st = hostio.run_dpocket(paths, ligs, prm, outs, detect=detect, free_result=free_result, group=2, io_threads=3)
+    assert st["n_files"] == 3 and st["n_written"] == 3 and st["n_read_failed"] == 0
+    tabs = [open(o).read().splitlines() for o in outs]
+    for t in tabs:
+        assert t[0].startswith("pdb lig overlap PP-crit PP-dst crit4 crit5 crit6 crit6_continue lig_vol pock_vol nb_AS") and t[0].endswith("TYR VAL")
+    assert [ln.split()[0] for ln in tabs[0][1:]] == paths and all(ln.split()[1] == "LIG" for ln in tabs[0][1:])
+    assert len(tabs[1]) - 1 + len(tabs[2]) - 1 == sum(npk)
+    ncol = len(tabs[0][0].split())
+    for t in tabs:
+        for ln in t[1:]:
+            f = ln.split()
+            assert len(f) == ncol
+            ovlp, dst, ligvol = float(f[2]), float(f[4]), float(f[9])
+            assert 0.0 <= ovlp <= 100.0 and dst >= 0.0 and 50.0 < ligvol < 2000.0
+    for ln in tabs[1][1:]:
+        f = ln.split()
+        assert float(f[2]) > 40.0 or float(f[4]) < 4.0
+    for ln in tabs[2][1:]:
+        f = ln.split()
+        assert not (float(f[2]) > 40.0 or float(f[4]) < 4.0)
+    for pth in paths:
+        assert os.path.exists(pth[:-4] + "_out/" + os.path.basename(pth)[:-4] + "_info.txt")
