@@ -82,7 +82,9 @@ def lib():
         L.fpkio_free_rows.argtypes = [C.POINTER(C.c_void_p)]
         L.fpkio_free_rows.restype = None
         L.fpkio_run_dpocket.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int, C.POINTER(capi.FpkParams), DETECT_FN, FREE_FN,
-                                        C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.POINTER(Stats)]
+                                        C.POINTER(C.c_char_p), C.c_char, C.c_int, C.c_int, C.c_int, C.POINTER(Stats)]
+        L.fpkio_write_output_mode.argtypes = [vp, C.c_char_p, C.POINTER(capi.FpkResult), C.c_char, C.POINTER(C.c_longlong)]
+        L.fpkio_write_output_mode.restype = C.c_int
         L.fpkio_run_dpocket.restype = C.c_int
         _lib = L
     return _lib
@@ -211,7 +213,7 @@ def run_list(paths, params, detect=None, free_result=None, group=0, io_threads=0
     return st.as_dict()
 
 
-def run_dpocket(paths, ligands, params, out_paths, detect=None, free_result=None, group=0, io_threads=0, quiet=1):
+def run_dpocket(paths, ligands, params, out_paths, detect=None, free_result=None, group=0, io_threads=0, quiet=1, write_mode="d"):
     """dpocket's loop (dpocket.c:83-130): complexes + ligand residue names in, <code>_out/ directories and the three tables out."""
     L = lib()
     if detect is None:
@@ -227,7 +229,7 @@ def run_dpocket(paths, ligands, params, out_paths, detect=None, free_result=None
     la = (C.c_char_p * n)(*[l.encode() for l in ligands])
     oa = (C.c_char_p * 3)(*[o.encode() for o in out_paths])
     st = Stats()
-    rc = L.fpkio_run_dpocket(pa, la, n, C.byref(params), detect, free_result, oa, group, io_threads, quiet, C.byref(st))
+    rc = L.fpkio_run_dpocket(pa, la, n, C.byref(params), detect, free_result, oa, write_mode.encode(), group, io_threads, quiet, C.byref(st))
     if rc != FPKIO_OK:
         raise RuntimeError("fpkio_run_dpocket failed: %d" % rc)
     return st.as_dict()

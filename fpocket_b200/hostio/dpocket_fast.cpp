@@ -62,7 +62,10 @@ int main(int argc, char **argv)
                       o2 = prefix.empty() ? "dpout_fpocketnp.txt" : prefix + "_fpn.txt";
     const char *outs[3] = {o0.c_str(), o1.c_str(), o2.c_str()};
     fpkio_stats S;
-    const int rc = fpkio_run_dpocket(pp.data(), ll.data(), (int)pp.size(), &P, fpk_detect_batch, fpk_result_free, outs, group, threads, quiet, &S);
+    // the reference decides its write mode from the name of the "input file", which for dpocket is the list (dparams.c:98, fparams.c:397-407)
+    const char wmode = strstr(listf.c_str(), ".pdb") ? 'p' : 'd';
+    if (strstr(listf.c_str(), ".cif")) { fprintf(stderr, "! a list name containing .cif selects the mmCIF writers: use build/dpocket_cuda\n"); return 3; }
+    const int rc = fpkio_run_dpocket(pp.data(), ll.data(), (int)pp.size(), &P, fpk_detect_batch, fpk_result_free, outs, wmode, group, threads, quiet, &S);
     if (rc != FPKIO_OK) fprintf(stderr, "! dpocket_fast: %d (%s)\n", rc, fpk_last_error());
     if (want_stats)
         printf("dpocket_fast: %d complexes, %d written (%lld pockets), %d unreadable / without ligand, %d failed | %.3f s wall, %.1f complexes/s | "

@@ -570,7 +570,14 @@ int fpkio_atom_text(const fpkio_file *f, int with_lig, int k, char *type, char *
 
 int fpkio_write_output(const fpkio_file *F, const char *pdb_path, const fpk_result *R, long long *bytes_out)
 {
+    return fpkio_write_output_mode(F, pdb_path, R, 'p', bytes_out);
+}
+
+int fpkio_write_output_mode(const fpkio_file *F, const char *pdb_path, const fpk_result *R, char write_mode, long long *bytes_out)
+{
     if (!F || !pdb_path || !R) return FPKIO_ERR_BAD_ARG;
+    if (write_mode != 'p' && write_mode != 'd') return FPKIO_ERR_UNSUPPORTED;      // 'm' / 'b': the mmCIF writers are not restated
+    const bool pdb_files = write_mode == 'p';
     // ---- names (fpout.c:71-80): remove_ext on the whole path, then remove_path ----
     std::string code = pdb_path, dir;
     { const size_t sl = code.rfind('/'); if (sl != std::string::npos) dir = code.substr(0, sl); }
@@ -583,12 +590,15 @@ int fpkio_write_output(const fpkio_file *F, const char *pdb_path, const fpk_resu
     const float *fx = R->atom_fx;
     bool ok = true;
     Out o;
-    // ---- write_visualization (write_visu.c:56-290) ----
-    o.clear(); substitute(o, TPL_VMD_SH, code);   ok &= write_file(base + "_VMD.sh", o, 0777, bytes_out);
-    o.clear(); substitute(o, TPL_TCL, code);      ok &= write_file(base + ".tcl", o, 0666, bytes_out);
-    o.clear(); substitute(o, TPL_PYMOL_SH, code); ok &= write_file(base + "_PYMOL.sh", o, 0777, bytes_out);
-    o.clear(); substitute(o, TPL_PML, code);      ok &= write_file(base + ".pml", o, 0666, bytes_out);
+    // ---- write_visualization (write_visu.c:56-290): only in PDB mode ----
+    if (pdb_files) {
+        o.clear(); substitute(o, TPL_VMD_SH, code);   ok &= write_file(base + "_VMD.sh", o, 0777, bytes_out);
+        o.clear(); substitute(o, TPL_TCL, code);      ok &= write_file(base + ".tcl", o, 0666, bytes_out);
+        o.clear(); substitute(o, TPL_PYMOL_SH, code); ok &= write_file(base + "_PYMOL.sh", o, 0777, bytes_out);
+        o.clear(); substitute(o, TPL_PML, code);      ok &= write_file(base + ".pml", o, 0666, bytes_out);
+    }
     // ---- <code>_out.pdb: every atom of pdb, then the spheres pocket by pocket (writepocket.c:262-305, voronoi.c:1437-1482) ----
+    if (pdb_files) {
     o.clear();
     o.room((size_t)(n + R->n_spheres) * 82 + 256);
     for (int k = 0; k < n; k++) atom_line(o, F->watoms[F->nolig[k]], fx ? fx + 4 * (size_t)k : nullptr);
@@ -604,6 +614,7 @@ int fpkio_write_output(const fpkio_file *F, const char *pdb_path, const fpk_resu
         }
     }
     ok &= write_file(base + "_out.pdb", o, 0666, bytes_out);
+    }
     // ---- <code>_info.txt (fpout.c:151-213) ----
     o.clear();
     for (int r = 0; r < R->n_pockets; r++) {
@@ -684,6 +695,7 @@ int fpkio_write_output(const fpkio_file *F, const char *pdb_path, const fpk_resu
         snprintf(nm, sizeof nm, "/pocket%d_vert.pqr", r + 1);
         ok &= write_file(pdir + nm, o, 0666, bytes_out);
 
+        if (!pdb_files) continue;          // writepocket.c:492-500: pocketN_atm.pdb only in PDB mode
         o.clear();
         o.put("HEADER\n"
               "HEADER This is a pdb format file writen by the programm fpocket.                 \n"
@@ -1027,17 +1039,19 @@ int fpkio_dpocket_rows(const fpkio_file *f, const char *fc, const char *lig, con
 void fpkio_free_rows(char *rows[3]) { if (rows) for (int k = 0; k < 3; k++) { free(rows[k]); rows[k] = nullptr; } }
 
 int fpkio_run_dpocket(const char *const *paths, const char *const *ligands, int n, const fpk_params *p, fpkio_detect_fn detect,
-                      fpkio_free_fn free_result, const char *const out_paths[3], int group, int io_threads, int quiet, fpkio_stats *stats)
+                      fpkio_free_fn free_result, const char *const out_paths[3], char write_mode, int group, int io_threads, int quiet, fpkio_stats *stats)
 {
     if (!paths || !ligands || n < 0 || !p || !out_paths) return FPKIO_ERR_BAD_ARG;
+    if (write_mode && write_mode != 'p' && write_mode != 'd') return FPKIO_ERR_UNSUPPORTED;
     std::vector<fpkio_read_opts> ro((size_t)n);
     for (int k = 0; k < n; k++) { memset(&ro[k], 0, sizeof ro[k]); snprintf(ro[k].ligand, sizeof ro[k].ligand, "%s", ligands[k] ? ligands[k] : ""); if (!ro[k].ligand[0] || !ro[k].ligand[1]) return FPKIO_ERR_BAD_ARG; }
     std::vector<std::string> rows((size_t)3 * n);                    // kept per complex: the tables are written in list order at the end
     const uint64_t seed = p->mc_seed;
     const int niter = p->nb_mcv_iter;
+    const char wmode = write_mode ? write_mode : 'd';
     const int rc = run_pipeline(paths, n, [&ro](int k) { return &ro[k]; }, p, detect, free_result, group, io_threads, quiet, stats,
                                 [&](int k, const fpkio_file *f, const fpk_result *r, long long *bytes) {
-                                    const int w = fpkio_write_output(f, paths[k], r, bytes);                 // dpocket.c:233
+                                    const int w = fpkio_write_output_mode(f, paths[k], r, wmode, bytes);      // dpocket.c:233
                                     if (w < 0) return w;
                                     char *t[3] = {nullptr, nullptr, nullptr};
                                     const float vol = fpkio_ligand_volume(f, niter, seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(k + 1)));

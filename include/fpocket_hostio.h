@@ -66,6 +66,10 @@ int  fpkio_atom_text(const fpkio_file *f, int with_lig, int k, char *type, char 
  * reference does with the empty list search_pocket returns (fpocket.c:225); only a failed clustering tree (FPK_ERR_NO_SPHERES) makes the
  * caller print "no pockets found" (fpmain.c:204). Returns the number of pockets written or FPKIO_ERR_*. bytes_out (may be NULL) += bytes. */
 int  fpkio_write_output(const fpkio_file *f, const char *pdb_path, const fpk_result *r, long long *bytes_out);
+/* the reference's global write_mode (fparams.c:60,397-407): 'p' = the PDB set above (what fpocket chooses for a .pdb input); 'd' = undecided:
+ * only _info.txt, _pockets.pqr and pockets/pocketK_vert.pqr are written - this is what the reference's dpocket leaves, because there the "input
+ * file" that decides the mode is the LIST file (dparams.c:98), whose name normally contains neither ".pdb" nor ".cif" */
+int  fpkio_write_output_mode(const fpkio_file *f, const char *pdb_path, const fpk_result *r, char write_mode, long long *bytes_out);
 
 /* ---- dpocket (dpocket.c:166-300) ------------------------------------------------------------------------------------------ */
 int  fpkio_nligand(const fpkio_file *f);                          /* pdb_cplx_l->natm_lig (the structure then carries n_lig / lig_atoms / lig_mol / atom_name_key) */
@@ -82,7 +86,8 @@ typedef int  (*fpkio_detect_fn)(const fpk_structure *in, int n, const fpk_params
 typedef void (*fpkio_free_fn)(fpk_result *r);
 struct fpkio_stats;
 int  fpkio_run_dpocket(const char *const *paths, const char *const *ligands, int n, const fpk_params *p, fpkio_detect_fn detect,
-                       fpkio_free_fn free_result, const char *const out_paths[3], int group, int io_threads, int quiet, struct fpkio_stats *stats);
+                       fpkio_free_fn free_result, const char *const out_paths[3], char write_mode /* 'd' (dpocket's usual) or 'p' */,
+                       int group, int io_threads, int quiet, struct fpkio_stats *stats);
 
 /* ---- the -F loop ------------------------------------------------------------------------------------------------------- */
 typedef struct fpkio_stats {

@@ -151,6 +151,7 @@ int main(int argc, char **argv)
     R.sph_cluster = slurp(f, ns * 4); R.cl_off = slurp(f, (nc + 1) * 4); R.cl_sph = slurp(f, ns * 4); R.desc = slurp(f, nc * sizeof(fpk_desc));
     R.rank_to_cluster = slurp(f, np * 4); R.atom_fx = slurp(f, na * 16);
     fclose(f);
+    if (getenv("REF_IO_WRITE_MODE")) { extern char write_mode[10]; strncpy(write_mode, getenv("REF_IO_WRITE_MODE"), 9); }   /* dpocket leaves it at "d" */
     c_lst_pockets *pockets = shim_rebuild(pdb, params, pdbw, &R, np ? FPK_OK : FPK_ERR_NO_POCKETS, 1);
     if (pockets) {                                         /* a list with no pocket left is still written (fpocket.c:225 returns it) */
         write_out_fpocket(pockets, pdb, pdbname);          /* fpmain.c:195 */

@@ -124,11 +124,17 @@ def test_dpocket_fast_equals_reference_io_around_the_library(tmp_path):
     da, db = tmp_path / "fast", tmp_path / "refio"
     da.mkdir(), db.mkdir()
     names = []
+    from fpocket_b200 import api
     for i, n in enumerate((2100, 2600, 3200, 2300)):
         s = synth.generate(20267900 + i, n, 0.065)
         rng = np.random.default_rng(40 + i)
-        c = s.xyz[rng.integers(0, s.n)] * 0.6 + s.xyz.mean(0) * 0.4
-        lig = (c + rng.normal(scale=2.2, size=(26, 3))).astype(np.float32)
+        if i < 3:       # the ligand sits in the best pocket of a first pass (as in bench.py); the last one is buried: no explicit pocket
+            r0 = api.detect(synth.to_structure(s), api.default_params())
+            c = r0["desc"]["bary"][r0["rank_to_cluster"][0]]
+            lig = synth.make_ligand(rng, c, natoms=26)
+        else:
+            c = s.xyz[rng.integers(0, s.n)] * 0.6 + s.xyz.mean(0) * 0.4
+            lig = (c + rng.normal(scale=2.2, size=(26, 3))).astype(np.float32)
         names.append("d%d.pdb" % i)
         for d in (da, db):
             synth.to_pdb(s, str(d / names[-1]), lig_xyz=lig)
@@ -141,13 +147,17 @@ def test_dpocket_fast_equals_reference_io_around_the_library(tmp_path):
     for nm in names:
         code = nm[:-4]
         a, b = _tree(str(da / (code + "_out"))), _tree(str(db / (code + "_out")))
-        assert a == b and len(a) >= 15, (code, sorted(k for k in set(a) | set(b) if a.get(k) != b.get(k))[:5])
+        assert a == b and len(a) >= 8, (code, sorted(k for k in set(a) | set(b) if a.get(k) != b.get(k))[:5])
     nrows = 0
     for tab in ("dpout_explicitp.txt", "dpout_fpocketp.txt", "dpout_fpocketnp.txt"):
         ta, tb = (da / tab).read_text().splitlines(), (db / tab).read_text().splitlines()
         assert ta[0] == tb[0] and len(ta) == len(tb), tab
         for x, y in zip(ta[1:], tb[1:]):
             fx, fy = x.split(), y.split()
+            if tab == "dpout_explicitp.txt" and fx[11] == "0":
+                # no sphere within reach of the ligand: the reference prints a record it never filled, and reset_desc() does not reset n_abpa
+                # (descriptors.c:88-130) - that column is whatever my_malloc returned
+                fx[36] = fy[36] = "-"
             assert fx[:9] == fy[:9] and fx[10:] == fy[10:], (tab, x, y)
             vx, vy = float(fx[9]), float(fy[9])
             assert abs(vx - vy) <= 0.25 * max(vx, vy) + 5.0, (tab, vx, vy)           # 300 samples each: a few percent of the box

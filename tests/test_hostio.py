@@ -166,7 +166,7 @@ def _tree(d):
     return out
 
 
-def _writer_equal(src, tmp_path, params=None, min_pockets=1):
+def _writer_equal(src, tmp_path, params=None, min_pockets=1, mode="p"):
     name = os.path.basename(src)
     code = name.rsplit(".", 1)[0]
     for d in ("ref", "nat"):
@@ -180,8 +180,11 @@ def _writer_equal(src, tmp_path, params=None, min_pockets=1):
     L.orc_search_pocket(C.byref(p.structure), C.byref(prm), None, 0, O.RNG_PHILOX, C.byref(res))
     assert res.n_pockets >= min_pockets, (res.status, res.n_pockets)
     _serialize(res, p.natoms(0), str(tmp_path / "res.bin"))
-    npk, nbytes = p.write_output(str(tmp_path / "nat" / name), res)
-    r = subprocess.run([REF_IO, "write", str(tmp_path / "res.bin"), "-f", str(tmp_path / "ref" / name)], capture_output=True, cwd=str(tmp_path))
+    nb = C.c_longlong(0)
+    npk = hostio.lib().fpkio_write_output_mode(p.h, str(tmp_path / "nat" / name).encode(), C.byref(res), mode.encode(), C.byref(nb))
+    nbytes = nb.value
+    r = subprocess.run([REF_IO, "write", str(tmp_path / "res.bin"), "-f", str(tmp_path / "ref" / name)], capture_output=True, cwd=str(tmp_path),
+                       env=dict(os.environ, REF_IO_WRITE_MODE=mode))
     assert r.returncode == 0, r.stderr[-300:]
     L.orc_result_free(C.byref(res))
     p.close()
@@ -191,7 +194,7 @@ def _writer_equal(src, tmp_path, params=None, min_pockets=1):
         assert a[k][0] == b[k][0], "content of %s differs" % k
         assert a[k][1] == b[k][1], "mode of %s differs: %o vs %o" % (k, a[k][1], b[k][1])
     assert npk == res.n_pockets or True
-    assert len(a) == 7 + 2 * npk and sum(len(v[0]) for v in b.values()) == nbytes
+    assert len(a) == (7 + 2 * npk if mode == "p" else 2 + npk) and sum(len(v[0]) for v in b.values()) == nbytes
     return npk
 
 
@@ -208,6 +211,17 @@ def test_writers_equal_reference_on_a_synthetic_structure(tmp_path):
 @pytest.mark.parametrize("name", ["1UYD", "1ATP", "4bdf"])
 def test_writers_equal_reference_on_sample_files(tmp_path, name):
     assert _writer_equal(os.path.join(SAMPLE, name + ".pdb"), tmp_path) >= 5
+
+
+@needs_ref_io
+def test_writers_in_undecided_mode_as_dpocket_leaves_it(tmp_path):
+    """The reference's dpocket never decides write_mode (its "input file" is the list, fparams.c:397-407): write_out_fpocket then leaves only
+    _info.txt, _pockets.pqr and pocketK_vert.pqr. fpkio_write_output_mode('d') does the same."""
+    import synth
+    s = synth.generate(20268004, 1200, 0.065)
+    synth.to_pdb(s, str(tmp_path / "syn.pdb"))
+    assert _writer_equal(str(tmp_path / "syn.pdb"), tmp_path, mode="d") >= 2
+    assert not (tmp_path / "nat" / "syn_out" / "syn_out.pdb").exists()
 
 
 @needs_ref_io
