@@ -394,3 +394,27 @@ def test_dpocket_loop_with_the_oracle_as_detector(tmp_path):
         assert not (float(f[2]) > 40.0 or float(f[4]) < 4.0)
     for pth in paths:
         assert os.path.exists(pth[:-4] + "_out/" + os.path.basename(pth)[:-4] + "_info.txt")
+
+
+def test_fast_programs_fail_loudly_without_a_gpu(tmp_path):
+    """build/fpocket_fast and build/dpocket_fast have no CPU detection path: without a usable sm_100 device they stop with the library's
+    error before anything is written; and they refuse, by name, the options whose routes are not restated."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import synth
+    fast, dfast = os.path.join(ROOT, "build", "fpocket_fast"), os.path.join(ROOT, "build", "dpocket_fast")
+    if not (os.path.exists(fast) and os.path.exists(dfast)):
+        pytest.skip("build/fpocket_fast not built")
+    s = synth.generate(20268401, 500, 0.065)
+    synth.to_pdb(s, str(tmp_path / "x.pdb"))
+    r = subprocess.run([fast, "-f", "x.pdb"], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 4 and "no CPU fallback" in r.stderr and not (tmp_path / "x_out").exists()
+    (tmp_path / "l.txt").write_text("x.pdb\tLIG\n")
+    r = subprocess.run([dfast, "-f", "l.txt"], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 4 and "no CPU fallback" in r.stderr and not (tmp_path / "dpout_explicitp.txt").exists()
+    for opt in (["-r", "1:LIG:A"], ["-a", "B"], ["-w", "m"], ["-C", "m"]):
+        r = subprocess.run([fast, "-f", "x.pdb"] + opt, cwd=str(tmp_path), capture_output=True, text=True)
+        assert r.returncode == 3 and "fpocket_cuda_batch" in r.stderr, (opt, r.stderr)
+    r = subprocess.run([fast, "-f", "x.cif"], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 3 and "mmCIF" in r.stderr
