@@ -9,7 +9,8 @@
 // --devices: one worker process per listed GPU (independent structures: no collective), file k of the list goes to worker k mod N; each
 // worker is this same program restricted to its device through CUDA_VISIBLE_DEVICES, with the I/O pool divided among them.
 //
-// Options outside the restated route (mmCIF input or -w m/b, -a, -r, -P, -l, -d, -x, -C != s, -e != e) are refused with a pointer to
+// -r resnumber:resname:chain (explicit ligand) and -P res:ins:chain.res:ins:chain (explicit pocket, -u) are handled as the reference does.
+// Options outside the restated route (mmCIF input or -w m/b, -a, -l, -d, -x, -C != s, -e != e) are refused with a pointer to
 // build/fpocket_cuda_batch (reference reader / writers around the same library). There is no CPU detection path.
 #include <cstdio>
 #include <cstdlib>
@@ -69,6 +70,9 @@ int main(int argc, char **argv)
         else if (o == "-A" || o == "--number_apol_asph_pocket") P.min_apol_neigh = atoi(val());
         else if (o == "-p" || o == "--ratio_apol_spheres_pocket") P.refine_min_apolar_asphere_prop = (float)atof(val());
         else if (o == "-v" || o == "--iterations_volume_mc") P.nb_mcv_iter = atoi(val());
+        else if (o == "-r" || o == "--custom_ligand") { fpkio_parse_custom_ligand(val(), &ro); }
+        else if (o == "-P" || o == "--custom_pocket") { fpkio_parse_custom_pocket(val(), &ro); }
+        else if (o == "-u" || o == "--min_n_explicit_pocket") P.min_n_explicit_pocket_atoms = atoi(val());
         else if (o == "-c" || o == "--drop_chains") chains(val(), 0);
         else if (o == "-k" || o == "--keep_chains") chains(val(), 1);
         else if (o == "-C" || o == "--clustering_method") { if (val()[0] != 's') return refuse("-C other than s (single linkage)"); }
@@ -80,11 +84,17 @@ int main(int argc, char **argv)
         else if (o == "--slice") { if (sscanf(val(), "%d/%d", &slice_k, &slice_n) != 2 || slice_n < 1 || slice_k < 0 || slice_k >= slice_n) { fprintf(stderr, "! bad --slice\n"); return 2; } }
         else if (o == "--quiet") quiet = 1;
         else if (o == "--stats") want_stats = 1;
-        else if (o == "-a" || o == "-r" || o == "-P" || o == "-l" || o == "-d" || o == "-x" || o == "-y" || o == "-u" || o == "-b") return refuse(o.c_str());
+        else if (o == "-a" || o == "-l" || o == "-d" || o == "-x" || o == "-y" || o == "-b") return refuse(o.c_str());
         else { fprintf(stderr, "! unknown option %s\n", o.c_str()); return 2; }
     }
     if (files.empty()) { fprintf(stderr, "usage: %s -f X.pdb | -F list.txt [fpocket detection options] [--threads T] [--group G] [--quiet] [--stats] [--devices 0,1,..]\n", argv[0]); return 2; }
     for (const auto &f : files) if (strstr(f.c_str(), ".cif")) return refuse("mmCIF input");
+    if (ro.n_xpocket > 0 && ro.has_xlig) {                   // fparams.c:409-413
+        fprintf(stderr, "\nERROR: you specified an explicit ligand (-r) AND an explicit pocke (-P) in the same fpocket run. This is currently not allowed, please use either the one or the other.\n\n");
+        return 2;
+    }
+    P.skip_clustering = (ro.has_xlig || ro.n_xpocket > 0) ? 1 : 0;                            // fpocket.c:114
+    P.xpocket_active = ro.n_xpocket > 0 ? 1 : 0;
     if (devices.size() > 1) {
         // one worker per GPU: re-run this command line with --slice k/N under CUDA_VISIBLE_DEVICES=<device k>
         const int nd = (int)devices.size();

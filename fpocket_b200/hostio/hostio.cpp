@@ -230,6 +230,7 @@ struct fpkio_file {
     std::vector<int32_t> iv;            // 2 x n: id res_id
     std::vector<int8_t> aa;
     std::vector<uint8_t> fl, wfl;
+    std::vector<float> xlig;            // -r: xyz triplets of the explicit ligand's records (pdb->xlig_x/y/z)
     std::vector<int32_t> lig_idx, lig_mol, name_key;   // dpocket: the known ligand (indices into watoms), its molecules, atom names of pdb packed
     fpk_structure st;
     long long bytes = 0;
@@ -287,6 +288,7 @@ int parse_pdb(const char *path, const char *data, size_t size, const fpkio_read_
     const char *p = data, *end = data + size;
     float x = 0, y = 0, z = 0;
     const bool ligmode = opts && opts->ligand[0] && opts->ligand[1];
+    const bool xlig = opts && opts->has_xlig;
     while (p < end) {
         size_t n = (size_t)(end - p) < (size_t)LINE_MAX_CHARS ? (size_t)(end - p) : (size_t)LINE_MAX_CHARS;
         if (const void *nl = memchr(p, '\n', n)) n = (size_t)((const char *)nl - p) + 1;
@@ -297,6 +299,15 @@ int parse_pdb(const char *path, const char *data, size_t size, const fpkio_read_
         if (is_atom || is_het) {
             if (!chain_passes(opts, L[21])) continue;
             x = slice_atof(L + 30, 8); y = slice_atof(L + 38, 8); z = slice_atof(L + 46, 8);
+            if (xlig && x < 9990 && y < 9990 && z < 9990) {      // rpdb.c:893-903,962-973: every record of the residue, whatever its alt-loc
+                char rb[8];
+                slice_strncpy(rb, L + 17, 4);
+                str_trim(rb);
+                if (opts->xlig_chain && L[21] == opts->xlig_chain && slice_atoi(L + 22, 4) == opts->xlig_resnumber &&
+                    opts->xlig_resname[0] == rb[0] && opts->xlig_resname[1] == rb[1] && opts->xlig_resname[2] == rb[2]) {
+                    F->xlig.push_back(x); F->xlig.push_back(y); F->xlig.push_back(z);
+                }
+            }
             if (!((L[16] == ' ' || L[16] == 'A') && x < 9990 && y < 9990 && z < 9990)) continue;
             bool in_lig = true, in_nolig = true, is_ligand_atom = false;
             char resb[8];
@@ -335,6 +346,10 @@ int parse_pdb(const char *path, const char *data, size_t size, const fpkio_read_
         uint8_t fl = 0;
         if (!strcmp(a.symbol, "H")) { fl |= FPK_ATOM_H; nh++; }
         if (a.symbol[0] == 'H') fl |= FPK_ATOM_H1;
+        if (opts && opts->n_xpocket > 0)                       // atom_in_explicit_pocket (voronoi.c:934-949)
+            for (int q = 0; q < opts->n_xpocket && q < 64; q++)
+                if (opts->xp_res[q] == a.res_id && opts->xp_chain[q] == a.chain[0] &&
+                    (opts->xp_ins[q] == a.insert || (opts->xp_ins[q] == '-' && (a.insert == ' ' || a.insert == 0)))) { fl |= FPK_ATOM_XPOCKET; break; }
         F->fl[k] = fl;
         avg += a.bf;
         if (a.bf < mn) mn = a.bf;
@@ -356,6 +371,7 @@ int parse_pdb(const char *path, const char *data, size_t size, const fpkio_read_
     s.wx = F->wf.data(); s.wy = s.wx + nw; s.wz = s.wx + 2 * (size_t)nw; s.wradius = s.wx + 3 * (size_t)nw; s.welectroneg = s.wx + 4 * (size_t)nw;
     s.wflags = F->wfl.data();
     s.same_pdb = 0;                     // fpmain.c:143-144: two objects
+    if (!F->xlig.empty()) { s.n_xlig = (int32_t)(F->xlig.size() / 3); s.xlig = F->xlig.data(); }
     if (ligmode) {
         if (F->lig_idx.empty()) { delete F; return FPKIO_ERR_NO_LIGAND; }
         // ligand molecules: runs of equal (chain, res_id) in file order (dpocket.c:211-222, neighbor.c:619-637)
@@ -994,6 +1010,48 @@ int fpkio_run_list(const char *const *paths, int n, const fpkio_read_opts *ropts
 }
 
 int fpkio_nligand(const fpkio_file *f) { return f ? (int)f->lig_idx.size() : 0; }
+
+int fpkio_parse_custom_ligand(const char *arg, fpkio_read_opts *o)          // fparams.c:241-262: strtok(optarg, ":"): number, name, chain
+{
+    if (!arg || !o) return FPKIO_ERR_BAD_ARG;
+    char tmp[256];
+    snprintf(tmp, sizeof tmp, "%s", arg);
+    int i = 0;
+    o->has_xlig = 1; o->xlig_resnumber = -1; o->xlig_resname[0] = 0; o->xlig_chain = 0;
+    for (char *t = strtok(tmp, ":"); t; t = strtok(nullptr, ":")) {
+        i++;
+        if (i == 1) o->xlig_resnumber = atoi(t);
+        else if (i == 2) snprintf(o->xlig_resname, sizeof o->xlig_resname, "%s", t);
+        else if (i == 3) o->xlig_chain = t[0];
+    }
+    if (o->xlig_resnumber <= -1) o->has_xlig = 0;          // "xlig_resnumber > -1" is the reference's test everywhere
+    return FPKIO_OK;
+}
+
+int fpkio_parse_custom_pocket(const char *arg, fpkio_read_opts *o)          // fparams.c:263-300
+{
+    if (!arg || !o) return FPKIO_ERR_BAD_ARG;
+    char tmp[512], res[256];
+    snprintf(tmp, sizeof tmp, "%s", arg);
+    o->n_xpocket = 0;
+    char *rest = tmp;
+    for (char *pt = strtok_r(rest, ".", &rest); pt && o->n_xpocket < 64; pt = strtok_r(rest, ".", &rest)) {
+        const int q = o->n_xpocket++;
+        o->xp_res[q] = 0; o->xp_ins[q] = 0; o->xp_chain[q] = 0;
+        snprintf(res, sizeof res, "%s", pt);
+        char *rest2 = res;
+        int apti = 0;
+        for (char *apt = strtok_r(rest2, ":", &rest2); apt; apt = strtok_r(rest2, ":", &rest2)) {
+            switch (apti) {                                 // no break in the reference's switch: every field also writes the later ones
+            case 0: o->xp_res[q] = (uint16_t)atoi(apt);     /* fall through */
+            case 1: o->xp_ins[q] = apt[0];                  /* fall through */
+            case 2: o->xp_chain[q] = apt[0];
+            }
+            apti++;
+        }
+    }
+    return FPKIO_OK;
+}
 
 float fpkio_ligand_volume(const fpkio_file *f, int niter, uint64_t seed)
 {

@@ -45,7 +45,19 @@ typedef struct fpkio_read_opts {
     int32_t chains_are_kept;     /* 0: -c (drop these chains), 1: -k (keep only these)         */
     char ligand[8];              /* dpocket: residue name of the known ligand (rpdb_open/rpdb_read with ligan != NULL, dpocket.c:186-203): its atoms
                                     are kept in pdb_w_lig only and flagged as the ligand; other HETATM groups count only when listed. "" = fpocket */
+    /* -r resnumber:resname:chain (fparams.c:241-262): the coordinates of that residue's records become pdb->xlig_* (rpdb.c:893-903,962-973):
+     * testVvertice then keeps only spheres that reach one of them (voronoi.c:1047-1066) and clustering is skipped (fpocket.c:114) */
+    int32_t has_xlig, xlig_resnumber;
+    char xlig_resname[8], xlig_chain;
+    /* -P res:ins:chain.res:ins:chain... (fparams.c:263-300): atoms of these residues get FPK_ATOM_XPOCKET (voronoi.c:934-949) */
+    int32_t n_xpocket;
+    uint16_t xp_res[64];
+    char xp_ins[64], xp_chain[64];
 } fpkio_read_opts;
+
+/* the reference's parsing of the -r and -P arguments, quirks included (strtok skips empty fields; the switch of fparams.c:285-293 falls through) */
+int  fpkio_parse_custom_ligand(const char *arg, fpkio_read_opts *o);
+int  fpkio_parse_custom_pocket(const char *arg, fpkio_read_opts *o);
 
 typedef struct fpkio_file fpkio_file;      /* one parsed input: both atom lists + the flat arrays handed to the library */
 

@@ -127,6 +127,7 @@ int main(int argc, char **argv)
         rec1("wradius", 'f', nw, s->wradius); rec1("welectroneg", 'f', nw, s->welectroneg); rec1("wflags", 'b', nw, s->wflags);
         int sp = s->same_pdb;
         rec1("same_pdb", 'i', 1, &sp);
+        rec1("xlig", 'f', 3 * s->n_xlig, s->xlig);
         dump_text("pdb", pdb);
         dump_text("pdbw", pdbw);
         if (ligname) {

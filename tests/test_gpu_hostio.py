@@ -163,3 +163,23 @@ def test_dpocket_fast_equals_reference_io_around_the_library(tmp_path):
             assert abs(vx - vy) <= 0.25 * max(vx, vy) + 5.0, (tab, vx, vy)           # 300 samples each: a few percent of the box
             nrows += 1
     assert nrows >= 4 + 40
+
+
+@pytest.mark.parametrize("extra", [("-r", "1224:PU8:A"), ("-P", "107:-:A.108:-:A.138:-:A.139:-:A.184:-:A", "-u", "2"), ("-k", "A")])
+def test_explicit_ligand_and_pocket_options_equal_reference_io(tmp_path, extra):
+    """fpocket -r (explicit ligand), -P (explicit pocket) and -k on the reference's 1UYD sample: build/fpocket_fast against the reference's
+    reader and writers around the same library."""
+    import shutil
+    src = os.path.join(ROOT, "build", "samples", "1UYD.pdb")
+    if not (os.path.exists(src) and os.path.exists(FAST) and os.path.exists(BATCH)):
+        pytest.skip("build/samples/1UYD.pdb, build/fpocket_fast or build/fpocket_cuda_batch missing")
+    env = dict(os.environ, FPOCKET_MC_SEED=str(SEED), TMPDIR=str(tmp_path))
+    da, db = tmp_path / "fast", tmp_path / "refio"
+    for d in (da, db):
+        d.mkdir()
+        shutil.copy(src, str(d / "1UYD.pdb"))
+        (d / "list.txt").write_text("1UYD.pdb\n")
+    subprocess.check_call([FAST, "-f", "1UYD.pdb", "--quiet", *extra], cwd=str(da), env=env)
+    subprocess.check_call([BATCH, "list.txt", *extra], cwd=str(db), env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    a, b = _tree(str(da / "1UYD_out")), _tree(str(db / "1UYD_out"))
+    assert a == b and len(a) >= 9, sorted(k for k in set(a) | set(b) if a.get(k) != b.get(k))[:5]

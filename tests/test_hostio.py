@@ -77,6 +77,9 @@ def _reader_equal(path, extra=(), opts=None):
         assert np.array_equal(iv, d[pfx + ".irc"]), (path, pfx)
         assert np.array_equal(t, d[pfx + ".text"]), (path, pfx)
         assert p.nhetatm(wl) == int(d[pfx + ".nhetatm"][0])
+    st = p.structure
+    xl = np.ctypeslib.as_array(st.xlig, (3 * st.n_xlig,)).copy() if st.n_xlig else np.zeros(0, np.float32)
+    assert np.array_equal(xl.view(np.uint32), d["xlig"].view(np.uint32)), (path, "xlig", st.n_xlig, len(d["xlig"]))
     p.close()
     return a["n"]
 
@@ -111,6 +114,28 @@ def test_reader_chain_filters(tmp_path):
     n_c = _reader_equal(dst, ("-c", "A"), hostio.ReadOpts.make(drop=["A"]))
     n_k = _reader_equal(dst, ("-k", "B,C"), hostio.ReadOpts.make(keep=["B", "C"]))
     assert 0 < n_c < n_all and 0 < n_k < n_all
+
+
+@needs_ref_io
+@needs_sample
+def test_reader_explicit_ligand_and_explicit_pocket(tmp_path):
+    """-r number:name:chain collects the coordinates of that residue's records (pdb->xlig_*), -P res:ins:chain.res:ins:chain flags the atoms of
+    those residues (FPK_ATOM_XPOCKET); both arguments are parsed with the reference's quirks (empty fields vanish, the -P switch falls through)."""
+    dst = str(tmp_path / "1UYD.pdb")
+    shutil.copy(os.path.join(SAMPLE, "1UYD.pdb"), dst)
+    o = hostio.ReadOpts.make(custom_ligand="1224:PU8:A")
+    assert o.has_xlig == 1 and o.xlig_resnumber == 1224 and o.xlig_chain == b"A"
+    assert _reader_equal(dst, ("-r", "1224:PU8:A"), o) > 1000
+    p = hostio.PdbFile(dst, opts=o)
+    assert p.structure.n_xlig > 10
+    p.close()
+    for spec, nflag in (("107:-:A.108:-:A.138:-:A", True), ("107::A.108::A", False)):        # "::" -> the insertion code becomes the chain letter: no atom matches
+        o = hostio.ReadOpts.make(custom_pocket=spec)
+        assert _reader_equal(dst, ("-P", spec), o) > 1000
+        p = hostio.PdbFile(dst, opts=o)
+        nf = int((p.arrays()["flags"] & capi.FPK_ATOM_XPOCKET != 0).sum())
+        assert (nf > 10) == nflag, (spec, nf)
+        p.close()
 
 
 @needs_ref_io
@@ -413,7 +438,7 @@ def test_fast_programs_fail_loudly_without_a_gpu(tmp_path):
     (tmp_path / "l.txt").write_text("x.pdb\tLIG\n")
     r = subprocess.run([dfast, "-f", "l.txt"], cwd=str(tmp_path), capture_output=True, text=True)
     assert r.returncode == 4 and "no CPU fallback" in r.stderr and not (tmp_path / "dpout_explicitp.txt").exists()
-    for opt in (["-r", "1:LIG:A"], ["-a", "B"], ["-w", "m"], ["-C", "m"]):
+    for opt in (["-a", "B"], ["-l", "2"], ["-w", "m"], ["-C", "m"]):
         r = subprocess.run([fast, "-f", "x.pdb"] + opt, cwd=str(tmp_path), capture_output=True, text=True)
         assert r.returncode == 3 and "fpocket_cuda_batch" in r.stderr, (opt, r.stderr)
     r = subprocess.run([fast, "-f", "x.cif"], cwd=str(tmp_path), capture_output=True, text=True)
