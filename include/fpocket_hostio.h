@@ -16,9 +16,9 @@
  *   fpkio_run_list      = the "-F list" loop (src/fpmain.c:61-76) as a three-stage pipeline: reader pool -> one
  *                         fpk_detect_batch call per group of files -> writer pool
  *
- * Scope: PDB input, PDB-mode output (the reference's default for a .pdb input, fparams.c:397-407), chain filters -c / -k.
- * Not restated (use build/fpocket_cuda_batch, which keeps the reference's reader and writers): mmCIF in or out, -a, -r, -P,
- * -l, -d, -x. fpkio_* refuse those explicitly (FPKIO_ERR_UNSUPPORTED); nothing falls back silently.
+ * Scope: PDB input, PDB-mode output (the reference's default for a .pdb input, fparams.c:397-407), chain filters -c / -k, explicit ligand -r,
+ * explicit pocket -P / -u, dpocket's ligand mode. Not restated (use build/fpocket_cuda_batch, which keeps the reference's reader and writers):
+ * mmCIF in or out, -a, -l, -d, -x. fpkio_* refuse those explicitly (FPKIO_ERR_UNSUPPORTED); nothing falls back silently.
  *
  * The library has no CUDA dependency of its own: the detection call is handed in (fpk_detect_batch in the product,
  * build/fpocket_fast), so the CPU tests can drive the same pipeline with the oracle as the detector.
