@@ -289,12 +289,24 @@ int parse_pdb(const char *path, const char *data, size_t size, const fpkio_read_
     float x = 0, y = 0, z = 0;
     const bool ligmode = opts && opts->ligand[0] && opts->ligand[1];
     const bool xlig = opts && opts->has_xlig;
+    // -l N: a first pass looks for MODEL records (rpdb.c:817-828); without any, the option has no effect
+    bool model_flag = false, model_read = false;
+    int cur_model = 0;
+    if (opts && opts->model_number > 0)
+        for (const char *q = data; q < end;) {
+            size_t n = (size_t)(end - q) < (size_t)LINE_MAX_CHARS ? (size_t)(end - q) : (size_t)LINE_MAX_CHARS;
+            if (const void *nl = memchr(q, '\n', n)) n = (size_t)((const char *)nl - q) + 1;
+            if (n >= 5 && !strncmp(q, "MODEL", 5)) { model_flag = true; break; }
+            q += n;
+        }
     while (p < end) {
         size_t n = (size_t)(end - p) < (size_t)LINE_MAX_CHARS ? (size_t)(end - p) : (size_t)LINE_MAX_CHARS;
         if (const void *nl = memchr(p, '\n', n)) n = (size_t)((const char *)nl - p) + 1;
         memcpy(L, p, n);
         L[n] = 0;
         p += n;
+        if (model_flag && !strncmp(L, "MODEL", 5) && ++cur_model == opts->model_number) model_read = true;      // rpdb.c:834-839
+        if (model_flag && !model_read) continue;
         const bool is_atom = !strncmp(L, "ATOM ", 5), is_het = !is_atom && !strncmp(L, "HETATM", 6);
         if (is_atom || is_het) {
             if (!chain_passes(opts, L[21])) continue;
@@ -328,7 +340,8 @@ int parse_pdb(const char *path, const char *data, size_t size, const fpkio_read_
             if (is_het && in_nolig) F->nhet[0]++;
             if (is_ligand_atom) F->lig_idx.push_back((int32_t)F->watoms.size() - 1);
             if (in_nolig) F->nolig.push_back((int32_t)F->watoms.size() - 1);
-        } else if (!strncmp(L, "END", 3)) break;                 // rpdb.c:975, :1420 (model_flag == 0): ENDMDL ends the file too
+        } else if (model_read && !strncmp(L, "ENDMDL", 6)) model_read = false;        // rpdb.c:972-973: the wanted model is over, nothing else is read
+        else if (!model_flag && !strncmp(L, "END", 3)) break;    // rpdb.c:975, :1420 (model_flag == 0): ENDMDL ends the file too
     }
     if (F->nolig.empty()) { delete F; return FPKIO_ERR_NO_ATOMS; }
     // ---- the flat arrays of fpk_structure (shim_flatten / shim_job_prepare) + the s_pdb B-factor statistics (rpdb.c:1429-1454) ----

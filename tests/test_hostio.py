@@ -139,6 +139,29 @@ def test_reader_explicit_ligand_and_explicit_pocket(tmp_path):
 
 
 @needs_ref_io
+def test_reader_model_number(tmp_path):
+    """-l N on a multi-model file: only the records of the N-th MODEL ... ENDMDL block; without -l the first ENDMDL ends the reading
+    (its first three letters are END, rpdb.c:975)."""
+    import synth
+    s = synth.generate(20268005, 600, 0.065)
+    synth.to_pdb(s, str(tmp_path / "m.pdb"))
+    body = [ln for ln in open(tmp_path / "m.pdb").read().splitlines() if ln.startswith("ATOM")]
+    txt = ""
+    for m in range(3):
+        txt += "MODEL     %4d\n" % (m + 1)
+        for ln in body[: 300 + 100 * m]:
+            txt += ln[:30] + "%8.3f" % (float(ln[30:38]) + 0.5 * m) + ln[38:] + "\n"
+        txt += "ENDMDL\n"
+    txt += "END\n"
+    path = str(tmp_path / "multi.pdb")
+    open(path, "w").write(txt)
+    assert _reader_equal(path) == 300
+    assert _reader_equal(path, ("-l", "2"), hostio.ReadOpts.make(model=2)) == 400
+    assert _reader_equal(path, ("-l", "3"), hostio.ReadOpts.make(model=3)) == 500
+    assert _reader_equal(str(tmp_path / "m.pdb"), ("-l", "2"), hostio.ReadOpts.make(model=2)) == s.n        # no MODEL record: no effect
+
+
+@needs_ref_io
 @needs_sample
 def test_reader_on_mutated_records(tmp_path):
     """The reference parses fixed columns out of a line buffer it never clears: short records read what an earlier line left there.
@@ -438,7 +461,7 @@ def test_fast_programs_fail_loudly_without_a_gpu(tmp_path):
     (tmp_path / "l.txt").write_text("x.pdb\tLIG\n")
     r = subprocess.run([dfast, "-f", "l.txt"], cwd=str(tmp_path), capture_output=True, text=True)
     assert r.returncode == 4 and "no CPU fallback" in r.stderr and not (tmp_path / "dpout_explicitp.txt").exists()
-    for opt in (["-a", "B"], ["-l", "2"], ["-w", "m"], ["-C", "m"]):
+    for opt in (["-a", "B"], ["-d"], ["-w", "m"], ["-C", "m"]):
         r = subprocess.run([fast, "-f", "x.pdb"] + opt, cwd=str(tmp_path), capture_output=True, text=True)
         assert r.returncode == 3 and "fpocket_cuda_batch" in r.stderr, (opt, r.stderr)
     r = subprocess.run([fast, "-f", "x.cif"], cwd=str(tmp_path), capture_output=True, text=True)
