@@ -18,12 +18,15 @@ class ReadOpts(C.Structure):
     _fields_ = [("n_chains", C.c_int32), ("chains", (C.c_char * 21) * 20), ("chains_are_kept", C.c_int32), ("ligand", C.c_char * 8),
                 ("has_xlig", C.c_int32), ("xlig_resnumber", C.c_int32), ("xlig_resname", C.c_char * 8), ("xlig_chain", C.c_char),
                 ("n_xpocket", C.c_int32), ("xp_res", C.c_uint16 * 64), ("xp_ins", C.c_char * 64), ("xp_chain", C.c_char * 64),
-                ("model_number", C.c_int32)]
+                ("n_lig_chains", C.c_int32), ("lig_chains", (C.c_char * 21) * 20), ("model_number", C.c_int32)]
 
     @classmethod
-    def make(cls, drop=None, keep=None, ligand=None, custom_ligand=None, custom_pocket=None, model=0):
+    def make(cls, drop=None, keep=None, ligand=None, custom_ligand=None, custom_pocket=None, model=0, lig_chains=None):
         o = cls()
         o.model_number = model
+        for i, nm in enumerate(lig_chains or []):
+            o.lig_chains[i].value = nm.encode()
+        o.n_lig_chains = len(lig_chains or [])
         if custom_ligand:
             lib().fpkio_parse_custom_ligand(custom_ligand.encode(), C.byref(o))
         if custom_pocket:

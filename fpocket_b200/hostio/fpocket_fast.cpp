@@ -10,7 +10,7 @@
 // worker is this same program restricted to its device through CUDA_VISIBLE_DEVICES, with the I/O pool divided among them.
 //
 // -r resnumber:resname:chain (explicit ligand) and -P res:ins:chain.res:ins:chain (explicit pocket, -u) are handled as the reference does.
-// Options outside the restated route (mmCIF input or -w m/b, -a, -d, -x, -C != s, -e != e) are refused with a pointer to
+// Options outside the restated route (mmCIF input or -w m/b, -d, -x, -C != s, -e != e) are refused with a pointer to
 // build/fpocket_cuda_batch (reference reader / writers around the same library). There is no CPU detection path.
 #include <cstdio>
 #include <cstdlib>
@@ -72,6 +72,12 @@ int main(int argc, char **argv)
         else if (o == "-v" || o == "--iterations_volume_mc") P.nb_mcv_iter = atoi(val());
         else if (o == "-r" || o == "--custom_ligand") { fpkio_parse_custom_ligand(val(), &ro); }
         else if (o == "-P" || o == "--custom_pocket") { fpkio_parse_custom_pocket(val(), &ro); }
+        else if (o == "-a" || o == "--chain_as_ligand") {        // fparams.c:186-201
+            char tmp[512];
+            snprintf(tmp, sizeof tmp, "%s", val());
+            ro.n_lig_chains = 0;
+            for (char *t = strtok(tmp, ",:"); t && ro.n_lig_chains < 20; t = strtok(nullptr, ",:")) snprintf(ro.lig_chains[ro.n_lig_chains++], 21, "%s", t);
+        }
         else if (o == "-l" || o == "--model_number") ro.model_number = atoi(val());
         else if (o == "-u" || o == "--min_n_explicit_pocket") P.min_n_explicit_pocket_atoms = atoi(val());
         else if (o == "-c" || o == "--drop_chains") chains(val(), 0);
@@ -85,7 +91,7 @@ int main(int argc, char **argv)
         else if (o == "--slice") { if (sscanf(val(), "%d/%d", &slice_k, &slice_n) != 2 || slice_n < 1 || slice_k < 0 || slice_k >= slice_n) { fprintf(stderr, "! bad --slice\n"); return 2; } }
         else if (o == "--quiet") quiet = 1;
         else if (o == "--stats") want_stats = 1;
-        else if (o == "-a" || o == "-d" || o == "-x" || o == "-y" || o == "-b") return refuse(o.c_str());
+        else if (o == "-d" || o == "-x" || o == "-y" || o == "-b") return refuse(o.c_str());
         else { fprintf(stderr, "! unknown option %s\n", o.c_str()); return 2; }
     }
     if (files.empty()) { fprintf(stderr, "usage: %s -f X.pdb | -F list.txt [fpocket detection options] [--threads T] [--group G] [--quiet] [--stats] [--devices 0,1,..]\n", argv[0]); return 2; }
@@ -94,7 +100,7 @@ int main(int argc, char **argv)
         fprintf(stderr, "\nERROR: you specified an explicit ligand (-r) AND an explicit pocke (-P) in the same fpocket run. This is currently not allowed, please use either the one or the other.\n\n");
         return 2;
     }
-    P.skip_clustering = (ro.has_xlig || ro.n_xpocket > 0) ? 1 : 0;                            // fpocket.c:114
+    P.skip_clustering = (ro.has_xlig || ro.n_xpocket > 0 || ro.n_lig_chains > 0) ? 1 : 0;     // fpocket.c:114 (-a sets xlig_resnumber = 0)
     P.xpocket_active = ro.n_xpocket > 0 ? 1 : 0;
     if (devices.size() > 1) {
         // one worker per GPU: re-run this command line with --slice k/N under CUDA_VISIBLE_DEVICES=<device k>

@@ -230,6 +230,8 @@ struct fpkio_file {
     std::vector<int32_t> iv;            // 2 x n: id res_id
     std::vector<int8_t> aa;
     std::vector<uint8_t> fl, wfl;
+    int nw_count = -1;                  // -a: watoms[0..nw_count) is pdb_w_lig, the rest holds pdb's own atoms (the two lists are then independent)
+    bool have_stats = false; float st_avg = 0, st_min = 0, st_max = 0;      // -a: B-factor statistics as the reference's loop over the stored atoms leaves them
     std::vector<float> xlig;            // -r: xyz triplets of the explicit ligand's records (pdb->xlig_x/y/z)
     std::vector<int32_t> lig_idx, lig_mol, name_key;   // dpocket: the known ligand (indices into watoms), its molecules, atom names of pdb packed
     fpk_structure st;
@@ -277,6 +279,157 @@ bool chain_passes(const fpkio_read_opts *o, char c)     // chains_to_delete (rpd
     return o->chains_are_kept ? hit : !hit;
 }
 
+
+// ---- -a (chain as ligand): the reference's two passes, literally ----------------------------------------------------------------------
+// rpdb_open counts with the CURRENT record's chain, rpdb_read decides its branch with the chain of the PREVIOUS record (chainbuf is updated
+// inside the branches, rpdb.c:1079-1081,1225-1227), so at every boundary between a ligand chain and another one the two disagree by one
+// record: the first record of a ligand chain is stored as a protein atom, the first record after it goes down the HETATM route. The atom
+// array has the size the first pass counted; stores beyond it are invisible, slots never stored stay zero (calloc). Reproduced as is.
+struct PassResult { std::vector<AtomRec> atoms; int natoms = 0, nhet = 0; std::vector<float> xlig; float avg = 0, mn = 0, mx = 0; };
+
+bool is_lig_chain(const fpkio_read_opts *o, char c)
+{
+    for (int i = 0; i < o->n_lig_chains && i < 20; i++) if (o->lig_chains[i][0] == c && o->lig_chains[i][1] == 0) return true;
+    return false;
+}
+
+struct LineReader {             // fgets(buf, 82, f) over a memory image, with the reference's never-cleared buffer
+    const char *p, *end;
+    char L[LINE_MAX_CHARS + 3];
+    LineReader(const char *d, size_t n) : p(d), end(d + n) { memset(L, 0, sizeof L); }
+    bool next()
+    {
+        if (p >= end) return false;
+        size_t n = (size_t)(end - p) < (size_t)LINE_MAX_CHARS ? (size_t)(end - p) : (size_t)LINE_MAX_CHARS;
+        if (const void *nl = memchr(p, '\n', n)) n = (size_t)((const char *)nl - p) + 1;
+        memcpy(L, p, n);
+        L[n] = 0;
+        p += n;
+        return true;
+    }
+};
+
+bool emulate_rpdb(const char *data, size_t size, const fpkio_read_opts *o, const int keep_lig, PassResult &R)
+{
+    const bool xlig_active = true;              // -a sets xlig_resnumber = 0 (fparams.c:201), and every test is "xlig_resnumber > -1"
+    auto rmatch = [&](const char *L, int resnbuf, const char *resb) {
+        return o->has_xlig && o->xlig_chain && L[21] == o->xlig_chain && resnbuf == o->xlig_resnumber && o->xlig_resname[0] == resb[0] &&
+               o->xlig_resname[1] == resb[1] && o->xlig_resname[2] == resb[2];
+    };
+    auto resname = [](const char *L, char *resb) { slice_strncpy(resb, L + 17, 4); str_trim(resb); };
+    bool model_flag = false;
+    if (o->model_number > 0) { LineReader s(data, size); while (s.next()) if (!strncmp(s.L, "MODEL", 5)) { model_flag = true; break; } }
+    // ---- rpdb_open: the counts (rpdb.c:830-978) ----
+    int natoms = 0, nhet = 0, nxl = 0;
+    {
+        LineReader f(data, size);
+        float x = 0, y = 0, z = 0;
+        int resnbuf = 0, cur_model = 0;
+        bool model_read = false;
+        char resb[8] = {0};
+        while (f.next()) {
+            const char *L = f.L;
+            if (model_flag && !strncmp(L, "MODEL", 5) && ++cur_model == o->model_number) model_read = true;
+            if (model_flag && !model_read) continue;
+            const bool is_atom = !strncmp(L, "ATOM ", 5), is_het = !strncmp(L, "HETATM", 6), isl = is_lig_chain(o, L[21]), ctd = chain_passes(o, L[21]);
+            if (is_atom && !isl) {
+                if (ctd) { resname(L, resb); x = slice_atof(L + 30, 8); y = slice_atof(L + 38, 8); z = slice_atof(L + 46, 8); resnbuf = slice_atoi(L + 22, 4); }
+                if ((L[16] == ' ' || L[16] == 'A') && x < 9990 && y < 9990 && z < 9990 && ctd) natoms++;
+                if (x < 9990 && y < 9990 && z < 9990 && xlig_active && rmatch(L, resnbuf, resb)) nxl++;
+            } else if (is_het || (is_atom && isl)) {
+                if (ctd) { x = slice_atof(L + 30, 8); y = slice_atof(L + 38, 8); z = slice_atof(L + 46, 8); resnbuf = slice_atoi(L + 22, 4); }
+                if ((L[16] == ' ' || L[16] == 'A') && x < 9990 && y < 9990 && z < 9990) {
+                    if (ctd) {
+                        resname(L, resb);
+                        if ((keep_lig && !is_water3(resb)) || (keep_lig && isl)) { natoms++; nhet++; }
+                        else if (!isl && keep_hetatm(resb)) { nhet++; natoms++; }
+                    }
+                    if (isl) nxl++;
+                }
+                if (x < 9990 && y < 9990 && z < 9990) {
+                    resname(L, resb);
+                    resnbuf = slice_atoi(L + 22, 4);
+                    if (xlig_active && ((isl && !is_water3(resb)) || rmatch(L, resnbuf, resb))) nxl++;
+                }
+            } else if (model_read && !strncmp(L, "ENDMDL", 6)) model_read = false;
+            else if (!model_flag && !strncmp(L, "END", 3)) break;
+        }
+    }
+    if (natoms == 0) return false;
+    R.natoms = natoms; R.nhet = nhet;
+    R.atoms.assign((size_t)natoms, AtomRec());
+    for (auto &a : R.atoms) memset(&a, 0, sizeof a);
+    // ---- rpdb_read: the stores (rpdb.c:1064-1424) ----
+    std::vector<AtomRec> extra;                 // stored beyond the counted size: invisible to the rest, but inside the B-factor loop
+    int iatoms = 0;
+    {
+        LineReader f(data, size);
+        float tx = 0, ty = 0, tz = 0;
+        int resnbuf = 0, cur_model = 0;
+        bool model_read = false;
+        char resb[8] = {0}, chainbuf = 0;       // the reference's chainbuf[0] is uninitialised before the first record
+        auto store = [&](const char *L) {
+            AtomRec a;
+            extract_atom(L, (int)strlen(L), slice_atof(L + 30, 8), slice_atof(L + 38, 8), slice_atof(L + 46, 8), a);
+            if (iatoms < natoms) R.atoms[(size_t)iatoms] = a; else extra.push_back(a);
+            iatoms++;
+        };
+        auto push_xlig = [&](const char *L) { R.xlig.push_back(slice_atof(L + 30, 8)); R.xlig.push_back(slice_atof(L + 38, 8)); R.xlig.push_back(slice_atof(L + 46, 8)); };
+        while (f.next()) {
+            const char *L = f.L;
+            if (model_flag && !strncmp(L, "MODEL", 5) && ++cur_model == o->model_number) model_read = true;
+            if (model_flag && !model_read) continue;
+            const bool is_atom = !strncmp(L, "ATOM ", 5), is_het = !strncmp(L, "HETATM", 6), prev_isl = is_lig_chain(o, chainbuf);
+            if (is_atom && !prev_isl) {
+                chainbuf = L[21];
+                const bool ctd = chain_passes(o, chainbuf), isl = is_lig_chain(o, chainbuf);
+                if (ctd) { tx = slice_atof(L + 30, 8); ty = slice_atof(L + 38, 8); tz = slice_atof(L + 46, 8); }
+                if ((L[16] == ' ' || L[16] == 'A') && tx < 9990 && ty < 9990 && tz < 9990) {
+                    if (ctd) { resname(L, resb); resnbuf = slice_atoi(L + 22, 4); }
+                    if (isl) push_xlig(L);
+                    if (ctd) store(L);          // "a simple atom": also the first record of a ligand chain
+                }
+                if (tx < 9990 && ty < 9990 && tz < 9990 && nxl) {
+                    resname(L, resb);
+                    resnbuf = slice_atoi(L + 22, 4);
+                    if ((isl && !is_water3(resb)) || rmatch(L, resnbuf, resb)) push_xlig(L);
+                }
+            } else if (is_het || (is_atom && prev_isl)) {
+                chainbuf = L[21];
+                const bool ctd = chain_passes(o, chainbuf), isl = is_lig_chain(o, chainbuf);
+                if (ctd) { tx = slice_atof(L + 30, 8); ty = slice_atof(L + 38, 8); tz = slice_atof(L + 46, 8); resnbuf = slice_atoi(L + 22, 4); }
+                if ((L[16] == ' ' || L[16] == 'A') && tx < 9990 && ty < 9990 && tz < 9990) {
+                    if (ctd) resname(L, resb);
+                    if (isl) push_xlig(L);
+                    if (ctd && nhet > 0) {      // "else if (pdb->lhetatm)"
+                        if ((keep_lig && !is_water3(resb)) || (keep_lig && isl)) store(L);
+                        else if (!isl && keep_hetatm(resb)) store(L);
+                    }
+                }
+                if (tx < 9990 && ty < 9990 && tz < 9990 && nxl) {
+                    resnbuf = slice_atoi(L + 22, 4);
+                    resname(L, resb);
+                    if ((isl && !is_water3(resb)) || rmatch(L, resnbuf, resb)) push_xlig(L);
+                }
+            } else if (model_read && !strncmp(L, "ENDMDL", 6)) model_read = false;
+            else if (!model_flag && !strncmp(L, "END", 3)) break;
+        }
+    }
+    // B-factor statistics over the STORED atoms (rpdb.c:1429-1454), hydrogens counted over the declared ones
+    float avg = 0.0f, mn = 0.0f, mx = 0.0f;
+    for (int i = 0; i < iatoms; i++) {
+        const AtomRec &a = i < natoms ? R.atoms[(size_t)i] : extra[(size_t)(i - natoms)];
+        avg += a.bf;
+        if (a.bf < mn) mn = a.bf;
+        if (a.bf > mx) mx = a.bf;
+    }
+    int nh = 0;
+    for (const AtomRec &a : R.atoms) if (!strcmp(a.symbol, "H")) nh++;
+    R.avg = avg / (iatoms - nh); R.mn = mn; R.mx = mx;
+    if ((int)(R.xlig.size() / 3) > nxl) R.xlig.resize((size_t)3 * nxl);
+    return true;
+}
+
 int parse_pdb(const char *path, const char *data, size_t size, const fpkio_read_opts *opts, fpkio_file **out)
 {
     fpkio_file *F = new fpkio_file();
@@ -286,6 +439,19 @@ int parse_pdb(const char *path, const char *data, size_t size, const fpkio_read_
     char L[LINE_MAX_CHARS + 3];
     memset(L, 0, sizeof L);
     const char *p = data, *end = data + size;
+    const bool chainlig = opts && opts->n_lig_chains > 0;
+    if (chainlig) {
+        if (opts->ligand[0]) { delete F; return FPKIO_ERR_UNSUPPORTED; }
+        PassResult A, W;
+        if (!emulate_rpdb(data, size, opts, 0, A) || !emulate_rpdb(data, size, opts, 1, W)) { delete F; return FPKIO_ERR_NO_ATOMS; }
+        F->watoms = W.atoms;
+        F->nw_count = (int)W.atoms.size();
+        for (size_t k = 0; k < A.atoms.size(); k++) { F->watoms.push_back(A.atoms[k]); F->nolig.push_back((int32_t)(F->nw_count + (int)k)); }
+        F->nhet[0] = A.nhet; F->nhet[1] = W.nhet;
+        F->xlig = A.xlig;
+        F->have_stats = true; F->st_avg = A.avg; F->st_min = A.mn; F->st_max = A.mx;
+        p = end;                                // the single-pass loop below is skipped
+    }
     float x = 0, y = 0, z = 0;
     const bool ligmode = opts && opts->ligand[0] && opts->ligand[1];
     const bool xlig = opts && opts->has_xlig;
@@ -345,7 +511,7 @@ int parse_pdb(const char *path, const char *data, size_t size, const fpkio_read_
     }
     if (F->nolig.empty()) { delete F; return FPKIO_ERR_NO_ATOMS; }
     // ---- the flat arrays of fpk_structure (shim_flatten / shim_job_prepare) + the s_pdb B-factor statistics (rpdb.c:1429-1454) ----
-    const int n = (int)F->nolig.size(), nw = (int)F->watoms.size();
+    const int n = (int)F->nolig.size(), nw = F->nw_count >= 0 ? F->nw_count : (int)F->watoms.size();
     F->f.resize((size_t)6 * n); F->iv.resize((size_t)2 * n); F->aa.resize(n); F->fl.resize(n);
     F->wf.resize((size_t)5 * nw); F->wfl.resize(nw);
     float avg = 0.0f, mn = 0.0f, mx = 0.0f;
@@ -379,6 +545,7 @@ int parse_pdb(const char *path, const char *data, size_t size, const fpkio_read_
     s.natoms = n;
     s.x = F->f.data(); s.y = s.x + n; s.z = s.x + 2 * (size_t)n; s.radius = s.x + 3 * (size_t)n; s.electroneg = s.x + 4 * (size_t)n; s.bfactor = s.x + 5 * (size_t)n;
     s.atom_id = F->iv.data(); s.res_id = s.atom_id + n; s.aa_idx = F->aa.data(); s.flags = F->fl.data();
+    if (F->have_stats) { avg = F->st_avg; mn = F->st_min; mx = F->st_max; }
     s.avg_bfactor = avg; s.min_bfactor = mn; s.max_bfactor = mx;
     s.natoms_w = nw;
     s.wx = F->wf.data(); s.wy = s.wx + nw; s.wz = s.wx + 2 * (size_t)nw; s.wradius = s.wx + 3 * (size_t)nw; s.welectroneg = s.wx + 4 * (size_t)nw;
@@ -579,7 +746,7 @@ int fpkio_read_pdb(const char *path, const fpkio_read_opts *opts, fpkio_file **o
 
 void fpkio_file_free(fpkio_file *f) { delete f; }
 const fpk_structure *fpkio_structure(const fpkio_file *f) { return f ? &f->st : nullptr; }
-int fpkio_natoms(const fpkio_file *f, int with_lig) { return !f ? 0 : with_lig ? (int)f->watoms.size() : (int)f->nolig.size(); }
+int fpkio_natoms(const fpkio_file *f, int with_lig) { return !f ? 0 : with_lig ? (f->nw_count >= 0 ? f->nw_count : (int)f->watoms.size()) : (int)f->nolig.size(); }
 int fpkio_nhetatm(const fpkio_file *f, int with_lig) { return !f ? 0 : f->nhet[with_lig ? 1 : 0]; }
 
 int fpkio_atom_text(const fpkio_file *f, int with_lig, int k, char *type, char *name, char *res_name, char *chain, char *symbol,

@@ -165,21 +165,22 @@ def test_dpocket_fast_equals_reference_io_around_the_library(tmp_path):
     assert nrows >= 4 + 40
 
 
-@pytest.mark.parametrize("extra", [("-r", "1224:PU8:A"), ("-P", "107:-:A.108:-:A.138:-:A.139:-:A.184:-:A", "-u", "2"), ("-k", "A")])
-def test_explicit_ligand_and_pocket_options_equal_reference_io(tmp_path, extra):
-    """fpocket -r (explicit ligand), -P (explicit pocket) and -k on the reference's 1UYD sample: build/fpocket_fast against the reference's
-    reader and writers around the same library."""
+@pytest.mark.parametrize("name,extra", [("1UYD", ("-r", "1224:PU8:A")), ("1UYD", ("-P", "107:-:A.108:-:A.138:-:A.139:-:A.184:-:A", "-u", "2")),
+                                        ("1UYD", ("-k", "A")), ("2P0R_mod", ("-a", "D")), ("1g50", ("-a", "B", "-m", "3.0"))])
+def test_explicit_ligand_and_pocket_options_equal_reference_io(tmp_path, name, extra):
+    """fpocket -r (explicit ligand), -P (explicit pocket), -k and -a (chain as ligand, the reference's tests/reference_output/2P0R_mod case) on the
+    reference's samples: build/fpocket_fast against the reference's reader and writers around the same library."""
     import shutil
-    src = os.path.join(ROOT, "build", "samples", "1UYD.pdb")
+    src = os.path.join(ROOT, "build", "samples", name + ".pdb")
     if not (os.path.exists(src) and os.path.exists(FAST) and os.path.exists(BATCH)):
-        pytest.skip("build/samples/1UYD.pdb, build/fpocket_fast or build/fpocket_cuda_batch missing")
+        pytest.skip("build/samples, build/fpocket_fast or build/fpocket_cuda_batch missing")
     env = dict(os.environ, FPOCKET_MC_SEED=str(SEED), TMPDIR=str(tmp_path))
     da, db = tmp_path / "fast", tmp_path / "refio"
     for d in (da, db):
         d.mkdir()
-        shutil.copy(src, str(d / "1UYD.pdb"))
-        (d / "list.txt").write_text("1UYD.pdb\n")
-    subprocess.check_call([FAST, "-f", "1UYD.pdb", "--quiet", *extra], cwd=str(da), env=env)
+        shutil.copy(src, str(d / (name + ".pdb")))
+        (d / "list.txt").write_text(name + ".pdb\n")
+    subprocess.check_call([FAST, "-f", name + ".pdb", "--quiet", *extra], cwd=str(da), env=env)
     subprocess.check_call([BATCH, "list.txt", *extra], cwd=str(db), env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    a, b = _tree(str(da / "1UYD_out")), _tree(str(db / "1UYD_out"))
+    a, b = _tree(str(da / (name + "_out"))), _tree(str(db / (name + "_out")))
     assert a == b and len(a) >= 9, sorted(k for k in set(a) | set(b) if a.get(k) != b.get(k))[:5]

@@ -139,6 +139,22 @@ def test_reader_explicit_ligand_and_explicit_pocket(tmp_path):
 
 
 @needs_ref_io
+@needs_sample
+@pytest.mark.parametrize("name,chains", [("2P0R_mod", ["D"]), ("1g50", ["B"]), ("1g50", ["A"]), ("3vi4", ["B", "D"])])
+def test_reader_chain_as_ligand(tmp_path, name, chains):
+    """-a: the reference's counting pass looks at the current record's chain, its storing pass at the previous record's (rpdb.c:1079,1225), so
+    one record goes astray at every boundary of a ligand chain and the declared atom count can differ from what was stored. The native
+    reader reproduces both passes: same atoms (zero-filled slots included), same explicit-ligand coordinates, same B-factor statistics."""
+    dst = str(tmp_path / (name + ".pdb"))
+    shutil.copy(os.path.join(SAMPLE, name + ".pdb"), dst)
+    o = hostio.ReadOpts.make(lig_chains=chains)
+    n = _reader_equal(dst, ("-a", ",".join(chains)), o)
+    p = hostio.PdbFile(dst, opts=o)
+    assert n > 1000 and p.structure.n_xlig > 20 and p.natoms(1) >= n
+    p.close()
+
+
+@needs_ref_io
 def test_reader_model_number(tmp_path):
     """-l N on a multi-model file: only the records of the N-th MODEL ... ENDMDL block; without -l the first ENDMDL ends the reading
     (its first three letters are END, rpdb.c:975)."""
@@ -461,7 +477,7 @@ def test_fast_programs_fail_loudly_without_a_gpu(tmp_path):
     (tmp_path / "l.txt").write_text("x.pdb\tLIG\n")
     r = subprocess.run([dfast, "-f", "l.txt"], cwd=str(tmp_path), capture_output=True, text=True)
     assert r.returncode == 4 and "no CPU fallback" in r.stderr and not (tmp_path / "dpout_explicitp.txt").exists()
-    for opt in (["-a", "B"], ["-d"], ["-w", "m"], ["-C", "m"]):
+    for opt in (["-x"], ["-d"], ["-w", "m"], ["-C", "m"]):
         r = subprocess.run([fast, "-f", "x.pdb"] + opt, cwd=str(tmp_path), capture_output=True, text=True)
         assert r.returncode == 3 and "fpocket_cuda_batch" in r.stderr, (opt, r.stderr)
     r = subprocess.run([fast, "-f", "x.cif"], cwd=str(tmp_path), capture_output=True, text=True)
