@@ -18,7 +18,7 @@ class ReadOpts(C.Structure):
     _fields_ = [("n_chains", C.c_int32), ("chains", (C.c_char * 21) * 20), ("chains_are_kept", C.c_int32), ("ligand", C.c_char * 8),
                 ("has_xlig", C.c_int32), ("xlig_resnumber", C.c_int32), ("xlig_resname", C.c_char * 8), ("xlig_chain", C.c_char),
                 ("n_xpocket", C.c_int32), ("xp_res", C.c_uint16 * 64), ("xp_ins", C.c_char * 64), ("xp_chain", C.c_char * 64),
-                ("n_lig_chains", C.c_int32), ("lig_chains", (C.c_char * 21) * 20), ("model_number", C.c_int32)]
+                ("n_lig_chains", C.c_int32), ("lig_chains", (C.c_char * 21) * 20), ("write_mode", C.c_char), ("model_number", C.c_int32)]
 
     @classmethod
     def make(cls, drop=None, keep=None, ligand=None, custom_ligand=None, custom_pocket=None, model=0, lig_chains=None):

@@ -10,7 +10,7 @@
 // worker is this same program restricted to its device through CUDA_VISIBLE_DEVICES, with the I/O pool divided among them.
 //
 // -r resnumber:resname:chain (explicit ligand) and -P res:ins:chain.res:ins:chain (explicit pocket, -u) are handled as the reference does.
-// Options outside the restated route (mmCIF input or -w m/b, -d, -x, -C != s, -e != e) are refused with a pointer to
+// Options outside the restated route (mmCIF input, -d, -x, -C != s, -e != e) are refused with a pointer to
 // build/fpocket_cuda_batch (reference reader / writers around the same library). There is no CPU detection path.
 #include <cstdio>
 #include <cstdlib>
@@ -84,7 +84,11 @@ int main(int argc, char **argv)
         else if (o == "-k" || o == "--keep_chains") chains(val(), 1);
         else if (o == "-C" || o == "--clustering_method") { if (val()[0] != 's') return refuse("-C other than s (single linkage)"); }
         else if (o == "-e" || o == "--clustering_measure") { if (val()[0] != 'e') return refuse("-e other than e (euclidean)"); }
-        else if (o == "-w" || o == "--write_mode") { const char *w = val(); if (w[0] != 'p' && w[0] != 'd') return refuse("-w other than pdb"); }
+        else if (o == "-w" || o == "--write_mode") {            // fparams.c:167-183: d | b(oth) | p(db) | m(mcif) | cif
+            const char *w = val();
+            if (w[0] != 'd' && w[0] != 'b' && w[0] != 'p' && w[0] != 'm' && strcmp(w, "cif")) printf("Writing mode invalid, set to default\n");
+            else ro.write_mode = !strcmp(w, "cif") ? 'm' : (w[0] == 'd' ? 'p' : w[0]);
+        }
         else if (o == "--threads") threads = atoi(val());
         else if (o == "--group") group = atoi(val());
         else if (o == "--devices") { char tmp[256]; snprintf(tmp, sizeof tmp, "%s", val()); for (char *t = strtok(tmp, ","); t; t = strtok(nullptr, ",")) devices.push_back(t); }

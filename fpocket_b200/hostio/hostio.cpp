@@ -716,6 +716,31 @@ void pqr_sphere(Out &o, int i, bool apolar, int resid, const float *c)
     o.ch('\n');
 }
 
+
+// write_mmcif_atom_line (writepdb.c:201-236): the occupancy column carries dA, blank alt-loc / insertion codes become '?'
+void cif_line(Out &o, const char *rec, int id, const char *sym, const char *name, char aloc, const char *res, const char *asym, int seq, char ins,
+              float x, float y, float z, float occ, int charge, int res_id, const char *chain)
+{
+    o.str_left(rec, 7); o.ch(' ');
+    { char b[16]; snprintf(b, sizeof b, "%d", id); o.str_left(b, 6); }
+    o.ch(' '); o.str_right(sym, 3); o.ch(' '); o.str_right(name, 4); o.ch(' ');
+    o.ch((aloc == 0 || aloc == ' ') ? '?' : aloc);
+    o.ch(' '); o.str_right(res, 4); o.ch(' '); o.str_right(asym, 6); o.ch(' ');
+    o.integer(seq, 0); o.ch(' ');
+    o.ch((ins == 0 || ins == ' ') ? '?' : ins);
+    o.ch(' '); o.fixed(x, 8, 3); o.ch(' '); o.fixed(y, 8, 3); o.ch(' '); o.fixed(z, 8, 3); o.ch(' '); o.fixed(occ, 6, 2); o.ch(' ');
+    if (charge == -1) o.put(" 0"); else o.integer(charge, 2);
+    o.ch(' '); o.integer(res_id, 0); o.ch(' '); o.put(chain); o.ch('\n');
+}
+void cif_atom(Out &o, const AtomRec &a, const float *fx)         // label_asym_id = chain, label_seq_id = res_id for a PDB input (rpdb.c:1150-1151)
+{
+    cif_line(o, a.type, a.id, a.symbol, a.name, a.aloc, a.res_name, a.chain, a.res_id, a.insert, a.x, a.y, a.z, fx ? fx[2] : 0.0f, a.charge, a.res_id, a.chain);
+}
+const char CIF_ATOM_SITE[] =                                      // writepocket.c:39-56
+    "loop_\n_atom_site.group_PDB\n_atom_site.id\n_atom_site.type_symbol\n_atom_site.label_atom_id\n_atom_site.label_alt_id\n_atom_site.label_comp_id\n"
+    "_atom_site.label_asym_id\n_atom_site.label_seq_id\n_atom_site.pdbx_PDB_ins_code\n_atom_site.Cartn_x\n_atom_site.Cartn_y\n_atom_site.Cartn_z\n"
+    "_atom_site.occupancy\n_atom_site.pdbx_formal_charge\n_atom_site.auth_seq_id\n_atom_site.auth_asym_id\n";
+
 void substitute(Out &o, const char *tpl, const std::string &code)
 {
     for (const char *q = tpl; *q; q++) if (*q == '\001') o.put(code); else o.ch(*q);
@@ -772,8 +797,8 @@ int fpkio_write_output(const fpkio_file *F, const char *pdb_path, const fpk_resu
 int fpkio_write_output_mode(const fpkio_file *F, const char *pdb_path, const fpk_result *R, char write_mode, long long *bytes_out)
 {
     if (!F || !pdb_path || !R) return FPKIO_ERR_BAD_ARG;
-    if (write_mode != 'p' && write_mode != 'd') return FPKIO_ERR_UNSUPPORTED;      // 'm' / 'b': the mmCIF writers are not restated
-    const bool pdb_files = write_mode == 'p';
+    if (write_mode != 'p' && write_mode != 'd' && write_mode != 'm' && write_mode != 'b') return FPKIO_ERR_UNSUPPORTED;
+    const bool pdb_files = write_mode == 'p' || write_mode == 'b', cif_files = write_mode == 'm' || write_mode == 'b';
     // ---- names (fpout.c:71-80): remove_ext on the whole path, then remove_path ----
     std::string code = pdb_path, dir;
     { const size_t sl = code.rfind('/'); if (sl != std::string::npos) dir = code.substr(0, sl); }
@@ -793,6 +818,12 @@ int fpkio_write_output_mode(const fpkio_file *F, const char *pdb_path, const fpk
         o.clear(); substitute(o, TPL_PYMOL_SH, code); ok &= write_file(base + "_PYMOL.sh", o, 0777, bytes_out);
         o.clear(); substitute(o, TPL_PML, code);      ok &= write_file(base + ".pml", o, 0666, bytes_out);
     }
+    if (cif_files) {
+        o.clear(); substitute(o, TPL_CIF_VMD_SH, code);   ok &= write_file(base + "_cif_VMD.sh", o, 0777, bytes_out);
+        o.clear(); substitute(o, TPL_CIF_TCL, code);      ok &= write_file(base + "_cif.tcl", o, 0666, bytes_out);
+        o.clear(); substitute(o, TPL_CIF_PYMOL_SH, code); ok &= write_file(base + "_cif_PYMOL.sh", o, 0777, bytes_out);
+        o.clear(); substitute(o, TPL_CIF_PML, code);      ok &= write_file(base + "_cif.pml", o, 0666, bytes_out);
+    }
     // ---- <code>_out.pdb: every atom of pdb, then the spheres pocket by pocket (writepocket.c:262-305, voronoi.c:1437-1482) ----
     if (pdb_files) {
     o.clear();
@@ -810,6 +841,23 @@ int fpkio_write_output_mode(const fpkio_file *F, const char *pdb_path, const fpk
         }
     }
     ok &= write_file(base + "_out.pdb", o, 0666, bytes_out);
+    }
+    // ---- <code>_out.cif (writepocket.c:307-357): atoms, then every sphere as "HETATM i V APOL . STP C rank" (write_mmcif_vert with no energies) ----
+    if (cif_files) {
+        o.clear();
+        o.room((size_t)(n + R->n_spheres) * 90 + 1024);
+        o.put("data_"); o.put(code); o.put("_out\n# \n"); o.put(CIF_ATOM_SITE);
+        for (int k = 0; k < n; k++) cif_atom(o, F->watoms[F->nolig[k]], fx ? fx + 4 * (size_t)k : nullptr);
+        for (int r = 0; r < R->n_pockets; r++) {
+            const int c = R->rank_to_cluster[r];
+            int i = 0;
+            for (int q = R->cl_off[c]; q < R->cl_off[c + 1]; q++) {
+                const float *xyz = R->sph_xyzr + 4 * (size_t)R->cl_sph[q];
+                cif_line(o, "HETATM", ++i, "V", "APOL", '.', "STP", "C", r + 1, '.', xyz[0], xyz[1], xyz[2], 0.0f, -1, r + 1, "C");
+            }
+        }
+        o.put("# \n");
+        ok &= write_file(base + "_out.cif", o, 0666, bytes_out);
     }
     // ---- <code>_info.txt (fpout.c:151-213) ----
     o.clear();
@@ -891,28 +939,7 @@ int fpkio_write_output_mode(const fpkio_file *F, const char *pdb_path, const fpk
         snprintf(nm, sizeof nm, "/pocket%d_vert.pqr", r + 1);
         ok &= write_file(pdir + nm, o, 0666, bytes_out);
 
-        if (!pdb_files) continue;          // writepocket.c:492-500: pocketN_atm.pdb only in PDB mode
-        o.clear();
-        o.put("HEADER\n"
-              "HEADER This is a pdb format file writen by the programm fpocket.                 \n"
-              "HEADER It represents the atoms contacted by the voronoi vertices of the pocket.  \n"
-              "HEADER                                                                           \n");
-        o.fmt("HEADER Information about the pocket %5d:\n", r + 1);
-        o.put("HEADER 0  - Pocket Score                      : "); o.fixed(d.score, 0, 4); o.ch('\n');
-        o.put("HEADER 1  - Drug Score                        : "); o.fixed(d.drug_score, 0, 4); o.ch('\n');
-        o.fmt("HEADER 2  - Number of alpha spheres           : %5d\n", d.nb_asph);
-        o.put("HEADER 3  - Mean alpha-sphere radius          : "); o.fixed(d.mean_asph_ray, 0, 4); o.ch('\n');
-        o.put("HEADER 4  - Mean alpha-sphere Solvent Acc.    : "); o.fixed(d.masph_sacc, 0, 4); o.ch('\n');
-        o.put("HEADER 5  - Mean B-factor of pocket residues  : "); o.fixed(d.flex, 0, 4); o.ch('\n');
-        o.put("HEADER 6  - Hydrophobicity Score              : "); o.fixed(d.hydrophobicity_score, 0, 4); o.ch('\n');
-        o.fmt("HEADER 7  - Polarity Score                    : %5d\n", d.polarity_score);
-        o.put("HEADER 8  - Amino Acid based volume Score     : "); o.fixed(d.volume_score, 0, 4); o.ch('\n');
-        o.put("HEADER 9  - Pocket volume (Monte Carlo)       : "); o.fixed(d.volume, 0, 4); o.ch('\n');
-        o.put("HEADER 10 - Pocket volume (convex hull)       : "); o.fixed(d.convex_hull_volume, 0, 4); o.ch('\n');
-        o.fmt("HEADER 11 - Charge Score                      : %5d\n", d.charge_score);
-        o.put("HEADER 12 - Local hydrophobic density Score   : "); o.fixed(d.mean_loc_hyd_dens, 0, 4); o.ch('\n');
-        o.fmt("HEADER 13 - Number of apolar alpha sphere     : %5d\n", d.nAlphaApol);
-        o.put("HEADER 14 - Proportion of apolar alpha sphere : "); o.fixed(d.apolar_asphere_prop, 0, 4); o.ch('\n');
+        if (!pdb_files && !cif_files) continue;     // writepocket.c:492-500: pocketN_atm.* only once a write mode is decided
         // atoms contacted by the pocket's spheres, unique by atom id, first seen first (writepocket.c:604-617, is_in_lst_atm compares ids)
         uniq.clear();
         for (int q = first; q < last; q++) {
@@ -924,10 +951,62 @@ int fpkio_write_output_mode(const fpkio_file *F, const char *pdb_path, const fpk
                 if (!seen) uniq.push_back(ng[j]);
             }
         }
-        for (const int32_t k : uniq) atom_line(o, F->watoms[F->nolig[k]], fx ? fx + 4 * (size_t)k : nullptr);
-        o.put("TER\nEND\n");
-        snprintf(nm, sizeof nm, "/pocket%d_atm.pdb", r + 1);
-        ok &= write_file(pdir + nm, o, 0666, bytes_out);
+        if (pdb_files) {
+            o.clear();
+            o.put("HEADER\n"
+                  "HEADER This is a pdb format file writen by the programm fpocket.                 \n"
+                  "HEADER It represents the atoms contacted by the voronoi vertices of the pocket.  \n"
+                  "HEADER                                                                           \n");
+            o.fmt("HEADER Information about the pocket %5d:\n", r + 1);
+            o.put("HEADER 0  - Pocket Score                      : "); o.fixed(d.score, 0, 4); o.ch('\n');
+            o.put("HEADER 1  - Drug Score                        : "); o.fixed(d.drug_score, 0, 4); o.ch('\n');
+            o.fmt("HEADER 2  - Number of alpha spheres           : %5d\n", d.nb_asph);
+            o.put("HEADER 3  - Mean alpha-sphere radius          : "); o.fixed(d.mean_asph_ray, 0, 4); o.ch('\n');
+            o.put("HEADER 4  - Mean alpha-sphere Solvent Acc.    : "); o.fixed(d.masph_sacc, 0, 4); o.ch('\n');
+            o.put("HEADER 5  - Mean B-factor of pocket residues  : "); o.fixed(d.flex, 0, 4); o.ch('\n');
+            o.put("HEADER 6  - Hydrophobicity Score              : "); o.fixed(d.hydrophobicity_score, 0, 4); o.ch('\n');
+            o.fmt("HEADER 7  - Polarity Score                    : %5d\n", d.polarity_score);
+            o.put("HEADER 8  - Amino Acid based volume Score     : "); o.fixed(d.volume_score, 0, 4); o.ch('\n');
+            o.put("HEADER 9  - Pocket volume (Monte Carlo)       : "); o.fixed(d.volume, 0, 4); o.ch('\n');
+            o.put("HEADER 10 - Pocket volume (convex hull)       : "); o.fixed(d.convex_hull_volume, 0, 4); o.ch('\n');
+            o.fmt("HEADER 11 - Charge Score                      : %5d\n", d.charge_score);
+            o.put("HEADER 12 - Local hydrophobic density Score   : "); o.fixed(d.mean_loc_hyd_dens, 0, 4); o.ch('\n');
+            o.fmt("HEADER 13 - Number of apolar alpha sphere     : %5d\n", d.nAlphaApol);
+            o.put("HEADER 14 - Proportion of apolar alpha sphere : "); o.fixed(d.apolar_asphere_prop, 0, 4); o.ch('\n');
+            for (const int32_t k : uniq) atom_line(o, F->watoms[F->nolig[k]], fx ? fx + 4 * (size_t)k : nullptr);
+            o.put("TER\nEND\n");
+            snprintf(nm, sizeof nm, "/pocket%d_atm.pdb", r + 1);
+            ok &= write_file(pdir + nm, o, 0666, bytes_out);
+        }
+        if (cif_files) {                            // write_pocket_mmcif (writepocket.c:642-720)
+            o.clear();
+            o.fmt("data_pocket%d_atm\n# \nloop_\n_struct.pdbx_descriptor\n", r + 1);
+            o.put("This is a mmcif format file writen by the programm fpocket.                 \n"
+                  "It represents the atoms contacted by the voronoi vertices of the pocket.  \n"
+                  "                                                                           \n");
+            o.fmt("Information about the pocket %5d:\n", r + 1);
+            o.put("0  - Pocket Score                      : "); o.fixed(d.score, 0, 4); o.ch('\n');
+            o.put("1  - Drug Score                        : "); o.fixed(d.drug_score, 0, 4); o.ch('\n');
+            o.fmt("2  - Number of alpha spheres           : %5d\n", d.nb_asph);
+            o.put("3  - Mean alpha-sphere radius          : "); o.fixed(d.mean_asph_ray, 0, 4); o.ch('\n');
+            o.put("4  - Mean alpha-sphere Solvent Acc.    : "); o.fixed(d.masph_sacc, 0, 4); o.ch('\n');
+            o.put("5  - Mean B-factor of pocket residues  : "); o.fixed(d.flex, 0, 4); o.ch('\n');
+            o.put("6  - Hydrophobicity Score              : "); o.fixed(d.hydrophobicity_score, 0, 4); o.ch('\n');
+            o.fmt("7  - Polarity Score                    : %5d\n", d.polarity_score);
+            o.put("8  - Amino Acid based volume Score     : "); o.fixed(d.volume_score, 0, 4); o.ch('\n');
+            o.put("9  - Pocket volume (Monte Carlo)       : "); o.fixed(d.volume, 0, 4); o.ch('\n');
+            o.put("10  -Pocket volume (convex hull)       : "); o.fixed(d.convex_hull_volume, 0, 4); o.ch('\n');
+            o.fmt("11 - Charge Score                      : %5d\n", d.charge_score);
+            o.put("12 - Local hydrophobic density Score   : "); o.fixed(d.mean_loc_hyd_dens, 0, 4); o.ch('\n');
+            o.fmt("13 - Number of apolar alpha sphere     : %5d\n", d.nAlphaApol);
+            o.put("14 - Proportion of apolar alpha sphere : "); o.fixed(d.apolar_asphere_prop, 0, 4); o.ch('\n');
+            o.put("# \n");
+            o.put(CIF_ATOM_SITE);
+            for (const int32_t k : uniq) cif_atom(o, F->watoms[F->nolig[k]], fx ? fx + 4 * (size_t)k : nullptr);
+            o.put("# \n");
+            snprintf(nm, sizeof nm, "/pocket%d_atm.cif", r + 1);
+            ok &= write_file(pdir + nm, o, 0666, bytes_out);
+        }
     }
     return ok ? R->n_pockets : FPKIO_ERR_WRITE;
 }
@@ -1186,7 +1265,9 @@ int fpkio_run_list(const char *const *paths, int n, const fpkio_read_opts *ropts
 {
     if (ropts && ropts->ligand[0]) return FPKIO_ERR_UNSUPPORTED;          // a known ligand is dpocket's business: fpkio_run_dpocket
     return run_pipeline(paths, n, [ropts](int) { return ropts; }, p, detect, free_result, group, io_threads, quiet, stats,
-                        [paths](int k, const fpkio_file *f, const fpk_result *r, long long *bytes) { return fpkio_write_output(f, paths[k], r, bytes); });
+                        [paths, ropts](int k, const fpkio_file *f, const fpk_result *r, long long *bytes) {
+                            return fpkio_write_output_mode(f, paths[k], r, (ropts && ropts->write_mode) ? ropts->write_mode : 'p', bytes);
+                        });
 }
 
 int fpkio_nligand(const fpkio_file *f) { return f ? (int)f->lig_idx.size() : 0; }

@@ -16,9 +16,9 @@
  *   fpkio_run_list      = the "-F list" loop (src/fpmain.c:61-76) as a three-stage pipeline: reader pool -> one
  *                         fpk_detect_batch call per group of files -> writer pool
  *
- * Scope: PDB input, PDB-mode output (the reference's default for a .pdb input, fparams.c:397-407), chain filters -c / -k, explicit ligand -r,
+ * Scope: PDB input, PDB- and mmCIF-mode output (-w; PDB is the reference's default for a .pdb input, fparams.c:397-407), chain filters -c / -k, explicit ligand -r,
  * explicit pocket -P / -u, chain as ligand -a, model -l, dpocket's ligand mode. Not restated (use build/fpocket_cuda_batch, which keeps the reference's reader and writers):
- * mmCIF in or out, -d, -x. fpkio_* refuse those explicitly (FPKIO_ERR_UNSUPPORTED); nothing falls back silently.
+ * mmCIF input, -d, -x. fpkio_* refuse those explicitly (FPKIO_ERR_UNSUPPORTED); nothing falls back silently.
  *
  * The library has no CUDA dependency of its own: the detection call is handed in (fpk_detect_batch in the product,
  * build/fpocket_fast), so the CPU tests can drive the same pipeline with the oracle as the detector.
@@ -56,6 +56,7 @@ typedef struct fpkio_read_opts {
     int32_t n_lig_chains;        /* -a: chains treated as the ligand (fparams.c:186-201): their records become pdb->xlig_* and leave pdb; the reference's
                                     two passes disagree at chain boundaries (rpdb_read tests the PREVIOUS record's chain, rpdb.c:1079,1225) - reproduced */
     char lig_chains[20][21];
+    char write_mode;             /* -w for fpkio_run_list: 0 or 'p' = PDB set, 'm' = mmCIF set, 'b' = both (fparams.c:167-183) */
     int32_t model_number;        /* -l: > 0 reads only the records of that MODEL ... ENDMDL block when the file has MODEL records (rpdb.c:817-840,972-976) */
 } fpkio_read_opts;
 

@@ -166,7 +166,8 @@ def test_dpocket_fast_equals_reference_io_around_the_library(tmp_path):
 
 
 @pytest.mark.parametrize("name,extra", [("1UYD", ("-r", "1224:PU8:A")), ("1UYD", ("-P", "107:-:A.108:-:A.138:-:A.139:-:A.184:-:A", "-u", "2")),
-                                        ("1UYD", ("-k", "A")), ("2P0R_mod", ("-a", "D")), ("1g50", ("-a", "B", "-m", "3.0"))])
+                                        ("1UYD", ("-k", "A")), ("2P0R_mod", ("-a", "D")), ("1g50", ("-a", "B", "-m", "3.0")),
+                                        ("1UYD", ("-w", "both")), ("5WA6", ("-w", "cif"))])
 def test_explicit_ligand_and_pocket_options_equal_reference_io(tmp_path, name, extra):
     """fpocket -r (explicit ligand), -P (explicit pocket), -k and -a (chain as ligand, the reference's tests/reference_output/2P0R_mod case) on the
     reference's samples: build/fpocket_fast against the reference's reader and writers around the same library."""

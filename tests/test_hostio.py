@@ -258,7 +258,7 @@ def _writer_equal(src, tmp_path, params=None, min_pockets=1, mode="p"):
         assert a[k][0] == b[k][0], "content of %s differs" % k
         assert a[k][1] == b[k][1], "mode of %s differs: %o vs %o" % (k, a[k][1], b[k][1])
     assert npk == res.n_pockets or True
-    assert len(a) == (7 + 2 * npk if mode == "p" else 2 + npk) and sum(len(v[0]) for v in b.values()) == nbytes
+    assert len(a) == {"p": 7 + 2 * npk, "m": 7 + 2 * npk, "b": 12 + 3 * npk, "d": 2 + npk}[mode] and sum(len(v[0]) for v in b.values()) == nbytes
     return npk
 
 
@@ -275,6 +275,16 @@ def test_writers_equal_reference_on_a_synthetic_structure(tmp_path):
 @pytest.mark.parametrize("name", ["1UYD", "1ATP", "4bdf"])
 def test_writers_equal_reference_on_sample_files(tmp_path, name):
     assert _writer_equal(os.path.join(SAMPLE, name + ".pdb"), tmp_path) >= 5
+
+
+@needs_ref_io
+@needs_sample
+@pytest.mark.parametrize("mode", ["m", "b"])
+def test_writers_mmcif_modes(tmp_path, mode):
+    """-w m / -w both on a PDB input: <code>_out.cif, pocketK_atm.cif and the four *_cif* scripts (write_pockets_single_mmcif, write_pocket_mmcif,
+    write_mmcif_atom_line, write_mmcif_vert: writepocket.c:307-357,642-720, writepdb.c:201-236, voronoi.c:1486-1511), byte for byte."""
+    assert _writer_equal(os.path.join(SAMPLE, "1UYD.pdb"), tmp_path, mode=mode) >= 5
+    assert (tmp_path / "nat" / "1UYD_out" / "1UYD_out.cif").exists()
 
 
 @needs_ref_io
@@ -477,7 +487,7 @@ def test_fast_programs_fail_loudly_without_a_gpu(tmp_path):
     (tmp_path / "l.txt").write_text("x.pdb\tLIG\n")
     r = subprocess.run([dfast, "-f", "l.txt"], cwd=str(tmp_path), capture_output=True, text=True)
     assert r.returncode == 4 and "no CPU fallback" in r.stderr and not (tmp_path / "dpout_explicitp.txt").exists()
-    for opt in (["-x"], ["-d"], ["-w", "m"], ["-C", "m"]):
+    for opt in (["-x"], ["-d"], ["-e", "b"], ["-C", "m"]):
         r = subprocess.run([fast, "-f", "x.pdb"] + opt, cwd=str(tmp_path), capture_output=True, text=True)
         assert r.returncode == 3 and "fpocket_cuda_batch" in r.stderr, (opt, r.stderr)
     r = subprocess.run([fast, "-f", "x.cif"], cwd=str(tmp_path), capture_output=True, text=True)
