@@ -160,7 +160,8 @@ def test_dpocket_fast_equals_reference_io_around_the_library(tmp_path):
                 fx[36] = fy[36] = "-"
             assert fx[:9] == fy[:9] and fx[10:] == fy[10:], (tab, x, y)
             vx, vy = float(fx[9]), float(fy[9])
-            assert abs(vx - vy) <= 0.25 * max(vx, vy) + 5.0, (tab, vx, vy)           # 300 samples each: a few percent of the box
+            # 300 samples each, the reference's from a time-seeded rand(): sigma ~ Vbox * sqrt(p(1-p)/300) ~ 10 % of the volume per draw
+            assert abs(vx - vy) <= 0.6 * max(vx, vy) + 30.0, (tab, vx, vy)
             nrows += 1
     assert nrows >= 4 + 40
 
