@@ -765,7 +765,18 @@ int fpkio_read_pdb(const char *path, const fpkio_read_opts *opts, fpkio_file **o
     *out = nullptr;
     if (strstr(path, ".cif")) return FPKIO_ERR_UNSUPPORTED;         // fpmain.c:229: mmCIF goes to read_mmcif, which is not restated
     std::string buf;
-    if (!read_whole(path, buf)) return FPKIO_ERR_OPEN;
+    if (!read_whole(path, buf)) {
+        // fopen_pdb_check_case (utils.c:704-727): the four characters before ".pdb" in upper case, then in lower case
+        std::string alt = path;
+        const size_t len = alt.size();
+        bool ok = false;
+        if (len >= 8) {
+            for (size_t i = len - 8; i <= len - 5; i++) alt[i] = (char)toupper((unsigned char)alt[i]);
+            ok = read_whole(alt.c_str(), buf);
+            if (!ok) { for (size_t i = len - 8; i <= len - 5; i++) alt[i] = (char)tolower((unsigned char)alt[i]); ok = read_whole(alt.c_str(), buf); }
+        }
+        if (!ok) return FPKIO_ERR_OPEN;
+    }
     return parse_pdb(path, buf.data(), buf.size(), opts, out);
 }
 

@@ -51,6 +51,10 @@ def test_refusals_and_errors(tmp_path):
     (tmp_path / "e.pdb").write_text("HEADER nothing\nHETATM    1  O   HOH A   1       1.000   2.000   3.000  1.00 10.00           O\nEND\n")
     assert L.fpkio_read_pdb(str(tmp_path / "e.pdb").encode(), None, C.byref(h)) == hostio.FPKIO_ERR_NO_ATOMS
     assert L.fpkio_write_output(None, b"x.pdb", None, None) == hostio.FPKIO_ERR_BAD_ARG
+    # fopen_pdb_check_case (utils.c:704-727): a code given in the wrong case is found in upper, then lower case
+    (tmp_path / "1ABC.pdb").write_text("ATOM      1  N   ALA A   1       1.000   2.000   3.000  1.00 10.00           N\nEND\n")
+    assert L.fpkio_read_pdb(str(tmp_path / "1abc.pdb").encode(), None, C.byref(h)) == hostio.FPKIO_OK and L.fpkio_natoms(h, 0) == 1
+    L.fpkio_file_free(h)
 
 
 # ---- reader -----------------------------------------------------------------------------------------------------------------------------
