@@ -97,8 +97,49 @@ def lib():
         L.fpkio_write_output_mode.argtypes = [vp, C.c_char_p, C.POINTER(capi.FpkResult), C.c_char, C.POINTER(C.c_longlong)]
         L.fpkio_write_output_mode.restype = C.c_int
         L.fpkio_run_dpocket.restype = C.c_int
+        L.fpkio_md_topology.argtypes = [vp, C.POINTER(capi.FpkStructure)]
+        L.fpkio_md_topology.restype = C.c_int
+        L.fpkio_dcd_open.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.fpkio_dcd_open.restype = C.c_int
+        L.fpkio_dcd_read.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+        L.fpkio_dcd_read.restype = C.c_int
+        L.fpkio_dcd_close.argtypes = [vp]
+        L.fpkio_dcd_close.restype = None
+        L.fpkio_md_write_outputs.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int,
+                                             C.POINTER(capi.FpkParams), C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_longlong)]
+        L.fpkio_md_write_outputs.restype = C.c_int
         _lib = L
     return _lib
+
+
+def read_dcd(path, max_frames=1 << 30):
+    """All frames of a DCD trajectory as float32 [nframes, natoms, 3] (fpkio_dcd_*)."""
+    L = lib()
+    h, na, nf = C.c_void_p(), C.c_int(), C.c_int()
+    rc = L.fpkio_dcd_open(path.encode(), C.byref(h), C.byref(na), C.byref(nf))
+    if rc != FPKIO_OK:
+        raise IOError("fpkio_dcd_open(%s) failed: %d" % (path, rc))
+    n = min(max_frames, max(nf.value, 1))
+    out = np.zeros((n, na.value, 3), np.float32)
+    got = L.fpkio_dcd_read(h, out.ctypes.data_as(C.POINTER(C.c_float)), n)
+    L.fpkio_dcd_close(h)
+    return out[:max(got, 0)], nf.value
+
+
+def md_write_outputs(pdbfile, dens, freq, origin, dims, n_snapshots, params, paths, use_drug_score=0):
+    """normalize / project / write_first_bfactor_density / write_md_grid x 2 (fpkio_md_write_outputs). paths: freq.dx, dens.dx, freq_iso, dens_iso, pdensities."""
+    d = np.ascontiguousarray(dens, np.float32).ravel()
+    f = np.ascontiguousarray(freq, np.float32).ravel()
+    o = np.ascontiguousarray(origin, np.float32)
+    dm = np.ascontiguousarray(dims, np.int32)
+    pa = (C.c_char_p * 5)(*[p.encode() for p in paths])
+    nb = C.c_longlong(0)
+    fp = C.POINTER(C.c_float)
+    rc = lib().fpkio_md_write_outputs(pdbfile.h, d.ctypes.data_as(fp), f.ctypes.data_as(fp), o.ctypes.data_as(fp), dm.ctypes.data_as(C.POINTER(C.c_int)),
+                                      n_snapshots, C.byref(params), use_drug_score, pa, C.byref(nb))
+    if rc != FPKIO_OK:
+        raise IOError("fpkio_md_write_outputs failed: %d" % rc)
+    return nb.value
 
 
 class PdbFile:

@@ -1402,3 +1402,182 @@ int fpkio_run_dpocket(const char *const *paths, const char *const *ligands, int 
 }
 
 }  // extern "C"
+
+// ====================================================== mdpocket =========================================================================
+struct fpkio_dcd {
+    FILE *f = nullptr;
+    bool swap = false, cell = false, dim4 = false;
+    int natoms = 0, nframes = 0, read = 0;
+    std::vector<float> tmp;
+};
+
+namespace {
+uint32_t bswap32(uint32_t v) { return (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24); }
+bool dcd_int(fpkio_dcd *d, int32_t *v) { uint32_t u; if (fread(&u, 4, 1, d->f) != 1) return false; if (d->swap) u = bswap32(u); *v = (int32_t)u; return true; }
+bool dcd_skip_record(fpkio_dcd *d)      // a Fortran record: length, payload, length
+{
+    int32_t n, m;
+    if (!dcd_int(d, &n) || n < 0 || fseek(d->f, n, SEEK_CUR) || !dcd_int(d, &m) || m != n) return false;
+    return true;
+}
+}  // namespace
+
+extern "C" {
+
+int fpkio_dcd_open(const char *path, fpkio_dcd **out, int *natoms, int *nframes)
+{
+    if (!path || !out) return FPKIO_ERR_BAD_ARG;
+    *out = nullptr;
+    fpkio_dcd *d = new fpkio_dcd();
+    d->f = fopen(path, "rb");
+    if (!d->f) { delete d; return FPKIO_ERR_OPEN; }
+    uint32_t first;
+    char magic[4];
+    if (fread(&first, 4, 1, d->f) != 1) { fpkio_dcd_close(d); return FPKIO_ERR_UNSUPPORTED; }
+    if (first == 84) d->swap = false; else if (bswap32(first) == 84) d->swap = true; else { fpkio_dcd_close(d); return FPKIO_ERR_UNSUPPORTED; }
+    int32_t ic[20];
+    if (fread(magic, 1, 4, d->f) != 4 || memcmp(magic, "CORD", 4) || fread(ic, 4, 20, d->f) != 20) { fpkio_dcd_close(d); return FPKIO_ERR_UNSUPPORTED; }
+    if (d->swap) for (int i = 0; i < 20; i++) ic[i] = (int32_t)bswap32((uint32_t)ic[i]);
+    int32_t tail;
+    if (!dcd_int(d, &tail) || tail != 84) { fpkio_dcd_close(d); return FPKIO_ERR_UNSUPPORTED; }
+    d->nframes = ic[0];
+    const bool charmm = ic[19] != 0;
+    d->cell = charmm && ic[10] != 0;
+    d->dim4 = charmm && ic[11] != 0;
+    if (ic[8] != 0) { fpkio_dcd_close(d); return FPKIO_ERR_UNSUPPORTED; }       // fixed atoms: frames after the first carry only the free ones
+    int32_t n, m;
+    if (!dcd_skip_record(d)) { fpkio_dcd_close(d); return FPKIO_ERR_UNSUPPORTED; }                     // title
+    if (!dcd_int(d, &n) || n != 4 || !dcd_int(d, &d->natoms) || !dcd_int(d, &m) || m != 4 || d->natoms <= 0) { fpkio_dcd_close(d); return FPKIO_ERR_UNSUPPORTED; }
+    d->tmp.resize((size_t)3 * d->natoms);
+    if (natoms) *natoms = d->natoms;
+    if (nframes) *nframes = d->nframes;
+    *out = d;
+    return FPKIO_OK;
+}
+
+int fpkio_dcd_read(fpkio_dcd *d, float *xyz, int max_frames)
+{
+    if (!d || !xyz || max_frames < 0) return FPKIO_ERR_BAD_ARG;
+    int got = 0;
+    const size_t na = (size_t)d->natoms;
+    while (got < max_frames) {
+        int32_t n;
+        if (d->cell) { if (!dcd_skip_record(d)) break; }
+        bool ok = true;
+        for (int c = 0; c < 3 && ok; c++) {
+            int32_t m;
+            ok = dcd_int(d, &n) && n == (int32_t)(4 * na) && fread(d->tmp.data() + c * na, 4, na, d->f) == na && dcd_int(d, &m) && m == n;
+        }
+        if (!ok) break;                      // end of file (or a truncated frame: what was read so far stands)
+        if (d->dim4 && !dcd_skip_record(d)) break;
+        float *dst = xyz + (size_t)3 * na * got;
+        const float *X = d->tmp.data(), *Y = X + na, *Z = Y + na;
+        if (d->swap) {
+            for (size_t j = 0; j < na; j++) {
+                uint32_t a, b, c2;
+                memcpy(&a, X + j, 4); memcpy(&b, Y + j, 4); memcpy(&c2, Z + j, 4);
+                a = bswap32(a); b = bswap32(b); c2 = bswap32(c2);
+                memcpy(dst + 3 * j, &a, 4); memcpy(dst + 3 * j + 1, &b, 4); memcpy(dst + 3 * j + 2, &c2, 4);
+            }
+        } else
+            for (size_t j = 0; j < na; j++) { dst[3 * j] = X[j]; dst[3 * j + 1] = Y[j]; dst[3 * j + 2] = Z[j]; }
+        got++;
+        d->read++;
+    }
+    return got;
+}
+
+void fpkio_dcd_close(fpkio_dcd *d) { if (d) { if (d->f) fclose(d->f); delete d; } }
+
+int fpkio_md_topology(const fpkio_file *f, fpk_structure *st)
+{
+    if (!f || !st) return FPKIO_ERR_BAD_ARG;
+    if (fpkio_natoms(f, 0) != fpkio_natoms(f, 1) || f->nw_count >= 0) return FPKIO_ERR_UNSUPPORTED;
+    *st = f->st;
+    st->natoms_w = 0; st->wx = st->wy = st->wz = st->wradius = st->welectroneg = nullptr; st->wflags = nullptr;
+    st->same_pdb = 1;                            // search_pocket(pdb, params, pdb): asa.c:315 compares pointers
+    return FPKIO_OK;
+}
+
+int fpkio_md_write_outputs(const fpkio_file *F, const float *dens, const float *freq, const float origin[3], const int dims[3], int n_snapshots,
+                           const fpk_params *p, int use_drug_score, const char *const paths[5], long long *bytes_out)
+{
+    if (!F || !dens || !freq || !origin || !dims || !p || !paths || n_snapshots <= 0) return FPKIO_ERR_BAD_ARG;
+    const int nx = dims[0], ny = dims[1], nz = dims[2];
+    const size_t ncell = (size_t)nx * ny * nz;
+    const float res = 1.0f;                      // M_MDP_GRID_RESOLUTION
+    std::vector<float> g[2];
+    for (int q = 0; q < 2; q++) {                // normalize_grid (mdpbase.c:354-364)
+        g[q].assign(q == 0 ? freq : dens, (q == 0 ? freq : dens) + ncell);
+        for (float &v : g[q]) v /= (float)n_snapshots;
+    }
+    bool ok = true;
+    Out o;
+    // ---- project_grid_on_atoms(densgrid) + write_first_bfactor_density (mdpbase.c:301-340, mdpout.c:177-191) ----
+    {
+        const float ng1 = (float)2.0 / res;      // M_MDP_ATOM_DENSITY_DIST / resolution
+        const std::vector<float> &D = g[1];
+        const int n = (int)F->nolig.size();
+        o.clear();
+        for (int k = 0; k < n; k++) {
+            const AtomRec &a = F->watoms[F->nolig[k]];
+            float density = 0.0f;
+            int ix = (int)floor(((double)a.x - 2.0 - (double)origin[0]) / (double)res);
+            const float maxix = (float)(int)ceil(((double)a.x + 2.0 - (double)origin[0]) / (double)res);
+            const float maxiy = (float)(int)ceil(((double)a.y + 2.0 - (double)origin[1]) / (double)res);
+            const float maxiz = (float)(int)ceil(((double)a.z + 2.0 - (double)origin[2]) / (double)res);
+            while (ix <= maxix && nx > ix && ix >= 0) {
+                int iy = (int)floor(((double)a.y - 2.0 - (double)origin[1]) / (double)res);
+                while (iy <= maxiy && ny > iy && iy >= 0) {
+                    int iz = (int)floor(((double)a.z - 2.0 - (double)origin[2]) / (double)res);
+                    while (iz <= maxiz && nz > iz && iz >= 0) { density += D[((size_t)ix * ny + iy) * nz + iz]; iz++; }
+                    iy++;
+                }
+                ix++;
+            }
+            const float bf = (float)log((double)(1 + density / (ng1) / (float)n_snapshots));
+            pdb_line(o, "ATOM", a.id, a.name, a.aloc, a.res_name, a.chain, a.res_id, a.insert, a.x, a.y, a.z, bf, 0, a.symbol, a.charge, 0.0f);
+        }
+        o.put("TER\nEND\n");
+        ok &= write_file(paths[4], o, 0666, bytes_out);
+    }
+    // ---- write_md_grid (mdpout.c:71-122): DX file + iso-surface PDB, frequency grid then density grid ----
+    const float iso[2] = {0.5f, 8.0f};           // M_MDP_DEFAULT_ISO_VALUE_FREQ / _DENS
+    for (int q = 0; q < 2; q++) {
+        Out dx, pi;
+        dx.room(ncell * 7 + 1024);
+        dx.put("# Data calculated by mdpocket, part of the fpocket package\n"
+               "# This is a standard DX file of occurences of cavities within MD trajectories.\n"
+               "# The file can be visualised using the freely available VMD software\n"
+               "# fpocket parameters used to create this dx file : \n");
+        dx.fmt("# \t-m %2.f (min alpha sphere size) -M %.2f (max alpha sphere size)\n", p->asph_min_size, p->asph_max_size);
+        dx.fmt("# \t-i %d (min number of alpha spheres per pocket)\n", p->min_pock_nb_asph);
+        if (use_drug_score) dx.put("# \t-S (Map drug score to density map!)\n");
+        dx.fmt("object 1 class gridpositions counts %d %d %d\n", nx, ny, nz);
+        dx.fmt("origin %.2f %.2f %.2f\n", origin[0], origin[1], origin[2]);
+        dx.fmt("delta %.2f 0 0\ndelta 0 %.2f 0\ndelta 0 0 %.2f\n", res, res, res);
+        dx.fmt("object 2 class gridconnections counts %d %d %d\n", nx, ny, nz);
+        dx.fmt("object 3 class array type double rank 0 items %d data follows\n", nx * ny * nz);
+        int i = 0;
+        size_t cnt = 0, idx = 0;
+        for (int cx = 0; cx < nx; cx++)
+            for (int cy = 0; cy < ny; cy++)
+                for (int cz = 0; cz < nz; cz++, idx++) {
+                    if (i == 3) { i = 0; dx.ch('\n'); }
+                    const float cv = g[q][idx];
+                    dx.fixed(cv, 0, 3); dx.ch(' ');
+                    if (cv >= iso[q]) {
+                        cnt++;
+                        const float rx = origin[0] + cx * res, ry = origin[1] + cy * res, rz = origin[2] + cz * res;
+                        pi.put("ATOM  "); pi.integer((long long)(int)cnt, 5); pi.put("  C   PTH     1    ");
+                        pi.fixed(rx, 8, 3); pi.fixed(ry, 8, 3); pi.fixed(rz, 8, 3); pi.fixed(0.0, 6, 2); pi.fixed(0.0, 6, 2); pi.ch('\n');
+                    }
+                    i++;
+                }
+        ok &= write_file(paths[q], dx, 0666, bytes_out);
+        ok &= write_file(paths[2 + q], pi, 0666, bytes_out);
+    }
+    return ok ? FPKIO_OK : FPKIO_ERR_WRITE;
+}
+
+}  // extern "C"

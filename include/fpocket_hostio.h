@@ -106,6 +106,23 @@ int  fpkio_run_dpocket(const char *const *paths, const char *const *ligands, int
                        fpkio_free_fn free_result, const char *const out_paths[3], char write_mode /* 'd' (dpocket's usual) or 'p' */,
                        int group, int io_threads, int quiet, struct fpkio_stats *stats);
 
+/* ---- mdpocket (mdpocket.c:71-340, mdpbase.c:301-371, mdpout.c:71-122,177-191) ---------------------------------------------- */
+/* the structure mdpocket hands to search_pocket(pdb, params, pdb) (mdpocket.c:844): ONE atom list, pdb_w_lig is pdb itself. st must stay alive
+ * as long as f; returns FPKIO_ERR_UNSUPPORTED when the file has HETATM groups the two reference passes of trajectory mode disagree on
+ * (rpdb_open counts with keep_lig = 0, rpdb_read stores with keep_lig = 1: mdpocket.c:810,193) */
+int  fpkio_md_topology(const fpkio_file *f, fpk_structure *st);
+/* CHARMM / NAMD DCD trajectory (the format of BASELINE configs[2]; little or big endian, optional unit-cell records): header, then frames
+ * de-interleaved into xyz[nframes][natoms][3] */
+typedef struct fpkio_dcd fpkio_dcd;
+int  fpkio_dcd_open(const char *path, fpkio_dcd **out, int *natoms, int *nframes);
+int  fpkio_dcd_read(fpkio_dcd *d, float *xyz, int max_frames);              /* returns the number of frames read (0 at the end) or FPKIO_ERR_* */
+void fpkio_dcd_close(fpkio_dcd *d);
+/* what follows the frame loop: normalize_grid on both grids, project_grid_on_atoms(density grid) into the B-factor column of the topology's atoms,
+ * write_first_bfactor_density, write_md_grid for both (DX + iso-surface PDB). dens / freq: un-normalised sums [nx][ny][nz] as fpk_md_fetch_grids
+ * returns them. paths: freq.dx, dens.dx, freq_iso.pdb, dens_iso.pdb, all_atom_pdensities.pdb */
+int  fpkio_md_write_outputs(const fpkio_file *topology, const float *dens, const float *freq, const float origin[3], const int dims[3], int n_snapshots,
+                            const fpk_params *p, int use_drug_score, const char *const paths[5], long long *bytes_out);
+
 /* ---- the -F loop ------------------------------------------------------------------------------------------------------- */
 typedef struct fpkio_stats {
     int32_t n_files, n_written, n_read_failed, n_no_pockets, n_detect_failed;

@@ -14,6 +14,11 @@
  *        same reading, then shim_rebuild() on the fpk_result stored in result.bin and the reference's write_out_fpocket()
  *        (src/fpout.c:55): the files the reference's writers produce for THAT result
  *
+ *   ref_io mdwrite <grids.bin> <prefix> <fpocket options, -f top.pdb ...>
+ *        what mdpocket_detect does after its frame loop (mdpocket.c:276-330) with the reference's own code: normalize_grid on both grids,
+ *        project_grid_on_atoms, write_first_bfactor_density, write_md_grid x 2 -> <prefix>_{freq,dens}.dx, _{freq_iso_0_5,dens_iso_8}.pdb,
+ *        _all_atom_pdensities.pdb. grids.bin: int32 {nx,ny,nz,n_snapshots,use_drug_score}, float origin[3], dens[ncell], freq[ncell] (sums)
+ *
  * result.bin (written by tests/test_hostio.py): int32 header {n_sites,n_tets,n_spheres,n_clusters,n_pockets,natoms,sizeof(fpk_desc)},
  * then sph_xyzr, sph_bary, sph_neigh, sph_type, sph_cluster, cl_off, cl_sph, desc, rank_to_cluster, atom_fx as raw arrays.
  */
@@ -24,6 +29,9 @@
 
 #include "fpocket.h"
 #include "fpout.h"
+#include "mdpbase.h"
+#include "mdparams.h"
+#include "mdpout.h"
 #include "fpocket_cuda.h"
 #include "shim.h"
 
@@ -88,6 +96,56 @@ int main(int argc, char **argv)
 {
     if (argc < 4) { fprintf(stderr, "usage: ref_io atoms out.dump <fpocket args> | ref_io write result.bin <fpocket args>\n"); return 2; }
     const int do_write = !strcmp(argv[1], "write");
+    if (!strcmp(argv[1], "mdwrite")) {
+        if (argc < 6) return 2;
+        int na = argc - 3;
+        char **av = malloc(sizeof(char *) * (na + 1));
+        av[0] = argv[0];
+        for (int i = 4; i < argc; i++) av[i - 3] = argv[i];
+        av[na] = NULL;
+        s_fparams *fp = get_fpocket_args(na, av);
+        if (!fp) return 2;
+        FILE *g = fopen(argv[2], "rb");
+        int h[5];
+        float org[3];
+        if (!g || fread(h, 4, 5, g) != 5 || fread(org, 4, 3, g) != 3) return 5;
+        const size_t nc = (size_t)h[0] * h[1] * h[2];
+        float *grid[2];
+        s_mdgrid *G[2];
+        for (int q = 0; q < 2; q++) {           /* 0 = density, 1 = frequency; the allocation pattern of init_md_grid (mdpbase.c:446-502) */
+            grid[q] = malloc(sizeof(float) * nc);
+            if (fread(grid[q], 4, nc, g) != nc) return 5;
+            G[q] = malloc(sizeof(s_mdgrid));
+            G[q]->resolution = M_MDP_GRID_RESOLUTION; G[q]->nx = h[0]; G[q]->ny = h[1]; G[q]->nz = h[2]; G[q]->n_snapshots = h[3];
+            G[q]->origin = malloc(sizeof(float) * 3);
+            for (int k = 0; k < 3; k++) G[q]->origin[k] = org[k];
+            G[q]->gridvalues = malloc(sizeof(float **) * h[0]);
+            for (int x = 0; x < h[0]; x++) {
+                G[q]->gridvalues[x] = malloc(sizeof(float *) * h[1]);
+                for (int y = 0; y < h[1]; y++) G[q]->gridvalues[x][y] = grid[q] + ((size_t)x * h[1] + y) * h[2];
+            }
+        }
+        fclose(g);
+        s_mdparams par;
+        memset(&par, 0, sizeof par);
+        par.fpar = fp; par.flag_scoring = h[4];
+        normalize_grid(G[1], h[3]);
+        normalize_grid(G[0], h[3]);
+        s_pdb *cp = rpdb_open(fp->pdb_path, NULL, M_DONT_KEEP_LIG, 0, fp);
+        if (!cp) return 3;
+        rpdb_read(cp, NULL, M_DONT_KEEP_LIG, 0, fp);
+        project_grid_on_atoms(G[0], cp);
+        char nm[512];
+        FILE *f1, *f2;
+        snprintf(nm, sizeof nm, "%s_all_atom_pdensities.pdb", argv[3]); f1 = fopen(nm, "w"); write_first_bfactor_density(f1, cp); fclose(f1);
+        snprintf(nm, sizeof nm, "%s_freq.dx", argv[3]); f1 = fopen(nm, "w");
+        snprintf(nm, sizeof nm, "%s_freq_iso_0_5.pdb", argv[3]); f2 = fopen(nm, "w");
+        write_md_grid(G[1], f1, f2, &par, M_MDP_DEFAULT_ISO_VALUE_FREQ); fclose(f1); fclose(f2);
+        snprintf(nm, sizeof nm, "%s_dens.dx", argv[3]); f1 = fopen(nm, "w");
+        snprintf(nm, sizeof nm, "%s_dens_iso_8.pdb", argv[3]); f2 = fopen(nm, "w");
+        write_md_grid(G[0], f1, f2, &par, M_MDP_DEFAULT_ISO_VALUE_DENS); fclose(f1); fclose(f2);
+        return 0;
+    }
     const char *ligname = NULL;
     int first = 3;
     if (argc > 5 && !strcmp(argv[3], "--lig")) { ligname = argv[4]; first = 5; }

@@ -186,3 +186,45 @@ def test_explicit_ligand_and_pocket_options_equal_reference_io(tmp_path, name, e
     subprocess.check_call([BATCH, "list.txt", *extra], cwd=str(db), env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     a, b = _tree(str(da / (name + "_out"))), _tree(str(db / (name + "_out")))
     assert a == b and len(a) >= 9, sorted(k for k in set(a) | set(b) if a.get(k) != b.get(k))[:5]
+
+
+@pytest.mark.parametrize("mode", ["dcd", "pdb_list"])
+def test_mdpocket_fast_equals_reference_program_on_the_library(tmp_path, mode):
+    """build/mdpocket_fast (native topology / DCD / snapshot readers, fpk_md_*, native DX / PDB writers) against build/mdpocket_cuda (the
+    reference's mdpocket: molfile DCD reader, rpdb, normalize_grid, project_grid_on_atoms, write_md_grid around the same fpk_md_* calls):
+    the five output files byte for byte, with and without -S."""
+    import sys
+    import numpy as np
+    import synth
+    mfast, mref = os.path.join(ROOT, "build", "mdpocket_fast"), os.path.join(ROOT, "build", "mdpocket_cuda")
+    if not (os.path.exists(mfast) and os.path.exists(mref)):
+        pytest.skip("build/mdpocket_fast or build/mdpocket_cuda not built")
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import gpu_md_file_to_file as mdf
+    s = synth.generate(20267950, 2200, 0.065)
+    rng = np.random.default_rng(9)
+    nfr = 40 if mode == "dcd" else 7
+    xyz = np.stack([s.xyz] + [np.round(s.xyz + rng.normal(scale=0.25, size=s.xyz.shape).astype(np.float32), 3) for _ in range(nfr - 1)]).astype(np.float32)
+    files = ("freq", "dens", "freq_iso_0_5.pdb", "dens_iso_8.pdb", "all_atom_pdensities.pdb")
+    for score in ((), ("-S",)):
+        outs = []
+        for exe, d in ((mfast, tmp_path / ("fast" + "".join(score))), (mref, tmp_path / ("ref" + "".join(score)))):
+            d.mkdir()
+            synth.to_pdb(s, str(d / "top.pdb"))
+            if mode == "dcd":
+                mdf.write_dcd(str(d / "traj.dcd"), xyz)
+                args = ["--trajectory_file", "traj.dcd", "--trajectory_format", "dcd", "-f", "top.pdb"]
+            else:
+                import copy
+                with open(d / "list.txt", "w") as f:
+                    for i in range(nfr):
+                        sf = copy.copy(s)
+                        sf.xyz = xyz[i]
+                        synth.to_pdb(sf, str(d / ("f%02d.pdb" % i)))
+                        f.write("f%02d.pdb\n" % i)
+                args = ["--pdb_list", "list.txt"]
+            subprocess.check_call([exe, *args, "-o", "run", *score], cwd=str(d), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            outs.append(d)
+        for nm in ("run_freq.dx", "run_dens.dx", "run_freq_iso_0_5.pdb", "run_dens_iso_8.pdb", "run_all_atom_pdensities.pdb"):
+            a, b = (outs[0] / nm).read_bytes(), (outs[1] / nm).read_bytes()
+            assert a == b and len(a) > 100, (mode, score, nm, len(a), len(b))

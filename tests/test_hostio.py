@@ -496,3 +496,76 @@ def test_fast_programs_fail_loudly_without_a_gpu(tmp_path):
         assert r.returncode == 3 and "fpocket_cuda_batch" in r.stderr, (opt, r.stderr)
     r = subprocess.run([fast, "-f", "x.cif"], cwd=str(tmp_path), capture_output=True, text=True)
     assert r.returncode == 3 and "mmCIF" in r.stderr
+
+
+# ---- mdpocket: DCD reader, what follows the frame loop ---------------------------------------------------------------------------------------
+def test_dcd_reader(tmp_path):
+    """fpkio_dcd_*: CHARMM DCD as the molfile plugin of the reference reads it; little and big endian, with and without unit-cell records."""
+    import struct
+    rng = np.random.default_rng(11)
+    F, N = 7, 123
+    xyz = rng.normal(scale=20.0, size=(F, N, 3)).astype(np.float32)
+    for endian, cell in (("<", False), (">", False), ("<", True)):
+        path = str(tmp_path / ("t%s%d.dcd" % ("le" if endian == "<" else "be", cell)))
+        with open(path, "wb") as f:
+            ic = [0] * 20
+            ic[0], ic[1], ic[2], ic[3], ic[19] = F, 1, 1, F, 24
+            ic[10] = 1 if cell else 0
+            hdr = b"CORD" + struct.pack(endian + "20i", *ic)
+            hdr = hdr[:40] + struct.pack(endian + "f", 1.0) + hdr[44:]
+            f.write(struct.pack(endian + "i", 84) + hdr + struct.pack(endian + "i", 84))
+            f.write(struct.pack(endian + "i", 84) + struct.pack(endian + "i", 1) + b"x".ljust(80) + struct.pack(endian + "i", 84))
+            f.write(struct.pack(endian + "iii", 4, N, 4))
+            for k in range(F):
+                if cell:
+                    f.write(struct.pack(endian + "i", 48) + struct.pack(endian + "6d", 50, 0, 50, 0, 0, 50) + struct.pack(endian + "i", 48))
+                for c in range(3):
+                    f.write(struct.pack(endian + "i", 4 * N) + xyz[k, :, c].astype(endian + "f4").tobytes() + struct.pack(endian + "i", 4 * N))
+        got, nf = hostio.read_dcd(path)
+        assert nf == F and got.shape == (F, N, 3) and np.array_equal(got.view(np.uint32), xyz.view(np.uint32)), (endian, cell)
+    (tmp_path / "bad.dcd").write_bytes(b"not a dcd file at all")
+    with pytest.raises(IOError):
+        hostio.read_dcd(str(tmp_path / "bad.dcd"))
+
+
+@needs_ref_io
+@pytest.mark.parametrize("score", [0, 1])
+def test_md_outputs_equal_reference_writers(tmp_path, score):
+    """normalize_grid, project_grid_on_atoms, write_first_bfactor_density and write_md_grid (mdpbase.c:301-364, mdpout.c:71-122,177-191) on the
+    grids of a few oracle frames: the five files must equal, byte for byte, what the reference's own functions write for the same grids."""
+    import synth
+    s = synth.generate(20268501, 900, 0.065)
+    top = str(tmp_path / "top.pdb")
+    synth.to_pdb(s, top)
+    pf = hostio.PdbFile(top)
+    st = capi.FpkStructure()
+    assert hostio.lib().fpkio_md_topology(pf.h, C.byref(st)) == hostio.FPKIO_OK and st.same_pdb == 1 and st.natoms_w == 0
+    prm = api.default_params()
+    prm.do_asa_and_volume = 0
+    rng = np.random.default_rng(5)
+    syn = synth.to_structure(s)
+    org = dims = None
+    dens = freq = None
+    nfr = 3
+    for k in range(nfr):
+        syn.x, syn.y, syn.z = (np.ascontiguousarray(np.round(s.xyz[:, c] + (0 if k == 0 else rng.normal(scale=0.15, size=s.n)), 3).astype(np.float32)) for c in range(3))
+        o, d, gd, gf, _ = O.md_grids(syn, prm, use_drug_score=score, origin=org, dims=dims)
+        if org is None:
+            org, dims, dens, freq = o, d, gd.copy(), gf.copy()
+        else:
+            dens += gd
+            freq += gf
+    assert dens.sum() > 100
+    paths = [str(tmp_path / ("nat_" + nm)) for nm in ("freq.dx", "dens.dx", "freq_iso_0_5.pdb", "dens_iso_8.pdb", "all_atom_pdensities.pdb")]
+    nb = hostio.md_write_outputs(pf, dens, freq, org, dims, nfr, prm, paths, use_drug_score=score)
+    with open(tmp_path / "grids.bin", "wb") as f:
+        f.write(np.array([dims[0], dims[1], dims[2], nfr, score], np.int32).tobytes() + np.asarray(org, np.float32).tobytes())
+        f.write(np.ascontiguousarray(dens, np.float32).tobytes() + np.ascontiguousarray(freq, np.float32).tobytes())
+    r = subprocess.run([REF_IO, "mdwrite", str(tmp_path / "grids.bin"), str(tmp_path / "ref"), "-f", top], capture_output=True)
+    assert r.returncode == 0, r.stderr[-300:]
+    total = 0
+    for nm in ("freq.dx", "dens.dx", "freq_iso_0_5.pdb", "dens_iso_8.pdb", "all_atom_pdensities.pdb"):
+        a, b = open(tmp_path / ("ref_" + nm), "rb").read(), open(tmp_path / ("nat_" + nm), "rb").read()
+        assert a == b, nm
+        total += len(b)
+    assert total == nb and total > 100000
