@@ -476,9 +476,9 @@ def main():
         out["mdpocket"] = {"metric": "frames/sec", "value": F * world / float(mm[0]), "frames_per_gpu": F, "atoms": int(s5.n),
                            "grid": [int(v) for v in dims], "includes": "H2D of every frame, detection, grid scatter, NCCL all-reduce of both grids"}
         md.close()
-        # file to file: the reference's mdpocket program on the fpk_md_* API (build/mdpocket_cuda, fpocket_b200/shim/mdpocket_cuda.c): DCD
-        # trajectory in through the reference's molfile reader (double-buffered against the GPU), DX grids / PDB files out through its writers
-        mexe = os.path.join(ROOT, "build", "mdpocket_cuda")
+        # file to file: build/mdpocket_fast (fpocket_b200/hostio/mdpocket_fast.cpp): topology PDB and DCD trajectory in through the native readers
+        # (double-buffered against the GPU), DX grids / PDB files out through the native writers (byte-identical to the reference's, tests/)
+        mexe = os.path.join(ROOT, "build", "mdpocket_fast")
         if rank == 0 and world == 1 and os.path.exists(mexe) and args.md_file_frames > 0:
             sys.path.insert(0, os.path.join(ROOT, "scripts"))
             import gpu_md_file_to_file as mdf
@@ -494,8 +494,8 @@ def main():
             tq = time.time() - tq
             okf = rcm == 0 and os.path.exists(os.path.join(tmpd, "mdpout_dens_grid.dx"))
             out["mdpocket"]["file_to_file"] = {"value": Ff / tq if okf else None, "unit": "frames/s", "frames": Ff, "process_wall_s": tq,
-                                               "includes": "one process: CUDA start-up, topology PDB, %d-frame DCD through the molfile reader, detection, grid scatter, "
-                                                           "the reference's normalize / project / DX / PDB writers" % Ff}
+                                               "includes": "one process (build/mdpocket_fast): CUDA start-up, topology PDB, %d-frame DCD, detection, grid scatter, "
+                                                           "normalize / project / DX / PDB writers" % Ff}
             subprocess.call(["rm", "-rf", tmpd])
         if rank == 0 and world == 1 and not args.no_cpu:
             nfr = 2 * ncores

@@ -45,13 +45,16 @@ if __name__ == "__main__":
     synth.to_pdb(s, os.path.join(tmp, "top.pdb"))
     write_dcd(os.path.join(tmp, "traj.dcd"), xyz)
     write_dcd(os.path.join(tmp, "ref.dcd"), xyz[:nref])
-    exe, ref = os.path.join(ROOT, "build", "mdpocket_cuda"), os.path.join(ROOT, "oracle", "_ref", "mdpocket")
-    if os.path.exists(exe):
+    ref = os.path.join(ROOT, "oracle", "_ref", "mdpocket")
+    for prog, what in (("mdpocket_fast", "native DCD reader / writers"), ("mdpocket_cuda", "the reference's molfile reader / writers")):
+        exe = os.path.join(ROOT, "build", prog)
+        if not os.path.exists(exe):
+            continue
+        d2 = os.path.join(tmp, prog); os.makedirs(d2)
         t = time.time()
-        subprocess.check_call([exe, "--trajectory_file", "traj.dcd", "--trajectory_format", "dcd", "-f", "top.pdb"], cwd=tmp, stdout=subprocess.DEVNULL)
+        subprocess.check_call([exe, "--trajectory_file", "../traj.dcd", "--trajectory_format", "dcd", "-f", "../top.pdb"], cwd=d2, stdout=subprocess.DEVNULL)
         dt = time.time() - t
-        print("mdpocket_cuda: %d frames, %.2f s process wall (CUDA start-up, DCD reading, detection, grids, DX / PDB writing): %.0f frames/s" % (F, dt, F / dt))
-        print("   outputs:", sorted(os.listdir(tmp))[:12])
+        print("%s (%s): %d frames, %.2f s process wall (CUDA start-up, DCD reading, detection, grids, DX / PDB writing): %.0f frames/s" % (prog, what, F, dt, F / dt))
     if os.path.exists(ref) and nref > 0:
         d2 = os.path.join(tmp, "r"); os.makedirs(d2)
         t = time.time()
