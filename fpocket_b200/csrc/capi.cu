@@ -97,6 +97,7 @@ extern "C" int fpk_init(const int *devices, int ndev)
         CK(cudaFuncSetAttribute(k_delaunay_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pr.sharedMemPerBlockOptin - fa.sharedSizeBytes)));
         CK(cudaFuncGetAttributes(&fa, k_hull_volume));
         CK(cudaFuncSetAttribute(k_hull_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pr.sharedMemPerBlockOptin - fa.sharedSizeBytes)));
+        CK(cudaFuncSetAttribute(k_hull_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HW_WARPS * sizeof(HullWarp))));
     }
     g_init = true;
     return FPK_OK;
@@ -250,6 +251,7 @@ struct fpk_batch {
     PocketDev Pk;
     int *d_clbase = nullptr, *d_sbase = nullptr;
     DelScratch *dHull = nullptr; int nHull = 0;
+    int *d_hull_fb = nullptr; int nHullWarp = 0;     // pockets the warp-per-pocket hull kernel hands to the Delaunay route
     DescScratch *dDesc = nullptr; int nDesc = 0;
     // compact outputs (device)
     float4 *c_xyzr = nullptr; float *c_bary = nullptr; int4 *c_neigh = nullptr; uint8_t *c_type = nullptr; int *c_cluster = nullptr;
@@ -549,6 +551,9 @@ static int batch_run(fpk_batch *b)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occD, k_descriptors, K4_THREADS, 0);
     occH = std::max(1, std::min(occH, FPK_HULL_MINBLOCKS)); occD = std::max(1, std::min(occD, 8));
     b->nHull = (int)std::max(1ll, std::min<long long>(NC, (long long)g_sms * occH));
+    int occW = FPK_HW_MINBLOCKS;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occW, k_hull_warp, HW_THREADS, HW_WARPS * sizeof(HullWarp));
+    b->nHullWarp = (int)std::max(1ll, std::min<long long>((NC + 32 * HW_WARPS - 1) / (32 * HW_WARPS), (long long)g_sms * std::max(1, occW)));
     b->nDesc = (int)std::max(1ll, std::min<long long>(NC, (long long)g_sms * occD));
     std::vector<DelScratch> hHull(b->nHull);
     std::vector<DescScratch> hDesc(b->nDesc);
@@ -566,6 +571,7 @@ static int batch_run(fpk_batch *b)
         b->c_type = a.take<uint8_t>(NS + 1); b->c_cluster = a.take<int>(NS + 1); b->c_cl_sph = a.take<int>(NS + 1);
         b->c_cl_off = a.take<int>(NC + n + 1);
         b->dHull = a.take<DelScratch>(b->nHull); b->dDesc = a.take<DescScratch>(b->nDesc);
+        b->d_hull_fb = a.take<int>(NC + 1);
         if (b->tot_lig > 0) b->Lg.crit = a.take<float>(4 * NC + 4);
         if (full) for (int i = 0; i < b->nHull; i++) del_scratch_layout(a, hHull[i], max_ns, 0, HULL_THREADS, false);
         for (int i = 0; i < b->nDesc; i++) hDesc[i].sa = a.take<int>(b->max_w + 1);
@@ -584,7 +590,13 @@ static int batch_run(fpk_batch *b)
     // (the kernels compute R = sph_off + cl_off[c]; with sph_off replaced by sbase for these arrays). See PocketDev.
     CK(cudaEventRecord(b->ev[3]));
     if (NC > 0) {
-        if (full) { k_hull_volume<<<b->nHull, HULL_THREADS, b->hull_dsm>>>(B, Pk, b->dHull, b->d_counters + 2, b->hull_picap); b->launches++; }
+        if (full) {
+            // K4b: one warp per pocket (incremental exact hull in shared memory); what it declines goes through the block-per-pocket Delaunay
+            static const int hw_enable = getenv("FPK_HULL_WARP") ? atoi(getenv("FPK_HULL_WARP")) : 1;
+            k_hull_warp<<<b->nHullWarp, HW_THREADS, HW_WARPS * sizeof(HullWarp)>>>(B, Pk, b->d_counters + 4, b->d_hull_fb, b->d_counters + 5, hw_enable);
+            k_hull_volume<<<b->nHull, HULL_THREADS, b->hull_dsm>>>(B, Pk, b->dHull, b->d_counters + 2, b->hull_picap, b->d_hull_fb, b->d_counters + 5);
+            b->launches += 2;
+        }
         CK(cudaEventRecord(b->ev[4]));
         k_descriptors<<<b->nDesc, K4_THREADS>>>(B, Pk, b->dDesc, b->d_counters + 3);
         CK(cudaEventRecord(b->ev[5]));

@@ -2,9 +2,83 @@
 #pragma once
 #include "k_delaunay.cuh"
 #include "k_pockets.cuh"
+#include "hull_warp.cuh"
 
 namespace fpk {
 
+// K4b, first kernel: one WARP per pocket, incremental exact hull in shared memory (hull_warp.cuh). Warps take chunks of 32
+// clusters from a counter, every lane decides whether its cluster gets a hull volume at all (voronoi.c:1244: fewer than 10
+// centres -> 0; clusters refine.c:124 always drops are never described), then the warp works through the chunk's pockets.
+// A pocket outside the fast path's limits goes on the list the Delaunay kernel below consumes.
+#ifndef FPK_HW_WARPS
+#define FPK_HW_WARPS 4
+#endif
+#ifndef FPK_HW_MINBLOCKS
+#define FPK_HW_MINBLOCKS 4
+#endif
+enum { HW_WARPS = FPK_HW_WARPS, HW_THREADS = 32 * FPK_HW_WARPS };
+__global__ void __launch_bounds__(HW_THREADS, FPK_HW_MINBLOCKS) k_hull_warp(BatchDev B, PocketDev Pk, int *chunk_counter, int *fb_list, int *fb_count,
+                                                                           int enable)
+{
+    extern __shared__ __align__(16) unsigned char hw_smem[];
+    const int lane = threadIdx.x & 31;
+    HullWarp &H = reinterpret_cast<HullWarp *>(hw_smem)[threadIdx.x >> 5];
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(chunk_counter, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= Pk.total_clusters) return;
+        const int item = base + lane;
+        int k = 0, off = 0, n = 0;
+        bool want = false;
+        if (item < Pk.total_clusters) {
+            int lo = 0, hi = B.nstruct;
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (Pk.clbase[mid] <= item) lo = mid; else hi = mid; }
+            k = lo;
+            const int c = item - Pk.clbase[k];
+            const int *cl_off = B.cl_off + B.S[k].sph_off + k;
+            off = cl_off[c]; n = cl_off[c + 1] - off;
+            const int *kc = B.counts + (size_t)k * CNT_STRIDE;
+            const bool xp = kc[CNT_XP] == 1 && c == kc[CNT_CLUSTERS] - 1;      // dpocket's explicit pocket: always described
+            want = !(n < 10 || (n < B.prm.min_pock_nb_asph && !xp));
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, want);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int it = base + src, ks = __shfl_sync(0xffffffffu, k, src), os = __shfl_sync(0xffffffffu, off, src),
+                      ns = __shfl_sync(0xffffffffu, n, src);
+            bool fast = enable && ns <= HW_NCAP;
+            if (fast) {
+                const int so = B.S[ks].sph_off;
+                const int *L = B.cl_sph + so + os;
+                const float4 *sx = B.s_xyzr + so;
+                const float4 v0 = sx[L[0]];
+                const long long ox = __double2ll_rn(__dmul_rn((double)v0.x, 1e6)), oy = __double2ll_rn(__dmul_rn((double)v0.y, 1e6)),
+                                oz = __double2ll_rn(__dmul_rn((double)v0.z, 1e6));
+                bool wide = false;
+                __syncwarp();
+                for (int i = lane; i < ns; i += 32) {
+                    const float4 v = sx[L[i]];
+                    const long long rx = __double2ll_rn(__dmul_rn((double)v.x, 1e6)) - ox, ry = __double2ll_rn(__dmul_rn((double)v.y, 1e6)) - oy,
+                                    rz = __double2ll_rn(__dmul_rn((double)v.z, 1e6)) - oz;
+                    wide |= llabs(rx) >= HW_MAXREL || llabs(ry) >= HW_MAXREL || llabs(rz) >= HW_MAXREL;
+                    H.px[i] = (int)rx; H.py[i] = (int)ry; H.pz[i] = (int)rz;
+                }
+                __syncwarp();
+                if (__any_sync(0xffffffffu, wide)) fast = false;
+                else {
+                    i128 tot = 0;
+                    if (hull_warp_run(H, ns, lane, &tot)) fast = false;
+                    else if (lane == 0) Pk.desc[it].convex_hull_volume = hull_total_to_volume(tot);
+                }
+            }
+            if (!fast && lane == 0) fb_list[atomicAdd(fb_count, 1)] = it;
+        }
+    }
+}
+
+// K4b, second kernel: the pockets the warp kernel handed over (more than HW_NCAP centres, degenerate, ...), one block each.
 // Replaces reference src/voronoi.c:1235-1291 get_convex_hull_volume -> src/qhull/src/qconvex/qconvex.c:37 run_qconvex("FS")
 // (text through temp files, a second qhull run per pocket). The hull volume equals the summed volume of the Delaunay
 // tetrahedra of the same points, so the block-parallel exact Delaunay of delaunay.cuh is reused on the pocket's centres
@@ -17,7 +91,8 @@ namespace fpk {
 #define FPK_HULL_THREADS 64
 #endif
 enum { HULL_THREADS = FPK_HULL_THREADS };
-__global__ void __launch_bounds__(HULL_THREADS, FPK_HULL_MINBLOCKS) k_hull_volume(BatchDev B, PocketDev Pk, const DelScratch *scratch, int *work_counter, int pi_cap)
+__global__ void __launch_bounds__(HULL_THREADS, FPK_HULL_MINBLOCKS) k_hull_volume(BatchDev B, PocketDev Pk, const DelScratch *scratch, int *work_counter, int pi_cap, const int *fb_list,
+                                                                                  const int *fb_count)
 {
     __shared__ int s_item;
     BlockDel &BD = blk();
@@ -30,19 +105,16 @@ __global__ void __launch_bounds__(HULL_THREADS, FPK_HULL_MINBLOCKS) k_hull_volum
     const DelScratch &X = scratch[blockIdx.x];
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_item = atomicAdd(work_counter, 1);
+        if (tid == 0) { const int w = atomicAdd(work_counter, 1); s_item = w < *fb_count ? fb_list[w] : -1; }
         __syncthreads();
         const int item = s_item;
-        if (item >= Pk.total_clusters) return;
+        if (item < 0) return;
         int lo = 0, hi = B.nstruct;
         while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (Pk.clbase[mid] <= item) lo = mid; else hi = mid; }
         const int k = lo, c = item - Pk.clbase[k];
         const StructDev S = B.S[k];
         const int *cl_off = B.cl_off + S.sph_off + k;
         const int off = cl_off[c], n = cl_off[c + 1] - off;
-        const int *kc = B.counts + (size_t)k * CNT_STRIDE;
-        const bool xp = kc[CNT_XP] == 1 && c == kc[CNT_CLUSTERS] - 1;      // dpocket's explicit pocket: always described
-        if (n < 10 || (n < B.prm.min_pock_nb_asph && !xp)) continue;     // voronoi.c:1244: volume 0 (desc is zero-initialised); always-dropped clusters (refine.c:124) too
         const int *L = B.cl_sph + S.sph_off + off;
         const float4 *sx = B.s_xyzr + S.sph_off;
         for (int i = tid; i < n; i += nt) {
@@ -68,10 +140,7 @@ __global__ void __launch_bounds__(HULL_THREADS, FPK_HULL_MINBLOCKS) k_hull_volum
         if (tid == 0) {
             i128 tot = 0;
             for (int t = 0; t < nt; t++) tot += (i128)(((u128)(unsigned long long)s_hi[t] << 64) | (u128)s_lo[t]);
-            long long h = (long long)(tot >> 64);
-            unsigned long long l = (unsigned long long)tot;
-            double vol = (double)h * 18446744073709551616.0 + (double)l;
-            Pk.desc[item].convex_hull_volume = (float)(vol / 6.0 * 1e-18);
+            Pk.desc[item].convex_hull_volume = hull_total_to_volume(tot);
         }
     }
 }
