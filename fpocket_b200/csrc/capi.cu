@@ -894,11 +894,12 @@ struct fpk_md {
     bool have_grid = false;
     float origin[3]; int dims[3];
     float *d_dens = nullptr, *d_freq = nullptr; unsigned *d_mask = nullptr; unsigned long long *d_nscat = nullptr;
+    long long *d_dens_fx = nullptr, *d_freq_fx = nullptr;      // -S: 32.32 fixed-point accumulators (order-free sums), see MdGrid
     float *d_geom = nullptr;
     int nwords = 0, nblocks = 0;
     long long frames = 0, launches = 0;
     float *pin[2] = {nullptr, nullptr}, *d_xyz[2] = {nullptr, nullptr}; size_t stage_cap = 0;     // double-buffered frame staging
-    ~fpk_md() { for (int q = 0; q < 2; q++) { if (pin[q]) cudaFreeHost(pin[q]); if (d_xyz[q]) cudaFree(d_xyz[q]); } delete b; cudaFree(d_dens); cudaFree(d_freq); cudaFree(d_mask); cudaFree(d_nscat); cudaFree(d_geom); }
+    ~fpk_md() { for (int q = 0; q < 2; q++) { if (pin[q]) cudaFreeHost(pin[q]); if (d_xyz[q]) cudaFree(d_xyz[q]); } delete b; cudaFree(d_dens); cudaFree(d_freq); cudaFree(d_mask); cudaFree(d_nscat); cudaFree(d_geom); cudaFree(d_dens_fx); cudaFree(d_freq_fx); }
 };
 
 static int md_prepare(fpk_md *m, int nframes)
@@ -996,12 +997,17 @@ extern "C" int fpk_md_set_grid(fpk_md *m, const float origin[3], const int dims[
     if (!m || !origin || !dims || dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return fail(FPK_ERR_BAD_ARG, "fpk_md_set_grid: bad arguments");
     for (int q = 0; q < 3; q++) { m->origin[q] = origin[q]; m->dims[q] = dims[q]; }
     size_t ncell = (size_t)dims[0] * dims[1] * dims[2];
-    cudaFree(m->d_dens); cudaFree(m->d_freq); cudaFree(m->d_mask); cudaFree(m->d_nscat);
+    cudaFree(m->d_dens); cudaFree(m->d_freq); cudaFree(m->d_mask); cudaFree(m->d_nscat); cudaFree(m->d_dens_fx); cudaFree(m->d_freq_fx);
+    m->d_dens_fx = m->d_freq_fx = nullptr;
     m->nwords = (int)((ncell + 31) / 32);
     m->nblocks = g_sms * 2;
     CK(cudaMalloc(&m->d_dens, sizeof(float) * ncell)); CK(cudaMalloc(&m->d_freq, sizeof(float) * ncell));
     CK(cudaMalloc(&m->d_mask, sizeof(unsigned) * (size_t)m->nwords * m->nblocks)); CK(cudaMalloc(&m->d_nscat, 8));
     CK(cudaMemset(m->d_dens, 0, sizeof(float) * ncell)); CK(cudaMemset(m->d_freq, 0, sizeof(float) * ncell)); CK(cudaMemset(m->d_nscat, 0, 8));
+    if (m->use_drug) {
+        CK(cudaMalloc(&m->d_dens_fx, sizeof(long long) * ncell)); CK(cudaMalloc(&m->d_freq_fx, sizeof(long long) * ncell));
+        CK(cudaMemset(m->d_dens_fx, 0, sizeof(long long) * ncell)); CK(cudaMemset(m->d_freq_fx, 0, sizeof(long long) * ncell));
+    }
     m->have_grid = true;
     return FPK_OK;
 }
@@ -1072,6 +1078,7 @@ extern "C" int fpk_md_push_frames(fpk_md *m, const float *xyz, int nframes)
             for (int q = 0; q < 3; q++) G.origin[q] = m->origin[q];
             G.nx = m->dims[0]; G.ny = m->dims[1]; G.nz = m->dims[2];
             G.dens = m->d_dens; G.freq = m->d_freq; G.mask = m->d_mask; G.nwords = m->nwords; G.use_drug_score = m->use_drug;
+            G.dens_fx = m->d_dens_fx; G.freq_fx = m->d_freq_fx;
             k_md_scatter<<<std::min(m->nblocks, nf), 256>>>(m->b->B, m->b->Pk, G, m->d_nscat);
             cudaError_t e = cudaStreamSynchronize(cudaStreamPerThread);
             if (e != cudaSuccess) rc = fail(FPK_ERR_CUDA, "k_md_scatter: %s", cudaGetErrorString(e));
@@ -1088,9 +1095,22 @@ extern "C" int fpk_md_push_frames(fpk_md *m, const float *xyz, int nframes)
     return FPK_OK;
 }
 
+// -S: the float grids are views of the fixed-point accumulators, refreshed whenever they are handed out
+static int md_refresh_float_grids(fpk_md *m)
+{
+    if (!m->d_dens_fx) return FPK_OK;
+    const size_t ncell = (size_t)m->dims[0] * m->dims[1] * m->dims[2];
+    k_md_fixed_to_float<<<g_sms * 4, 256>>>(m->d_dens_fx, m->d_dens, ncell);
+    k_md_fixed_to_float<<<g_sms * 4, 256>>>(m->d_freq_fx, m->d_freq, ncell);
+    m->launches += 2;
+    CK(cudaStreamSynchronize(cudaStreamPerThread));
+    return FPK_OK;
+}
+
 extern "C" int fpk_md_device_grids(fpk_md *m, void **dens, void **freq, size_t *ncell)
 {
     if (!m || !m->have_grid) return fail(FPK_ERR_BAD_ARG, "no grid");
+    { int rc = md_refresh_float_grids(m); if (rc) return rc; }
     if (dens) *dens = m->d_dens;
     if (freq) *freq = m->d_freq;
     if (ncell) *ncell = (size_t)m->dims[0] * m->dims[1] * m->dims[2];
@@ -1100,6 +1120,7 @@ extern "C" int fpk_md_fetch_grids(fpk_md *m, float *dens, float *freq)
 {
     if (!m || !m->have_grid) return fail(FPK_ERR_BAD_ARG, "no grid");
     size_t ncell = (size_t)m->dims[0] * m->dims[1] * m->dims[2];
+    { int rc = md_refresh_float_grids(m); if (rc) return rc; }
     if (dens) CK(cudaMemcpy(dens, m->d_dens, sizeof(float) * ncell, cudaMemcpyDeviceToHost));
     if (freq) CK(cudaMemcpy(freq, m->d_freq, sizeof(float) * ncell, cudaMemcpyDeviceToHost));
     return FPK_OK;

@@ -156,7 +156,22 @@ struct MdGrid {
     unsigned *mask;            // [gridDim.x * nwords]
     int nwords;
     int use_drug_score;
+    // -S: the increments are floats (the pocket's drug score). Float atomics would make the sums depend on the order in which blocks
+    // reach a cell, i.e. differ in the last bits from run to run; they are accumulated as 32.32 fixed-point integers instead (exact,
+    // order-free) and converted to the float grids when those are read (k_md_fixed_to_float).
+    long long *dens_fx, *freq_fx;
 };
+#define FPK_MD_FX_ONE 4294967296.0
+__device__ __forceinline__ void md_add(float *grid, long long *fx, size_t g, float incre, long long incre_fx)
+{
+    if (fx) atomicAdd(reinterpret_cast<unsigned long long *>(fx) + g, (unsigned long long)incre_fx);
+    else atomicAdd(&grid[g], incre);
+}
+__global__ void k_md_fixed_to_float(const long long *fx, float *grid, size_t ncell)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < ncell; i += (size_t)gridDim.x * blockDim.x)
+        grid[i] = (float)((double)fx[i] / FPK_MD_FX_ONE);
+}
 
 __device__ __forceinline__ int md_idx(int o, float v, float org, float res, int ctr)
 {
@@ -186,6 +201,7 @@ __global__ void __launch_bounds__(256) k_md_scatter(BatchDev B, PocketDev Pk, Md
         for (int r = 0; r < npk; r++) {                                 // pockets in rank order: "first toucher" is per pocket
             const int c = rank[r];
             const float incre = G.use_drug_score ? D[c].drug_score : 1.0f;
+            const long long incre_fx = G.dens_fx ? __double2ll_rn((double)incre * FPK_MD_FX_ONE) : 0;
             const int off = cl_off[c], n = cl_off[c + 1] - off;
             for (int q = tid; q < n; q += nt) {
                 const float4 v = sx[cl_sph[off + q]];
@@ -197,7 +213,7 @@ __global__ void __launch_bounds__(256) k_md_scatter(BatchDev B, PocketDev Pk, Md
                     int gx = md_idx(sxi, v.x, G.origin[0], res, xidx), gy = md_idx(syi, v.y, G.origin[1], res, yidx),
                         gz = md_idx(szi, v.z, G.origin[2], res, zidx);
                     if (((gx != xidx) || (gy != yidx) || (gz != zidx)) && gx >= 0 && gy >= 0 && gz >= 0 && gx < nx && gy < ny && gz < nz)
-                        atomicAdd(&G.dens[((size_t)gx * ny + gy) * nz + gz], incre);
+                        md_add(G.dens, G.dens_fx, ((size_t)gx * ny + gy) * nz + gz, incre, incre_fx);
                 }
                 // frequency: half-width (int)((ray/2)/res) (mdpbase.c:218), each cell at most once per frame
                 const int s = (int)(((double)v.w / 2.0) / (double)res);
@@ -208,13 +224,13 @@ __global__ void __launch_bounds__(256) k_md_scatter(BatchDev B, PocketDev Pk, Md
                     if (((gx != xidx) || (gy != yidx) || (gz != zidx)) && gx >= 0 && gy >= 0 && gz >= 0 && gx < nx && gy < ny && gz < nz) {
                         size_t g = ((size_t)gx * ny + gy) * nz + gz;
                         unsigned bit = 1u << (g & 31);
-                        if (!(atomicOr(&mask[g >> 5], bit) & bit)) atomicAdd(&G.freq[g], incre);
+                        if (!(atomicOr(&mask[g >> 5], bit) & bit)) md_add(G.freq, G.freq_fx, g, incre, incre_fx);
                     }
                 }
                 // the centre cell is incremented once per POCKET, with the indices of its LAST sphere (mdpbase.c:164-166, :255-260)
                 if (q == n - 1 && xidx < nx && yidx < ny && zidx < nz && xidx >= 0 && yidx >= 0 && zidx >= 0) {
                     size_t g = ((size_t)xidx * ny + yidx) * nz + zidx;
-                    atomicAdd(&G.dens[g], incre);
+                    md_add(G.dens, G.dens_fx, g, incre, incre_fx);
                 }
             }
             __syncthreads();
@@ -226,7 +242,7 @@ __global__ void __launch_bounds__(256) k_md_scatter(BatchDev B, PocketDev Pk, Md
                 if (xidx < nx && yidx < ny && zidx < nz && xidx >= 0 && yidx >= 0 && zidx >= 0) {
                     size_t g = ((size_t)xidx * ny + yidx) * nz + zidx;
                     unsigned bit = 1u << (g & 31);
-                    if (!(atomicOr(&mask[g >> 5], bit) & bit)) atomicAdd(&G.freq[g], incre);
+                    if (!(atomicOr(&mask[g >> 5], bit) & bit)) md_add(G.freq, G.freq_fx, g, incre, incre_fx);
                 }
                 atomicAdd(nscattered, (unsigned long long)n);
             }

@@ -186,7 +186,10 @@ int fpk_md_grid_from_frame(fpk_md *m, const float *xyz, float origin[3], int dim
 int fpk_md_set_grid(fpk_md *m, const float origin[3], const int dims[3]);
 /* detect + calculate_md_dens_grid + update_md_grid for nframes frames; xyz = [nframes][natoms][3] host floats */
 int fpk_md_push_frames(fpk_md *m, const float *xyz, int nframes);
-/* device pointers of the two accumulators (float[nx*ny*nz]) so the caller can sum them across ranks (NCCL) */
+/* device pointers of the two accumulators (float[nx*ny*nz]) so the caller can sum them across ranks (NCCL).
+ * With -S the increments are floats (drug scores): they are summed as 32.32 fixed-point integers so that the result does not depend on
+ * the order in which frames reach a cell (same input, same bytes); the float grids are refreshed from those sums by this call and by
+ * fpk_md_fetch_grids, so call it again after pushing more frames. */
 int fpk_md_device_grids(fpk_md *m, void **dens, void **freq, size_t *ncell);
 int fpk_md_fetch_grids(fpk_md *m, float *dens, float *freq);    /* D2H, un-normalised sums (normalize_grid stays host, mdpbase.c:354) */
 long long fpk_md_counter(const fpk_md *m, int which);            /* 0 frames, 1 spheres scattered, 2 launches */

@@ -227,7 +227,7 @@ def test_md_grids_equal_oracle(case):
     m.set_grid(org, dims)
     m.push_frames(np.concatenate([xyz, xyz, xyz]))
     gd, gf = m.fetch_grids()
-    if score:   # float increments: atomics change the summation order
+    if score:   # float increments: the reference adds them one by one in float, the library sums them exactly (32.32 fixed point, order-free)
         assert np.allclose(gd, 3 * dens, rtol=1e-5, atol=1e-6) and np.allclose(gf, 3 * freq, rtol=1e-5, atol=1e-6)
     else:
         assert np.array_equal(gd, 3 * dens) and np.array_equal(gf, 3 * freq)
@@ -265,6 +265,48 @@ def test_md_trajectory_of_distinct_frames_equals_oracle():
         freq += ff
     assert np.array_equal(gd, dens) and np.array_equal(gf, freq)
     assert gd.sum() > 0 and gf.sum() > 0
+
+
+def test_md_grids_with_drug_score_do_not_depend_on_how_frames_are_pushed():
+    """-S: the increments are floats. The library sums them in 32.32 fixed point, so the grids are the same bits whether the frames
+    arrive one by one (the reference's loop, build/mdpocket_cuda) or in one block (build/mdpocket_fast), and equal, to float rounding,
+    the reference's frame-by-frame float sums (oracle)."""
+    import copy
+    import synth
+    api = _api()
+    s = synth.generate(20269501, 2300, 0.065)
+    st = synth.to_structure(s)
+    p = api.default_params()
+    rng = np.random.default_rng(4)
+    frames = np.round(s.xyz[None] + rng.normal(scale=0.25, size=(9,) + s.xyz.shape).astype(np.float32), 3).astype(np.float32)
+    frames[0] = s.xyz
+    grids = []
+    for how in ("block", "single", "pairs"):
+        m = api.MdPocket(st, p, use_drug_score=True)
+        org, dims = m.grid_from_frame(frames[:1])
+        m.set_grid(org, dims)
+        if how == "block":
+            m.push_frames(frames)
+        else:
+            step = 1 if how == "single" else 2
+            for i in range(0, len(frames), step):
+                m.push_frames(frames[i:i + step])
+        grids.append(m.fetch_grids())
+        m.close()
+    for gd, gf in grids[1:]:
+        assert np.array_equal(gd, grids[0][0]) and np.array_equal(gf, grids[0][1])
+    dens = np.zeros(dims, np.float32)
+    freq = np.zeros(dims, np.float32)
+    pm = api.default_params()
+    pm.do_asa_and_volume = 0                    # mdpocket.c:89
+    for f in frames:
+        sf = copy.copy(st)
+        sf.x, sf.y, sf.z = (np.ascontiguousarray(f[:, k]) for k in range(3))
+        _, _, dd, ff, _ = O.md_grids(sf, pm, origin=org, dims=dims, use_drug_score=1)
+        dens += dd
+        freq += ff
+    assert np.allclose(grids[0][0], dens, rtol=1e-5, atol=1e-6) and np.allclose(grids[0][1], freq, rtol=1e-5, atol=1e-6)
+    assert grids[0][0].sum() > 0 and grids[0][1].sum() > 0
 
 
 def _points_structure(xyz):
