@@ -22,10 +22,10 @@
 namespace fpk {
 
 #ifndef FPK_HW_NCAP
-#define FPK_HW_NCAP 512
+#define FPK_HW_NCAP 1024
 #endif
 #ifndef FPK_HW_FCAP
-#define FPK_HW_FCAP 768
+#define FPK_HW_FCAP 1024
 #endif
 enum { HW_NCAP = FPK_HW_NCAP, HW_FCAP = FPK_HW_FCAP, HW_IDMASK = 1023, HW_MAXREL = 1 << 30 };
 static_assert(HW_NCAP <= 1024, "face words hold 10-bit point ids");

@@ -11,10 +11,10 @@ namespace fpk {
 // centres -> 0; clusters refine.c:124 always drops are never described), then the warp works through the chunk's pockets.
 // A pocket outside the fast path's limits goes on the list the Delaunay kernel below consumes.
 #ifndef FPK_HW_WARPS
-#define FPK_HW_WARPS 4
+#define FPK_HW_WARPS 2         // 22 KB of shared memory per warp: 2 x 5 blocks per SM measured best (profiles/r01_k4b_hull_capacity_ab.log)
 #endif
 #ifndef FPK_HW_MINBLOCKS
-#define FPK_HW_MINBLOCKS 4
+#define FPK_HW_MINBLOCKS 5
 #endif
 enum { HW_WARPS = FPK_HW_WARPS, HW_THREADS = 32 * FPK_HW_WARPS };
 __global__ void __launch_bounds__(HW_THREADS, FPK_HW_MINBLOCKS) k_hull_warp(BatchDev B, PocketDev Pk, int *chunk_counter, int *fb_list, int *fb_count,

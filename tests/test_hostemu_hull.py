@@ -41,7 +41,7 @@ def emu_hull(ki):
     return rc, v.value, ve.value
 
 
-@pytest.mark.parametrize("n,seed", [(4, 0), (5, 1), (10, 2), (15, 3), (60, 4), (200, 5), (512, 6)])
+@pytest.mark.parametrize("n,seed", [(4, 0), (5, 1), (10, 2), (15, 3), (60, 4), (200, 5), (512, 6), (1024, 7)])
 def test_hull_volume_equals_delaunay_volume_on_random_clouds(n, seed):
     rng = np.random.default_rng(seed)
     for rep in range(20):
@@ -55,7 +55,7 @@ def test_hull_volume_equals_delaunay_volume_on_random_clouds(n, seed):
 def test_hull_volume_on_points_of_a_sphere_surface():
     """All points are hull vertices: the face count reaches 2n - 4; above the face capacity the routine declines."""
     rng = np.random.default_rng(11)
-    for n, expect in ((300, 0), (386, 0), (500, 1)):
+    for n, expect in ((300, 0), (514, 0), (600, 1)):
         x = rng.normal(size=(n, 3))
         ki = (x / np.linalg.norm(x, axis=1)[:, None] * 15e6).astype(np.int64)
         rc0, _, vol0 = O.delaunay(ki)
@@ -77,7 +77,7 @@ def test_hull_volume_on_the_golden_pockets():
         done = 0
         for c in range(len(off) - 1):
             idx = o["cl_sph"][off[c]:off[c + 1]]
-            if len(idx) < 10 or len(idx) > 512:
+            if len(idx) < 10 or len(idx) > 1024:
                 continue
             rc0, _, vol0 = O.delaunay(ki[idx])
             rc, v, ve = emu_hull(ki[idx])
@@ -107,6 +107,6 @@ def test_hull_volume_degenerate_inputs():
     flat = ki.copy(); flat[:, 2] = 7
     assert emu_hull(flat)[0] == 1
     # too many points / too wide: pre-checks
-    assert emu_hull(np.zeros((513, 3), np.int64))[0] == 2
+    assert emu_hull(np.zeros((1025, 3), np.int64))[0] == 2
     wide = ki.copy(); wide[5, 0] += 1 << 31
     assert emu_hull(wide)[0] == 2
