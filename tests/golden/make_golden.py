@@ -31,6 +31,10 @@ CASES = [
     ("1UYD_explicit", "1UYD.pdb", ["--seed", "16"], ["-r", "1224:PU8:A"]),       # test_fpocket.py:117
     ("2P0R_mod_aD", "2P0R_mod.pdb", ["--seed", "17"], ["-a", "D"]),              # test_fpocket.py:125
     ("5RGF_cif", "5RGF.cif", ["--seed", "18"], []),                              # test_mmcif.py:77
+    ("4URL", "4URL.pdb", ["--seed", "20"], []),                                   # test_fpocket.py:69 (the largest of the default list)
+    ("2P0R_cD", "2P0R.pdb", ["--seed", "21"], ["-c", "D"]),                       # test_fpocket.py:111 drop a chain
+    ("6X3P_cif", "6X3P.cif", ["--seed", "22"], []),                               # test_mmcif.py:82
+    ("1QNH_cif_aCD", "1QNH.cif", ["--seed", "23"], ["-a", "C,D"]),                # test_mmcif.py:92 chains as ligand, mmCIF reader
     ("1UYD_dpocket", "1UYD.pdb", ["--seed", "19", "--lig", "PU8"], []),            # dpocket.c:186-290 with the known ligand
     ("md_2yex", "mdpocket/2yex.pdb", ["--md"], []),                           # mdpocket.c:833 call shape
     ("md_3ot3_S", "mdpocket/3ot3.pdb", ["--md", "--score"], []),              # -S drug-score increments
