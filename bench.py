@@ -344,15 +344,16 @@ def main():
            "k_hull_volume": 16 * S + 4 * P0}
     ach = alg[dom] / (per_stage[dom] * 1e-3) / 1e9
     whole = (32 * N + 32 * T + 108 * S + 160 * P0)
-    traffic = None
+    traffic, traffic_n = None, 0
     try:        # DRAM bytes of the dominant kernel from the committed ncu --set full capture, scaled to this launch by algorithmic bytes
         tj = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
         if tj["kernel"] == dom:
             traffic = tj["dram_bytes"] * alg[dom] / tj["algorithmic_bytes"]
+            traffic_n = tj["structures"]
     except Exception:
         pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-            "traffic_source": "profiles/k1_traffic.json (ncu dram__bytes_read+write of a 296-structure launch, scaled by algorithmic bytes)" if traffic else None,
+            "traffic_source": ("profiles/k1_traffic.json (ncu dram__bytes_read+write of a %d-structure launch, scaled by algorithmic bytes)" % traffic_n) if traffic else None,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": per_stage[dom],
             "whole_path": {"algorithmic_bytes_per_step": whole, "achieved_gbs": whole / (t_dev / args.steps) / 1e9,
                            "frac": whole / (t_dev / args.steps) / 1e9 / peak}}
