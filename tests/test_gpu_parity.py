@@ -309,6 +309,31 @@ def test_md_grids_with_drug_score_do_not_depend_on_how_frames_are_pushed():
     assert grids[0][0].sum() > 0 and grids[0][1].sum() > 0
 
 
+def test_hull_volume_is_the_same_through_both_routes(tmp_path):
+    """K4b has two routes to the same exact integer: one warp per pocket (incremental hull, hull_warp.cuh) and, for what that declines, one
+    block per pocket (Delaunay of the centres, k_hull_volume). FPK_HULL_WARP=0 (read once per process) sends every pocket through the second
+    route and its hand-over list: a child process runs two golden cases that way and must report the floats this process gets."""
+    import os
+    import subprocess
+    import sys
+    api = _api()
+    code = ("import sys, numpy as np\n"
+            "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import golden_cases as G\n"
+            "from fpocket_b200 import api\n"
+            "for c in sys.argv[2:]:\n"
+            "    st, p = G.inputs(G.load(c))\n"
+            "    np.save(sys.argv[1] + '/' + c + '.npy', api.detect(st, p)['desc']['convex_hull_volume'])\n") % (O.ROOT, os.path.join(O.ROOT, "tests"))
+    cases = ["5WA6", "4URL"]
+    env = dict(os.environ, FPK_HULL_WARP="0")
+    subprocess.check_call([sys.executable, "-c", code, str(tmp_path)] + cases, env=env)
+    for c in cases:
+        st, p = G.inputs(G.load(c))
+        here = api.detect(st, p)["desc"]["convex_hull_volume"]
+        there = np.load(str(tmp_path / (c + ".npy")))
+        assert np.array_equal(here, there) and (here > 0).sum() >= 10, c
+
+
 def _points_structure(xyz):
     """a bare point set as a structure (carbon atoms, one residue each): only the Delaunay stage is of interest"""
     from fpocket_b200 import capi
