@@ -614,6 +614,17 @@ static int batch_run(fpk_batch *b)
     { int rcq = fetch_counts(b); if (rcq) return rcq; }
     CK(cudaGetLastError());
     for (int i = 0; i < 6; i++) cudaEventElapsedTime(&b->ms[i], b->ev[i], b->ev[i + 1]);
+#ifdef FPK_K4_PROFILE
+    {
+        unsigned long long h[12] = {0}, z[12] = {0};
+        cudaMemcpyFromSymbol(h, g_k4prof, sizeof h);
+        cudaMemcpyToSymbol(g_k4prof, z, sizeof z);
+        fprintf(stderr, "k_descriptors split: %llu clusters below min_pock_nb_asph, %.1f M block cycles (%.0f each); %llu others, %.1f M block cycles (%.0f each)\n",
+                h[1], h[0] / 1e6, h[1] ? (double)h[0] / h[1] : 0.0, h[3], h[2] / 1e6, h[3] ? (double)h[2] / h[3] : 0.0);
+        if (h[1]) fprintf(stderr, "k_descriptors split, the first kind by phase (cycles per cluster): fetch + contacted atoms %.0f, CSR %.0f, sums / surroundings / SASA %.0f, per-atom epilogue %.0f, record %.0f\n",
+                          (double)h[4] / h[1], (double)h[5] / h[1], (double)h[6] / h[1], (double)h[7] / h[1], (double)h[8] / h[1]);
+    }
+#endif
     cudaEventElapsedTime(&b->ms[7], b->ev[0], b->ev[6]);
     return FPK_OK;
 }

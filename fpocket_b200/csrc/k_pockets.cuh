@@ -244,6 +244,10 @@ __device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 96;" 
 // K4: one block per cluster. After the contacted-atom lists are built the block splits:
 //   warp 0     - the reference's sequential float sums (pair loop of descriptors.c:186-236 etc.), in the reference's order;
 //   warps 1..3 - surrounding atoms, the two SASA passes and the Monte-Carlo volume (integer counts: order-free).
+#ifdef FPK_K4_PROFILE
+// measurement build only (scripts/gpu_k4_split.sh): block cycles and counts of work items, [0,1] clusters below min_pock_nb_asph, [2,3] the others
+__device__ unsigned long long g_k4prof[12];      // [4..8]: the first kind by phase (fetch + contacted atoms, CSR, sums / surroundings / SASA, per-atom epilogue, record)
+#endif
 __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, PocketDev Pk, const DescScratch *scratch, int *work_counter)
 {
     __shared__ int s_item, s_U, s_cnt[100], s_sm[40], s_segcnt[3], s_mcdim[4], s_mcmode, s_asanext, s_mcnext;
@@ -257,9 +261,24 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
     const DescScratch &X = scratch[blockIdx.x];
     const fpk_params &prm = B.prm;
+#ifdef FPK_K4_PROFILE
+    long long prof_t = 0, prof_p[4] = {0, 0, 0, 0}; int prof_class = -1;
+#endif
     for (;;) {
         __syncthreads();
         if (tid == 0) s_item = atomicAdd(work_counter, 1);
+#ifdef FPK_K4_PROFILE
+        if (tid == 0) {
+            const long long now = clock64();
+            if (prof_class >= 0) { atomicAdd(&g_k4prof[2 * prof_class], (unsigned long long)(now - prof_t)); atomicAdd(&g_k4prof[2 * prof_class + 1], 1ull); }
+            if (prof_class == 0) {
+                atomicAdd(&g_k4prof[4], (unsigned long long)(prof_p[0] - prof_t)); atomicAdd(&g_k4prof[5], (unsigned long long)(prof_p[1] - prof_p[0]));
+                atomicAdd(&g_k4prof[6], (unsigned long long)(prof_p[2] - prof_p[1])); atomicAdd(&g_k4prof[7], (unsigned long long)(prof_p[3] - prof_p[2]));
+                atomicAdd(&g_k4prof[8], (unsigned long long)(now - prof_p[3]));
+            }
+            prof_t = now;
+        }
+#endif
         __syncthreads();
         const int item = s_item;
         if (item >= Pk.total_clusters) return;
@@ -294,6 +313,9 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
         const bool observable = explicit_pocket || n >= prm.min_pock_nb_asph;      // below it the cluster is always dropped (refine.c:124): no MC samples
         const bool insm = n <= MC_SMEM_SPH;
         const float correct = -1.6f;
+#ifdef FPK_K4_PROFILE
+        prof_class = observable ? 1 : 0;
+#endif
 
         // ---- 1. warp 0: unique contacted atoms by atom id, first-seen order (pocket.c:1280-1320); warps 1..3: MC sphere tile ----------
         if (wid == 0) {
@@ -346,6 +368,9 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
             if (tid == 33) { s_asanext = 0; s_mcnext = 0; }
         }
         __syncthreads();
+#ifdef FPK_K4_PROFILE
+        if (tid == 0) { prof_p[0] = clock64(); }
+#endif
         const int U = s_U;
         // ---- 2. spheres touching each unique atom (CSR) ----------------------------------------------------------------------------
         for (int u = tid; u <= U; u += nt) toff[u] = 0;
@@ -362,6 +387,9 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
         __syncthreads();
         for (int u = tid; u < 4 * U; u += nt) acc[u] = 0;
         __syncthreads();
+#ifdef FPK_K4_PROFILE
+        if (tid == 0) { prof_p[1] = clock64(); }
+#endif
 
         // ---- work shared by all four warps once warp 0 is through with its sequential sums (3a): contacted atoms of the SASA pass and
         // chunks of Monte-Carlo samples are handed out through two counters in shared memory; both only add integers, so who does what is free
@@ -711,6 +739,9 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
             if (observable) mc_samples();
         }
         __syncthreads();
+#ifdef FPK_K4_PROFILE
+        if (tid == 0) { prof_p[2] = clock64(); }
+#endif
 
         // ---- 6. the ASA / volume part of the record (needs the counts of all four warps) ----------------------------------------------
         // 6a. per contacted atom, all threads: the two areas (asa.c:330,384: an f64 expression rounded to f32) and the per-atom side effects
@@ -739,28 +770,47 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
             }
         }
         __syncthreads();
-        // 6b. one thread: only the float sums whose order is the reference's (atoms in first-seen order, probe 1.4 then 2.2)
-        if (tid == 0) {
-            fpk_desc d = s_desc;
+#ifdef FPK_K4_PROFILE
+        if (tid == 0) { prof_p[3] = clock64(); }
+#endif
+        // 6b. only the float sums whose order is the reference's (atoms in first-seen order, probe 1.4 then 2.2). The rest of the block waits for
+        //     this, so the per-atom values are fetched 32 atoms at a time by the lanes of warp 0 (one 16-byte load each) and handed round by shuffles:
+        //     every lane adds the same values in the same order; the two passes of the reference touch disjoint sums and are fused.
+        if (wid == 0) {
+            float apol14 = s_desc.surf_apol_vdw14, pol14 = s_desc.surf_pol_vdw14, v14 = s_desc.surf_vdw14;
+            float apol22 = s_desc.surf_apol_vdw22, pol22 = s_desc.surf_pol_vdw22, v22 = s_desc.surf_vdw22;
+            int nabpa = s_desc.n_abpa;
             if (full) {
-                for (int u = 0; u < U; u++) {
-                    const float area = __int_as_float(acc[4 * u]);
-                    if (acc[4 * u + 2]) d.surf_apol_vdw14 = d.surf_apol_vdw14 + area; else d.surf_pol_vdw14 = d.surf_pol_vdw14 + area;
-                    d.surf_vdw14 = d.surf_vdw14 + area;
+                for (int base = 0; base < U; base += 32) {
+                    const int u = base + lane;
+                    int4 a = make_int4(0, 0, 0, 0);
+                    if (u < U) a = *reinterpret_cast<const int4 *>(acc + 4 * (size_t)u);
+                    const int cnt = min(32, U - base);
+                    for (int q = 0; q < cnt; q++) {
+                        const float a14 = __int_as_float(__shfl_sync(0xffffffffu, a.x, q)), a22 = __int_as_float(__shfl_sync(0xffffffffu, a.y, q));
+                        const int apolar_atom = __shfl_sync(0xffffffffu, a.z, q), flag = __shfl_sync(0xffffffffu, a.w, q);
+                        if (apolar_atom) { apol14 = apol14 + a14; apol22 = apol22 + a22; }
+                        else { pol14 = pol14 + a14; nabpa += flag; pol22 = pol22 + a22; }
+                        v14 = v14 + a14; v22 = v22 + a22;
+                    }
                 }
-                for (int u = 0; u < U; u++) {
-                    const float area = __int_as_float(acc[4 * u + 1]);
-                    if (acc[4 * u + 2]) d.surf_apol_vdw22 = d.surf_apol_vdw22 + area;
-                    else { d.n_abpa += acc[4 * u + 3]; d.surf_pol_vdw22 = d.surf_pol_vdw22 + area; }
-                    d.surf_vdw22 = d.surf_vdw22 + area;
-                }
-                const float vbox = (s_mcbox[1] - s_mcbox[0]) * (s_mcbox[3] - s_mcbox[2]) * (s_mcbox[5] - s_mcbox[4]);
-                float sum_volume = 0.0f;
-                for (int li = 0; li < 100; li++) sum_volume += ((float)s_cnt[li]) / ((float)prm.nb_mcv_iter) * vbox;
-                d.volume = observable ? sum_volume / (float)100 : 0.0f;
             }
-            d.convex_hull_volume = D->convex_hull_volume;       // written by k_hull_volume before this kernel
-            *D = d;
+            if (lane == 0) {
+                fpk_desc d = s_desc;
+                if (full) {
+                    d.surf_apol_vdw14 = apol14; d.surf_pol_vdw14 = pol14; d.surf_vdw14 = v14;
+                    d.surf_apol_vdw22 = apol22; d.surf_pol_vdw22 = pol22; d.surf_vdw22 = v22; d.n_abpa = nabpa;
+                    d.volume = 0.0f;
+                    if (observable) {
+                        const float vbox = (s_mcbox[1] - s_mcbox[0]) * (s_mcbox[3] - s_mcbox[2]) * (s_mcbox[5] - s_mcbox[4]);
+                        float sum_volume = 0.0f;
+                        for (int li = 0; li < 100; li++) sum_volume += ((float)s_cnt[li]) / ((float)prm.nb_mcv_iter) * vbox;
+                        d.volume = sum_volume / (float)100;
+                    }
+                }
+                d.convex_hull_volume = D->convex_hull_volume;       // written by k_hull_warp / k_hull_volume before this kernel
+                *D = d;
+            }
         }
     }
 }
