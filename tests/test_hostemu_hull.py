@@ -110,3 +110,40 @@ def test_hull_volume_degenerate_inputs():
     assert emu_hull(np.zeros((1025, 3), np.int64))[0] == 2
     wide = ki.copy(); wide[5, 0] += 1 << 31
     assert emu_hull(wide)[0] == 2
+
+
+def test_hull_volume_fuzz_on_degenerate_and_structured_sets():
+    """Small-integer clouds (coplanar, collinear and repeated points everywhere), points on a coarse lattice, on three planes, along a tube: whenever
+    the oracle's Delaunay exists the routine must either decline or return exactly its volume; a flat set is always declined."""
+    rng = np.random.default_rng(20260)
+    done = 0
+    for it in range(900):
+        kind = it % 5
+        if kind == 0:
+            n = int(rng.integers(4, 40))
+            span = int(rng.choice([2, 3, 4, 6, 10, 50, 1000]))
+            ki = rng.integers(0, span, size=(n, 3)).astype(np.int64) * int(rng.choice([1, 1000, 1000000]))
+        else:
+            n = int(rng.integers(10, 300))
+            if kind == 1:
+                ki = (rng.normal(size=(n, 3)) * 3e6).astype(np.int64)
+                ki[rng.integers(0, n, size=n // 10)] = ki[0]
+            elif kind == 2:
+                ki = rng.integers(-8, 8, size=(n, 3)).astype(np.int64) * 500000
+            elif kind == 3:
+                ki = (rng.random((n, 3)) * 2e7).astype(np.int64)
+                ki[:n // 3, 0] = 0
+                ki[n // 3:2 * n // 3, 1] = 7000000
+            else:
+                t = rng.random(n) * 3e7
+                ki = np.stack([t, 2e6 * np.sin(t / 4e6) + rng.normal(size=n) * 1.5e6, rng.normal(size=n) * 1.5e6], 1).astype(np.int64)
+        rc0, _, vol0 = O.delaunay(ki)
+        rc, v, ve = emu_hull(ki)
+        if rc0 != 0:
+            assert rc == 1
+            continue
+        assert rc in (0, 1)
+        if rc == 0:
+            assert ve == vol0 and v == np.float32(vol0), (kind, n)
+            done += 1
+    assert done > 800
