@@ -232,6 +232,12 @@ __device__ __forceinline__ float unif_from_bits(unsigned r31, float mn, float mx
     return mn + rnd;
 }
 
+#ifndef FPK_K4_STAGE_TOUCHING
+#define FPK_K4_STAGE_TOUCHING 0
+#endif
+#ifndef FPK_K4_SEARCH_NEAR
+#define FPK_K4_SEARCH_NEAR 0
+#endif
 struct DescScratch {          // per resident block of K4
     int *sa;                  // [natoms_w max] surrounding atoms of the current pocket (asa.c:84-112), three ordered segments
 };
@@ -261,6 +267,10 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
     const DescScratch &X = scratch[blockIdx.x];
     const fpk_params &prm = B.prm;
+#if FPK_K4_SEARCH_NEAR
+    __shared__ int s_klast;           // in shared memory: a register that lives across the whole work item costs the kernel 300 bytes of spills
+    if (tid == 0) s_klast = -1;
+#endif
 #ifdef FPK_K4_PROFILE
     long long prof_t = 0, prof_p[4] = {0, 0, 0, 0}; int prof_class = -1;
 #endif
@@ -284,6 +294,15 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
         if (item >= Pk.total_clusters) return;
         // (structure, cluster) of this work item
         int lo = 0, hi = B.nstruct;
+#if FPK_K4_SEARCH_NEAR
+        // EXPERIMENT, off by default, not yet measured on a GPU (DESIGN.md par. 9): items are handed out in order, so the structure of a block's next
+        // item is almost always the one of its last item or the next one: two loads instead of a 12-step chain of dependent ones
+        const int k_last = s_klast;       // written after the first barrier of the previous item, read after the two barriers of this one
+        if (k_last >= 0) {
+            if (Pk.clbase[k_last] <= item && item < Pk.clbase[k_last + 1]) { lo = k_last; hi = k_last + 1; }
+            else if (k_last + 2 <= B.nstruct && Pk.clbase[k_last + 1] <= item && item < Pk.clbase[k_last + 2]) { lo = k_last + 1; hi = k_last + 2; }
+        }
+#endif
         while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (Pk.clbase[mid] <= item) lo = mid; else hi = mid; }
         const int k = lo, c = item - Pk.clbase[k];
         const StructDev S = B.S[k];
@@ -371,6 +390,9 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
 #ifdef FPK_K4_PROFILE
         if (tid == 0) { prof_p[0] = clock64(); }
 #endif
+#if FPK_K4_SEARCH_NEAR
+        if (tid == 0) s_klast = k;
+#endif
         const int U = s_U;
         // ---- 2. spheres touching each unique atom (CSR) ----------------------------------------------------------------------------
         for (int u = tid; u <= U; u += nt) toff[u] = 0;
@@ -426,6 +448,13 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                     ncand += __popc(bal);
                 }
             }
+#if FPK_K4_STAGE_TOUCHING
+            // EXPERIMENT, off by default, not yet measured or parity-checked on a GPU (DESIGN.md par. 9): the spheres touching this atom are read by every
+            // one of the 200 tests through three dependent global loads (tlist -> L -> sx); copy them once behind the burial candidates instead
+            const int t0 = toff[u], ntouch = toff[u + 1] - t0;
+            const bool staged = !overflow && ncand + ntouch <= ASA_CAND;
+            if (staged) for (int q = lane; q < ntouch; q += 32) cand[ASA_CAND - ntouch + q] = sx[L[tlist[t0 + q]]];
+#endif
             __syncwarp();
             for (int it = lane; it < 200; it += 32) {
                 const int pass = it >= 100 ? 1 : 0, kp = it - 100 * pass;
@@ -434,6 +463,14 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                 const float ty = (float)((double)cy + (double)c_spiral[3 * kp + 1] * ((double)crad + probe));
                 const float tz = (float)((double)cz + (double)c_spiral[3 * kp + 2] * ((double)crad + probe));
                 bool vref = true;                                   // "vrefburried": not inside any touching alpha sphere
+#if FPK_K4_STAGE_TOUCHING
+                if (staged) {
+                    for (int q = 0; q < ntouch && vref; q++) {
+                        const float4 v = cand[ASA_CAND - ntouch + q];
+                        if (f_ddist(tx, ty, tz, v.x, v.y, v.z) <= v.w * v.w) vref = false;
+                    }
+                } else
+#endif
                 for (int q = toff[u]; q < toff[u + 1] && vref; q++) {
                     float4 v = sx[L[tlist[q]]];
                     if (f_ddist(tx, ty, tz, v.x, v.y, v.z) <= v.w * v.w) vref = false;
