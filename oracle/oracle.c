@@ -568,6 +568,22 @@ void orc_result_free(fpk_result *r)
     memset(r, 0, sizeof *r);
 }
 
+/* ---------------------------------------- mdpocket characterize mode ---------------------------------------- */
+/* mdpocket.c:436-460 (one snapshot of mdpocket_characterize): after search_pocket, extract_wanted_vertices (mdpocket.c:695-745) gathers the spheres of the
+ * SURVIVING pockets, in rank order and pocket order, once for EVERY point of the wanted zone within (float)M_MDP_CUBE_SIDE / 2.0 = 1.0 of the centre
+ * (dist() <= 1.0: a sphere near three points is listed three times); get_pocket_contacted_atms + set_descriptors then describe that list as one pocket
+ * (no normalisation, no score), with the side effects of ASA on the snapshot's atoms. The zone is handed in before the call; the record is read back after. */
+static const float *g_want_xyz = NULL;
+static int g_want_n = 0;
+static int *g_want_idx = NULL, g_want_nidx = 0, *g_want_atoms = NULL, g_want_natoms = 0;
+static fpk_desc g_want_desc;
+void orc_set_wanted_zone(const float *xyz, int n) { g_want_xyz = xyz; g_want_n = xyz ? n : 0; }
+int orc_get_wanted(const int **idx, int *nidx, const int **atoms, int *natoms, fpk_desc *d)
+{
+    *idx = g_want_idx; *nidx = g_want_nidx; *atoms = g_want_atoms; *natoms = g_want_natoms; *d = g_want_desc;
+    return g_want_nidx;
+}
+
 int orc_search_pocket(const fpk_structure *in, const fpk_params *p, const int *tets_in, int ntets, int rng_mode, fpk_result *out)
 {
     memset(out, 0, sizeof *out);
@@ -692,6 +708,39 @@ int orc_search_pocket(const fpk_structure *in, const fpk_params *p, const int *t
             set_descriptors(in, p, S, idx, n, out->iface_atoms, out->n_iface, d, fx, pts, rng_mode, nc);
             g_force_observable = 0;
             free(fx);
+        }
+    }
+    free(g_want_idx); free(g_want_atoms); g_want_idx = g_want_atoms = NULL; g_want_nidx = g_want_natoms = 0;
+    memset(&g_want_desc, 0, sizeof g_want_desc);
+    if (g_want_n > 0 && nk > 0) {
+        int cap = 64, n = 0;
+        int *idx = malloc(sizeof(int) * (size_t)cap);
+        for (int k = 0; k < nk; k++) {
+            const int c = keep[k];
+            for (int i = out->cl_off[c]; i < out->cl_off[c + 1]; i++) {
+                const sph_t *v = S + out->cl_sph[i];
+                for (int z = 0; z < g_want_n; z++)
+                    if ((double)f_dist(g_want_xyz[3 * z], g_want_xyz[3 * z + 1], g_want_xyz[3 * z + 2], v->x, v->y, v->z) <= (double)(float)2.0 / 2.0) {
+                        if (n == cap) { cap *= 2; idx = realloc(idx, sizeof(int) * (size_t)cap); }
+                        idx[n++] = out->cl_sph[i];
+                    }
+            }
+        }
+        g_want_idx = idx; g_want_nidx = n;
+        if (n > 0) {
+            int *atoms = malloc(sizeof(int) * 4 * (size_t)(n + 1)), na = 0;
+            for (int i = 0; i < n; i++)
+                for (int k = 0; k < 4; k++) {
+                    int a = S[idx[i]].neigh[k], seen = 0;
+                    for (int q = 0; q < na; q++) if (in->atom_id[atoms[q]] == in->atom_id[a]) { seen = 1; break; }
+                    if (!seen) atoms[na++] = a;
+                }
+            g_want_atoms = atoms; g_want_natoms = na;
+            g_want_desc.n_atoms = na;
+            g_want_desc.first_sphere = idx[0];
+            g_force_observable = 1;                   /* the record of the zone is written for every snapshot: always with volume and hull */
+            set_descriptors(in, p, S, idx, n, atoms, na, &g_want_desc, out->atom_fx, pts, rng_mode, nc + 1);
+            g_force_observable = 0;
         }
     }
     free(S);

@@ -51,6 +51,10 @@ int orc_search_pocket(const fpk_structure *in, const fpk_params *p, const int *t
 void orc_result_free(fpk_result *r);
 /* dpocket ligand queries on a finished result (called by orc_search_pocket when in->n_lig > 0): fills xspheres, iface_atoms, pk_* */
 void orc_ligand_queries(const fpk_structure *in, const fpk_params *p, fpk_result *out);
+/* mdpocket characterize mode (mdpocket.c:436-460, :695-745): hand the wanted zone in before orc_search_pocket, read the zone's record back after it.
+ * The zone pointer is borrowed; pass NULL to switch the mode off again. */
+void orc_set_wanted_zone(const float *xyz, int n);
+int orc_get_wanted(const int **idx, int *nidx, const int **atoms, int *natoms, fpk_desc *d);
 
 /* mdpocket grids (mdpbase.c). Spheres of surviving pockets in final pocket order. */
 void orc_md_grid_geometry(const fpk_result *r, float origin[3], int dims[3]);           /* init_md_grid :444-502 */

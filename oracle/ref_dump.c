@@ -20,7 +20,8 @@
  *   optional: dpocket's ligand queries (--lig NAME: the structure is loaded as dpocket.c:186-203 does, and the
  *             reference's own neighbor.c / atom.c functions are called on the final pockets)            (dpocket.c:228-290)
  *
- * Usage:  ref_dump <out.dump> [--md] [--seed S] [--lig NAME] <fpocket options, e.g. -f X.pdb -m 3.0>
+ * Usage:  ref_dump <out.dump> [--md] [--seed S] [--lig NAME] [--want ZONE.pdb] <fpocket options, e.g. -f X.pdb -m 3.0>
+ *   --want  one snapshot of mdpocket's characterize mode (mdpocket.c:436-460) on the final pockets: spheres near the points of ZONE.pdb
  *   --md    mimic mdpocket's call (mdpocket.c:833-846): search_pocket(pdb,params,pdb),
  *           ASA/volume/hull off (mdpocket.c:89), then the three grids of frame 1.
  *
@@ -37,6 +38,7 @@
 #include "fpout.h"
 #include "mdpbase.h"
 #include "mdparams.h"
+#include "mdpocket.h"
 #include "read_mmcif.h"
 #include "neighbor.h"
 #include "dparams.h"
@@ -304,9 +306,10 @@ int main(int argc, char **argv)
     const char *outp = argv[1];
     int md = 0, md_score = 0, a = 2;
     long seed = -1;
-    char *ligname = NULL;
+    char *ligname = NULL, *wantname = NULL;
     for (;;) {
         if (a + 1 < argc && !strcmp(argv[a], "--lig")) { ligname = argv[a + 1]; a += 2; continue; }
+        if (a + 1 < argc && !strcmp(argv[a], "--want")) { wantname = argv[a + 1]; a += 2; continue; }
         if (a < argc && !strcmp(argv[a], "--md")) { md = 1; a++; }
         else if (a < argc && !strcmp(argv[a], "--score")) { md_score = 1; a++; }
         else if (a + 1 < argc && !strcmp(argv[a], "--seed")) { seed = atol(argv[a + 1]); a += 2; }
@@ -320,7 +323,7 @@ int main(int argc, char **argv)
     s_fparams *params = get_fpocket_args(nargs, args);
     if (!params) { fprintf(stderr, "bad fpocket args\n"); return 2; }
     params->fpocket_running = md ? 0 : 1;
-    if (md) params->flag_do_asa_and_volume_calculations = 0;   /* mdpocket.c:89 */
+    if (md && !wantname) params->flag_do_asa_and_volume_calculations = 0;   /* mdpocket.c:89: mdpocket_detect only; characterize keeps the default */
     char *pdbname = params->pdb_path;
     int cif = strstr(pdbname, ".cif") != NULL;
     s_pdb *pdb, *pdb_w_lig;
@@ -420,6 +423,45 @@ int main(int argc, char **argv)
         rec1("grid.origin", 'f', 4, org);
         dump_grid("grid.dens", dens);
         dump_grid("grid.freq", freq);
+    }
+    if (wantname && pockets->n_pockets > 0) {
+        /* one snapshot of mdpocket_characterize (mdpocket.c:436-460): the spheres of the surviving pockets within M_MDP_CUBE_SIDE / 2 of a point of
+         * the wanted zone, once per point that reaches them (extract_wanted_vertices, mdpocket.c:695-745), described as ONE pocket by set_descriptors */
+        s_pdb *wp = rpdb_open(wantname, NULL, M_DONT_KEEP_LIG, 0, params);
+        if (!wp) { fprintf(stderr, "cannot read %s\n", wantname); return 5; }
+        rpdb_read(wp, NULL, M_DONT_KEEP_LIG, 0, params);
+        float *wxyz = malloc(sizeof(float) * 3 * (wp->natoms + 1));
+        for (int j = 0; j < wp->natoms; j++) { wxyz[3 * j] = wp->latoms_p[j]->x; wxyz[3 * j + 1] = wp->latoms_p[j]->y; wxyz[3 * j + 2] = wp->latoms_p[j]->z; }
+        int d2w[2] = {wp->natoms, 3};
+        rec("want.points", 'f', 2, d2w, wxyz);
+        s_pocket *cp = extract_wanted_vertices(pockets, wp);
+        int nv = (int)cp->v_lst->n_vertices, j = 0, natms = 0;
+        s_vvertice **tab = malloc(sizeof(s_vvertice *) * (nv + 1));
+        int *ids = malloc(sizeof(int) * (nv + 1));
+        for (node_vertice *c = cp->v_lst->first; c; c = c->next) { tab[j] = c->vertice; ids[j] = (int)(c->vertice - lvert->vertices); j++; }
+        rec1("want.sph", 'i', nv, ids);
+        if (nv > 0) {
+            s_atm **patoms = get_pocket_contacted_atms(cp, &natms);
+            int *pa = malloc(sizeof(int) * (natms + 1));
+            for (j = 0; j < natms; j++) pa[j] = (int)(patoms[j] - pdb->latoms);
+            rec1("want.atoms", 'i', natms, pa);
+            set_descriptors(patoms, natms, tab, nv, cp->pdesc, params->nb_mcv_iter, pdb, params->flag_do_asa_and_volume_calculations);
+            s_desc *d = cp->pdesc;
+            float F[NDESC_F] = {0};
+            F[1] = d->drug_score; F[2] = d->hydrophobicity_score; F[3] = d->volume_score;
+            F[4] = d->volume; F[5] = d->convex_hull_volume; F[6] = d->prop_polar_atm; F[7] = d->mean_asph_ray;
+            F[8] = d->masph_sacc; F[9] = d->apolar_asphere_prop; F[10] = d->mean_loc_hyd_dens; F[11] = d->as_density;
+            F[12] = d->as_max_dst; F[13] = d->flex; F[14] = d->nas_norm; F[15] = d->polarity_score_norm;
+            F[16] = d->mean_loc_hyd_dens_norm; F[17] = d->prop_asapol_norm; F[18] = d->as_density_norm; F[19] = d->as_max_dst_norm;
+            F[20] = d->surf_vdw14; F[21] = d->surf_vdw22; F[22] = d->surf_pol_vdw14; F[23] = d->surf_pol_vdw22;
+            F[24] = d->surf_apol_vdw14; F[25] = d->surf_apol_vdw22; F[26] = d->as_max_r;
+            int I[NDESC_I] = {0};
+            I[0] = d->nb_asph; I[1] = d->polarity_score; I[2] = d->charge_score; I[3] = d->n_abpa;
+            for (j = 0; j < 20; j++) I[11 + j] = d->aa_compo[j];
+            rec1("want.desc_f", 'f', NDESC_F, F);
+            rec1("want.desc_i", 'i', NDESC_I, I);
+            dump_atom_effects("want.atom_fx", pdb);
+        }
     }
     if (ligname && pdb_w_lig->natm_lig > 0 && pockets->n_pockets > 0) {
         /* dpocket.c:204-290 on the final pockets, with the reference's own functions */

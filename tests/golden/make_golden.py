@@ -38,6 +38,8 @@ CASES = [
     ("1UYD_dpocket", "1UYD.pdb", ["--seed", "19", "--lig", "PU8"], []),            # dpocket.c:186-290 with the known ligand
     ("md_2yex", "mdpocket/2yex.pdb", ["--md"], []),                           # mdpocket.c:833 call shape
     ("md_3ot3_S", "mdpocket/3ot3.pdb", ["--md", "--score"], []),              # -S drug-score increments
+    # one snapshot of mdpocket's characterize mode (mdpocket.c:436-460): zone = the first 70 grid points of the reference's own mdpout_dens_iso_8.pdb
+    ("mdchar_3pa3", "mdpocket/3pa3.pdb", ["--md", "--seed", "31", "--want", "@zone70"], []),
 ]
 
 
@@ -55,6 +57,11 @@ def main():
         shutil.copy(src, loc)
         os.chmod(loc, 0o644)
         out = os.path.join(tmp, name + ".dump")
+        if "@zone70" in dflags:
+            zone = os.path.join(tmp, "zone70.pdb")
+            with open(os.path.join(REF, "data", "sample", "mdpocket", "mdpout_dens_iso_8.pdb")) as f:
+                open(zone, "w").writelines(f.readlines()[:70])
+            dflags = [zone if x == "@zone70" else x for x in dflags]
         subprocess.run([DUMP, out] + dflags + ["-f", loc] + opts, check=True, stdout=subprocess.DEVNULL,
                        stderr=subprocess.DEVNULL, cwd=tmp)
         d = read_dump(out)

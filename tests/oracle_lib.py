@@ -81,6 +81,30 @@ def canonicalize(tets):
     return t
 
 
+def characterize(st, params, zone, tets=None, rng_mode=RNG_PHILOX):
+    """One snapshot of mdpocket's characterize mode through the oracle (oracle.c orc_set_wanted_zone): the usual result plus the zone's sphere
+    list (with repeats), its contacted atoms and its descriptor record."""
+    L = lib()
+    zone = np.ascontiguousarray(zone, dtype=np.float32)
+    L.orc_set_wanted_zone.argtypes = [C.POINTER(C.c_float), C.c_int]
+    L.orc_set_wanted_zone.restype = None
+    L.orc_get_wanted.argtypes = [C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int), C.POINTER(capi.FpkDesc)]
+    L.orc_get_wanted.restype = C.c_int
+    L.orc_set_wanted_zone(zone.ctypes.data_as(C.POINTER(C.c_float)), len(zone))
+    try:
+        r = search_pocket(st, params, tets=tets, rng_mode=rng_mode)
+        idx, atoms = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
+        ni, na = C.c_int(), C.c_int()
+        d = capi.FpkDesc()
+        L.orc_get_wanted(C.byref(idx), C.byref(ni), C.byref(atoms), C.byref(na), C.byref(d))
+        r["want_sph"] = np.array([idx[i] for i in range(ni.value)], dtype=np.int32)
+        r["want_atoms"] = np.array([atoms[i] for i in range(na.value)], dtype=np.int32)
+        r["want_desc"] = d
+    finally:
+        L.orc_set_wanted_zone(None, 0)
+    return r
+
+
 def search_pocket(st, params, tets=None, rng_mode=RNG_PHILOX):
     """Run the oracle pipeline. tets=None -> the oracle's own exact Delaunay (canonical order)."""
     L = lib()

@@ -90,3 +90,28 @@ def test_oracle_ligand_queries_equal_the_reference_functions():
     assert len({int(ids[s]) for s in ours}) == len(ref) == len({int(ids[s]) for s in ref})
     got = np.stack([r["pk_ovlp"], r["pk_dst"], r["pk_c4"], r["pk_c5"]], 1)
     assert np.array_equal(got, d["lig.crit"])
+
+
+@pytest.mark.parametrize("case", G.MDCHAR_CASES)
+def test_oracle_characterize_snapshot_equals_the_reference(case):
+    """mdpocket characterize mode, one snapshot (mdpocket.c:436-460): fed the reference's tets and libc rand() stream, the oracle's list of zone
+    spheres (surviving pockets in rank order, one entry per zone point within 1.0 of the centre: repeats included, mdpocket.c:695-745), the atoms they
+    contact and the record set_descriptors makes of them - Monte-Carlo volume, hull volume and the ASA side effects on the atoms included - must be
+    the reference's bit for bit. Oracle first (SURVEY par. 8 row f3): the GPU path for this mode is the next round's work."""
+    d = G.load(case)
+    st, p = G.inputs(d)
+    r = O.characterize(st, p, d["want.points"], tets=d["qh.tets_seen"], rng_mode=O.RNG_LIBC)
+    assert r["n_spheres"] == len(d["sph0.f"]) and r["n_pockets"] == len(d["fin.off"]) - 1
+    assert len(d["want.sph"]) > 50 and len(set(d["want.sph"].tolist())) < len(d["want.sph"])      # the fixture does contain repeats
+    assert np.array_equal(r["want_sph"], d["want.sph"])
+    assert np.array_equal(r["want_atoms"], d["want.atoms"])
+    D, F, I = r["want_desc"], d["want.desc_f"], d["want.desc_i"]
+    for k, n in enumerate(G.DESC_F):
+        if n in ("score", "drug_score") or n.endswith("_norm"):
+            continue                                  # the zone's record is never normalised or scored (mdpocket.c:453)
+        assert np.float32(getattr(D, n)) == F[k] or (np.isnan(getattr(D, n)) and np.isnan(F[k])), (n, getattr(D, n), F[k])
+    for k, n in enumerate(("nb_asph", "polarity_score", "charge_score", "n_abpa")):
+        assert getattr(D, n) == I[k], n
+    assert list(D.aa_compo) == I[11:31].tolist()
+    assert D.volume > 0 and D.convex_hull_volume > 0 and D.nb_asph == len(d["want.sph"])
+    assert G.eq_nan(r["atom_fx"], d["want.atom_fx"])
