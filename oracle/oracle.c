@@ -166,6 +166,12 @@ static int filter_tets(const fpk_structure *in, const fpk_params *p, const int *
  * connected components of the graph  sqrt(dx^2+dy^2+dz^2) (f64 of f32 centres) <= (double)clust_max_dist,
  * numbered by lowest sphere index (SURVEY Appendix B check). */
 static int uf_find(int *par, int i) { while (par[i] != i) { par[i] = par[par[i]]; i = par[i]; } return i; }
+/* -e (fparams.c: distance_measure): 'e' euclid (the default, clusterlib.c:933-1018) or 'b' city block (clusterlib.c:1022-1083: the MEAN of the three absolute
+ * differences, weights 1). Single linkage cut at clust_max_dist is the connected components of "distance <= cut" under either. fpk_params has no field
+ * for it yet (the library refuses anything but 'e'): the oracle takes it through this switch (oracle first, SURVEY par. 8 row f4). */
+static int g_distance_measure = 'e';
+void orc_set_distance_measure(int c) { g_distance_measure = c; }
+
 static int cluster_spheres(sph_t *S, int ns, float clust_max_dist, int skip)
 {
     if (skip) { for (int i = 0; i < ns; i++) S[i].cluster = 0; return ns ? 1 : 0; }
@@ -176,10 +182,18 @@ static int cluster_spheres(sph_t *S, int ns, float clust_max_dist, int skip)
         double xi = (double)S[i].x, yi = (double)S[i].y, zi = (double)S[i].z;
         for (int j = i + 1; j < ns; j++) {
             double result = 0.;
-            double term = xi - (double)S[j].x; result += term * term;
-            term = yi - (double)S[j].y; result += term * term;
-            term = zi - (double)S[j].z; result += term * term;
-            result = sqrt(result);
+            if (g_distance_measure == 'b') {
+                double tweight = 0;
+                double term = xi - (double)S[j].x; result = result + 1.0 * fabs(term); tweight += 1.0;
+                term = yi - (double)S[j].y; result = result + 1.0 * fabs(term); tweight += 1.0;
+                term = zi - (double)S[j].z; result = result + 1.0 * fabs(term); tweight += 1.0;
+                result /= tweight;
+            } else {
+                double term = xi - (double)S[j].x; result += term * term;
+                term = yi - (double)S[j].y; result += term * term;
+                term = zi - (double)S[j].z; result += term * term;
+                result = sqrt(result);
+            }
             if (!(result > cut)) {
                 int a = uf_find(par, i), b = uf_find(par, j);
                 if (a != b) { if (a < b) par[b] = a; else par[a] = b; }

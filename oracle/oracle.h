@@ -54,6 +54,8 @@ void orc_ligand_queries(const fpk_structure *in, const fpk_params *p, fpk_result
 /* mdpocket characterize mode (mdpocket.c:436-460, :695-745): hand the wanted zone in before orc_search_pocket, read the zone's record back after it.
  * The zone pointer is borrowed; pass NULL to switch the mode off again. */
 void orc_set_wanted_zone(const float *xyz, int n);
+/* -e: 'e' (default) or 'b' city block for the clustering distance; a process-wide switch, reset it to 'e' after use */
+void orc_set_distance_measure(int c);
 int orc_get_wanted(const int **idx, int *nidx, const int **atoms, int *natoms, fpk_desc *d);
 
 /* mdpocket grids (mdpbase.c). Spheres of surviving pockets in final pocket order. */

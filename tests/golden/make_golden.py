@@ -39,6 +39,7 @@ CASES = [
     ("md_2yex", "mdpocket/2yex.pdb", ["--md"], []),                           # mdpocket.c:833 call shape
     ("md_3ot3_S", "mdpocket/3ot3.pdb", ["--md", "--score"], []),              # -S drug-score increments
     # one snapshot of mdpocket's characterize mode (mdpocket.c:436-460): zone = the first 70 grid points of the reference's own mdpout_dens_iso_8.pdb
+    ("alt_1UYD_eb", "1UYD.pdb", ["--seed", "32"], ["-e", "b"]),                  # test_fpocket.py:91 uses -e b (city-block clustering distance)
     ("mdchar_3pa3", "mdpocket/3pa3.pdb", ["--md", "--seed", "31", "--want", "@zone70"], []),
 ]
 
