@@ -766,6 +766,8 @@ int orc_search_pocket(const fpk_structure *in, const fpk_params *p, const int *t
  * :598 count_atm_prop_vert_neigh, atom.c:264 atm_corsp, dpocket.c:246-270. The reference finds the pairs by sweeping an x-sorted
  * merged array outwards from every ligand atom until the x-gap exceeds the criterion; what it returns are the SETS / counts of the
  * strict relation dist() < d, restated here directly (pinned against the reference's own functions by tests/golden, the _dpocket fixture). */
+static int g_interface_method = 1;       /* dparams.h:41-44; fpk_params has no field for it yet: oracle first, like the distance measure */
+void orc_set_interface_method(int m) { g_interface_method = m; }
 void orc_ligand_queries(const fpk_structure *in, const fpk_params *p, fpk_result *out)
 {
     const int nl = in->n_lig, ns = out->n_spheres, na = in->natoms, np = out->n_pockets;
@@ -784,6 +786,27 @@ void orc_ligand_queries(const fpk_structure *in, const fpk_params *p, fpk_result
                 }
             }
         }
+    }
+    if (g_interface_method == 2) {
+        /* dparams.h:44 M_INTERFACE_METHOD2 (dpocket.c:331-336, neighbor.c:67 get_mol_atm_neigh): the atoms of the complex with dist() < dcrit to a ligand
+         * atom, the ligand's own atoms excluded. pdb is pdb_w_lig without the ligand, in the same order: index in pdb = index in pdb_w_lig minus the
+         * ligand atoms before it. (The reference excludes and de-duplicates by atom ID, neighbor.c:118: with repeated ids in a file its result is an
+         * order-dependent subset; this is the relation itself, as for the spheres above.) */
+        const int nw = in->natoms_w ? in->natoms_w : in->natoms;
+        unsigned char *isl = calloc((size_t)nw + 1, 1);
+        for (int l = 0; l < nl; l++) isl[in->lig_atoms[l]] = 1;
+        memset(af, 0, (size_t)na + 1);
+        int pi = 0;
+        for (int a = 0; a < nw; a++) {
+            if (isl[a]) continue;
+            if (pi < na)
+                for (int l = 0; l < nl; l++) {
+                    int b = in->lig_atoms[l];
+                    if (f_dist(wx[a], wy[a], wz[a], wx[b], wy[b], wz[b]) < dcrit) { af[pi] = 1; break; }
+                }
+            pi++;
+        }
+        free(isl);
     }
     out->xspheres = malloc(sizeof(int) * ((size_t)ns + 1));
     out->iface_atoms = malloc(sizeof(int) * ((size_t)na + 1));

@@ -506,6 +506,23 @@ int main(int argc, char **argv)
         }
         int d2[2] = {q, 4};
         rec("lig.crit", 'f', 2, d2, crit);
+        /* dpocket's other interface definition (dparams.h:44 M_INTERFACE_METHOD2, dpocket.c:331-336): the atoms of the complex within M_LIG_NEIG_DIST of a
+         * ligand atom, ligand excluded; indices into pdb_w_lig. Last, because get_sorted_list re-sorts the atoms it is given. */
+        {
+            int nai2 = 0;
+            s_atm **if2 = get_mol_atm_neigh(lig, nal, pdb_w_lig->latoms_p, pdb_w_lig->natoms, M_LIG_NEIG_DIST, &nai2);
+            int *i2 = malloc(sizeof(int) * (nai2 + 1));
+            for (j = 0; j < nai2; j++) i2[j] = (int)(if2[j] - pdb_w_lig->latoms);
+            rec1("lig.iface2", 'i', nai2, i2);
+            float *ov2 = malloc(sizeof(float) * (pockets->n_pockets + 1));
+            q = 0;
+            for (cur = pockets->first; cur; cur = cur->next) {
+                int nbpa = 0;
+                s_atm **patoms = get_vert_contacted_atms(cur->pocket->v_lst, &nbpa);
+                ov2[q++] = atm_corsp(if2, nai2, patoms, nbpa);
+            }
+            rec1("lig.ovlp2", 'f', q, ov2);
+        }
     }
     rec_i("status", 0);
     fclose(OUT);

@@ -140,3 +140,22 @@ def test_oracle_city_block_clustering_equals_the_reference(case):
     assert [int(r["cl_sph"][r["cl_off"][c]]) for c in r["rank_to_cluster"]] == ref_first
     e = O.search_pocket(st, p, tets=d["qh.tets_seen"], rng_mode=O.RNG_LIBC)
     assert e["n_clusters"] != r["n_clusters"]
+
+
+def test_oracle_interface_method_2_equals_the_reference_function():
+    """dpocket's second interface definition (dparams.h:44, dpocket.c:331-336): the atoms within 4.0 of a ligand atom. The oracle's set equals what
+    the reference's get_mol_atm_neigh returned on the same complex (neighbor.c:67; indices of pdb_w_lig mapped to pdb by skipping the ligand), and the
+    per-pocket overlap atm_corsp computes with it is the reference's bit for bit. Oracle first: the library has method 1 only."""
+    d = G.load("1UYD_dpocket")
+    st, p = G.inputs(d)
+    O.lib().orc_set_interface_method(2)
+    try:
+        r = O.search_pocket(st, p, tets=d["qh.tets_seen"], rng_mode=O.RNG_LIBC)
+    finally:
+        O.lib().orc_set_interface_method(1)
+    lig = np.sort(d["lig.atoms"])
+    ref = np.sort(np.array([w - np.searchsorted(lig, w) for w in d["lig.iface2"]], dtype=np.int32))
+    assert len(ref) > 20 and not set(d["lig.iface2"].tolist()) & set(lig.tolist())
+    assert np.array_equal(r["iface_atoms"], ref)
+    assert np.array_equal(r["pk_ovlp"], d["lig.ovlp2"])
+    assert not np.array_equal(d["lig.ovlp2"], d["lig.crit"][:, 0])          # the two definitions do differ on this complex
