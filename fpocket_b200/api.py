@@ -28,12 +28,14 @@ def _check(rc, lib, what):
 
 
 def init(device=None):
+    """fpk_init: `device` = None (the current device, or $FPK_DEVICES), one device index, or a list of devices the library shards over."""
     lib = _lib()
     if device is None:
         rc = lib.fpk_init(None, 0)
     else:
-        d = (C.c_int32 * 1)(int(device))
-        rc = lib.fpk_init(d, 1)
+        devs = [int(device)] if np.isscalar(device) else [int(v) for v in device]
+        d = (C.c_int32 * len(devs))(*devs)
+        rc = lib.fpk_init(d, len(devs))
     if rc != capi.FPK_OK:
         raise FpkError("fpk_init failed (%d): %s" % (rc, (lib.fpk_last_error() or b"").decode()))
 

@@ -197,6 +197,7 @@ def declare(lib):
     vp = C.c_void_p
     sig = {
         "fpk_init": (C.c_int, [_ip, C.c_int]),
+        "fpk_device_count": (C.c_int, []),
         "fpk_shutdown": (None, []),
         "fpk_last_error": (C.c_char_p, []),
         "fpk_version": (C.c_char_p, []),

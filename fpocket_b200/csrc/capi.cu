@@ -22,11 +22,23 @@
 using namespace fpk;
 
 // ------------------------------------------------------------------------------------------------------------------
+// Last error: every thread keeps its own message; the most recent one of ANY thread is also kept process-wide, because the library
+// itself works on helper threads (fpk_detect_batch, fpk_md_push_frames) and callers report from another thread than the one that failed.
 static thread_local std::string g_err;
+static std::mutex g_err_mu;
+static std::string g_err_last;
+static thread_local std::string g_err_ret;
 static std::atomic<long long> g_tot_h2d(0), g_tot_d2h(0);      // bytes moved by fpk_detect_batch since load (fpk_batch_counter(NULL, 6 / 7))
-static int g_dev = -1, g_sms = 0;
+static std::vector<int> g_devs;                                // the devices fpk_init was given (fpk_detect_batch and fpk_md_* shard over them)
+static int g_sms = 0;
 static bool g_init = false;
 
+static void set_err(const std::string &m)
+{
+    g_err = m;
+    std::lock_guard<std::mutex> g(g_err_mu);
+    g_err_last = m;
+}
 static int fail(int code, const char *fmt, ...)
 {
     char buf[512];
@@ -34,7 +46,7 @@ static int fail(int code, const char *fmt, ...)
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
-    g_err = buf;
+    set_err(buf);
     return code;
 }
 #define CK(call)                                                                                           \
@@ -43,7 +55,13 @@ static int fail(int code, const char *fmt, ...)
         if (e_ != cudaSuccess) return fail(FPK_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-extern "C" const char *fpk_last_error(void) { return g_err.c_str(); }
+extern "C" const char *fpk_last_error(void)
+{
+    if (!g_err.empty()) return g_err.c_str();
+    std::lock_guard<std::mutex> g(g_err_mu);
+    g_err_ret = g_err_last;
+    return g_err_ret.c_str();
+}
 extern "C" const char *fpk_version(void) { return "fpocket_b200 0.1 (sm_100a)"; }
 
 extern "C" void fpk_default_params(fpk_params *p)
@@ -78,20 +96,29 @@ extern "C" int fpk_init(const int *devices, int ndev)
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
         return fail(FPK_ERR_NO_DEVICE, "no CUDA device (%s); libfpocket_cuda has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
-    int dev = 0;
-    if (devices && ndev > 0) dev = devices[0];
-    else cudaGetDevice(&dev);
-    cudaDeviceProp pr;
-    CK(cudaGetDeviceProperties(&pr, dev));
-    if (pr.major < 10) return fail(FPK_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev, pr.major, pr.minor);
-    CK(cudaSetDevice(dev));
-    g_dev = dev; g_sms = pr.multiProcessorCount;
+    std::vector<int> devs;
+    if (devices && ndev > 0) devs.assign(devices, devices + ndev);
+    else if (const char *ev = getenv("FPK_DEVICES")) {          // "all" or a comma-separated list: lets any program on the library use several GPUs
+        if (!strcmp(ev, "all")) for (int d = 0; d < count; d++) devs.push_back(d);
+        else for (const char *q = ev; *q;) { devs.push_back(atoi(q)); while (*q && *q != ',') q++; if (*q == ',') q++; }
+    }
+    if (devs.empty()) { int dev = 0; cudaGetDevice(&dev); devs.push_back(dev); }
+    for (size_t i = 0; i < devs.size(); i++) {
+        if (devs[i] < 0 || devs[i] >= count) return fail(FPK_ERR_BAD_ARG, "fpk_init: device %d does not exist (%d devices)", devs[i], count);
+        for (size_t j = 0; j < i; j++) if (devs[j] == devs[i]) return fail(FPK_ERR_BAD_ARG, "fpk_init: device %d listed twice", devs[i]);
+    }
     float pts[300];
     spiral_points(pts);
-    CK(cudaMemcpyToSymbol(c_spiral, pts, sizeof pts));
-    // dynamic shared memory of the two Delaunay kernels: opted in ONCE to the device maximum (a per-batch setting would race between
-    // the host threads of fpk_detect_batch); each launch then asks for what its batch needs
-    {
+    int sms = 0;
+    for (int dev : devs) {
+        cudaDeviceProp pr;
+        CK(cudaGetDeviceProperties(&pr, dev));
+        if (pr.major < 10) return fail(FPK_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev, pr.major, pr.minor);
+        CK(cudaSetDevice(dev));
+        sms = sms ? std::min(sms, pr.multiProcessorCount) : pr.multiProcessorCount;
+        CK(cudaMemcpyToSymbol(c_spiral, pts, sizeof pts));
+        // dynamic shared memory of the Delaunay kernels: opted in ONCE per device to the device maximum (a per-batch setting would race
+        // between the host threads of fpk_detect_batch); each launch then asks for what its batch needs
         cudaFuncAttributes fa;
         CK(cudaFuncGetAttributes(&fa, k_delaunay_filter));
         CK(cudaFuncSetAttribute(k_delaunay_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pr.sharedMemPerBlockOptin - fa.sharedSizeBytes)));
@@ -99,16 +126,19 @@ extern "C" int fpk_init(const int *devices, int ndev)
         CK(cudaFuncSetAttribute(k_hull_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pr.sharedMemPerBlockOptin - fa.sharedSizeBytes)));
         CK(cudaFuncSetAttribute(k_hull_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HW_WARPS * sizeof(HullWarp))));
     }
+    CK(cudaSetDevice(devs[0]));
+    g_devs = devs; g_sms = sms;
     g_init = true;
     return FPK_OK;
 }
+extern "C" int fpk_device_count(void) { return g_init ? (int)g_devs.size() : 0; }
 static void pool_clear();
 static void pin_clear();
 extern "C" void fpk_shutdown(void) { pool_clear(); pin_clear(); g_init = false; }
 
 static int ensure_init()
 {
-    if (g_init) { cudaSetDevice(g_dev); return FPK_OK; }
+    if (g_init) { cudaSetDevice(g_devs[0]); return FPK_OK; }
     return fpk_init(nullptr, 0);
 }
 
@@ -191,7 +221,7 @@ static char *pin_get(size_t need, size_t *cap)
     }
     char *p = nullptr;
     size_t want = need + need / 4 + 4096;
-    if (cudaHostAlloc((void **)&p, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaHostAlloc((void **)&p, want, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     *cap = want;
     return p;
 }
@@ -227,7 +257,10 @@ struct HostResults {            // owner of the host arrays of one fetch: one pi
 
 struct fpk_batch {
     int n = 0;
+    int dev = -1;                      // the device this context's arenas live on
     fpk_params prm;
+    std::vector<fpk_structure> sane;   // the caller's structures, unusable ones replaced by an empty structure
+    std::vector<int> bad;              // FPK_ERR_BAD_ARG for those
     std::vector<StructDev> S;
     std::vector<int> natoms;
     long long tot_atoms = 0, tot_w = 0, tot_sites = 0, tot_xlig = 0, tot_sphcap = 0, tot_tetcap = 0, tot_lig = 0;
@@ -264,34 +297,68 @@ struct fpk_batch {
     float ms[8] = {0};
     long long launches = 0, h2d = 0, d2h = 0;
     bool events = false;
-    ~fpk_batch() { A1.release(); A2.release(); if (hin) cudaFreeHost(hin); if (pin_counts) cudaFreeHost(pin_counts); if (events) for (auto &e : ev) cudaEventDestroy(e); }
+    ~fpk_batch()
+    {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (dev >= 0 && dev != cur) cudaSetDevice(dev);
+        A1.release(); A2.release();
+        if (hin) cudaFreeHost(hin);
+        if (pin_counts) cudaFreeHost(pin_counts);
+        if (events) for (auto &e : ev) cudaEventDestroy(e);
+        if (dev >= 0 && dev != cur && cur >= 0) cudaSetDevice(cur);
+    }
 };
 
 static inline size_t sph_cap_for(const fpk_params &p, int nsites, double factor_override)
 {
     // typical proteins keep ~0.6 spheres per heavy atom at default radii; everything (7 tets/atom) otherwise
     double f = factor_override > 0 ? factor_override : ((p.asph_max_size <= 6.3f && p.asph_min_size >= 3.3f) ? 1.6 : 7.2);
-    return (size_t)(f * nsites) + 64;
+    size_t slack = 64;
+    if (factor_override <= 0)
+        if (const char *e = getenv("FPK_SPH_CAP_FACTOR")) { f = atof(e); slack = 0; }      // test knob: forces the FPK_ERR_CAPACITY re-run (tests/test_gpu_parity.py)
+    return (size_t)(f * nsites) + slack;
+}
+
+// what makes ONE structure unusable; the batch goes on without it (the reference's -F loop moves on to the next file, fpmain.c:61-76)
+static const char *structure_defect(const fpk_structure &s)
+{
+    if (s.natoms < 0 || s.natoms_w < 0 || s.n_xlig < 0 || s.n_lig < 0) return "negative count";
+    if (s.natoms > 0 && (!s.x || !s.y || !s.z || !s.radius || !s.electroneg || !s.bfactor || !s.atom_id || !s.res_id || !s.aa_idx || !s.flags)) return "NULL atom array";
+    if (s.natoms_w > 0 && (!s.wx || !s.wy || !s.wz || !s.wradius || !s.welectroneg || !s.wflags)) return "NULL pdb_w_lig array";
+    if (s.natoms_w == 0 && !s.same_pdb) return "natoms_w == 0 requires same_pdb = 1";
+    if (s.n_xlig > 0 && !s.xlig) return "NULL explicit-ligand array";
+    if (s.n_lig > 0 && (!s.lig_atoms || !s.lig_mol)) return "NULL ligand array";
+    for (int i = 0; i < s.n_lig; i++)
+        if (s.lig_atoms[i] < 0 || s.lig_atoms[i] >= (s.natoms_w ? s.natoms_w : s.natoms)) return "ligand atom index out of range";
+    // contacted atoms are made unique by id (pocket.c:1298) but ASA works on pointers (asa.c:51): both coincide iff ids are unique
+    bool inc = true;
+    for (int i = 1; i < s.natoms && inc; i++) inc = s.atom_id[i] > s.atom_id[i - 1];
+    if (!inc) {
+        std::vector<int> ids(s.atom_id, s.atom_id + s.natoms);
+        std::sort(ids.begin(), ids.end());
+        if (std::adjacent_find(ids.begin(), ids.end()) != ids.end()) return "duplicate atom ids are not supported";
+    }
+    return nullptr;
 }
 
 static int batch_pack(fpk_batch *b, const fpk_structure *in, int n, const fpk_params *p, double cap_factor)
 {
     b->n = n; b->prm = *p;
     b->S.resize(n); b->natoms.resize(n); b->lig_n.assign(n, 0);
+    b->sane.assign(in, in + n); b->bad.assign(n, 0);
     b->max_sites = b->max_w = b->max_sphcap = 0; b->h2d = b->d2h = 0;
     long long ao = 0, wo = 0, so = 0, xo = 0, sc = 0, tc = 0, lo = 0;
     b->has_names = false;
     for (int k = 0; k < n; k++) {
-        const fpk_structure &s = in[k];
-        if (s.natoms < 0 || (s.natoms > 0 && (!s.x || !s.y || !s.z || !s.radius || !s.electroneg || !s.bfactor || !s.atom_id || !s.res_id || !s.aa_idx || !s.flags)))
-            return fail(FPK_ERR_BAD_ARG, "structure %d: NULL atom array", k);
-        if (s.natoms_w > 0 && (!s.wx || !s.wy || !s.wz || !s.wradius || !s.welectroneg || !s.wflags))
-            return fail(FPK_ERR_BAD_ARG, "structure %d: NULL pdb_w_lig array", k);
-        if (s.natoms_w == 0 && !s.same_pdb)
-            return fail(FPK_ERR_BAD_ARG, "structure %d: natoms_w == 0 requires same_pdb = 1", k);
-        if (s.n_lig < 0 || (s.n_lig > 0 && (!s.lig_atoms || !s.lig_mol))) return fail(FPK_ERR_BAD_ARG, "structure %d: NULL ligand array", k);
-        for (int i = 0; i < s.n_lig; i++)
-            if (s.lig_atoms[i] < 0 || s.lig_atoms[i] >= (s.natoms_w ? s.natoms_w : s.natoms)) return fail(FPK_ERR_BAD_ARG, "structure %d: ligand atom index out of range", k);
+        if (const char *why = structure_defect(in[k])) {     // reported in out[k].status; the rest of the batch is processed
+            fail(FPK_ERR_BAD_ARG, "structure %d: %s", k, why);
+            b->bad[k] = FPK_ERR_BAD_ARG;
+            fpk_structure &e = b->sane[k];
+            memset(&e, 0, sizeof e);
+            e.same_pdb = 1;
+        }
+        const fpk_structure &s = b->sane[k];
         lo += s.n_lig;
         b->lig_n[k] = s.n_lig;
         if (s.n_lig > 0 && s.atom_name_key) b->has_names = true;
@@ -299,15 +366,6 @@ static int batch_pack(fpk_batch *b, const fpk_structure *in, int n, const fpk_pa
         memset(&d, 0, sizeof d);
         int ns = 0;
         for (int i = 0; i < s.natoms; i++) ns += !(s.flags[i] & FPK_ATOM_H);
-        // contacted atoms are made unique by id (pocket.c:1298) but ASA works on pointers (asa.c:51): both coincide iff ids are unique
-        bool inc = true;
-        for (int i = 1; i < s.natoms && inc; i++) inc = s.atom_id[i] > s.atom_id[i - 1];
-        if (!inc) {
-            std::vector<int> ids(s.atom_id, s.atom_id + s.natoms);
-            std::sort(ids.begin(), ids.end());
-            if (std::adjacent_find(ids.begin(), ids.end()) != ids.end())
-                return fail(FPK_ERR_BAD_ARG, "structure %d: duplicate atom ids are not supported", k);
-        }
         d.atom_off = (int)ao; d.natoms = s.natoms; d.prop_off = (int)ao;
         d.w_off = (int)wo; d.natoms_w = s.natoms_w;
         d.site_off = (int)so; d.nsites = ns;
@@ -353,6 +411,8 @@ static size_t del_scratch_layout(Arena &a, DelScratch &x, int nmax, int scap, in
 static int batch_upload(fpk_batch *b, const fpk_structure *in)
 {
     const int n = b->n;
+    if (in) in = b->sane.data();          // unusable structures were replaced by empty ones in batch_pack
+    cudaGetDevice(&b->dev);
     int occ1 = 2, occ3 = 4;
     // K1 shared-memory plan. The kernel is bound by the latency of dependent tet / claim loads, so what counts is the number of
     // resident warps: three blocks of eight warps per SM at 80 registers (launch bounds) beat two blocks at 128 by 11 % even though
@@ -432,7 +492,7 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
             if (b->hin) cudaFreeHost(b->hin);
             b->hin = nullptr; b->hin_cap = 0;
             const size_t want = b->in_bytes + b->in_bytes / 8 + 4096;
-            cudaError_t e = cudaHostAlloc((void **)&b->hin, want, cudaHostAllocDefault);
+            cudaError_t e = cudaHostAlloc((void **)&b->hin, want, cudaHostAllocPortable);
             if (e != cudaSuccess) return fail(FPK_ERR_CUDA, "cudaHostAlloc(%zu bytes): %s", want, cudaGetErrorString(e));
             b->hin_cap = want;
         }
@@ -636,7 +696,7 @@ static int fetch_counts(fpk_batch *b)
     if (cnt > b->pin_counts_cap) {
         if (b->pin_counts) cudaFreeHost(b->pin_counts);
         b->pin_counts = nullptr; b->pin_counts_cap = 0;
-        CK(cudaHostAlloc((void **)&b->pin_counts, sizeof(int) * (cnt + cnt / 4 + 64), cudaHostAllocDefault));
+        CK(cudaHostAlloc((void **)&b->pin_counts, sizeof(int) * (cnt + cnt / 4 + 64), cudaHostAllocPortable));
         b->pin_counts_cap = cnt + cnt / 4 + 64;
     }
     CK(cudaMemcpyAsync(b->pin_counts, b->B.counts, sizeof(int) * cnt, cudaMemcpyDeviceToHost, cudaStreamPerThread));
@@ -704,7 +764,7 @@ static int batch_fetch(fpk_batch *b, fpk_result *out)
         const int *c = &b->h_counts[(size_t)k * CNT_STRIDE];
         fpk_result &r = out[k];
         memset(&r, 0, sizeof r);
-        r.status = c[CNT_STATUS];
+        r.status = b->bad[k] ? b->bad[k] : c[CNT_STATUS];
         r.n_sites = b->S[k].nsites;
         r.n_tets = c[CNT_TETS];
         const bool have = c[CNT_STATUS] == FPK_OK || c[CNT_STATUS] == FPK_ERR_NO_SPHERES || c[CNT_STATUS] == FPK_ERR_NO_POCKETS;
@@ -788,17 +848,26 @@ extern "C" void fpk_batch_destroy(fpk_batch *b) { delete b; }
 // unpack, each on its own CUDA stream (the library is compiled with --default-stream per-thread), so that one chunk's copies and
 // host-side packing overlap another chunk's kernels. Worker contexts (device arenas, pinned mirrors) are pooled across calls.
 static std::mutex g_pool_mu;
-static std::vector<fpk_batch *> g_pool;
-static fpk_batch *pool_get()
+static std::vector<fpk_batch *> g_pool;        // idle contexts of all devices (a context's arenas stay on the device that made them)
+static fpk_batch *pool_get(int dev)
 {
-    std::lock_guard<std::mutex> g(g_pool_mu);
-    if (!g_pool.empty()) { fpk_batch *b = g_pool.back(); g_pool.pop_back(); return b; }
-    return new fpk_batch();
+    {
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        for (size_t i = 0; i < g_pool.size(); i++)
+            if (g_pool[i]->dev == dev) { fpk_batch *b = g_pool[i]; g_pool.erase(g_pool.begin() + i); return b; }
+    }
+    fpk_batch *b = new fpk_batch();
+    b->dev = dev;
+    return b;
 }
 static void pool_put(fpk_batch *b)
 {
-    std::lock_guard<std::mutex> g(g_pool_mu);
-    if (g_pool.size() < 8) g_pool.push_back(b); else delete b;      // two concurrent callers x four threads (libfpocket_hostio) keep their contexts: a cudaFree here would serialise the device
+    {
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        // two concurrent callers x four threads per device (libfpocket_hostio) keep their contexts: a cudaFree here would serialise the device
+        if (g_pool.size() < 8 * std::max<size_t>(1, g_devs.size())) { g_pool.push_back(b); return; }
+    }
+    delete b;
 }
 static void pool_clear()
 {
@@ -831,12 +900,17 @@ extern "C" int fpk_detect_batch(const fpk_structure *in, int n, const fpk_params
     if (!in || n <= 0 || !p) return fail(FPK_ERR_BAD_ARG, "fpk_detect_batch: bad arguments");
     int rc = ensure_init();
     if (rc) return rc;
+    memset(out, 0, sizeof(fpk_result) * (size_t)n);      // whatever happens, every out[k] can be handed to fpk_result_free
+    const int ndev = (int)g_devs.size();
     // Chunking: K1 keeps 3 x 148 = 444 blocks resident, so a launch wants well over that many structures, and the last round of chunks
     // should keep every host thread busy: ~1,200 structures per chunk, the number of chunks a multiple of the thread count when the batch
     // allows (measured on 6,144 structures, 4 threads: 512 -> 7,668, 1,024 -> 7,867, 1,536 -> 8,268 structures/s end to end).
-    int chunk = 0, nthreads = 4;
+    // With several devices (fpk_init's list) every device gets its own group of host threads; chunks are handed out from one counter,
+    // so a faster or less loaded device simply takes more of them.
+    int chunk = 0, per_dev = 4;
     if (const char *e = getenv("FPK_CHUNK")) chunk = std::max(1, atoi(e));
-    if (const char *e = getenv("FPK_HOST_THREADS")) nthreads = std::max(1, std::min(8, atoi(e)));
+    if (const char *e = getenv("FPK_HOST_THREADS")) per_dev = std::max(1, std::min(8, atoi(e)));
+    int nthreads = per_dev * ndev;
     if (chunk <= 0) {
         int nc = (n + 1199) / 1200;
         if (n >= 600 * nthreads) nc = std::max(nthreads, (nc / nthreads) * nthreads);
@@ -846,7 +920,7 @@ extern "C" int fpk_detect_batch(const fpk_structure *in, int n, const fpk_params
     const int nchunks = (n + chunk - 1) / chunk;
     nthreads = std::min(nthreads, nchunks);
     if (nthreads <= 1) {
-        fpk_batch *b = pool_get();
+        fpk_batch *b = pool_get(g_devs[0]);
         for (int c = 0; c < nchunks && !rc; c++) rc = detect_chunk(b, in + (size_t)c * chunk, std::min(chunk, n - c * chunk), p, out + (size_t)c * chunk);
         pool_put(b);
     } else {
@@ -855,8 +929,9 @@ extern "C" int fpk_detect_batch(const fpk_structure *in, int n, const fpk_params
         std::vector<std::thread> th;
         for (int t = 0; t < nthreads; t++)
             th.emplace_back([&, t]() {
-                cudaSetDevice(g_dev);
-                fpk_batch *b = pool_get();
+                const int dev = g_devs[t % ndev];         // thread t works for device t mod ndev: the first ndev threads cover every device
+                cudaSetDevice(dev);
+                fpk_batch *b = pool_get(dev);
                 for (;;) {
                     const int c = next.fetch_add(1);
                     if (c >= nchunks || err.load()) break;
@@ -867,23 +942,28 @@ extern "C" int fpk_detect_batch(const fpk_structure *in, int n, const fpk_params
             });
         for (auto &x : th) x.join();
         rc = err.load();
-        if (rc) for (auto &m : msgs) if (!m.empty()) g_err = m;
+        if (rc) for (auto &m : msgs) if (!m.empty()) set_err(m);
     }
     if (getenv("FPK_TRACE"))
-        fprintf(stderr, "fpk_detect_batch: %d structures, %d chunks, %d threads; cumulative host ms: pack %.1f upload %.1f run %.1f fetch %.1f\n", n, nchunks,
-                nthreads, g_t_pack.load() / 1e6, g_t_up.load() / 1e6, g_t_run.load() / 1e6, g_t_fetch.load() / 1e6);
+        fprintf(stderr, "fpk_detect_batch: %d structures, %d chunks, %d threads on %d device(s); cumulative host ms: pack %.1f upload %.1f run %.1f fetch %.1f\n", n, nchunks,
+                nthreads, ndev, g_t_pack.load() / 1e6, g_t_up.load() / 1e6, g_t_run.load() / 1e6, g_t_fetch.load() / 1e6);
+    if (rc) {
+        // a CUDA or allocation failure (never a defect of one structure: those are reported per structure): nothing half-made is handed back
+        const std::string keep = g_err;
+        for (int k = 0; k < n; k++) { fpk_result_free(&out[k]); memset(&out[k], 0, sizeof out[k]); out[k].status = rc; }
+        set_err(keep);
+        return rc;
+    }
     // a structure whose sphere buffer overflowed is re-run alone with the worst-case capacity (7 tets per atom)
-    if (!rc) {
-        for (int k = 0; k < n; k++) {
-            if (out[k].status != FPK_ERR_CAPACITY) continue;
-            fpk_batch *b2 = new fpk_batch();
-            fpk_result r2;
-            if (!batch_pack(b2, in + k, 1, p, 7.5) && !batch_upload(b2, in + k) && !batch_run(b2) && !batch_fetch(b2, &r2)) {
-                fpk_result_free(&out[k]);
-                out[k] = r2;
-            }
-            delete b2;
+    for (int k = 0; k < n; k++) {
+        if (out[k].status != FPK_ERR_CAPACITY) continue;
+        fpk_batch *b2 = new fpk_batch();
+        fpk_result r2;
+        if (!batch_pack(b2, in + k, 1, p, 7.5) && !batch_upload(b2, in + k) && !batch_run(b2) && !batch_fetch(b2, &r2)) {
+            fpk_result_free(&out[k]);
+            out[k] = r2;
         }
+        delete b2;
     }
     return rc;
 }
@@ -895,35 +975,60 @@ extern "C" int fpk_detect(const fpk_structure *in, const fpk_params *p, fpk_resu
 }
 
 // =================================================== mdpocket =======================================================
-struct fpk_md {
+// One MdDev per device of fpk_init's list: its own batch skeleton, frame staging and pair of grids. fpk_md_push_frames cuts a block of
+// frames into one contiguous share per device (frames are independent once frame 1 has fixed the grid, mdpbase.c:444-502),
+// a host thread per device pushes its share; the grids are summed into device 0 when they are read (md_reduce: peer copies + an add
+// kernel, integer-valued floats or 32.32 fixed point with -S: exact and order-free either way). With one process per GPU (torchrun) the
+// caller sums fpk_md_device_grids across ranks with NCCL instead.
+struct MdDev {
+    int dev = 0;
     fpk_batch *b = nullptr;            // re-used for every chunk of frames (geometry of the buffers is fixed)
+    float *d_dens = nullptr, *d_freq = nullptr; unsigned *d_mask = nullptr; unsigned long long *d_nscat = nullptr;
+    long long *d_dens_fx = nullptr, *d_freq_fx = nullptr;      // -S: 32.32 fixed-point accumulators (order-free sums), see MdGrid
+    float *d_geom = nullptr;
+    void *d_peer = nullptr; size_t peer_cap = 0;               // device 0 only: landing buffer for another device's grid
+    int nwords = 0, nblocks = 0;
+    long long frames = 0, launches = 0;
+    bool used = false;                 // frames were scattered into these grids since the last reduction
+    float *pin[2] = {nullptr, nullptr}, *d_xyz[2] = {nullptr, nullptr}; size_t stage_cap = 0;     // double-buffered frame staging
+    void free_grids()
+    {
+        cudaFree(d_dens); cudaFree(d_freq); cudaFree(d_mask); cudaFree(d_nscat); cudaFree(d_dens_fx); cudaFree(d_freq_fx);
+        d_dens = d_freq = nullptr; d_mask = nullptr; d_nscat = nullptr; d_dens_fx = d_freq_fx = nullptr;
+    }
+    ~MdDev()
+    {
+        cudaSetDevice(dev);
+        for (int q = 0; q < 2; q++) { if (pin[q]) cudaFreeHost(pin[q]); if (d_xyz[q]) cudaFree(d_xyz[q]); }
+        delete b;
+        free_grids();
+        cudaFree(d_geom); cudaFree(d_peer);
+    }
+};
+struct fpk_md {
     fpk_structure topo;
     std::vector<float> tx, ty, tz, trad, ten, tbf; std::vector<int> tid_, tres; std::vector<int8_t> taa; std::vector<uint8_t> tfl;
     fpk_params prm;
     int use_drug = 0;
-    int chunk = 0;
     bool have_grid = false;
+    bool float_stale = true;           // -S: the float grids have to be refreshed from the fixed-point sums before they are read
     float origin[3]; int dims[3];
-    float *d_dens = nullptr, *d_freq = nullptr; unsigned *d_mask = nullptr; unsigned long long *d_nscat = nullptr;
-    long long *d_dens_fx = nullptr, *d_freq_fx = nullptr;      // -S: 32.32 fixed-point accumulators (order-free sums), see MdGrid
-    float *d_geom = nullptr;
-    int nwords = 0, nblocks = 0;
-    long long frames = 0, launches = 0;
-    float *pin[2] = {nullptr, nullptr}, *d_xyz[2] = {nullptr, nullptr}; size_t stage_cap = 0;     // double-buffered frame staging
-    ~fpk_md() { for (int q = 0; q < 2; q++) { if (pin[q]) cudaFreeHost(pin[q]); if (d_xyz[q]) cudaFree(d_xyz[q]); } delete b; cudaFree(d_dens); cudaFree(d_freq); cudaFree(d_mask); cudaFree(d_nscat); cudaFree(d_geom); cudaFree(d_dens_fx); cudaFree(d_freq_fx); }
+    std::vector<MdDev *> D;            // D[0] holds the summed grids
+    ~fpk_md() { for (MdDev *d : D) delete d; if (!g_devs.empty()) cudaSetDevice(g_devs[0]); }
 };
 
-static int md_prepare(fpk_md *m, int nframes)
+static int md_prepare(fpk_md *m, MdDev *q, int nframes)
 {
     // (re)build the batch skeleton for `nframes` frames: properties uploaded once, coordinates per push
-    if (m->b && m->b->n == nframes) return FPK_OK;
-    delete m->b;
-    m->b = new fpk_batch();
-    fpk_batch *b = m->b;
+    if (q->b && q->b->n == nframes) return FPK_OK;
+    delete q->b;
+    q->b = new fpk_batch();
+    fpk_batch *b = q->b;
     const fpk_structure &t = m->topo;
     std::vector<fpk_structure> fr(nframes, t);
     int rc = batch_pack(b, fr.data(), nframes, &m->prm, 0.0);
     if (rc) return rc;
+    if (b->bad[0]) return FPK_ERR_BAD_ARG;
     // all frames share one copy of the properties and of the site map
     for (int k = 0; k < nframes; k++) { b->S[k].prop_off = 0; b->S[k].site_off = 0; b->S[k].w_off = 0; b->S[k].natoms_w = 0; b->S[k].same_pdb = 1; }
     b->tot_w = 0; b->tot_sites = b->S[0].nsites;
@@ -952,30 +1057,38 @@ __global__ void k_md_deinterleave(const float *xyz, size_t tot, float *ax, float
         ax[i] = xyz[3 * i]; ay[i] = xyz[3 * i + 1]; az[i] = xyz[3 * i + 2];
     }
 }
+__global__ void k_md_add_f32(float *dst, const float *src, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+__global__ void k_md_add_i64(long long *dst, const long long *src, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] += src[i];
+}
 
 // host -> pinned bounce buffer -> device staging buffer `slot`, on the calling thread's stream (returns after the copy has landed)
-static int md_stage_chunk(fpk_md *m, int slot, const float *xyz, int nframes)
+static int md_stage_chunk(fpk_md *m, MdDev *q, int slot, const float *xyz, int nframes)
 {
     const size_t bytes = sizeof(float) * 3 * (size_t)m->topo.natoms * nframes;
-    if (bytes > m->stage_cap) return fail(FPK_ERR_BAD_ARG, "md staging buffer too small");
-    memcpy(m->pin[slot], xyz, bytes);
-    CK(cudaMemcpyAsync(m->d_xyz[slot], m->pin[slot], bytes, cudaMemcpyHostToDevice, cudaStreamPerThread));
+    if (bytes > q->stage_cap) return fail(FPK_ERR_BAD_ARG, "md staging buffer too small");
+    memcpy(q->pin[slot], xyz, bytes);
+    CK(cudaMemcpyAsync(q->d_xyz[slot], q->pin[slot], bytes, cudaMemcpyHostToDevice, cudaStreamPerThread));
     CK(wait_stream());
     return FPK_OK;
 }
 
-static int md_ensure_staging(fpk_md *m, int chunk_frames)
+static int md_ensure_staging(fpk_md *m, MdDev *q, int chunk_frames)
 {
     const size_t need = sizeof(float) * 3 * (size_t)m->topo.natoms * chunk_frames;
-    if (need <= m->stage_cap) return FPK_OK;
-    for (int q = 0; q < 2; q++) {
-        if (m->pin[q]) cudaFreeHost(m->pin[q]);
-        if (m->d_xyz[q]) cudaFree(m->d_xyz[q]);
-        m->pin[q] = nullptr; m->d_xyz[q] = nullptr;
-        CK(cudaHostAlloc((void **)&m->pin[q], need, cudaHostAllocDefault));
-        CK(cudaMalloc((void **)&m->d_xyz[q], need));
+    if (need <= q->stage_cap) return FPK_OK;
+    for (int z = 0; z < 2; z++) {
+        if (q->pin[z]) cudaFreeHost(q->pin[z]);
+        if (q->d_xyz[z]) cudaFree(q->d_xyz[z]);
+        q->pin[z] = nullptr; q->d_xyz[z] = nullptr;
+        CK(cudaHostAlloc((void **)&q->pin[z], need, cudaHostAllocPortable));
+        CK(cudaMalloc((void **)&q->d_xyz[z], need));
     }
-    m->stage_cap = need;
+    q->stage_cap = need;
     return FPK_OK;
 }
 
@@ -983,6 +1096,10 @@ extern "C" fpk_md *fpk_md_begin(const fpk_structure *topo, const fpk_params *p, 
 {
     if (ensure_init()) return nullptr;
     if (!topo || !p || topo->natoms <= 0) { fail(FPK_ERR_BAD_ARG, "fpk_md_begin: bad arguments"); return nullptr; }
+    if (!topo->radius || !topo->electroneg || !topo->bfactor || !topo->atom_id || !topo->res_id || !topo->aa_idx || !topo->flags) {
+        fail(FPK_ERR_BAD_ARG, "fpk_md_begin: NULL atom property array");
+        return nullptr;
+    }
     fpk_md *m = new fpk_md();
     const int na = topo->natoms;
     // own copies of the topology (the caller's arrays need not outlive this call)
@@ -996,10 +1113,12 @@ extern "C" fpk_md *fpk_md_begin(const fpk_structure *topo, const fpk_params *p, 
     m->topo.electroneg = m->ten.data(); m->topo.bfactor = m->tbf.data(); m->topo.atom_id = m->tid_.data();
     m->topo.res_id = m->tres.data(); m->topo.aa_idx = m->taa.data(); m->topo.flags = m->tfl.data();
     m->topo.natoms_w = 0; m->topo.same_pdb = 1; m->topo.n_xlig = 0; m->topo.xlig = nullptr; m->topo.n_lig = 0; m->topo.lig_atoms = nullptr; m->topo.lig_mol = nullptr; m->topo.atom_name_key = nullptr;     // mdpocket.c:844 search_pocket(pdb, params, pdb)
+    if (const char *why = structure_defect(m->topo)) { fail(FPK_ERR_BAD_ARG, "fpk_md_begin: %s", why); delete m; return nullptr; }
     m->prm = *p;
     m->prm.do_asa_and_volume = 0;          // mdpocket.c:89
     m->prm.want_tets = 0;
     m->use_drug = use_drug_score;
+    for (int dev : g_devs) { MdDev *q = new MdDev(); q->dev = dev; m->D.push_back(q); }
     return m;
 }
 
@@ -1007,57 +1126,62 @@ extern "C" int fpk_md_set_grid(fpk_md *m, const float origin[3], const int dims[
 {
     if (!m || !origin || !dims || dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return fail(FPK_ERR_BAD_ARG, "fpk_md_set_grid: bad arguments");
     for (int q = 0; q < 3; q++) { m->origin[q] = origin[q]; m->dims[q] = dims[q]; }
-    size_t ncell = (size_t)dims[0] * dims[1] * dims[2];
-    cudaFree(m->d_dens); cudaFree(m->d_freq); cudaFree(m->d_mask); cudaFree(m->d_nscat); cudaFree(m->d_dens_fx); cudaFree(m->d_freq_fx);
-    m->d_dens_fx = m->d_freq_fx = nullptr;
-    m->nwords = (int)((ncell + 31) / 32);
-    m->nblocks = g_sms * 2;
-    CK(cudaMalloc(&m->d_dens, sizeof(float) * ncell)); CK(cudaMalloc(&m->d_freq, sizeof(float) * ncell));
-    CK(cudaMalloc(&m->d_mask, sizeof(unsigned) * (size_t)m->nwords * m->nblocks)); CK(cudaMalloc(&m->d_nscat, 8));
-    CK(cudaMemset(m->d_dens, 0, sizeof(float) * ncell)); CK(cudaMemset(m->d_freq, 0, sizeof(float) * ncell)); CK(cudaMemset(m->d_nscat, 0, 8));
-    if (m->use_drug) {
-        CK(cudaMalloc(&m->d_dens_fx, sizeof(long long) * ncell)); CK(cudaMalloc(&m->d_freq_fx, sizeof(long long) * ncell));
-        CK(cudaMemset(m->d_dens_fx, 0, sizeof(long long) * ncell)); CK(cudaMemset(m->d_freq_fx, 0, sizeof(long long) * ncell));
+    const size_t ncell = (size_t)dims[0] * dims[1] * dims[2];
+    for (MdDev *q : m->D) {
+        CK(cudaSetDevice(q->dev));
+        q->free_grids();
+        q->nwords = (int)((ncell + 31) / 32);
+        q->nblocks = g_sms * 2;
+        CK(cudaMalloc(&q->d_dens, sizeof(float) * ncell)); CK(cudaMalloc(&q->d_freq, sizeof(float) * ncell));
+        CK(cudaMalloc(&q->d_mask, sizeof(unsigned) * (size_t)q->nwords * q->nblocks)); CK(cudaMalloc(&q->d_nscat, 8));
+        CK(cudaMemset(q->d_dens, 0, sizeof(float) * ncell)); CK(cudaMemset(q->d_freq, 0, sizeof(float) * ncell)); CK(cudaMemset(q->d_nscat, 0, 8));
+        if (m->use_drug) {
+            CK(cudaMalloc(&q->d_dens_fx, sizeof(long long) * ncell)); CK(cudaMalloc(&q->d_freq_fx, sizeof(long long) * ncell));
+            CK(cudaMemset(q->d_dens_fx, 0, sizeof(long long) * ncell)); CK(cudaMemset(q->d_freq_fx, 0, sizeof(long long) * ncell));
+        }
+        q->used = false;
     }
-    m->have_grid = true;
+    CK(cudaSetDevice(m->D[0]->dev));
+    m->have_grid = true; m->float_stale = true;
     return FPK_OK;
 }
 
 extern "C" int fpk_md_grid_from_frame(fpk_md *m, const float *xyz, float origin[3], int dims[3])
 {
     if (!m || !xyz) return fail(FPK_ERR_BAD_ARG, "fpk_md_grid_from_frame: bad arguments");
-    int rc = md_prepare(m, 1);
-    if (!rc) rc = md_ensure_staging(m, 1);
-    if (!rc) rc = md_stage_chunk(m, 0, xyz, 1);
+    MdDev *q = m->D[0];
+    CK(cudaSetDevice(q->dev));
+    int rc = md_prepare(m, q, 1);
+    if (!rc) rc = md_ensure_staging(m, q, 1);
+    if (!rc) rc = md_stage_chunk(m, q, 0, xyz, 1);
     if (!rc) {
         const size_t tot = (size_t)m->topo.natoms;
-        k_md_deinterleave<<<64, 256>>>(m->d_xyz[0], tot, const_cast<float *>(m->b->B.ax), const_cast<float *>(m->b->B.ay), const_cast<float *>(m->b->B.az));
+        k_md_deinterleave<<<64, 256>>>(q->d_xyz[0], tot, const_cast<float *>(q->b->B.ax), const_cast<float *>(q->b->B.ay), const_cast<float *>(q->b->B.az));
     }
-    if (!rc) rc = batch_run(m->b);
+    if (!rc) rc = batch_run(q->b);
     if (rc) return rc;
-    m->launches += m->b->launches;
-    if (!m->d_geom) CK(cudaMalloc(&m->d_geom, sizeof(float) * 8));
-    k_md_geometry<<<1, 32>>>(m->b->B, 0, m->d_geom);
-    m->launches++;
+    q->launches += q->b->launches;
+    if (!q->d_geom) CK(cudaMalloc(&q->d_geom, sizeof(float) * 8));
+    k_md_geometry<<<1, 32>>>(q->b->B, 0, q->d_geom);
+    q->launches++;
     float g[6];
-    CK(cudaMemcpy(g, m->d_geom, sizeof g, cudaMemcpyDeviceToHost));
-    for (int q = 0; q < 3; q++) { origin[q] = g[q]; dims[q] = (int)g[3 + q]; }
+    CK(cudaMemcpy(g, q->d_geom, sizeof g, cudaMemcpyDeviceToHost));
+    for (int z = 0; z < 3; z++) { origin[z] = g[z]; dims[z] = (int)g[3 + z]; }
     return FPK_OK;
 }
 
-extern "C" int fpk_md_push_frames(fpk_md *m, const float *xyz, int nframes)
+// detect + scatter `nframes` frames on ONE device (the calling thread has made it current)
+static int md_push_on(fpk_md *m, MdDev *q, const float *xyz, int nframes)
 {
-    if (!m || !xyz || nframes <= 0) return fail(FPK_ERR_BAD_ARG, "fpk_md_push_frames: bad arguments");
-    if (!m->have_grid) return fail(FPK_ERR_BAD_ARG, "fpk_md_push_frames: set the grid first (fpk_md_set_grid)");
     const size_t na = (size_t)m->topo.natoms;
     const int chunk_max = std::max(256, g_sms * 2 * 8);         // a whole number of structures per resident K1 block (2 per SM)
-    int rc = md_ensure_staging(m, std::min(chunk_max, nframes));
+    int rc = md_ensure_staging(m, q, std::min(chunk_max, nframes));
     typedef std::chrono::steady_clock clk;
     double t_run = 0, t_scatter = 0, t_prep = 0;
     if (rc) return rc;
     // chunk k+1 is staged (host copy into pinned memory + H2D) by a helper thread on its own stream while chunk k is detected
     const int nchunks = (nframes + chunk_max - 1) / chunk_max;
-    rc = md_stage_chunk(m, 0, xyz, std::min(chunk_max, nframes));
+    rc = md_stage_chunk(m, q, 0, xyz, std::min(chunk_max, nframes));
     if (rc) return rc;
     for (int c = 0; c < nchunks; c++) {
         const int f0 = c * chunk_max, nf = std::min(chunk_max, nframes - f0);
@@ -1067,54 +1191,120 @@ extern "C" int fpk_md_push_frames(fpk_md *m, const float *xyz, int nframes)
         if (c + 1 < nchunks) {
             const int f1 = f0 + chunk_max, nf1 = std::min(chunk_max, nframes - f1);
             pre = std::thread([&, f1, nf1, c]() {
-                cudaSetDevice(g_dev);
-                pre_rc = md_stage_chunk(m, (c + 1) & 1, xyz + 3 * na * (size_t)f1, nf1);
+                cudaSetDevice(q->dev);
+                pre_rc = md_stage_chunk(m, q, (c + 1) & 1, xyz + 3 * na * (size_t)f1, nf1);
                 if (pre_rc) pre_err = g_err;
             });
         }
         auto t0 = clk::now();
-        rc = md_prepare(m, nf);
+        rc = md_prepare(m, q, nf);
         auto t1 = clk::now();
         t_prep += std::chrono::duration<double, std::milli>(t1 - t0).count();
         if (!rc) {
             const size_t tot = na * (size_t)nf;
-            k_md_deinterleave<<<g_sms * 4, 256>>>(m->d_xyz[c & 1], tot, const_cast<float *>(m->b->B.ax), const_cast<float *>(m->b->B.ay), const_cast<float *>(m->b->B.az));
-            m->b->h2d += (long long)(sizeof(float) * 3 * tot);
-            rc = batch_run(m->b);
+            k_md_deinterleave<<<g_sms * 4, 256>>>(q->d_xyz[c & 1], tot, const_cast<float *>(q->b->B.ax), const_cast<float *>(q->b->B.ay), const_cast<float *>(q->b->B.az));
+            q->b->h2d += (long long)(sizeof(float) * 3 * tot);
+            rc = batch_run(q->b);
             t_run += std::chrono::duration<double, std::milli>(clk::now() - t1).count();
         }
         if (!rc) {
             auto t2 = clk::now();
             MdGrid G;
-            for (int q = 0; q < 3; q++) G.origin[q] = m->origin[q];
+            for (int z = 0; z < 3; z++) G.origin[z] = m->origin[z];
             G.nx = m->dims[0]; G.ny = m->dims[1]; G.nz = m->dims[2];
-            G.dens = m->d_dens; G.freq = m->d_freq; G.mask = m->d_mask; G.nwords = m->nwords; G.use_drug_score = m->use_drug;
-            G.dens_fx = m->d_dens_fx; G.freq_fx = m->d_freq_fx;
-            k_md_scatter<<<std::min(m->nblocks, nf), 256>>>(m->b->B, m->b->Pk, G, m->d_nscat);
+            G.dens = q->d_dens; G.freq = q->d_freq; G.mask = q->d_mask; G.nwords = q->nwords; G.use_drug_score = m->use_drug;
+            G.dens_fx = q->d_dens_fx; G.freq_fx = q->d_freq_fx;
+            k_md_scatter<<<std::min(q->nblocks, nf), 256>>>(q->b->B, q->b->Pk, G, q->d_nscat);
             cudaError_t e = cudaStreamSynchronize(cudaStreamPerThread);
             if (e != cudaSuccess) rc = fail(FPK_ERR_CUDA, "k_md_scatter: %s", cudaGetErrorString(e));
-            m->launches += m->b->launches + 2;
-            m->frames += nf;
+            q->launches += q->b->launches + 2;
+            q->frames += nf;
+            q->used = true;
             t_scatter += std::chrono::duration<double, std::milli>(clk::now() - t2).count();
         }
         if (pre.joinable()) pre.join();
         if (rc) return rc;
-        if (pre_rc) { g_err = pre_err; return pre_rc; }
+        if (pre_rc) { set_err(pre_err); return pre_rc; }
     }
     CK(cudaDeviceSynchronize());
-    if (getenv("FPK_TRACE")) fprintf(stderr, "fpk_md_push_frames: %d frames, %d chunks; host ms: prepare %.1f detect %.1f scatter %.1f\n", nframes, nchunks, t_prep, t_run, t_scatter);
+    if (getenv("FPK_TRACE")) fprintf(stderr, "fpk_md_push_frames: device %d: %d frames, %d chunks; host ms: prepare %.1f detect %.1f scatter %.1f\n", q->dev, nframes, nchunks, t_prep, t_run, t_scatter);
     return FPK_OK;
 }
 
-// -S: the float grids are views of the fixed-point accumulators, refreshed whenever they are handed out
+extern "C" int fpk_md_push_frames(fpk_md *m, const float *xyz, int nframes)
+{
+    if (!m || !xyz || nframes <= 0) return fail(FPK_ERR_BAD_ARG, "fpk_md_push_frames: bad arguments");
+    if (!m->have_grid) return fail(FPK_ERR_BAD_ARG, "fpk_md_push_frames: set the grid first (fpk_md_set_grid)");
+    m->float_stale = true;
+    const int ndev = (int)m->D.size();
+    const size_t na = (size_t)m->topo.natoms;
+    // contiguous shares of at least 64 frames per device; a short push (the reference's frame-by-frame loop) stays on device 0
+    const int nuse = std::max(1, std::min(ndev, nframes / 64));
+    if (nuse == 1) {
+        CK(cudaSetDevice(m->D[0]->dev));
+        return md_push_on(m, m->D[0], xyz, nframes);
+    }
+    std::vector<int> rcs(nuse, FPK_OK);
+    std::vector<std::string> msgs(nuse);
+    std::vector<std::thread> th;
+    for (int d = 0; d < nuse; d++) {
+        const int f0 = (int)((long long)nframes * d / nuse), f1 = (int)((long long)nframes * (d + 1) / nuse);
+        th.emplace_back([&, d, f0, f1]() {
+            cudaSetDevice(m->D[d]->dev);
+            rcs[d] = md_push_on(m, m->D[d], xyz + 3 * na * (size_t)f0, f1 - f0);
+            if (rcs[d]) msgs[d] = g_err;
+        });
+    }
+    for (auto &t : th) t.join();
+    cudaSetDevice(m->D[0]->dev);
+    for (int d = 0; d < nuse; d++) if (rcs[d]) { set_err(msgs[d]); return rcs[d]; }
+    return FPK_OK;
+}
+
+// sum the grids of devices 1.. into device 0 and clear them (so that a later reduction does not count them twice)
+static int md_reduce(fpk_md *m)
+{
+    MdDev *z = m->D[0];
+    const size_t ncell = (size_t)m->dims[0] * m->dims[1] * m->dims[2];
+    const size_t esz = m->use_drug ? sizeof(long long) : sizeof(float);
+    CK(cudaSetDevice(z->dev));
+    for (size_t d = 1; d < m->D.size(); d++) {
+        MdDev *q = m->D[d];
+        if (!q->used) continue;
+        if (z->peer_cap < ncell * esz) { cudaFree(z->d_peer); z->d_peer = nullptr; z->peer_cap = 0; CK(cudaMalloc(&z->d_peer, ncell * esz)); z->peer_cap = ncell * esz; }
+        for (int g = 0; g < 2; g++) {
+            void *src = m->use_drug ? (void *)(g ? q->d_freq_fx : q->d_dens_fx) : (void *)(g ? q->d_freq : q->d_dens);
+            CK(cudaMemcpyPeer(z->d_peer, z->dev, src, q->dev, ncell * esz));
+            if (m->use_drug) k_md_add_i64<<<g_sms * 4, 256>>>(g ? z->d_freq_fx : z->d_dens_fx, (const long long *)z->d_peer, ncell);
+            else k_md_add_f32<<<g_sms * 4, 256>>>(g ? z->d_freq : z->d_dens, (const float *)z->d_peer, ncell);
+            CK(cudaStreamSynchronize(cudaStreamPerThread));
+            z->launches++;
+        }
+        CK(cudaSetDevice(q->dev));
+        if (m->use_drug) { CK(cudaMemset(q->d_dens_fx, 0, ncell * esz)); CK(cudaMemset(q->d_freq_fx, 0, ncell * esz)); }
+        else { CK(cudaMemset(q->d_dens, 0, ncell * esz)); CK(cudaMemset(q->d_freq, 0, ncell * esz)); }
+        q->used = false;
+        CK(cudaSetDevice(z->dev));
+        m->float_stale = true;
+    }
+    return FPK_OK;
+}
+
+// -S: the float grids are views of the fixed-point accumulators, refreshed when frames were pushed since they were last handed out.
+// (Not on every call: a caller that summed the float grids across ranks in place - fpk_md_device_grids, NCCL all-reduce - must read
+// back what it summed, not this rank's share again.)
 static int md_refresh_float_grids(fpk_md *m)
 {
-    if (!m->d_dens_fx) return FPK_OK;
+    int rc = md_reduce(m);
+    if (rc) return rc;
+    MdDev *z = m->D[0];
+    if (!z->d_dens_fx || !m->float_stale) { m->float_stale = false; return FPK_OK; }
     const size_t ncell = (size_t)m->dims[0] * m->dims[1] * m->dims[2];
-    k_md_fixed_to_float<<<g_sms * 4, 256>>>(m->d_dens_fx, m->d_dens, ncell);
-    k_md_fixed_to_float<<<g_sms * 4, 256>>>(m->d_freq_fx, m->d_freq, ncell);
-    m->launches += 2;
+    k_md_fixed_to_float<<<g_sms * 4, 256>>>(z->d_dens_fx, z->d_dens, ncell);
+    k_md_fixed_to_float<<<g_sms * 4, 256>>>(z->d_freq_fx, z->d_freq, ncell);
+    z->launches += 2;
     CK(cudaStreamSynchronize(cudaStreamPerThread));
+    m->float_stale = false;
     return FPK_OK;
 }
 
@@ -1122,8 +1312,8 @@ extern "C" int fpk_md_device_grids(fpk_md *m, void **dens, void **freq, size_t *
 {
     if (!m || !m->have_grid) return fail(FPK_ERR_BAD_ARG, "no grid");
     { int rc = md_refresh_float_grids(m); if (rc) return rc; }
-    if (dens) *dens = m->d_dens;
-    if (freq) *freq = m->d_freq;
+    if (dens) *dens = m->D[0]->d_dens;
+    if (freq) *freq = m->D[0]->d_freq;
     if (ncell) *ncell = (size_t)m->dims[0] * m->dims[1] * m->dims[2];
     return FPK_OK;
 }
@@ -1132,16 +1322,21 @@ extern "C" int fpk_md_fetch_grids(fpk_md *m, float *dens, float *freq)
     if (!m || !m->have_grid) return fail(FPK_ERR_BAD_ARG, "no grid");
     size_t ncell = (size_t)m->dims[0] * m->dims[1] * m->dims[2];
     { int rc = md_refresh_float_grids(m); if (rc) return rc; }
-    if (dens) CK(cudaMemcpy(dens, m->d_dens, sizeof(float) * ncell, cudaMemcpyDeviceToHost));
-    if (freq) CK(cudaMemcpy(freq, m->d_freq, sizeof(float) * ncell, cudaMemcpyDeviceToHost));
+    if (dens) CK(cudaMemcpy(dens, m->D[0]->d_dens, sizeof(float) * ncell, cudaMemcpyDeviceToHost));
+    if (freq) CK(cudaMemcpy(freq, m->D[0]->d_freq, sizeof(float) * ncell, cudaMemcpyDeviceToHost));
     return FPK_OK;
 }
 extern "C" long long fpk_md_counter(const fpk_md *m, int which)
 {
     if (!m) return -1;
-    if (which == 0) return m->frames;
-    if (which == 2) return m->launches;
-    if (which == 1 && m->d_nscat) { unsigned long long v = 0; cudaMemcpy(&v, m->d_nscat, 8, cudaMemcpyDeviceToHost); return (long long)v; }
-    return 0;
+    long long v = 0;
+    for (const MdDev *q : m->D) {
+        if (which == 0) v += q->frames;
+        else if (which == 2) v += q->launches;
+        else if (which == 1 && q->d_nscat) { unsigned long long u = 0; cudaSetDevice(q->dev); cudaMemcpy(&u, q->d_nscat, 8, cudaMemcpyDeviceToHost); v += (long long)u; }
+        else if (which == 3) v += q->frames > 0 ? 1 : 0;          // devices that took a share of the frames
+    }
+    if (!m->D.empty()) cudaSetDevice(m->D[0]->dev);
+    return v;
 }
 extern "C" void fpk_md_end(fpk_md *m) { delete m; }

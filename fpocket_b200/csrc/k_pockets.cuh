@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(256) k_cluster(BatchDev B, const ClusterScratc
             if (tid == 0) { counts[CNT_CLUSTERS] = 0; counts[CNT_STATUS] = FPK_ERR_NO_SPHERES; }
             continue;
         }
-        if (ns == 0) { if (tid == 0) { counts[CNT_CLUSTERS] = 0; counts[CNT_STATUS] = FPK_ERR_NO_POCKETS; } continue; }
+        // no sphere at all with clustering skipped (-r / -P): assign_pockets returns NULL, search_pocket returns NULL (pocket.c:77, fpocket.c:160)
+        if (ns == 0) { if (tid == 0) { counts[CNT_CLUSTERS] = 0; counts[CNT_STATUS] = FPK_ERR_NO_SPHERES; } continue; }
         if (B.prm.skip_clustering) {                 // explicit pocket: every sphere has the same resid -> one pocket
             for (int i = tid; i < ns; i += nt) { par[i] = 0; cl_sph[i] = i; }
             if (tid == 0) { cl_off[0] = 0; cl_off[1] = ns; counts[CNT_CLUSTERS] = 1; }

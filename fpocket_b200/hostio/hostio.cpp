@@ -1162,7 +1162,7 @@ int run_pipeline(const char *const *paths, int n, const OptsOf &opts_of, const f
                         const bool have_list = (R->status == FPK_OK || R->status == FPK_ERR_NO_POCKETS);
                         if (have_list) w = sink(g->first + k, g->files[k], R, &bytes);
                         else {
-                            if (!quiet && R->status == FPK_ERR_NO_SPHERES) fprintf(stderr, "Error in creating clustering tree, return NULL pointer...breaking up");
+                            if (!quiet && R->status == FPK_ERR_NO_SPHERES && !p->skip_clustering) fprintf(stderr, "Error in creating clustering tree, return NULL pointer...breaking up");      // with -r / -P the reference returns NULL without a word (pocket.c:77)
                             if (!quiet) printf("no pockets found\n");                            // fpmain.c:204
                         }
                         if (w < 0 && !quiet) fprintf(stderr, "! could not write the results of %s\n", paths[g->first + k]);

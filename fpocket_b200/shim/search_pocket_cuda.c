@@ -219,7 +219,8 @@ c_lst_pockets *shim_rebuild(s_pdb *pdb, s_fparams *params, s_pdb *pdb_w_lig, fpk
     const int n = pdb->natoms;
     memset(Rp, 0, sizeof *Rp);
     if (rc == FPK_ERR_NO_SPHERES) {
-        fprintf(stderr, "Error in creating clustering tree, return NULL pointer...breaking up");      /* fpocket.c:137 */
+        if (params->xlig_resnumber == -1 && params->xpocket_n == 0)        /* with -r / -P the reference returns NULL without a word (pocket.c:77) */
+            fprintf(stderr, "Error in creating clustering tree, return NULL pointer...breaking up");      /* fpocket.c:137 */
         fpk_result_free(&R);
         return NULL;
     }

@@ -156,7 +156,11 @@ typedef struct fpk_result {
 } fpk_result;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
-int fpk_init(const int *devices, int ndev);   /* devices==NULL: use the current device. Fails loudly without a GPU. */
+/* devices = the GPUs the library may use: fpk_detect_batch hands its chunks to all of them, fpk_md_push_frames gives every one a
+ * contiguous share of the frames and sums the grids (reference loops fpmain.c:61-76, mdpocket.c:235-271).
+ * devices == NULL: $FPK_DEVICES ("all" or "0,2,3") if set, else the current device. Fails loudly without a GPU. */
+int fpk_init(const int *devices, int ndev);
+int fpk_device_count(void);                   /* devices in use (0 before fpk_init) */
 void fpk_shutdown(void);
 const char *fpk_last_error(void);
 const char *fpk_version(void);
@@ -186,13 +190,14 @@ int fpk_md_grid_from_frame(fpk_md *m, const float *xyz, float origin[3], int dim
 int fpk_md_set_grid(fpk_md *m, const float origin[3], const int dims[3]);
 /* detect + calculate_md_dens_grid + update_md_grid for nframes frames; xyz = [nframes][natoms][3] host floats */
 int fpk_md_push_frames(fpk_md *m, const float *xyz, int nframes);
-/* device pointers of the two accumulators (float[nx*ny*nz]) so the caller can sum them across ranks (NCCL).
+/* device pointers of the two accumulators (float[nx*ny*nz], on the first device, already summed over the library's devices) so that
+ * a caller running one process per GPU can sum them across ranks in place (NCCL all-reduce) and then read them with fpk_md_fetch_grids.
  * With -S the increments are floats (drug scores): they are summed as 32.32 fixed-point integers so that the result does not depend on
  * the order in which frames reach a cell (same input, same bytes); the float grids are refreshed from those sums by this call and by
- * fpk_md_fetch_grids, so call it again after pushing more frames. */
+ * fpk_md_fetch_grids when frames were pushed since the last refresh (never otherwise: what the caller summed in place stays). */
 int fpk_md_device_grids(fpk_md *m, void **dens, void **freq, size_t *ncell);
 int fpk_md_fetch_grids(fpk_md *m, float *dens, float *freq);    /* D2H, un-normalised sums (normalize_grid stays host, mdpbase.c:354) */
-long long fpk_md_counter(const fpk_md *m, int which);            /* 0 frames, 1 spheres scattered, 2 launches */
+long long fpk_md_counter(const fpk_md *m, int which);            /* 0 frames, 1 spheres scattered, 2 launches, 3 devices that took frames */
 void fpk_md_end(fpk_md *m);
 
 #ifdef __cplusplus

@@ -622,7 +622,8 @@ int orc_search_pocket(const fpk_structure *in, const fpk_params *p, const int *t
     free(own_tets); free(ki); free(xd); free(site2atom);
     out->n_spheres = ns;
     out->atom_fx = calloc((size_t)natoms * 4 + 4, sizeof(float));
-    if (!p->skip_clustering && ns < 2) {          /* clusterlib.c:3969 -> fpocket.c:135-139 */
+    if ((!p->skip_clustering && ns < 2) || ns == 0) {          /* clusterlib.c:3969 -> fpocket.c:135-139; no sphere at all with -r / -P: assign_pockets
+                                                                   returns NULL (pocket.c:77), search_pocket returns NULL and nothing is written */
         free(S);
         out->status = FPK_ERR_NO_SPHERES;
         return out->status;

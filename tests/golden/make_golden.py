@@ -36,6 +36,12 @@ CASES = [
     ("6X3P_cif", "6X3P.cif", ["--seed", "22"], []),                               # test_mmcif.py:82
     ("1QNH_cif_aCD", "1QNH.cif", ["--seed", "23"], ["-a", "C,D"]),                # test_mmcif.py:92 chains as ligand, mmCIF reader
     ("1UYD_dpocket", "1UYD.pdb", ["--seed", "19", "--lig", "PU8"], []),            # dpocket.c:186-290 with the known ligand
+    # option branches of fparams.c:113-530 that the default cases never take (untested on the GPU)
+    ("5WA6_i30_A2_v1000", "5WA6.pdb", ["--seed", "41"], ["-i", "30", "-A", "2", "-v", "1000"]),                     # -i, -A, -v
+    ("5WA6_p01", "5WA6.pdb", ["--seed", "45"], ["-p", "0.1"]),            # -p: with refine.c:129-130's precedence every pocket that is not 100 % apolar is dropped
+    ("3LKF_i8_A4", "3LKF.pdb", ["--seed", "42"], ["-i", "8", "-A", "4"]),                                         # min_pock_nb_asph below the default: the MC skip keys on it
+    ("1UYD_P_u2", "1UYD.pdb", ["--seed", "43"], ["-P", "51:-:A.52:-:A.55:-:A.93:-:A.98:-:A.107:-:A.138:-:A.139:-:A.184:-:A", "-u", "2"]),   # explicit pocket by residues
+    ("1UYD_P_u4", "1UYD.pdb", ["--seed", "44"], ["-P", "51:-:A.52:-:A.55:-:A.91:-:A.93:-:A.96:-:A.98:-:A.107:-:A.138:-:A.139:-:A.150:-:A.184:-:A"]),  # default -u 4
     ("md_2yex", "mdpocket/2yex.pdb", ["--md"], []),                           # mdpocket.c:833 call shape
     ("md_3ot3_S", "mdpocket/3ot3.pdb", ["--md", "--score"], []),              # -S drug-score increments
     # one snapshot of mdpocket's characterize mode (mdpocket.c:436-460): zone = the first 70 grid points of the reference's own mdpout_dens_iso_8.pdb

@@ -50,3 +50,20 @@ def pocket_sets(r, clusters):
     """set of frozensets of sphere keys for the given cluster indices"""
     keys = canon_sphere_keys(r["sph_neigh"])
     return [frozenset(keys[s] for s in r["cl_sph"][r["cl_off"][c]:r["cl_off"][c + 1]]) for c in clusters]
+
+
+# ---- every structure of the reference's data/sample, atoms as the reference's readers parsed them (tests/golden/make_sample_fixtures.py) ----
+SAMPLES_DIR = os.path.join(GOLD, "samples")
+SAMPLES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(SAMPLES_DIR, "*.npz")))
+
+
+def load_sample(name):
+    """A sample fixture in the shape of load(): pdb's atoms are the masked subsequence of pdb_w_lig's; of qhull's tetrahedra only the
+    tail the reference never read is kept (d["qh.tets"][d["qh.n_seen"] - 1:] is that tail, as in the full fixtures)."""
+    d = dict(np.load(os.path.join(SAMPLES_DIR, name + ".npz")))
+    m = d["in_pdb"].astype(bool)
+    for k in ("f", "i", "symbol", "res_name"):
+        d["pdb." + k] = d["pdbw." + k][m]
+    d["qh.tets"] = d["qh.tail"]
+    d["qh.n_seen"] = np.array([1])
+    return d
