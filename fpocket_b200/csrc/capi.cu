@@ -122,6 +122,8 @@ extern "C" int fpk_init(const int *devices, int ndev)
         cudaFuncAttributes fa;
         CK(cudaFuncGetAttributes(&fa, k_delaunay_filter));
         CK(cudaFuncSetAttribute(k_delaunay_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pr.sharedMemPerBlockOptin - fa.sharedSizeBytes)));
+        CK(cudaFuncGetAttributes(&fa, k_delaunay_grid));
+        CK(cudaFuncSetAttribute(k_delaunay_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pr.sharedMemPerBlockOptin - fa.sharedSizeBytes)));
         CK(cudaFuncGetAttributes(&fa, k_hull_volume));
         CK(cudaFuncSetAttribute(k_hull_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pr.sharedMemPerBlockOptin - fa.sharedSizeBytes)));
         CK(cudaFuncSetAttribute(k_hull_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HW_WARPS * sizeof(HullWarp))));
@@ -269,6 +271,11 @@ struct fpk_batch {
     LigDev Lg;                         // dpocket ligand queries (tot_lig > 0)
     std::vector<int> h_ni;
     int max_sites = 0, max_w = 0, max_sphcap = 0;
+    // structures above k1_max_sites are triangulated one at a time by the WHOLE GPU (k_delaunay_grid), the others by one block each (K1)
+    int k1_max_sites = 0x7fffffff, max_sites_big = 0, max_sphcap_big = 0, max_sphcap_small = 0;
+    std::vector<int> big;              // indices of the former
+    GridDel *dGrid = nullptr; int nGridBlocks = 0; size_t grid_dsm = 0;
+    DelScratch hGridX;
     int md_shared_props = 0;           // mdpocket: all frames share the property arrays
     // stage 1 device
     Arena A1, A2;
@@ -348,6 +355,15 @@ static int batch_pack(fpk_batch *b, const fpk_structure *in, int n, const fpk_pa
     b->S.resize(n); b->natoms.resize(n); b->lig_n.assign(n, 0);
     b->sane.assign(in, in + n); b->bad.assign(n, 0);
     b->max_sites = b->max_w = b->max_sphcap = 0; b->h2d = b->d2h = 0;
+    b->max_sites_big = b->max_sphcap_big = b->max_sphcap_small = 0; b->big.clear();
+    // One block per structure is the right grain for a batch; a large complex (BASELINE configs[3]) or a lone structure would leave the
+    // GPU idle: from 12,000 sites on - or 2,500 when the call holds at most four structures - the whole GPU works on ONE triangulation.
+    {
+        int thr = 12000;
+        if (const char *e = getenv("FPK_GRID_MIN_SITES")) thr = std::max(4, atoi(e));
+        else if (n <= 4) thr = 2500;
+        b->k1_max_sites = thr - 1;
+    }
     long long ao = 0, wo = 0, so = 0, xo = 0, sc = 0, tc = 0, lo = 0;
     b->has_names = false;
     for (int k = 0; k < n; k++) {
@@ -376,7 +392,8 @@ static int batch_pack(fpk_batch *b, const fpk_structure *in, int n, const fpk_pa
         d.tet_off = (int)tc; d.tet_cap = p->want_tets ? 8 * ns + 64 : 0;
         b->natoms[k] = s.natoms;
         ao += s.natoms; wo += s.natoms_w; so += ns; xo += s.n_xlig; sc += d.sph_cap; tc += d.tet_cap;
-        b->max_sites = std::max(b->max_sites, ns);
+        if (ns > b->k1_max_sites) { b->big.push_back(k); b->max_sites_big = std::max(b->max_sites_big, ns); b->max_sphcap_big = std::max(b->max_sphcap_big, d.sph_cap); }
+        else { b->max_sites = std::max(b->max_sites, ns); b->max_sphcap_small = std::max(b->max_sphcap_small, d.sph_cap); }
         b->max_w = std::max(b->max_w, s.natoms_w ? s.natoms_w : s.natoms);
         b->max_sphcap = std::max(b->max_sphcap, d.sph_cap);
         if (ao > 2000000000ll || sc + n > 2000000000ll || tc > 500000000ll) return fail(FPK_ERR_BAD_ARG, "batch too large for 32-bit offsets; split it");
@@ -469,14 +486,26 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
         B.counts = a.take<int>((size_t)n * CNT_STRIDE);
         b->d_counters = a.take<int>(8);
         B.tets_out = b->tot_tetcap ? a.take<int>(4 * b->tot_tetcap) : nullptr;
-        for (int i = 0; i < b->nDel; i++) del_scratch_layout(a, hDel[i], b->max_sites, b->max_sphcap, FPK_K1_THREADS, true);
+        for (int i = 0; i < b->nDel; i++) del_scratch_layout(a, hDel[i], std::max(4, b->max_sites), std::max(64, b->max_sphcap_small), FPK_K1_THREADS, true);
+        if (!b->big.empty()) {
+            b->dGrid = a.take<GridDel>(1);
+            del_scratch_layout(a, b->hGridX, b->max_sites_big, b->max_sphcap_big, FPK_K1_THREADS, true);
+        }
         for (int i = 0; i < b->nClu; i++) {
             hClu[i].cellcnt = a.take<int>(CELLMAX + 2); hClu[i].cellsph = a.take<int>(b->max_sphcap + 1);
             hClu[i].tmp = a.take<int>(b->max_sphcap + 2); hClu[i].scap = b->max_sphcap;
         }
     });
     if (rc) return rc;
-    B.nstruct = n; B.S = b->dS; B.prm = b->prm; B.work_order = b->d_order; B.work_counter = b->d_counters;
+    B.nstruct = n; B.S = b->dS; B.prm = b->prm; B.work_order = b->d_order; B.work_counter = b->d_counters; B.k1_max_sites = b->k1_max_sites;
+    if (!b->big.empty()) {
+        int occg = 1;
+        b->grid_dsm = FPK_BD_BYTES + (FPK_K1_THREADS / 32) * sizeof(WarpCav);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occg, k_delaunay_grid, FPK_K1_THREADS, b->grid_dsm);
+        occg = std::max(1, std::min(occg, FPK_K1_MINBLOCKS));
+        if (const char *e = getenv("FPK_GRID_BLOCKS_PER_SM")) occg = std::max(1, std::min(occg, atoi(e)));      // tuning knob (profiles/)
+        b->nGridBlocks = g_sms * occg;
+    }
     std::vector<int> order(n);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return b->S[x].nsites > b->S[y].nsites; });
@@ -580,6 +609,12 @@ static int batch_run(fpk_batch *b)
     CK(cudaMemsetAsync(b->d_counters, 0, sizeof(int) * 8));
     CK(cudaMemsetAsync(B.counts, 0, sizeof(int) * (size_t)n * CNT_STRIDE));
     CK(cudaEventRecord(b->ev[0]));
+    for (int kb : b->big) {            // large structures: one cooperative launch each, every resident block on the same triangulation
+        if (b->S[kb].nsites < 4) continue;
+        void *args[] = {(void *)&B, (void *)&b->hGridX, (void *)&b->dGrid, (void *)&kb};
+        CK(cudaLaunchCooperativeKernel((void *)k_delaunay_grid, dim3(b->nGridBlocks), dim3(FPK_K1_THREADS), args, b->grid_dsm, cudaStreamPerThread));
+        b->launches++;
+    }
     k_delaunay_filter<<<b->nDel, FPK_K1_THREADS, b->k1_dsm>>>(B, b->dDel, b->k1_picap);
     CK(cudaEventRecord(b->ev[1]));
     k_cluster<<<b->nClu, 256>>>(B, b->dClu, b->d_counters + 1);

@@ -51,6 +51,7 @@ struct BatchDev {
     const int *work_order;     // structures, largest first
     int *work_counter;
     int *tets_out;             // optional
+    int k1_max_sites;          // structures with more sites were triangulated by the grid-wide kernel (k_delaunay_grid.cuh): K1 skips them
 };
 
 // ---- arithmetic mirrored from the reference (gcc x86-64, no FMA): compile with -fmad=false ---------------

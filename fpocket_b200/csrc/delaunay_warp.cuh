@@ -189,11 +189,15 @@ __device__ __forceinline__ bool in_conflict_v(const int *tet, const int *Pi, con
 __device__ __forceinline__ int2 ldcg2(const int *p) { return __ldcg(reinterpret_cast<const int2 *>(p)); }
 
 // ---- claim phase: locate the point, flood its cavity while claiming it (all 32 lanes, identical arguments) ------------------------
-template <bool SM> __device__ __noinline__ int w2_locate_and_claim(int rank, int own_hint, int *ncav_out)
+// GRID: the triangulation is shared by every block of a cooperative launch (k_delaunay_grid.cuh): the counters live in global memory
+// (c.cnt) instead of the block's shared memory; everything else - per-warp state, cavity records - stays with the block.
+template <bool SM, bool GRID = false> __device__ __noinline__ int w2_locate_and_claim(int rank, int own_hint, int *ncav_out)
 {
     BlockDel &S = blk();
     DelaunayCtx &c = S.C;
     WarpCav &W = my_cav();
+    int *const cnt = GRID ? c.cnt : S.cnt;
+    if (GRID) __builtin_assume(__isGlobal(cnt));
     const int *Pi = SM ? sm_sites() : c.Pi;
     int *const tet = c.tet, *const claim = c.claim, *const hint = c.hint;
     const int *const order = c.order;
@@ -216,7 +220,7 @@ template <bool SM> __device__ __noinline__ int w2_locate_and_claim(int rank, int
         ix = ix < 0 ? 0 : (ix >= g ? g - 1 : ix); iy = iy < 0 ? 0 : (iy >= g ? g - 1 : iy); iz = iz < 0 ? 0 : (iz >= g ? g - 1 : iz);
         t = hint[(ix * g + iy) * g + iz];
     }
-    if (t < 0) t = S.cnt[C_RECENT];
+    if (t < 0) t = cnt[C_RECENT];
     int4 v, nb;
     int dead = 0;
 #pragma unroll 1
@@ -226,11 +230,11 @@ template <bool SM> __device__ __noinline__ int w2_locate_and_claim(int rank, int
         if (v.x == T_DEAD) {                // a dead tet forwards to a tet of the star that replaced it
             dead++;
             if (dead > 200) return ST_ERR;
-            t = dead == 64 ? S.cnt[C_RECENT] : nb.x;
+            t = dead == 64 ? cnt[C_RECENT] : nb.x;
             continue;
         }
         if (steps - dead >= WALK_CAP) {     // bound the claim phase: go on from here in the next sub-round
-            if (lane == 0) { S.resume[threadIdx.x >> 5] = t; atomicAdd(&S.cnt[C_NWALK], steps - dead); atomicAdd(&S.cnt[C_NHOP], dead); }
+            if (lane == 0) { S.resume[threadIdx.x >> 5] = t; atomicAdd(&cnt[C_NWALK], steps - dead); atomicAdd(&cnt[C_NHOP], dead); }
             return ST_LOST;
         }
         const int k = inf_slot4(v);
@@ -254,7 +258,7 @@ template <bool SM> __device__ __noinline__ int w2_locate_and_claim(int rank, int
         const unsigned dupm = __ballot_sync(FPK_FULL, dup) & 0xfu, neg = __ballot_sync(FPK_FULL, o < 0) & 0xfu;
         if (dupm) { if (lane == 0) S.resume[threadIdx.x >> 5] = -1; *ncav_out = comp4(v, __ffs(dupm) - 1); return ST_DUP; }      // coincident site: reports the vertex it duplicates
         if (!neg) {
-            if (lane == 0) { atomicAdd(&S.cnt[C_NWALK], steps - dead + 1); atomicAdd(&S.cnt[C_NATTEMPT], 1); atomicAdd(&S.cnt[C_NHOP], dead); }
+            if (lane == 0) { atomicAdd(&cnt[C_NWALK], steps - dead + 1); atomicAdd(&cnt[C_NATTEMPT], 1); atomicAdd(&cnt[C_NHOP], dead); }
             break;
         }
         t = comp4(nb, __ffs(neg) - 1);
@@ -320,7 +324,7 @@ template <bool SM> __device__ __noinline__ int w2_locate_and_claim(int rank, int
         __syncwarp();
         if (lostm) { *ncav_out = ncav; return ST_LOST; }
     }
-    if (lane == 0) atomicAdd(&S.cnt[C_NLEVEL], nlev);
+    if (lane == 0) atomicAdd(&cnt[C_NLEVEL], nlev);
     *ncav_out = ncav;
     return ST_CLAIMED;
 }
@@ -360,11 +364,13 @@ __device__ __forceinline__ void w2_reset_claims(int ncav)
 }
 
 // a winner replaces its cavity (in W) by the star of p. Returns a new tet (the warp's next walk starts there) or -1.
-__device__ __noinline__ int w2_commit_insertion(int rank, int ncav, int popstack)
+template <bool GRID = false> __device__ __noinline__ int w2_commit_insertion(int rank, int ncav, int popstack)
 {
     BlockDel &S = blk();
     DelaunayCtx &c = S.C;
     WarpCav &W = my_cav();
+    int *const gc = GRID ? c.cnt : S.cnt;       // the triangulation counters (global memory in a grid-wide run)
+    if (GRID) __builtin_assume(__isGlobal(gc));
     int *const tet = c.tet, *const claim = c.claim, *const mark = c.mark, *const hint = c.hint;
     int *const popst = c.freest[popstack], *const pushst = c.freest[popstack ^ 1];
     __builtin_assume(__isGlobal(tet)); __builtin_assume(__isGlobal(claim)); __builtin_assume(__isGlobal(mark)); __builtin_assume(__isGlobal(hint));
@@ -385,12 +391,12 @@ __device__ __noinline__ int w2_commit_insertion(int rank, int ncav, int popstack
         if (!m) continue;
         const int cnt = __popc(m), my = __popc(m & ((1u << lane) - 1u));
         int fb = 0;
-        if (lane == 0) fb = atomicAdd(&S.cnt[C_NFREE0 + popstack], -cnt);
+        if (lane == 0) fb = atomicAdd(&gc[C_NFREE0 + popstack], -cnt);
         fb = __shfl_sync(FPK_FULL, fb, 0);
         const int fi = fb - 1 - my;                                          // index into the free stack, < 0: take a fresh slot
         const unsigned fresh = __ballot_sync(FPK_FULL, isrim && fi < 0);
         int nbase = 0;
-        if (fresh && lane == 0) nbase = atomicAdd(&S.cnt[C_NTET], __popc(fresh));
+        if (fresh && lane == 0) nbase = atomicAdd(&gc[C_NTET], __popc(fresh));
         nbase = __shfl_sync(FPK_FULL, nbase, 0);
         if (isrim) {
             int nt = fi >= 0 ? popst[fi] : nbase + __popc(fresh & ((1u << lane) - 1u));
@@ -425,7 +431,7 @@ __device__ __noinline__ int w2_commit_insertion(int rank, int ncav, int popstack
         }
         nrim += cnt;
     }
-    if (__any_sync(FPK_FULL, bad)) { if (lane == 0) S.cnt[C_STATUS] = DERR_CAPACITY; return -1; }
+    if (__any_sync(FPK_FULL, bad)) { if (lane == 0) gc[C_STATUS] = DERR_CAPACITY; return -1; }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) mynew = min(mynew, __shfl_xor_sync(FPK_FULL, mynew, d));
     const int firstnew = mynew;
@@ -454,7 +460,7 @@ __device__ __noinline__ int w2_commit_insertion(int rank, int ncav, int popstack
     __syncwarp();
     // ---- pass C: the cavity dies; its slots go to the stack the NEXT sub-round pops ---------------------------------------------------
     int base = 0;
-    if (lane == 0) base = atomicAdd(&S.cnt[C_NFREE0 + (popstack ^ 1)], ncav);
+    if (lane == 0) base = atomicAdd(&gc[C_NFREE0 + (popstack ^ 1)], ncav);
     base = __shfl_sync(FPK_FULL, base, 0);
 #pragma unroll 1
     for (int i = lane; i < ncav; i += 32) {
@@ -469,7 +475,7 @@ __device__ __noinline__ int w2_commit_insertion(int rank, int ncav, int popstack
         int ix = (int)((double)e[0] * c.hinv), iy = (int)((double)e[1] * c.hinv), iz = (int)((double)e[2] * c.hinv);
         ix = ix < 0 ? 0 : (ix >= g ? g - 1 : ix); iy = iy < 0 ? 0 : (iy >= g ? g - 1 : iy); iz = iz < 0 ? 0 : (iz >= g ? g - 1 : iz);
         hint[(ix * g + iy) * g + iz] = firstnew;
-        S.cnt[C_RECENT] = firstnew;
+        gc[C_RECENT] = firstnew;
     }
     return firstnew;
 }

@@ -319,6 +319,7 @@ __global__ void __launch_bounds__(FPK_K1_THREADS, FPK_K1_MINBLOCKS) k_delaunay_f
         const StructDev S = B.S[k];
         const int n = S.nsites;
         int *counts = B.counts + (size_t)k * CNT_STRIDE;
+        if (n > B.k1_max_sites) continue;          // done by the whole GPU (k_delaunay_grid)
         if (n < 4) {
             if (tid == 0) { counts[CNT_TETS] = 0; counts[CNT_SPHERES] = 0; counts[CNT_STATUS] = FPK_ERR_DEGENERATE; }
             continue;

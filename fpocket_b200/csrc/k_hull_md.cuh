@@ -1,6 +1,7 @@
 // K4b: convex-hull volume of a pocket's sphere centres; K5: mdpocket grid scatter.
 #pragma once
 #include "k_delaunay.cuh"
+#include "k_delaunay_grid.cuh"
 #include "k_pockets.cuh"
 #include "hull_warp.cuh"
 

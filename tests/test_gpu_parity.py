@@ -255,6 +255,75 @@ def test_large_structure_sites_in_global_memory():
     assert rc == 0 and np.array_equal(r["tets"], tets)
 
 
+def test_grid_wide_delaunay_equals_oracle():
+    """BASELINE configs[3] path: from 12,000 sites on (2,500 for a lone structure) ONE triangulation is built by every block of a
+    cooperative launch (csrc/k_delaunay_grid.cuh) instead of one block. 60,000 heavy atoms: the tetrahedra are the oracle's, as a set."""
+    api = _api()
+    st = _synth(20269310, 60000)
+    p = api.default_params()
+    p.want_tets = 1
+    r = api.detect(st, p)
+    assert r["status"] == 0 and r["n_sites"] == st.natoms > 59000
+    _, ki, _ = O.sites(st)
+    rc, tets, _ = O.delaunay(ki)
+    assert rc == 0 and r["n_tets"] == len(tets)
+    assert np.array_equal(r["tets"], tets)
+
+
+def test_grid_wide_and_block_paths_in_one_batch(monkeypatch):
+    """A batch that mixes both routes (the threshold lowered so that two of five structures take the grid-wide kernel): every result, the
+    whole record, equals the oracle; and the same structures through the other route give the same bytes."""
+    api = _api()
+    sts = [_synth(20269320 + i, n) for i, n in enumerate((2300, 6100, 2500, 7400, 3100))]
+    p = api.default_params()
+    p.want_tets = 1
+    want = [O.search_pocket(st, p, tets=None, rng_mode=O.RNG_PHILOX) for st in sts]
+    monkeypatch.setenv("FPK_GRID_MIN_SITES", "6000")
+    got = api.detect_batch(sts, p)
+    monkeypatch.setenv("FPK_GRID_MIN_SITES", "1000000")          # everything by one block each
+    got_block = api.detect_batch(sts, p)
+    monkeypatch.setenv("FPK_GRID_MIN_SITES", "100")              # everything by the whole GPU, one after the other
+    got_grid = api.detect_batch(sts, p)
+    for k, (st, o) in enumerate(zip(sts, want)):
+        for r in (got[k], got_block[k], got_grid[k]):
+            assert np.array_equal(r["tets"], got_block[k]["tets"])
+            assert_same_result(r, o, "mixed routes %d" % k)
+
+
+def test_large_complex_has_the_empty_sphere_property():
+    """150,000 heavy atoms (BASELINE configs[3], the bench's generator and seed), the whole pipeline: 1,039,790 tetrahedra equal to the
+    oracle's, every array of the result equal to the oracle's bit for bit (the oracle needs ~30 s for it), plus properties that do not
+    depend on any oracle - every kept alpha sphere touches its four atoms, holds no atom, has its radius inside the window."""
+    api = _api()
+    st = _synth(20260401, 150000)
+    p = api.default_params()
+    p.want_tets = 1
+    r = api.detect(st, p)
+    assert r["status"] == 0 and r["n_sites"] == st.natoms
+    o = O.search_pocket(st, p, tets=None, rng_mode=O.RNG_PHILOX)
+    _, ki, _ = O.sites(st)
+    rc, tets, _ = O.delaunay(ki)
+    assert rc == 0 and np.array_equal(r["tets"], tets)
+    assert_same_result(r, o, "150k")
+    assert 6.0 * st.natoms < r["n_tets"] < 7.5 * st.natoms
+    ns = r["n_spheres"]
+    assert ns > 0.2 * st.natoms and r["n_pockets"] > 100
+    xyz = np.stack([st.x, st.y, st.z], -1).astype(np.float64)
+    rng = np.random.default_rng(2)
+    pick = rng.choice(ns, size=400, replace=False)
+    c, rad = r["sph_xyzr"][pick, :3].astype(np.float64), r["sph_xyzr"][pick, 3].astype(np.float64)
+    for q in range(0, 400, 50):
+        d = np.linalg.norm(xyz[None] - c[q:q + 50, None], axis=2)
+        dn = np.take_along_axis(d, r["sph_neigh"][pick[q:q + 50]].astype(np.int64), 1)
+        assert np.all(np.abs(dn - rad[q:q + 50, None]) < 2e-3)
+        assert np.all(d.min(1) > rad[q:q + 50] - 2e-3)
+    assert np.all((r["sph_xyzr"][:, 3] >= 3.4 - 1e-3) & (r["sph_xyzr"][:, 3] <= 6.2 + 1e-3))
+    keys = r["sph_neigh"]
+    assert len(np.unique(keys, axis=0)) == ns            # no sphere twice
+    order = np.lexsort((keys[:, 3], keys[:, 2], keys[:, 1], keys[:, 0]))
+    assert np.array_equal(order, np.arange(ns))          # canonical order: ascending site tuples
+
+
 def test_edge_cases():
     from fpocket_b200 import capi
     api = _api()
