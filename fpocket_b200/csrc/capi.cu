@@ -276,6 +276,8 @@ struct fpk_batch {
     std::vector<int> big;              // indices of the former
     GridDel *dGrid = nullptr; int nGridBlocks = 0; size_t grid_dsm = 0;
     DelScratch hGridX;
+    ClusterGridScratch hCluG; int nCluGridBlocks = 0;
+    AtomGrid AG;                       // cell grid over the heavy atoms of every structure (K4's surrounding atoms)
     int md_shared_props = 0;           // mdpocket: all frames share the property arrays
     // stage 1 device
     Arena A1, A2;
@@ -473,11 +475,21 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
         b->dClu = a.take<ClusterScratch>(b->nClu);
         b->Lg.lig_off = a.take<int>(n + 1); b->Lg.lig_idx = a.take<int>(b->tot_lig + 1); b->Lg.lig_mol = a.take<int>(b->tot_lig + 1);
         b->Lg.name_key = b->has_names ? a.take<int>(b->tot_atoms + 1) : nullptr;
+        int *cbase = a.take<int>(n + 1);
+        b->AG.cbase = cbase;
         a.take<char>(0);
         b->in_bytes = a.used;                      // everything above is input: mirrored in pinned host memory, one copy
         if (b->tot_lig > 0) {
             b->Lg.xpos = a.take<int>(b->tot_sphcap + n + 1); b->Lg.ipos = a.take<int>(b->tot_atoms + n + 1);
             b->Lg.ilist = a.take<int>(b->tot_atoms + n + 1); b->Lg.ni = a.take<int>(n);
+        }
+        {
+            long long cells = 0;
+            for (int k = 0; k < n; k++) cells += (b->S[k].natoms_w ? b->S[k].natoms_w : b->S[k].natoms) / 4 + 66;
+            b->AG.cellend = a.take<int>((size_t)cells + 2);
+            b->AG.cellatom = a.take<int>((size_t)b->tot_w + (size_t)b->tot_atoms + 2);      // addressed at w_off, or tot_w + atom_off
+            b->AG.same_base = (int)b->tot_w; b->AG.min_atoms = K4_GRID_MIN_ATOMS;
+            b->AG.geom = a.take<float4>(n); b->AG.dims = a.take<int4>(n);
         }
         B.s_xyzr = a.take<float4>(b->tot_sphcap); B.s_bary = a.take<float>(3 * b->tot_sphcap);
         B.s_neigh = a.take<int4>(b->tot_sphcap); B.s_key = a.take<int4>(b->tot_sphcap);
@@ -490,10 +502,14 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
         if (!b->big.empty()) {
             b->dGrid = a.take<GridDel>(1);
             del_scratch_layout(a, b->hGridX, b->max_sites_big, b->max_sphcap_big, FPK_K1_THREADS, true);
+            b->hCluG.cellcnt = a.take<int>(CELLMAX + 2); b->hCluG.cellsph = a.take<int>(b->max_sphcap_big + 1);
+            b->hCluG.tmp = a.take<int>(b->max_sphcap_big + 2); b->hCluG.bb = a.take<float>(6 * (size_t)g_sms * 8);
+            b->hCluG.glob = a.take<int>(4); b->hCluG.scap = b->max_sphcap_big;
         }
         for (int i = 0; i < b->nClu; i++) {
-            hClu[i].cellcnt = a.take<int>(CELLMAX + 2); hClu[i].cellsph = a.take<int>(b->max_sphcap + 1);
-            hClu[i].tmp = a.take<int>(b->max_sphcap + 2); hClu[i].scap = b->max_sphcap;
+            const int sc = std::max(64, b->max_sphcap_small);
+            hClu[i].cellcnt = a.take<int>(CELLMAX + 2); hClu[i].cellsph = a.take<int>(sc + 1);
+            hClu[i].tmp = a.take<int>(sc + 2); hClu[i].scap = sc;
         }
     });
     if (rc) return rc;
@@ -505,11 +521,17 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
         occg = std::max(1, std::min(occg, FPK_K1_MINBLOCKS));
         if (const char *e = getenv("FPK_GRID_BLOCKS_PER_SM")) occg = std::max(1, std::min(occg, atoi(e)));      // tuning knob (profiles/)
         b->nGridBlocks = g_sms * occg;
+        int occc = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occc, k_cluster_grid, 256, 0);
+        b->nCluGridBlocks = g_sms * std::max(1, std::min(occc, 4));
     }
     std::vector<int> order(n);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return b->S[x].nsites > b->S[y].nsites; });
+    std::vector<int> hcb(n + 1, 0);
+    for (int k = 0; k < n; k++) hcb[k + 1] = hcb[k] + (b->S[k].natoms_w ? b->S[k].natoms_w : b->S[k].natoms) / 4 + 66;
     if (!in) {          // mdpocket skeleton: descriptors only; properties and coordinates are uploaded by the caller
+        CK(cudaMemcpy(const_cast<int *>(b->AG.cbase), hcb.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(b->dS, b->S.data(), sizeof(StructDev) * n, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(b->d_order, order.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(b->dDel, hDel.data(), sizeof(DelScratch) * b->nDel, cudaMemcpyHostToDevice));
@@ -532,6 +554,7 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
         memcpy(mir(b->d_order), order.data(), sizeof(int) * n);
         memcpy(mir(b->dDel), hDel.data(), sizeof(DelScratch) * b->nDel);
         memcpy(mir(b->dClu), hClu.data(), sizeof(ClusterScratch) * b->nClu);
+        memcpy(mir(b->AG.cbase), hcb.data(), sizeof(int) * (n + 1));
         float *hx = (float *)mir(B.ax), *hy = (float *)mir(B.ay), *hz = (float *)mir(B.az), *hr = (float *)mir(B.arad), *he = (float *)mir(B.aen),
               *hb = (float *)mir(B.abf);
         int *hid = (int *)mir(B.aid), *hres = (int *)mir(B.ares), *hs2a = (int *)mir(B.site2atom);
@@ -617,9 +640,15 @@ static int batch_run(fpk_batch *b)
     }
     k_delaunay_filter<<<b->nDel, FPK_K1_THREADS, b->k1_dsm>>>(B, b->dDel, b->k1_picap);
     CK(cudaEventRecord(b->ev[1]));
+    for (int kb : b->big) {
+        void *args[] = {(void *)&B, (void *)&b->hCluG, (void *)&kb};
+        CK(cudaLaunchCooperativeKernel((void *)k_cluster_grid, dim3(b->nCluGridBlocks), dim3(256), args, 0, cudaStreamPerThread));
+        b->launches++;
+    }
     k_cluster<<<b->nClu, 256>>>(B, b->dClu, b->d_counters + 1);
     const bool lig = b->tot_lig > 0 && b->prm.skip_clustering == 0;
     if (lig) { k_ligand_select<<<n, 256>>>(B, b->Lg); b->launches++; }
+    if (b->prm.do_asa_and_volume) { k_atom_grid<<<n, 256>>>(B, b->AG); b->launches++; }
     CK(cudaEventRecord(b->ev[2]));
     b->launches += 2;
     // ---- the one host round trip: per-structure counts -> exact sizes of the pocket-level arrays -----------------------
@@ -669,7 +698,9 @@ static int batch_run(fpk_batch *b)
         b->d_hull_fb = a.take<int>(NC + 1);
         if (b->tot_lig > 0) b->Lg.crit = a.take<float>(4 * NC + 4);
         if (full) for (int i = 0; i < b->nHull; i++) del_scratch_layout(a, hHull[i], max_ns, 0, HULL_THREADS, false);
-        for (int i = 0; i < b->nDesc; i++) hDesc[i].sa = a.take<int>(b->max_w + 1);
+        size_t sacap = 64;
+        while (sacap < (size_t)b->max_w + 1) sacap <<= 1;          // the list is sorted by a bitonic network: padded to a power of two
+        for (int i = 0; i < b->nDesc; i++) hDesc[i].sa = a.take<int>(sacap);
     });
     if (rc) return rc;
     Pk.clbase = b->d_clbase; Pk.sbase = b->d_sbase; Pk.total_clusters = (int)NC;
@@ -693,7 +724,7 @@ static int batch_run(fpk_batch *b)
             b->launches += 2;
         }
         CK(cudaEventRecord(b->ev[4]));
-        k_descriptors<<<b->nDesc, K4_THREADS>>>(B, Pk, b->dDesc, b->d_counters + 3);
+        k_descriptors<<<b->nDesc, K4_THREADS>>>(B, Pk, b->dDesc, b->d_counters + 3, b->AG);
         CK(cudaEventRecord(b->ev[5]));
         k_finalize<<<n, 128>>>(B, Pk);
         if (full) { k_atom_fx<<<(unsigned)NC, 64>>>(B, Pk); b->launches++; }
