@@ -35,13 +35,14 @@ class FpkParams(C.Structure):
         ("do_asa_and_volume", C.c_int32), ("skip_clustering", C.c_int32), ("xpocket_active", C.c_int32),
         ("min_n_explicit_pocket_atoms", C.c_int32), ("want_tets", C.c_int32), ("mc_seed", C.c_uint64),
         ("lig_interface_dist", C.c_float), ("lig_crit_dist", C.c_float),
+        ("distance_measure", C.c_int32), ("lig_interface_method", C.c_int32),
     ]
 
 
 def default_params(**kw):
     """init_def_fparams (reference src/fparams.c:63-95, headers/fparams.h:33-63)."""
     p = FpkParams(np.float32(3.4), np.float32(6.2), np.float32(2.4), 0.0, np.float32(0.7),
-                  3, 300, 15, 1, 0, 0, 4, 0, 20260101, np.float32(4.0), np.float32(3.0))
+                  3, 300, 15, 1, 0, 0, 4, 0, 20260101, np.float32(4.0), np.float32(3.0), 0, 1)
     for k, v in kw.items():
         setattr(p, k, v)
     return p
@@ -88,7 +89,7 @@ class FpkResult(C.Structure):
         ("cl_atoms", _ip), ("desc", C.POINTER(FpkDesc)), ("n_pockets", C.c_int32), ("rank_to_cluster", _ip),
         ("atom_fx", _fp), ("_owner", C.c_void_p),
         ("n_xspheres", C.c_int32), ("xspheres", _ip), ("xdesc", C.POINTER(FpkDesc)), ("n_iface", C.c_int32), ("iface_atoms", _ip),
-        ("pk_ovlp", _fp), ("pk_dst", _fp), ("pk_c4", _fp), ("pk_c5", _fp),
+        ("pk_ovlp", _fp), ("pk_dst", _fp), ("pk_c4", _fp), ("pk_c5", _fp), ("lig_volume", C.c_float),
     ]
 
 
@@ -124,6 +125,7 @@ def result_to_dict(r, natoms):
         d["iface_atoms"] = _arr(r.iface_atoms, (r.n_iface,), np.int32)
         for k in ("pk_ovlp", "pk_dst", "pk_c4", "pk_c5"):
             d[k] = _arr(getattr(r, k), (npk,), np.float32)
+        d["lig_volume"] = float(r.lig_volume)
     return d
 
 

@@ -72,6 +72,7 @@ extern "C" void fpk_default_params(fpk_params *p)
     p->min_apol_neigh = 3; p->nb_mcv_iter = 300; p->min_pock_nb_asph = 15;
     p->do_asa_and_volume = 1; p->min_n_explicit_pocket_atoms = 4; p->mc_seed = 20260101ull;
     p->lig_interface_dist = (float)4.0; p->lig_crit_dist = (float)3.0;
+    p->distance_measure = 'e'; p->lig_interface_method = 1;
 }
 
 // asa.c:438-454 get_points_on_sphere(100): computed with the host libm exactly as the reference does
@@ -270,6 +271,7 @@ struct fpk_batch {
     std::vector<int> lig_n;
     LigDev Lg;                         // dpocket ligand queries (tot_lig > 0)
     std::vector<int> h_ni;
+    std::vector<float> h_ligvol;
     int max_sites = 0, max_w = 0, max_sphcap = 0;
     // structures above k1_max_sites are triangulated one at a time by the WHOLE GPU (k_delaunay_grid), the others by one block each (K1)
     int k1_max_sites = 0x7fffffff, max_sites_big = 0, max_sphcap_big = 0, max_sphcap_small = 0;
@@ -294,6 +296,7 @@ struct fpk_batch {
     int *d_clbase = nullptr, *d_sbase = nullptr;
     DelScratch *dHull = nullptr; int nHull = 0;
     int *d_hull_fb = nullptr; int nHullWarp = 0;     // pockets the warp-per-pocket hull kernel hands to the Delaunay route
+    unsigned char *d_small_done = nullptr;           // clusters k_descriptors_small (one warp each) has described
     DescScratch *dDesc = nullptr; int nDesc = 0;
     // compact outputs (device)
     float4 *c_xyzr = nullptr; float *c_bary = nullptr; int4 *c_neigh = nullptr; uint8_t *c_type = nullptr; int *c_cluster = nullptr;
@@ -696,7 +699,8 @@ static int batch_run(fpk_batch *b)
         b->c_cl_off = a.take<int>(NC + n + 1);
         b->dHull = a.take<DelScratch>(b->nHull); b->dDesc = a.take<DescScratch>(b->nDesc);
         b->d_hull_fb = a.take<int>(NC + 1);
-        if (b->tot_lig > 0) b->Lg.crit = a.take<float>(4 * NC + 4);
+        b->d_small_done = a.take<unsigned char>(NC + 1);
+        if (b->tot_lig > 0) { b->Lg.crit = a.take<float>(4 * NC + 4); b->Lg.lig_vol = a.take<float>(n + 1); }
         if (full) for (int i = 0; i < b->nHull; i++) del_scratch_layout(a, hHull[i], max_ns, 0, HULL_THREADS, false);
         size_t sacap = 64;
         while (sacap < (size_t)b->max_w + 1) sacap <<= 1;          // the list is sorted by a bitonic network: padded to a power of two
@@ -724,7 +728,15 @@ static int batch_run(fpk_batch *b)
             b->launches += 2;
         }
         CK(cudaEventRecord(b->ev[4]));
-        k_descriptors<<<b->nDesc, K4_THREADS>>>(B, Pk, b->dDesc, b->d_counters + 3, b->AG);
+        // small clusters (fewer than min_pock_nb_asph spheres: nine in ten) by one warp each, the others by one block each
+        static const int small_enable = getenv("FPK_K4_SMALL") ? atoi(getenv("FPK_K4_SMALL")) : 1;
+        CK(cudaMemsetAsync(b->d_small_done, 0, (size_t)NC + 1, cudaStreamPerThread));
+        if (small_enable) {
+            const int nsb = (int)std::max(1ll, std::min<long long>((NC + 32 * K4S_WARPS - 1) / (32 * K4S_WARPS), (long long)g_sms * 8));
+            k_descriptors_small<<<nsb, K4S_THREADS>>>(B, Pk, b->d_counters + 6, b->AG, b->d_small_done);
+            b->launches++;
+        }
+        k_descriptors<<<b->nDesc, K4_THREADS>>>(B, Pk, b->dDesc, b->d_counters + 3, b->AG, b->d_small_done);
         CK(cudaEventRecord(b->ev[5]));
         k_finalize<<<n, 128>>>(B, Pk);
         if (full) { k_atom_fx<<<(unsigned)NC, 64>>>(B, Pk); b->launches++; }
@@ -732,6 +744,7 @@ static int batch_run(fpk_batch *b)
     } else {
         CK(cudaEventRecord(b->ev[4])); CK(cudaEventRecord(b->ev[5]));
     }
+    if (lig) CK(cudaMemsetAsync(b->Lg.lig_vol, 0, sizeof(float) * (size_t)n, cudaStreamPerThread));
     if (lig && NC > 0) { k_ligand<<<n, 256>>>(B, Pk, b->Lg); b->launches++; }
     k_compact<<<n, 128>>>(B, b->d_sbase, b->c_xyzr, b->c_bary, b->c_neigh, b->c_type, b->c_cluster, b->c_cl_sph, b->c_cl_off, b->d_clbase);
     b->launches++;
@@ -804,9 +817,9 @@ static int batch_fetch(fpk_batch *b, fpk_result *out)
     float *crit = nullptr, *pk4 = nullptr;
     if (lig) {
         ilist = H->take<int>(NA + n + 1); crit = H->take<float>(4 * NC + 4); pk4 = H->take<float>(4 * NC + 4);
-        b->h_ni.resize(n);
+        b->h_ni.resize(n); b->h_ligvol.resize(n);
         if ((rc = d2h(b, ilist, b->Lg.ilist, NA + n)) || (rc = d2h(b, crit, b->Lg.crit, 4 * NC)) ||
-            (rc = d2h(b, b->h_ni.data(), b->Lg.ni, (size_t)n))) { delete H; return rc; }
+            (rc = d2h(b, b->h_ni.data(), b->Lg.ni, (size_t)n)) || (rc = d2h(b, b->h_ligvol.data(), b->Lg.lig_vol, (size_t)n))) { delete H; return rc; }
     }
     CK(wait_stream());
     if (b->B.tets_out) {
@@ -858,6 +871,7 @@ static int batch_fetch(fpk_batch *b, fpk_result *out)
         if (lig && in_has_lig(b, k)) {
             if (xp) { r.n_xspheres = c[CNT_NX]; r.xspheres = r.cl_sph + r.cl_off[nc - 1]; r.xdesc = r.desc + (nc - 1); }
             r.n_iface = b->h_ni[k]; r.iface_atoms = ilist + b->S[k].atom_off + k;
+            r.lig_volume = b->h_ligvol[k];
             float *o = pk4 + 4 * (size_t)c0;
             const int np = r.n_pockets;
             r.pk_ovlp = o; r.pk_dst = o + np; r.pk_c4 = o + 2 * np; r.pk_c5 = o + 3 * np;
@@ -964,6 +978,9 @@ extern "C" int fpk_detect_batch(const fpk_structure *in, int n, const fpk_params
 {
     if (!out) return fail(FPK_ERR_BAD_ARG, "null result array");
     if (!in || n <= 0 || !p) return fail(FPK_ERR_BAD_ARG, "fpk_detect_batch: bad arguments");
+    if (p->distance_measure != 0 && p->distance_measure != 'e' && p->distance_measure != 'b')
+        return fail(FPK_ERR_BAD_ARG, "distance measure '%c' is not supported (-e e or -e b; there is no CPU fallback)", p->distance_measure);
+    if (p->lig_interface_method < 0 || p->lig_interface_method > 2) return fail(FPK_ERR_BAD_ARG, "ligand interface method %d (dparams.h:41-44 knows 1 and 2)", p->lig_interface_method);
     int rc = ensure_init();
     if (rc) return rc;
     memset(out, 0, sizeof(fpk_result) * (size_t)n);      // whatever happens, every out[k] can be handed to fpk_result_free

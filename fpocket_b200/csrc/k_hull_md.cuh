@@ -291,6 +291,7 @@ struct LigDev {
     int *ilist;                // interface atoms (ascending) per structure at atom_off + k
     int *ni;                   // [nstruct]
     float *crit;               // [4 * total_clusters]: ovlp, dst, c4, c5 of the pocket ranked r of structure k at 4 * (clbase[k] + r)
+    float *lig_vol;            // [nstruct] Monte-Carlo volume of the ligand (atom.c:156)
 };
 enum { LIG_MAXMOL = 64 };
 
@@ -314,8 +315,26 @@ __global__ void __launch_bounds__(256) k_ligand_select(BatchDev B, LigDev G)
     int *xpos = G.xpos + S.sph_off + k, *ipos = G.ipos + S.atom_off + k, *ilist = G.ilist + S.atom_off + k;
     int *cl_off = B.cl_off + S.sph_off + k, *cl_sph = B.cl_sph + S.sph_off;
     const float dcrit = B.prm.lig_interface_dist;
+    const bool method2 = B.prm.lig_interface_method == 2;
     for (int i = tid; i <= na; i += nt) ipos[i] = 0;
     __syncthreads();
+    if (method2) {
+        // dparams.h:44 M_INTERFACE_METHOD2 (dpocket.c:331-336, neighbor.c:67 get_mol_atm_neigh): the atoms of the complex with dist() < dcrit to
+        // a ligand atom, the ligand's own atoms excluded. pdb is pdb_w_lig without the ligand, in the same order: index in pdb = index in
+        // pdb_w_lig minus the ligand atoms before it.
+        const int nwl = S.natoms_w ? S.natoms_w : S.natoms;
+        for (int a = tid; a < nwl; a += nt) {
+            int before = 0;
+            bool isl = false;
+            for (int l = 0; l < nl; l++) { before += lig[l] < a; isl |= lig[l] == a; }
+            const int pi = a - before;
+            if (isl || pi >= na) continue;
+            const float x = wx[W0 + a], y = wy[W0 + a], z = wz[W0 + a];
+            bool nearl = false;
+            for (int l = 0; l < nl && !nearl; l++) nearl = f_dist(x, y, z, wx[W0 + lig[l]], wy[W0 + lig[l]], wz[W0 + lig[l]]) < dcrit;
+            if (nearl) ipos[pi] = 1;
+        }
+    }
     for (int s = tid; s <= ns; s += nt) {
         int near = 0;
         if (s < ns) {
@@ -325,6 +344,7 @@ __global__ void __launch_bounds__(256) k_ligand_select(BatchDev B, LigDev G)
                 const float lx = wx[W0 + lig[l]], ly = wy[W0 + lig[l]], lz = wz[W0 + lig[l]];
                 if (f_dist(v.x, v.y, v.z, lx, ly, lz) < dcrit) {
                     near = 1;
+                    if (method2) continue;
                     const int a[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                     for (int j = 0; j < 4; j++)         // neighbor.h:30 M_INTERFACE_SEARCH_DIST 8.0
@@ -354,7 +374,7 @@ __global__ void __launch_bounds__(256) k_ligand(BatchDev B, PocketDev Pk, LigDev
     const StructDev S = B.S[k];
     const int *counts = B.counts + (size_t)k * CNT_STRIDE;
     const int L0 = G.lig_off[k], nl = G.lig_off[k + 1] - L0;
-    if (nl <= 0 || counts[CNT_STATUS] != FPK_OK) return;
+    if (nl <= 0 || (counts[CNT_STATUS] != FPK_OK && counts[CNT_STATUS] != FPK_ERR_NO_POCKETS)) return;
     const int W0 = S.natoms_w ? S.w_off : S.atom_off;
     const float *wx = S.natoms_w ? B.wx : B.ax, *wy = S.natoms_w ? B.wy : B.ay, *wz = S.natoms_w ? B.wz : B.az;
     const int *lig = G.lig_idx + L0, *mol = G.lig_mol + L0;
@@ -362,13 +382,46 @@ __global__ void __launch_bounds__(256) k_ligand(BatchDev B, PocketDev Pk, LigDev
     const int *ilist = G.ilist + S.atom_off + k;
     const int ni = G.ni[k];
     const float ccrit = B.prm.lig_crit_dist;
-    const int npk = counts[CNT_POCKETS];
+    const int npk = counts[CNT_STATUS] == FPK_OK ? counts[CNT_POCKETS] : 0;
     const int *cl_off = B.cl_off + S.sph_off + k, *cl_sph = B.cl_sph + S.sph_off;
     const int *rank = Pk.rank_to_cluster + Pk.sbase[k] + k;
     const fpk_desc *D = Pk.desc + Pk.clbase[k];
     int nmol = 0;
     for (int l = 0; l < nl; l++) nmol = max(nmol, mol[l] + 1);
     nmol = min(nmol, LIG_MAXMOL);
+    if (wid == nwarp - 1) {
+        // atom.c:156 get_mol_volume_ptr(ligand, nb_mcv_iter) (dpocket.c:245): box with the reference's else-if updates (one lane, in order),
+        // samples over the lanes, first-hit loop over the ligand's atoms; Philox counter (sample, 0x11A, 0, 0), key mc_seed
+        const float *wr = S.natoms_w ? B.wrad : B.arad;
+        const int WQ0 = S.natoms_w ? S.w_off : S.prop_off;
+        float xmin = 0, xmax = 0, ymin = 0, ymax = 0, zmin = 0, zmax = 0, t;
+        for (int l = 0; l < nl; l++) {
+            const float x = wx[W0 + lig[l]], y = wy[W0 + lig[l]], z = wz[W0 + lig[l]], rr = wr[WQ0 + lig[l]];
+            if (l == 0) { xmin = x - rr; xmax = x + rr; ymin = y - rr; ymax = y + rr; zmin = z - rr; zmax = z + rr; }
+            else {
+                if (xmin > (t = x - rr)) xmin = t; else if (xmax < (t = x + rr)) xmax = t;
+                if (ymin > (t = y - rr)) ymin = t; else if (ymax < (t = y + rr)) ymax = t;
+                if (zmin > (t = z - rr)) zmin = t; else if (zmax < (t = z + rr)) zmax = t;
+            }
+        }
+        const float vbox = (xmax - xmin) * (ymax - ymin) * (zmax - zmin);
+        const int niter = B.prm.nb_mcv_iter;
+        int nb_in = 0;
+        for (int i = lane; i < niter; i += 32) {
+            unsigned o[4];
+            philox4x32((unsigned)i, 0x11Au, 0u, 0u, (unsigned)B.prm.mc_seed, (unsigned)(B.prm.mc_seed >> 32), o);
+            const float xr = unif_from_bits(o[0] >> 1, xmin, xmax), yr = unif_from_bits(o[1] >> 1, ymin, ymax), zr = unif_from_bits(o[2] >> 1, zmin, zmax);
+            bool in = false;
+            for (int l = 0; l < nl && !in; l++) {
+                const float xt = wx[W0 + lig[l]] - xr, yt = wy[W0 + lig[l]] - yr, zt = wz[W0 + lig[l]] - zr, rr = wr[WQ0 + lig[l]];
+                in = (rr * rr) > (xt * xt + yt * yt + zt * zt);
+            }
+            nb_in += in;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) nb_in += __shfl_xor_sync(0xffffffffu, nb_in, d);
+        if (lane == 0) G.lig_vol[k] = niter > 0 ? ((float)nb_in) / ((float)niter) * vbox : 0.0f;
+    }
     for (int r = wid; r < npk; r += nwarp) {
         const int c = rank[r], off = cl_off[c], n = cl_off[c + 1] - off;
         const int *Lp = cl_sph + off;

@@ -64,6 +64,25 @@ __device__ __forceinline__ void uf_union(int *par, int a, int b)
     }
 }
 
+// the clustering distance of two sphere centres (f32 promoted to f64 as prepare_vertices_for_cluster_lib does, voronoi.c:283):
+// -e e  clusterlib.c:933-1018 euclid      sqrt(sum of squares)
+// -e b  clusterlib.c:1022-1083 cityblock  (|dx| + |dy| + |dz|) / 3 - the MEAN of the absolute differences (weights 1, tweight 3)
+__device__ __forceinline__ double pair_distance(bool cityblock, double xi, double yi, double zi, const float4 &w)
+{
+    double result = 0.;
+    if (cityblock) {
+        double tweight = 0;
+        double term = xi - (double)w.x; result = result + 1.0 * fabs(term); tweight += 1.0;
+        term = yi - (double)w.y; result = result + 1.0 * fabs(term); tweight += 1.0;
+        term = zi - (double)w.z; result = result + 1.0 * fabs(term); tweight += 1.0;
+        return result / tweight;
+    }
+    double term = xi - (double)w.x; result += term * term;
+    term = yi - (double)w.y; result += term * term;
+    term = zi - (double)w.z; result += term * term;
+    return sqrt(result);
+}
+
 __global__ void __launch_bounds__(256) k_cluster(BatchDev B, const ClusterScratch *scratch, int *work_counter)
 {
     __shared__ int s_k, s_sm[40], s_dims[4];
@@ -115,7 +134,9 @@ __global__ void __launch_bounds__(256) k_cluster(BatchDev B, const ClusterScratc
         if (tid == 0) {
             for (int w = 1; w < (nt >> 5); w++)
                 for (int c = 0; c < 3; c++) { mn[c] = fminf(mn[c], s_mn[w][c]); mx[c] = fmaxf(mx[c], s_mx[w][c]); }
-            float cell = B.prm.clust_max_dist * 1.001f + 1e-4f;      // >= cut, so neighbours are within +-1 cell
+            // cell edge >= the largest per-axis difference a linked pair can have, so neighbours are within +-1 cell: the cut itself for the
+            // euclidean distance, 3 x the cut for the city-block MEAN (|dx| <= |dx| + |dy| + |dz| = 3 x mean)
+            float cell = (B.prm.distance_measure == 'b' ? 3.0f : 1.0f) * B.prm.clust_max_dist * 1.001f + 1e-4f;
             int d0, d1, d2;
             for (;;) {
                 d0 = (int)((mx[0] - mn[0]) / cell) + 1; d1 = (int)((mx[1] - mn[1]) / cell) + 1; d2 = (int)((mx[2] - mn[2]) / cell) + 1;
@@ -150,6 +171,7 @@ __global__ void __launch_bounds__(256) k_cluster(BatchDev B, const ClusterScratc
         // cellcnt[c] now holds the END of cell c (= old start of c+1); start of c = end of c-1
         // ---- union over the  d <= cut  graph (clusterlib.c:933 euclid in f64 on the f32 centres) --------------------------
         const double cut = (double)B.prm.clust_max_dist;
+        const bool cityblock = B.prm.distance_measure == 'b';
         for (int i = tid; i < ns; i += nt) {
             float4 v = sx[i];
             int cid = X.tmp[i];
@@ -164,12 +186,7 @@ __global__ void __launch_bounds__(256) k_cluster(BatchDev B, const ClusterScratc
                             int j = X.cellsph[q];
                             if (j >= i) continue;
                             float4 w = sx[j];
-                            double result = 0.;
-                            double term = xi - (double)w.x; result += term * term;
-                            term = yi - (double)w.y; result += term * term;
-                            term = zi - (double)w.z; result += term * term;
-                            result = sqrt(result);
-                            if (!(result > cut)) uf_union(par, i, j);
+                            if (!(pair_distance(cityblock, xi, yi, zi, w) > cut)) uf_union(par, i, j);
                         }
                     }
         }
@@ -287,7 +304,7 @@ __global__ void __launch_bounds__(256) k_cluster_grid(BatchDev B, ClusterGridScr
     for (int c = 0; c < 3; c++) { mn[c] = 3e38f; mx[c] = -3e38f; }
     for (int b = 0; b < (int)gridDim.x; b++)
         for (int c = 0; c < 3; c++) { mn[c] = fminf(mn[c], __ldcg(&X.bb[6 * b + c])); mx[c] = fmaxf(mx[c], __ldcg(&X.bb[6 * b + 3 + c])); }
-    float cell = B.prm.clust_max_dist * 1.001f + 1e-4f;      // >= cut, so neighbours are within +-1 cell
+    float cell = (B.prm.distance_measure == 'b' ? 3.0f : 1.0f) * B.prm.clust_max_dist * 1.001f + 1e-4f;      // see k_cluster
     int d0, d1, d2;
     for (;;) {
         d0 = (int)((mx[0] - mn[0]) / cell) + 1; d1 = (int)((mx[1] - mn[1]) / cell) + 1; d2 = (int)((mx[2] - mn[2]) / cell) + 1;
@@ -317,6 +334,7 @@ __global__ void __launch_bounds__(256) k_cluster_grid(BatchDev B, ClusterGridScr
     grid.sync();
     // ---- union over the  d <= cut  graph (clusterlib.c:933 euclid in f64 on the f32 centres) ------------------------------------------
     const double cut = (double)B.prm.clust_max_dist;
+    const bool cityblock = B.prm.distance_measure == 'b';
     for (int i = gtid; i < ns; i += gnt) {
         const float4 v = sx[i];
         const int cid = X.tmp[i];
@@ -331,12 +349,7 @@ __global__ void __launch_bounds__(256) k_cluster_grid(BatchDev B, ClusterGridScr
                         const int j = X.cellsph[q];
                         if (j >= i) continue;
                         const float4 w = sx[j];
-                        double result = 0.;
-                        double term = xi - (double)w.x; result += term * term;
-                        term = yi - (double)w.y; result += term * term;
-                        term = zi - (double)w.z; result += term * term;
-                        result = sqrt(result);
-                        if (!(result > cut)) uf_union_cg(par, i, j);
+                        if (!(pair_distance(cityblock, xi, yi, zi, w) > cut)) uf_union_cg(par, i, j);
                     }
                 }
     }
@@ -505,7 +518,8 @@ __device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 96;" 
 // measurement build only (scripts/gpu_k4_split.sh): block cycles and counts of work items, [0,1] clusters below min_pock_nb_asph, [2,3] the others
 __device__ unsigned long long g_k4prof[12];      // [4..8]: the first kind by phase (fetch + contacted atoms, CSR, sums / surroundings / SASA, per-atom epilogue, record)
 #endif
-__global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, PocketDev Pk, const DescScratch *scratch, int *work_counter, AtomGrid AG)
+__global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, PocketDev Pk, const DescScratch *scratch, int *work_counter, AtomGrid AG,
+                                                               const unsigned char *small_done)
 {
     __shared__ int s_item, s_U, s_cnt[100], s_sm[40], s_segcnt[3], s_mcdim[4], s_mcmode, s_asanext, s_mcnext, s_nsa;
     __shared__ float s_mcbox[6], s_mch[3], s_bb[3][6];
@@ -543,6 +557,7 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
         __syncthreads();
         const int item = s_item;
         if (item >= Pk.total_clusters) return;
+        if (small_done && small_done[item]) continue;          // a small cluster that k_descriptors_small (one warp) has already described
         // (structure, cluster) of this work item
         int lo = 0, hi = B.nstruct;
 #if FPK_K4_SEARCH_NEAR
@@ -1149,6 +1164,411 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                 d.convex_hull_volume = D->convex_hull_volume;       // written by k_hull_warp / k_hull_volume before this kernel
                 *D = d;
             }
+        }
+    }
+}
+
+// ============================================= K4s: descriptors of the small clusters, one WARP each ==============================
+// Nine clusters in ten have fewer than min_pock_nb_asph spheres: refine.c:124 always drops them, yet all of them enter the min-max
+// normalisation (pocket.c:664-785) and their ASA pass leaves its marks on the atoms (asa.c:337,392-396), so they must be described.
+// k_descriptors gives each of them a block of four warps that mostly wait for one another (round 1: 38 % of K4's time at 127 k cycles per
+// small cluster). Here a warp does one such cluster from start to end with no block barrier - same loops, same operation order, so the
+// same bits: contacted atoms, the reference-order sums, surrounding atoms, the two SASA passes, the record. Spheres, the touching-sphere
+// masks (<= 32 spheres: one word per atom), the surrounding atoms and the burial candidates sit in 5.5 KB of shared memory per warp.
+// A cluster that does not fit (more than K4S_SA surrounding atoms, more than ASA_CAND candidates) is left to k_descriptors: `done` tells.
+enum { K4S_WARPS = 4, K4S_THREADS = 32 * K4S_WARPS, K4S_SA = 512, K4S_NMAX = 32 };
+struct SmallWarp {
+    float4 cand[ASA_CAND];
+    float4 sph[K4S_NMAX];
+    int sa[K4S_SA];
+    unsigned tmask[4 * K4S_NMAX];
+    unsigned char candapol[ASA_CAND];
+    fpk_desc d;
+    int cursor;
+};
+__global__ void __launch_bounds__(K4S_THREADS, 8) k_descriptors_small(BatchDev B, PocketDev Pk, int *chunk_counter, AtomGrid AG, unsigned char *done)
+{
+    __shared__ SmallWarp s_w[K4S_WARPS];
+    const int lane = threadIdx.x & 31;
+    SmallWarp &W = s_w[threadIdx.x >> 5];
+    const fpk_params &prm = B.prm;
+    const bool full = prm.do_asa_and_volume != 0;
+    const int nlimit = min(prm.min_pock_nb_asph, K4S_NMAX + 1);
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(chunk_counter, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= Pk.total_clusters) return;
+        int my_k = 0, my_off = 0, my_n = 0;
+        bool want = false;
+        if (base + lane < Pk.total_clusters) {
+            const int item = base + lane;
+            int lo = 0, hi = B.nstruct;
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (Pk.clbase[mid] <= item) lo = mid; else hi = mid; }
+            my_k = lo;
+            const int c = item - Pk.clbase[lo];
+            const int *cl_off = B.cl_off + B.S[lo].sph_off + lo;
+            my_off = cl_off[c]; my_n = cl_off[c + 1] - my_off;
+            const int *kc = B.counts + (size_t)lo * CNT_STRIDE;
+            const bool xp = kc[CNT_XP] == 1 && c == kc[CNT_CLUSTERS] - 1;
+            want = my_n < nlimit && my_n > 0 && !xp;
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, want);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int item = base + src, k = __shfl_sync(0xffffffffu, my_k, src), off = __shfl_sync(0xffffffffu, my_off, src),
+                      n = __shfl_sync(0xffffffffu, my_n, src);
+            const int c = item - Pk.clbase[k];
+            const StructDev S = B.S[k];
+            const int R = Pk.sbase[k] + off;
+            const int *L = B.cl_sph + S.sph_off + off;
+            const float4 *sx = B.s_xyzr + S.sph_off;
+            const int4 *sn = B.s_neigh + S.sph_off;
+            const uint8_t *sty = B.s_type + S.sph_off;
+            const float *sb = B.s_bary + 3 * (size_t)S.sph_off;
+            int *uat = Pk.cl_atoms + 4 * (size_t)R, *entu = Pk.ent_u + 4 * (size_t)R;
+            int *acc = Pk.acc + 16 * (size_t)R;
+            float *fxv = Pk.fx_val + 16 * (size_t)R;
+            fpk_desc *D = Pk.desc + item;
+            const int A0 = S.atom_off, Q0 = S.prop_off;
+            const bool same = S.same_pdb != 0;
+            const int W0 = S.natoms_w ? S.w_off : S.atom_off, WQ0 = S.natoms_w ? S.w_off : S.prop_off, nw = S.natoms_w ? S.natoms_w : S.natoms;
+            const unsigned whmask = S.natoms_w ? FPK_ATOM_H : FPK_ATOM_H1;
+            const float *wx = S.natoms_w ? B.wx : B.ax, *wy = S.natoms_w ? B.wy : B.ay, *wz = S.natoms_w ? B.wz : B.az;
+            const float *wr = S.natoms_w ? B.wrad : B.arad, *we = S.natoms_w ? B.wen : B.aen;
+            const uint8_t *wf = S.natoms_w ? B.wfl : B.afl;
+            __syncwarp();
+            if (lane < n) W.sph[lane] = sx[L[lane]];
+            for (int u = lane; u < 4 * K4S_NMAX; u += 32) W.tmask[u] = 0u;
+            __syncwarp();
+            // ---- 1. unique contacted atoms by atom id, first-seen order (pocket.c:1280-1320) -----------------------------------------
+            int U = 0;
+            for (int b0 = 0; b0 < 4 * n; b0 += 32) {
+                const int e = b0 + lane;
+                const bool valid = e < 4 * n;
+                int a = -1, id = -2 - lane;
+                if (valid) {
+                    const int4 q = sn[L[e >> 2]];
+                    const int j = e & 3;
+                    a = j == 0 ? q.x : (j == 1 ? q.y : (j == 2 ? q.z : q.w));
+                    id = B.aid[Q0 + a];
+                }
+                int dupidx = -1;
+                for (int u = 0; u < U; u++)
+                    if (B.aid[Q0 + uat[u]] == id) dupidx = u;
+                const unsigned m = __match_any_sync(0xffffffffu, id);
+                const int leader = __ffs(m) - 1;
+                const bool isnew = valid && dupidx < 0 && lane == leader;
+                const unsigned bal = __ballot_sync(0xffffffffu, isnew);
+                const int pos = U + __popc(bal & ((1u << lane) - 1u));
+                if (isnew) uat[pos] = a;
+                const int lp = __shfl_sync(0xffffffffu, pos, leader);
+                if (valid) { const int uu = dupidx >= 0 ? dupidx : lp; entu[e] = uu; atomicOr(&W.tmask[uu], 1u << (e >> 2)); }
+                U += __popc(bal);
+                __syncwarp();
+            }
+            for (int u = lane; u < 4 * U; u += 32) acc[u] = 0;
+            // ---- 3a. the sequential float sums, in the reference's order (descriptors.c:186-236, same code as k_descriptors' warp 0) ---
+            float as_density = 0.0f, as_max_dst = -1.0f, lane_max = -1.0f;
+            int mlhd_cnt = 0, nAlphaApol = 0;
+            for (int i = 0; i < n; i++) {
+                const float4 vi = W.sph[i];
+                const bool apol_i = sty[L[i]] == 0;
+                int napol = 0;
+                if (apol_i) {
+                    for (int j = lane; j < n; j += 32) {
+                        if (j == i || sty[L[j]] != 0) continue;
+                        const float4 vj = W.sph[j];
+                        if ((double)(f_dist(vi.x, vi.y, vi.z, vj.x, vj.y, vj.z) - (vj.w + vi.w)) <= 0.) napol++;
+                    }
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) napol += __shfl_xor_sync(0xffffffffu, napol, d);
+                    mlhd_cnt += napol;
+                    nAlphaApol++;
+                }
+                for (int b0 = i + 1; b0 < n; b0 += 32) {
+                    const int j = b0 + lane;
+                    float dj = 0.0f;
+                    if (j < n) {
+                        const float4 vj = W.sph[j];
+                        dj = f_dist(vi.x, vi.y, vi.z, vj.x, vj.y, vj.z);
+                        lane_max = fmaxf(lane_max, dj);
+                    }
+                    const int cntj = min(32, n - b0);
+                    for (int q = 0; q < cntj; q++) as_density += __shfl_sync(0xffffffffu, dj, q);
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) lane_max = fmaxf(lane_max, __shfl_xor_sync(0xffffffffu, lane_max, d));
+            if (lane_max > as_max_dst) as_max_dst = lane_max;
+            __syncwarp();
+            for (int u = lane; u < U; u += 32) {        // first occurrence of every residue id (descriptors.c:408 in_tab)
+                const int rid = B.ares[Q0 + uat[u]];
+                bool seen = false;
+                for (int q = 0; q < u && !seen; q++) seen = B.ares[Q0 + uat[q]] == rid;
+                entu[u] = seen ? 0 : 1;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                float mean_r = 0.0f, masph = 0.0f, as_max_r = -1.0f, ps0 = 0.0f, ps1 = 0.0f, ps2 = 0.0f;
+                int napolc = 0;
+                for (int i = 0; i < n; i++) {
+                    const int si = L[i];
+                    const float4 v = W.sph[i];
+                    if (v.w > as_max_r) as_max_r = v.w;
+                    mean_r += v.w;
+                    const float dd = f_dist(v.x, v.y, v.z, sb[3 * si], sb[3 * si + 1], sb[3 * si + 2]);
+                    masph += dd / v.w;
+                    ps0 += v.x; ps1 += v.y; ps2 += v.z;
+                    if (sty[si] == 0) napolc++;
+                }
+                fpk_desc d;
+                memset(&d, 0, sizeof d);
+                d.first_sphere = L[0];
+                d.nAlphaApol = napolc; d.nAlphaPol = n - napolc;
+                d.bary[0] = ps0 / (float)n; d.bary[1] = ps1 / (float)n; d.bary[2] = ps2 / (float)n;
+                d.n_atoms = U;
+                if (U > 1) {
+                    int nb_res = 0, nb_polar = 0;
+                    float flex = 0.0f, hyd = 0.0f, vol = 0.0f;
+                    for (int u = 0; u < U; u++) {
+                        const int a = Q0 + uat[u];
+                        if (entu[u]) {
+                            const int aa = B.aaa[a];
+                            if (aa >= 0) {
+                                d.aa_compo[aa]++;
+                                hyd += c_aa_hyd[aa]; d.polarity_score += c_aa_pol[aa]; vol += c_aa_vol[aa]; d.charge_score += c_aa_chg[aa];
+                            }
+                            nb_res++;
+                        }
+                        flex += B.abf[a];
+                        if ((double)B.aen[a] > 2.7) nb_polar++;
+                    }
+                    d.hydrophobicity_score = hyd / (float)nb_res;
+                    d.volume_score = vol / (float)nb_res;
+                    d.flex = flex / (float)U;
+                    d.prop_polar_atm = (float)((double)(((float)nb_polar) / ((float)U)) * 100.0);
+                }
+                d.mean_loc_hyd_dens = nAlphaApol > 0 ? (float)mlhd_cnt / (float)nAlphaApol : 0.0f;
+                d.as_max_dst = as_max_dst;
+                d.apolar_asphere_prop = (float)nAlphaApol / (float)n;
+                d.masph_sacc = masph / (float)n;
+                d.mean_asph_ray = mean_r / (float)n;
+                d.nb_asph = n;
+                d.as_density = (float)((double)as_density / ((n * n - n) * 0.5));
+                d.as_max_r = as_max_r;
+                W.d = d;
+            }
+            __syncwarp();
+            bool fits = true;
+            if (full) {
+                // ---- 3b. surrounding atoms (asa.c:84-112), in atom order ---------------------------------------------------------------
+                float bmn[3] = {3e38f, 3e38f, 3e38f}, bmx[3] = {-3e38f, -3e38f, -3e38f};
+                if (lane < n) {
+                    const float4 v = W.sph[lane];
+                    const float rp = v.w + 1.01f;
+                    bmn[0] = v.x - rp; bmn[1] = v.y - rp; bmn[2] = v.z - rp; bmx[0] = v.x + rp; bmx[1] = v.y + rp; bmx[2] = v.z + rp;
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1)
+#pragma unroll
+                    for (int q = 0; q < 3; q++) {
+                        bmn[q] = fminf(bmn[q], __shfl_xor_sync(0xffffffffu, bmn[q], d));
+                        bmx[q] = fmaxf(bmx[q], __shfl_xor_sync(0xffffffffu, bmx[q], d));
+                    }
+                int nsa = 0;
+                if (nw <= K4_GRID_MIN_ATOMS) {
+                    for (int b0 = 0; b0 < nw && fits; b0 += 32) {
+                        const int i = b0 + lane;
+                        bool in = false;
+                        if (i < nw && !(wf[WQ0 + i] & whmask)) {
+                            const float x = wx[W0 + i], y = wy[W0 + i], z = wz[W0 + i];
+                            if (x >= bmn[0] && x <= bmx[0] && y >= bmn[1] && y <= bmx[1] && z >= bmn[2] && z <= bmx[2]) {
+                                for (int q = 0; q < n && !in; q++) {
+                                    const float4 v = W.sph[q];
+                                    const double rp = (double)v.w + 1.0;
+                                    in = (double)f_ddist(x, y, z, v.x, v.y, v.z) < rp * rp;
+                                }
+                            }
+                        }
+                        const unsigned bal = __ballot_sync(0xffffffffu, in);
+                        if (nsa + __popc(bal) > K4S_SA) { fits = false; break; }
+                        if (in) W.sa[nsa + __popc(bal & ((1u << lane) - 1u))] = i;
+                        nsa += __popc(bal);
+                    }
+                } else {                   // large structure: the cells of the atom grid the box overlaps, then a sort (atom order matters, asa.c:313-325)
+                    const float4 gg = AG.geom[k];
+                    const int4 gd = AG.dims[k];
+                    const int *cellend = AG.cellend + AG.cbase[k];
+                    const int *cellatom = AG.cellatom + (S.natoms_w ? S.w_off : AG.same_base + S.atom_off);
+                    const int x0 = max(0, min(gd.x - 1, (int)floorf((bmn[0] - gg.x) / gg.w))), x1 = max(0, min(gd.x - 1, (int)floorf((bmx[0] - gg.x) / gg.w)));
+                    const int y0 = max(0, min(gd.y - 1, (int)floorf((bmn[1] - gg.y) / gg.w))), y1 = max(0, min(gd.y - 1, (int)floorf((bmx[1] - gg.y) / gg.w)));
+                    const int z0 = max(0, min(gd.z - 1, (int)floorf((bmn[2] - gg.z) / gg.w))), z1 = max(0, min(gd.z - 1, (int)floorf((bmx[2] - gg.z) / gg.w)));
+                    const int ny = y1 - y0 + 1, nz = z1 - z0 + 1, ncb = (x1 - x0 + 1) * ny * nz;
+                    int *cursor = &W.cursor;
+                    if (lane == 0) *cursor = 0;
+                    __syncwarp();
+                    for (int ci = lane; ci < ncb; ci += 32) {
+                        const int cz = z0 + ci % nz, cy = y0 + (ci / nz) % ny, cx = x0 + ci / (nz * ny);
+                        const int cid = (cx * gd.y + cy) * gd.z + cz;
+                        const int lo = cid ? cellend[cid - 1] : 0, hi = cellend[cid];
+                        for (int q2 = lo; q2 < hi; q2++) {
+                            const int i = cellatom[q2];
+                            const float x = wx[W0 + i], y = wy[W0 + i], z = wz[W0 + i];
+                            if (!(x >= bmn[0] && x <= bmx[0] && y >= bmn[1] && y <= bmx[1] && z >= bmn[2] && z <= bmx[2])) continue;
+                            bool in = false;
+                            for (int q = 0; q < n && !in; q++) {
+                                const float4 v = W.sph[q];
+                                const double rp = (double)v.w + 1.0;
+                                in = (double)f_ddist(x, y, z, v.x, v.y, v.z) < rp * rp;
+                            }
+                            if (in) { const int pos = atomicAdd(cursor, 1); if (pos < K4S_SA) W.sa[pos] = i; }
+                        }
+                    }
+                    __syncwarp();
+                    nsa = *cursor;
+                    __syncwarp();
+                    if (lane == 0) *cursor = 0;
+                    if (nsa > K4S_SA) fits = false;
+                    else {
+                        int npad = 32;
+                        while (npad < nsa) npad <<= 1;
+                        for (int i = nsa + lane; i < npad; i += 32) W.sa[i] = 0x7fffffff;
+                        __syncwarp();
+                        for (int kk = 2; kk <= npad; kk <<= 1)
+                            for (int j = kk >> 1; j > 0; j >>= 1) {
+                                for (int i = lane; i < npad; i += 32) {
+                                    const int ixj = i ^ j;
+                                    if (ixj > i) {
+                                        const int a = W.sa[i], b2 = W.sa[ixj];
+                                        if ((a > b2) == ((i & kk) == 0)) { W.sa[i] = b2; W.sa[ixj] = a; }
+                                    }
+                                }
+                                __syncwarp();
+                            }
+                    }
+                }
+                __syncwarp();
+                // ---- 4. 100-point spiral SASA, probes 1.4 and 2.2 (asa.c:240-419), one contacted atom after the other --------------------
+                for (int u = 0; u < U && fits; u++) {
+                    const int cura = uat[u];
+                    const float cx = B.ax[A0 + cura], cy = B.ay[A0 + cura], cz = B.az[A0 + cura], crad = B.arad[Q0 + cura];
+                    const float reach = crad + 2.2f + 2.2f + 0.01f;
+                    int ncand = 0;
+                    for (int b0 = 0; b0 < nsa; b0 += 32) {
+                        const int j = b0 + lane;
+                        bool take = false;
+                        int a = -1;
+                        float ax_ = 0, ay_ = 0, az_ = 0, ar_ = 0;
+                        if (j < nsa) {
+                            a = W.sa[j];
+                            if (!(same && a == cura)) {                 // asa.c:315 pointer inequality
+                                ax_ = wx[W0 + a]; ay_ = wy[W0 + a]; az_ = wz[W0 + a]; ar_ = wr[WQ0 + a];
+                                const float dx = ax_ - cx, dy = ay_ - cy, dz = az_ - cz, rr = reach + ar_;
+                                take = dx * dx + dy * dy + dz * dz <= rr * rr;
+                            }
+                        }
+                        const unsigned bal = __ballot_sync(0xffffffffu, take);
+                        if (ncand + __popc(bal) > ASA_CAND) { fits = false; break; }
+                        if (take) {
+                            const int pos = ncand + __popc(bal & ((1u << lane) - 1u));
+                            W.cand[pos] = make_float4(ax_, ay_, az_, ar_);
+                            W.candapol[pos] = (double)we[WQ0 + a] < 2.8 ? 1 : 0;
+                        }
+                        ncand += __popc(bal);
+                    }
+                    __syncwarp();
+                    if (!fits) break;
+                    const unsigned touching = W.tmask[u];
+                    int c14 = 0, c22 = 0, cap = 0, cpo = 0;
+                    for (int it = lane; it < 200; it += 32) {
+                        const int pass = it >= 100 ? 1 : 0, kp = it - 100 * pass;
+                        const double probe = pass == 0 ? 1.4 : 2.2;
+                        const float tx = (float)((double)cx + (double)c_spiral[3 * kp] * ((double)crad + probe));
+                        const float ty = (float)((double)cy + (double)c_spiral[3 * kp + 1] * ((double)crad + probe));
+                        const float tz = (float)((double)cz + (double)c_spiral[3 * kp + 2] * ((double)crad + probe));
+                        bool vref = true;
+                        for (unsigned tm = touching; tm && vref; tm &= tm - 1) {
+                            const float4 v = W.sph[__ffs(tm) - 1];
+                            if (f_ddist(tx, ty, tz, v.x, v.y, v.z) <= v.w * v.w) vref = false;
+                        }
+                        if (vref) continue;
+                        int hit = -1;
+                        for (int j = 0; j < ncand; j++) {
+                            const float4 q = W.cand[j];
+                            const float dsq = f_ddist(tx, ty, tz, q.x, q.y, q.z);
+                            const double rr = (double)q.w + probe;
+                            if ((double)dsq < rr * rr) { hit = W.candapol[j]; break; }
+                        }
+                        if (hit < 0) { if (pass == 0) c14++; else c22++; }
+                        else if (pass == 0) { if (hit) cap++; else cpo++; }
+                    }
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) {
+                        c14 += __shfl_xor_sync(0xffffffffu, c14, d); c22 += __shfl_xor_sync(0xffffffffu, c22, d);
+                        cap += __shfl_xor_sync(0xffffffffu, cap, d); cpo += __shfl_xor_sync(0xffffffffu, cpo, d);
+                    }
+                    if (lane == 0) *reinterpret_cast<int4 *>(acc + 4 * (size_t)u) = make_int4(c14, c22, cap, cpo);
+                    __syncwarp();
+                }
+            }
+            if (!fits) continue;                    // k_descriptors takes it (done[item] stays 0); nothing written so far is read by anyone else
+            __syncwarp();
+            // ---- 6a. per contacted atom: the two areas and the side effects on the atom (asa.c:330-337,384-396) ----------------------------
+            if (full) {
+                for (int u = lane; u < U; u += 32) {
+                    const int a = Q0 + uat[u];
+                    const size_t ga = (size_t)A0 + uat[u];
+                    const float crad = B.arad[a];
+                    const bool apolar_atom = (double)B.aen[a] < 2.8;
+                    const float a14 = (float)((4 * 3.1415926535897932384626433832795 * ((double)crad + 1.4) * ((double)crad + 1.4) / (double)(float)100) * (double)acc[4 * u]);
+                    const float a22 = (float)((4 * 3.1415926535897932384626433832795 * ((double)crad + 2.2) * ((double)crad + 2.2) / (double)(float)100) * (double)acc[4 * u + 1]);
+                    const float na = (float)acc[4 * u + 2], np = (float)acc[4 * u + 3];
+                    fxv[4 * u + 0] = na / (na + np);
+                    fxv[4 * u + 1] = a14;
+                    float flag = 0.0f;
+                    atomicMax(&Pk.fx_who[2 * ga], c);
+                    if (!apolar_atom && a22 < a14 && (double)a14 <= 10.0 && (double)a22 >= 0.0) {
+                        fxv[4 * u + 2] = a22 - a14;
+                        flag = 1.0f;
+                        atomicMax(&Pk.fx_who[2 * ga + 1], c);
+                    }
+                    fxv[4 * u + 3] = flag;
+                    acc[4 * u] = __float_as_int(a14); acc[4 * u + 1] = __float_as_int(a22); acc[4 * u + 2] = apolar_atom ? 1 : 0; acc[4 * u + 3] = (int)flag;
+                }
+            }
+            __syncwarp();
+            // ---- 6b. the float sums whose order is the reference's (atoms in first-seen order, probe 1.4 then 2.2) ---------------------------
+            float apol14 = 0.0f, pol14 = 0.0f, v14 = 0.0f, apol22 = 0.0f, pol22 = 0.0f, v22 = 0.0f;
+            int nabpa = 0;
+            if (full) {
+                for (int b0 = 0; b0 < U; b0 += 32) {
+                    const int u = b0 + lane;
+                    int4 a = make_int4(0, 0, 0, 0);
+                    if (u < U) a = *reinterpret_cast<const int4 *>(acc + 4 * (size_t)u);
+                    const int cntu = min(32, U - b0);
+                    for (int q = 0; q < cntu; q++) {
+                        const float a14 = __int_as_float(__shfl_sync(0xffffffffu, a.x, q)), a22 = __int_as_float(__shfl_sync(0xffffffffu, a.y, q));
+                        const int apolar_atom = __shfl_sync(0xffffffffu, a.z, q), flag = __shfl_sync(0xffffffffu, a.w, q);
+                        if (apolar_atom) { apol14 = apol14 + a14; apol22 = apol22 + a22; }
+                        else { pol14 = pol14 + a14; nabpa += flag; pol22 = pol22 + a22; }
+                        v14 = v14 + a14; v22 = v22 + a22;
+                    }
+                }
+            }
+            if (lane == 0) {
+                fpk_desc d = W.d;
+                if (full) {
+                    d.surf_apol_vdw14 = apol14; d.surf_pol_vdw14 = pol14; d.surf_vdw14 = v14;
+                    d.surf_apol_vdw22 = apol22; d.surf_pol_vdw22 = pol22; d.surf_vdw22 = v22; d.n_abpa = nabpa;
+                    d.volume = 0.0f;               // below min_pock_nb_asph: always dropped, no Monte-Carlo samples (see k_descriptors)
+                }
+                d.convex_hull_volume = D->convex_hull_volume;
+                *D = d;
+                done[item] = 1;
+            }
+            __syncwarp();
         }
     }
 }

@@ -3,11 +3,11 @@
 // explicit-pocket spheres and record, interface atoms, overlap / distance / consensus criteria per pocket: kernels K1-K6), native writers of
 // every <code>_out/ directory and of the three tables dpout_explicitp.txt / dpout_fpocketp.txt / dpout_fpocketnp.txt (rows in list order).
 //
-//   dpocket_fast -f list.txt [-o prefix] [-d dist] [-e] [-m f] [-M f] [-D f] [-i n] [-A n] [-p f] [-v n] [--threads T] [--group G] [--quiet] [--stats]
+//   dpocket_fast -f list.txt [-o prefix] [-d dist] [-e | -E] [-m f] [-M f] [-D f] [-i n] [-A n] [-p f] [-v n] [--threads T] [--group G] [--quiet] [--stats]
 //
-// list.txt: "<complex.pdb> <ligand residue name>" per line (dparams.c:206-240). Interface method 2 (-E) is refused: build/dpocket_cuda (the
-// reference's program on the same library) is the route for everything outside this one. The ligand's own Monte-Carlo volume (column lig_vol)
-// has no reference stream to copy (libc rand() seeded with the time): it is drawn from a counter-based stream keyed by the seed.
+// list.txt: "<complex.pdb> <ligand residue name>" per line (dparams.c:206-240). Both interface definitions (-e: atoms contacted by spheres near the
+// ligand, -E: atoms within 4 A of a ligand atom, dparams.h:41-44) are computed by the library (K6), as is the ligand's own Monte-Carlo volume (column
+// lig_vol), which has no reference stream to copy (libc rand() seeded with the time): it is drawn from a counter-based stream keyed by the seed.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -29,8 +29,8 @@ int main(int argc, char **argv)
         if (o == "-f") listf = val();
         else if (o == "-o") { prefix = val(); const size_t dot = prefix.rfind('.'); if (dot != std::string::npos) prefix.erase(dot); }      // remove_ext (dparams.c:127)
         else if (o == "-d") P.lig_interface_dist = (float)atof(val());
-        else if (o == "-e") P.lig_interface_dist = 4.0f;                     // M_VERT_LIG_NEIG_DIST
-        else if (o == "-E") { fprintf(stderr, "! dpocket_fast implements the alpha-sphere interface definition only (method 1): use build/dpocket_cuda\n"); return 3; }
+        else if (o == "-e") { P.lig_interface_method = 1; P.lig_interface_dist = 4.0f; }      // M_INTERFACE_METHOD1, M_VERT_LIG_NEIG_DIST
+        else if (o == "-E") { P.lig_interface_method = 2; P.lig_interface_dist = 4.0f; }      // M_INTERFACE_METHOD2, M_LIG_NEIG_DIST (dparams.c:116-119)
         else if (o == "-m") P.asph_min_size = (float)atof(val());
         else if (o == "-M") P.asph_max_size = (float)atof(val());
         else if (o == "-D") P.clust_max_dist = (float)atof(val());

@@ -83,7 +83,7 @@ int main(int argc, char **argv)
         else if (o == "-c" || o == "--drop_chains") chains(val(), 0);
         else if (o == "-k" || o == "--keep_chains") chains(val(), 1);
         else if (o == "-C" || o == "--clustering_method") { if (val()[0] != 's') return refuse("-C other than s (single linkage)"); }
-        else if (o == "-e" || o == "--clustering_measure") { if (val()[0] != 'e') return refuse("-e other than e (euclidean)"); }
+        else if (o == "-e" || o == "--clustering_measure") { const char m = val()[0]; if (m != 'e' && m != 'b') return refuse("-e other than e (euclidean) or b (city block)"); P.distance_measure = m; }
         else if (o == "-w" || o == "--write_mode") {            // fparams.c:167-183: d | b(oth) | p(db) | m(mcif) | cif
             const char *w = val();
             if (w[0] != 'd' && w[0] != 'b' && w[0] != 'p' && w[0] != 'm' && strcmp(w, "cif")) printf("Writing mode invalid, set to default\n");

@@ -1384,7 +1384,8 @@ int fpkio_run_dpocket(const char *const *paths, const char *const *ligands, int 
                                     const int w = fpkio_write_output_mode(f, paths[k], r, wmode, bytes);      // dpocket.c:233
                                     if (w < 0) return w;
                                     char *t[3] = {nullptr, nullptr, nullptr};
-                                    const float vol = fpkio_ligand_volume(f, niter, seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(k + 1)));
+                                    const float vol = r->lig_volume;          // get_mol_volume_ptr (atom.c:156): computed with the ligand queries (K6)
+                                    (void)seed; (void)niter;
                                     if (fpkio_dpocket_rows(f, paths[k], ligands[k], r, vol, t) >= 0)
                                         for (int q = 0; q < 3; q++) rows[(size_t)3 * k + q] = t[q];
                                     fpkio_free_rows(t);

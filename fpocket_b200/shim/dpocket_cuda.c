@@ -6,8 +6,8 @@
  * The reference runs search_pocket, then walks x-sorted arrays on the host for the ligand's neighbourhood (neighbor.c), computes a
  * full descriptor record for the explicit pocket (set_descriptors: ASA, Monte-Carlo volume, hull - dpocket.c:341-350) and four
  * criteria per pocket. Here ONE fpk_detect() call with the ligand attached (fpk_structure.n_lig) returns all of it: pockets,
- * explicit-pocket spheres + record (xdesc), interface atoms, ovlp / dst / c4 / c5 per pocket. Loading the complex, write_out_fpocket,
- * the ligand's own volume (get_mol_volume_ptr) and write_pocket_desc stay the reference's code.
+ * explicit-pocket spheres + record (xdesc), interface atoms (either definition, dparams.h:41-44), ovlp / dst / c4 / c5 per pocket and the
+ * ligand's own volume (get_mol_volume_ptr). Loading the complex, write_out_fpocket and write_pocket_desc stay the reference's code.
  * The rest of dpocket.c is linked as it is (shim/Makefile weakens the reference object's own desc_pocket so that this one is called).
  * Interface method 2 (-e, atoms within a distance of the ligand) is not supported: refused with a message.
  */
@@ -45,10 +45,6 @@ static void fill_desc(s_desc *d, const fpk_desc *g)
 
 void desc_pocket(char fcomplexe[], const char ligname[], s_dparams *par, FILE *f[3])
 {
-    if (par->interface_method != M_INTERFACE_METHOD1) {
-        fprintf(stdout, "ERROR - libfpocket_cuda implements the alpha-sphere interface definition only (method 1)\n");
-        return;
-    }
     if (!shim_supported(par->fpar)) return;
     /* dpocket.c:186-203 */
     s_pdb *pdb_l = rpdb_open(fcomplexe, ligname, M_KEEP_LIG, 0, par->fpar);
@@ -80,6 +76,7 @@ void desc_pocket(char fcomplexe[], const char ligname[], s_dparams *par, FILE *f
     fpk_params P;
     shim_params(par->fpar, &P);
     P.lig_interface_dist = par->interface_dist_crit;
+    P.lig_interface_method = par->interface_method;                                 /* dparams.h:41-44, dpocket.c:331-336 */
     fpk_result R;
     memset(&R, 0, sizeof R);
     const int rc = fpk_detect(&job.st, &P, &R);
@@ -92,6 +89,7 @@ void desc_pocket(char fcomplexe[], const char ligname[], s_dparams *par, FILE *f
     }
     s_desc *edesc = allocate_s_desc();
     if (R.xdesc) fill_desc(edesc, R.xdesc);
+    const float lig_volume = R.lig_volume;
     shim_job_release(&job);
     free(la); free(lm); free(nk);
     c_lst_pockets *pockets = shim_rebuild(pdb_nl, par->fpar, pdb_l, &R, rc, P.do_asa_and_volume);
@@ -100,7 +98,7 @@ void desc_pocket(char fcomplexe[], const char ligname[], s_dparams *par, FILE *f
         return;
     }
     write_out_fpocket(pockets, pdb_nl, fcomplexe);                  /* dpocket.c:233 */
-    const float vol = get_mol_volume_ptr(lig, nal, par->fpar->nb_mcv_iter);          /* the ligand's own volume: reference code */
+    const float vol = lig_volume;                                                   /* get_mol_volume_ptr (atom.c:156) on the GPU (K6) */
     write_pocket_desc(fcomplexe, ligname, edesc, vol, 100.0, 0.0, 1.0, 1.0, f[0]);
     node_pocket *cur = pockets->first;
     int q = 0;

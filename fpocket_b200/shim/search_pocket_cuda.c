@@ -167,14 +167,15 @@ void shim_params(const s_fparams *params, fpk_params *P)
     P->skip_clustering = (params->xlig_resnumber != -1 || params->xpocket_n > 0);      /* fpocket.c:114 */
     P->xpocket_active = params->xpocket_n > 0;
     P->min_n_explicit_pocket_atoms = params->min_n_explicit_pocket_atoms;
+    P->distance_measure = params->distance_measure;                                      /* -e e | b (clusterlib.c:933,1022) */
     P->mc_seed = (uint64_t)time(NULL);                                                    /* voronoi.c:87 srand(time(NULL)) */
     if (getenv("FPOCKET_MC_SEED")) P->mc_seed = strtoull(getenv("FPOCKET_MC_SEED"), NULL, 10);
 }
 
 int shim_supported(const s_fparams *params)
 {
-    if (params->clustering_method != 's' || params->distance_measure != 'e') {
-        fprintf(stderr, "! libfpocket_cuda implements single linkage on euclidean distances only (-C s -e e); got -C %c -e %c\n",
+    if (params->clustering_method != 's' || (params->distance_measure != 'e' && params->distance_measure != 'b')) {
+        fprintf(stderr, "! libfpocket_cuda implements single linkage on euclidean or city-block distances only (-C s, -e e or b); got -C %c -e %c\n",
                 params->clustering_method, params->distance_measure);
         return 0;
     }

@@ -63,6 +63,10 @@ typedef struct fpk_params {
     /* dpocket ligand queries (only read when a structure carries ligand atoms, fpk_structure.n_lig > 0) */
     float lig_interface_dist;             /* dparams.h:42 M_VERT_LIG_NEIG_DIST 4.0: spheres within it of a ligand atom define the explicit pocket */
     float lig_crit_dist;                  /* tpocket.h:32-33 M_CRIT4_D = M_CRIT5_D = 3.0                                                        */
+    int32_t distance_measure;             /* -e (fparams.h distance_measure): 0 or 'e' euclid (clusterlib.c:933), 'b' city block = the MEAN of the three
+                                             absolute differences (clusterlib.c:1022-1083). Single linkage only (-C s); anything else: FPK_ERR_BAD_ARG */
+    int32_t lig_interface_method;         /* dpocket -E (dparams.h:41-44): 0 or 1 = atoms contacted by spheres near the ligand (neighbor.c:313),
+                                             2 = atoms within lig_interface_dist of a ligand atom (neighbor.c:67 get_mol_atm_neigh)              */
 } fpk_params;
 
 /* flattened s_pdb pair (reference headers/rpdb.h:69-98, atom.h:29-77). Arrays are caller-owned, read-only. */
@@ -153,6 +157,8 @@ typedef struct fpk_result {
     float *pk_dst;             /* [n_pockets] min distance ligand atom - pocket barycentre (dpocket.c:253-261)                           */
     float *pk_c4;              /* [n_pockets] count_atm_prop_vert_neigh(.., lig_crit_dist) (neighbor.c:598, dpocket.c:266)               */
     float *pk_c5;              /* [n_pockets] count_pocket_lig_vert_ovlp(.., lig_crit_dist) (neighbor.c:490, dpocket.c:268)              */
+    float lig_volume;          /* get_mol_volume_ptr(ligand atoms, nb_mcv_iter) (atom.c:156, dpocket.c:245): Monte-Carlo volume of the ligand's vdW
+                                  spheres; the reference draws from time-seeded rand(), here Philox keyed by mc_seed                      */
 } fpk_result;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */

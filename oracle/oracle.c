@@ -172,8 +172,9 @@ static int uf_find(int *par, int i) { while (par[i] != i) { par[i] = par[par[i]]
 static int g_distance_measure = 'e';
 void orc_set_distance_measure(int c) { g_distance_measure = c; }
 
-static int cluster_spheres(sph_t *S, int ns, float clust_max_dist, int skip)
+static int cluster_spheres(sph_t *S, int ns, float clust_max_dist, int skip, int measure)
 {
+    if (measure == 'b' || measure == 'e') g_distance_measure = measure;        /* fpk_params.distance_measure; 0 keeps what orc_set_distance_measure chose */
     if (skip) { for (int i = 0; i < ns; i++) S[i].cluster = 0; return ns ? 1 : 0; }
     int *par = malloc(sizeof(int) * (size_t)(ns + 1));
     for (int i = 0; i < ns; i++) par[i] = i;
@@ -628,7 +629,9 @@ int orc_search_pocket(const fpk_structure *in, const fpk_params *p, const int *t
         out->status = FPK_ERR_NO_SPHERES;
         return out->status;
     }
-    int nc = cluster_spheres(S, ns, p->clust_max_dist, p->skip_clustering);
+    const int saved_measure = g_distance_measure;
+    int nc = cluster_spheres(S, ns, p->clust_max_dist, p->skip_clustering, p->distance_measure);
+    g_distance_measure = saved_measure;
     out->n_clusters = nc;
     out->sph_xyzr = malloc(sizeof(float) * 4 * (size_t)(ns + 1)); out->sph_bary = malloc(sizeof(float) * 3 * (size_t)(ns + 1));
     out->sph_neigh = malloc(sizeof(int) * 4 * (size_t)(ns + 1)); out->sph_type = malloc((size_t)ns + 1); out->sph_cluster = malloc(sizeof(int) * (size_t)(ns + 1));
@@ -788,7 +791,7 @@ void orc_ligand_queries(const fpk_structure *in, const fpk_params *p, fpk_result
             }
         }
     }
-    if (g_interface_method == 2) {
+    if (g_interface_method == 2 || p->lig_interface_method == 2) {
         /* dparams.h:44 M_INTERFACE_METHOD2 (dpocket.c:331-336, neighbor.c:67 get_mol_atm_neigh): the atoms of the complex with dist() < dcrit to a ligand
          * atom, the ligand's own atoms excluded. pdb is pdb_w_lig without the ligand, in the same order: index in pdb = index in pdb_w_lig minus the
          * ligand atoms before it. (The reference excludes and de-duplicates by atom ID, neighbor.c:118: with repeated ids in a file its result is an
@@ -859,6 +862,34 @@ void orc_ligand_queries(const fpk_structure *in, const fpk_params *p, fpk_result
         out->pk_dst[r] = dst; out->pk_c4[r] = c4; out->pk_c5[r] = (float)c5n / (float)n;
     }
     free(hit); free(tot);
+    /* atom.c:156 get_mol_volume_ptr(ligand atoms, nb_mcv_iter) (dpocket.c:245): box with the else-if updates, first-hit loop; the reference's
+     * draws come from time-seeded rand(), here from Philox: counter (sample, 0x11A, 0, 0), key mc_seed (the library's stream) */
+    {
+        float xmin = 0, xmax = 0, ymin = 0, ymax = 0, zmin = 0, zmax = 0, t;
+        const float *wr = in->natoms_w ? in->wradius : in->radius;
+        for (int l = 0; l < nl; l++) {
+            const int a = in->lig_atoms[l];
+            if (l == 0) { xmin = wx[a] - wr[a]; xmax = wx[a] + wr[a]; ymin = wy[a] - wr[a]; ymax = wy[a] + wr[a]; zmin = wz[a] - wr[a]; zmax = wz[a] + wr[a]; }
+            else {
+                if (xmin > (t = wx[a] - wr[a])) xmin = t; else if (xmax < (t = wx[a] + wr[a])) xmax = t;
+                if (ymin > (t = wy[a] - wr[a])) ymin = t; else if (ymax < (t = wy[a] + wr[a])) ymax = t;
+                if (zmin > (t = wz[a] - wr[a])) zmin = t; else if (zmax < (t = wz[a] + wr[a])) zmax = t;
+            }
+        }
+        const float vbox = (xmax - xmin) * (ymax - ymin) * (zmax - zmin);
+        int nb_in = 0;
+        for (int i = 0; i < p->nb_mcv_iter; i++) {
+            unsigned o[4];
+            orc_philox4x32((unsigned)i, 0x11Au, 0u, 0u, (unsigned)p->mc_seed, (unsigned)(p->mc_seed >> 32), o);
+            const float xr = unif_from_bits(o[0] >> 1, xmin, xmax), yr = unif_from_bits(o[1] >> 1, ymin, ymax), zr = unif_from_bits(o[2] >> 1, zmin, zmax);
+            for (int l = 0; l < nl; l++) {
+                const int a = in->lig_atoms[l];
+                const float xt = wx[a] - xr, yt = wy[a] - yr, zt = wz[a] - zr;
+                if ((wr[a] * wr[a]) > (xt * xt + yt * yt + zt * zt)) { nb_in++; break; }
+            }
+        }
+        out->lig_volume = (nl > 0 && p->nb_mcv_iter > 0) ? ((float)nb_in) / ((float)p->nb_mcv_iter) * vbox : 0.0f;
+    }
 }
 
 /* ---------------------------------------- mdpocket grids ---------------------------------------- */

@@ -10,8 +10,8 @@ import oracle_lib as O
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 _FILES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "*.npz")))
 MDCHAR_CASES = [c for c in _FILES if c.startswith("mdchar_")]      # one snapshot of mdpocket's characterize mode (oracle-only so far)
-ALT_CASES = [c for c in _FILES if c.startswith("alt_")]              # options the library refuses so far (-e b): oracle-only, SURVEY 8 f4
-ALL = [c for c in _FILES if c not in MDCHAR_CASES and c not in ALT_CASES]
+ALT_CASES = [c for c in _FILES if c.startswith("alt_")]              # non-default clustering distance (-e b): on the GPU since round 2
+ALL = [c for c in _FILES if c not in MDCHAR_CASES]
 FPOCKET_CASES = [c for c in ALL if not c.startswith("md_")]
 MD_CASES = [c for c in ALL if c.startswith("md_")]
 

@@ -179,6 +179,8 @@ def params_from_dump(d, **kw):
     p.skip_clustering = int(not (pi[4] == -1 and pi[5] == 0))
     p.xpocket_active = int(pi[5] > 0)
     p.min_n_explicit_pocket_atoms = int(pi[6])
+    if len(pi) > 8 and int(pi[8]) in (ord("e"), ord("b")):
+        p.distance_measure = int(pi[8])          # -e (fparams.c): 'e' euclid, 'b' city block
     for k, v in kw.items():
         setattr(p, k, v)
     return p

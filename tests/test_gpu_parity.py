@@ -46,6 +46,7 @@ def assert_same_result(r, o, what=""):
     if "xspheres" in o:             # dpocket ligand queries (K6)
         for k in ("xspheres", "iface_atoms", "pk_ovlp", "pk_dst", "pk_c4", "pk_c5"):
             assert k in r and np.array_equal(r[k], o[k]), (what, k)
+        assert np.float32(r["lig_volume"]) == np.float32(o["lig_volume"]) and r["lig_volume"] > 0, (what, "ligand volume", r["lig_volume"], o["lig_volume"])
         assert (r["xdesc"] is None) == (o["xdesc"] is None), what
         if o["xdesc"] is not None:      # the explicit pocket's own record (dpocket.c:350), bit for bit
             for n in r["xdesc"].dtype.names:
@@ -163,6 +164,47 @@ def test_one_unusable_structure_does_not_abort_the_batch():
     assert got[1]["status"] == capi.FPK_ERR_BAD_ARG and got[1]["n_spheres"] == 0
     assert_same_result(got[0], o, "before the bad one")
     assert_same_result(got[2], o, "after the bad one")
+
+
+def test_city_block_clustering_equals_the_reference():
+    """-e b (clusterlib.c:1022-1083, the MEAN absolute difference) on the GPU (K3 with another pair test, cell edge 3 x the cut): equal to the
+    oracle bit for bit, equal to the unmodified reference's run of `fpocket -f 1UYD.pdb -e b` within the stated tolerances, different from -e e;
+    also on a synthetic batch, together with a structure that takes the grid-wide clustering kernel."""
+    import refcompare as RC
+    api = _api()
+    d = G.load("alt_1UYD_eb")
+    st, p = G.inputs(d)
+    assert p.distance_measure == ord("b")
+    r = api.detect(st, p)
+    o = O.search_pocket(st, p, tets=None, rng_mode=O.RNG_PHILOX)
+    assert_same_result(r, o, "-e b")
+    RC.compare(r, d, st, p, what="-e b")
+    pe = G.inputs(d)[1]
+    pe.distance_measure = ord("e")
+    assert api.detect(st, pe)["n_clusters"] != r["n_clusters"]
+    sts = [_synth(20269330 + i, n) for i, n in enumerate((2100, 13000, 2900))]
+    pb = api.default_params()
+    pb.distance_measure = ord("b")
+    for st2, r2 in zip(sts, api.detect_batch(sts, pb)):
+        assert_same_result(r2, O.search_pocket(st2, pb, tets=None, rng_mode=O.RNG_PHILOX), "-e b synthetic")
+
+
+def test_dpocket_interface_method_2_equals_the_reference():
+    """dpocket -E (dparams.h:44, dpocket.c:331-336): the interface = atoms within 4.0 of a ligand atom (neighbor.c:67 get_mol_atm_neigh). K6's set
+    equals the oracle's and what the reference's own function returned on 1UYD / PU8; so does the overlap atm_corsp computes with it."""
+    api = _api()
+    d = G.load("1UYD_dpocket")
+    st, p = G.inputs(d)
+    p.lig_interface_method = 2
+    r = api.detect(st, p)
+    o = O.search_pocket(st, p, tets=None, rng_mode=O.RNG_PHILOX)
+    assert_same_result(r, o, "interface method 2")
+    lig = np.sort(d["lig.atoms"])
+    ref = np.sort(np.array([w - np.searchsorted(lig, w) for w in d["lig.iface2"]], dtype=np.int32))
+    assert len(ref) > 20 and np.array_equal(r["iface_atoms"], ref)
+    p.lig_interface_method = 1
+    r1 = api.detect(st, p)
+    assert len(r1["iface_atoms"]) != len(ref) and r1["lig_volume"] == r["lig_volume"]
 
 
 def test_batch_equals_single():

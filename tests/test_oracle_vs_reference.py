@@ -120,16 +120,13 @@ def test_oracle_characterize_snapshot_equals_the_reference(case):
 @pytest.mark.parametrize("case", G.ALT_CASES)
 def test_oracle_city_block_clustering_equals_the_reference(case):
     """-e b (clusterlib.c:1022-1083: mean absolute difference) with single linkage: clusters, every descriptor, drop and rank equal the reference's bit
-    for bit, and differ from the default run's (reference tests/test_fpocket.py:83-91 only asks for the difference). Oracle first (SURVEY par. 8 row f4):
-    the library still refuses -e other than e."""
+    for bit, and differ from the default run's (reference tests/test_fpocket.py:83-91 only asks for the difference). The library computes it too since round 2
+    (tests/test_gpu_parity.py::test_city_block_clustering_equals_the_reference)."""
     d = G.load(case)
     assert int(d["params.i"][8]) == ord("b")
     st, p = G.inputs(d)
-    O.lib().orc_set_distance_measure(ord("b"))
-    try:
-        r = O.search_pocket(st, p, tets=d["qh.tets_seen"], rng_mode=O.RNG_LIBC)
-    finally:
-        O.lib().orc_set_distance_measure(ord("e"))
+    assert p.distance_measure == ord("b")           # fpk_params.distance_measure, taken from the reference's own parameter dump
+    r = O.search_pocket(st, p, tets=d["qh.tets_seen"], rng_mode=O.RNG_LIBC)
     assert np.array_equal(r["cl_off"], d["pre.off"]) and np.array_equal(r["cl_sph"], d["pre.sph"])
     D, F, I = r["desc"], d["pre.desc_f"], d["pre.desc_i"]
     for k, n in enumerate(G.DESC_F):
@@ -138,6 +135,7 @@ def test_oracle_city_block_clustering_equals_the_reference(case):
         assert np.array_equal(D[n], I[:, k]), n
     ref_first = [int(d["fin.sph"][o]) for o in d["fin.off"][:-1]]
     assert [int(r["cl_sph"][r["cl_off"][c]]) for c in r["rank_to_cluster"]] == ref_first
+    p.distance_measure = ord("e")
     e = O.search_pocket(st, p, tets=d["qh.tets_seen"], rng_mode=O.RNG_LIBC)
     assert e["n_clusters"] != r["n_clusters"]
 
