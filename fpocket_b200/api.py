@@ -197,6 +197,27 @@ class MdPocket:
             raise FpkError("fpk_md_fetch_grids failed")
         return dens.reshape(self.dims), freq.reshape(self.dims)
 
+    def characterize(self, xyz, zone):
+        """mdpocket's characterize mode (mdpocket.c:428-460) for every frame of `xyz`: the spheres of the surviving pockets within 1.0 of a point of
+        `zone` ([nzone, 3]; once per such point), the atoms they contact and their descriptor record. Returns one dict per frame."""
+        a, ptr = self._xyz(xyz)
+        zone = np.ascontiguousarray(zone, dtype=np.float32).reshape(-1, 3)
+        out = (capi.FpkZone * len(a))()
+        rc = self.lib.fpk_md_characterize(self.h, ptr, len(a), zone.ctypes.data_as(C.POINTER(C.c_float)), len(zone), out)
+        if rc != capi.FPK_OK:
+            raise FpkError("fpk_md_characterize failed (%d): %s" % (rc, (self.lib.fpk_last_error() or b"").decode()))
+        res = []
+        for z in out:
+            n = z.n_entries
+            d = np.zeros(1, capi.DESC_DTYPE)
+            C.memmove(d.ctypes.data, C.addressof(z.desc), capi.DESC_DTYPE.itemsize)
+            res.append({"status": z.status, "n_spheres_frame": z.n_spheres_frame, "n_pockets_frame": z.n_pockets_frame,
+                        "spheres": capi._arr(z.spheres, (n,), np.int32), "sph_xyzr": capi._arr(z.sph_xyzr, (n, 4), np.float32),
+                        "sph_type": capi._arr(z.sph_type, (n,), np.uint8), "atoms": capi._arr(z.atoms, (z.n_atoms,), np.int32),
+                        "desc": d[0], "atom_fx": capi._arr(z.atom_fx, (self.natoms, 4), np.float32) if z.atom_fx else None})
+            self.lib.fpk_zone_free(C.byref(z))
+        return res
+
     def counter(self, which):
         return int(self.lib.fpk_md_counter(self.h, which))
 

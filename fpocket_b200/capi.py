@@ -93,6 +93,14 @@ class FpkResult(C.Structure):
     ]
 
 
+class FpkZone(C.Structure):
+    _fields_ = [
+        ("status", C.c_int32), ("n_spheres_frame", C.c_int32), ("n_pockets_frame", C.c_int32), ("n_entries", C.c_int32),
+        ("spheres", _ip), ("sph_xyzr", _fp), ("sph_type", _bp), ("n_atoms", C.c_int32), ("atoms", _ip), ("desc", FpkDesc),
+        ("atom_fx", _fp), ("_owner", C.c_void_p),
+    ]
+
+
 def _arr(ptr, shape, dtype):
     n = int(np.prod(shape))
     if n == 0 or not ptr:
@@ -220,6 +228,8 @@ def declare(lib):
         "fpk_md_device_grids": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "fpk_md_fetch_grids": (C.c_int, [vp, _fp, _fp]),
         "fpk_md_counter": (C.c_longlong, [vp, C.c_int]),
+        "fpk_md_characterize": (C.c_int, [vp, _fp, C.c_int, _fp, C.c_int, C.POINTER(FpkZone)]),
+        "fpk_zone_free": (None, [C.POINTER(FpkZone)]),
         "fpk_md_end": (None, [vp]),
     }
     for name, (res, args) in sig.items():

@@ -1066,6 +1066,9 @@ extern "C" int fpk_detect(const fpk_structure *in, const fpk_params *p, fpk_resu
 struct MdDev {
     int dev = 0;
     fpk_batch *b = nullptr;            // re-used for every chunk of frames (geometry of the buffers is fixed)
+    fpk_batch *bc = nullptr;           // characterize mode: the same with ASA and volumes on (mdpocket.c:360-660 keeps the default)
+    Arena A3;                          // the zone batch of the current chunk
+    float *d_zone = nullptr; int nzone_cap = 0;
     float *d_dens = nullptr, *d_freq = nullptr; unsigned *d_mask = nullptr; unsigned long long *d_nscat = nullptr;
     long long *d_dens_fx = nullptr, *d_freq_fx = nullptr;      // -S: 32.32 fixed-point accumulators (order-free sums), see MdGrid
     float *d_geom = nullptr;
@@ -1083,9 +1086,10 @@ struct MdDev {
     {
         cudaSetDevice(dev);
         for (int q = 0; q < 2; q++) { if (pin[q]) cudaFreeHost(pin[q]); if (d_xyz[q]) cudaFree(d_xyz[q]); }
-        delete b;
+        delete b; delete bc;
+        A3.release();
         free_grids();
-        cudaFree(d_geom); cudaFree(d_peer);
+        cudaFree(d_geom); cudaFree(d_peer); cudaFree(d_zone);
     }
 };
 struct fpk_md {
@@ -1100,16 +1104,19 @@ struct fpk_md {
     ~fpk_md() { for (MdDev *d : D) delete d; if (!g_devs.empty()) cudaSetDevice(g_devs[0]); }
 };
 
-static int md_prepare(fpk_md *m, MdDev *q, int nframes)
+static int md_prepare(fpk_md *m, MdDev *q, int nframes, bool characterize = false)
 {
     // (re)build the batch skeleton for `nframes` frames: properties uploaded once, coordinates per push
-    if (q->b && q->b->n == nframes) return FPK_OK;
-    delete q->b;
-    q->b = new fpk_batch();
-    fpk_batch *b = q->b;
+    fpk_batch *&slot = characterize ? q->bc : q->b;
+    if (slot && slot->n == nframes) return FPK_OK;
+    delete slot;
+    slot = new fpk_batch();
+    fpk_batch *b = slot;
     const fpk_structure &t = m->topo;
     std::vector<fpk_structure> fr(nframes, t);
-    int rc = batch_pack(b, fr.data(), nframes, &m->prm, 0.0);
+    fpk_params prm = m->prm;
+    if (characterize) prm.do_asa_and_volume = 1;
+    int rc = batch_pack(b, fr.data(), nframes, &prm, 0.0);
     if (rc) return rc;
     if (b->bad[0]) return FPK_ERR_BAD_ARG;
     // all frames share one copy of the properties and of the site map
@@ -1409,6 +1416,155 @@ extern "C" int fpk_md_fetch_grids(fpk_md *m, float *dens, float *freq)
     if (freq) CK(cudaMemcpy(freq, m->D[0]->d_freq, sizeof(float) * ncell, cudaMemcpyDeviceToHost));
     return FPK_OK;
 }
+// ---- characterize mode (mdpocket.c:360-660): full detection of every frame, then the zone's sphere list described as one pocket --------
+struct ZoneOwner { std::atomic<int> refs{0}; std::vector<char> blk; };
+extern "C" void fpk_zone_free(fpk_zone *z)
+{
+    if (!z || !z->_owner) return;
+    ZoneOwner *o = static_cast<ZoneOwner *>(z->_owner);
+    memset(z, 0, sizeof *z);
+    if (o->refs.fetch_sub(1) == 1) delete o;
+}
+
+static int md_characterize_chunk(fpk_md *m, MdDev *q, const float *xyz, int nf, int nzone, fpk_zone *out)
+{
+    int rc = md_prepare(m, q, nf, true);
+    if (!rc) rc = md_ensure_staging(m, q, nf);
+    if (!rc) rc = md_stage_chunk(m, q, 0, xyz, nf);
+    if (rc) return rc;
+    fpk_batch *b = q->bc;
+    const size_t na = (size_t)m->topo.natoms, tot = na * (size_t)nf;
+    k_md_deinterleave<<<g_sms * 4, 256>>>(q->d_xyz[0], tot, const_cast<float *>(b->B.ax), const_cast<float *>(b->B.ay), const_cast<float *>(b->B.az));
+    rc = batch_run(b);
+    if (rc) return rc;
+    q->launches += b->launches + 1;
+    q->frames += nf;
+    for (int f = 0; f < nf; f++) {
+        memset(&out[f], 0, sizeof out[f]);
+        const int *c = &b->h_counts[(size_t)f * CNT_STRIDE];
+        out[f].status = c[CNT_STATUS] == FPK_OK ? FPK_ERR_NO_POCKETS : c[CNT_STATUS];
+        out[f].n_spheres_frame = c[CNT_SPHERES]; out[f].n_pockets_frame = c[CNT_POCKETS];
+    }
+    if (b->tot_clusters == 0 || nzone <= 0) return FPK_OK;
+    // ---- pass 0: how many (sphere, zone point) entries does every frame have? -----------------------------------------------------
+    ZoneDev Z;
+    memset(&Z, 0, sizeof Z);
+    Z.zone = q->d_zone; Z.nzone = nzone;
+    int *d_ecount = nullptr;
+    CK(cudaMalloc(&d_ecount, sizeof(int) * (size_t)nf));
+    Z.ecount = d_ecount;
+    k_zone_select<<<nf, 256>>>(b->B, b->Pk, Z, 0);
+    std::vector<int> ecount(nf), ebase(nf + 1, 0), clbase2(nf + 1, 0);
+    cudaError_t e = cudaMemcpy(ecount.data(), d_ecount, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToHost);
+    cudaFree(d_ecount);
+    if (e != cudaSuccess) return fail(FPK_ERR_CUDA, "k_zone_select: %s", cudaGetErrorString(e));
+    int maxE = 1;
+    for (int f = 0; f < nf; f++) { ebase[f + 1] = ebase[f] + ecount[f]; clbase2[f + 1] = clbase2[f] + (ecount[f] > 0 ? 1 : 0); maxE = std::max(maxE, ecount[f]); }
+    const long long E = ebase[nf], NC2 = clbase2[nf];
+    q->launches++;
+    if (E == 0) return FPK_OK;
+    // ---- the zone batch: one structure per frame whose spheres are the entries, one cluster each -----------------------------------
+    const int nHull2 = (int)std::min<long long>(NC2, 16);
+    std::vector<DelScratch> hHull2(nHull2);
+    StructDev *dS2 = nullptr;
+    int *d_ebase = nullptr, *d_clbase2 = nullptr, *d_fb = nullptr, *d_cnt = nullptr;
+    unsigned char *d_done = nullptr;
+    DelScratch *dHull2 = nullptr;
+    PocketDev P2;
+    memset(&P2, 0, sizeof P2);
+    rc = arena_build(q->A3, [&](Arena &a) {
+        d_ebase = a.take<int>(nf + 1); d_clbase2 = a.take<int>(nf + 1); dS2 = a.take<StructDev>(nf);
+        Z.entry_sphere = a.take<int>(E + 1);
+        Z.z_xyzr = a.take<float4>(E + 1); Z.z_bary = a.take<float>(3 * E + 3); Z.z_neigh = a.take<int4>(E + 1); Z.z_type = a.take<uint8_t>(E + 1);
+        Z.z_cl_sph = a.take<int>(E + 1); Z.z_cl_off = a.take<int>(E + 2 * (size_t)nf + 2);
+        Z.z_counts = a.take<int>((size_t)nf * CNT_STRIDE); Z.z_mcid = a.take<int>(nf);
+        P2.desc = a.take<fpk_desc>(NC2 + 1);
+        P2.cl_atoms = a.take<int>(4 * E + 4); P2.ent_u = a.take<int>(4 * E + 4); P2.touch_off = a.take<int>(5 * E + 5);
+        P2.touch_list = a.take<int>(4 * E + 4); P2.acc = a.take<int>(16 * E + 16); P2.fx_val = a.take<float>(16 * E + 16);
+        P2.fx_who = a.take<int>(2 * b->tot_atoms + 2); P2.atom_fx = a.take<float>(4 * b->tot_atoms + 4);
+        P2.rank_to_cluster = a.take<int>(E + nf + 1);
+        d_fb = a.take<int>(NC2 + 1); d_done = a.take<unsigned char>(NC2 + 1); d_cnt = a.take<int>(8);
+        dHull2 = a.take<DelScratch>(nHull2);
+        for (int i = 0; i < nHull2; i++) del_scratch_layout(a, hHull2[i], maxE, 0, HULL_THREADS, false);
+    });
+    if (rc) return rc;
+    Z.ebase = d_ebase;
+    std::vector<StructDev> S2(b->S.begin(), b->S.begin() + nf);
+    for (int f = 0; f < nf; f++) { S2[f].sph_off = ebase[f]; S2[f].sph_cap = ecount[f]; }
+    CK(cudaMemcpyAsync(d_ebase, ebase.data(), sizeof(int) * (nf + 1), cudaMemcpyHostToDevice, cudaStreamPerThread));
+    CK(cudaMemcpyAsync(d_clbase2, clbase2.data(), sizeof(int) * (nf + 1), cudaMemcpyHostToDevice, cudaStreamPerThread));
+    CK(cudaMemcpyAsync(dS2, S2.data(), sizeof(StructDev) * nf, cudaMemcpyHostToDevice, cudaStreamPerThread));
+    CK(cudaMemcpyAsync(dHull2, hHull2.data(), sizeof(DelScratch) * nHull2, cudaMemcpyHostToDevice, cudaStreamPerThread));
+    CK(cudaMemsetAsync(P2.desc, 0, sizeof(fpk_desc) * (size_t)(NC2 + 1), cudaStreamPerThread));
+    CK(cudaMemsetAsync(P2.fx_who, 0xff, sizeof(int) * (2 * (size_t)b->tot_atoms + 2), cudaStreamPerThread));
+    CK(cudaMemcpyAsync(P2.atom_fx, b->Pk.atom_fx, sizeof(float) * 4 * (size_t)b->tot_atoms, cudaMemcpyDeviceToDevice, cudaStreamPerThread));   // the frame's own pass came first
+    CK(cudaMemsetAsync(d_done, 0, (size_t)NC2 + 1, cudaStreamPerThread));
+    CK(cudaMemsetAsync(d_cnt, 0, sizeof(int) * 8, cudaStreamPerThread));
+    k_zone_select<<<nf, 256>>>(b->B, b->Pk, Z, 1);
+    BatchDev B2 = b->B;
+    B2.S = dS2; B2.s_xyzr = Z.z_xyzr; B2.s_bary = Z.z_bary; B2.s_neigh = Z.z_neigh; B2.s_type = Z.z_type;
+    B2.cl_off = Z.z_cl_off; B2.cl_sph = Z.z_cl_sph; B2.counts = Z.z_counts;
+    B2.prm.min_pock_nb_asph = 0;            // the zone's record is written for every snapshot: always with volume and hull (mdpocket.c:453)
+    P2.clbase = d_clbase2; P2.sbase = d_ebase; P2.total_clusters = (int)NC2; P2.mc_id = Z.z_mcid;
+    const size_t hull_dsm = FPK_BD_BYTES + (HULL_THREADS / 32) * sizeof(WarpCav) + 16;
+    const int nhw = (int)std::max(1ll, std::min<long long>((NC2 + 32 * HW_WARPS - 1) / (32 * HW_WARPS), (long long)g_sms * FPK_HW_MINBLOCKS));
+    k_hull_warp<<<nhw, HW_THREADS, HW_WARPS * sizeof(HullWarp)>>>(B2, P2, d_cnt + 4, d_fb, d_cnt + 5, 1);
+    k_hull_volume<<<nHull2, HULL_THREADS, hull_dsm>>>(B2, P2, dHull2, d_cnt + 2, 0, d_fb, d_cnt + 5);
+    k_descriptors<<<(int)std::min<long long>(NC2, b->nDesc), K4_THREADS>>>(B2, P2, b->dDesc, d_cnt + 3, b->AG, d_done);
+    k_atom_fx<<<(unsigned)NC2, 64>>>(B2, P2);
+    q->launches += 5;
+    // ---- results -----------------------------------------------------------------------------------------------------------------------
+    ZoneOwner *own = new ZoneOwner();
+    const size_t bytes = 4 * (size_t)E + 16 * (size_t)E + (size_t)E + 16 * (size_t)E + sizeof(fpk_desc) * (size_t)NC2 + 16 * (size_t)b->tot_atoms + 1024;
+    own->blk.resize(bytes);
+    char *w = own->blk.data();
+    auto carve = [&](size_t n) { char *r = w; w += (n + 15) & ~(size_t)15; return r; };
+    int *h_sph = (int *)carve(4 * (size_t)E);
+    float *h_xyzr = (float *)carve(16 * (size_t)E);
+    uint8_t *h_type = (uint8_t *)carve((size_t)E);
+    int *h_atoms = (int *)carve(16 * (size_t)E);
+    fpk_desc *h_desc = (fpk_desc *)carve(sizeof(fpk_desc) * (size_t)NC2);
+    float *h_fx = (float *)carve(16 * (size_t)b->tot_atoms);
+    e = cudaMemcpy(h_sph, Z.entry_sphere, 4 * (size_t)E, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(h_xyzr, Z.z_xyzr, 16 * (size_t)E, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(h_type, Z.z_type, (size_t)E, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(h_atoms, P2.cl_atoms, 16 * (size_t)E, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(h_desc, P2.desc, sizeof(fpk_desc) * (size_t)NC2, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(h_fx, P2.atom_fx, 16 * (size_t)b->tot_atoms, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { delete own; return fail(FPK_ERR_CUDA, "characterize: %s", cudaGetErrorString(e)); }
+    for (int f = 0; f < nf; f++) {
+        fpk_zone &z = out[f];
+        z.atom_fx = h_fx + 4 * (size_t)b->S[f].atom_off;
+        z._owner = own; own->refs++;
+        if (ecount[f] == 0) continue;
+        z.status = FPK_OK;
+        z.n_entries = ecount[f];
+        z.spheres = h_sph + ebase[f]; z.sph_xyzr = h_xyzr + 4 * (size_t)ebase[f]; z.sph_type = h_type + ebase[f];
+        z.desc = h_desc[clbase2[f]];
+        z.desc.first_sphere = z.spheres[0];
+        z.n_atoms = z.desc.n_atoms;
+        z.atoms = h_atoms + 4 * (size_t)ebase[f];          // device layout: 4 slots per entry, the first n_atoms used
+    }
+    return FPK_OK;
+}
+
+extern "C" int fpk_md_characterize(fpk_md *m, const float *xyz, int nframes, const float *zone_xyz, int nzone, fpk_zone *out)
+{
+    if (!m || !xyz || nframes <= 0 || !out || nzone < 0 || (nzone > 0 && !zone_xyz)) return fail(FPK_ERR_BAD_ARG, "fpk_md_characterize: bad arguments");
+    MdDev *q = m->D[0];
+    CK(cudaSetDevice(q->dev));
+    if (nzone > q->nzone_cap) { cudaFree(q->d_zone); q->d_zone = nullptr; q->nzone_cap = 0; CK(cudaMalloc(&q->d_zone, sizeof(float) * 3 * (size_t)nzone)); q->nzone_cap = nzone; }
+    if (nzone > 0) CK(cudaMemcpy(q->d_zone, zone_xyz, sizeof(float) * 3 * (size_t)nzone, cudaMemcpyHostToDevice));
+    const size_t na = (size_t)m->topo.natoms;
+    const int chunk = 256;
+    for (int f0 = 0; f0 < nframes; f0 += chunk) {
+        const int nf = std::min(chunk, nframes - f0);
+        int rc = md_characterize_chunk(m, q, xyz + 3 * na * (size_t)f0, nf, nzone, out + f0);
+        if (rc) { for (int f = 0; f < f0 + nf; f++) fpk_zone_free(&out[f]); return rc; }
+    }
+    return FPK_OK;
+}
+
 extern "C" long long fpk_md_counter(const fpk_md *m, int which)
 {
     if (!m) return -1;

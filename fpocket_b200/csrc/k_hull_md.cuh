@@ -276,6 +276,82 @@ __global__ void k_md_geometry(BatchDev B, int k, float *out /* origin[3], dims[3
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// K7: mdpocket's characterize mode. Replaces, per snapshot, reference src/mdpocket.c:695-745 extract_wanted_vertices: the spheres of the
+// SURVIVING pockets, in rank order and pocket order, listed once for EVERY point of the wanted zone within (float)M_MDP_CUBE_SIDE / 2.0 = 1.0
+// of the centre (dist() <= 1.0: a sphere near three points is listed three times). The list is described as ONE pocket by
+// get_pocket_contacted_atms + set_descriptors (mdpocket.c:446-453): here the entries become the spheres of a second batch ("zone batch":
+// one structure per frame, one cluster each) that the hull and descriptor kernels process unchanged.
+struct ZoneDev {
+    const float *zone;         // [3 * nzone]
+    int nzone;
+    int *ecount;               // [nstruct] entries of every frame (pass 0)
+    const int *ebase;          // [nstruct + 1] exclusive scan (pass 1)
+    int *entry_sphere;         // [E] sphere index inside the frame
+    float4 *z_xyzr; float *z_bary; int4 *z_neigh; uint8_t *z_type;      // [E] the zone batch's sphere arrays
+    int *z_cl_sph, *z_cl_off;  // [E], [E + 2 nstruct + 2]
+    int *z_counts;             // [nstruct * CNT_STRIDE]
+    int *z_mcid;               // [nstruct]
+};
+__global__ void __launch_bounds__(256) k_zone_select(BatchDev B, PocketDev Pk, ZoneDev Z, int pass)
+{
+    __shared__ int s_w[8], s_base;
+    const int k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const StructDev S = B.S[k];
+    const int *counts = B.counts + (size_t)k * CNT_STRIDE;
+    const int npk = counts[CNT_STATUS] == FPK_OK ? counts[CNT_POCKETS] : 0;
+    const int *cl_off = B.cl_off + S.sph_off + k, *cl_sph = B.cl_sph + S.sph_off;
+    const int *rank = Pk.rank_to_cluster + Pk.sbase[k] + k;
+    const float4 *sx = B.s_xyzr + S.sph_off;
+    int nsurv = 0;
+    for (int r = 0; r < npk; r++) nsurv += cl_off[rank[r] + 1] - cl_off[rank[r]];
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    const int e0 = pass ? Z.ebase[k] : 0;
+    for (int j0 = 0; j0 < nsurv; j0 += nt) {
+        const int j = j0 + tid;
+        int s = -1, cnt = 0;
+        if (j < nsurv) {
+            int r = 0, acc = 0;
+            for (; r < npk; r++) { const int m = cl_off[rank[r] + 1] - cl_off[rank[r]]; if (j < acc + m) break; acc += m; }
+            s = cl_sph[cl_off[rank[r]] + (j - acc)];
+            const float4 v = sx[s];
+            for (int z = 0; z < Z.nzone; z++)
+                cnt += (double)f_dist(Z.zone[3 * z], Z.zone[3 * z + 1], Z.zone[3 * z + 2], v.x, v.y, v.z) <= (double)(float)2.0 / 2.0;
+        }
+        const int inc = warp_incl_scan(cnt);
+        if (lane == 31) s_w[wid] = inc;
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < wid; w++) before += s_w[w];
+        if (pass && cnt > 0) {
+            const float4 v = sx[s];
+            for (int q = 0; q < cnt; q++) {
+                const int loc = before + inc - cnt + q, e = e0 + loc;
+                Z.entry_sphere[e] = s;
+                Z.z_xyzr[e] = v; Z.z_neigh[e] = B.s_neigh[S.sph_off + s]; Z.z_type[e] = B.s_type[S.sph_off + s];
+                Z.z_bary[3 * (size_t)e] = B.s_bary[3 * (size_t)(S.sph_off + s)]; Z.z_bary[3 * (size_t)e + 1] = B.s_bary[3 * (size_t)(S.sph_off + s) + 1];
+                Z.z_bary[3 * (size_t)e + 2] = B.s_bary[3 * (size_t)(S.sph_off + s) + 2];
+                Z.z_cl_sph[e] = loc;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < (nt >> 5); w++) t += s_w[w]; s_base += t; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const int E = s_base;
+        if (!pass) Z.ecount[k] = E;
+        else {
+            Z.z_cl_off[e0 + k] = 0; Z.z_cl_off[e0 + k + 1] = E;
+            int *zc = Z.z_counts + (size_t)k * CNT_STRIDE;
+            for (int q = 0; q < CNT_STRIDE; q++) zc[q] = 0;
+            zc[CNT_SPHERES] = E; zc[CNT_CLUSTERS] = E > 0 ? 1 : 0; zc[CNT_STATUS] = E > 0 ? FPK_OK : FPK_ERR_NO_POCKETS;
+            Z.z_mcid[k] = counts[CNT_CLUSTERS] + 1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // K6: dpocket's ligand queries. Replaces reference src/neighbor.c:192 get_mol_vert_neigh, :313 get_mol_ctd_atm_neigh (interface
 // search), :490 count_pocket_lig_vert_ovlp, :598 count_atm_prop_vert_neigh, src/atom.c:264 atm_corsp and the barycentre distance of
 // src/dpocket.c:253-261. The reference finds the pairs by sweeping an x-sorted merged array (sort.c:86 get_sorted_list); the RESULTS

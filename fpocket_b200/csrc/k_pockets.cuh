@@ -32,6 +32,8 @@ struct PocketDev {            // cluster-level arrays, sized after K3 (exact num
     int total_clusters;
     const int *xp_ilist;      // dpocket: interface atoms of structure k at atom_off + k (ascending), count xp_ni[k]; nullptr without ligands
     const int *xp_ni;
+    const int *mc_id;         // [nstruct] or nullptr: the cluster number the Monte-Carlo stream of structure k is keyed with instead of the
+                              // cluster's own (mdpocket's zone record, k_hull_md.cuh K7: it is drawn as cluster n_clusters + 1 of its frame)
 };
 
 struct ClusterScratch {       // per resident block of K3
@@ -774,6 +776,7 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
             const float hx = s_mch[0], hy = s_mch[1], hz = s_mch[2];
             const int niter = prm.nb_mcv_iter;
             const unsigned k0 = (unsigned)prm.mc_seed, k1 = (unsigned)(prm.mc_seed >> 32);
+            const unsigned mcid = Pk.mc_id ? (unsigned)Pk.mc_id[k] : (unsigned)c;
             const int total = 100 * niter;
             for (;;) {
                 int base = 0;
@@ -784,7 +787,7 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                 for (int s = base + lane; s < stop; s += 32) {
                     const int li = s / niter, i = s - li * niter;
                     unsigned o[4];
-                    philox4x32((unsigned)i, (unsigned)li, (unsigned)c, 0u, k0, k1, o);
+                    philox4x32((unsigned)i, (unsigned)li, mcid, 0u, k0, k1, o);
                     const float xr = unif_from_bits(o[0] >> 1, xmin, xmax), yr = unif_from_bits(o[1] >> 1, ymin, ymax),
                                 zr = unif_from_bits(o[2] >> 1, zmin, zmax);
                     bool in = false;

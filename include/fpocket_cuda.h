@@ -203,6 +203,26 @@ int fpk_md_push_frames(fpk_md *m, const float *xyz, int nframes);
  * fpk_md_fetch_grids when frames were pushed since the last refresh (never otherwise: what the caller summed in place stays). */
 int fpk_md_device_grids(fpk_md *m, void **dens, void **freq, size_t *ncell);
 int fpk_md_fetch_grids(fpk_md *m, float *dens, float *freq);    /* D2H, un-normalised sums (normalize_grid stays host, mdpbase.c:354) */
+/* mdpocket's characterize mode (mdpocket.c:360-660), the per-snapshot body of its loop (:428-460): full detection of the frame (ASA and
+ * volumes on, as that mode keeps them), then the spheres of the surviving pockets that lie within 1.0 A of a point of the wanted zone, once
+ * per such point (extract_wanted_vertices, :695-745), the atoms they contact and the descriptor record set_descriptors makes of that list
+ * (never normalised or scored), with the side effects of its ASA pass on the frame's atoms. out[f] is filled for every frame. */
+typedef struct fpk_zone {
+    int32_t status;            /* FPK_OK, FPK_ERR_NO_POCKETS (no sphere of a surviving pocket near the zone) or the frame's detection status */
+    int32_t n_spheres_frame;   /* kept alpha spheres of the frame */
+    int32_t n_pockets_frame;   /* surviving pockets of the frame */
+    int32_t n_entries;         /* length of the zone's sphere list (repeats included) */
+    int32_t *spheres;          /* [n_entries] index of the sphere in the frame's canonical sphere list */
+    float *sph_xyzr;           /* [n_entries*4] what write_pqr_vert prints (mdpocket.c:444) */
+    uint8_t *sph_type;         /* [n_entries] */
+    int32_t n_atoms;
+    int32_t *atoms;            /* [n_atoms] get_pocket_contacted_atms of the list, first-seen order */
+    fpk_desc desc;             /* set_descriptors of the list: volume and hull volume always computed */
+    float *atom_fx;            /* [natoms*4] per-atom ASA side effects after the zone's pass (last writer: the zone) */
+    void *_owner;
+} fpk_zone;
+int fpk_md_characterize(fpk_md *m, const float *xyz, int nframes, const float *zone_xyz, int nzone, fpk_zone *out);
+void fpk_zone_free(fpk_zone *z);
 long long fpk_md_counter(const fpk_md *m, int which);            /* 0 frames, 1 spheres scattered, 2 launches, 3 devices that took frames */
 void fpk_md_end(fpk_md *m);
 

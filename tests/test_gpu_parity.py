@@ -487,6 +487,58 @@ def test_md_grids_with_drug_score_do_not_depend_on_how_frames_are_pushed():
     assert grids[0][0].sum() > 0 and grids[0][1].sum() > 0
 
 
+@pytest.mark.parametrize("case", G.MDCHAR_CASES)
+def test_md_characterize_equals_oracle_and_the_reference(case):
+    """mdpocket's characterize mode on the GPU (fpk_md_characterize: K7 zone selection + the hull / descriptor kernels on the zone batch), one
+    snapshot of the reference's sample trajectory and the first 70 points of its own mdpout_dens_iso_8.pdb: the zone's sphere list (repeats
+    included), the atoms it contacts, its record (Monte-Carlo and hull volume included) and the per-atom effects equal the oracle's bit for bit
+    (canonical order); against the unmodified reference's run the list holds the same spheres the same number of times, the same atoms, and
+    the record agrees within the tolerances of tests/refcompare.py. A second, displaced frame in the same call checks the batching."""
+    import refcompare as RC
+    api = _api()
+    d = G.load(case)
+    st, p = G.inputs(d)
+    zone = d["want.points"]
+    xyz = np.stack([st.x, st.y, st.z], -1)
+    frames = np.stack([xyz, xyz + np.float32(0.5), xyz]).astype(np.float32)
+    m = api.MdPocket(st, p)
+    got = m.characterize(frames, zone)
+    m.close()
+    o = O.characterize(st, p, zone, tets=None, rng_mode=O.RNG_PHILOX)
+    for z in (got[0], got[2]):
+        assert z["status"] == 0 and z["n_spheres_frame"] == o["n_spheres"] and z["n_pockets_frame"] == o["n_pockets"]
+        assert np.array_equal(z["spheres"], o["want_sph"]) and len(z["spheres"]) > 50
+        assert np.array_equal(z["sph_xyzr"], o["sph_xyzr"][o["want_sph"]])
+        assert np.array_equal(z["atoms"], o["want_atoms"])
+        D = o["want_desc"]
+        for n in G.DESC_F:
+            if n in ("score", "drug_score") or n.endswith("_norm"):
+                continue                                  # the zone's record is never normalised or scored (mdpocket.c:453)
+            a, b = np.float32(z["desc"][n]), np.float32(getattr(D, n))
+            assert a == b or (np.isnan(a) and np.isnan(b)), (n, a, b)
+        for n in ("nb_asph", "polarity_score", "charge_score", "n_abpa", "n_atoms", "first_sphere"):
+            assert int(z["desc"][n]) == int(getattr(D, n)), n
+        assert z["desc"]["aa_compo"].tolist() == list(D.aa_compo)
+        assert z["desc"]["volume"] > 0 and z["desc"]["convex_hull_volume"] > 0
+        assert G.eq_nan(z["atom_fx"], o["atom_fx"])
+    assert got[1]["n_spheres_frame"] == o["n_spheres"]           # a rigid shift keeps every sphere; the zone did not move with it
+    assert len(got[1]["spheres"]) != len(got[0]["spheres"])
+    # against the unmodified reference (its order is qhull's): same multiset of spheres, same atoms, record within tolerance
+    keys = G.canon_sphere_keys(o["sph_neigh"])
+    ref_keys = G.canon_sphere_keys(d["sph0.i"][:, :4])
+    if set(ref_keys) == set(keys):
+        mine = sorted(keys[s] for s in got[0]["spheres"])
+        theirs = sorted(ref_keys[s] for s in d["want.sph"])
+        assert mine == theirs
+        assert sorted(got[0]["atoms"].tolist()) == sorted(d["want.atoms"].tolist())
+        F = d["want.desc_f"]
+        for k, n in enumerate(G.DESC_F):
+            if n in RC.PLAIN and n not in RC.RESIDUE_BASED:
+                assert np.isclose(got[0]["desc"][n], F[k], rtol=RC.F_RTOL, atol=2e-5, equal_nan=True), (n, got[0]["desc"][n], F[k])
+        assert np.isclose(got[0]["desc"]["convex_hull_volume"], F[G.DESC_F.index("convex_hull_volume")], rtol=RC.F_RTOL)
+        assert abs(got[0]["desc"]["volume"] - F[G.DESC_F.index("volume")]) < 0.1 * F[G.DESC_F.index("volume")]
+
+
 def test_hull_volume_is_the_same_through_both_routes(tmp_path):
     """K4b has two routes to the same exact integer: one warp per pocket (incremental hull, hull_warp.cuh) and, for what that declines, one
     block per pocket (Delaunay of the centres, k_hull_volume). FPK_HULL_WARP=0 (read once per process) sends every pocket through the second
