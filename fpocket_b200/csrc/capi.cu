@@ -1505,7 +1505,7 @@ static int md_characterize_chunk(fpk_md *m, MdDev *q, const float *xyz, int nf, 
     B2.S = dS2; B2.s_xyzr = Z.z_xyzr; B2.s_bary = Z.z_bary; B2.s_neigh = Z.z_neigh; B2.s_type = Z.z_type;
     B2.cl_off = Z.z_cl_off; B2.cl_sph = Z.z_cl_sph; B2.counts = Z.z_counts;
     B2.prm.min_pock_nb_asph = 0;            // the zone's record is written for every snapshot: always with volume and hull (mdpocket.c:453)
-    P2.clbase = d_clbase2; P2.sbase = d_ebase; P2.total_clusters = (int)NC2; P2.mc_id = Z.z_mcid;
+    P2.clbase = d_clbase2; P2.sbase = d_ebase; P2.total_clusters = (int)NC2; P2.mc_id = Z.z_mcid; P2.sph_uid = Z.entry_sphere;
     const size_t hull_dsm = FPK_BD_BYTES + (HULL_THREADS / 32) * sizeof(WarpCav) + 16;
     const int nhw = (int)std::max(1ll, std::min<long long>((NC2 + 32 * HW_WARPS - 1) / (32 * HW_WARPS), (long long)g_sms * FPK_HW_MINBLOCKS));
     k_hull_warp<<<nhw, HW_THREADS, HW_WARPS * sizeof(HullWarp)>>>(B2, P2, d_cnt + 4, d_fb, d_cnt + 5, 1);

@@ -32,6 +32,8 @@ struct PocketDev {            // cluster-level arrays, sized after K3 (exact num
     int total_clusters;
     const int *xp_ilist;      // dpocket: interface atoms of structure k at atom_off + k (ascending), count xp_ni[k]; nullptr without ligands
     const int *xp_ni;
+    const int *sph_uid;       // nullptr, or per sphere of the batch its identity: mdpocket's zone list holds the same sphere several times, and
+                              // descriptors.c:201 skips a sphere's own copies by POINTER (vc != vcur), not by position
     const int *mc_id;         // [nstruct] or nullptr: the cluster number the Monte-Carlo stream of structure k is keyed with instead of the
                               // cluster's own (mdpocket's zone record, k_hull_md.cuh K7: it is drawn as cluster n_clusters + 1 of its frame)
 };
@@ -828,8 +830,10 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                 const bool apol_i = sty[L[i]] == 0;
                 int napol = 0;
                 if (apol_i) {
+                    const int uid_i = Pk.sph_uid ? Pk.sph_uid[S.sph_off + L[i]] : 0;
                     for (int j = lane; j < n; j += 32) {
                         if (j == i || sty[L[j]] != 0) continue;
+                        if (Pk.sph_uid && Pk.sph_uid[S.sph_off + L[j]] == uid_i) continue;          // another copy of the same sphere (vc != vcur)
                         float4 vj = sx[L[j]];
                         if ((double)(f_dist(vi.x, vi.y, vi.z, vj.x, vj.y, vj.z) - (vj.w + vi.w)) <= 0.) napol++;
                     }
