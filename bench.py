@@ -212,7 +212,9 @@ def main():
     ap.add_argument("--md-frames", type=int, default=2048, help="also measure mdpocket frames/s on a synthetic trajectory of this many frames per GPU (0: skip)")
     ap.add_argument("--md-file-frames", type=int, default=8192, help="also run build/mdpocket_cuda file to file on a DCD trajectory of this many frames (0: skip)")
     ap.add_argument("--dpocket", type=int, default=1000, help="also measure dpocket (BASELINE configs[4]): this many ligand-bound synthetic structures per GPU (0: skip)")
-    ap.add_argument("--large", type=int, default=0, help="also time ONE synthetic complex of this many heavy atoms (BASELINE configs[3]: 150000) on rank 0")
+    ap.add_argument("--large", type=int, default=150000, help="also time ONE synthetic complex of this many heavy atoms (BASELINE configs[3]: 150000) on rank 0 (0: skip)")
+    ap.add_argument("--strong", type=int, default=10000, help="also measure configs[1] as stated: this many structures IN TOTAL, shared out over the GPUs (strong scaling; 0: skip)")
+    ap.add_argument("--md-total-frames", type=int, default=20000, help="also measure configs[2] as stated: a trajectory of this many frames IN TOTAL, frames shared out over the GPUs (0: skip)")
     ap.add_argument("--files", type=int, default=2000, help="also measure the file-to-file -F loop (native PDB reader -> fpk_detect_batch -> native writers) on this many workload structures per GPU (0: skip)")
     ap.add_argument("--cores", type=int, default=0, help="after the workload is generated, pin this process to the first N cores (emulates the per-rank share of a busy multi-GPU box)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -336,6 +338,7 @@ def main():
     # ---- roofline of the dominant kernel ---------------------------------------------------------------------------------------
     peak, peak_src = measured_peak()
     stage_names = ["k_delaunay_filter", "k_cluster", "host_count_roundtrip+alloc", "k_hull_volume", "k_descriptors", "k_finalize+k_atom_fx+k_compact"]
+    # (k_hull_volume = k_hull_warp + k_hull_volume; k_descriptors = k_descriptors_small + k_descriptors: one CUDA-event interval each)
     per_stage = {stage_names[i]: kms[i] / args.steps for i in range(6)}
     dom = max(("k_delaunay_filter", "k_hull_volume", "k_descriptors", "k_cluster"), key=lambda k: per_stage[k])
     # algorithmic bytes: B = 32 N + 32 T + 108 S + 160 P0 per structure; split per kernel in DESIGN.md
@@ -410,6 +413,27 @@ def main():
                       "note": "fpk_detect_batch() on host arrays: chunks of ~1,200 structures through pack -> pinned H2D -> kernels -> pinned D2H -> unpack on 4 host "
                               "threads / CUDA streams; wall clock around the call, results freed inside the timed region"}
 
+    # ---- configs[1] as stated (strong scaling): `--strong` structures IN TOTAL, rank r takes its share of the same workload ---------
+    if args.strong > 0:
+        share = max(1, args.strong // world)
+        sb = batch if share == args.structures else api.Batch(structs[:share], p)
+        sb.run()
+        barrier()
+        sdev = 0.0
+        ssteps = max(1, min(args.steps, 5))
+        for _ in range(ssteps):
+            sb.run()
+            sdev += sb.kernel_ms(7)
+        barrier()
+        ss = torch.tensor([sdev / 1e3], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(ss, op=dist.ReduceOp.MAX)
+        out["config2_strong"] = {"metric": "structures/sec", "value": share * world * ssteps / float(ss[0]), "structures_total": share * world,
+                                 "structures_per_gpu": share, "scaling": "strong", "steps": ssteps, "ms_per_step": float(ss[0]) / ssteps * 1e3,
+                                 "includes": "device-timed whole steps (inputs resident), max over ranks; no collective"}
+        if sb is not batch:
+            sb.close()
+
     # ---- file to file: the -F loop on PDB files, native reader pool -> fpk_detect_batch -> native writer pool ---------
     if f2f_dir is not None:
         from fpocket_b200 import hostio
@@ -474,8 +498,44 @@ def main():
         mm = torch.tensor([tm], device="cuda", dtype=torch.float64)
         if dist is not None:
             dist.all_reduce(mm, op=dist.ReduceOp.MAX)
-        out["mdpocket"] = {"metric": "frames/sec", "value": F * world / float(mm[0]), "frames_per_gpu": F, "atoms": int(s5.n),
+        out["mdpocket"] = {"metric": "frames/sec", "value": F * world / float(mm[0]), "frames_per_gpu": F, "atoms": int(s5.n), "scaling": "weak",
                            "grid": [int(v) for v in dims], "includes": "H2D of every frame, detection, grid scatter, NCCL all-reduce of both grids"}
+        # roofline of the frame path (B_frame = B(structure, ASA / volume / hull off) + 8 B x sum over kept spheres of (26 + (2 floor(r/2) + 1)^3)
+        # for the grid read-modify-write + 4 B x cells / 8 for the per-frame bit mask), from one fetched frame's counts
+        try:
+            one = api.detect(synth.to_structure(s5), api.default_params(do_asa_and_volume=0))
+            rr = one["sph_xyzr"][:, 3]
+            stencil = float(np.sum(26 + (2 * np.floor(rr / 2.0) + 1) ** 3))
+            b_frame = 32 * one["n_sites"] + 32 * one["n_tets"] + 108 * one["n_spheres"] + 160 * one["n_clusters"] + 8 * stencil + int(np.prod(dims)) / 2
+            ach = b_frame * F / float(mm[0]) / 1e9
+            out["mdpocket"]["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                                           "algorithmic_bytes_per_frame": b_frame, "peak_source": peak_src,
+                                           "note": "whole frame path per GPU incl. the H2D of the frame; the kernels are the structure path's (K1 dominates)"}
+        except Exception as ex:          # the roofline is an annotation: never lose the line for it
+            out["mdpocket"]["roofline"] = {"error": str(ex)}
+        # configs[2] as stated (strong scaling): a 20,000-frame trajectory IN TOTAL, contiguous frame blocks per GPU, grids summed once with NCCL
+        if args.md_total_frames > 0:
+            Fs = max(64, args.md_total_frames // world)
+            reps = (Fs + F - 1) // F
+            xs = np.concatenate([xyz] * reps)[:Fs] if reps > 1 else xyz[:Fs]
+            md.set_grid(org, dims)
+            barrier()
+            ts = time.perf_counter()
+            md.push_frames(xs)
+            if dist is not None:
+                gd, gf = md.torch_grids()
+                dist.all_reduce(gd)
+                dist.all_reduce(gf)
+            barrier()
+            ts = time.perf_counter() - ts
+            st_ = torch.tensor([ts], device="cuda", dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(st_, op=dist.ReduceOp.MAX)
+            out["mdpocket"]["strong"] = {"value": Fs * world / float(st_[0]), "unit": "frames/s", "frames_total": Fs * world, "frames_per_gpu": Fs,
+                                         "scaling": "strong", "seconds": float(st_[0]),
+                                         "includes": "BASELINE configs[2]: one trajectory of %d frames of the 5,000-atom protein, contiguous blocks per GPU, H2D of every "
+                                                     "frame, detection, scatter, one NCCL all-reduce of the two grids" % (Fs * world)}
+            del xs
         md.close()
         # file to file: build/mdpocket_fast (fpocket_b200/hostio/mdpocket_fast.cpp): topology PDB and DCD trajectory in through the native readers
         # (double-buffered against the GPU), DX grids / PDB files out through the native writers (byte-identical to the reference's, tests/)
@@ -532,7 +592,11 @@ def main():
         dd = torch.tensor([td], device="cuda", dtype=torch.float64)
         if dist is not None:
             dist.all_reduce(dd, op=dist.ReduceOp.MAX)
+        dp_alg = (32 * N + 32 * T + 108 * S + 160 * P0) / max(1, args.structures) * nd          # the structure path's bytes (the ligand arrays add < 1 %)
         out["dpocket"] = {"metric": "structures/sec", "value": nd * world / float(dd[0]), "structures_per_gpu": nd, "with_explicit_pocket": int(okd),
+                          "roofline": {"bound": "hbm", "achieved": dp_alg / float(dd[0]) / 1e9, "peak": peak, "unit": "GB/s", "frac": dp_alg / float(dd[0]) / 1e9 / peak,
+                                       "traffic": None, "algorithmic_bytes_per_call": dp_alg, "peak_source": peak_src,
+                                       "note": "end to end through fpk_detect_batch (host buffers): pack, H2D, K1-K6, D2H, unpack"},
                           "mean_overlap_of_top_pocket_pct": mean_ovlp,
                           "includes": "fpk_detect_batch on host arrays with the known ligand: detection, ligand queries (K6), the explicit pocket's descriptor "
                                       "record; H2D/D2H inside; 28-atom ligand placed in the best pocket of a first pass"}
@@ -593,9 +657,22 @@ def main():
         bb = api.Batch([big], p)
         bb.run()
         bb.run()
-        out["large_complex"] = {"heavy_atoms": int(big.n_sites), "seconds": bb.kernel_ms(7) / 1e3, "tets": bb.counter(1), "spheres": bb.counter(2),
-                                "pockets": bb.counter(4), "tets_per_s": bb.counter(1) / max(1e-9, bb.kernel_ms(0) / 1e3),
-                                "stage_ms": {"k_delaunay_filter": bb.kernel_ms(0), "k_cluster": bb.kernel_ms(1), "k_hull_volume": bb.kernel_ms(3), "k_descriptors": bb.kernel_ms(4)}}
+        bb.run()
+        nb, tb_, sb_ = int(big.n_sites), bb.counter(1), bb.counter(2)
+        alg_big = 32 * nb + 32 * tb_ + 36 * sb_
+        out["large_complex"] = {"heavy_atoms": nb, "seconds": bb.kernel_ms(7) / 1e3, "tets": tb_, "spheres": sb_,
+                                "pockets": bb.counter(4), "tets_per_s": tb_ / max(1e-9, bb.kernel_ms(0) / 1e3),
+                                "stage_ms": {"k_delaunay_grid": bb.kernel_ms(0), "k_cluster_grid": bb.kernel_ms(1), "k_hull_warp": bb.kernel_ms(3),
+                                             "k_descriptors(+small)": bb.kernel_ms(4)},
+                                "roofline": {"bound": "hbm", "kernel": "k_delaunay_grid", "achieved": alg_big / max(1e-9, bb.kernel_ms(0) * 1e-3) / 1e9, "peak": peak,
+                                             "unit": "GB/s", "frac": alg_big / max(1e-9, bb.kernel_ms(0) * 1e-3) / 1e9 / peak, "traffic": None,
+                                             "algorithmic_bytes_per_launch": alg_big, "ms_per_launch": bb.kernel_ms(0), "peak_source": peak_src},
+                                "includes": "BASELINE configs[3]: ONE complex on the whole GPU (cooperative launches: every resident block on the same triangulation / "
+                                            "clustering), inputs resident, third run"}
+        try:
+            out["large_complex"]["reference"] = json.load(open(os.path.join(ROOT, "profiles", "r02_reference_150k.json")))
+        except Exception:
+            pass
         bb.close()
 
     # ---- CPU baseline: the unmodified reference on this box's cores, bounded sample ------------------------------------------------

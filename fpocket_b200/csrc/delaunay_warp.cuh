@@ -382,7 +382,12 @@ template <bool GRID = false> __device__ __noinline__ int w2_commit_insertion(int
     __syncwarp();
     int mynew = 0x7fffffff, nrim = 0;
     bool bad = false;
-    // ---- pass A: one new tet per rim face (slots allocated warp-wide), outside adjacency both ways ----------------------------------
+    // ---- pass A: one new tet per rim face, outside adjacency both ways -----------------------------------------------------------------
+    // Slots: the k-th new tet takes the slot of the k-th cavity tet (the cavity dies in this very step, its records are in shared memory and
+    // nobody else may touch it: winners' cavities neither overlap nor touch). The star of p almost always has more tets than the cavity
+    // (2 V - 4 faces around V rim vertices against V - 3 + interior edges); only the surplus comes from the free stack / fresh slots, and
+    // only a cavity with more tets than rim faces leaves dead slots behind (pass C). New tets therefore land in cache lines the warp has
+    // just read instead of in slots recycled from anywhere in the mesh, and tets that are neighbours in space stay neighbours in memory.
 #pragma unroll 1
     for (int base = 0; base < 4 * ncav; base += 32) {
         const int e = base + lane, f = e >> 2, q = e & 3;
@@ -390,16 +395,20 @@ template <bool GRID = false> __device__ __noinline__ int w2_commit_insertion(int
         const unsigned m = __ballot_sync(FPK_FULL, isrim);
         if (!m) continue;
         const int cnt = __popc(m), my = __popc(m & ((1u << lane) - 1u));
+        const int kth = nrim + my;                                           // index of this lane's new tet among the warp's new tets
+        const bool reuse = isrim && kth < ncav;
+        const unsigned extra = __ballot_sync(FPK_FULL, isrim && !reuse);     // new tets beyond the cavity's own slots
+        const int nextra = __popc(extra), myx = __popc(extra & ((1u << lane) - 1u));
         int fb = 0;
-        if (lane == 0) fb = atomicAdd(&gc[C_NFREE0 + popstack], -cnt);
+        if (nextra && lane == 0) fb = atomicAdd(&gc[C_NFREE0 + popstack], -nextra);
         fb = __shfl_sync(FPK_FULL, fb, 0);
-        const int fi = fb - 1 - my;                                          // index into the free stack, < 0: take a fresh slot
-        const unsigned fresh = __ballot_sync(FPK_FULL, isrim && fi < 0);
+        const int fi = nextra ? fb - 1 - myx : -1;                           // index into the free stack, < 0: take a fresh slot
+        const unsigned fresh = __ballot_sync(FPK_FULL, isrim && !reuse && fi < 0);
         int nbase = 0;
         if (fresh && lane == 0) nbase = atomicAdd(&gc[C_NTET], __popc(fresh));
         nbase = __shfl_sync(FPK_FULL, nbase, 0);
         if (isrim) {
-            int nt = fi >= 0 ? popst[fi] : nbase + __popc(fresh & ((1u << lane) - 1u));
+            int nt = reuse ? W.id[kth] : (fi >= 0 ? popst[fi] : nbase + __popc(fresh & ((1u << lane) - 1u)));
             if (nt >= c.cap) { bad = true; nt = -1; }
             if (nt >= 0) {
                 const int cur = W.id[f];
@@ -458,16 +467,19 @@ template <bool GRID = false> __device__ __noinline__ int w2_commit_insertion(int
         if (prev >= 0) { TNp(nt)[j] = prev >> 2; TNp(prev >> 2)[prev & 3] = nt; }
     }
     __syncwarp();
-    // ---- pass C: the cavity dies; its slots go to the stack the NEXT sub-round pops ---------------------------------------------------
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&gc[C_NFREE0 + (popstack ^ 1)], ncav);
-    base = __shfl_sync(FPK_FULL, base, 0);
+    // ---- pass C: cavity tets whose slot no new tet took (a cavity with more tets than rim faces: rare) die; their slots go to the stack the
+    // NEXT sub-round pops ------------------------------------------------------------------------------------------------------------------
+    if (nrim < ncav) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&gc[C_NFREE0 + (popstack ^ 1)], ncav - nrim);
+        base = __shfl_sync(FPK_FULL, base, 0);
 #pragma unroll 1
-    for (int i = lane; i < ncav; i += 32) {
-        const int cur = W.id[i];
-        TVp(cur)[0] = T_DEAD;
-        TNp(cur)[0] = firstnew;
-        pushst[base + i] = cur;
+        for (int i = nrim + lane; i < ncav; i += 32) {
+            const int cur = W.id[i];
+            TVp(cur)[0] = T_DEAD;
+            TNp(cur)[0] = firstnew;
+            pushst[base + i - nrim] = cur;
+        }
     }
     if (lane == 0) {
         const int g = c.hg;
