@@ -90,7 +90,25 @@ FPK_HD uint64_t brio_key(int site_id, const double *p, const double mn[3], doubl
         int v = (int)((p[a] - mn[a]) * inv1024);
         q[a] = v < 0 ? 0 : (v > 1023 ? 1023 : v);
     }
+#ifdef FPK_BRIO_MORTON
     uint64_t m = spread10((uint32_t)q[0]) | (spread10((uint32_t)q[1]) << 1) | (spread10((uint32_t)q[2]) << 2);
+#else
+    // Hilbert order inside a round (Skilling's transpose form, 10 bits per axis): unlike the Z curve it never jumps, so the walk from a
+    // warp's previous point to its next one stays short (the order changes nothing in the result: the triangulation is unique)
+    uint32_t X[3] = {(uint32_t)q[0], (uint32_t)q[1], (uint32_t)q[2]};
+    for (uint32_t Q = 1u << 9; Q > 1; Q >>= 1) {
+        const uint32_t P = Q - 1;
+        for (int i = 0; i < 3; i++) {
+            if (X[i] & Q) X[0] ^= P;
+            else { const uint32_t t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+        }
+    }
+    X[1] ^= X[0]; X[2] ^= X[1];
+    uint32_t t = 0;
+    for (uint32_t Q = 1u << 9; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
+    X[0] ^= t; X[1] ^= t; X[2] ^= t;
+    uint64_t m = (spread10(X[0]) << 2) | (spread10(X[1]) << 1) | spread10(X[2]);
+#endif
     return ((uint64_t)round << 54) | (m << 24) | (uint64_t)(uint32_t)site_id;
 }
 
