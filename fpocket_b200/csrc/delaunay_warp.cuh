@@ -40,6 +40,9 @@ struct BlockDel {
     int first4[4];
     int bigw;
     int resume[FPK_MAXWARPS];      // tet at which the warp's capped walk stopped (-1: none)
+    int prew_rank[FPK_MAXWARPS];   // the point a warp located AHEAD of time while it waited for the slower claimants of a sub-round ...
+    int prew_tet[FPK_MAXWARPS];    // ... and where that walk got to
+    int ndone;                     // claimants that have finished the claim phase of the current sub-round
 };
 #define FPK_BD_BYTES ((sizeof(BlockDel) + 15) & ~(size_t)15)
 __device__ __forceinline__ unsigned char *dsm_base() { extern __shared__ __align__(16) unsigned char fpk_dsm[]; return fpk_dsm; }
@@ -213,6 +216,7 @@ template <bool SM, bool GRID = false> __device__ __noinline__ int w2_locate_and_
     // start of the walk: where an earlier attempt on this point stopped, else the warp's last new tet (the previous point of its
     // Morton-ordered chunk), else the hint grid's tet for the point's cell, else the most recent tet of the block
     int t = S.resume[threadIdx.x >> 5];
+    if (t < 0 && !GRID && S.prew_rank[threadIdx.x >> 5] == rank) t = S.prew_tet[threadIdx.x >> 5];      // located ahead of time (w2_prewalk)
     if (t < 0) t = own_hint;
     if (t < 0) {
         const int g = c.hg;
@@ -327,6 +331,48 @@ template <bool SM, bool GRID = false> __device__ __noinline__ int w2_locate_and_
     if (lane == 0) atomicAdd(&cnt[C_NLEVEL], nlev);
     *ncav_out = ncav;
     return ST_CLAIMED;
+}
+
+// A warp that has finished its claim while slower claimants of the block are still at it uses the wait: it walks towards its NEXT point
+// (read-only, the mesh does not change before the barrier) and stops as soon as the last claimant is done, so the barrier is never held up.
+// Where it got to is only a hint for the next sub-round's walk (a tet destroyed meanwhile forwards or has been replaced in place).
+template <bool SM> __device__ __noinline__ void w2_prewalk(int rank_next, int start, int nactive)
+{
+    BlockDel &S = blk();
+    DelaunayCtx &c = S.C;
+    const int *Pi = SM ? sm_sites() : c.Pi;
+    int *const tet = c.tet;
+    __builtin_assume(__isGlobal(tet)); __builtin_assume(__isGlobal(c.order));
+    if (!SM) __builtin_assume(__isGlobal(Pi));
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int p = c.order[rank_next];
+    const P3 pp = ldp(Pi, p);
+    int t = start;
+#pragma unroll 1
+    for (int steps = 0; steps < 2 * WALK_CAP; steps++) {
+        if (*reinterpret_cast<volatile int *>(&S.ndone) >= nactive) break;          // everybody is waiting for the barrier now
+        const int4 v = *reinterpret_cast<const int4 *>(TVp(t));
+        const int4 nb = *reinterpret_cast<const int4 *>(TNp(t));
+        if (v.x == T_DEAD) { t = nb.x; continue; }
+        const int k = inf_slot4(v);
+        if (k >= 0) {
+            if (in_conflict_v(tet, Pi, v, nb, p, pp)) break;
+            t = comp4(nb, k);
+            continue;
+        }
+        int o = 1;
+        if (lane < 4) {
+            int iq = v.x, i1 = v.y, i2 = v.z, i3 = v.w;
+            if (lane & 1) { const int t0 = iq; iq = i1; i1 = i2; i2 = i3; i3 = t0; }
+            if (lane & 2) { int t0 = iq; iq = i2; i2 = t0; t0 = i1; i1 = i3; i3 = t0; }
+            o = orient3d_v(Pi, i1, i2, i3, p, ldp(Pi, i1), ldp(Pi, i2), ldp(Pi, i3), pp);
+            if (!(lane & 1)) o = -o;
+        }
+        const unsigned neg = __ballot_sync(FPK_FULL, o < 0) & 0xfu;
+        if (!neg) break;
+        t = comp4(nb, __ffs(neg) - 1);
+    }
+    if (lane == 0) { S.prew_rank[w] = rank_next; S.prew_tet[w] = t; }
 }
 
 __device__ __forceinline__ bool w2_verify_claims(int rank, int ncav)

@@ -8,6 +8,10 @@
 #include "common.cuh"
 #include "delaunay_warp.cuh"
 
+#ifndef FPK_K1_PREWALK
+#define FPK_K1_PREWALK 1          // use the wait for the slowest claimant of a sub-round to locate the warp's next point (delaunay_warp.cuh w2_prewalk)
+#endif
+
 namespace fpk {
 
 struct DelScratch {
@@ -197,9 +201,10 @@ __device__ int block_delaunay(int pi_cap, const DelScratch &X, int n, const doub
     for (int i = tid; i < hgc * hgc * hgc; i += nt) X.hint[i] = -1;
     for (int i = tid; i < n; i += nt) X.rep[i] = i;
     const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-    if (lane == 0) { S.tinfo[4 * wid] = -1; S.tinfo[4 * wid + 3] = -1; S.resume[wid] = -1; }
+    if (lane == 0) { S.tinfo[4 * wid] = -1; S.tinfo[4 * wid + 3] = -1; S.resume[wid] = -1; S.prew_rank[wid] = -1; S.prew_tet[wid] = -1; }
     __syncthreads();
     if (tid == 0) {
+        S.ndone = 0;
         for (int r = R - 1; r >= 0; r--) if (X.rstart[r] > X.rstart[r + 1]) X.rstart[r] = X.rstart[r + 1];
         X.rstart[0] = 0;
         C.n = n; C.P = X.P; C.Pi = Pi; C.tet = X.tet; C.claim = X.claim; C.mark = X.mark;
@@ -224,12 +229,23 @@ __device__ int block_delaunay(int pi_cap, const DelScratch &X, int n, const doub
         for (;;) {
             int work = w_phase_assign(C, wid) ? 1 : 0;
             if (S.cnt[C_STATUS]) work = 0;
-            if (!__syncthreads_or(work)) break;
+            const int nactive = __syncthreads_count(work) >> 5;            // claimants of this sub-round (all 32 lanes of a warp vote alike)
+            if (!nactive) break;
             // ---- claim: walk + cavity flood on a read-only mesh ----------------------------------------------------------
             const int rank = work ? ti[0] : -1;
             int st = ST_IDLE, ncav = 0;
-            if (rank >= 0) st = sm_pts ? w2_locate_and_claim<true>(rank, ti[3], &ncav) : w2_locate_and_claim<false>(rank, ti[3], &ncav);
+            if (rank >= 0) {
+                st = sm_pts ? w2_locate_and_claim<true>(rank, ti[3], &ncav) : w2_locate_and_claim<false>(rank, ti[3], &ncav);
+                __syncwarp();
+                if (lane == 0) atomicAdd(&S.ndone, 1);
+                // while the slower claimants finish: locate the warp's next point (only a likely winner moves on to it)
+                const int nxt = S.cursor[2 * wid];
+                if (FPK_K1_PREWALK && st == ST_CLAIMED && nxt < S.cursor[2 * wid + 1]) {
+                    if (sm_pts) w2_prewalk<true>(nxt, my_cav().id[0], nactive); else w2_prewalk<false>(nxt, my_cav().id[0], nactive);
+                }
+            }
             __syncthreads();
+            if (tid == 0) S.ndone = 0;
             // ---- verify: a claimant wins iff nothing stronger touched its cavity or rim ---------------------------------
             if (st == ST_CLAIMED) st = w2_verify_claims(rank, ncav) ? ST_WIN : ST_LOST;
             __syncthreads();
