@@ -46,12 +46,13 @@ int main(int argc, char **argv)
         else if (o == "-A") P.min_apol_neigh = atoi(val());
         else if (o == "-p") P.refine_min_apolar_asphere_prop = (float)atof(val());
         else if (o == "--stats") want_stats = 1;
+        else if (o == "--devices") setenv("FPK_DEVICES", val(), 1);       // "all" or "0,1,..": the library shards every block of frames over them and sums the grids
         else if (o == "-w" || o == "--selected_pocket") return refuse("characterize mode (--selected_pocket)");
         else if (o == "-P" || o == "-T" || o == "-x" || o == "-a") return refuse(o.c_str());
         else { fprintf(stderr, "! unknown option %s\n", o.c_str()); return 2; }
     }
     const bool use_traj = !traj.empty();
-    if (use_traj == !listf.empty()) { fprintf(stderr, "usage: %s --trajectory_file T.dcd --trajectory_format dcd -f top.pdb | --pdb_list list.txt  [-o prefix] [-S] [fpocket detection options]\n", argv[0]); return 2; }
+    if (use_traj == !listf.empty()) { fprintf(stderr, "usage: %s --trajectory_file T.dcd --trajectory_format dcd -f top.pdb | --pdb_list list.txt  [-o prefix] [-S] [--devices all|0,1,..] [fpocket detection options]\n", argv[0]); return 2; }
     if (use_traj && strncmp(fmt.c_str(), "dcd", 3)) return refuse("trajectory formats other than dcd");
     std::vector<std::string> snaps;
     if (!use_traj) {
@@ -78,7 +79,7 @@ int main(int argc, char **argv)
     if (fpk_init(nullptr, 0) != FPK_OK) { fprintf(stderr, "! %s\n", fpk_last_error()); return 4; }
     fpk_md *md = fpk_md_begin(&st, &P, score);
     if (!md) { fprintf(stderr, "! libfpocket_cuda: %s\n", fpk_last_error()); return 4; }
-    const int BLOCK = 2368;                                      // frames handed to the library at a time
+    const int BLOCK = 2368 * (fpk_device_count() > 0 ? fpk_device_count() : 1);      // frames handed to the library at a time (a share of 2,368 per device)
     std::vector<float> buf[2];
     buf[0].resize((size_t)3 * na * BLOCK); buf[1].resize((size_t)3 * na * BLOCK);
     float origin[3];

@@ -108,3 +108,36 @@ def test_grids_summed_in_place_by_the_caller_are_what_fetch_returns(score):
     if score:
         assert gd3.sum() > gd.sum() and not np.array_equal(gd3, gd2)
     m.close()
+
+
+def test_mdpocket_fast_on_all_devices_writes_the_same_files(tmp_path):
+    """build/mdpocket_fast --devices all (one trajectory on every GPU of the box, BASELINE configs[2] as stated): the five output files are
+    byte-identical to a one-device run."""
+    import filecmp
+    import os
+    import subprocess
+    import sys
+    import synth
+    exe = os.path.join(O.ROOT, "build", "mdpocket_fast")
+    if not os.path.exists(exe):
+        pytest.skip("build/mdpocket_fast not built")
+    sys.path.insert(0, os.path.join(O.ROOT, "scripts"))
+    import gpu_md_file_to_file as mdf
+    s = _synth(20269870, 1500)
+    rng = np.random.default_rng(12)
+    nfr = 64 * max(2, _ndev()) + 9
+    frames = np.round(s.xyz[None] + rng.normal(scale=0.2, size=(nfr,) + s.xyz.shape).astype(np.float32), 3).astype(np.float32)
+    frames[0] = s.xyz
+    outs = []
+    for tag, extra in (("one", ["--devices", "0"]), ("all", ["--devices", "all"])):
+        d = tmp_path / tag
+        d.mkdir()
+        synth.to_pdb(s, str(d / "top.pdb"))
+        mdf.write_dcd(str(d / "traj.dcd"), frames)
+        r = subprocess.run([exe, "--trajectory_file", "traj.dcd", "--trajectory_format", "dcd", "-f", "top.pdb"] + extra, cwd=str(d), capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs.append(d)
+    names = sorted(f for f in os.listdir(outs[0]) if f.startswith("mdpout"))
+    assert len(names) >= 4
+    for f in names:
+        assert filecmp.cmp(str(outs[0] / f), str(outs[1] / f), shallow=False), f
