@@ -85,12 +85,21 @@ def test_reference_program_with_cuda_search_pocket(tmp_path, n):
     if os.path.exists(REF):
         subprocess.check_call([REF, "-f", "x.pdb"], cwd=str(dr), env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         ref = _info(str(dr / "x_out" / "x_info.txt"))
+        # Set equality modulo the explained tail: the reference loses the spheres of the last <= 4095 bytes of qhull's output
+        # (voronoi.c:138-155; a handful of spheres, DESIGN.md par. 3), which can touch a pocket or two. Every other pocket must be OURS,
+        # atom for atom; the touched ones must still be recognisable.
         assert abs(len(ref) - len(got)) <= 2
-        ours = [_atoms(str(out), k + 1) for k in range(len(got))]
-        for k in range(min(5, len(ref))):
-            a = _atoms(str(dr / "x_out"), k + 1)
+        ours = [frozenset(_atoms(str(out), k + 1)) for k in range(len(got))]
+        theirs = [frozenset(_atoms(str(dr / "x_out"), k + 1)) for k in range(len(ref))]
+        inexact = [a for a in theirs if a not in set(ours)]
+        assert len(inexact) <= 3, (len(inexact), len(theirs))
+        for a in inexact:
             best = max(len(a & b) / float(len(a | b)) for b in ours)
-            assert best >= 0.8, (k, best)
+            assert best >= 0.6, best
+        # the ranking of the pockets both runs have, in the reference's order, is ours
+        common = [a for a in theirs if a in set(ours)]
+        pos = [ours.index(a) for a in common]
+        assert sum(1 for i in range(1, len(pos)) if pos[i] < pos[i - 1]) <= 2, pos
 
 
 def test_batch_driver_writes_what_the_single_file_program_writes(tmp_path):
@@ -182,8 +191,11 @@ def test_mdpocket_program_on_the_library(tmp_path):
         subprocess.check_call([ref, "--pdb_list", "list.txt"], cwd=str(dr), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         rd, ro = _read_dx(str(dr / "mdpout_dens_grid.dx"))
         if rd.shape == dens.shape and np.allclose(ro, org, atol=0.011):
+            # the same stencils on the same spheres; what may differ: the spheres of the reference's lost tail (a few per frame) and the
+            # once-per-pocket centre cell, which follows the pocket's LAST sphere (DESIGN.md par. 5)
             cc = np.corrcoef(rd.ravel(), dens.ravel())[0, 1]
-            assert cc > 0.97, cc
+            assert cc > 0.995, cc
+            assert np.mean(np.abs(rd - dens) > 5.1e-4) < 0.01
 
 
 def test_dpocket_program_on_the_library(tmp_path):
