@@ -898,6 +898,8 @@ extern "C" fpk_batch *fpk_batch_create(const fpk_structure *in, int n, const fpk
     if (!in || n <= 0 || !p) { fail(FPK_ERR_BAD_ARG, "fpk_batch_create: bad arguments"); return nullptr; }
     fpk_batch *b = new fpk_batch();
     if (batch_pack(b, in, n, p, 0.0) || batch_upload(b, in)) { delete b; return nullptr; }
+    // the upload was queued on THIS thread's stream: it must have landed before the handle can be run from any other thread (stream)
+    if (wait_stream() != cudaSuccess) { fail(FPK_ERR_CUDA, "fpk_batch_create: upload failed"); delete b; return nullptr; }
     return b;
 }
 extern "C" int fpk_batch_run(fpk_batch *b) { return b ? batch_run(b) : fail(FPK_ERR_BAD_ARG, "null batch"); }

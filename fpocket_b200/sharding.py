@@ -1,6 +1,7 @@
-"""Multi-GPU plumbing of the path: structures and trajectory frames are independent units, so ranks only need to agree on who
-takes what; the one exchange step of the whole design is the sum of mdpocket's two grids (NCCL all-reduce on the GPU box, any
-torch.distributed backend in tests). Mirrors the loops of reference src/fpmain.c:61-76 (-F list) and src/mdpocket.c:235-271."""
+"""Who takes what when one process per GPU is used (torchrun; bench.py): structures and trajectory frames are independent units, so the
+ranks only need to agree on the assignment, without communication. The one exchange step of the design - the sum of mdpocket's two
+grids - is a plain all-reduce on fpk_md_device_grids() done by the caller; inside ONE process the library shards over its device list
+itself (fpk_init, csrc/capi.cu). Mirrors the loops of reference src/fpmain.c:61-76 (-F list) and src/mdpocket.c:235-271."""
 import numpy as np
 
 
@@ -23,16 +24,3 @@ def shard_frames(n_frames, rank, world):
     per = (n_frames + world - 1) // world
     lo = min(n_frames, rank * per)
     return lo, min(n_frames, lo + per)
-
-
-def broadcast_grid_geometry(t, dist, src=0):
-    """origin[3] (and dims) decided by rank 0 from frame 0 -> every rank (24 bytes)."""
-    dist.broadcast(t, src=src)
-    return t
-
-
-def sum_grids(grids, dist):
-    """density and frequency grids: one all-reduce(sum) each, at the end of the run (before normalize_grid, mdpbase.c:354)."""
-    for g in grids:
-        dist.all_reduce(g)
-    return grids
