@@ -573,11 +573,15 @@ def _points_structure(xyz):
                           np.zeros(n, np.int8), np.zeros(n, np.uint8), (np.float32(20), np.float32(0), np.float32(20)), w=None, same_pdb=1)
 
 
-def test_delaunay_on_degenerate_and_random_point_sets():
-    """The shared-memory fast path has its own exact predicates and symbolic perturbation (delaunay_warp.cuh): cubic lattices (every
+@pytest.mark.parametrize("route", ["block", "grid"])
+def test_delaunay_on_degenerate_and_random_point_sets(route, monkeypatch):
+    """(route = grid: the same sets, one after the other, through the grid-wide kernel k_delaunay_grid - coincident sites, over-sized
+    cavities on the serial path and the symbolic perturbation with the counters in global memory.)
+    The shared-memory fast path has its own exact predicates and symbolic perturbation (delaunay_warp.cuh): cubic lattices (every
     point cospherical / coplanar with many others), duplicated sites, thin slabs and random clouds of many sizes, all in ONE batch,
     must give exactly the oracle's tetrahedra (same perturbation scheme, so the same triangulation of the degenerate sets)."""
     api = _api()
+    monkeypatch.setenv("FPK_GRID_MIN_SITES", "4" if route == "grid" else "1000000")
     rng = np.random.default_rng(11)
     sets = []
     g = np.stack(np.meshgrid(*[np.arange(6)] * 3, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
