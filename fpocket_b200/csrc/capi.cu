@@ -704,7 +704,8 @@ static int batch_run(fpk_batch *b)
         if (full) for (int i = 0; i < b->nHull; i++) del_scratch_layout(a, hHull[i], max_ns, 0, HULL_THREADS, false);
         size_t sacap = 64;
         while (sacap < (size_t)b->max_w + 1) sacap <<= 1;          // the list is sorted by a bitonic network: padded to a power of two
-        for (int i = 0; i < b->nDesc; i++) hDesc[i].sa = a.take<int>(sacap);
+        const size_t nbits = b->max_w > K4_GRID_MIN_ATOMS ? (size_t)b->max_w / 32 + 2 : 1;       // the bit map is only used from K4_GRID_MIN_ATOMS atoms on
+        for (int i = 0; i < b->nDesc; i++) { hDesc[i].sa = a.take<int>(sacap); hDesc[i].bits = a.take<unsigned>(nbits); }
     });
     if (rc) return rc;
     Pk.clbase = b->d_clbase; Pk.sbase = b->d_sbase; Pk.total_clusters = (int)NC;
