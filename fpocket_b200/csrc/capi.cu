@@ -521,8 +521,11 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
         int occg = 1;
         b->grid_dsm = FPK_BD_BYTES + (FPK_K1_THREADS / 32) * sizeof(WarpCav);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occg, k_delaunay_grid, FPK_K1_THREADS, b->grid_dsm);
-        occg = std::max(1, std::min(occg, FPK_K1_MINBLOCKS));
-        if (const char *e = getenv("FPK_GRID_BLOCKS_PER_SM")) occg = std::max(1, std::min(occg, atoi(e)));      // tuning knob (profiles/)
+        // ONE block per SM: the kernel is bound by its grid barriers (82 % of warp samples), whose cost grows with the number of blocks, not by
+        // the number of points in flight - measured on the 150,000-atom complex: 25.2 ms with 148 blocks, 28.7 with 296, 27.8 with 444
+        // (profiles/r02_k1g_blocks_per_sm.log)
+        occg = std::max(1, std::min(occg, 1));
+        if (const char *e = getenv("FPK_GRID_BLOCKS_PER_SM")) occg = std::max(1, std::min(FPK_K1_MINBLOCKS, atoi(e)));      // tuning knob (profiles/)
         b->nGridBlocks = g_sms * occg;
         int occc = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occc, k_cluster_grid, 256, 0);
