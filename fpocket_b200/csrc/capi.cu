@@ -150,10 +150,19 @@ static int ensure_init()
 // thread sleeps). Measured on one B200 with the process pinned to 2, 4 and 16 cores (4 library threads; profiles/README.md): e2e
 // 7,102 / 7,191 / 7,218 structures/s spinning, 7,191 / 7,233 / 7,239 blocking - the host threads are not what bounds the call, so
 // spinning stays the default and blocking is a knob for boxes where the cores are needed elsewhere.
+// Round 2, 8 GPUs on a 32-core box (4 cores per rank; profiles/r02_8gpu_trace.txt): fpk_detect_batch is the same either way, but mdpocket's push
+// loop (a staging helper thread beside the spinning caller) gains 10 % when the waits sleep. Default therefore: block when this process has fewer
+// than 8 cores per device to itself (torchrun's LOCAL_WORLD_SIZE tells how many ranks share the box), spin otherwise; FPK_SYNC=spin|block overrides.
 static bool block_sync()
 {
-    const char *e = getenv("FPK_SYNC");
-    return e && !strcmp(e, "block");
+    static const int mode = []() {
+        if (const char *e = getenv("FPK_SYNC")) return !strcmp(e, "block") ? 1 : 0;
+        const int cores = (int)std::thread::hardware_concurrency();
+        const char *lw = getenv("LOCAL_WORLD_SIZE");
+        const int ranks = lw ? std::max(1, atoi(lw)) : 1;
+        return (cores > 0 && cores / ranks < 8) ? 1 : 0;
+    }();
+    return mode != 0;
 }
 static cudaError_t wait_stream()
 {
