@@ -1593,28 +1593,51 @@ __global__ void __launch_bounds__(128) k_finalize(BatchDev B, PocketDev Pk)
     const fpk_params &prm = B.prm;
     __shared__ float s_f[10];
     __shared__ int s_i[6];
-    // ---- pocket.c:664-785: min/max with the reference's sequential-scan semantics (first value NaN poisons both bounds) ----------
-    if (tid < 7) {
-        // 0 as_max_dst 1 as_density 2 mean_loc_hyd_dens 3 flex 4 apolar_asphere_prop | 5 polarity_score 6 nb_asph (ints)
-        if (tid < 5) {
-            float M = 0, m = 0;
-            for (int i = 0; i < nc; i++) {
-                const fpk_desc &d = D[i];
-                float v = tid == 0 ? d.as_max_dst : tid == 1 ? d.as_density : tid == 2 ? d.mean_loc_hyd_dens : tid == 3 ? d.flex : d.apolar_asphere_prop;
-                if (i == 0) M = m = v;
-                else if (v > M) M = v;
-                else if (v < m) m = v;
+    // ---- pocket.c:664-785: min/max over all clusters. The reference scans in list order: M = m = first value, then "if (v > M) M = v; else if
+    // (v < m) m = v". Since m <= M always, that is the plain maximum and minimum over the values that compare at all (a NaN never does), EXCEPT
+    // that a NaN FIRST value stays in both bounds for good. So: block-wide max / min that skip NaNs, then the first value's NaN rule.
+    {
+        __shared__ float s_rf[4][10];
+        __shared__ int s_ri[4][4];
+        float fM[5], fm[5];
+        int iM[2], im[2];
+#pragma unroll
+        for (int q = 0; q < 5; q++) { fM[q] = -3.4e38f; fm[q] = 3.4e38f; }
+        iM[0] = iM[1] = -2147483647 - 1; im[0] = im[1] = 2147483647;
+        for (int i = tid; i < nc; i += nt) {
+            const fpk_desc &d = D[i];
+            const float v[5] = {d.as_max_dst, d.as_density, d.mean_loc_hyd_dens, d.flex, d.apolar_asphere_prop};
+#pragma unroll
+            for (int q = 0; q < 5; q++) { if (v[q] > fM[q]) fM[q] = v[q]; if (v[q] < fm[q]) fm[q] = v[q]; }
+            iM[0] = max(iM[0], d.polarity_score); im[0] = min(im[0], d.polarity_score);
+            iM[1] = max(iM[1], d.nb_asph); im[1] = min(im[1], d.nb_asph);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int q = 0; q < 5; q++) { fM[q] = fmaxf(fM[q], __shfl_xor_sync(0xffffffffu, fM[q], o)); fm[q] = fminf(fm[q], __shfl_xor_sync(0xffffffffu, fm[q], o)); }
+#pragma unroll
+            for (int q = 0; q < 2; q++) { iM[q] = max(iM[q], __shfl_xor_sync(0xffffffffu, iM[q], o)); im[q] = min(im[q], __shfl_xor_sync(0xffffffffu, im[q], o)); }
+        }
+        if ((tid & 31) == 0) {
+            for (int q = 0; q < 5; q++) { s_rf[tid >> 5][2 * q] = fM[q]; s_rf[tid >> 5][2 * q + 1] = fm[q]; }
+            for (int q = 0; q < 2; q++) { s_ri[tid >> 5][2 * q] = iM[q]; s_ri[tid >> 5][2 * q + 1] = im[q]; }
+        }
+        __syncthreads();
+        if (tid == 0 && nc > 0) {
+            const fpk_desc &d0 = D[0];
+            const float v0[5] = {d0.as_max_dst, d0.as_density, d0.mean_loc_hyd_dens, d0.flex, d0.apolar_asphere_prop};
+            for (int q = 0; q < 5; q++) {
+                float M = s_rf[0][2 * q], m = s_rf[0][2 * q + 1];
+                for (int w = 1; w < (nt >> 5); w++) { M = fmaxf(M, s_rf[w][2 * q]); m = fminf(m, s_rf[w][2 * q + 1]); }
+                if (v0[q] != v0[q]) M = m = v0[q];              // the first value is a NaN: nothing compares with it afterwards
+                s_f[2 * q] = M; s_f[2 * q + 1] = m;
             }
-            s_f[2 * tid] = M; s_f[2 * tid + 1] = m;
-        } else {
-            int M = 0, m = 0;
-            for (int i = 0; i < nc; i++) {
-                int v = tid == 5 ? D[i].polarity_score : D[i].nb_asph;
-                if (i == 0) M = m = v;
-                else if (v > M) M = v;
-                else if (v < m) m = v;
+            for (int q = 0; q < 2; q++) {
+                int M = s_ri[0][2 * q], m = s_ri[0][2 * q + 1];
+                for (int w = 1; w < (nt >> 5); w++) { M = max(M, s_ri[w][2 * q]); m = min(m, s_ri[w][2 * q + 1]); }
+                s_i[2 * q] = M; s_i[2 * q + 1] = m;
             }
-            s_i[2 * (tid - 5)] = M; s_i[2 * (tid - 5) + 1] = m;
         }
     }
     __syncthreads();
