@@ -1192,6 +1192,8 @@ struct SmallWarp {
     unsigned char candapol[ASA_CAND];
     fpk_desc d;
     int cursor;
+    int entu[4 * K4S_NMAX];             // entry (sphere, slot) -> position of its atom; then: first occurrence of the atom's residue id (descriptors.c:408)
+    unsigned cnt4[4 * K4S_NMAX];        // per contacted atom the four SASA tallies (each <= 100), one byte each: free points at 1.4 / 2.2, apolar / polar burying atoms
 };
 __global__ void __launch_bounds__(K4S_THREADS, 8) k_descriptors_small(BatchDev B, PocketDev Pk, int *chunk_counter, AtomGrid AG, unsigned char *done)
 {
@@ -1234,8 +1236,8 @@ __global__ void __launch_bounds__(K4S_THREADS, 8) k_descriptors_small(BatchDev B
             const int4 *sn = B.s_neigh + S.sph_off;
             const uint8_t *sty = B.s_type + S.sph_off;
             const float *sb = B.s_bary + 3 * (size_t)S.sph_off;
-            int *uat = Pk.cl_atoms + 4 * (size_t)R, *entu = Pk.ent_u + 4 * (size_t)R;
-            int *acc = Pk.acc + 16 * (size_t)R;
+            int *uat = Pk.cl_atoms + 4 * (size_t)R;
+            int *const entu = W.entu;                 // this kernel keeps its per-cluster scratch in shared memory (k_descriptors: global, Pk.ent_u / Pk.acc)
             float *fxv = Pk.fx_val + 16 * (size_t)R;
             fpk_desc *D = Pk.desc + item;
             const int A0 = S.atom_off, Q0 = S.prop_off;
@@ -1275,7 +1277,6 @@ __global__ void __launch_bounds__(K4S_THREADS, 8) k_descriptors_small(BatchDev B
                 U += __popc(bal);
                 __syncwarp();
             }
-            for (int u = lane; u < 4 * U; u += 32) acc[u] = 0;
             // ---- 3a. the sequential float sums, in the reference's order (descriptors.c:186-236, same code as k_descriptors' warp 0) ---
             float as_density = 0.0f, as_max_dst = -1.0f, lane_max = -1.0f;
             int mlhd_cnt = 0, nAlphaApol = 0;
@@ -1516,48 +1517,47 @@ __global__ void __launch_bounds__(K4S_THREADS, 8) k_descriptors_small(BatchDev B
                         c14 += __shfl_xor_sync(0xffffffffu, c14, d); c22 += __shfl_xor_sync(0xffffffffu, c22, d);
                         cap += __shfl_xor_sync(0xffffffffu, cap, d); cpo += __shfl_xor_sync(0xffffffffu, cpo, d);
                     }
-                    if (lane == 0) *reinterpret_cast<int4 *>(acc + 4 * (size_t)u) = make_int4(c14, c22, cap, cpo);
+                    if (lane == 0) W.cnt4[u] = (unsigned)c14 | ((unsigned)c22 << 8) | ((unsigned)cap << 16) | ((unsigned)cpo << 24);
                     __syncwarp();
                 }
             }
             if (!fits) continue;                    // k_descriptors takes it (done[item] stays 0); nothing written so far is read by anyone else
             __syncwarp();
-            // ---- 6a. per contacted atom: the two areas and the side effects on the atom (asa.c:330-337,384-396) ----------------------------
-            if (full) {
-                for (int u = lane; u < U; u += 32) {
-                    const int a = Q0 + uat[u];
-                    const size_t ga = (size_t)A0 + uat[u];
-                    const float crad = B.arad[a];
-                    const bool apolar_atom = (double)B.aen[a] < 2.8;
-                    const float a14 = (float)((4 * 3.1415926535897932384626433832795 * ((double)crad + 1.4) * ((double)crad + 1.4) / (double)(float)100) * (double)acc[4 * u]);
-                    const float a22 = (float)((4 * 3.1415926535897932384626433832795 * ((double)crad + 2.2) * ((double)crad + 2.2) / (double)(float)100) * (double)acc[4 * u + 1]);
-                    const float na = (float)acc[4 * u + 2], np = (float)acc[4 * u + 3];
-                    fxv[4 * u + 0] = na / (na + np);
-                    fxv[4 * u + 1] = a14;
-                    float flag = 0.0f;
-                    atomicMax(&Pk.fx_who[2 * ga], c);
-                    if (!apolar_atom && a22 < a14 && (double)a14 <= 10.0 && (double)a22 >= 0.0) {
-                        fxv[4 * u + 2] = a22 - a14;
-                        flag = 1.0f;
-                        atomicMax(&Pk.fx_who[2 * ga + 1], c);
-                    }
-                    fxv[4 * u + 3] = flag;
-                    acc[4 * u] = __float_as_int(a14); acc[4 * u + 1] = __float_as_int(a22); acc[4 * u + 2] = apolar_atom ? 1 : 0; acc[4 * u + 3] = (int)flag;
-                }
-            }
-            __syncwarp();
-            // ---- 6b. the float sums whose order is the reference's (atoms in first-seen order, probe 1.4 then 2.2) ---------------------------
+            // ---- 6. per contacted atom: the two areas and the side effects on the atom (asa.c:330-337,384-396), and - 32 atoms at a time, handed
+            // round by shuffles so that every lane adds the same values in the same order - the float sums whose order is the reference's (atoms
+            // in first-seen order, probe 1.4 then 2.2; the two passes of the reference touch disjoint sums and are fused)
             float apol14 = 0.0f, pol14 = 0.0f, v14 = 0.0f, apol22 = 0.0f, pol22 = 0.0f, v22 = 0.0f;
             int nabpa = 0;
             if (full) {
                 for (int b0 = 0; b0 < U; b0 += 32) {
                     const int u = b0 + lane;
-                    int4 a = make_int4(0, 0, 0, 0);
-                    if (u < U) a = *reinterpret_cast<const int4 *>(acc + 4 * (size_t)u);
+                    float my14 = 0.0f, my22 = 0.0f;
+                    int myapol = 0, myflag = 0;
+                    if (u < U) {
+                        const int a = Q0 + uat[u];
+                        const size_t ga = (size_t)A0 + uat[u];
+                        const float crad = B.arad[a];
+                        const bool apolar_atom = (double)B.aen[a] < 2.8;
+                        const unsigned c4 = W.cnt4[u];
+                        const float a14 = (float)((4 * 3.1415926535897932384626433832795 * ((double)crad + 1.4) * ((double)crad + 1.4) / (double)(float)100) * (double)(int)(c4 & 0xffu));
+                        const float a22 = (float)((4 * 3.1415926535897932384626433832795 * ((double)crad + 2.2) * ((double)crad + 2.2) / (double)(float)100) * (double)(int)((c4 >> 8) & 0xffu));
+                        const float na = (float)(int)((c4 >> 16) & 0xffu), np = (float)(int)(c4 >> 24);
+                        fxv[4 * u + 0] = na / (na + np);
+                        fxv[4 * u + 1] = a14;
+                        float flag = 0.0f;
+                        atomicMax(&Pk.fx_who[2 * ga], c);
+                        if (!apolar_atom && a22 < a14 && (double)a14 <= 10.0 && (double)a22 >= 0.0) {
+                            fxv[4 * u + 2] = a22 - a14;
+                            flag = 1.0f;
+                            atomicMax(&Pk.fx_who[2 * ga + 1], c);
+                        }
+                        fxv[4 * u + 3] = flag;
+                        my14 = a14; my22 = a22; myapol = apolar_atom ? 1 : 0; myflag = (int)flag;
+                    }
                     const int cntu = min(32, U - b0);
                     for (int q = 0; q < cntu; q++) {
-                        const float a14 = __int_as_float(__shfl_sync(0xffffffffu, a.x, q)), a22 = __int_as_float(__shfl_sync(0xffffffffu, a.y, q));
-                        const int apolar_atom = __shfl_sync(0xffffffffu, a.z, q), flag = __shfl_sync(0xffffffffu, a.w, q);
+                        const float a14 = __shfl_sync(0xffffffffu, my14, q), a22 = __shfl_sync(0xffffffffu, my22, q);
+                        const int apolar_atom = __shfl_sync(0xffffffffu, myapol, q), flag = __shfl_sync(0xffffffffu, myflag, q);
                         if (apolar_atom) { apol14 = apol14 + a14; apol22 = apol22 + a22; }
                         else { pol14 = pol14 + a14; nabpa += flag; pol22 = pol22 + a22; }
                         v14 = v14 + a14; v22 = v22 + a22;
