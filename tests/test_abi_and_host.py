@@ -38,8 +38,9 @@ def test_ctypes_mirror_matches_header_layout():
 #include <stddef.h>
 #include "fpocket_cuda.h"
 int main(void) {
-  printf("%zu %zu %zu %zu\n", sizeof(fpk_params), sizeof(fpk_structure), sizeof(fpk_desc), sizeof(fpk_result));
-  printf("%zu %zu %zu %zu\n", offsetof(fpk_params, mc_seed), offsetof(fpk_structure, xlig), offsetof(fpk_desc, final_rank), offsetof(fpk_result, _owner));
+  printf("%zu %zu %zu %zu %zu\n", sizeof(fpk_params), sizeof(fpk_structure), sizeof(fpk_desc), sizeof(fpk_result), sizeof(fpk_zone));
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", offsetof(fpk_params, mc_seed), offsetof(fpk_structure, xlig), offsetof(fpk_desc, final_rank), offsetof(fpk_result, _owner),
+         offsetof(fpk_params, lig_interface_method), offsetof(fpk_result, lig_volume), offsetof(fpk_zone, atom_fx));
   return 0; }'''
     tmp = os.path.join(ROOT, "tests", "hostemu", "_build")
     os.makedirs(tmp, exist_ok=True)
@@ -47,9 +48,10 @@ int main(void) {
     open(cfile, "w").write(src)
     subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", exe, cfile])
     out = subprocess.check_output([exe]).decode().split()
-    sizes, offs = [int(v) for v in out[:4]], [int(v) for v in out[4:]]
-    assert sizes == [C.sizeof(capi.FpkParams), C.sizeof(capi.FpkStructure), C.sizeof(capi.FpkDesc), C.sizeof(capi.FpkResult)]
-    assert offs == [capi.FpkParams.mc_seed.offset, capi.FpkStructure.xlig.offset, capi.FpkDesc.final_rank.offset, capi.FpkResult._owner.offset]
+    sizes, offs = [int(v) for v in out[:5]], [int(v) for v in out[5:]]
+    assert sizes == [C.sizeof(capi.FpkParams), C.sizeof(capi.FpkStructure), C.sizeof(capi.FpkDesc), C.sizeof(capi.FpkResult), C.sizeof(capi.FpkZone)]
+    assert offs == [capi.FpkParams.mc_seed.offset, capi.FpkStructure.xlig.offset, capi.FpkDesc.final_rank.offset, capi.FpkResult._owner.offset,
+                    capi.FpkParams.lig_interface_method.offset, capi.FpkResult.lig_volume.offset, capi.FpkZone.atom_fx.offset]
 
 
 def test_no_cpu_fallback():
