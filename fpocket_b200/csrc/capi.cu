@@ -269,6 +269,7 @@ struct HostResults {            // owner of the host arrays of one fetch: one pi
 
 struct fpk_batch {
     int n = 0;
+    int n_cap = 0;                     // mdpocket: frames the skeleton was built for (n may be set lower, md_prepare)
     int dev = -1;                      // the device this context's arenas live on
     fpk_params prm;
     std::vector<fpk_structure> sane;   // the caller's structures, unusable ones replaced by an empty structure
@@ -648,7 +649,7 @@ static int batch_run(fpk_batch *b)
     CK(cudaMemsetAsync(B.counts, 0, sizeof(int) * (size_t)n * CNT_STRIDE));
     CK(cudaEventRecord(b->ev[0]));
     for (int kb : b->big) {            // large structures: one cooperative launch each, every resident block on the same triangulation
-        if (b->S[kb].nsites < 4) continue;
+        if (b->S[kb].nsites < 4 || kb >= n) continue;
         void *args[] = {(void *)&B, (void *)&b->hGridX, (void *)&b->dGrid, (void *)&kb};
         CK(cudaLaunchCooperativeKernel((void *)k_delaunay_grid, dim3(b->nGridBlocks), dim3(FPK_K1_THREADS), args, b->grid_dsm, cudaStreamPerThread));
         b->launches++;
@@ -656,6 +657,7 @@ static int batch_run(fpk_batch *b)
     k_delaunay_filter<<<b->nDel, FPK_K1_THREADS, b->k1_dsm>>>(B, b->dDel, b->k1_picap);
     CK(cudaEventRecord(b->ev[1]));
     for (int kb : b->big) {
+        if (kb >= n) continue;
         void *args[] = {(void *)&B, (void *)&b->hCluG, (void *)&kb};
         CK(cudaLaunchCooperativeKernel((void *)k_cluster_grid, dim3(b->nCluGridBlocks), dim3(256), args, 0, cudaStreamPerThread));
         b->launches++;
@@ -1123,7 +1125,9 @@ static int md_prepare(fpk_md *m, MdDev *q, int nframes, bool characterize = fals
 {
     // (re)build the batch skeleton for `nframes` frames: properties uploaded once, coordinates per push
     fpk_batch *&slot = characterize ? q->bc : q->b;
-    if (slot && slot->n == nframes) return FPK_OK;
+    // a skeleton built for more frames serves fewer (the last chunk of a push, a shorter push): all frames have the same shape, so the first
+    // nframes entries of every array are exactly the skeleton of nframes frames; rebuilding it (pack, arenas, uploads) cost more than a chunk's kernels
+    if (slot && slot->n_cap >= nframes) { slot->n = nframes; slot->B.nstruct = nframes; return FPK_OK; }
     delete slot;
     slot = new fpk_batch();
     fpk_batch *b = slot;
@@ -1152,6 +1156,7 @@ static int md_prepare(fpk_md *m, MdDev *q, int nframes, bool characterize = fals
     for (int i = 0; i < t.natoms; i++) if (!(t.flags[i] & FPK_ATOM_H)) s2a.push_back(i);
     CK(cudaMemcpy(const_cast<int *>(B.site2atom), s2a.data(), sizeof(int) * s2a.size(), cudaMemcpyHostToDevice));
     b->h2d += (long long)(na * 22 + s2a.size() * 4);
+    b->n_cap = nframes;
     return FPK_OK;
 }
 
@@ -1279,7 +1284,10 @@ extern "C" int fpk_md_grid_from_frame(fpk_md *m, const float *xyz, float origin[
 static int md_push_on(fpk_md *m, MdDev *q, const float *xyz, int nframes)
 {
     const size_t na = (size_t)m->topo.natoms;
-    const int chunk_max = std::max(256, g_sms * 2 * 8);         // a whole number of structures per resident K1 block (2 per SM)
+    // frames per launch of the pipeline; the next chunk is staged (host copy into pinned memory + H2D) meanwhile. Measured on the 20,000-frame
+    // trajectory (profiles/r02_md_chunk_sweep2.log): 1,184 frames per chunk 10,333 frames/s, 2,368 9,068 (a 2,048-frame push: 10,264 / 10,324)
+    int chunk_max = std::max(256, g_sms * 8);
+    if (const char *e = getenv("FPK_MD_CHUNK")) chunk_max = std::max(64, atoi(e));      // tuning knob (profiles/)
     int rc = md_ensure_staging(m, q, std::min(chunk_max, nframes));
     typedef std::chrono::steady_clock clk;
     double t_run = 0, t_scatter = 0, t_prep = 0;
