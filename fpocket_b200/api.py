@@ -213,7 +213,7 @@ class MdPocket:
             C.memmove(d.ctypes.data, C.addressof(z.desc), capi.DESC_DTYPE.itemsize)
             res.append({"status": z.status, "n_spheres_frame": z.n_spheres_frame, "n_pockets_frame": z.n_pockets_frame,
                         "spheres": capi._arr(z.spheres, (n,), np.int32), "sph_xyzr": capi._arr(z.sph_xyzr, (n, 4), np.float32),
-                        "sph_type": capi._arr(z.sph_type, (n,), np.uint8), "atoms": capi._arr(z.atoms, (z.n_atoms,), np.int32),
+                        "sph_type": capi._arr(z.sph_type, (n,), np.uint8), "sph_pocket": capi._arr(z.sph_pocket, (n,), np.int32), "atoms": capi._arr(z.atoms, (z.n_atoms,), np.int32),
                         "desc": d[0], "atom_fx": capi._arr(z.atom_fx, (self.natoms, 4), np.float32) if z.atom_fx else None})
             self.lib.fpk_zone_free(C.byref(z))
         return res

@@ -96,7 +96,7 @@ class FpkResult(C.Structure):
 class FpkZone(C.Structure):
     _fields_ = [
         ("status", C.c_int32), ("n_spheres_frame", C.c_int32), ("n_pockets_frame", C.c_int32), ("n_entries", C.c_int32),
-        ("spheres", _ip), ("sph_xyzr", _fp), ("sph_type", _bp), ("n_atoms", C.c_int32), ("atoms", _ip), ("desc", FpkDesc),
+        ("spheres", _ip), ("sph_xyzr", _fp), ("sph_type", _bp), ("sph_pocket", _ip), ("n_atoms", C.c_int32), ("atoms", _ip), ("desc", FpkDesc),
         ("atom_fx", _fp), ("_owner", C.c_void_p),
     ]
 

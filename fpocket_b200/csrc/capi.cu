@@ -1497,7 +1497,7 @@ static int md_characterize_chunk(fpk_md *m, MdDev *q, const float *xyz, int nf, 
     memset(&P2, 0, sizeof P2);
     rc = arena_build(q->A3, [&](Arena &a) {
         d_ebase = a.take<int>(nf + 1); d_clbase2 = a.take<int>(nf + 1); dS2 = a.take<StructDev>(nf);
-        Z.entry_sphere = a.take<int>(E + 1);
+        Z.entry_sphere = a.take<int>(E + 1); Z.entry_pocket = a.take<int>(E + 1);
         Z.z_xyzr = a.take<float4>(E + 1); Z.z_bary = a.take<float>(3 * E + 3); Z.z_neigh = a.take<int4>(E + 1); Z.z_type = a.take<uint8_t>(E + 1);
         Z.z_cl_sph = a.take<int>(E + 1); Z.z_cl_off = a.take<int>(E + 2 * (size_t)nf + 2);
         Z.z_counts = a.take<int>((size_t)nf * CNT_STRIDE); Z.z_mcid = a.take<int>(nf);
@@ -1538,17 +1538,19 @@ static int md_characterize_chunk(fpk_md *m, MdDev *q, const float *xyz, int nf, 
     q->launches += 5;
     // ---- results -----------------------------------------------------------------------------------------------------------------------
     ZoneOwner *own = new ZoneOwner();
-    const size_t bytes = 4 * (size_t)E + 16 * (size_t)E + (size_t)E + 16 * (size_t)E + sizeof(fpk_desc) * (size_t)NC2 + 16 * (size_t)b->tot_atoms + 1024;
+    const size_t bytes = 8 * (size_t)E + 16 * (size_t)E + (size_t)E + 16 * (size_t)E + sizeof(fpk_desc) * (size_t)NC2 + 16 * (size_t)b->tot_atoms + 1024;
     own->blk.resize(bytes);
     char *w = own->blk.data();
     auto carve = [&](size_t n) { char *r = w; w += (n + 15) & ~(size_t)15; return r; };
     int *h_sph = (int *)carve(4 * (size_t)E);
+    int *h_pk = (int *)carve(4 * (size_t)E);
     float *h_xyzr = (float *)carve(16 * (size_t)E);
     uint8_t *h_type = (uint8_t *)carve((size_t)E);
     int *h_atoms = (int *)carve(16 * (size_t)E);
     fpk_desc *h_desc = (fpk_desc *)carve(sizeof(fpk_desc) * (size_t)NC2);
     float *h_fx = (float *)carve(16 * (size_t)b->tot_atoms);
     e = cudaMemcpy(h_sph, Z.entry_sphere, 4 * (size_t)E, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(h_pk, Z.entry_pocket, 4 * (size_t)E, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(h_xyzr, Z.z_xyzr, 16 * (size_t)E, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(h_type, Z.z_type, (size_t)E, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(h_atoms, P2.cl_atoms, 16 * (size_t)E, cudaMemcpyDeviceToHost);
@@ -1562,7 +1564,7 @@ static int md_characterize_chunk(fpk_md *m, MdDev *q, const float *xyz, int nf, 
         if (ecount[f] == 0) continue;
         z.status = FPK_OK;
         z.n_entries = ecount[f];
-        z.spheres = h_sph + ebase[f]; z.sph_xyzr = h_xyzr + 4 * (size_t)ebase[f]; z.sph_type = h_type + ebase[f];
+        z.spheres = h_sph + ebase[f]; z.sph_xyzr = h_xyzr + 4 * (size_t)ebase[f]; z.sph_type = h_type + ebase[f]; z.sph_pocket = h_pk + ebase[f];
         z.desc = h_desc[clbase2[f]];
         z.desc.first_sphere = z.spheres[0];
         z.n_atoms = z.desc.n_atoms;

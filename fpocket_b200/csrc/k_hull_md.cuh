@@ -287,6 +287,7 @@ struct ZoneDev {
     int *ecount;               // [nstruct] entries of every frame (pass 0)
     const int *ebase;          // [nstruct + 1] exclusive scan (pass 1)
     int *entry_sphere;         // [E] sphere index inside the frame
+    int *entry_pocket;         // [E] 1-based rank of the pocket it belongs to (vertice->resid)
     float4 *z_xyzr; float *z_bary; int4 *z_neigh; uint8_t *z_type;      // [E] the zone batch's sphere arrays
     int *z_cl_sph, *z_cl_off;  // [E], [E + 2 nstruct + 2]
     int *z_counts;             // [nstruct * CNT_STRIDE]
@@ -309,9 +310,9 @@ __global__ void __launch_bounds__(256) k_zone_select(BatchDev B, PocketDev Pk, Z
     const int e0 = pass ? Z.ebase[k] : 0;
     for (int j0 = 0; j0 < nsurv; j0 += nt) {
         const int j = j0 + tid;
-        int s = -1, cnt = 0;
+        int s = -1, cnt = 0, r = 0;
         if (j < nsurv) {
-            int r = 0, acc = 0;
+            int acc = 0;
             for (; r < npk; r++) { const int m = cl_off[rank[r] + 1] - cl_off[rank[r]]; if (j < acc + m) break; acc += m; }
             s = cl_sph[cl_off[rank[r]] + (j - acc)];
             const float4 v = sx[s];
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(256) k_zone_select(BatchDev B, PocketDev Pk, Z
             const float4 v = sx[s];
             for (int q = 0; q < cnt; q++) {
                 const int loc = before + inc - cnt + q, e = e0 + loc;
-                Z.entry_sphere[e] = s;
+                Z.entry_sphere[e] = s; Z.entry_pocket[e] = r + 1;
                 Z.z_xyzr[e] = v; Z.z_neigh[e] = B.s_neigh[S.sph_off + s]; Z.z_type[e] = B.s_type[S.sph_off + s];
                 Z.z_bary[3 * (size_t)e] = B.s_bary[3 * (size_t)(S.sph_off + s)]; Z.z_bary[3 * (size_t)e + 1] = B.s_bary[3 * (size_t)(S.sph_off + s) + 1];
                 Z.z_bary[3 * (size_t)e + 2] = B.s_bary[3 * (size_t)(S.sph_off + s) + 2];

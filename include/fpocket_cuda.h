@@ -215,6 +215,7 @@ typedef struct fpk_zone {
     int32_t *spheres;          /* [n_entries] index of the sphere in the frame's canonical sphere list */
     float *sph_xyzr;           /* [n_entries*4] what write_pqr_vert prints (mdpocket.c:444) */
     uint8_t *sph_type;         /* [n_entries] */
+    int32_t *sph_pocket;       /* [n_entries] 1-based rank of the pocket the sphere belongs to (vertice->resid, refine.c:223: the residue number write_pqr_vert prints) */
     int32_t n_atoms;
     int32_t *atoms;            /* [n_atoms] get_pocket_contacted_atms of the list, first-seen order */
     fpk_desc desc;             /* set_descriptors of the list: volume and hull volume always computed */

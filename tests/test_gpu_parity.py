@@ -510,6 +510,9 @@ def test_md_characterize_equals_oracle_and_the_reference(case):
         assert np.array_equal(z["spheres"], o["want_sph"]) and len(z["spheres"]) > 50
         assert np.array_equal(z["sph_xyzr"], o["sph_xyzr"][o["want_sph"]])
         assert np.array_equal(z["atoms"], o["want_atoms"])
+        rank_of = np.zeros(o["n_clusters"], np.int32)
+        rank_of[o["rank_to_cluster"]] = np.arange(1, o["n_pockets"] + 1)
+        assert np.array_equal(z["sph_pocket"], rank_of[o["sph_cluster"][z["spheres"]]])        # vertice->resid = final rank of the sphere's pocket
         D = o["want_desc"]
         for n in G.DESC_F:
             if n in ("score", "drug_score") or n.endswith("_norm"):
