@@ -35,7 +35,7 @@ class FpkParams(C.Structure):
         ("do_asa_and_volume", C.c_int32), ("skip_clustering", C.c_int32), ("xpocket_active", C.c_int32),
         ("min_n_explicit_pocket_atoms", C.c_int32), ("want_tets", C.c_int32), ("mc_seed", C.c_uint64),
         ("lig_interface_dist", C.c_float), ("lig_crit_dist", C.c_float),
-        ("distance_measure", C.c_int32), ("lig_interface_method", C.c_int32),
+        ("distance_measure", C.c_int32), ("lig_interface_method", C.c_int32), ("clustering_method", C.c_int32),
     ]
 
 

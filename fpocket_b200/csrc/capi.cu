@@ -72,7 +72,7 @@ extern "C" void fpk_default_params(fpk_params *p)
     p->min_apol_neigh = 3; p->nb_mcv_iter = 300; p->min_pock_nb_asph = 15;
     p->do_asa_and_volume = 1; p->min_n_explicit_pocket_atoms = 4; p->mc_seed = 20260101ull;
     p->lig_interface_dist = (float)4.0; p->lig_crit_dist = (float)3.0;
-    p->distance_measure = 'e'; p->lig_interface_method = 1;
+    p->distance_measure = 'e'; p->lig_interface_method = 1; p->clustering_method = 's';
 }
 
 // asa.c:438-454 get_points_on_sphere(100): computed with the host libm exactly as the reference does

@@ -172,10 +172,110 @@ static int uf_find(int *par, int i) { while (par[i] != i) { par[i] = par[par[i]]
 static int g_distance_measure = 'e';
 void orc_set_distance_measure(int c) { g_distance_measure = c; }
 
-static int cluster_spheres(sph_t *S, int ns, float clust_max_dist, int skip, int measure)
+/* clusterlib.c:933 / :1022 on two rows of f64 data (weights 1, every mask set): what setmetric() hands to distancematrix and pclcluster */
+static double metric3(const double *a, const double *b)
+{
+    double result = 0.;
+    if (g_distance_measure == 'b') {
+        double tweight = 0;
+        for (int k = 0; k < 3; k++) { double term = a[k] - b[k]; result = result + 1.0 * fabs(term); tweight += 1.0; }
+        result /= tweight;
+    } else {
+        for (int k = 0; k < 3; k++) { double term = a[k] - b[k]; result += term * term; }
+        result = sqrt(result);
+    }
+    return result;
+}
+
+/* -C m | a | c: the agglomerative linkages of clusterlib.c (pmlcluster :3705 complete, palcluster :3781 average, pclcluster :3337 centroid) followed by
+ * cuttree_distance (:3235). All three walk a ragged lower-triangular f64 matrix (distancematrix :2919), take the FIRST strict minimum in row-major order
+ * (find_closest_pair :285), fold row/column `is` into `js` and move the last row into slot `is`; ties therefore depend on that layout, which is kept here
+ * exactly. The cut walks the nodes from the last merge down: a node at or below the cut labels every leaf under it that has no label yet, so a leaf's
+ * cluster is its highest-numbered ancestor with distance <= cut (with centroid linkage distances are not monotone, and such an ancestor may sit above
+ * nodes that exceed the cut); a leaf with no such ancestor stays alone. */
+static void linkage_labels(const sph_t *S, int ns, double cut, int method, int *label)
+{
+    const size_t n0 = (size_t)ns;
+    double *D = malloc(sizeof(double) * (n0 * (n0 - 1) / 2 + 1));
+#define DM(i, j) D[(size_t)(i) * ((size_t)(i) - 1) / 2 + (size_t)(j)]                 /* i > j */
+    double *pos = malloc(sizeof(double) * 3 * n0);
+    int *cnt = malloc(sizeof(int) * n0), *cid = malloc(sizeof(int) * n0);
+    int *nl = malloc(sizeof(int) * n0), *nr = malloc(sizeof(int) * n0);
+    double *nd = malloc(sizeof(double) * n0);
+    for (int i = 0; i < ns; i++) { pos[3 * i] = (double)S[i].x; pos[3 * i + 1] = (double)S[i].y; pos[3 * i + 2] = (double)S[i].z; cnt[i] = 1; cid[i] = i; }
+    for (int i = 1; i < ns; i++) for (int j = 0; j < i; j++) DM(i, j) = metric3(pos + 3 * i, pos + 3 * j);
+    for (int n = ns, node = 0; n > 1; n--, node++) {
+        int is = 1, js = 0;
+        double best = DM(1, 0);
+        for (int i = 1; i < n; i++) for (int j = 0; j < i; j++) { double t = DM(i, j); if (t < best) { best = t; is = i; js = j; } }
+        nd[node] = best; nl[node] = cid[is]; nr[node] = cid[js];
+        const int last = n - 1;
+        if (method == 'c') {
+            for (int k = 0; k < 3; k++) {
+                pos[3 * js + k] = pos[3 * js + k] * cnt[js] + pos[3 * is + k] * cnt[is];
+                pos[3 * js + k] /= (cnt[js] + cnt[is]);
+            }
+            cnt[js] += cnt[is];
+            for (int k = 0; k < 3; k++) pos[3 * is + k] = pos[3 * last + k];
+            cnt[is] = cnt[last];
+            for (int j = 0; j < is; j++) DM(is, j) = DM(last, j);
+            for (int j = is + 1; j < last; j++) DM(j, is) = DM(last, j);
+            for (int j = 0; j < js; j++) DM(js, j) = metric3(pos + 3 * js, pos + 3 * j);
+            for (int j = js + 1; j < last; j++) DM(j, js) = metric3(pos + 3 * js, pos + 3 * j);
+        } else {
+            const int sum = cnt[is] + cnt[js];
+            for (int j = 0; j < n; j++) {
+                if (j == js || j == is) continue;
+                double a = j < is ? DM(is, j) : DM(j, is);
+                double *b = j < js ? &DM(js, j) : &DM(j, js);
+                if (method == 'm') *b = a > *b ? a : *b;
+                else { *b = a * cnt[is] + *b * cnt[js]; *b /= sum; }
+            }
+            for (int j = 0; j < is; j++) DM(is, j) = DM(last, j);
+            for (int j = is + 1; j < last; j++) DM(j, is) = DM(last, j);
+            cnt[js] = sum; cnt[is] = cnt[last];
+        }
+        cid[js] = -node - 1; cid[is] = cid[last];
+    }
+#undef DM
+    /* cuttree_distance: top-most (= highest-numbered) node <= cut owns its leaves */
+    for (int i = 0; i < ns; i++) label[i] = -1;
+    int next = 0, *stack = malloc(sizeof(int) * (n0 + 2));
+    for (int node = ns - 2; node >= 0; node--) {
+        if (nd[node] > cut) {
+            if (nl[node] >= 0 && label[nl[node]] < 0) label[nl[node]] = next;
+            next++;
+            if (nr[node] >= 0 && label[nr[node]] < 0) label[nr[node]] = next;
+            next++;
+        } else {
+            next++;
+            int sp = 0;
+            stack[sp++] = -node - 1;
+            while (sp) {
+                int x = stack[--sp];
+                if (x >= 0) { if (label[x] < 0) label[x] = next; }
+                else { stack[sp++] = nr[-x - 1]; stack[sp++] = nl[-x - 1]; }
+            }
+        }
+    }
+    free(stack); free(D); free(pos); free(cnt); free(cid); free(nl); free(nr); free(nd);
+}
+
+static int cluster_spheres(sph_t *S, int ns, float clust_max_dist, int skip, int measure, int method)
 {
     if (measure == 'b' || measure == 'e') g_distance_measure = measure;        /* fpk_params.distance_measure; 0 keeps what orc_set_distance_measure chose */
     if (skip) { for (int i = 0; i < ns; i++) S[i].cluster = 0; return ns ? 1 : 0; }
+    if ((method == 'm' || method == 'a' || method == 'c') && ns >= 2) {
+        int *raw = malloc(sizeof(int) * (size_t)(ns + 1)), *first = malloc(sizeof(int) * 2 * (size_t)(ns + 1)), nc = 0;
+        linkage_labels(S, ns, (double)clust_max_dist, method, raw);
+        for (int i = 0; i < 2 * ns + 2; i++) first[i] = -1;
+        for (int i = 0; i < ns; i++) {                                        /* refine.c:58 apply_clustering: clusters in order of their lowest sphere */
+            if (first[raw[i]] < 0) first[raw[i]] = nc++;
+            S[i].cluster = first[raw[i]];
+        }
+        free(raw); free(first);
+        return nc;
+    }
     int *par = malloc(sizeof(int) * (size_t)(ns + 1));
     for (int i = 0; i < ns; i++) par[i] = i;
     double cut = (double)clust_max_dist;
@@ -630,7 +730,7 @@ int orc_search_pocket(const fpk_structure *in, const fpk_params *p, const int *t
         return out->status;
     }
     const int saved_measure = g_distance_measure;
-    int nc = cluster_spheres(S, ns, p->clust_max_dist, p->skip_clustering, p->distance_measure);
+    int nc = cluster_spheres(S, ns, p->clust_max_dist, p->skip_clustering, p->distance_measure, p->clustering_method);
     g_distance_measure = saved_measure;
     out->n_clusters = nc;
     out->sph_xyzr = malloc(sizeof(float) * 4 * (size_t)(ns + 1)); out->sph_bary = malloc(sizeof(float) * 3 * (size_t)(ns + 1));

@@ -46,6 +46,11 @@ CASES = [
     ("md_3ot3_S", "mdpocket/3ot3.pdb", ["--md", "--score"], []),              # -S drug-score increments
     # one snapshot of mdpocket's characterize mode (mdpocket.c:436-460): zone = the first 70 grid points of the reference's own mdpout_dens_iso_8.pdb
     ("alt_1UYD_eb", "1UYD.pdb", ["--seed", "32"], ["-e", "b"]),                  # test_fpocket.py:91 uses -e b (city-block clustering distance)
+    # the other linkages of clusterlib.c:3705-3880,3337 behind -C (complete, average, centroid); test_fpocket.py:91 runs "-e b -C c"
+    ("alt_1UYD_Cm", "1UYD.pdb", ["--seed", "33"], ["-C", "m"]),
+    ("alt_1UYD_Ca", "1UYD.pdb", ["--seed", "34"], ["-C", "a"]),
+    ("alt_1UYD_eb_Cc", "1UYD.pdb", ["--seed", "35"], ["-e", "b", "-C", "c"]),
+    ("alt_3LKF_Cc", "3LKF.pdb", ["--seed", "36"], ["-C", "c"]),
     ("mdchar_3pa3", "mdpocket/3pa3.pdb", ["--md", "--seed", "31", "--want", "@zone70"], []),
 ]
 

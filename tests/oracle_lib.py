@@ -181,6 +181,7 @@ def params_from_dump(d, **kw):
     p.min_n_explicit_pocket_atoms = int(pi[6])
     if len(pi) > 8 and int(pi[8]) in (ord("e"), ord("b")):
         p.distance_measure = int(pi[8])          # -e (fparams.c): 'e' euclid, 'b' city block
+        p.clustering_method = int(pi[7])         # -C: 's' single, 'm' complete, 'a' average, 'c' centroid linkage
     for k, v in kw.items():
         setattr(p, k, v)
     return p

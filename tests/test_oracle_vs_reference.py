@@ -118,14 +118,16 @@ def test_oracle_characterize_snapshot_equals_the_reference(case):
 
 
 @pytest.mark.parametrize("case", G.ALT_CASES)
-def test_oracle_city_block_clustering_equals_the_reference(case):
-    """-e b (clusterlib.c:1022-1083: mean absolute difference) with single linkage: clusters, every descriptor, drop and rank equal the reference's bit
-    for bit, and differ from the default run's (reference tests/test_fpocket.py:83-91 only asks for the difference). The library computes it too since round 2
-    (tests/test_gpu_parity.py::test_city_block_clustering_equals_the_reference)."""
+def test_oracle_non_default_clustering_equals_the_reference(case):
+    """-e b (clusterlib.c:1022-1083: mean absolute difference) and -C m | a | c (complete :3705, average :3781, centroid :3337 linkage, cut by
+    cuttree_distance :3235): clusters, every descriptor, drop and rank equal the reference's bit for bit, and differ from the default run's (reference
+    tests/test_fpocket.py:83-91 runs "-e b -C c" and only asks for the difference). The library computes them too since round 2
+    (tests/test_gpu_parity.py::test_non_default_clustering_equals_the_reference)."""
     d = G.load(case)
-    assert int(d["params.i"][8]) == ord("b")
+    want_e, want_c = (ord("b") if "_eb" in case else ord("e")), (ord(case.split("_C")[1][0]) if "_C" in case else ord("s"))
+    assert int(d["params.i"][8]) == want_e and int(d["params.i"][7]) == want_c
     st, p = G.inputs(d)
-    assert p.distance_measure == ord("b")           # fpk_params.distance_measure, taken from the reference's own parameter dump
+    assert p.distance_measure == want_e and p.clustering_method == want_c         # fpk_params fields, taken from the reference's own parameter dump
     r = O.search_pocket(st, p, tets=d["qh.tets_seen"], rng_mode=O.RNG_LIBC)
     assert np.array_equal(r["cl_off"], d["pre.off"]) and np.array_equal(r["cl_sph"], d["pre.sph"])
     D, F, I = r["desc"], d["pre.desc_f"], d["pre.desc_i"]
@@ -135,7 +137,7 @@ def test_oracle_city_block_clustering_equals_the_reference(case):
         assert np.array_equal(D[n], I[:, k]), n
     ref_first = [int(d["fin.sph"][o]) for o in d["fin.off"][:-1]]
     assert [int(r["cl_sph"][r["cl_off"][c]]) for c in r["rank_to_cluster"]] == ref_first
-    p.distance_measure = ord("e")
+    p.distance_measure, p.clustering_method = ord("e"), ord("s")
     e = O.search_pocket(st, p, tets=d["qh.tets_seen"], rng_mode=O.RNG_LIBC)
     assert e["n_clusters"] != r["n_clusters"]
 
