@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "k_hull_md.cuh"
+#include "k_linkage.cuh"
 
 using namespace fpk;
 
@@ -293,6 +294,7 @@ struct fpk_batch {
     int md_shared_props = 0;           // mdpocket: all frames share the property arrays
     // stage 1 device
     Arena A1, A2;
+    Arena AL;                         // -C m | a | c: pool of distance matrices (k_linkage), sized from the sphere counts of the run
     BatchDev B;
     StructDev *dS = nullptr;
     DelScratch *dDel = nullptr; int nDel = 0;
@@ -324,7 +326,7 @@ struct fpk_batch {
         int cur = -1;
         cudaGetDevice(&cur);
         if (dev >= 0 && dev != cur) cudaSetDevice(dev);
-        A1.release(); A2.release();
+        A1.release(); A2.release(); AL.release();
         if (hin) cudaFreeHost(hin);
         if (pin_counts) cudaFreeHost(pin_counts);
         if (events) for (auto &e : ev) cudaEventDestroy(e);
@@ -640,6 +642,52 @@ __global__ void k_compact(BatchDev B, const int *sbase, float4 *xyzr, float *bar
 }
 
 static int fetch_counts(fpk_batch *b);
+
+// -C m | a | c (k_linkage.cuh): the sphere counts come back first (one more host round trip, only on this route), the pool of distance
+// matrices is sized from them, and the structures are clustered in as many waves as the pool needs. A structure on the whole-GPU route, or
+// whose matrix alone exceeds the pool, is refused with FPK_ERR_BAD_ARG (the reference would need the same n^2 / 2 doubles and O(n^3) time).
+static int run_linkage(fpk_batch *b)
+{
+    const int n = b->n;
+    { int rc = fetch_counts(b); if (rc) return rc; }
+    size_t freeb = 0, totb = 0;
+    CK(cudaMemGetInfo(&freeb, &totb));
+    size_t budget = (freeb + b->AL.cap) / 2;
+    if (const char *e = getenv("FPK_LINK_POOL_MB")) budget = (size_t)atof(e) << 20;
+    std::vector<LinkItem> items;
+    std::vector<int> wave_start, refused;
+    size_t used = 0, pool = 0;
+    for (int k = 0; k < n; k++) {
+        const int *c = &b->h_counts[(size_t)k * CNT_STRIDE];
+        if (c[CNT_STATUS] != FPK_OK || c[CNT_SPHERES] < 2) continue;
+        const size_t need = (linkage_bytes((size_t)c[CNT_SPHERES]) + 255) & ~(size_t)255;
+        if (b->S[k].nsites > b->k1_max_sites || need > budget) { refused.push_back(k); continue; }
+        if (wave_start.empty() || used + need > budget) { wave_start.push_back((int)items.size()); used = 0; }
+        items.push_back(LinkItem{k, c[CNT_SPHERES], (unsigned long long)used});
+        used += need;
+        pool = std::max(pool, used);
+    }
+    for (int k : refused) {
+        const int v = FPK_ERR_BAD_ARG;
+        CK(cudaMemcpyAsync(b->B.counts + (size_t)k * CNT_STRIDE + CNT_STATUS, &v, sizeof v, cudaMemcpyHostToDevice, cudaStreamPerThread));
+        CK(wait_stream());
+    }
+    if (items.empty()) return FPK_OK;
+    LinkItem *d_items = nullptr;
+    unsigned char *d_pool = nullptr;
+    int rc = arena_build(b->AL, [&](Arena &a) { d_items = a.take<LinkItem>(items.size()); d_pool = a.take<unsigned char>(pool + 256); });
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(d_items, items.data(), sizeof(LinkItem) * items.size(), cudaMemcpyHostToDevice, cudaStreamPerThread));
+    CK(wait_stream());
+    wave_start.push_back((int)items.size());
+    for (size_t w = 0; w + 1 < wave_start.size(); w++) {
+        k_linkage<<<wave_start[w + 1] - wave_start[w], 256, 0, cudaStreamPerThread>>>(b->B, d_items + wave_start[w], d_pool);
+        b->launches++;
+    }
+    CK(cudaGetLastError());
+    return FPK_OK;
+}
+
 static int batch_run(fpk_batch *b)
 {
     const int n = b->n;
@@ -656,6 +704,10 @@ static int batch_run(fpk_batch *b)
     }
     k_delaunay_filter<<<b->nDel, FPK_K1_THREADS, b->k1_dsm>>>(B, b->dDel, b->k1_picap);
     CK(cudaEventRecord(b->ev[1]));
+    {
+        const int cm = b->prm.clustering_method;
+        if ((cm == 'm' || cm == 'a' || cm == 'c') && !b->prm.skip_clustering) { int rcl = run_linkage(b); if (rcl) return rcl; }
+    }
     for (int kb : b->big) {
         if (kb >= n) continue;
         void *args[] = {(void *)&B, (void *)&b->hCluG, (void *)&kb};
@@ -907,10 +959,31 @@ extern "C" void fpk_result_free(fpk_result *r)
     if (H->refs.fetch_sub(1) == 1) delete H;
 }
 
+// parameter values the kernels have no path for (there is no CPU fallback to hand them to)
+static const char *params_defect(const fpk_params *p)
+{
+    static thread_local char msg[160];
+    if (p->distance_measure != 0 && p->distance_measure != 'e' && p->distance_measure != 'b') {
+        snprintf(msg, sizeof msg, "distance measure '%c' is not supported (-e e or -e b; there is no CPU fallback)", p->distance_measure);
+        return msg;
+    }
+    const int cm = p->clustering_method;
+    if (cm != 0 && cm != 's' && cm != 'm' && cm != 'a' && cm != 'c') {
+        snprintf(msg, sizeof msg, "clustering method '%c' is not one of clusterlib's s, m, a, c (clusterlib.c:3886)", cm);
+        return msg;
+    }
+    if (p->lig_interface_method < 0 || p->lig_interface_method > 2) {
+        snprintf(msg, sizeof msg, "ligand interface method %d (dparams.h:41-44 knows 1 and 2)", p->lig_interface_method);
+        return msg;
+    }
+    return nullptr;
+}
+
 extern "C" fpk_batch *fpk_batch_create(const fpk_structure *in, int n, const fpk_params *p)
 {
     if (ensure_init()) return nullptr;
     if (!in || n <= 0 || !p) { fail(FPK_ERR_BAD_ARG, "fpk_batch_create: bad arguments"); return nullptr; }
+    if (const char *why = params_defect(p)) { fail(FPK_ERR_BAD_ARG, "%s", why); return nullptr; }
     fpk_batch *b = new fpk_batch();
     if (batch_pack(b, in, n, p, 0.0) || batch_upload(b, in)) { delete b; return nullptr; }
     // the upload was queued on THIS thread's stream: it must have landed before the handle can be run from any other thread (stream)
@@ -995,9 +1068,7 @@ extern "C" int fpk_detect_batch(const fpk_structure *in, int n, const fpk_params
 {
     if (!out) return fail(FPK_ERR_BAD_ARG, "null result array");
     if (!in || n <= 0 || !p) return fail(FPK_ERR_BAD_ARG, "fpk_detect_batch: bad arguments");
-    if (p->distance_measure != 0 && p->distance_measure != 'e' && p->distance_measure != 'b')
-        return fail(FPK_ERR_BAD_ARG, "distance measure '%c' is not supported (-e e or -e b; there is no CPU fallback)", p->distance_measure);
-    if (p->lig_interface_method < 0 || p->lig_interface_method > 2) return fail(FPK_ERR_BAD_ARG, "ligand interface method %d (dparams.h:41-44 knows 1 and 2)", p->lig_interface_method);
+    if (const char *why = params_defect(p)) return fail(FPK_ERR_BAD_ARG, "%s", why);
     int rc = ensure_init();
     if (rc) return rc;
     memset(out, 0, sizeof(fpk_result) * (size_t)n);      // whatever happens, every out[k] can be handed to fpk_result_free
@@ -1206,6 +1277,7 @@ extern "C" fpk_md *fpk_md_begin(const fpk_structure *topo, const fpk_params *p, 
 {
     if (ensure_init()) return nullptr;
     if (!topo || !p || topo->natoms <= 0) { fail(FPK_ERR_BAD_ARG, "fpk_md_begin: bad arguments"); return nullptr; }
+    if (const char *why = params_defect(p)) { fail(FPK_ERR_BAD_ARG, "fpk_md_begin: %s", why); return nullptr; }
     if (!topo->radius || !topo->electroneg || !topo->bfactor || !topo->atom_id || !topo->res_id || !topo->aa_idx || !topo->flags) {
         fail(FPK_ERR_BAD_ARG, "fpk_md_begin: NULL atom property array");
         return nullptr;

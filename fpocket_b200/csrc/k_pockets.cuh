@@ -118,6 +118,9 @@ __global__ void __launch_bounds__(256) k_cluster(BatchDev B, const ClusterScratc
             if (tid == 0) { cl_off[0] = 0; cl_off[1] = ns; counts[CNT_CLUSTERS] = 1; }
             continue;
         }
+        // -C m | a | c: k_linkage (k_linkage.cuh) has already left par[i] = lowest sphere of i's cluster; only the numbering below remains
+        const bool linked = B.prm.clustering_method == 'm' || B.prm.clustering_method == 'a' || B.prm.clustering_method == 'c';
+        if (!linked) {
         // ---- bounding box of the centres --------------------------------------------------------------
         float mn[3] = {3e38f, 3e38f, 3e38f}, mx[3] = {-3e38f, -3e38f, -3e38f};
         for (int i = tid; i < ns; i += nt) {
@@ -193,6 +196,7 @@ __global__ void __launch_bounds__(256) k_cluster(BatchDev B, const ClusterScratc
                             if (!(pair_distance(cityblock, xi, yi, zi, w) > cut)) uf_union(par, i, j);
                         }
                     }
+        }
         }
         __syncthreads();
         // ---- flatten; number clusters by their lowest sphere (order apply_clustering leaves, refine.c:58-93) ------------------

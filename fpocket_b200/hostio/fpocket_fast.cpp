@@ -82,7 +82,7 @@ int main(int argc, char **argv)
         else if (o == "-u" || o == "--min_n_explicit_pocket") P.min_n_explicit_pocket_atoms = atoi(val());
         else if (o == "-c" || o == "--drop_chains") chains(val(), 0);
         else if (o == "-k" || o == "--keep_chains") chains(val(), 1);
-        else if (o == "-C" || o == "--clustering_method") { if (val()[0] != 's') return refuse("-C other than s (single linkage)"); }
+        else if (o == "-C" || o == "--clustering_method") { const char m = val()[0]; if (m != 's' && m != 'm' && m != 'a' && m != 'c') return refuse("-C other than s, m, a, c (clusterlib's linkages)"); P.clustering_method = m; }
         else if (o == "-e" || o == "--clustering_measure") { const char m = val()[0]; if (m != 'e' && m != 'b') return refuse("-e other than e (euclidean) or b (city block)"); P.distance_measure = m; }
         else if (o == "-w" || o == "--write_mode") {            // fparams.c:167-183: d | b(oth) | p(db) | m(mcif) | cif
             const char *w = val();

@@ -168,15 +168,16 @@ void shim_params(const s_fparams *params, fpk_params *P)
     P->xpocket_active = params->xpocket_n > 0;
     P->min_n_explicit_pocket_atoms = params->min_n_explicit_pocket_atoms;
     P->distance_measure = params->distance_measure;                                      /* -e e | b (clusterlib.c:933,1022) */
+    P->clustering_method = params->clustering_method;                                    /* -C s | m | a | c (clusterlib.c:3886) */
     P->mc_seed = (uint64_t)time(NULL);                                                    /* voronoi.c:87 srand(time(NULL)) */
     if (getenv("FPOCKET_MC_SEED")) P->mc_seed = strtoull(getenv("FPOCKET_MC_SEED"), NULL, 10);
 }
 
 int shim_supported(const s_fparams *params)
 {
-    if (params->clustering_method != 's' || (params->distance_measure != 'e' && params->distance_measure != 'b')) {
-        fprintf(stderr, "! libfpocket_cuda implements single linkage on euclidean or city-block distances only (-C s, -e e or b); got -C %c -e %c\n",
-                params->clustering_method, params->distance_measure);
+    const char c = params->clustering_method, e = params->distance_measure;
+    if ((c != 's' && c != 'm' && c != 'a' && c != 'c') || (e != 'e' && e != 'b')) {
+        fprintf(stderr, "! libfpocket_cuda implements clusterlib's four linkages on euclidean or city-block distances (-C s|m|a|c, -e e|b); got -C %c -e %c\n", c, e);
         return 0;
     }
     return 1;

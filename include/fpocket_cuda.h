@@ -64,7 +64,7 @@ typedef struct fpk_params {
     float lig_interface_dist;             /* dparams.h:42 M_VERT_LIG_NEIG_DIST 4.0: spheres within it of a ligand atom define the explicit pocket */
     float lig_crit_dist;                  /* tpocket.h:32-33 M_CRIT4_D = M_CRIT5_D = 3.0                                                        */
     int32_t distance_measure;             /* -e (fparams.h distance_measure): 0 or 'e' euclid (clusterlib.c:933), 'b' city block = the MEAN of the three
-                                             absolute differences (clusterlib.c:1022-1083). Single linkage only (-C s); anything else: FPK_ERR_BAD_ARG */
+                                             absolute differences (clusterlib.c:1022-1083); anything else: FPK_ERR_BAD_ARG                             */
     int32_t lig_interface_method;         /* dpocket -E (dparams.h:41-44): 0 or 1 = atoms contacted by spheres near the ligand (neighbor.c:313),
                                              2 = atoms within lig_interface_dist of a ligand atom (neighbor.c:67 get_mol_atm_neigh)              */
     int32_t clustering_method;            /* -C (fparams.h clustering_method): 0 or 's' single linkage (clusterlib.c:3514), 'm' complete (:3705), 'a' average

@@ -189,6 +189,63 @@ def test_city_block_clustering_equals_the_reference():
         assert_same_result(r2, O.search_pocket(st2, pb, tets=None, rng_mode=O.RNG_PHILOX), "-e b synthetic")
 
 
+@pytest.mark.parametrize("case", [c for c in G.ALT_CASES if "_C" in c])
+def test_linkage_clustering_equals_the_reference(case):
+    """-C m | a | c (clusterlib.c:3705 complete, :3781 average, :3337 centroid linkage, cut by cuttree_distance :3235) on the GPU (K3L k_linkage:
+    the reference's matrix layout and moves with cached row minima): equal to the oracle bit for bit, equal to the unmodified reference's run
+    (`-C m`, `-C a`, `-e b -C c` - the parameters of the reference's own tests/test_fpocket.py:91 - and `-C c`) within the stated tolerances,
+    and different from single linkage."""
+    import refcompare as RC
+    api = _api()
+    d = G.load(case)
+    st, p = G.inputs(d)
+    assert chr(p.clustering_method) in "mac"
+    r = api.detect(st, p)
+    o = O.search_pocket(st, p, tets=None, rng_mode=O.RNG_PHILOX)
+    assert_same_result(r, o, case)
+    RC.compare(r, d, st, p, what=case)
+    ps = G.inputs(d)[1]
+    ps.clustering_method = ord("s")
+    assert api.detect(st, ps)["n_clusters"] != r["n_clusters"]
+
+
+@pytest.mark.parametrize("method,measure", [("m", "e"), ("a", "e"), ("c", "e"), ("c", "b"), ("a", "b")])
+def test_linkage_clustering_on_a_synthetic_batch(method, measure, monkeypatch):
+    """the same on a batch of synthetic structures (1,200 - 2,900 heavy atoms), with a pool so small that the batch needs several waves and
+    the largest structure is refused (FPK_ERR_BAD_ARG, the batch goes on), and on mdpocket's per-frame body (descriptors off)."""
+    api = _api()
+    from fpocket_b200 import capi
+    sts = [_synth(20269400 + i, n) for i, n in enumerate((1200, 2900, 1700, 2200, 1500))]
+    p = api.default_params()
+    p.clustering_method, p.distance_measure = ord(method), ord(measure)
+    want = [O.search_pocket(st, p, tets=None, rng_mode=O.RNG_PHILOX) for st in sts]
+    for st, r, o in zip(sts, api.detect_batch(sts, p), want):
+        assert_same_result(r, o, "-C %s -e %s" % (method, measure))
+        assert r["n_clusters"] > 20
+    ns = sorted(o["n_spheres"] for o in want)
+    pool_mb = 8.0 * (ns[-2] ** 2 / 2 + 40 * ns[-2]) / 2 ** 20 * 1.15           # room for the second largest matrix, not for the largest
+    monkeypatch.setenv("FPK_LINK_POOL_MB", str(int(pool_mb) + 1))
+    got = api.detect_batch(sts, p)
+    for st, r, o in zip(sts, got, want):
+        if o["n_spheres"] == ns[-1]:
+            assert r["status"] == capi.FPK_ERR_BAD_ARG and r["n_pockets"] == 0
+        else:
+            assert_same_result(r, o, "-C %s in waves" % method)
+    monkeypatch.delenv("FPK_LINK_POOL_MB")
+    p.do_asa_and_volume = 0
+    r = api.detect(sts[2], p)
+    assert_same_result(r, O.search_pocket(sts[2], p, tets=None, rng_mode=O.RNG_PHILOX), "-C %s without descriptors" % method)
+
+
+def test_unknown_clustering_method_is_refused():
+    api = _api()
+    st = _synth(20269420, 1300)
+    p = api.default_params()
+    p.clustering_method = ord("x")
+    with pytest.raises(api.FpkError, match="clustering method"):
+        api.detect(st, p)
+
+
 def test_dpocket_interface_method_2_equals_the_reference():
     """dpocket -E (dparams.h:44, dpocket.c:331-336): the interface = atoms within 4.0 of a ligand atom (neighbor.c:67 get_mol_atm_neigh). K6's set
     equals the oracle's and what the reference's own function returned on 1UYD / PU8; so does the overlap atm_corsp computes with it."""

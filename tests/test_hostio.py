@@ -491,7 +491,7 @@ def test_fast_programs_fail_loudly_without_a_gpu(tmp_path):
     (tmp_path / "l.txt").write_text("x.pdb\tLIG\n")
     r = subprocess.run([dfast, "-f", "l.txt"], cwd=str(tmp_path), capture_output=True, text=True)
     assert r.returncode == 4 and "no CPU fallback" in r.stderr and not (tmp_path / "dpout_explicitp.txt").exists()
-    for opt in (["-x"], ["-d"], ["-e", "c"], ["-C", "m"]):            # -e b (city block) is restated since round 2
+    for opt in (["-x"], ["-d"], ["-e", "c"], ["-C", "w"]):            # -e b (city block) and -C m | a | c are on the GPU since round 2
         r = subprocess.run([fast, "-f", "x.pdb"] + opt, cwd=str(tmp_path), capture_output=True, text=True)
         assert r.returncode == 3 and "fpocket_cuda_batch" in r.stderr, (opt, r.stderr)
     r = subprocess.run([fast, "-f", "x.cif"], cwd=str(tmp_path), capture_output=True, text=True)
