@@ -43,8 +43,10 @@ def _atoms(dirpath, k):
     return ids
 
 
-@pytest.mark.parametrize("n", [2300, 4100])
-def test_reference_program_with_cuda_search_pocket(tmp_path, n):
+@pytest.mark.parametrize("n,opts", [(2300, []), (4100, []), (2300, ["-e", "b", "-C", "c"]), (2300, ["-C", "a"])])
+def test_reference_program_with_cuda_search_pocket(tmp_path, n, opts):
+    """opts: the default run, and the non-default clustering of the reference's own tests/test_fpocket.py:91 ("-e b -C c") parsed by the
+    reference's fparams.c and carried through the shim into fpk_params."""
     if not os.path.exists(EXE):
         pytest.skip("build/fpocket_cuda not built (needs the reference tree: make -C fpocket_b200/shim)")
     import synth
@@ -55,7 +57,7 @@ def test_reference_program_with_cuda_search_pocket(tmp_path, n):
         d.mkdir()
         synth.to_pdb(s, str(d / "x.pdb"))
     env = dict(os.environ, FPOCKET_MC_SEED=str(SEED), TMPDIR=str(tmp_path))
-    subprocess.check_call([EXE, "-f", "x.pdb"], cwd=str(dg), env=env, stdout=subprocess.DEVNULL)
+    subprocess.check_call([EXE, "-f", "x.pdb"] + opts, cwd=str(dg), env=env, stdout=subprocess.DEVNULL)
     out = dg / "x_out"
     assert (out / "x_info.txt").exists() and (out / "x_out.pdb").exists() and (out / "x_pockets.pqr").exists()
     got = _info(str(out / "x_info.txt"))
@@ -67,8 +69,12 @@ def test_reference_program_with_cuda_search_pocket(tmp_path, n):
     st.natoms_w, st.same_pdb = st.natoms, 0
     p = api.default_params()
     p.mc_seed = SEED
+    for o, v in zip(opts[::2], opts[1::2]):
+        setattr(p, {"-e": "distance_measure", "-C": "clustering_method"}[o], ord(v))
     r = api.detect(st, p)
     assert r["status"] == 0 and len(got) == r["n_pockets"]
+    if opts:
+        assert r["n_clusters"] != api.detect(st, api.default_params())["n_clusters"]
     D = r["desc"]
     fields = {"Score": "score", "Druggability Score": "drug_score", "Number of Alpha Spheres": "nb_asph", "Total SASA": "surf_vdw14",
               "Polar SASA": "surf_pol_vdw14", "Apolar SASA": "surf_apol_vdw14", "Volume": "volume", "Mean local hydrophobic density": "mean_loc_hyd_dens",
@@ -83,7 +89,7 @@ def test_reference_program_with_cuda_search_pocket(tmp_path, n):
         assert _atoms(str(out), k + 1) == atoms
     # ---- against the unmodified reference on the same file -------------------------------------------------------------------
     if os.path.exists(REF):
-        subprocess.check_call([REF, "-f", "x.pdb"], cwd=str(dr), env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        subprocess.check_call([REF, "-f", "x.pdb"] + opts, cwd=str(dr), env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         ref = _info(str(dr / "x_out" / "x_info.txt"))
         # Set equality modulo the explained tail: the reference loses the spheres of the last <= 4095 bytes of qhull's output
         # (voronoi.c:138-155; a handful of spheres, DESIGN.md par. 3), which can touch a pocket or two. Every other pocket must be OURS,
