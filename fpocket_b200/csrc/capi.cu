@@ -771,7 +771,11 @@ static int batch_run(fpk_batch *b)
         size_t sacap = 64;
         while (sacap < (size_t)b->max_w + 1) sacap <<= 1;          // the list is sorted by a bitonic network: padded to a power of two
         const size_t nbits = b->max_w > K4_GRID_MIN_ATOMS ? (size_t)b->max_w / 32 + 2 : 1;       // the bit map is only used from K4_GRID_MIN_ATOMS atoms on
-        for (int i = 0; i < b->nDesc; i++) { hDesc[i].sa = a.take<int>(sacap); hDesc[i].bits = a.take<unsigned>(nbits); }
+        for (int i = 0; i < b->nDesc; i++) {
+            hDesc[i].sa = a.take<int>(sacap); hDesc[i].bits = a.take<unsigned>(nbits);
+            hDesc[i].sph = a.take<float4>(K4_STAGE_MAX); hDesc[i].sphk = a.take<int>(K4_STAGE_MAX);
+            hDesc[i].sphmc = a.take<float4>(K4_STAGE_MAX); hDesc[i].mcent = a.take<unsigned short>(K4_MC_GENT);
+        }
     });
     if (rc) return rc;
     Pk.clbase = b->d_clbase; Pk.sbase = b->d_sbase; Pk.total_clusters = (int)NC;
@@ -822,13 +826,16 @@ static int batch_run(fpk_batch *b)
     for (int i = 0; i < 6; i++) cudaEventElapsedTime(&b->ms[i], b->ev[i], b->ev[i + 1]);
 #ifdef FPK_K4_PROFILE
     {
-        unsigned long long h[12] = {0}, z[12] = {0};
+        unsigned long long h[24] = {0}, z[24] = {0};
         cudaMemcpyFromSymbol(h, g_k4prof, sizeof h);
         cudaMemcpyToSymbol(g_k4prof, z, sizeof z);
         fprintf(stderr, "k_descriptors split: %llu clusters below min_pock_nb_asph, %.1f M block cycles (%.0f each); %llu others, %.1f M block cycles (%.0f each)\n",
                 h[1], h[0] / 1e6, h[1] ? (double)h[0] / h[1] : 0.0, h[3], h[2] / 1e6, h[3] ? (double)h[2] / h[3] : 0.0);
         if (h[1]) fprintf(stderr, "k_descriptors split, the first kind by phase (cycles per cluster): fetch + contacted atoms %.0f, CSR %.0f, sums / surroundings / SASA %.0f, per-atom epilogue %.0f, record %.0f\n",
                           (double)h[4] / h[1], (double)h[5] / h[1], (double)h[6] / h[1], (double)h[7] / h[1], (double)h[8] / h[1]);
+        if (h[12]) fprintf(stderr, "k_descriptors split, %llu clusters of >= 256 spheres (%.0f on average), k-cycles per cluster: contacted atoms %.0f, CSR %.0f, then from there: warp 0's sums done at %.0f, "
+                           "surroundings at %.0f, last SASA atom at %.0f, Monte-Carlo (all) at %.0f; per-atom epilogue %.0f, record %.0f\n", h[12], (double)h[13] / h[12],
+                           h[14] / 1e3 / h[12], h[15] / 1e3 / h[12], h[16] / 1e3 / h[12], h[17] / 1e3 / h[12], h[18] / 1e3 / h[12], h[19] / 1e3 / h[12], h[20] / 1e3 / h[12], h[21] / 1e3 / h[12]);
     }
 #endif
     cudaEventElapsedTime(&b->ms[7], b->ev[0], b->ev[6]);

@@ -512,10 +512,17 @@ __device__ __forceinline__ float unif_from_bits(unsigned r31, float mn, float mx
 struct DescScratch {          // per resident block of K4
     int *sa;                  // [natoms_w max] surrounding atoms of the current pocket (asa.c:84-112), three ordered segments
     unsigned *bits;           // [natoms_w max / 32 + 1] large structures: one bit per atom of pdb_w_lig (marked by the pocket's spheres)
+    // the pocket's spheres in pocket order, copied once per pocket of up to K4_STAGE_MAX spheres: warp 0's pair loops (n^2 / 2 reads in the
+    // reference's order) then read consecutive 16-byte records from L1 instead of chasing  cl_sph -> s_xyzr  through L2 for every pair
+    float4 *sph;              // [K4_STAGE_MAX] (x, y, z, ray)
+    int *sphk;                // [K4_STAGE_MAX] bit 0: polar; bits 1..: the sphere's identity (zone batches list a sphere once per zone point)
+    float4 *sphmc;            // [K4_STAGE_MAX] (x, y, z, (ray - 1.6)^2): the Monte-Carlo tile of a pocket too large for the shared one
+    unsigned short *mcent;    // [K4_MC_GENT] Monte-Carlo cell entries of a pocket whose lists do not fit the shared array
 };
 
 enum { K4_THREADS = 128, K4_WORKERS = 96, MC_SMEM_SPH = 512, MC_CELLS = 512, MC_ENTRIES = 4096, ASA_CAND = 128,
-       K4_GRID_MIN_ATOMS = 10000 };      // from here on the surrounding atoms of a pocket come from the structure's cell grid (AtomGrid)
+       K4_GRID_MIN_ATOMS = 10000,        // from here on the surrounding atoms of a pocket come from the structure's cell grid (AtomGrid)
+       K4_STAGE_MAX = 2048, K4_MC_GENT = 32768 };
 
 // barrier among warps 1..3 only (warp 0 runs the reference-order sequential sums meanwhile)
 __device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
@@ -525,7 +532,7 @@ __device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 96;" 
 //   warps 1..3 - surrounding atoms, the two SASA passes and the Monte-Carlo volume (integer counts: order-free).
 #ifdef FPK_K4_PROFILE
 // measurement build only (scripts/gpu_k4_split.sh): block cycles and counts of work items, [0,1] clusters below min_pock_nb_asph, [2,3] the others
-__device__ unsigned long long g_k4prof[12];      // [4..8]: the first kind by phase (fetch + contacted atoms, CSR, sums / surroundings / SASA, per-atom epilogue, record)
+__device__ unsigned long long g_k4prof[24];      // [12..21]: clusters of >= 256 spheres: count, spheres, then cycles by phase (see capi.cu)      // [4..8]: the first kind by phase (fetch + contacted atoms, CSR, sums / surroundings / SASA, per-atom epilogue, record)
 #endif
 __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, PocketDev Pk, const DescScratch *scratch, int *work_counter, AtomGrid AG,
                                                                const unsigned char *small_done)
@@ -546,7 +553,8 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
     if (tid == 0) s_klast = -1;
 #endif
 #ifdef FPK_K4_PROFILE
-    long long prof_t = 0, prof_p[4] = {0, 0, 0, 0}; int prof_class = -1;
+    long long prof_t = 0, prof_p[4] = {0, 0, 0, 0}; int prof_class = -1, prof_n = 0;
+    __shared__ unsigned long long s_prof[4];      // end of warp 0's sums, of the workers' surroundings, of the last SASA atom
 #endif
     for (;;) {
         __syncthreads();
@@ -559,6 +567,13 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                 atomicAdd(&g_k4prof[4], (unsigned long long)(prof_p[0] - prof_t)); atomicAdd(&g_k4prof[5], (unsigned long long)(prof_p[1] - prof_p[0]));
                 atomicAdd(&g_k4prof[6], (unsigned long long)(prof_p[2] - prof_p[1])); atomicAdd(&g_k4prof[7], (unsigned long long)(prof_p[3] - prof_p[2]));
                 atomicAdd(&g_k4prof[8], (unsigned long long)(now - prof_p[3]));
+            }
+            if (prof_class >= 0 && prof_n >= 256) {
+                atomicAdd(&g_k4prof[12], 1ull); atomicAdd(&g_k4prof[13], (unsigned long long)prof_n);
+                atomicAdd(&g_k4prof[14], (unsigned long long)(prof_p[0] - prof_t)); atomicAdd(&g_k4prof[15], (unsigned long long)(prof_p[1] - prof_p[0]));
+                atomicAdd(&g_k4prof[16], s_prof[0] - (unsigned long long)prof_p[1]); atomicAdd(&g_k4prof[17], s_prof[1] - (unsigned long long)prof_p[1]);
+                atomicAdd(&g_k4prof[18], s_prof[2] - (unsigned long long)prof_p[1]); atomicAdd(&g_k4prof[19], (unsigned long long)(prof_p[2] - prof_p[1]));
+                atomicAdd(&g_k4prof[20], (unsigned long long)(prof_p[3] - prof_p[2])); atomicAdd(&g_k4prof[21], (unsigned long long)(now - prof_p[3]));
             }
             prof_t = now;
         }
@@ -606,9 +621,13 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
         const bool explicit_pocket = kcnt[CNT_XP] == 1 && c == kcnt[CNT_CLUSTERS] - 1;     // dpocket.c:350: described from the interface atoms
         const bool observable = explicit_pocket || n >= prm.min_pock_nb_asph;      // below it the cluster is always dropped (refine.c:124): no MC samples
         const bool insm = n <= MC_SMEM_SPH;
+        const bool stg = n <= K4_STAGE_MAX;           // the pocket's spheres are copied to X.sph / X.sphk (and X.sphmc beyond the shared tile)
+        const float4 *Xs = X.sph;
+        const int *Xk = X.sphk;
         const float correct = -1.6f;
 #ifdef FPK_K4_PROFILE
-        prof_class = observable ? 1 : 0;
+        prof_class = observable ? 1 : 0; prof_n = n;
+        if (tid == 0) { s_prof[0] = s_prof[1] = s_prof[2] = 0ull; }
 #endif
 
         // ---- 1. warp 0: unique contacted atoms by atom id, first-seen order (pocket.c:1280-1320); warps 1..3: MC sphere tile ----------
@@ -639,9 +658,16 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                 __syncwarp();
             }
             if (lane == 0) s_U = U;
-        } else if (full) {
-            if (insm)
-                for (int i = tid - 32; i < n; i += K4_WORKERS) { float4 v = sx[L[i]]; v.w = (correct + v.w) * (v.w + correct); s_sph[i] = v; }
+        } else if (stg) {
+            for (int i = tid - 32; i < n; i += K4_WORKERS) {
+                const int si = L[i];
+                float4 v = sx[si];
+                X.sph[i] = v;
+                X.sphk[i] = ((Pk.sph_uid ? Pk.sph_uid[S.sph_off + si] : si) << 1) | (sty[si] != 0 ? 1 : 0);
+                if (full) { v.w = (correct + v.w) * (v.w + correct); if (insm) s_sph[i] = v; else X.sphmc[i] = v; }
+            }
+        }
+        if (wid != 0 && full) {
             if (tid == 32) {        // MC box (voronoi.c:1172-1195: +correct on both sides, else-if updates), one thread, reference order
                 float xmin = 0, xmax = 0, ymin = 0, ymax = 0, zmin = 0, zmax = 0, xt, yt, zt;
                 for (int i = 0; i < n; i++) {
@@ -798,7 +824,7 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                     const float xr = unif_from_bits(o[0] >> 1, xmin, xmax), yr = unif_from_bits(o[1] >> 1, ymin, ymax),
                                 zr = unif_from_bits(o[2] >> 1, zmin, zmax);
                     bool in = false;
-                    if (mode) {
+                    if (mode == 1) {
                         const int a = max(0, min(dx - 1, (int)floorf((xr - xmin) * hx))), b = max(0, min(dy - 1, (int)floorf((yr - ymin) * hy))),
                                   d = max(0, min(dz - 1, (int)floorf((zr - zmin) * hz)));
                         const int cid = (a * dy + b) * dz + d;
@@ -807,6 +833,26 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                             const float4 v = s_sph[s_ent[j]];
                             const float xt = v.x - xr, yt = v.y - yr, zt = v.z - zr;
                             in = v.w > (xt * xt + yt * yt + zt * zt);
+                        }
+                    } else if (mode == 2) {           // a large pocket: the same cell lists, entries (and beyond 512 spheres the tile) in the block's global scratch
+                        const int a = max(0, min(dx - 1, (int)floorf((xr - xmin) * hx))), b = max(0, min(dy - 1, (int)floorf((yr - ymin) * hy))),
+                                  d = max(0, min(dz - 1, (int)floorf((zr - zmin) * hz)));
+                        const int cid = (a * dy + b) * dz + d;
+                        const int e0 = cid ? s_cell[cid - 1] : 0, e1 = s_cell[cid];
+                        const unsigned short *entg = X.mcent;
+                        if (insm) {
+                            for (int j = e0; j < e1 && !in; j++) {
+                                const float4 v = s_sph[entg[j]];
+                                const float xt = v.x - xr, yt = v.y - yr, zt = v.z - zr;
+                                in = v.w > (xt * xt + yt * yt + zt * zt);
+                            }
+                        } else {
+                            const float4 *tileg = X.sphmc;
+                            for (int j = e0; j < e1 && !in; j++) {
+                                const float4 v = tileg[entg[j]];
+                                const float xt = v.x - xr, yt = v.y - yr, zt = v.z - zr;
+                                in = v.w > (xt * xt + yt * yt + zt * zt);
+                            }
                         }
                     } else if (insm) {
                         for (int j = 0; j < n && !in; j++) {
@@ -831,10 +877,19 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
             float as_density = 0.0f, as_max_dst = -1.0f, lane_max = -1.0f;
             int mlhd_cnt = 0, nAlphaApol = 0;
             for (int i = 0; i < n; i++) {
-                const float4 vi = sx[L[i]];
-                const bool apol_i = sty[L[i]] == 0;
+                const float4 vi = stg ? Xs[i] : sx[L[i]];
+                const int key_i = stg ? Xk[i] : 0;
+                const bool apol_i = stg ? !(key_i & 1) : sty[L[i]] == 0;
                 int napol = 0;
-                if (apol_i) {
+                if (apol_i && stg) {
+                    // two spheres are "the same" iff they carry the same identity (vc != vcur, descriptors.c:199): i itself, or in a zone batch another copy of it
+                    for (int j = lane; j < n; j += 32) {
+                        const int key_j = Xk[j];
+                        if ((key_j & 1) || key_j == key_i) continue;
+                        const float4 vj = Xs[j];
+                        if ((double)(f_dist(vi.x, vi.y, vi.z, vj.x, vj.y, vj.z) - (vj.w + vi.w)) <= 0.) napol++;
+                    }
+                } else if (apol_i) {
                     const int uid_i = Pk.sph_uid ? Pk.sph_uid[S.sph_off + L[i]] : 0;
                     for (int j = lane; j < n; j += 32) {
                         if (j == i || sty[L[j]] != 0) continue;
@@ -842,6 +897,8 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                         float4 vj = sx[L[j]];
                         if ((double)(f_dist(vi.x, vi.y, vi.z, vj.x, vj.y, vj.z) - (vj.w + vi.w)) <= 0.) napol++;
                     }
+                }
+                if (apol_i) {
 #pragma unroll
                     for (int d = 16; d > 0; d >>= 1) napol += __shfl_xor_sync(0xffffffffu, napol, d);
                     mlhd_cnt += napol;
@@ -851,7 +908,7 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                     int j = base + lane;
                     float dj = 0.0f;
                     if (j < n) {
-                        float4 vj = sx[L[j]];
+                        const float4 vj = stg ? Xs[j] : sx[L[j]];
                         dj = f_dist(vi.x, vi.y, vi.z, vj.x, vj.y, vj.z);
                         lane_max = fmaxf(lane_max, dj);       // the maximum does not depend on the order: kept per lane, reduced once
                     }
@@ -884,7 +941,7 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                 int napolc = 0;
                 for (int i = 0; i < n; i++) {
                     const int si = L[i];
-                    const float4 v = sx[si];
+                    const float4 v = stg ? Xs[i] : sx[si];
                     if (v.w > as_max_r) as_max_r = v.w;
                     mean_r += v.w;
                     float dd = f_dist(v.x, v.y, v.z, sb[3 * si], sb[3 * si + 1], sb[3 * si + 2]);
@@ -930,6 +987,9 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                 d.as_max_r = as_max_r;
                 s_desc = d;
             }
+#ifdef FPK_K4_PROFILE
+            if (lane == 0) s_prof[0] = (unsigned long long)clock64();
+#endif
             if (full) {
                 // the workers have ARRIVED at barrier 2 once the surrounding atoms (X.sa) and the Monte-Carlo cell grid are in place; warp 0 waits for
                 // that only now, then takes samples (observable clusters) or contacted atoms (the rest: s_ent is idle there and holds its candidates)
@@ -943,7 +1003,7 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                 // cell grid over the box: a sample only meets the spheres registered in its cell (the test is an OR: order-free)
                 if (wt == 0) {
                     int mode = 0;
-                    if (insm && n >= 24) {
+                    if ((insm || stg) && n >= 24) {
                         const float ex = xmax - xmin, ey = ymax - ymin, ez = zmax - zmin;
                         const int dx = max(1, min(8, (int)(ex / 4.5f))), dy = max(1, min(8, (int)(ey / 4.5f))), dz = max(1, min(8, (int)(ez / 4.5f)));
                         s_mcdim[0] = dx; s_mcdim[1] = dy; s_mcdim[2] = dz;
@@ -959,8 +1019,9 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                     for (int i = wt; i <= ncell; i += K4_WORKERS) s_cell[i] = 0;
                     workers_sync();
                     for (int pass = 0; pass < 2; pass++) {
+                        const bool gent = s_mcmode == 2;          // decided after the counting pass
                         for (int i = wt; i < n; i += K4_WORKERS) {
-                            const float4 v = s_sph[i];
+                            const float4 v = insm ? s_sph[i] : X.sphmc[i];
                             const float r = sqrtf(fmaxf(v.w, 0.0f)) + 2e-3f;
                             const int x0 = max(0, min(dx - 1, (int)floorf((v.x - r - xmin) * hx))), x1 = max(0, min(dx - 1, (int)floorf((v.x + r - xmin) * hx)));
                             const int y0 = max(0, min(dy - 1, (int)floorf((v.y - r - ymin) * hy))), y1 = max(0, min(dy - 1, (int)floorf((v.y + r - ymin) * hy)));
@@ -968,7 +1029,11 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                             for (int a = x0; a <= x1; a++) for (int b = y0; b <= y1; b++) for (int d = z0; d <= z1; d++) {
                                 const int cid = (a * dy + b) * dz + d;
                                 if (pass == 0) atomicAdd(&s_cell[cid], 1);
-                                else { const int slot = atomicAdd(&s_cell[cid], 1); if (slot < MC_ENTRIES) s_ent[slot] = (unsigned short)i; }
+                                else {
+                                    const int slot = atomicAdd(&s_cell[cid], 1);
+                                    if (gent) { if (slot < K4_MC_GENT) X.mcent[slot] = (unsigned short)i; }
+                                    else if (slot < MC_ENTRIES) s_ent[slot] = (unsigned short)i;
+                                }
                             }
                         }
                         workers_sync();
@@ -982,7 +1047,8 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                                     if (i <= ncell) s_cell[i] = run + inc - v;
                                     run += __shfl_sync(0xffffffffu, inc, 31);
                                 }
-                                if (lane == 0 && run > MC_ENTRIES) s_mcmode = 0;       // does not fit: every sample meets every sphere
+                                // lists that do not fit the shared array go to the block's global scratch; beyond that every sample meets every sphere
+                                if (lane == 0) { if (run > K4_MC_GENT) s_mcmode = 0; else if (run > MC_ENTRIES || !insm) s_mcmode = 2; }
                             }
                             workers_sync();
                             if (!s_mcmode) break;
@@ -1082,6 +1148,9 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                 if (lane == 0) s_segcnt[ww] = nseg;
             }
             workers_sync();
+#ifdef FPK_K4_PROFILE
+            if (wt == 0) s_prof[1] = (unsigned long long)clock64();
+#endif
             __threadfence_block();
             asm volatile("bar.arrive 2, 128;" ::: "memory");          // lets warp 0 in (it may still be busy with its sums: nobody waits for it here)
         }
@@ -1099,6 +1168,9 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                     if (u >= U) break;
                     asa_atom(u, cand, candapol);
                 }
+#ifdef FPK_K4_PROFILE
+            if (lane == 0) atomicMax(&s_prof[2], (unsigned long long)clock64());
+#endif
             // ---- 5. Monte-Carlo volume (voronoi.c:1150-1233), radius ray-1.6, 100 x nb_mcv_iter samples ------------------------------
             if (observable) mc_samples();
         }
