@@ -633,6 +633,7 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
         // ---- 1. warp 0: unique contacted atoms by atom id, first-seen order (pocket.c:1280-1320); warps 1..3: MC sphere tile ----------
         if (wid == 0) {
             int U = 0;
+            int *uids = tlist;
             for (int base = 0; base < 4 * n; base += 32) {
                 int e = base + lane;
                 bool valid = e < 4 * n;
@@ -644,14 +645,15 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                     id = B.aid[Q0 + a];
                 }
                 int dupidx = -1;
+#pragma unroll 4
                 for (int u = 0; u < U; u++)
-                    if (B.aid[Q0 + uat[u]] == id) dupidx = u;
+                    if (uids[u] == id) dupidx = u;          // the ids of the atoms found so far, kept beside the list (touch_list is idle until step 2)
                 unsigned m = __match_any_sync(0xffffffffu, id);
                 int leader = __ffs(m) - 1;
                 bool isnew = valid && dupidx < 0 && lane == leader;
                 unsigned bal = __ballot_sync(0xffffffffu, isnew);
                 int pos = U + __popc(bal & ((1u << lane) - 1u));
-                if (isnew) uat[pos] = a;
+                if (isnew) { uat[pos] = a; uids[pos] = id; }
                 int lp = __shfl_sync(0xffffffffu, pos, leader);
                 if (valid) entu[e] = dupidx >= 0 ? dupidx : lp;
                 U += __popc(bal);
@@ -883,11 +885,11 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                 int napol = 0;
                 if (apol_i && stg) {
                     // two spheres are "the same" iff they carry the same identity (vc != vcur, descriptors.c:199): i itself, or in a zone batch another copy of it
-                    for (int j = lane; j < n; j += 32) {
+#pragma unroll 4
+                    for (int j = lane; j < n; j += 32) {          // integer count: order-free, so the loads of several rounds may be in flight together
                         const int key_j = Xk[j];
-                        if ((key_j & 1) || key_j == key_i) continue;
                         const float4 vj = Xs[j];
-                        if ((double)(f_dist(vi.x, vi.y, vi.z, vj.x, vj.y, vj.z) - (vj.w + vi.w)) <= 0.) napol++;
+                        if (!((key_j & 1) || key_j == key_i) && (double)(f_dist(vi.x, vi.y, vi.z, vj.x, vj.y, vj.z) - (vj.w + vi.w)) <= 0.) napol++;
                     }
                 } else if (apol_i) {
                     const int uid_i = Pk.sph_uid ? Pk.sph_uid[S.sph_off + L[i]] : 0;
@@ -904,11 +906,14 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                     mlhd_cnt += napol;
                     nAlphaApol++;
                 }
+                float4 vnext = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i + 1 + lane < n) vnext = stg ? Xs[i + 1 + lane] : sx[L[i + 1 + lane]];
                 for (int base = i + 1; base < n; base += 32) {
                     int j = base + lane;
                     float dj = 0.0f;
+                    const float4 vj = vnext;
+                    if (j + 32 < n) vnext = stg ? Xs[j + 32] : sx[L[j + 32]];      // requested before this chunk's 32 dependent additions
                     if (j < n) {
-                        const float4 vj = stg ? Xs[j] : sx[L[j]];
                         dj = f_dist(vi.x, vi.y, vi.z, vj.x, vj.y, vj.z);
                         lane_max = fmaxf(lane_max, dj);       // the maximum does not depend on the order: kept per lane, reduced once
                     }
@@ -929,63 +934,108 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
             const int *alist = explicit_pocket ? Pk.xp_ilist + S.atom_off + k : uat;
             const int UA = explicit_pocket ? Pk.xp_ni[k] : U;
             // first occurrence of every residue id among them (descriptors.c:408 in_tab), one lane per atom
-            for (int u = lane; u < UA; u += 32) {
-                const int rid = B.ares[Q0 + alist[u]];
-                bool seen = false;
-                for (int q = 0; q < u && !seen; q++) seen = B.ares[Q0 + alist[q]] == rid;
-                entu[u] = seen ? 0 : 1;                     // ent_u is free once the CSR is built
-            }
+            if (UA <= 16 * n) {
+                // the residue ids are fetched once (fx_val is idle until 6a) and the search runs over that list instead of chasing atom -> residue per step
+                int *rids = reinterpret_cast<int *>(fxv);
+                for (int u = lane; u < UA; u += 32) rids[u] = B.ares[Q0 + alist[u]];
+                __syncwarp();
+                for (int u = lane; u < UA; u += 32) {
+                    const int rid = rids[u];
+                    bool seen = false;
+                    int q = 0;
+                    for (; q + 4 <= u && !seen; q += 4) seen = rids[q] == rid || rids[q + 1] == rid || rids[q + 2] == rid || rids[q + 3] == rid;
+                    for (; q < u && !seen; q++) seen = rids[q] == rid;
+                    entu[u] = seen ? 0 : 1;                 // ent_u is free once the CSR is built
+                }
+            } else
+                for (int u = lane; u < UA; u += 32) {
+                    const int rid = B.ares[Q0 + alist[u]];
+                    bool seen = false;
+                    for (int q = 0; q < u && !seen; q++) seen = B.ares[Q0 + alist[q]] == rid;
+                    entu[u] = seen ? 0 : 1;
+                }
             __syncwarp();
-            if (lane == 0) {
+            {
+                // per-sphere and per-atom sums: every lane fetches one element of a chunk of 32 (the loads of a chunk are in flight together), then all
+                // lanes add the 32 values in list order - the same additions in the same order as the reference's loops (descriptors.c:238-246, :355-436)
                 float mean_r = 0.0f, masph = 0.0f, as_max_r = -1.0f, ps0 = 0.0f, ps1 = 0.0f, ps2 = 0.0f;
                 int napolc = 0;
-                for (int i = 0; i < n; i++) {
-                    const int si = L[i];
-                    const float4 v = stg ? Xs[i] : sx[si];
-                    if (v.w > as_max_r) as_max_r = v.w;
-                    mean_r += v.w;
-                    float dd = f_dist(v.x, v.y, v.z, sb[3 * si], sb[3 * si + 1], sb[3 * si + 2]);
-                    masph += dd / v.w;
-                    ps0 += v.x; ps1 += v.y; ps2 += v.z;
-                    if (sty[si] == 0) napolc++;
+                for (int base = 0; base < n; base += 32) {
+                    const int i = base + lane;
+                    float4 v = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+                    float q = 0.0f;
+                    bool ap = false;
+                    if (i < n) {
+                        const int si = L[i];
+                        v = stg ? Xs[i] : sx[si];
+                        const float dd = f_dist(v.x, v.y, v.z, sb[3 * si], sb[3 * si + 1], sb[3 * si + 2]);
+                        q = dd / v.w;
+                        ap = sty[si] == 0;
+                    }
+                    napolc += __popc(__ballot_sync(0xffffffffu, ap));
+                    const int cnt = min(32, n - base);
+                    for (int t = 0; t < cnt; t++) {
+                        const float w = __shfl_sync(0xffffffffu, v.w, t);
+                        if (w > as_max_r) as_max_r = w;
+                        mean_r += w;
+                        masph += __shfl_sync(0xffffffffu, q, t);
+                        ps0 += __shfl_sync(0xffffffffu, v.x, t); ps1 += __shfl_sync(0xffffffffu, v.y, t); ps2 += __shfl_sync(0xffffffffu, v.z, t);
+                    }
                 }
-                fpk_desc d;
-                memset(&d, 0, sizeof d);
-                d.first_sphere = L[0];
-                d.nAlphaApol = napolc; d.nAlphaPol = n - napolc;
-                d.bary[0] = ps0 / (float)n; d.bary[1] = ps1 / (float)n; d.bary[2] = ps2 / (float)n;      // refine.c:192-240
-                d.n_atoms = U;
+                for (int w = lane; w < (int)(sizeof(fpk_desc) / sizeof(int)); w += 32) reinterpret_cast<int *>(&s_desc)[w] = 0;
+                __syncwarp();
+                int nb_res = 0, nb_polar = 0, pol_sc = 0, chg_sc = 0;
+                float flex = 0.0f, hyd = 0.0f, vol = 0.0f;
                 // atom based (descriptors.c:355-436, :453-513)
                 if (UA > 1) {
-                    int nb_res = 0, nb_polar = 0;
-                    float flex = 0.0f, hyd = 0.0f, vol = 0.0f;
-                    for (int u = 0; u < UA; u++) {
-                        const int a = Q0 + alist[u];
-                        if (entu[u]) {
-                            int aa = B.aaa[a];
-                            if (aa >= 0) {
-                                d.aa_compo[aa]++;
-                                hyd += c_aa_hyd[aa]; d.polarity_score += c_aa_pol[aa]; vol += c_aa_vol[aa]; d.charge_score += c_aa_chg[aa];
-                            }
-                            nb_res++;
+                    for (int base = 0; base < UA; base += 32) {
+                        const int u = base + lane;
+                        int aa = -1;
+                        bool fl = false, pl = false;
+                        float bf = 0.0f;
+                        if (u < UA) {
+                            const int a = Q0 + alist[u];
+                            fl = entu[u] != 0;
+                            if (fl) aa = B.aaa[a];
+                            bf = B.abf[a];
+                            pl = (double)B.aen[a] > 2.7;
                         }
-                        flex += B.abf[a];
-                        if ((double)B.aen[a] > 2.7) nb_polar++;
+                        nb_res += __popc(__ballot_sync(0xffffffffu, fl));
+                        nb_polar += __popc(__ballot_sync(0xffffffffu, pl));
+                        const int cnt = min(32, UA - base);
+                        for (int t = 0; t < cnt; t++) {
+                            const int aat = __shfl_sync(0xffffffffu, aa, t);        // < 0: not the first atom of its residue, or no standard residue
+                            if (aat >= 0) {
+                                if (lane == 0) s_desc.aa_compo[aat]++;
+                                hyd += c_aa_hyd[aat]; pol_sc += c_aa_pol[aat]; vol += c_aa_vol[aat]; chg_sc += c_aa_chg[aat];
+                            }
+                            flex += __shfl_sync(0xffffffffu, bf, t);
+                        }
                     }
-                    d.hydrophobicity_score = hyd / (float)nb_res;
-                    d.volume_score = vol / (float)nb_res;
-                    d.flex = flex / (float)UA;
-                    d.prop_polar_atm = (float)((double)(((float)nb_polar) / ((float)UA)) * 100.0);
                 }
-                d.mean_loc_hyd_dens = nAlphaApol > 0 ? (float)mlhd_cnt / (float)nAlphaApol : 0.0f;
-                d.as_max_dst = as_max_dst;
-                d.apolar_asphere_prop = (float)nAlphaApol / (float)n;
-                d.masph_sacc = masph / (float)n;
-                d.mean_asph_ray = mean_r / (float)n;
-                d.nb_asph = n;
-                d.as_density = (float)((double)as_density / ((n * n - n) * 0.5));
-                d.as_max_r = as_max_r;
-                s_desc = d;
+                __syncwarp();
+                if (lane == 0) {
+                    fpk_desc &d = s_desc;
+                    d.first_sphere = L[0];
+                    d.nAlphaApol = napolc; d.nAlphaPol = n - napolc;
+                    d.bary[0] = ps0 / (float)n; d.bary[1] = ps1 / (float)n; d.bary[2] = ps2 / (float)n;      // refine.c:192-240
+                    d.n_atoms = U;
+                    if (UA > 1) {
+                        d.polarity_score = pol_sc; d.charge_score = chg_sc;
+                        d.hydrophobicity_score = hyd / (float)nb_res;
+                        d.volume_score = vol / (float)nb_res;
+                        d.flex = flex / (float)UA;
+                        d.prop_polar_atm = (float)((double)(((float)nb_polar) / ((float)UA)) * 100.0);
+                    }
+                    d.mean_loc_hyd_dens = nAlphaApol > 0 ? (float)mlhd_cnt / (float)nAlphaApol : 0.0f;
+                    d.as_max_dst = as_max_dst;
+                    d.apolar_asphere_prop = (float)nAlphaApol / (float)n;
+                    d.masph_sacc = masph / (float)n;
+                    d.mean_asph_ray = mean_r / (float)n;
+                    d.nb_asph = n;
+                    d.as_density = (float)((double)as_density / ((n * n - n) * 0.5));
+                    d.as_max_r = as_max_r;
+                }
             }
 #ifdef FPK_K4_PROFILE
             if (lane == 0) s_prof[0] = (unsigned long long)clock64();
