@@ -505,6 +505,7 @@ static int batch_upload(fpk_batch *b, const fpk_structure *in)
             b->AG.cellatom = a.take<int>((size_t)b->tot_w + (size_t)b->tot_atoms + 2);      // addressed at w_off, or tot_w + atom_off
             b->AG.same_base = (int)b->tot_w; b->AG.min_atoms = K4_GRID_MIN_ATOMS;
             b->AG.geom = a.take<float4>(n); b->AG.dims = a.take<int4>(n);
+            b->AG.cbox = a.take<float4>(2 * (((size_t)b->tot_w + (size_t)b->tot_atoms) / 32 + (size_t)n + 2));
         }
         B.s_xyzr = a.take<float4>(b->tot_sphcap); B.s_bary = a.take<float>(3 * b->tot_sphcap);
         B.s_neigh = a.take<int4>(b->tot_sphcap); B.s_key = a.take<int4>(b->tot_sphcap);

@@ -406,7 +406,15 @@ struct AtomGrid {
     const int *cbase;         // [nstruct + 1]
     float4 *geom;             // [nstruct] (x0, y0, z0, cell edge)
     int4 *dims;               // [nstruct] (d0, d1, d2, 0)
+    // every structure, whatever its size: bounding box of the heavy atoms of every run of 32 consecutive atoms of pdb_w_lig (two float4: min, max), at
+    // chunk_base(k) + c. Atoms come in chain order, so such a run is a few residues, ~10 A across: k_descriptors_small scans only the runs whose box
+    // meets the cluster's (in ascending order: the atom order asa.c:84-112 leaves is kept) instead of all atoms of the structure for every cluster.
+    float4 *cbox;
 };
+__device__ __forceinline__ size_t chunk_base(const AtomGrid &AG, const StructDev &S, int k)
+{
+    return (size_t)((S.natoms_w ? S.w_off : AG.same_base + S.atom_off) >> 5) + (size_t)k;
+}
 __global__ void __launch_bounds__(256) k_atom_grid(BatchDev B, AtomGrid AG)
 {
     __shared__ int s_sm[40], s_dims[4];
@@ -420,6 +428,23 @@ __global__ void __launch_bounds__(256) k_atom_grid(BatchDev B, AtomGrid AG)
     int *cellend = AG.cellend + AG.cbase[k];
     int *cellatom = AG.cellatom + (S.natoms_w ? S.w_off : AG.same_base + S.atom_off);
     const int ccap = AG.cbase[k + 1] - AG.cbase[k] - 2;
+    {
+        float4 *cbx = AG.cbox + 2 * chunk_base(AG, S, k);
+        const int nch = (nw + 31) >> 5;
+        for (int c = wid; c < nch; c += nt >> 5) {
+            const int i = 32 * c + lane;
+            float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+            if (i < nw && !(wf[WQ0 + i] & whmask)) { lo[0] = hi[0] = wx[W0 + i]; lo[1] = hi[1] = wy[W0 + i]; lo[2] = hi[2] = wz[W0 + i]; }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1)
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    lo[q] = fminf(lo[q], __shfl_xor_sync(0xffffffffu, lo[q], d));
+                    hi[q] = fmaxf(hi[q], __shfl_xor_sync(0xffffffffu, hi[q], d));
+                }
+            if (lane == 0) { cbx[2 * c] = make_float4(lo[0], lo[1], lo[2], 0.0f); cbx[2 * c + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f); }
+        }
+    }
     if (nw <= AG.min_atoms) return;          // nobody will ask: K4 scans the atoms of a small structure directly
     float mn[3] = {3e38f, 3e38f, 3e38f}, mx[3] = {-3e38f, -3e38f, -3e38f};
     for (int i = tid; i < nw; i += nt) {
@@ -1513,23 +1538,36 @@ __global__ void __launch_bounds__(K4S_THREADS, 8) k_descriptors_small(BatchDev B
                     }
                 int nsa = 0;
                 if (nw <= K4_GRID_MIN_ATOMS) {
-                    for (int b0 = 0; b0 < nw && fits; b0 += 32) {
-                        const int i = b0 + lane;
-                        bool in = false;
-                        if (i < nw && !(wf[WQ0 + i] & whmask)) {
-                            const float x = wx[W0 + i], y = wy[W0 + i], z = wz[W0 + i];
-                            if (x >= bmn[0] && x <= bmx[0] && y >= bmn[1] && y <= bmx[1] && z >= bmn[2] && z <= bmx[2]) {
-                                for (int q = 0; q < n && !in; q++) {
-                                    const float4 v = W.sph[q];
-                                    const double rp = (double)v.w + 1.0;
-                                    in = (double)f_ddist(x, y, z, v.x, v.y, v.z) < rp * rp;
+                    // runs of 32 consecutive atoms whose box meets the cluster's, in ascending order (AtomGrid.cbox): same atoms, same order as the full scan
+                    const float4 *cbx = AG.cbox + 2 * chunk_base(AG, S, k);
+                    const int nch = (nw + 31) >> 5;
+                    for (int c0 = 0; c0 < nch && fits; c0 += 32) {
+                        const int ci = c0 + lane;
+                        bool ov = false;
+                        if (ci < nch) {
+                            const float4 lo = cbx[2 * ci], hi = cbx[2 * ci + 1];
+                            ov = lo.x <= bmx[0] && hi.x >= bmn[0] && lo.y <= bmx[1] && hi.y >= bmn[1] && lo.z <= bmx[2] && hi.z >= bmn[2];
+                        }
+                        unsigned runs = __ballot_sync(0xffffffffu, ov);
+                        while (runs && fits) {
+                            const int i = 32 * (c0 + __ffs(runs) - 1) + lane;
+                            runs &= runs - 1;
+                            bool in = false;
+                            if (i < nw && !(wf[WQ0 + i] & whmask)) {
+                                const float x = wx[W0 + i], y = wy[W0 + i], z = wz[W0 + i];
+                                if (x >= bmn[0] && x <= bmx[0] && y >= bmn[1] && y <= bmx[1] && z >= bmn[2] && z <= bmx[2]) {
+                                    for (int q = 0; q < n && !in; q++) {
+                                        const float4 v = W.sph[q];
+                                        const double rp = (double)v.w + 1.0;
+                                        in = (double)f_ddist(x, y, z, v.x, v.y, v.z) < rp * rp;
+                                    }
                                 }
                             }
+                            const unsigned bal = __ballot_sync(0xffffffffu, in);
+                            if (nsa + __popc(bal) > K4S_SA) { fits = false; break; }
+                            if (in) W.sa[nsa + __popc(bal & ((1u << lane) - 1u))] = i;
+                            nsa += __popc(bal);
                         }
-                        const unsigned bal = __ballot_sync(0xffffffffu, in);
-                        if (nsa + __popc(bal) > K4S_SA) { fits = false; break; }
-                        if (in) W.sa[nsa + __popc(bal & ((1u << lane) - 1u))] = i;
-                        nsa += __popc(bal);
                     }
                 } else {                   // large structure: the cells of the atom grid the box overlaps, then a sort (atom order matters, asa.c:313-325)
                     const float4 gg = AG.geom[k];
