@@ -534,6 +534,10 @@ __device__ __forceinline__ float unif_from_bits(unsigned r31, float mn, float mx
 #ifndef FPK_K4_SEARCH_NEAR
 #define FPK_K4_SEARCH_NEAR 0
 #endif
+#ifndef FPK_K4_MC_GRID_MIN
+#define FPK_K4_MC_GRID_MIN 48      // pockets below it test every sample against every sphere: all lanes walk the same list, which beats the shorter but
+                                  // divergent cell lists up to ~50 spheres (profiles/r02_k4_mc_grid_min.log: 12: 93.6 ms, 24: 90.4-91.1, 48: 88.1, 64: 88.2, 112: 89.7, 160: 91.2)
+#endif
 struct DescScratch {          // per resident block of K4
     int *sa;                  // [natoms_w max] surrounding atoms of the current pocket (asa.c:84-112), three ordered segments
     unsigned *bits;           // [natoms_w max / 32 + 1] large structures: one bit per atom of pdb_w_lig (marked by the pocket's spheres)
@@ -1078,7 +1082,7 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
                 // cell grid over the box: a sample only meets the spheres registered in its cell (the test is an OR: order-free)
                 if (wt == 0) {
                     int mode = 0;
-                    if ((insm || stg) && n >= 24) {
+                    if ((insm || stg) && n >= FPK_K4_MC_GRID_MIN) {
                         const float ex = xmax - xmin, ey = ymax - ymin, ez = zmax - zmin;
                         const int dx = max(1, min(8, (int)(ex / 4.5f))), dy = max(1, min(8, (int)(ey / 4.5f))), dz = max(1, min(8, (int)(ez / 4.5f)));
                         s_mcdim[0] = dx; s_mcdim[1] = dy; s_mcdim[2] = dz;
