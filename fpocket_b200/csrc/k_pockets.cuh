@@ -574,7 +574,9 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
     __shared__ float4 s_cand[3][ASA_CAND];                 // per worker warp: burial candidates of the current atom (x, y, z, radius)
     __shared__ unsigned char s_candapol[3][ASA_CAND];
     __shared__ fpk_desc s_desc;                            // warp 0's part of the record (everything but ASA / volume)
+    __shared__ float s_spiral[300];                        // spiral points: the lanes read 32 different ones at once (constant memory would serialise that)
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < 300; i += nt) s_spiral[i] = c_spiral[i];       // visible after the first barrier of the work loop
     const DescScratch &X = scratch[blockIdx.x];
     const fpk_params &prm = B.prm;
 #if FPK_K4_SEARCH_NEAR
@@ -791,9 +793,9 @@ __global__ void __launch_bounds__(K4_THREADS, 8) k_descriptors(BatchDev B, Pocke
             for (int it = lane; it < 200; it += 32) {
                 const int pass = it >= 100 ? 1 : 0, kp = it - 100 * pass;
                 const double probe = pass == 0 ? 1.4 : 2.2;
-                const float tx = (float)((double)cx + (double)c_spiral[3 * kp] * ((double)crad + probe));
-                const float ty = (float)((double)cy + (double)c_spiral[3 * kp + 1] * ((double)crad + probe));
-                const float tz = (float)((double)cz + (double)c_spiral[3 * kp + 2] * ((double)crad + probe));
+                const float tx = (float)((double)cx + (double)s_spiral[3 * kp] * ((double)crad + probe));
+                const float ty = (float)((double)cy + (double)s_spiral[3 * kp + 1] * ((double)crad + probe));
+                const float tz = (float)((double)cz + (double)s_spiral[3 * kp + 2] * ((double)crad + probe));
                 bool vref = true;                                   // "vrefburried": not inside any touching alpha sphere
 #if FPK_K4_STAGE_TOUCHING
                 if (staged) {
@@ -1353,6 +1355,9 @@ struct SmallWarp {
 __global__ void __launch_bounds__(K4S_THREADS, 8) k_descriptors_small(BatchDev B, PocketDev Pk, int *chunk_counter, AtomGrid AG, unsigned char *done)
 {
     __shared__ SmallWarp s_w[K4S_WARPS];
+    __shared__ float s_spiral[300];          // the lanes of a warp read 32 DIFFERENT points at once: from constant memory that is 32 serialised reads
+    for (int i = threadIdx.x; i < 300; i += blockDim.x) s_spiral[i] = c_spiral[i];
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     SmallWarp &W = s_w[threadIdx.x >> 5];
     const fpk_params &prm = B.prm;
@@ -1661,9 +1666,9 @@ __global__ void __launch_bounds__(K4S_THREADS, 8) k_descriptors_small(BatchDev B
                     for (int it = lane; it < 200; it += 32) {
                         const int pass = it >= 100 ? 1 : 0, kp = it - 100 * pass;
                         const double probe = pass == 0 ? 1.4 : 2.2;
-                        const float tx = (float)((double)cx + (double)c_spiral[3 * kp] * ((double)crad + probe));
-                        const float ty = (float)((double)cy + (double)c_spiral[3 * kp + 1] * ((double)crad + probe));
-                        const float tz = (float)((double)cz + (double)c_spiral[3 * kp + 2] * ((double)crad + probe));
+                        const float tx = (float)((double)cx + (double)s_spiral[3 * kp] * ((double)crad + probe));
+                        const float ty = (float)((double)cy + (double)s_spiral[3 * kp + 1] * ((double)crad + probe));
+                        const float tz = (float)((double)cz + (double)s_spiral[3 * kp + 2] * ((double)crad + probe));
                         bool vref = true;
                         for (unsigned tm = touching; tm && vref; tm &= tm - 1) {
                             const float4 v = W.sph[__ffs(tm) - 1];
