@@ -1351,6 +1351,7 @@ struct SmallWarp {
     int cursor;
     int entu[4 * K4S_NMAX];             // entry (sphere, slot) -> position of its atom; then: first occurrence of the atom's residue id (descriptors.c:408)
     unsigned cnt4[4 * K4S_NMAX];        // per contacted atom the four SASA tallies (each <= 100), one byte each: free points at 1.4 / 2.2, apolar / polar burying atoms
+    unsigned char plist[208];           // the test points of the current atom (0..199: probe 1.4 then 2.2) that lie inside a touching sphere
 };
 __global__ void __launch_bounds__(K4S_THREADS, 8) k_descriptors_small(BatchDev B, PocketDev Pk, int *chunk_counter, AtomGrid AG, unsigned char *done)
 {
@@ -1663,18 +1664,36 @@ __global__ void __launch_bounds__(K4S_THREADS, 8) k_descriptors_small(BatchDev B
                     if (!fits) break;
                     const unsigned touching = W.tmask[u];
                     int c14 = 0, c22 = 0, cap = 0, cpo = 0;
-                    for (int it = lane; it < 200; it += 32) {
+                    // two steps, so that the burial loop runs with full warps: (a) which of the 200 test points lie inside a touching sphere (about one in
+                    // five; the others count for nothing, asa.c:306-312), (b) those, 32 at a time, against the burial candidates. Only counts: order-free.
+                    int npts = 0;
+                    for (int r = 0; r < 7; r++) {
+                        const int it = lane + 32 * r;
+                        bool inside = false;
+                        if (it < 200) {
+                            const int pass = it >= 100 ? 1 : 0, kp = it - 100 * pass;
+                            const double probe = pass == 0 ? 1.4 : 2.2;
+                            const float tx = (float)((double)cx + (double)s_spiral[3 * kp] * ((double)crad + probe));
+                            const float ty = (float)((double)cy + (double)s_spiral[3 * kp + 1] * ((double)crad + probe));
+                            const float tz = (float)((double)cz + (double)s_spiral[3 * kp + 2] * ((double)crad + probe));
+                            for (unsigned tm = touching; tm && !inside; tm &= tm - 1) {
+                                const float4 v = W.sph[__ffs(tm) - 1];
+                                if (f_ddist(tx, ty, tz, v.x, v.y, v.z) <= v.w * v.w) inside = true;
+                            }
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, inside);
+                        if (inside) W.plist[npts + __popc(m & ((1u << lane) - 1u))] = (unsigned char)it;
+                        npts += __popc(m);
+                    }
+                    __syncwarp();
+                    for (int b0 = 0; b0 < npts; b0 += 32) {
+                        if (b0 + lane >= npts) continue;
+                        const int it = W.plist[b0 + lane];
                         const int pass = it >= 100 ? 1 : 0, kp = it - 100 * pass;
                         const double probe = pass == 0 ? 1.4 : 2.2;
                         const float tx = (float)((double)cx + (double)s_spiral[3 * kp] * ((double)crad + probe));
                         const float ty = (float)((double)cy + (double)s_spiral[3 * kp + 1] * ((double)crad + probe));
                         const float tz = (float)((double)cz + (double)s_spiral[3 * kp + 2] * ((double)crad + probe));
-                        bool vref = true;
-                        for (unsigned tm = touching; tm && vref; tm &= tm - 1) {
-                            const float4 v = W.sph[__ffs(tm) - 1];
-                            if (f_ddist(tx, ty, tz, v.x, v.y, v.z) <= v.w * v.w) vref = false;
-                        }
-                        if (vref) continue;
                         int hit = -1;
                         for (int j = 0; j < ncand; j++) {
                             const float4 q = W.cand[j];
