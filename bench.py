@@ -410,7 +410,7 @@ def main():
             dist.all_reduce(ee, op=dist.ReduceOp.MAX)
         out["e2e"] = {"value": ne2e * world / float(ee[0]), "unit": "structures/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                       "structures_per_call": ne2e, "ok": int(ok), "steps": e2e_steps,
-                      "note": "fpk_detect_batch() on host arrays: chunks of ~1,200 structures through pack -> pinned H2D -> kernels -> pinned D2H -> unpack on 4 host "
+                      "note": "fpk_detect_batch() on host arrays: chunks of ~1,200 structures through pack -> pinned H2D -> kernels -> pinned D2H -> unpack on 4 or 8 host "
                               "threads / CUDA streams; wall clock around the call, results freed inside the timed region"}
 
     # ---- configs[1] as stated (strong scaling): `--strong` structures IN TOTAL, rank r takes its share of the same workload ---------

@@ -1086,7 +1086,15 @@ extern "C" int fpk_detect_batch(const fpk_structure *in, int n, const fpk_params
     // allows (measured on 6,144 structures, 4 threads: 512 -> 7,668, 1,024 -> 7,867, 1,536 -> 8,268 structures/s end to end).
     // With several devices (fpk_init's list) every device gets its own group of host threads; chunks are handed out from one counter,
     // so a faster or less loaded device simply takes more of them.
+    // host threads per device: 4, or 8 when this process has at least 16 cores per device to itself (measured on the 16-core box, one GPU: e2e 11,100
+    // structures/s with 4, 11,181 with 6, 11,322 with 8, profiles/r02f_e2e_threads.log; with 8 ranks on 32 cores more threads only fight for cores)
     int chunk = 0, per_dev = 4;
+    {
+        const int cores = (int)std::thread::hardware_concurrency();
+        const char *lw = getenv("LOCAL_WORLD_SIZE");
+        const int ranks = lw ? std::max(1, atoi(lw)) : 1;
+        if (cores / ranks / std::max(1, ndev) >= 16) per_dev = 8;
+    }
     if (const char *e = getenv("FPK_CHUNK")) chunk = std::max(1, atoi(e));
     if (const char *e = getenv("FPK_HOST_THREADS")) per_dev = std::max(1, std::min(8, atoi(e)));
     int nthreads = per_dev * ndev;
