@@ -68,7 +68,10 @@ typedef struct fpk_params {
     int32_t lig_interface_method;         /* dpocket -E (dparams.h:41-44): 0 or 1 = atoms contacted by spheres near the ligand (neighbor.c:313),
                                              2 = atoms within lig_interface_dist of a ligand atom (neighbor.c:67 get_mol_atm_neigh)              */
     int32_t clustering_method;            /* -C (fparams.h clustering_method): 0 or 's' single linkage (clusterlib.c:3514), 'm' complete (:3705), 'a' average
-                                             (:3781), 'c' centroid (:3337), each cut by cuttree_distance (:3235) at clust_max_dist                 */
+                                             (:3781), 'c' centroid (:3337), each cut by cuttree_distance (:3235) at clust_max_dist. m / a / c keep a
+                                             dense f64 distance matrix per structure (4 S^2 bytes for S spheres) in a pool of half the free device
+                                             memory (FPK_LINK_POOL_MB overrides): a structure whose matrix alone exceeds it, or one large enough for
+                                             the whole-GPU route, gets status FPK_ERR_BAD_ARG; anything else: the call fails with FPK_ERR_BAD_ARG   */
 } fpk_params;
 
 /* flattened s_pdb pair (reference headers/rpdb.h:69-98, atom.h:29-77). Arrays are caller-owned, read-only. */
