@@ -314,6 +314,19 @@ static int cluster_spheres(sph_t *S, int ns, float clust_max_dist, int skip, int
     return nc;
 }
 
+/* test entry: the clustering step alone on n centres (x, y, z per point), any method / measure; label[i] = cluster of point i, numbered by lowest member */
+int orc_cluster_points(const float *xyz, int n, float clust_max_dist, int measure, int method, int *label)
+{
+    sph_t *S = calloc((size_t)n + 1, sizeof(sph_t));
+    for (int i = 0; i < n; i++) { S[i].x = xyz[3 * i]; S[i].y = xyz[3 * i + 1]; S[i].z = xyz[3 * i + 2]; }
+    const int saved = g_distance_measure;
+    const int nc = cluster_spheres(S, n, clust_max_dist, 0, measure, method);
+    g_distance_measure = saved;
+    for (int i = 0; i < n; i++) label[i] = S[i].cluster;
+    free(S);
+    return nc;
+}
+
 /* aa.c:60-80 property table: volume score, hydrophobicity, charge, polarity */
 static const float AA_VOL[20] = {2, 7, 3, 3, 3, 4, 4, 1, 4, 5, 5, 6, 5, 6, 3, 2, 3, 8, 7, 4};
 static const float AA_HYD[20] = {41, -14, -28, -55, 49, -10, -31, 0, 8, 99, 97, -23, 74, 100, -46, -5, 13, 97, 63, 76};

@@ -56,6 +56,8 @@ void orc_ligand_queries(const fpk_structure *in, const fpk_params *p, fpk_result
 void orc_set_wanted_zone(const float *xyz, int n);
 /* -e: 'e' (default) or 'b' city block for the clustering distance; a process-wide switch, reset it to 'e' after use */
 void orc_set_distance_measure(int c);
+/* the clustering step alone (tests): n centres, cut, -e measure ('e' | 'b'), -C method ('s' | 'm' | 'a' | 'c'); returns the number of clusters */
+int orc_cluster_points(const float *xyz, int n, float clust_max_dist, int measure, int method, int *label);
 /* dpocket: 1 (default) interface = atoms contacted by the spheres near the ligand, 2 = atoms within the distance of a ligand atom (dparams.h:41-44) */
 void orc_set_interface_method(int m);
 int orc_get_wanted(const int **idx, int *nidx, const int **atoms, int *natoms, fpk_desc *d);
