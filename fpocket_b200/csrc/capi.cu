@@ -645,7 +645,7 @@ __global__ void k_compact(BatchDev B, const int *sbase, float4 *xyzr, float *bar
 static int fetch_counts(fpk_batch *b);
 
 // -C m | a | c (k_linkage.cuh): the sphere counts come back first (one more host round trip, only on this route), the pool of distance
-// matrices is sized from them, and the structures are clustered in as many waves as the pool needs. A structure on the whole-GPU route, or
+// matrices is sized from them (at most 16 GB per worker context), and the structures are clustered in as many waves as the pool needs. A structure on the whole-GPU route, or
 // whose matrix alone exceeds the pool, is refused with FPK_ERR_BAD_ARG (the reference would need the same n^2 / 2 doubles and O(n^3) time).
 static int run_linkage(fpk_batch *b)
 {
@@ -653,7 +653,8 @@ static int run_linkage(fpk_batch *b)
     { int rc = fetch_counts(b); if (rc) return rc; }
     size_t freeb = 0, totb = 0;
     CK(cudaMemGetInfo(&freeb, &totb));
-    size_t budget = (freeb + b->AL.cap) / 2;
+    // half of what is free, at most 16 GB: up to eight worker contexts of fpk_detect_batch run side by side on a device, each with its own pool
+    size_t budget = std::min((freeb + b->AL.cap) / 2, (size_t)16 << 30);
     if (const char *e = getenv("FPK_LINK_POOL_MB")) budget = (size_t)atof(e) << 20;
     std::vector<LinkItem> items;
     std::vector<int> wave_start, refused;

@@ -70,7 +70,7 @@ typedef struct fpk_params {
     int32_t clustering_method;            /* -C (fparams.h clustering_method): 0 or 's' single linkage (clusterlib.c:3514), 'm' complete (:3705), 'a' average
                                              (:3781), 'c' centroid (:3337), each cut by cuttree_distance (:3235) at clust_max_dist. m / a / c keep a
                                              dense f64 distance matrix per structure (4 S^2 bytes for S spheres) in a pool of half the free device
-                                             memory (FPK_LINK_POOL_MB overrides): a structure whose matrix alone exceeds it, or one large enough for
+                                             memory, at most 16 GB per worker context (FPK_LINK_POOL_MB overrides): a structure whose matrix alone exceeds it, or one large enough for
                                              the whole-GPU route, gets status FPK_ERR_BAD_ARG; anything else: the call fails with FPK_ERR_BAD_ARG   */
 } fpk_params;
 
